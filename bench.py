@@ -1,0 +1,349 @@
+#!/usr/bin/env python
+"""bench.py — scans/sec of the LiLi-OM per-scan hot path on B200 (BASELINE.json metric).
+
+One "step" = one scan through the hot path:
+    feature extraction (raw sweep) -> VoxelGrid(0.4) of the surf features -> ITERS x
+    [5-NN in the voxel map + plane fit + residual/Jacobian + 27-scalar reduce + 6x6 solve + pose update]
+
+N = 1 workload (BASELINE.json configs[1]): 24k-pt Livox-Horizon sweep, 1 M-pt voxel map, 10 GN iterations.
+N > 1 : --multi sharded (default; configs[3]: 5 M-pt map sharded by 8 m block hash, one 29-scalar NCCL
+        all-reduce per iteration, strong scaling) or --multi replicas (independent scan streams, weak scaling).
+
+value  : scans/s with the sweep already resident in HBM (only the 56-byte pose returns to the host).
+e2e    : scans/s through the reference-facing calls with HOST buffers — Preprocessing node call
+         (H2D raw sweep, D2H the three published clouds) + LidarOdometry node call (H2D surf cloud,
+         D2H pose + surf_last_ds).
+roofline: kNN+Jacobian kernel, algorithmic bytes (SURVEY.md §8 d) / CUDA-event duration / measured HBM peak.
+cpu_baseline: the CPU oracle (restatement of the reference, oracle/) on the host cores, bounded sample.
+--impl reference: the same workload on the CPU oracle with all host threads (the reference itself cannot
+         be built here: needs ROS/PCL/Eigen/Ceres).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ITERS = 10
+METRIC = "scans/sec (24k-pt sweep vs 1M-pt map); kNN+Jacobian HBM GB/s vs peak"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--multi", default="sharded", choices=["sharded", "replicas"])
+    ap.add_argument("--map-points", type=int, default=0, help="override the map size")
+    ap.add_argument("--sweeps", type=int, default=8, help="distinct synthetic sweeps cycled through the steps")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dense-queries", action="store_true", help="roofline micro-run: every surf feature is a query (no scan DS)")
+    return ap.parse_args()
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (recipe's clocks line)."""
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for k, nm in enumerate(names):
+                    if r[2 + k].lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_workload(n_map: int, n_sweeps: int, variant: int = 0):
+    from liliom_b200 import synth
+    m, _ = synth.make_map(n_map)
+    T0 = synth.default_true_pose()
+    sweeps = []
+    for k in range(n_sweeps):
+        T = np.array(T0); T[4] += 0.7 * k; T[5] += 0.15 * k       # sensor advancing through the block
+        if variant == 0:
+            pts, q = synth.make_horizon_sweep(T, seed=1 + k)
+        else:
+            pts, q = synth.make_hdl64_sweep(T, seed=2 + k)
+        sweeps.append(dict(T=T, guess=synth.perturbed_pose(T), pts=pts, q=q))
+    return m, sweeps
+
+
+# ---------------------------------------------------------------------------------------------- CPU oracle legs
+def cpu_scan(O, tree, sw, nthreads):
+    surf, edge, cut = O.extract_horizon(sw["pts"], sw["q"])
+    ds = O.voxelgrid(surf, 0.4)
+    rc, pose, st = O.scan_to_map_gn(tree, ds, sw["guess"], ITERS, nthreads)
+    return pose, len(ds)
+
+
+def run_reference(args):
+    """--impl reference: the oracle port on the host cores (rank 0 only)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+    n_map = args.map_points or 1_000_000
+    m, sweeps = make_workload(n_map, min(args.sweeps, 4))
+    t0 = time.perf_counter(); tree = O.KdTree(m); t_build = time.perf_counter() - t0
+    cores = os.cpu_count() or 1
+    # pick the faster of 1 thread / all threads on one probe scan (OpenMP over queries can lose on shared hosts)
+    best_nt, best_t = 1, None
+    for nt in sorted({1, cores}):
+        t0 = time.perf_counter(); cpu_scan(O, tree, sweeps[0], nt); dt = time.perf_counter() - t0
+        if best_t is None or dt < best_t:
+            best_nt, best_t = nt, dt
+    steps = max(1, min(args.steps, int(60.0 / max(best_t, 1e-3))))
+    for k in range(min(args.warmup, 2)):
+        cpu_scan(O, tree, sweeps[k % len(sweeps)], best_nt)
+    t0 = time.perf_counter()
+    for k in range(steps):
+        cpu_scan(O, tree, sweeps[k % len(sweeps)], best_nt)
+    dt = time.perf_counter() - t0
+    val = steps / dt
+    sample = f"{steps} scans (extract + VoxelGrid + {ITERS} GN iters, kd-tree prebuilt in {t_build:.2f}s, excluded)"
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "scans/s", "n_gpus": args.gpus, "steps": steps,
+            "warmup": min(args.warmup, 2), "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"24k-pt Horizon sweep vs {n_map}-pt voxel map, {ITERS} GN iters (CPU oracle port of the reference path)",
+                       "map_points": n_map, "iters": ITERS},
+            "cpu_baseline": {"value": val, "unit": "scans/s", "cores": best_nt, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_leg(m, sweeps):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+    tree = O.KdTree(m)
+    cpu_scan(O, tree, sweeps[0], 1)
+    n = 0
+    t0 = time.perf_counter()
+    while True:
+        cpu_scan(O, tree, sweeps[n % len(sweeps)], 1)
+        n += 1
+        if time.perf_counter() - t0 > 10.0 or n >= 200:
+            break
+    dt = time.perf_counter() - t0
+    return {"value": n / dt, "unit": "scans/s", "cores": 1, "kind": "port",
+            "sample": f"{n} scans in {dt:.1f}s, 1 thread (the reference nodes are single-threaded), kd-tree build excluded"}
+
+
+# ---------------------------------------------------------------------------------------------- GPU legs
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    import torch
+    import liliom_b200 as L
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    multi = world > 1
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU oracle")
+    torch.cuda.set_device(local_rank)
+    if multi:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    sharded = multi and args.multi == "sharded"
+    n_map = args.map_points or (5_000_000 if sharded else 1_000_000)
+
+    m, sweeps = make_workload(n_map, args.sweeps)
+    if multi and not sharded:     # replicas: every rank gets its own scan stream
+        sweeps = sweeps[rank % len(sweeps):] + sweeps[:rank % len(sweeps)]
+
+    prm = L.default_params(0)
+    if args.dense_queries:
+        prm.leaf_scan = 0.0        # no scan down-sampling: every surf feature is a query (roofline micro-run)
+    ctx = L.Context(prm, device=local_rank)
+    stream = torch.cuda.Stream()
+    ctx.set_stream(stream.cuda_stream)
+    if sharded:
+        uid = [L.comm_get_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        ctx.comm_init(uid[0], world, rank)
+    ctx.map_set_points(m)
+    ctx.set_kernel_timing(True)
+
+    # pinned host buffers for the e2e leg (the contract: inputs come from pinned host memory)
+    pin_sweeps = []
+    for sw in sweeps:
+        t = torch.from_numpy(sw["pts"].view(np.uint8).reshape(-1)).pin_memory()
+        pin_sweeps.append(t.numpy().view(L.PT48))
+    cap = max(len(s["pts"]) for s in sweeps)
+    out_surf = torch.empty(cap * 48, dtype=torch.uint8).pin_memory().numpy().view(L.PT48)
+    out_ds = torch.empty(cap * 48, dtype=torch.uint8).pin_memory().numpy().view(L.PT48)
+    pose_buf = torch.empty(7, dtype=torch.float64).pin_memory().numpy()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")     # > 126 MB L2
+
+    def barrier():
+        if multi:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident(k):
+        sw = sweeps[k % len(sweeps)]
+        ns, ne, nc = ctx.extract_resident(sw["q"])
+        pose, st, nds = ctx.odometry_resident(sw["guess"], ITERS, mode=L.MODE_GN)
+        return pose, nds
+
+    def step_e2e(k):
+        i = k % len(sweeps)
+        surf, edge, cut = ctx.extract_horizon(pin_sweeps[i], sweeps[i]["q"])          # Preprocessing node call
+        out_surf[:len(surf)] = surf                                                    # (the topic hop, host memory)
+        pose, st, ds = ctx.odometry(out_surf[:len(surf)], sweeps[i]["guess"], ITERS, mode=L.MODE_GN, ds_out=out_ds, pose_out=pose_buf)
+        h2d = len(pin_sweeps[i]) * 48 + len(surf) * 48 + 56
+        d2h = (len(surf) + len(edge) + len(cut)) * 48 + len(ds) * 48 + 56
+        return pose, h2d, d2h
+
+    def timed(fn, steps, warmup, prep=None):
+        for k in range(warmup):
+            if prep: prep(k)
+            fn(k)
+        barrier()
+        tot_ms = 0.0
+        last = None
+        with torch.cuda.stream(stream):
+            for k in range(steps):
+                if prep: prep(k)
+                flush.fill_(k & 0xff)                       # evict L2 between steps (cold-cache scans)
+                e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                last = fn(k)
+                e1.record(stream)
+                e1.synchronize()
+                tot_ms += e0.elapsed_time(e1)
+        barrier()
+        if multi:
+            t = torch.tensor([tot_ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            tot_ms = float(t.item())
+        return tot_ms, last
+
+    def prep_resident(k):
+        ctx.upload_scan(sweeps[k % len(sweeps)]["pts"])     # untimed: the sweep is resident when the step starts
+
+    # ---- timed region 1: device-resident
+    ctx.counters(reset=True)
+    with ClockSampler(local_rank) as clk:
+        ms_res, last = timed(step_resident, args.steps, max(args.warmup, 3), prep_resident)
+        cnt = ctx.counters(reset=True)
+        # ---- timed region 2: end to end with host buffers
+        ms_e2e, last_e2e = timed(step_e2e, args.steps, max(args.warmup, 3))
+    clocks = clk.summary()
+    cnt_e2e = ctx.counters(reset=True)
+
+    scans_total = args.steps * (world if (multi and not sharded) else 1)
+    value = scans_total / (ms_res * 1e-3)
+    e2e_val = scans_total / (ms_e2e * 1e-3)
+
+    # ---- roofline of the kNN+Jacobian kernel (algorithmic bytes per SURVEY.md §8 d)
+    peak, peak_src = measured_peak()
+    roof = None
+    if cnt.knn_launches:
+        qpl = cnt.knn_queries / cnt.knn_launches
+        cbar = cnt.knn_candidates / max(cnt.knn_queries, 1)
+        bytes_per_launch = qpl * (16 + 27 * 8 + 16 * cbar)
+        t_launch = cnt.knn_ms * 1e-3 / cnt.knn_launches
+        ach = bytes_per_launch / t_launch / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "knn_traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        roof = {"bound": "hbm", "kernel": "k_knn_plane", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "traffic": traffic, "peak_source": peak_src, "queries_per_launch": qpl, "candidates_per_query": cbar,
+                "algorithmic_bytes_per_launch": bytes_per_launch, "us_per_launch": t_launch * 1e6,
+                "min_bytes_per_launch": qpl * 96.0}
+
+    if rank != 0:
+        if multi:
+            dist.destroy_process_group()
+        return
+    cpu = None if args.no_cpu_baseline or multi else cpu_baseline_leg(m if n_map <= 1_000_000 else m[:1_000_000], sweeps[:4])
+    pose, nq = last
+    line = {
+        "metric": METRIC, "value": value, "unit": "scans/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_res / args.steps, "higher_is_better": True,
+        "scaling": "weak" if (multi and not sharded) else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": (f"24k-pt Livox-Horizon sweep ({len(sweeps[0]['pts'])} returns) vs {n_map}-pt voxel map, {ITERS} GN iters"
+                                + (", map sharded by 8 m block hash + 29-scalar NCCL all-reduce per iteration" if sharded else "")
+                                + (", independent scan stream per GPU" if (multi and not sharded) else "")),
+                   "map_points": n_map, "iters": ITERS, "queries_per_scan": int(nq), "dense_queries": bool(args.dense_queries),
+                   "l2": "256 MB buffer written between timed steps (L2 flushed); each step timed with its own CUDA-event pair on the launch stream",
+                   "multi": args.multi if multi else "single"},
+        "gpu_launches": int(cnt.launches),
+        "lib_calls": int(cnt.lib_launches),
+        "e2e": {"value": e2e_val, "unit": "scans/s", "ms_per_step": ms_e2e / args.steps,
+                "h2d_bytes_per_step": int(last_e2e[1]), "d2h_bytes_per_step": int(last_e2e[2])},
+        "clocks": clocks,
+        "roofline": roof,
+        "cpu_baseline": cpu,
+        "pose_err_m": float(np.linalg.norm(np.asarray(pose)[4:] - sweeps[(args.steps - 1) % len(sweeps)]["T"][4:])),
+    }
+    print(json.dumps(line), flush=True)
+    if multi:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

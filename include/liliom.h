@@ -1,0 +1,222 @@
+/* liliom.h — C ABI of libliliom_b200.so: a B200-native (sm_100a) drop-in for the per-scan hot
+ * path of KIT-ISAS/lili-om.  The reference has no FFI/plugin interface for this path (it is
+ * private member functions of two ROS node classes), so each entry point cites the reference
+ * code it replaces; INTEGRATION.md shows the call a maintainer adds inside the node.
+ * Citations are relative to the reference repository root
+ * (L/ = LiLi-OM/, R/ = LiLi-OM-ROT/).
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every pointer is caller-owned HOST memory unless a
+ *    function says "_dev"; the library never retains a host pointer after returning;
+ *  - every call is synchronous from the caller's view (the context's stream is drained before
+ *    return), matching the single-threaded ROS spinner the reference runs on
+ *    (L/src/Preprocessing.cpp:417, L/src/LidarOdometry.cpp:697-703);
+ *  - a context is NOT thread-safe and not re-entrant: one per node, one caller thread;
+ *  - return value 0 = OK, <0 = LILIOM_E_* ; on error outputs and the pose are left untouched,
+ *    mirroring the reference's "ROS_WARN + early return" (L/src/LidarOdometry.cpp:485-488);
+ *  - pose layout [qw,qx,qy,qz,tx,ty,tz] fp64 = abs_pose (L/src/LidarOdometry.cpp:34-36);
+ *  - point layouts are PCL's: 48-byte pcl::PointXYZINormal (L/include/utils/common.h:72-73)
+ *    and 32-byte pcl::PointXYZI (R/include/utils/common.h:73), i.e. the bytes
+ *    pcl::fromROSMsg / toROSMsg produce and consume.
+ *  - there is NO CPU fallback: without a CUDA device liliom_create fails with LILIOM_E_CUDA.
+ */
+#ifndef LILIOM_H
+#define LILIOM_H
+#include <stddef.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LILIOM_ABI_VERSION 1
+
+enum {
+    LILIOM_OK          = 0,
+    LILIOM_E_ARG       = -1,  /* null pointer, negative size, bad stride/mode */
+    LILIOM_E_CUDA      = -2,  /* CUDA runtime error / no device (see liliom_last_error) */
+    LILIOM_E_FEWMAP    = -3,  /* map has < 10 points: pose untouched (L/src/LidarOdometry.cpp:485-488) */
+    LILIOM_E_CAPACITY  = -4,  /* caller buffer or configured capacity too small */
+    LILIOM_E_GRID      = -5,  /* map extent too large for the dense 1 m cell table */
+    LILIOM_E_LINES     = -6,  /* line_num not in {16,32,64} (R/src/Preprocessing.cpp:344-347) */
+    LILIOM_E_NCCL      = -7,  /* NCCL unavailable or failed */
+    LILIOM_E_NOMAP     = -8   /* scan_to_map called before any map was set */
+};
+
+typedef struct liliom_ctx liliom_ctx;
+
+typedef struct { float x, y, z, w; } liliom_f4;
+typedef struct { float x, y, z, w; float nx, ny, nz, nw; float intensity, curvature, p0, p1; } liliom_pt48; /* pcl::PointXYZINormal */
+typedef struct { float x, y, z, w; float intensity, p0, p1, p2; } liliom_pt32;                             /* pcl::PointXYZI */
+
+/* Every tunable the reference reads from the ROS parameter server or hard-codes on this path. */
+typedef struct {
+    int    abi_version;        /* = LILIOM_ABI_VERSION */
+    int    point_stride;       /* 48 (Horizon package) or 32 (ROT package) */
+    /* Preprocessing — Horizon: /preprocessing/{surf_thres,edge_thres}, L/src/Preprocessing.cpp:44-54 */
+    double surf_thres;         /* default 0.2 */
+    double edge_thres;         /* default 4.0 */
+    /* Preprocessing — ROT: /preprocessing/{line_num,ds_rate}, R/src/Preprocessing.cpp:67-75; ds_v :14 */
+    int    line_num;           /* 16 | 32 | 64 */
+    int    ds_rate;            /* ring decimation */
+    float  rot_ds_leaf;        /* 0.6 */
+    /* LidarOdometry: leaf sizes L/src/LidarOdometry.cpp:155-156; gates :365,:389,:400; Huber :507; FIFO :290 */
+    float  leaf_scan;          /* 0.4 */
+    float  leaf_map;           /* 0.4 */
+    double knn_max_sqdist;     /* 1.0  — 5th-neighbour squared distance gate (<= 4.0 supported) */
+    double plane_thres;        /* 0.06 */
+    double weight_gate;        /* 0.4  */
+    double huber_a;            /* 0.1  */
+    int    max_map_frames;     /* 20   */
+    /* capacities (device buffers are sized from these at create time and grown on demand) */
+    int    max_scan_points;    /* raw points per sweep, default 400000 (R/src/Preprocessing.cpp:9-12) */
+    int    max_map_points;     /* default 2,000,000 */
+} liliom_params;
+
+/* variant 0 = Horizon package defaults (config L/config/config_fr_iosb.yaml),
+ * variant 1 = ROT package defaults (R/config/config_fr_iosb.yaml). */
+void liliom_default_params(liliom_params* p, int variant);
+
+int  liliom_create(liliom_ctx** out, const liliom_params* p, int device);
+void liliom_destroy(liliom_ctx* c);
+const char* liliom_strerror(int code);
+const char* liliom_last_error(const liliom_ctx* c);   /* detail of the last LILIOM_E_CUDA/NCCL */
+
+/* ===================== L1: feature extraction ===================== */
+
+/* Replaces the body of Preprocessing::cloudHandler between pcl::fromROSMsg and pcl::toROSMsg,
+ * L/src/Preprocessing.cpp:219-383 (removeNaN, removeClosedPointCloud 0.1 m, gyro de-skew,
+ * 6x4000 binning, 664-patch PCA labelling).  pts = n points as published by FormatConvert
+ * (L/src/FormatConvert.cpp:14-22: intensity = line + 0.1*t/t_end, curvature = 0.1*reflectivity).
+ * q_imu_wxyz = the un-normalised q_iMU produced by processIMU (:135-171), which stays host-side.
+ * Outputs (capacities in points) = the three clouds published at :385-401.
+ * The surf features stay resident on the device for liliom_odometry_resident(). */
+int liliom_extract_horizon(liliom_ctx* c, const liliom_pt48* pts, int n, const double q_imu_wxyz[4],
+                           liliom_pt48* surf_out, int surf_cap, int* n_surf,
+                           liliom_pt48* edge_out, int edge_cap, int* n_edge,
+                           liliom_pt48* cutted_out, int cut_cap, int* n_cut);
+
+/* Replaces R/src/Preprocessing.cpp:276-509 (removeNaN, removeClosedPointCloud 3.0 m, ring id,
+ * azimuth/relTime, de-skew with q_lb*q*q_lb^-1, 11-point curvature, per-segment sort + greedy
+ * labelling, per-ring VoxelGrid 0.6 of the less-flat points).
+ * edge_out = cornerPointsLessSharp, surf_out = surfPointsLessFlat, cutted_out = laserCloud (:511-527). */
+int liliom_extract_rot(liliom_ctx* c, const liliom_pt32* pts, int n, const double q_imu_wxyz[4],
+                       const double q_lb_wxyz[4],
+                       liliom_pt32* surf_out, int surf_cap, int* n_surf,
+                       liliom_pt32* edge_out, int edge_cap, int* n_edge,
+                       liliom_pt32* cutted_out, int cut_cap, int* n_cut);
+/* Test hook: per-point cloudLabel / cloudCurvature (R/src/Preprocessing.cpp:9-12) of the last
+ * liliom_extract_rot call, in laserCloud order; either pointer may be NULL. */
+int liliom_extract_rot_labels(liliom_ctx* c, int* label_out, float* curv_out, int cap);
+
+/* pcl::VoxelGrid::filter (L/src/LidarOdometry.cpp:315-323; R/src/Preprocessing.cpp:502-508):
+ * centroid of all fields per occupied voxel, output in ascending voxel index. stride = 48|32. */
+int liliom_voxelgrid(liliom_ctx* c, const void* pts, int n, int stride, float leaf,
+                     void* out, int cap, int* n_out);
+
+/* ===================== L2: scan-to-map ===================== */
+
+/* Local-map lifecycle, replaces buildLocalMap + downSampleCloud(map) + kd-tree build
+ * (L/src/LidarOdometry.cpp:280-303, 316-317, 490).
+ * push_frame: transformCloud (:246-278) of one frame's down-sampled surf cloud by its saved pose,
+ *   appended to the FIFO of the last `max_map_frames` frames (:290-299);
+ * rebuild: concatenation (:301-302) -> VoxelGrid(leaf_map) -> 1 m cell grid (the kd-tree's stand-in).
+ * n_map_out (optional) = surf_from_map_ds size. */
+int liliom_map_push_frame(liliom_ctx* c, const void* surf_ds_body, int n, const double pose7[7]);
+int liliom_map_rebuild(liliom_ctx* c, int* n_map_out);
+int liliom_map_clear(liliom_ctx* c);
+/* Install an already down-sampled world-frame map (float4 xyz*, w ignored) — the synthetic
+ * 1 M..10 M-point maps of the benchmark configs.  With a communicator (liliom_comm_init) each
+ * rank keeps only the 8 m blocks it owns plus a halo. */
+int liliom_map_set_points(liliom_ctx* c, const liliom_f4* xyzw, int m);
+int liliom_map_size(const liliom_ctx* c);        /* points resident on this rank */
+int liliom_map_download(liliom_ctx* c, liliom_f4* xyzw_out, int cap, int* m_out);  /* surf_from_map_ds */
+
+enum { LILIOM_MODE_CERES = 0, LILIOM_MODE_GN = 1 };
+
+typedef struct {
+    int    n_corr;       /* surf_res_cnt at the linearisation pose (L/src/LidarOdometry.cpp:408) */
+    int    lm_iters;     /* LM iterations run by this outer iteration (1 in GN mode) */
+    double cost;         /* 1/2 sum rho(r^2) at the linearisation pose */
+    double jtj_jtr[27];  /* upper triangle of J^T J (21, row-major) + J^T r (6); tangent = [rot, trans] */
+    double pose7[7];     /* pose after this outer iteration */
+} liliom_iter_stats;
+
+/* Replaces downSampleCloud(scan) + updateTransformationWithCeres up to :561
+ * (L/src/LidarOdometry.cpp:319-322, 483-561; R/src/LidarOdometry.cpp:469-547).
+ * feats = surf_last_ds (already down-sampled, body frame; stride 48|32|16 — only xyz is read).
+ * mode CERES: match_cnt outer iterations of [findCorrespondingSurfFeatures (:352-413) + a
+ *   Ceres-2.0-default LM of <= max_num_iter iterations, Huber(0.1), 15 ms cap disabled];
+ * mode GN   : match_cnt iterations of [re-associate + one Gauss-Newton step] (max_num_iter ignored).
+ * stats: NULL or match_cnt entries. */
+int liliom_scan_to_map(liliom_ctx* c, const void* feats_body, int n, int stride, double pose7_inout[7],
+                       int match_cnt, int max_num_iter, int mode, liliom_iter_stats* stats);
+
+/* Same, on the surf features left on the device by the last liliom_extract_* call:
+ * VoxelGrid(leaf_scan) then scan-to-map, no host round trip (both nodes in one process).
+ * ds_out (optional, capacity ds_cap) receives surf_last_ds for savePoses (:345-349). */
+int liliom_odometry_resident(liliom_ctx* c, double pose7_inout[7], int match_cnt, int max_num_iter, int mode,
+                             liliom_iter_stats* stats, void* ds_out, int ds_cap, int* n_ds);
+
+/* The LidarOdometry node's view of the same step: surf_feats = the /surf_features cloud as received
+ * (host, point_stride bytes per point, NOT yet down-sampled; L/src/LidarOdometry.cpp:165-169).
+ * Runs downSampleCloud(scan) (:319-322) and the scan-to-map solve on the device; ds_out receives
+ * surf_last_ds (what savePoses stores, :345-349, and what liliom_map_push_frame later takes). */
+int liliom_odometry(liliom_ctx* c, const void* surf_feats, int n, double pose7_inout[7], int match_cnt, int max_num_iter,
+                    int mode, liliom_iter_stats* stats, void* ds_out, int ds_cap, int* n_ds);
+
+/* Test hook: one pass of findCorrespondingSurfFeatures at pose7 (no pose update).
+ * valid: n bytes; plane: n*4 floats {w*nx,w*ny,w*nz,w*d} (:401-405); nn_idx: n*5 indices into
+ * the map in the order returned by liliom_map_download; sqd: n*5. Any output may be NULL. */
+int liliom_find_surf_corr(liliom_ctx* c, const void* feats_body, int n, int stride, const double pose7[7],
+                          unsigned char* valid, float* plane, int* nn_idx, float* sqd, double out29[29]);
+
+/* ===================== backend kernel reuse ===================== */
+/* findCorrespondingCornerFeatures, L/src/BackendFusion.cpp:1531-1599 (variant 0) /
+ * R/src/BackendFusion.cpp:1394-1462 (variant 1).  Uses the map installed in `c` as the edge map. */
+int liliom_correspond_edge(liliom_ctx* c, const void* feats_body, int n, int stride, const double pose7[7],
+                           int variant, unsigned char* valid, float* pa, float* pb);
+/* findCorrespondingSurfFeatures of the backend, R/src/BackendFusion.cpp:1464-1520
+ * (kd_max_radius, surf_dist_thres, weight gate, score = lidar_const*w). */
+int liliom_correspond_surf(liliom_ctx* c, const void* feats_body, int n, int stride, const double pose7[7],
+                           double kd_max_radius, double surf_dist_thres, double w_gate, double lidar_const,
+                           unsigned char* valid, float* plane, double* score);
+
+/* ===================== multi-GPU (one context per rank) ===================== */
+/* 128-byte NCCL unique id: rank 0 calls get, the launcher broadcasts it, every rank calls init.
+ * After init, liliom_map_set_points shards the map by 8 m block hash (+halo) and every
+ * liliom_scan_to_map / liliom_odometry_resident is COLLECTIVE: per iteration one all-reduce of
+ * the 27 J^T J|J^T r scalars (+cost,count) then an identical 6x6 solve on every rank. */
+int liliom_comm_get_unique_id(void* id128);
+int liliom_comm_init(liliom_ctx* c, const void* id128, int nranks, int rank);
+
+/* ===================== instrumentation ===================== */
+typedef struct {
+    unsigned long long launches;      /* kernels of this library launched since create/reset */
+    unsigned long long lib_launches;  /* CUB sort/scan calls issued (library plumbing) */
+    double knn_ms;                    /* sum of CUDA-event durations of the kNN+Jacobian kernel */
+    unsigned long long knn_launches;  /* number of timed launches in knn_ms */
+    unsigned long long knn_queries;   /* queries processed by those launches */
+    unsigned long long knn_candidates;/* map points examined by those launches (sum of block sizes) */
+} liliom_counters;
+int liliom_get_counters(liliom_ctx* c, liliom_counters* out, int reset);
+/* 1: bracket every kNN+Jacobian launch with CUDA events on the context stream (default 0). */
+int liliom_set_kernel_timing(liliom_ctx* c, int on);
+/* Run all library work on a caller-owned CUDA stream (cudaStream_t passed as void*; NULL restores the
+ * context's own stream).  Calls stay synchronous; this only lets the caller bracket them with events. */
+int liliom_set_stream(liliom_ctx* c, void* cuda_stream);
+/* Device-resident benchmark hooks.  upload_scan: copy a raw sweep (point_stride bytes per point) into
+ * HBM; extract_resident: run the extractor of the context's variant on it without downloading the
+ * clouds (q_lb ignored for the Horizon variant); the surf features stay resident for
+ * liliom_odometry_resident(). */
+int liliom_upload_scan(liliom_ctx* c, const void* pts, int n);
+int liliom_extract_resident(liliom_ctx* c, const double q_imu_wxyz[4], const double q_lb_wxyz[4],
+                            int* n_surf, int* n_edge, int* n_cut);
+/* keep `n` feature points resident (feats stride 16/32/48) */
+int liliom_upload_feats(liliom_ctx* c, const void* feats_body, int n, int stride);
+/* run scan-to-map on the resident features; pose in/out on host but no other traffic */
+int liliom_scan_to_map_resident(liliom_ctx* c, double pose7_inout[7], int match_cnt, int max_num_iter, int mode,
+                                liliom_iter_stats* stats);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LILIOM_H */

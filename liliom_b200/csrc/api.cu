@@ -1,0 +1,495 @@
+// C ABI of libliliom_b200.so (see include/liliom.h for the contract and reference citations).
+#include "ctx.cuh"
+#include "dev_math.cuh"
+#include <new>
+
+namespace lili {
+void nccl_destroy(liliom_ctx* c);
+
+// ---- map sharding (multi-GPU): keep a point when any 8 m block touched by its halo box is owned by `rank`
+__device__ __forceinline__ unsigned sh_block_hash(int bx, int by, int bz) {
+    unsigned h = (unsigned)bx * 73856093u ^ (unsigned)by * 19349663u ^ (unsigned)bz * 83492791u;
+    h ^= h >> 15; h *= 0x2c1b3c6du; h ^= h >> 12;
+    return h;
+}
+__global__ void k_shard_flags(const float4* __restrict__ p, int n, float halo, int nranks, int rank, int* __restrict__ flags) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n) return;
+    int f = 0;
+    if (i < n) {
+        float4 v = p[i];
+        for (int c = 0; c < 8 && !f; ++c) {
+            float x = v.x + ((c & 1) ? halo : -halo), y = v.y + ((c & 2) ? halo : -halo), z = v.z + ((c & 4) ? halo : -halo);
+            int bx = (int)floorf(x * 0.125f), by = (int)floorf(y * 0.125f), bz = (int)floorf(z * 0.125f);
+            if ((int)(sh_block_hash(bx, by, bz) % (unsigned)nranks) == rank) f = 1;
+        }
+    }
+    flags[i] = f;
+}
+__global__ void k_compact_f4(const float4* __restrict__ in, const int* __restrict__ flags, const int* __restrict__ pos, int n, float4* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && flags[i]) out[pos[i]] = in[i];
+}
+
+// transformCloud (L/src/LidarOdometry.cpp:246-278; R/src/LidarOdometry.cpp:239-264)
+__global__ void k_transform_cloud(const unsigned char* __restrict__ in, int n, int stride, Q4 q, D3 t, unsigned char* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 a = *reinterpret_cast<const float4*>(in + (size_t)i * stride);
+    D3 r = qrot_x(q, D3{(double)a.x, (double)a.y, (double)a.z});
+    float4 o = make_float4((float)addx(r.x, t.x), (float)addx(r.y, t.y), (float)addx(r.z, t.z), 1.0f);
+    *reinterpret_cast<float4*>(out + (size_t)i * stride) = o;
+    if (stride == 48) {
+        const float4 b = *reinterpret_cast<const float4*>(in + (size_t)i * stride + 16);
+        const float4 cc = *reinterpret_cast<const float4*>(in + (size_t)i * stride + 32);
+        D3 nr = qrot_x(q, D3{(double)b.x, (double)b.y, (double)b.z});
+        *reinterpret_cast<float4*>(out + (size_t)i * stride + 16) = make_float4((float)nr.x, (float)nr.y, (float)nr.z, 0.f);
+        *reinterpret_cast<float4*>(out + (size_t)i * stride + 32) = make_float4(cc.x, cc.y, 0.f, 0.f);
+    } else {
+        const float4 b = *reinterpret_cast<const float4*>(in + (size_t)i * stride + 16);
+        *reinterpret_cast<float4*>(out + (size_t)i * stride + 16) = make_float4(b.x, 0.f, 0.f, 0.f);
+    }
+}
+
+static int install_map_from_xyzw(liliom_ctx* c, int m) {
+    // c->map_xyzw holds m float4 (w = global index).  Shard when a communicator is attached.
+    c->map_n_global = m;
+    if (c->nranks > 1 && m > 0) {
+        LILI_CUDA(c, c->flags.ensure(((size_t)m + 2) * 4));
+        LILI_CUDA(c, c->idx_a.ensure(((size_t)m + 2) * 4));
+        LILI_CUDA(c, c->map_ds.ensure((size_t)m * sizeof(float4)));
+        float cell = 1.0f;
+        while ((double)cell * (double)cell < c->prm.knn_max_sqdist) cell *= 2.0f;
+        k_shard_flags<<<cdiv(m + 1, 256), 256, 0, c->stream>>>(c->map_xyzw.as<float4>(), m, cell, c->nranks, c->rank, c->flags.as<int>());
+        LILI_TRY(launch_check(c, "k_shard_flags"));
+        LILI_TRY(exclusive_scan_i32(c, c->flags.as<int>(), c->idx_a.as<int>(), m));
+        k_compact_f4<<<cdiv(m, 256), 256, 0, c->stream>>>(c->map_xyzw.as<float4>(), c->flags.as<int>(), c->idx_a.as<int>(), m, c->map_ds.as<float4>());
+        LILI_TRY(launch_check(c, "k_compact_f4"));
+        int local = 0;
+        LILI_CUDA(c, cudaMemcpyAsync(&local, c->idx_a.as<int>() + m, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        LILI_CUDA(c, cudaStreamSynchronize(c->stream));
+        LILI_CUDA(c, cudaMemcpyAsync(c->map_xyzw.p, c->map_ds.p, (size_t)local * sizeof(float4), cudaMemcpyDeviceToDevice, c->stream));
+        m = local;
+    }
+    return grid_build(c, m);
+}
+
+static int upload_feats(liliom_ctx* c, const void* feats, int n, int stride) {
+    if (n < 0 || (n > 0 && !feats)) return LILIOM_E_ARG;
+    if (stride != 16 && stride != 32 && stride != 48) return LILIOM_E_ARG;
+    c->n_feats = n;
+    if (n == 0) return LILIOM_OK;
+    LILI_CUDA(c, c->feats.ensure((size_t)n * sizeof(float4)));
+    if (stride == 16) {
+        LILI_CUDA(c, cudaMemcpyAsync(c->feats.p, feats, (size_t)n * 16, cudaMemcpyHostToDevice, c->stream));
+    } else {
+        LILI_CUDA(c, c->raw.ensure((size_t)n * stride));
+        LILI_CUDA(c, cudaMemcpyAsync(c->raw.p, feats, (size_t)n * stride, cudaMemcpyHostToDevice, c->stream));
+        LILI_TRY(repack_to_f4(c, c->raw.p, n, stride, c->feats.as<float4>()));
+    }
+    return LILIOM_OK;
+}
+
+}  // namespace lili
+
+using namespace lili;
+
+extern "C" void liliom_default_params(liliom_params* p, int variant) {
+    if (!p) return;
+    memset(p, 0, sizeof(*p));
+    p->abi_version = LILIOM_ABI_VERSION;
+    p->point_stride = variant == 1 ? 32 : 48;
+    p->surf_thres = 0.2;         // L/config/config_fr_iosb.yaml:5
+    p->edge_thres = 4.0;         // L/config/config_fr_iosb.yaml:6
+    p->line_num = 64;            // R/config/config_fr_iosb.yaml
+    p->ds_rate = variant == 1 ? 4 : 1;
+    p->rot_ds_leaf = 0.6f;       // R/src/Preprocessing.cpp:14
+    p->leaf_scan = 0.4f;         // L/src/LidarOdometry.cpp:155
+    p->leaf_map = 0.4f;          // L/src/LidarOdometry.cpp:156
+    p->knn_max_sqdist = 1.0;     // :365
+    p->plane_thres = 0.06;       // :389
+    p->weight_gate = 0.4;        // :400
+    p->huber_a = 0.1;            // :507
+    p->max_map_frames = 20;      // :290
+    p->max_scan_points = 400000; // R/src/Preprocessing.cpp:9-12
+    p->max_map_points = 2000000;
+}
+
+extern "C" const char* liliom_strerror(int code) {
+    switch (code) {
+        case LILIOM_OK: return "ok";
+        case LILIOM_E_ARG: return "invalid argument";
+        case LILIOM_E_CUDA: return "CUDA error (see liliom_last_error)";
+        case LILIOM_E_FEWMAP: return "not enough feature points from the map (< 10): pose unchanged";
+        case LILIOM_E_CAPACITY: return "buffer capacity too small";
+        case LILIOM_E_GRID: return "map extent too large for the dense cell grid";
+        case LILIOM_E_LINES: return "wrong scan number (line_num must be 16, 32 or 64)";
+        case LILIOM_E_NCCL: return "NCCL error (see liliom_last_error)";
+        case LILIOM_E_NOMAP: return "no map installed";
+        default: return "unknown error";
+    }
+}
+
+extern "C" const char* liliom_last_error(const liliom_ctx* c) { return c ? c->last_error.c_str() : ""; }
+
+extern "C" int liliom_create(liliom_ctx** out, const liliom_params* p, int device) {
+    if (!out || !p) return LILIOM_E_ARG;
+    *out = nullptr;
+    if (p->abi_version != LILIOM_ABI_VERSION) return LILIOM_E_ARG;
+    if (p->point_stride != 48 && p->point_stride != 32) return LILIOM_E_ARG;
+    if (!(p->knn_max_sqdist > 0) || p->knn_max_sqdist > 4.0) return LILIOM_E_ARG;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return LILIOM_E_CUDA;   // no CPU fallback
+    liliom_ctx* c = new (std::nothrow) liliom_ctx();
+    if (!c) return LILIOM_E_ARG;
+    c->prm = *p;
+    c->device = device;
+    LILI_CUDA(c, cudaSetDevice(device));
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->sm_count = prop.multiProcessorCount;
+    cudaError_t e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete c; return LILIOM_E_CUDA; }
+    c->stream = c->own_stream;
+    c->h_pin_bytes = 1 << 20;
+    e = cudaHostAlloc(&c->h_pin, c->h_pin_bytes, cudaHostAllocDefault);
+    if (e != cudaSuccess) { cudaStreamDestroy(c->own_stream); delete c; return LILIOM_E_CUDA; }
+    *out = c;
+    return LILIOM_OK;
+}
+
+extern "C" void liliom_destroy(liliom_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    nccl_destroy(c);
+    DevBuf* bufs[] = {&c->raw, &c->cut, &c->surf, &c->edge, &c->flags, &c->scan_tmp, &c->idx_a, &c->idx_b, &c->hz_mat, &c->hz_stage_surf,
+                      &c->hz_stage_edge, &c->hz_counts, &c->rot_keys, &c->rot_keys2, &c->rot_vals, &c->rot_vals2, &c->rot_cloud, &c->rot_curv,
+                      &c->rot_label, &c->rot_picked, &c->rot_sort, &c->rot_ring, &c->rot_meta, &c->rot_lessflat, &c->rot_seg_edge, &c->vg_keys,
+                      &c->vg_keys2, &c->vg_vals, &c->vg_vals2, &c->vg_flags, &c->vg_rank, &c->vg_params, &c->vg_out, &c->vg_minmax, &c->vg_count,
+                      &c->cub_tmp, &c->map_raw, &c->map_ds, &c->map_xyzw, &c->map_sorted, &c->cell_start, &c->grid_keys, &c->grid_keys2,
+                      &c->grid_vals, &c->grid_vals2, &c->feats, &c->corr_valid, &c->corr_plane, &c->nn_idx, &c->nn_sqd, &c->pose_dev,
+                      &c->partials, &c->neq, &c->stats_dev, &c->counter, &c->lm_state, &c->raw_scan};
+    for (DevBuf* b : bufs) b->release();
+    for (auto& f : c->frames) f.buf.release();
+    for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
+    if (c->h_pin) cudaFreeHost(c->h_pin);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete c;
+}
+
+// ===================== L1 =====================
+extern "C" int liliom_extract_horizon(liliom_ctx* c, const liliom_pt48* pts, int n, const double q_imu[4],
+                                      liliom_pt48* surf_out, int surf_cap, int* n_surf, liliom_pt48* edge_out, int edge_cap, int* n_edge,
+                                      liliom_pt48* cut_out, int cut_cap, int* n_cut) {
+    if (!c || n < 0 || (n > 0 && !pts) || !q_imu || !n_surf || !n_edge || !n_cut) return LILIOM_E_ARG;
+    if (c->prm.point_stride != 48) return LILIOM_E_ARG;
+    LILI_CUDA(c, cudaSetDevice(c->device));
+    LILI_CUDA(c, c->raw.ensure((size_t)(n > 0 ? n : 1) * 48));
+    if (n > 0) LILI_CUDA(c, cudaMemcpyAsync(c->raw.p, pts, (size_t)n * 48, cudaMemcpyHostToDevice, c->stream));
+    int ns = 0, ne = 0, nc = 0;
+    LILI_TRY(horizon_extract_dev(c, n, q_imu, &ns, &ne, &nc));
+    if ((surf_out && ns > surf_cap) || (edge_out && ne > edge_cap) || (cut_out && nc > cut_cap)) return LILIOM_E_CAPACITY;
+    if (surf_out && ns) LILI_CUDA(c, cudaMemcpyAsync(surf_out, c->surf.p, (size_t)ns * 48, cudaMemcpyDeviceToHost, c->stream));
+    if (edge_out && ne) LILI_CUDA(c, cudaMemcpyAsync(edge_out, c->edge.p, (size_t)ne * 48, cudaMemcpyDeviceToHost, c->stream));
+    if (cut_out && nc) LILI_CUDA(c, cudaMemcpyAsync(cut_out, c->cut.p, (size_t)nc * 48, cudaMemcpyDeviceToHost, c->stream));
+    LILI_CUDA(c, cudaStreamSynchronize(c->stream));
+    *n_surf = ns; *n_edge = ne; *n_cut = nc;
+    return LILIOM_OK;
+}
+
+extern "C" int liliom_extract_rot(liliom_ctx* c, const liliom_pt32* pts, int n, const double q_imu[4], const double q_lb[4],
+                                  liliom_pt32* surf_out, int surf_cap, int* n_surf, liliom_pt32* edge_out, int edge_cap, int* n_edge,
+                                  liliom_pt32* cut_out, int cut_cap, int* n_cut) {
+    if (!c || n < 0 || (n > 0 && !pts) || !q_imu || !q_lb || !n_surf || !n_edge || !n_cut) return LILIOM_E_ARG;
+    if (c->prm.point_stride != 32) return LILIOM_E_ARG;
+    LILI_CUDA(c, cudaSetDevice(c->device));
+    LILI_CUDA(c, c->raw.ensure((size_t)(n > 0 ? n : 1) * 32));
+    if (n > 0) LILI_CUDA(c, cudaMemcpyAsync(c->raw.p, pts, (size_t)n * 32, cudaMemcpyHostToDevice, c->stream));
+    int ns = 0, ne = 0, nc = 0;
+    LILI_TRY(rot_extract_dev(c, n, q_imu, q_lb, &ns, &ne, &nc));
+    if ((surf_out && ns > surf_cap) || (edge_out && ne > edge_cap) || (cut_out && nc > cut_cap)) return LILIOM_E_CAPACITY;
+    if (surf_out && ns) LILI_CUDA(c, cudaMemcpyAsync(surf_out, c->surf.p, (size_t)ns * 32, cudaMemcpyDeviceToHost, c->stream));
+    if (edge_out && ne) LILI_CUDA(c, cudaMemcpyAsync(edge_out, c->edge.p, (size_t)ne * 32, cudaMemcpyDeviceToHost, c->stream));
+    if (cut_out && nc) LILI_CUDA(c, cudaMemcpyAsync(cut_out, c->rot_cloud.p, (size_t)nc * 32, cudaMemcpyDeviceToHost, c->stream));
+    LILI_CUDA(c, cudaStreamSynchronize(c->stream));
+    *n_surf = ns; *n_edge = ne; *n_cut = nc;
+    return LILIOM_OK;
+}
+
+extern "C" int liliom_extract_rot_labels(liliom_ctx* c, int* label_out, float* curv_out, int cap) {
+    if (!c) return LILIOM_E_ARG;
+    const int n = c->n_rot_cloud;
+    if (n > cap) return LILIOM_E_CAPACITY;
+    LILI_CUDA(c, cudaSetDevice(c->device));
+    if (label_out && n) LILI_CUDA(c, cudaMemcpyAsync(label_out, c->rot_label.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (curv_out && n) LILI_CUDA(c, cudaMemcpyAsync(curv_out, c->rot_curv.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+    LILI_CUDA(c, cudaStreamSynchronize(c->stream));
+    return LILIOM_OK;
+}
+
+extern "C" int liliom_voxelgrid(liliom_ctx* c, const void* pts, int n, int stride, float leaf, void* out, int cap, int* n_out) {
+    if (!c || n < 0 || (n > 0 && !pts) || !n_out || !(leaf > 0)) return LILIOM_E_ARG;
+    if (stride != 48 && stride != 32) return LILIOM_E_ARG;
+    LILI_CUDA(c, cudaSetDevice(c->device));
+    *n_out = 0;
+    if (n == 0) return LILIOM_OK;
+    LILI_CUDA(c, c->raw.ensure((size_t)n * stride));
+    LILI_CUDA(c, c->vg_out.ensure((size_t)n * stride));
+    LILI_CUDA(c, c->vg_count.ensure(16));
+    LILI_CUDA(c, cudaMemcpyAsync(c->raw.p, pts, (size_t)n * stride, cudaMemcpyHostToDevice, c->stream));
+    LILI_TRY(voxelgrid_dev(c, c->raw.p, n, stride, leaf, c->vg_out.p, c->vg_count.as<int>()));
+    int* hp = reinterpret_cast<int*>(c->h_pin);
+    LILI_CUDA(c, cudaMemcpyAsync(hp, c->vg_count.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    LILI_CUDA(c, cudaStreamSynchronize(c->stream));
+    const int m = hp[0];
+    if (out && m > cap) return LILIOM_E_CAPACITY;
+    if (out && m) {
+        LILI_CUDA(c, cudaMemcpyAsync(out, c->vg_out.p, (size_t)m * stride, cudaMemcpyDeviceToHost, c->stream));
+        LILI_CUDA(c, cudaStreamSynchronize(c->stream));
+    }
+    *n_out = m;
+    return LILIOM_OK;
+}
+
+// ===================== L2: map =====================
+extern "C" int liliom_map_clear(liliom_ctx* c) {
+    if (!c) return LILIOM_E_ARG;
+    for (auto& f : c->frames) f.buf.release();
+    c->frames.clear();
+    c->map_ready = false; c->map_n = 0; c->map_n_global = 0;
+    return LILIOM_OK;
+}
+
+extern "C" int liliom_map_push_frame(liliom_ctx* c, const void* surf_ds_body, int n, const double pose7[7]) {
+    if (!c || n < 0 || (n > 0 && !surf_ds_body) || !pose7) return LILIOM_E_ARG;
+    LILI_CUDA(c, cudaSetDevice(c->device));
+    const int stride = c->prm.point_stride;
+    if ((int)c->frames.size() >= c->prm.max_map_frames && !c->frames.empty()) {      // L/src/LidarOdometry.cpp:293-296 pop_front
+        c->frames.front().buf.release();
+        c->frames.erase(c->frames.begin());
+    }
+    Frame f;
+    f.n = n;
+    if (n > 0) {
+        LILI_CUDA(c, f.buf.ensure((size_t)n * stride));
+        LILI_CUDA(c, c->raw.ensure((size_t)n * stride));
+        LILI_CUDA(c, cudaMemcpyAsync(c->raw.p, surf_ds_body, (size_t)n * stride, cudaMemcpyHostToDevice, c->stream));
+        Q4 q{pose7[0], pose7[1], pose7[2], pose7[3]};
+        D3 t{pose7[4], pose7[5], pose7[6]};
+        k_transform_cloud<<<cdiv(n, 256), 256, 0, c->stream>>>((const unsigned char*)c->raw.p, n, stride, q, t, (unsigned char*)f.buf.p);
+        LILI_TRY(launch_check(c, "k_transform_cloud"));
+        LILI_CUDA(c, cudaStreamSynchronize(c->stream));
+    }
+    c->frames.push_back(f);
+    return LILIOM_OK;
+}
+
+extern "C" int liliom_map_rebuild(liliom_ctx* c, int* n_map_out) {
+    if (!c) return LILIOM_E_ARG;
+    LILI_CUDA(c, cudaSetDevice(c->device));
+    const int stride = c->prm.point_stride;
+    size_t total = 0;
+    for (auto& f : c->frames) total += (size_t)f.n;
+    c->map_ready = false; c->map_n = 0; c->map_n_global = 0;
+    if (n_map_out) *n_map_out = 0;
+    if (total == 0) { c->map_ready = true; return LILIOM_OK; }
+    LILI_CUDA(c, c->map_raw.ensure(total * stride));
+    LILI_CUDA(c, c->map_ds.ensure(total * stride));
+    LILI_CUDA(c, c->vg_count.ensure(16));
+    size_t off = 0;
+    for (auto& f : c->frames) {                                                    // :301-302 concatenation, oldest first
+        if (f.n) LILI_CUDA(c, cudaMemcpyAsync((unsigned char*)c->map_raw.p + off * stride, f.buf.p, (size_t)f.n * stride, cudaMemcpyDeviceToDevice, c->stream));
+        off += (size_t)f.n;
+    }
+    LILI_TRY(voxelgrid_dev(c, c->map_raw.p, (int)total, stride, c->prm.leaf_map, c->map_ds.p, c->vg_count.as<int>()));   // :316-317
+    int* hp = reinterpret_cast<int*>(c->h_pin);
+    LILI_CUDA(c, cudaMemcpyAsync(hp, c->vg_count.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    LILI_CUDA(c, cudaStreamSynchronize(c->stream));
+    const int m = hp[0];
+    LILI_CUDA(c, c->map_xyzw.ensure((size_t)(m > 0 ? m : 1) * sizeof(float4)));
+    LILI_TRY(repack_to_f4(c, c->map_ds.p, m, stride, c->map_xyzw.as<float4>()));
+    c->map_n_global = m;
+    if (c->nranks > 1) LILI_TRY(install_map_from_xyzw(c, m));
+    else LILI_TRY(grid_build(c, m));
+    LILI_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (n_map_out) *n_map_out = m;
+    return LILIOM_OK;
+}
+
+extern "C" int liliom_map_set_points(liliom_ctx* c, const liliom_f4* xyzw, int m) {
+    if (!c || m < 0 || (m > 0 && !xyzw)) return LILIOM_E_ARG;
+    LILI_CUDA(c, cudaSetDevice(c->device));
+    c->map_ready = false;
+    LILI_CUDA(c, c->map_xyzw.ensure((size_t)(m > 0 ? m : 1) * sizeof(float4)));
+    LILI_CUDA(c, c->raw.ensure((size_t)(m > 0 ? m : 1) * sizeof(float4)));
+    if (m > 0) {
+        LILI_CUDA(c, cudaMemcpyAsync(c->raw.p, xyzw, (size_t)m * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+        LILI_TRY(repack_to_f4(c, c->raw.p, m, 16, c->map_xyzw.as<float4>()));
+    }
+    LILI_TRY(install_map_from_xyzw(c, m));
+    LILI_CUDA(c, cudaStreamSynchronize(c->stream));
+    return LILIOM_OK;
+}
+
+extern "C" int liliom_map_size(const liliom_ctx* c) { return c ? c->map_n : 0; }
+
+extern "C" int liliom_map_download(liliom_ctx* c, liliom_f4* out, int cap, int* m_out) {
+    if (!c || !m_out) return LILIOM_E_ARG;
+    LILI_CUDA(c, cudaSetDevice(c->device));
+    const int m = c->map_n;
+    *m_out = m;
+    if (!out) return LILIOM_OK;
+    if (m > cap) return LILIOM_E_CAPACITY;
+    if (m) LILI_CUDA(c, cudaMemcpyAsync(out, c->map_xyzw.p, (size_t)m * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+    LILI_CUDA(c, cudaStreamSynchronize(c->stream));
+    return LILIOM_OK;
+}
+
+// ===================== L2: scan-to-map =====================
+extern "C" int liliom_upload_feats(liliom_ctx* c, const void* feats, int n, int stride) {
+    if (!c) return LILIOM_E_ARG;
+    LILI_CUDA(c, cudaSetDevice(c->device));
+    LILI_TRY(upload_feats(c, feats, n, stride));
+    LILI_CUDA(c, cudaStreamSynchronize(c->stream));
+    return LILIOM_OK;
+}
+
+extern "C" int liliom_scan_to_map_resident(liliom_ctx* c, double pose7[7], int match_cnt, int max_num_iter, int mode, liliom_iter_stats* stats) {
+    if (!c || !pose7 || (mode != LILIOM_MODE_CERES && mode != LILIOM_MODE_GN) || match_cnt < 0) return LILIOM_E_ARG;
+    LILI_CUDA(c, cudaSetDevice(c->device));
+    return s2m_run(c, pose7, match_cnt, max_num_iter, mode, stats, false, nullptr);
+}
+
+extern "C" int liliom_scan_to_map(liliom_ctx* c, const void* feats, int n, int stride, double pose7[7], int match_cnt, int max_num_iter,
+                                  int mode, liliom_iter_stats* stats) {
+    if (!c || !pose7 || (mode != LILIOM_MODE_CERES && mode != LILIOM_MODE_GN) || match_cnt < 0) return LILIOM_E_ARG;
+    LILI_CUDA(c, cudaSetDevice(c->device));
+    if (!c->map_ready) return LILIOM_E_NOMAP;
+    if (c->map_n_global < 10) return LILIOM_E_FEWMAP;
+    LILI_TRY(upload_feats(c, feats, n, stride));
+    return s2m_run(c, pose7, match_cnt, max_num_iter, mode, stats, false, nullptr);
+}
+
+static int odometry_on_resident_surf(liliom_ctx* c, double pose7[7], int match_cnt, int max_num_iter, int mode, liliom_iter_stats* stats,
+                                     void* ds_out, int ds_cap, int* n_ds);
+
+extern "C" int liliom_odometry(liliom_ctx* c, const void* surf_feats, int n, double pose7[7], int match_cnt, int max_num_iter, int mode,
+                               liliom_iter_stats* stats, void* ds_out, int ds_cap, int* n_ds) {
+    if (!c || !pose7 || n < 0 || (n > 0 && !surf_feats) || (mode != LILIOM_MODE_CERES && mode != LILIOM_MODE_GN) || match_cnt < 0) return LILIOM_E_ARG;
+    LILI_CUDA(c, cudaSetDevice(c->device));
+    const int stride = c->prm.point_stride;
+    LILI_CUDA(c, c->surf.ensure((size_t)(n > 0 ? n : 1) * stride));
+    if (n > 0) LILI_CUDA(c, cudaMemcpyAsync(c->surf.p, surf_feats, (size_t)n * stride, cudaMemcpyHostToDevice, c->stream));
+    c->n_surf_dev = n;
+    return odometry_on_resident_surf(c, pose7, match_cnt, max_num_iter, mode, stats, ds_out, ds_cap, n_ds);
+}
+
+extern "C" int liliom_set_stream(liliom_ctx* c, void* cuda_stream) {
+    if (!c) return LILIOM_E_ARG;
+    LILI_CUDA(c, cudaSetDevice(c->device));
+    LILI_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->stream = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
+    return LILIOM_OK;
+}
+
+extern "C" int liliom_upload_scan(liliom_ctx* c, const void* pts, int n) {
+    if (!c || n < 0 || (n > 0 && !pts)) return LILIOM_E_ARG;
+    LILI_CUDA(c, cudaSetDevice(c->device));
+    const int stride = c->prm.point_stride;
+    LILI_CUDA(c, c->raw_scan.ensure((size_t)(n > 0 ? n : 1) * stride));
+    if (n > 0) LILI_CUDA(c, cudaMemcpyAsync(c->raw_scan.p, pts, (size_t)n * stride, cudaMemcpyHostToDevice, c->stream));
+    LILI_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->n_raw_scan = n;
+    return LILIOM_OK;
+}
+
+extern "C" int liliom_extract_resident(liliom_ctx* c, const double q_imu[4], const double q_lb[4], int* n_surf, int* n_edge, int* n_cut) {
+    if (!c || !q_imu || !n_surf || !n_edge || !n_cut) return LILIOM_E_ARG;
+    LILI_CUDA(c, cudaSetDevice(c->device));
+    const int stride = c->prm.point_stride;
+    const int n = c->n_raw_scan;
+    // the extractors read c->raw: a device-to-device copy keeps the resident sweep reusable across steps
+    LILI_CUDA(c, c->raw.ensure((size_t)(n > 0 ? n : 1) * stride));
+    if (n > 0) LILI_CUDA(c, cudaMemcpyAsync(c->raw.p, c->raw_scan.p, (size_t)n * stride, cudaMemcpyDeviceToDevice, c->stream));
+    if (stride == 48) return horizon_extract_dev(c, n, q_imu, n_surf, n_edge, n_cut);
+    const double ident[4] = {1, 0, 0, 0};
+    return rot_extract_dev(c, n, q_imu, q_lb ? q_lb : ident, n_surf, n_edge, n_cut);
+}
+
+static int odometry_on_resident_surf(liliom_ctx* c, double pose7[7], int match_cnt, int max_num_iter, int mode, liliom_iter_stats* stats,
+                                     void* ds_out, int ds_cap, int* n_ds) {
+    if (!c || !pose7 || (mode != LILIOM_MODE_CERES && mode != LILIOM_MODE_GN) || match_cnt < 0) return LILIOM_E_ARG;
+    LILI_CUDA(c, cudaSetDevice(c->device));
+    const int stride = c->prm.point_stride;
+    const int n = c->n_surf_dev;
+    LILI_CUDA(c, c->vg_out.ensure((size_t)(n > 0 ? n : 1) * stride));
+    LILI_CUDA(c, c->vg_count.ensure(16));
+    int m = n;
+    if (c->prm.leaf_scan > 0.0f) {
+        LILI_TRY(voxelgrid_dev(c, c->surf.p, n, stride, c->prm.leaf_scan, c->vg_out.p, c->vg_count.as<int>()));      // L/src/LidarOdometry.cpp:321-322
+        int* hp = reinterpret_cast<int*>(c->h_pin) + 1024;
+        LILI_CUDA(c, cudaMemcpyAsync(hp, c->vg_count.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        LILI_CUDA(c, cudaStreamSynchronize(c->stream));
+        m = hp[0];
+    } else if (n > 0) {   // leaf_scan == 0: benchmark mode, every surf feature is a query
+        LILI_CUDA(c, cudaMemcpyAsync(c->vg_out.p, c->surf.p, (size_t)n * stride, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    if (n_ds) *n_ds = m;
+    if (ds_out && m > ds_cap) return LILIOM_E_CAPACITY;
+    LILI_CUDA(c, c->feats.ensure((size_t)(m > 0 ? m : 1) * sizeof(float4)));
+    LILI_TRY(repack_to_f4(c, c->vg_out.p, m, stride, c->feats.as<float4>()));
+    c->n_feats = m;
+    if (ds_out && m) LILI_CUDA(c, cudaMemcpyAsync(ds_out, c->vg_out.p, (size_t)m * stride, cudaMemcpyDeviceToHost, c->stream));
+    if (!c->map_ready) { LILI_CUDA(c, cudaStreamSynchronize(c->stream)); return LILIOM_E_NOMAP; }
+    if (c->map_n_global < 10) { LILI_CUDA(c, cudaStreamSynchronize(c->stream)); return LILIOM_E_FEWMAP; }
+    return s2m_run(c, pose7, match_cnt, max_num_iter, mode, stats, false, nullptr);
+}
+
+extern "C" int liliom_odometry_resident(liliom_ctx* c, double pose7[7], int match_cnt, int max_num_iter, int mode, liliom_iter_stats* stats,
+                                        void* ds_out, int ds_cap, int* n_ds) {
+    return odometry_on_resident_surf(c, pose7, match_cnt, max_num_iter, mode, stats, ds_out, ds_cap, n_ds);
+}
+
+extern "C" int liliom_find_surf_corr(liliom_ctx* c, const void* feats, int n, int stride, const double pose7[7], unsigned char* valid,
+                                     float* plane, int* nn_idx, float* sqd, double out29[29]) {
+    if (!c || !pose7) return LILIOM_E_ARG;
+    LILI_CUDA(c, cudaSetDevice(c->device));
+    if (!c->map_ready) return LILIOM_E_NOMAP;
+    if (c->map_n_global < 10) return LILIOM_E_FEWMAP;
+    LILI_TRY(upload_feats(c, feats, n, stride));
+    double p[7];
+    memcpy(p, pose7, sizeof(p));
+    LILI_TRY(s2m_run(c, p, 0, 0, LILIOM_MODE_GN, nullptr, true, out29));
+    if (n > 0) {
+        if (valid) LILI_CUDA(c, cudaMemcpyAsync(valid, c->corr_valid.p, (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+        if (plane) LILI_CUDA(c, cudaMemcpyAsync(plane, c->corr_plane.p, (size_t)n * 16, cudaMemcpyDeviceToHost, c->stream));
+        if (nn_idx) LILI_CUDA(c, cudaMemcpyAsync(nn_idx, c->nn_idx.p, (size_t)n * 20, cudaMemcpyDeviceToHost, c->stream));
+        if (sqd) LILI_CUDA(c, cudaMemcpyAsync(sqd, c->nn_sqd.p, (size_t)n * 20, cudaMemcpyDeviceToHost, c->stream));
+        LILI_CUDA(c, cudaStreamSynchronize(c->stream));
+    }
+    return LILIOM_OK;
+}
+
+// ===================== instrumentation =====================
+extern "C" int liliom_get_counters(liliom_ctx* c, liliom_counters* out, int reset) {
+    if (!c || !out) return LILIOM_E_ARG;
+    LILI_CUDA(c, cudaSetDevice(c->device));
+    unsigned long long cand = 0;
+    if (c->counter.p) {
+        LILI_CUDA(c, cudaMemcpyAsync(&cand, c->counter.as<unsigned char>() + 16, sizeof(cand), cudaMemcpyDeviceToHost, c->stream));
+        LILI_CUDA(c, cudaStreamSynchronize(c->stream));
+    }
+    c->cnt.knn_candidates = cand;
+    *out = c->cnt;
+    if (reset) {
+        c->cnt = liliom_counters{};
+        if (c->counter.p) LILI_CUDA(c, cudaMemsetAsync(c->counter.as<unsigned char>() + 16, 0, 8, c->stream));
+    }
+    return LILIOM_OK;
+}
+
+extern "C" int liliom_set_kernel_timing(liliom_ctx* c, int on) {
+    if (!c) return LILIOM_E_ARG;
+    c->time_kernels = on != 0;
+    return LILIOM_OK;
+}

@@ -1,0 +1,198 @@
+// BackendFusion correspondence searches on the same kNN core:
+//   point-to-line : L/src/BackendFusion.cpp:1531-1599 (variant 0), R/src/BackendFusion.cpp:1394-1462 (variant 1)
+//   point-to-plane: R/src/BackendFusion.cpp:1464-1520 (configurable radius / plane gate / weight gate / score)
+// The sliding-window optimiser that consumes them is out of scope; these kernels only produce
+// the per-feature residual inputs (line end points a/b, weighted plane, score).
+#include "ctx.cuh"
+#include "dev_math.cuh"
+#include "knn_core.cuh"
+
+namespace lili {
+
+struct BkArgs {
+    const float4* feats; int n;
+    const float4* map; const int* cell_start; GridDesc g;
+    Q4 q; D3 t;
+    int variant;
+    double max_sqd, plane_thres, w_gate, lidar_const;
+    unsigned char* valid; float* pa; float* pb; float4* plane; double* score;
+};
+
+__global__ void __launch_bounds__(kBlock) k_backend_edge(BkArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int sub = lane & (kLanes - 1), oct = lane / kLanes;
+    const unsigned omask = ((1u << kLanes) - 1u) << (oct * kLanes);
+    const int qi = (blockIdx.x * blockDim.x + threadIdx.x) / kLanes;
+    if (qi >= a.n) return;   // uniform per octet
+    const float inf = __int_as_float(0x7f800000);
+    float4 f = a.feats[qi];
+    D3 pw = qrot_x(a.q, D3{(double)f.x, (double)f.y, (double)f.z});
+    const float sx = (float)addx(pw.x, a.t.x), sy = (float)addx(pw.y, a.t.y), sz = (float)addx(pw.z, a.t.z);
+    Top5 top{inf, inf, inf, inf, inf, -1, -1, -1, -1, -1};
+    unsigned long long cand = 0;
+    octet_knn5(sx, sy, sz, a.map, a.cell_start, a.g, sub, omask, top, cand);
+    if (sub != 0) return;
+    bool ok = false;
+    float A3[3] = {0, 0, 0}, B3[3] = {0, 0, 0};
+    if (top.p4 >= 0 && (double)top.d4 < 1.0) {                                        // L:1543
+        const int pos[5] = {top.p0, top.p1, top.p2, top.p3, top.p4};
+        double px[5], py[5], pz[5], cx = 0, cy = 0, cz = 0;
+        for (int j = 0; j < 5; ++j) {
+            float4 m = a.map[pos[j]];
+            px[j] = m.x; py[j] = m.y; pz[j] = m.z;
+            cx = addx(cx, px[j]); cy = addx(cy, py[j]); cz = addx(cz, pz[j]);
+        }
+        cx = cx / 5.0; cy = cy / 5.0; cz = cz / 5.0;                                  // L:1555
+        double a00 = 0, a10 = 0, a20 = 0, a11 = 0, a21 = 0, a22 = 0;
+        for (int j = 0; j < 5; ++j) {                                                  // L:1560-1564
+            double z0 = subx(px[j], cx), z1 = subx(py[j], cy), z2 = subx(pz[j], cz);
+            a00 = addx(a00, mulx(z0, z0)); a10 = addx(a10, mulx(z1, z0)); a20 = addx(a20, mulx(z2, z0));
+            a11 = addx(a11, mulx(z1, z1)); a21 = addx(a21, mulx(z2, z1)); a22 = addx(a22, mulx(z2, z2));
+        }
+        double ev[3], evec[3][3];
+        eigen_sym3(a00, a10, a20, a11, a21, a22, ev, evec);                            // L:1568
+        if (ev[2] > 3 * ev[1]) {                                                       // L:1575
+            const double ux = evec[0][2], uy = evec[1][2], uz = evec[2][2];
+            const double ax = cx + 0.1 * ux, ay = cy + 0.1 * uy, az = cz + 0.1 * uz;   // L:1579
+            const double bx = cx - 0.1 * ux, by = cy - 0.1 * uy, bz = cz - 0.1 * uz;   // L:1580
+            ok = true;
+            if (a.variant == 1) {                                                      // R:1435-1439
+                const double ux_ = sx - ax, uy_ = sy - ay, uz_ = sz - az;
+                const double vx_ = sx - bx, vy_ = sy - by, vz_ = sz - bz;
+                const double nx = uy_ * vz_ - uz_ * vy_, ny = uz_ * vx_ - ux_ * vz_, nz = ux_ * vy_ - uy_ * vx_;
+                const double dx = ax - bx, dy = ay - by, dz = az - bz;
+                const double dist = sqrt(nx * nx + ny * ny + nz * nz) / sqrt(dx * dx + dy * dy + dz * dz);
+                if (!(dist < 0.1)) ok = false;
+            }
+            if (ok) {
+                A3[0] = (float)ax; A3[1] = (float)ay; A3[2] = (float)az;
+                B3[0] = (float)bx; B3[1] = (float)by; B3[2] = (float)bz;
+            }
+        }
+    }
+    a.valid[qi] = ok ? 1 : 0;
+    for (int k = 0; k < 3; ++k) { a.pa[3 * (size_t)qi + k] = A3[k]; a.pb[3 * (size_t)qi + k] = B3[k]; }
+}
+
+__global__ void __launch_bounds__(kBlock) k_backend_surf(BkArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int sub = lane & (kLanes - 1), oct = lane / kLanes;
+    const unsigned omask = ((1u << kLanes) - 1u) << (oct * kLanes);
+    const int qi = (blockIdx.x * blockDim.x + threadIdx.x) / kLanes;
+    if (qi >= a.n) return;
+    const float inf = __int_as_float(0x7f800000);
+    float4 f = a.feats[qi];
+    D3 pw = qrot_x(a.q, D3{(double)f.x, (double)f.y, (double)f.z});
+    const float sx = (float)addx(pw.x, a.t.x), sy = (float)addx(pw.y, a.t.y), sz = (float)addx(pw.z, a.t.z);
+    Top5 top{inf, inf, inf, inf, inf, -1, -1, -1, -1, -1};
+    unsigned long long cand = 0;
+    octet_knn5(sx, sy, sz, a.map, a.cell_start, a.g, sub, omask, top, cand);
+    if (sub != 0) return;
+    bool ok = false;
+    float4 pl = make_float4(0, 0, 0, 0);
+    double sc = 0;
+    if (top.p4 >= 0 && (double)top.d4 < a.max_sqd) {                                   // R:1476
+        const int pos[5] = {top.p0, top.p1, top.p2, top.p3, top.p4};
+        double A[5][3], B[5];
+        float4 m[5];
+        for (int j = 0; j < 5; ++j) { m[j] = a.map[pos[j]]; A[j][0] = m[j].x; A[j][1] = m[j].y; A[j][2] = m[j].z; B[j] = -1.0; }
+        double nv[3];
+        colpiv_qr_solve_5x3(A, B, nv);                                                 // R:1484
+        double n2 = nv[0] * nv[0] + nv[1] * nv[1] + nv[2] * nv[2];
+        double nn = sqrt(n2);
+        double normInverse = 1.0 / nn;
+        if (n2 > 0) { nv[0] /= nn; nv[1] /= nn; nv[2] /= nn; }
+        bool planeValid = true;
+        for (int j = 0; j < 5; ++j)                                                    // R:1489-1497
+            if (fabs(nv[0] * m[j].x + nv[1] * m[j].y + nv[2] * m[j].z + normInverse) > a.plane_thres) planeValid = false;
+        if (planeValid) {
+            float pd = (float)addx(addx(addx(mulx(nv[0], (double)sx), mulx(nv[1], (double)sy)), mulx(nv[2], (double)sz)), normInverse);
+            float rng = __fsqrt_rn(__fsqrt_rn(faddx(faddx(fmulx(sx, sx), fmulx(sy, sy)), fmulx(sz, sz))));
+            float weight = (float)subx(1.0, mulx(0.9, (double)fabsf(pd)) / (double)rng);   // R:1502
+            if ((double)weight > a.w_gate) {                                           // R:1504
+                pl = make_float4((float)mulx((double)weight, nv[0]), (float)mulx((double)weight, nv[1]),
+                                 (float)mulx((double)weight, nv[2]), (float)mulx((double)weight, normInverse));
+                sc = a.lidar_const * (double)weight;                                   // R:1515
+                ok = true;
+            }
+        }
+    }
+    a.valid[qi] = ok ? 1 : 0;
+    a.plane[qi] = pl;
+    a.score[qi] = sc;
+}
+
+static int backend_prepare(liliom_ctx* c, const void* feats, int n, int stride) {
+    if (!c->map_ready) return LILIOM_E_NOMAP;
+    if (n < 0 || (n > 0 && !feats)) return LILIOM_E_ARG;
+    if (stride != 16 && stride != 32 && stride != 48) return LILIOM_E_ARG;
+    c->n_feats = n;
+    if (n == 0) return LILIOM_OK;
+    LILI_CUDA(c, c->feats.ensure((size_t)n * sizeof(float4)));
+    if (stride == 16) {
+        LILI_CUDA(c, cudaMemcpyAsync(c->feats.p, feats, (size_t)n * 16, cudaMemcpyHostToDevice, c->stream));
+    } else {
+        LILI_CUDA(c, c->raw.ensure((size_t)n * stride));
+        LILI_CUDA(c, cudaMemcpyAsync(c->raw.p, feats, (size_t)n * stride, cudaMemcpyHostToDevice, c->stream));
+        LILI_TRY(repack_to_f4(c, c->raw.p, n, stride, c->feats.as<float4>()));
+    }
+    return LILIOM_OK;
+}
+
+}  // namespace lili
+
+using namespace lili;
+
+extern "C" int liliom_correspond_edge(liliom_ctx* c, const void* feats, int n, int stride, const double pose7[7], int variant,
+                                      unsigned char* valid, float* pa, float* pb) {
+    if (!c || !pose7 || !valid || !pa || !pb || (variant != 0 && variant != 1)) return LILIOM_E_ARG;
+    LILI_CUDA(c, cudaSetDevice(c->device));
+    LILI_TRY(backend_prepare(c, feats, n, stride));
+    if (n == 0) return LILIOM_OK;
+    LILI_CUDA(c, c->corr_valid.ensure((size_t)n + 16));
+    LILI_CUDA(c, c->corr_plane.ensure((size_t)n * 24 + 16));
+    BkArgs a{};
+    a.feats = c->feats.as<float4>(); a.n = n; a.map = c->map_sorted.as<float4>(); a.cell_start = c->cell_start.as<int>(); a.g = c->grid;
+    a.q = Q4{pose7[0], pose7[1], pose7[2], pose7[3]}; a.t = D3{pose7[4], pose7[5], pose7[6]};
+    a.variant = variant;
+    a.valid = c->corr_valid.as<unsigned char>();
+    a.pa = c->corr_plane.as<float>(); a.pb = a.pa + 3 * (size_t)n;
+    k_backend_edge<<<cdiv((long long)n * kLanes, kBlock), kBlock, 0, c->stream>>>(a);
+    LILI_TRY(launch_check(c, "k_backend_edge"));
+    LILI_CUDA(c, cudaMemcpyAsync(valid, a.valid, (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    LILI_CUDA(c, cudaMemcpyAsync(pa, a.pa, (size_t)n * 12, cudaMemcpyDeviceToHost, c->stream));
+    LILI_CUDA(c, cudaMemcpyAsync(pb, a.pb, (size_t)n * 12, cudaMemcpyDeviceToHost, c->stream));
+    LILI_CUDA(c, cudaStreamSynchronize(c->stream));
+    return LILIOM_OK;
+}
+
+extern "C" int liliom_correspond_surf(liliom_ctx* c, const void* feats, int n, int stride, const double pose7[7], double kd_max_radius,
+                                      double surf_dist_thres, double w_gate, double lidar_const, unsigned char* valid, float* plane,
+                                      double* score) {
+    if (!c || !pose7 || !valid || !plane || !score) return LILIOM_E_ARG;
+    LILI_CUDA(c, cudaSetDevice(c->device));
+    {   // the grid's cell size bounds the exact search radius
+        float cell = 1.0f / c->grid.inv_cell;
+        if (c->map_ready && c->map_n > 0 && kd_max_radius > (double)cell * (double)cell) {
+            c->last_error = "kd_max_radius exceeds the cell size the map grid was built with (raise params.knn_max_sqdist)";
+            return LILIOM_E_ARG;
+        }
+    }
+    LILI_TRY(backend_prepare(c, feats, n, stride));
+    if (n == 0) return LILIOM_OK;
+    LILI_CUDA(c, c->corr_valid.ensure((size_t)n + 16));
+    LILI_CUDA(c, c->corr_plane.ensure((size_t)n * 16 + 16));
+    LILI_CUDA(c, c->nn_sqd.ensure((size_t)n * 8 + 16));
+    BkArgs a{};
+    a.feats = c->feats.as<float4>(); a.n = n; a.map = c->map_sorted.as<float4>(); a.cell_start = c->cell_start.as<int>(); a.g = c->grid;
+    a.q = Q4{pose7[0], pose7[1], pose7[2], pose7[3]}; a.t = D3{pose7[4], pose7[5], pose7[6]};
+    a.max_sqd = kd_max_radius; a.plane_thres = surf_dist_thres; a.w_gate = w_gate; a.lidar_const = lidar_const;
+    a.valid = c->corr_valid.as<unsigned char>(); a.plane = c->corr_plane.as<float4>(); a.score = c->nn_sqd.as<double>();
+    k_backend_surf<<<cdiv((long long)n * kLanes, kBlock), kBlock, 0, c->stream>>>(a);
+    LILI_TRY(launch_check(c, "k_backend_surf"));
+    LILI_CUDA(c, cudaMemcpyAsync(valid, a.valid, (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    LILI_CUDA(c, cudaMemcpyAsync(plane, a.plane, (size_t)n * 16, cudaMemcpyDeviceToHost, c->stream));
+    LILI_CUDA(c, cudaMemcpyAsync(score, a.score, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
+    LILI_CUDA(c, cudaStreamSynchronize(c->stream));
+    return LILIOM_OK;
+}

@@ -1,0 +1,86 @@
+// Multi-GPU plumbing: NCCL is resolved at run time with dlopen so that single-GPU users need no
+// NCCL at all, and so that inside a PyTorch process the already-loaded libnccl.so.2 is reused.
+// The only collective on the path is the per-iteration all-reduce of the 29 fp64 scalars
+// (21 J^T J + 6 J^T r + cost + count): 232 bytes, latency-bound over NVLink 5 / NVSwitch.
+#include "ctx.cuh"
+#include <dlfcn.h>
+
+namespace lili {
+
+struct Id128 { char b[128]; };   // ncclUniqueId (passed by value)
+
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(void*) = nullptr;
+    int (*CommInitRank)(void**, int, Id128, int) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+
+static NcclApi g_nccl;
+
+static bool load_nccl(std::string* err) {
+    if (g_nccl.lib) return true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+        g_nccl.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (g_nccl.lib) break;
+    }
+    if (!g_nccl.lib) { if (err) *err = std::string("dlopen libnccl.so.2 failed: ") + dlerror(); return false; }
+    g_nccl.GetUniqueId = (int (*)(void*))dlsym(g_nccl.lib, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (int (*)(void**, int, Id128, int))dlsym(g_nccl.lib, "ncclCommInitRank");
+    g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(g_nccl.lib, "ncclAllReduce");
+    g_nccl.CommDestroy = (int (*)(void*))dlsym(g_nccl.lib, "ncclCommDestroy");
+    g_nccl.GetErrorString = (const char* (*)(int))dlsym(g_nccl.lib, "ncclGetErrorString");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce) {
+        if (err) *err = "libnccl is missing ncclGetUniqueId/ncclCommInitRank/ncclAllReduce";
+        return false;
+    }
+    return true;
+}
+
+int nccl_allreduce_sum_f64(liliom_ctx* c, double* buf, int count) {
+    if (!c->nccl_comm) return LILIOM_E_NCCL;
+    // ncclFloat64 = 8, ncclSum = 0
+    int r = g_nccl.AllReduce(buf, buf, (size_t)count, 8, 0, c->nccl_comm, c->stream);
+    if (r != 0) {
+        c->last_error = std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error");
+        return LILIOM_E_NCCL;
+    }
+    c->cnt.lib_launches++;
+    return LILIOM_OK;
+}
+
+void nccl_destroy(liliom_ctx* c) {
+    if (c->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->nccl_comm);
+    c->nccl_comm = nullptr;
+}
+
+}  // namespace lili
+
+extern "C" int liliom_comm_get_unique_id(void* id128) {
+    if (!id128) return LILIOM_E_ARG;
+    std::string err;
+    if (!lili::load_nccl(&err)) return LILIOM_E_NCCL;
+    return lili::g_nccl.GetUniqueId(id128) == 0 ? LILIOM_OK : LILIOM_E_NCCL;
+}
+
+extern "C" int liliom_comm_init(liliom_ctx* c, const void* id128, int nranks, int rank) {
+    if (!c || !id128 || nranks < 1 || rank < 0 || rank >= nranks) return LILIOM_E_ARG;
+    std::string err;
+    if (!lili::load_nccl(&err)) { c->last_error = err; return LILIOM_E_NCCL; }
+    LILI_CUDA(c, cudaSetDevice(c->device));
+    lili::Id128 id;
+    memcpy(id.b, id128, 128);
+    void* comm = nullptr;
+    int r = lili::g_nccl.CommInitRank(&comm, nranks, id, rank);
+    if (r != 0) {
+        c->last_error = std::string("ncclCommInitRank: ") + (lili::g_nccl.GetErrorString ? lili::g_nccl.GetErrorString(r) : "error");
+        return LILIOM_E_NCCL;
+    }
+    c->nccl_comm = comm;
+    c->nranks = nranks;
+    c->rank = rank;
+    return LILIOM_OK;
+}

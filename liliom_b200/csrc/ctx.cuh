@@ -1,0 +1,169 @@
+// Internal context of libliliom_b200.so (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "../../include/liliom.h"
+
+namespace lili {
+
+// One growable device allocation.  Buffers only grow; 180 GB of HBM3e per GPU makes
+// reallocation-on-demand a cold path (first scan), never a steady-state cost.
+struct DevBuf {
+    void*  p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+// Parameters of one VoxelGrid pass, produced on the device (no host round trip).
+struct VgParams {
+    float inv_leaf;
+    int   min_b[3];
+    int   div_b[3];
+    int   mul[3];
+    int   overflow;    // PCL: "Leaf size is too small" -> output = input
+    int   n_finite;
+};
+
+// Dense cell grid over the down-sampled map (the kd-tree's stand-in).
+struct GridDesc {
+    float inv_cell;        // 1 / cell size (power of two => exact)
+    int   org[3];          // cell coordinate of grid cell (0,0,0)
+    int   dim[3];
+    int   ncells;
+};
+
+constexpr int kStatsDoubles = 40;   // per outer iteration on the device: n_corr, lm_iters, cost, 27, pose7, pad
+constexpr int kNormEq = 29;         // 21 + 6 + cost + count
+
+struct Frame {        // one entry of recent_surf_frames (world frame, point_stride bytes per point)
+    DevBuf buf;
+    int n = 0;
+};
+
+}  // namespace lili
+
+struct liliom_ctx {
+    liliom_params prm;
+    int device = 0;
+    cudaStream_t stream = nullptr;       // stream all work is issued on (own_stream unless liliom_set_stream)
+    cudaStream_t own_stream = nullptr;
+    std::string last_error;
+    int sm_count = 148;
+
+    // ---- staging (pinned host) ----
+    void*  h_pin = nullptr;      // small pinned block: counts, pose, stats
+    size_t h_pin_bytes = 0;
+
+    // ---- extraction ----
+    lili::DevBuf raw, cut, surf, edge, flags, scan_tmp, idx_a, idx_b;
+    lili::DevBuf hz_mat, hz_stage_surf, hz_stage_edge, hz_counts;
+    lili::DevBuf rot_keys, rot_keys2, rot_vals, rot_vals2, rot_cloud, rot_curv, rot_label, rot_picked, rot_sort, rot_ring, rot_meta, rot_lessflat, rot_seg_edge;
+    int n_surf_dev = 0;          // surf features resident after the last extract call
+    lili::DevBuf raw_scan;       // resident raw sweep (liliom_upload_scan)
+    int n_raw_scan = 0;
+    int n_rot_cloud = 0;
+
+    // ---- voxel grid scratch ----
+    lili::DevBuf vg_keys, vg_keys2, vg_vals, vg_vals2, vg_flags, vg_rank, vg_params, vg_out, vg_minmax, vg_count;
+    lili::DevBuf cub_tmp;
+
+    // ---- map ----
+    std::vector<lili::Frame> frames;     // FIFO, oldest first
+    lili::DevBuf map_raw;                // concatenated frames (stride bytes)
+    lili::DevBuf map_ds;                 // VoxelGrid output (stride bytes) or installed float4
+    lili::DevBuf map_xyzw;               // float4 in map_download order (w = index)
+    lili::DevBuf map_sorted;             // float4 sorted by cell, w = original index bits
+    lili::DevBuf cell_start;             // ncells + 1
+    lili::DevBuf grid_keys, grid_keys2, grid_vals, grid_vals2;
+    lili::GridDesc grid{};
+    int map_n = 0;                       // points resident on this rank (sorted grid)
+    int map_n_global = 0;
+    bool map_ready = false;
+
+    // ---- scan-to-map ----
+    lili::DevBuf feats;                  // float4 body-frame queries
+    int n_feats = 0;
+    lili::DevBuf corr_valid, corr_plane, nn_idx, nn_sqd;
+    lili::DevBuf pose_dev;               // 7 doubles (current) + 7 (candidate)
+    lili::DevBuf partials;               // grid x 29 doubles
+    lili::DevBuf neq;                    // 29 doubles (reduced)
+    lili::DevBuf stats_dev;              // iterations x kStatsDoubles
+    lili::DevBuf counter;                // last-block ticket + scratch ints
+    lili::DevBuf lm_state;
+
+    // ---- multi-GPU ----
+    void* nccl_comm = nullptr;
+    int nranks = 1, rank = 0;
+
+    // ---- instrumentation ----
+    liliom_counters cnt{};
+    bool time_kernels = false;
+    std::vector<cudaEvent_t> ev_pool;
+    size_t ev_used = 0;
+    std::vector<std::pair<size_t, unsigned long long>> ev_pending;  // (event pair index, queries)
+};
+
+namespace lili {
+
+inline int fail_cuda(liliom_ctx* c, cudaError_t e, const char* where) {
+    char buf[256];
+    snprintf(buf, sizeof(buf), "%s: %s", where, cudaGetErrorString(e));
+    if (c) c->last_error = buf;
+    return LILIOM_E_CUDA;
+}
+
+#define LILI_CUDA(c, expr)                                                      \
+    do {                                                                        \
+        cudaError_t _e = (expr);                                                \
+        if (_e != cudaSuccess) return lili::fail_cuda((c), _e, #expr);          \
+    } while (0)
+
+#define LILI_TRY(expr)                    \
+    do {                                  \
+        int _r = (expr);                  \
+        if (_r != LILIOM_OK) return _r;   \
+    } while (0)
+
+inline int launch_check(liliom_ctx* c, const char* name) {
+    cudaError_t e = cudaGetLastError();
+    c->cnt.launches++;
+    if (e != cudaSuccess) return fail_cuda(c, e, name);
+    return LILIOM_OK;
+}
+
+inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ---- modules (implemented in the .cu files) ----
+int sort_pairs_u32(liliom_ctx* c, const uint32_t* kin, uint32_t* kout, const int* vin, int* vout, int n, int end_bit);
+int sort_pairs_u64(liliom_ctx* c, const unsigned long long* kin, unsigned long long* kout, const int* vin, int* vout, int n, int end_bit);
+int exclusive_scan_i32(liliom_ctx* c, const int* in, int* out, int n);   // out has n+1 entries (total at out[n])
+
+// VoxelGrid on device buffers; d_count receives the output count (int, device).
+int voxelgrid_dev(liliom_ctx* c, const void* d_in, int n, int stride, float leaf, void* d_out, int* d_count);
+
+// grid build from float4 points already on the device (map_xyzw[0..m)).
+int grid_build(liliom_ctx* c, int m);
+
+int s2m_run(liliom_ctx* c, double pose7[7], int match_cnt, int max_num_iter, int mode, liliom_iter_stats* stats,
+            bool want_corr, double out29[29]);
+
+int horizon_extract_dev(liliom_ctx* c, int n, const double q_imu[4], int* n_surf, int* n_edge, int* n_cut);
+int rot_extract_dev(liliom_ctx* c, int n, const double q_imu[4], const double q_lb[4], int* n_surf, int* n_edge, int* n_cut);
+
+int repack_to_f4(liliom_ctx* c, const void* d_in, int n, int stride, float4* d_out);
+
+}  // namespace lili

@@ -1,0 +1,377 @@
+// Device scalar routines of the LiLi-OM hot path (sm_100a).
+// The *_x ("exact") helpers spell every operation with round-to-nearest intrinsics so that
+// nvcc never contracts them into FMAs: they reproduce bit-for-bit what the reference's
+// generic x86-64 build computes (no FMA), which is what makes the
+// label / index outputs bit-exact.  Routines without _x may be contracted; they only feed
+// tolerance-checked fp64 results.
+#pragma once
+#include <cuda_runtime.h>
+#include <cfloat>
+
+namespace lili {
+
+struct D3 { double x, y, z; };
+struct Q4 { double w, x, y, z; };
+
+__device__ __forceinline__ double mulx(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double addx(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double subx(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ float fmulx(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float faddx(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float fsubx(float a, float b) { return __fsub_rn(a, b); }
+
+__device__ __forceinline__ D3 cross_x(D3 a, D3 b) {
+    return {subx(mulx(a.y, b.z), mulx(a.z, b.y)), subx(mulx(a.z, b.x), mulx(a.x, b.z)), subx(mulx(a.x, b.y), mulx(a.y, b.x))};
+}
+
+// Eigen::Quaterniond * Vector3d (QuaternionBase::_transformVector), not normalising:
+//   uv = q.vec x v; uv += uv; v + w*uv + q.vec x uv
+// reference call sites: L/src/LidarOdometry.cpp:231, L/src/Preprocessing.cpp:118.
+__device__ __forceinline__ D3 qrot_x(Q4 q, D3 v) {
+    D3 qv{q.x, q.y, q.z};
+    D3 uv = cross_x(qv, v);
+    uv = {addx(uv.x, uv.x), addx(uv.y, uv.y), addx(uv.z, uv.z)};
+    D3 c = cross_x(qv, uv);
+    return {addx(addx(v.x, mulx(q.w, uv.x)), c.x), addx(addx(v.y, mulx(q.w, uv.y)), c.y), addx(addx(v.z, mulx(q.w, uv.z)), c.z)};
+}
+
+// Hamilton product, Eigen operand order (a * b), exact ops.
+__device__ __forceinline__ Q4 qmul_x(Q4 a, Q4 b) {
+    Q4 r;
+    r.w = subx(subx(subx(mulx(a.w, b.w), mulx(a.x, b.x)), mulx(a.y, b.y)), mulx(a.z, b.z));
+    r.x = subx(addx(addx(mulx(a.w, b.x), mulx(a.x, b.w)), mulx(a.y, b.z)), mulx(a.z, b.y));
+    r.y = subx(addx(addx(mulx(a.w, b.y), mulx(a.y, b.w)), mulx(a.z, b.x)), mulx(a.x, b.z));
+    r.z = subx(addx(addx(mulx(a.w, b.z), mulx(a.z, b.w)), mulx(a.x, b.y)), mulx(a.y, b.x));
+    return r;
+}
+
+// Eigen::Quaterniond::inverse()
+__device__ __forceinline__ Q4 qinv_x(Q4 q) {
+    double n2 = addx(addx(addx(mulx(q.w, q.w), mulx(q.x, q.x)), mulx(q.y, q.y)), mulx(q.z, q.z));
+    if (n2 > 0) return {q.w / n2, -q.x / n2, -q.y / n2, -q.z / n2};
+    return {0, 0, 0, 0};
+}
+
+// Eigen::Quaterniond::slerp(t, other) from `a`, result not re-normalised
+// (L/src/Preprocessing.cpp:114-115).  acos/sin are CUDA's fp64 routines (<= 1-2 ulp from
+// glibc's); their results are narrowed to fp32 point coordinates downstream.
+__device__ __forceinline__ Q4 qslerp_x(Q4 a, double t, Q4 b) {
+    const double one = 1.0 - DBL_EPSILON;
+    double d = addx(addx(addx(mulx(a.w, b.w), mulx(a.x, b.x)), mulx(a.y, b.y)), mulx(a.z, b.z));
+    double absD = fabs(d);
+    double s0, s1;
+    if (absD >= one) {
+        s0 = subx(1.0, t);
+        s1 = t;
+    } else {
+        double theta = acos(absD);
+        double sinTheta = sin(theta);
+        s0 = sin(mulx(subx(1.0, t), theta)) / sinTheta;
+        s1 = sin(mulx(t, theta)) / sinTheta;
+    }
+    if (d < 0) s1 = -s1;
+    return {addx(mulx(s0, a.w), mulx(s1, b.w)), addx(mulx(s0, a.x), mulx(s1, b.x)),
+            addx(mulx(s0, a.y), mulx(s1, b.y)), addx(mulx(s0, a.z), mulx(s1, b.z))};
+}
+
+// ---------------------------------------------------------------------------------------
+// 3x3 symmetric eigen-decomposition following the algorithm of
+// Eigen::SelfAdjointEigenSolver<Matrix3d> (iterative path): max-abs scaling, closed-form 3x3
+// Householder tridiagonalisation, implicit symmetric QR with Wilkinson shift, ascending order.
+// Following the same algorithm (rather than an analytic solver) keeps eigenvector SIGNS equal
+// to the reference's, which end up in the published normal_x/y/z fields
+// (L/src/Preprocessing.cpp:354-360, 368-376).  Compile the including TU with --fmad=false
+// when bit-stable labels are required.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void givens_rot(double p, double q, double& c, double& s) {
+    if (q == 0.0) {
+        c = p < 0 ? -1.0 : 1.0; s = 0.0;
+    } else if (p == 0.0) {
+        c = 0.0; s = q < 0 ? 1.0 : -1.0;
+    } else if (fabs(p) > fabs(q)) {
+        double t = q / p;
+        double u = sqrt(1.0 + t * t);
+        if (p < 0) u = -u;
+        c = 1.0 / u; s = -t * c;
+    } else {
+        double t = p / q;
+        double u = sqrt(1.0 + t * t);
+        if (q < 0) u = -u;
+        s = -1.0 / u; c = -t * s;
+    }
+}
+
+__device__ __forceinline__ double hypot_pos(double x, double y) {
+    double ax = fabs(x), ay = fabs(y);
+    double p = ax > ay ? ax : ay;
+    if (p == 0.0) return 0.0;
+    double qp = (ax > ay ? ay : ax) / p;
+    return p * sqrt(1.0 + qp * qp);
+}
+
+// a: symmetric, lower triangle read (a00,a10,a20,a11,a21,a22). evec[r][c] = component r of eigenvector c.
+__device__ inline void eigen_sym3(double a00, double a10, double a20, double a11, double a21, double a22,
+                                  double eval[3], double evec[3][3]) {
+    double scale = fmax(fmax(fmax(fabs(a00), fabs(a10)), fmax(fabs(a20), fabs(a11))), fmax(fabs(a21), fabs(a22)));
+    if (scale == 0.0) scale = 1.0;
+    a00 /= scale; a10 /= scale; a20 /= scale; a11 /= scale; a21 /= scale; a22 /= scale;
+    double diag[3], sub[2];
+    double Q[3][3];
+    diag[0] = a00;
+    double v1norm2 = a20 * a20;
+    if (v1norm2 <= DBL_MIN) {
+        diag[1] = a11; diag[2] = a22; sub[0] = a10; sub[1] = a21;
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) Q[i][j] = (i == j) ? 1.0 : 0.0;
+    } else {
+        double beta = sqrt(a10 * a10 + v1norm2);
+        double invBeta = 1.0 / beta;
+        double m01 = a10 * invBeta;
+        double m02 = a20 * invBeta;
+        double q = 2.0 * m01 * a21 + m02 * (a22 - a11);
+        diag[1] = a11 + m02 * q;
+        diag[2] = a22 - m02 * q;
+        sub[0] = beta;
+        sub[1] = a21 - m01 * q;
+        Q[0][0] = 1; Q[0][1] = 0;   Q[0][2] = 0;
+        Q[1][0] = 0; Q[1][1] = m01; Q[1][2] = m02;
+        Q[2][0] = 0; Q[2][1] = m02; Q[2][2] = -m01;
+    }
+    int end = 2, start = 0, iter = 0;
+    const double precision_inv = 1.0 / DBL_EPSILON;
+    while (end > 0) {
+        for (int i = start; i < end; ++i) {
+            if (fabs(sub[i]) < DBL_MIN) {
+                sub[i] = 0.0;
+            } else {
+                double ss = precision_inv * sub[i];
+                if (ss * ss <= (fabs(diag[i]) + fabs(diag[i + 1]))) sub[i] = 0.0;
+            }
+        }
+        while (end > 0 && sub[end - 1] == 0.0) end--;
+        if (end <= 0) break;
+        iter++;
+        if (iter > 90) break;
+        start = end - 1;
+        while (start > 0 && sub[start - 1] != 0.0) start--;
+        double td = (diag[end - 1] - diag[end]) * 0.5;
+        double e = sub[end - 1];
+        double mu = diag[end];
+        if (td == 0.0) {
+            mu -= fabs(e);
+        } else if (e != 0.0) {
+            double e2 = e * e;
+            double h = hypot_pos(td, e);
+            if (e2 == 0.0) mu -= e / ((td + (td > 0 ? h : -h)) / e);
+            else mu -= e2 / (td + (td > 0 ? h : -h));
+        }
+        double x = diag[start] - mu;
+        double z = sub[start];
+        for (int k = start; k < end && z != 0.0; ++k) {
+            double c, s;
+            givens_rot(x, z, c, s);
+            double sdk = s * diag[k] + c * sub[k];
+            double dkp1 = s * sub[k] + c * diag[k + 1];
+            diag[k] = c * (c * diag[k] - s * sub[k]) - s * (c * sub[k] - s * diag[k + 1]);
+            diag[k + 1] = s * sdk + c * dkp1;
+            sub[k] = c * sdk - s * dkp1;
+            if (k > start) sub[k - 1] = c * sub[k - 1] - s * z;
+            x = sub[k];
+            if (k < end - 1) {
+                z = -s * sub[k + 1];
+                sub[k + 1] = c * sub[k + 1];
+            }
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                double qk = Q[r][k], qk1 = Q[r][k + 1];
+                Q[r][k] = c * qk - s * qk1;
+                Q[r][k + 1] = s * qk + c * qk1;
+            }
+        }
+    }
+    for (int i = 0; i < 2; ++i) {
+        int k = i;
+        for (int j = i + 1; j < 3; ++j) if (diag[j] < diag[k]) k = j;
+        if (k != i) {
+            double t = diag[i]; diag[i] = diag[k]; diag[k] = t;
+            for (int r = 0; r < 3; ++r) { double u = Q[r][i]; Q[r][i] = Q[r][k]; Q[r][k] = u; }
+        }
+    }
+    for (int i = 0; i < 3; ++i) {
+        eval[i] = diag[i] * scale;
+        for (int r = 0; r < 3; ++r) evec[r][i] = Q[r][i];
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// 5x3 least squares  A n = b  by column-pivoted Householder QR in fp64 (the algorithm of
+// Eigen::ColPivHouseholderQR, L/src/LidarOdometry.cpp:375): map points sit hundreds of metres
+// from the origin with sub-metre spread, so normal equations (condition squared) would cost
+// ~1e-4 m in the plane offset — QR keeps it at ~1e-9 m.
+// Everything is register-resident (fully unrolled, column permutation via swaps).
+// ---------------------------------------------------------------------------------------
+__device__ inline void colpiv_qr_solve_5x3(double A[5][3], double b[5], double x[3]) {
+    double nu[3], ndir[3], tau[3];
+    int perm[3] = {0, 1, 2};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        double s = 0;
+#pragma unroll
+        for (int i = 0; i < 5; ++i) s += A[i][k] * A[i][k];
+        nu[k] = ndir[k] = sqrt(s);
+    }
+    double maxn = fmax(nu[0], fmax(nu[1], nu[2]));
+    double th = maxn * DBL_EPSILON;
+    const double threshold_helper = th * th / 5.0;
+    const double downdate_thr = 1.4901161193847656e-08;   // sqrt(DBL_EPSILON)
+    int nonzero = 3;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        int big = k;
+        double bigv = nu[k];
+#pragma unroll
+        for (int j = k + 1; j < 3; ++j) if (nu[j] > bigv) { bigv = nu[j]; big = j; }
+        double big_sq = bigv * bigv;
+        if (nonzero == 3 && big_sq < threshold_helper * double(5 - k)) nonzero = k;
+        if (big != k) {
+#pragma unroll
+            for (int j = k + 1; j < 3; ++j) {
+                if (j == big) {
+#pragma unroll
+                    for (int i = 0; i < 5; ++i) { double t = A[i][k]; A[i][k] = A[i][j]; A[i][j] = t; }
+                    double t = nu[k]; nu[k] = nu[j]; nu[j] = t;
+                    t = ndir[k]; ndir[k] = ndir[j]; ndir[j] = t;
+                    int p = perm[k]; perm[k] = perm[j]; perm[j] = p;
+                }
+            }
+        }
+        double tail = 0;
+#pragma unroll
+        for (int i = k + 1; i < 5; ++i) tail += A[i][k] * A[i][k];
+        double c0 = A[k][k], beta, tk;
+        if (tail <= DBL_MIN) {
+            tk = 0; beta = c0;
+#pragma unroll
+            for (int i = k + 1; i < 5; ++i) A[i][k] = 0;
+        } else {
+            beta = sqrt(c0 * c0 + tail);
+            if (c0 >= 0) beta = -beta;
+            double inv = c0 - beta;
+#pragma unroll
+            for (int i = k + 1; i < 5; ++i) A[i][k] = A[i][k] / inv;
+            tk = (beta - c0) / beta;
+        }
+        A[k][k] = beta;
+        tau[k] = tk;
+        if (tk != 0) {
+#pragma unroll
+            for (int j = k + 1; j < 3; ++j) {
+                double tmp = A[k][j];
+#pragma unroll
+                for (int i = k + 1; i < 5; ++i) tmp += A[i][k] * A[i][j];
+                A[k][j] -= tk * tmp;
+#pragma unroll
+                for (int i = k + 1; i < 5; ++i) A[i][j] -= tk * A[i][k] * tmp;
+            }
+        }
+#pragma unroll
+        for (int j = k + 1; j < 3; ++j) {
+            if (nu[j] != 0) {
+                double temp = fabs(A[k][j]) / nu[j];
+                temp = (1.0 + temp) * (1.0 - temp);
+                temp = temp < 0 ? 0 : temp;
+                double r = nu[j] / ndir[j];
+                double temp2 = temp * r * r;
+                if (temp2 <= downdate_thr) {
+                    double s = 0;
+#pragma unroll
+                    for (int i = k + 1; i < 5; ++i) s += A[i][j] * A[i][j];
+                    ndir[j] = sqrt(s);
+                    nu[j] = ndir[j];
+                } else {
+                    nu[j] *= sqrt(temp);
+                }
+            }
+        }
+    }
+    x[0] = x[1] = x[2] = 0;
+    if (nonzero == 0) return;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        if (k < nonzero && tau[k] != 0) {
+            double tmp = b[k];
+#pragma unroll
+            for (int i = k + 1; i < 5; ++i) tmp += A[i][k] * b[i];
+            b[k] -= tau[k] * tmp;
+#pragma unroll
+            for (int i = k + 1; i < 5; ++i) b[i] -= tau[k] * A[i][k] * tmp;
+        }
+    }
+    double c[3] = {b[0], b[1], b[2]};
+#pragma unroll
+    for (int i = 2; i >= 0; --i) {
+        if (i < nonzero) {
+            double s = c[i];
+#pragma unroll
+            for (int j = i + 1; j < 3; ++j) if (j < nonzero) s -= A[i][j] * c[j];
+            c[i] = s / A[i][i];
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        if (i < nonzero) {
+            // scatter through the permutation without dynamic register indexing
+            if (perm[i] == 0) x[0] = c[i];
+            else if (perm[i] == 1) x[1] = c[i];
+            else x[2] = c[i];
+        }
+    }
+}
+
+// 6x6 SPD solve (LDL^T), H given as the 21-scalar upper triangle (row-major), rhs b. Returns false on a non-finite / zero pivot.
+__device__ inline bool solve6_ldlt(const double* s21, const double* rhs, double x[6]) {
+    double H[6][6];
+    int k = 0;
+    for (int a = 0; a < 6; ++a) for (int b = a; b < 6; ++b) { H[a][b] = s21[k]; H[b][a] = s21[k]; ++k; }
+    double L[6][6], D[6];
+    for (int j = 0; j < 6; ++j) {
+        double d = H[j][j];
+        for (int m = 0; m < j; ++m) d -= L[j][m] * L[j][m] * D[m];
+        if (!(fabs(d) > 1e-300) || !isfinite(d)) return false;
+        D[j] = d;
+        L[j][j] = 1;
+        for (int i = j + 1; i < 6; ++i) {
+            double s = H[i][j];
+            for (int m = 0; m < j; ++m) s -= L[i][m] * L[j][m] * D[m];
+            L[i][j] = s / d;
+        }
+    }
+    double y[6];
+    for (int i = 0; i < 6; ++i) { double s = rhs[i]; for (int m = 0; m < i; ++m) s -= L[i][m] * y[m]; y[i] = s; }
+    for (int i = 0; i < 6; ++i) y[i] /= D[i];
+    for (int i = 5; i >= 0; --i) { double s = y[i]; for (int m = i + 1; m < 6; ++m) s -= L[m][i] * x[m]; x[i] = s; }
+    for (int i = 0; i < 6; ++i) if (!isfinite(x[i])) return false;
+    return true;
+}
+
+// ceres::QuaternionParameterization::Plus on q, identity on t.
+__device__ inline void pose_plus(const double x[7], const double d[6], double out[7]) {
+    double nd = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+    if (nd > 0.0) {
+        double sn, cs;
+        sincos(nd, &sn, &cs);
+        double sbd = sn / nd;
+        double dw = cs, dx = sbd * d[0], dy = sbd * d[1], dz = sbd * d[2];
+        out[0] = dw * x[0] - dx * x[1] - dy * x[2] - dz * x[3];
+        out[1] = dw * x[1] + dx * x[0] + dy * x[3] - dz * x[2];
+        out[2] = dw * x[2] + dy * x[0] + dz * x[1] - dx * x[3];
+        out[3] = dw * x[3] + dz * x[0] + dx * x[2] - dy * x[1];
+    } else {
+        out[0] = x[0]; out[1] = x[1]; out[2] = x[2]; out[3] = x[3];
+    }
+    out[4] = x[4] + d[3]; out[5] = x[5] + d[4]; out[6] = x[6] + d[5];
+}
+
+}  // namespace lili

@@ -1,0 +1,492 @@
+// Spinning-LiDAR (LOAM-style) feature extraction on sm_100a — replaces the loops of
+// Preprocessing::cloudHandler, R/src/Preprocessing.cpp:280-509.
+//
+//   k_rot_pre      removeNaN + removeClosedPointCloud 3.0 m (:280-281), elevation -> scanID
+//                  (:315-347), raw azimuth -atan2f(y,x) (:349); first/last surviving index
+//   k_rot_hp       the sequential `halfPassed` latch (:350-358) as a prefix-min: the first valid
+//                  index whose (un-latched) azimuth passes startOri + pi
+//   (stable sort)  bucket by ring preserving arrival order == laserCloudScans[scanID] (:371,378-382)
+//   k_rot_build    azimuth wrap (:350-365), relTime (:367), intensity (:368), de-skew with
+//                  q_lb*slerp*q_lb^-1 (:153-177) -> laserCloud; ring start/end
+//   k_rot_curv     11-point curvature in the literal left-to-right fp32 order (:385-394)
+//   k_rot_ring     one CTA per ring: its 6 segments in order (the picked[] marks of segment j
+//                  are visible to segment j+1, :401-500): shared-memory bitonic sort by
+//                  (curvature, index), then lane 0 walks the sorted list — <=2 sharp, <=10
+//                  less-sharp, +-5 neighbour suppression, <=4 flat, less-flat flags
+//   k_rot_lf_*     per-ring pcl::VoxelGrid(0.6) of the less-flat points (:502-508), all rings
+//                  in one batch with 64-bit (ring, voxel) keys
+//   k_rot_edge_emit  ordered compaction of the <=10 edge picks per segment (:517-521)
+// atan/atan2 use lili::det_atanf/det_atan2f (bit-identical to glibc 2.39, see detmath.h).
+// Compiled with --fmad=false so every fp32 expression rounds like the reference's x86-64 build.
+#include "ctx.cuh"
+#include "dev_math.cuh"
+#include "detmath.h"
+#include <climits>
+
+namespace lili {
+
+struct Pt32 { float4 a, b; };   // {x,y,z,1} {intensity,0,0,0}
+
+constexpr int ROT_MAX_RINGS = 64;
+constexpr int ROT_SEG_CAP = 4096;          // max points per segment (ring <= ~24k points)
+constexpr int ROT_RING_CAP = 16384;        // picked[] bytes per ring in shared memory
+constexpr double ROT_PI = 3.14159265358979323846;   // M_PI
+
+// meta layout (ints): [0] first idx, [1] last idx, [2] halfPassed idx, [3] n_valid (cloudSize),
+// [4] error flag, [5] n_lessflat, [6] n_edge, [8..8+64) ring_first, [72..72+64) ring_end
+constexpr int M_FIRST = 0, M_LAST = 1, M_HP = 2, M_NVALID = 3, M_ERR = 4, M_NLF = 5, M_NEDGE = 6, M_RF = 8, M_RE = 72, M_SIZE = 144;
+
+__global__ void k_rot_meta_init(int* meta) {
+    int t = threadIdx.x;
+    if (t < M_SIZE) meta[t] = 0;
+    if (t == M_FIRST) meta[t] = INT_MAX;
+    if (t == M_LAST) meta[t] = -1;
+    if (t == M_HP) meta[t] = INT_MAX;
+}
+
+__device__ __forceinline__ bool rot_keep(float4 a) {
+    const float thres = 3.0f;
+    if (!(isfinite(a.x) && isfinite(a.y) && isfinite(a.z))) return false;
+    return !(a.x * a.x + a.y * a.y + a.z * a.z < thres * thres);
+}
+
+__global__ void k_rot_pre(const Pt32* __restrict__ pts, int n, int n_scans, uint32_t* __restrict__ keys, int* __restrict__ vals,
+                          float* __restrict__ ori, int* __restrict__ meta) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 a = pts[i].a;
+    uint32_t key = 255u;
+    float o = 0.f;
+    if (rot_keep(a)) {
+        atomicMin(&meta[M_FIRST], i);
+        atomicMax(&meta[M_LAST], i);
+        float angle = (float)((double)(det_atanf(a.z / sqrtf(a.x * a.x + a.y * a.y)) * 180.0f) / ROT_PI);    // :315
+        int scanID = 0;
+        bool ok = true;
+        if (n_scans == 16) {
+            scanID = (int)((double)((angle + 15.0f) / 2.0f) + 0.5);
+            if (scanID > (n_scans - 1) || scanID < 0) ok = false;
+        } else if (n_scans == 32) {
+            scanID = (int)(((double)angle + 92.0 / 3.0) * 3.0 / 4.0);
+            if (scanID > (n_scans - 1) || scanID < 0) ok = false;
+        } else {
+            if ((double)angle >= -8.83) scanID = (int)((double)(2.0f - angle) * 3.0 + 0.5);
+            else scanID = n_scans / 2 + (int)((-8.83 - (double)angle) * 2.0 + 0.5);
+            if (angle > 2.0f || (double)angle < -24.33 || scanID > 50 || scanID < 0) ok = false;
+        }
+        o = -det_atan2f(a.y, a.x);                                                                          // :349
+        if (ok) key = (uint32_t)scanID;
+    }
+    keys[i] = key;
+    vals[i] = i;
+    ori[i] = o;
+}
+
+__device__ __forceinline__ void rot_start_end(const Pt32* __restrict__ pts, const int* __restrict__ meta, float& startOri, float& endOri) {
+    float4 f = pts[meta[M_FIRST]].a, l = pts[meta[M_LAST]].a;
+    startOri = -det_atan2f(f.y, f.x);                                                                       // :285
+    endOri = (float)((double)(-det_atan2f(l.y, l.x)) + 2 * ROT_PI);                                         // :286-288
+    if ((double)(endOri - startOri) > 3 * ROT_PI) endOri = (float)((double)endOri - 2 * ROT_PI);            // :290-294
+    else if ((double)(endOri - startOri) < ROT_PI) endOri = (float)((double)endOri + 2 * ROT_PI);
+}
+
+// un-latched branch of :350-358 for every valid point; the latch fires at the smallest such index
+__global__ void k_rot_hp(const Pt32* __restrict__ pts, int n, const uint32_t* __restrict__ keys, const float* __restrict__ ori_raw,
+                         int* __restrict__ meta) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || keys[i] == 255u) return;
+    if (meta[M_FIRST] == INT_MAX) return;
+    float startOri, endOri;
+    rot_start_end(pts, meta, startOri, endOri);
+    float ori = ori_raw[i];
+    if ((double)ori < (double)startOri - ROT_PI / 2) ori = (float)((double)ori + 2 * ROT_PI);
+    else if ((double)ori > (double)startOri + ROT_PI * 3 / 2) ori = (float)((double)ori - 2 * ROT_PI);
+    if ((double)(ori - startOri) > ROT_PI) atomicMin(&meta[M_HP], i);
+}
+
+__global__ void k_rot_build(const Pt32* __restrict__ pts, int n, const uint32_t* __restrict__ skeys, const int* __restrict__ svals,
+                            const float* __restrict__ ori_raw, Q4 qIMU, Q4 q_lb, Pt32* __restrict__ cloud, int* __restrict__ meta) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const uint32_t key = skeys[s];
+    const uint32_t prev = s > 0 ? skeys[s - 1] : 0xffffffffu;
+    if (key != prev) {
+        if (s > 0 && prev != 255u) meta[M_RE + prev] = s;
+        if (key != 255u) meta[M_RF + key] = s;
+        if (key == 255u) meta[M_NVALID] = s;
+    }
+    if (s == n - 1 && key != 255u) { meta[M_RE + key] = n; meta[M_NVALID] = n; }
+    if (key == 255u) return;
+    const int i = svals[s];
+    float startOri, endOri;
+    rot_start_end(pts, meta, startOri, endOri);
+    float ori = ori_raw[i];
+    if (i <= meta[M_HP]) {                                                                                  // :350-358
+        if ((double)ori < (double)startOri - ROT_PI / 2) ori = (float)((double)ori + 2 * ROT_PI);
+        else if ((double)ori > (double)startOri + ROT_PI * 3 / 2) ori = (float)((double)ori - 2 * ROT_PI);
+    } else {                                                                                                // :359-365
+        ori = (float)((double)ori + 2 * ROT_PI);
+        if ((double)ori < (double)endOri - ROT_PI * 3 / 2) ori = (float)((double)ori + 2 * ROT_PI);
+        else if ((double)ori > (double)endOri + ROT_PI / 2) ori = (float)((double)ori - 2 * ROT_PI);
+    }
+    const float relTime = (ori - startOri) / (endOri - startOri);                                           // :367
+    const float intensity = (float)((double)(int)key + 0.1 * (double)relTime);                              // :368
+    // undistortion, :153-177
+    const int line = (int)intensity;
+    double dt_i = (double)(intensity - (float)line);
+    double ratio_i = dt_i / 0.1;
+    if (ratio_i >= 1.0) ratio_i = 1.0;
+    Q4 q_si = qslerp_x(Q4{1, 0, 0, 0}, ratio_i, qIMU);
+    q_si = qmul_x(qmul_x(q_lb, q_si), qinv_x(q_lb));                                                        // :168
+    const float4 a = pts[i].a;
+    D3 ps = qrot_x(q_si, D3{(double)a.x, (double)a.y, (double)a.z});
+    Pt32 o;
+    o.a = make_float4((float)ps.x, (float)ps.y, (float)ps.z, 1.0f);
+    o.b = make_float4(intensity, 0.f, 0.f, 0.f);
+    cloud[s] = o;
+}
+
+__global__ void k_rot_curv(const Pt32* __restrict__ cloud, const int* __restrict__ meta, float* __restrict__ curv, int* __restrict__ label,
+                           int* __restrict__ lessflat, int n_alloc) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n_alloc) return;
+    const int cloudSize = meta[M_NVALID];
+    float c = 0.f;
+    if (i >= 5 && i < cloudSize - 5) {
+        const float4 m5 = cloud[i - 5].a, m4 = cloud[i - 4].a, m3 = cloud[i - 3].a, m2 = cloud[i - 2].a, m1 = cloud[i - 1].a,
+                     p0 = cloud[i].a, p1 = cloud[i + 1].a, p2 = cloud[i + 2].a, p3 = cloud[i + 3].a, p4 = cloud[i + 4].a, p5 = cloud[i + 5].a;
+        float dX = m5.x + m4.x + m3.x + m2.x + m1.x - 10.0f * p0.x + p1.x + p2.x + p3.x + p4.x + p5.x;
+        float dY = m5.y + m4.y + m3.y + m2.y + m1.y - 10.0f * p0.y + p1.y + p2.y + p3.y + p4.y + p5.y;
+        float dZ = m5.z + m4.z + m3.z + m2.z + m1.z - 10.0f * p0.z + p1.z + p2.z + p3.z + p4.z + p5.z;
+        c = dX * dX + dY * dY + dZ * dZ;                                                                    // :390
+    }
+    if (i < n_alloc) { curv[i] = c; label[i] = 0; }
+    lessflat[i] = 0;   // includes the scan sentinel at n_alloc
+}
+
+// dynamic shared memory of k_rot_ring
+struct RingSmem {
+    unsigned long long keys[ROT_SEG_CAP];      // (curvature bits << 32) | index
+    float4 pts[ROT_SEG_CAP + 16];              // segment window [sp-5, ep+5]
+    unsigned char picked[ROT_RING_CAP];        // cloudNeighborPicked of this ring
+};
+
+__global__ void __launch_bounds__(512) k_rot_ring(const Pt32* __restrict__ cloud, const float* __restrict__ curv, int* __restrict__ meta,
+                                                  int ds_rate, int* __restrict__ label, int* __restrict__ lessflat,
+                                                  int* __restrict__ seg_edge /* [rings*6][10] */, int* __restrict__ seg_cnt /* [rings*6] */) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    RingSmem& S = *reinterpret_cast<RingSmem*>(smem_raw);
+    const int ring = blockIdx.x;
+    const int rf = meta[M_RF + ring], re = meta[M_RE + ring];
+    const int scanStart = rf + 5, scanEnd = re - 6;                                                         // :379-381
+    for (int j = 0; j < 6; ++j) if (threadIdx.x == 0) seg_cnt[ring * 6 + j] = 0;
+    if (re <= rf) return;                                   // empty ring
+    if (scanEnd - scanStart < 6 || ring % ds_rate != 0) return;                                             // :402
+    const int ring_len = re - rf;
+    if (ring_len > ROT_RING_CAP) { if (threadIdx.x == 0) meta[M_ERR] = 1; return; }
+    for (int k = threadIdx.x; k < ring_len; k += blockDim.x) S.picked[k] = 0;
+    __syncthreads();
+    for (int j = 0; j < 6; ++j) {
+        const int sp = scanStart + (scanEnd - scanStart) * j / 6;                                           // :406-407
+        const int ep = scanStart + (scanEnd - scanStart) * (j + 1) / 6 - 1;
+        const int L = ep - sp + 1;
+        if (L > ROT_SEG_CAP) { if (threadIdx.x == 0) meta[M_ERR] = 1; return; }
+        int P = 1;
+        while (P < L) P <<= 1;
+        for (int k = threadIdx.x; k < P; k += blockDim.x) {
+            unsigned long long key = ~0ull;
+            if (k < L) key = ((unsigned long long)__float_as_uint(curv[sp + k]) << 32) | (unsigned)(sp + k);
+            S.keys[k] = key;
+        }
+        for (int k = threadIdx.x; k < L + 10; k += blockDim.x) S.pts[k] = cloud[sp - 5 + k].a;
+        __syncthreads();
+        // bitonic sort ascending on (curvature, index): curvature >= 0 so its bit pattern orders like the value
+        for (int size = 2; size <= P; size <<= 1) {
+            for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                for (int t = threadIdx.x; t < P / 2; t += blockDim.x) {
+                    int lo = 2 * t - (t & (stride - 1));
+                    int hi = lo + stride;
+                    bool up = ((lo & size) == 0);
+                    unsigned long long a = S.keys[lo], b = S.keys[hi];
+                    if ((a > b) == up) { S.keys[lo] = b; S.keys[hi] = a; }
+                }
+                __syncthreads();
+            }
+        }
+        if (threadIdx.x == 0) {
+            auto PT = [&](int ind) -> const float4& { return S.pts[ind - sp + 5]; };
+            auto gap2 = [&](int a, int b) {
+                float dX = PT(a).x - PT(b).x, dY = PT(a).y - PT(b).y, dZ = PT(a).z - PT(b).z;
+                return dX * dX + dY * dY + dZ * dZ;
+            };
+            auto suppress = [&](int ind) {                                                                  // :434-451
+                for (int l = 1; l <= 5; l++) {
+                    if ((double)gap2(ind + l, ind + l - 1) > 0.05) break;
+                    S.picked[ind + l - rf] = 1;
+                }
+                for (int l = -1; l >= -5; l--) {
+                    if ((double)gap2(ind + l, ind + l + 1) > 0.05) break;
+                    S.picked[ind + l - rf] = 1;
+                }
+            };
+            int largest = 0, nedge = 0;
+            for (int k = L - 1; k >= 0; --k) {                                                              // :413-453
+                const unsigned long long key = S.keys[k];
+                const int ind = (int)(unsigned)(key & 0xffffffffu);
+                const float cv = __uint_as_float((unsigned)(key >> 32));
+                if (!((double)cv > 2.0)) break;      // sorted: nothing further can be picked (no side effects skipped)
+                if (S.picked[ind - rf] == 0) {
+                    largest++;
+                    if (largest <= 2) { label[ind] = 2; seg_edge[(ring * 6 + j) * 10 + nedge++] = ind; }
+                    else if (largest <= 10) { label[ind] = 1; seg_edge[(ring * 6 + j) * 10 + nedge++] = ind; }
+                    else break;
+                    S.picked[ind - rf] = 1;
+                    suppress(ind);
+                }
+            }
+            seg_cnt[ring * 6 + j] = nedge;
+            int smallest = 0;
+            for (int k = 0; k < L; ++k) {                                                                   // :456-492
+                const unsigned long long key = S.keys[k];
+                const int ind = (int)(unsigned)(key & 0xffffffffu);
+                const float cv = __uint_as_float((unsigned)(key >> 32));
+                if (!((double)cv < 0.1)) break;      // sorted ascending: the rest cannot qualify
+                const float4& p = PT(ind);
+                if ((double)(p.x * p.x + p.y * p.y + p.z * p.z) < 0.25) continue;
+                if (S.picked[ind - rf] == 0) {
+                    label[ind] = -1;
+                    smallest++;
+                    if (smallest >= 4) break;
+                    S.picked[ind - rf] = 1;
+                    suppress(ind);
+                }
+            }
+        }
+        __syncthreads();
+        for (int k = sp + (int)threadIdx.x; k <= ep; k += blockDim.x) {                                     // :494-499
+            const float4& p = S.pts[k - sp + 5];
+            bool far = !((double)(p.x * p.x + p.y * p.y + p.z * p.z) < 0.25);
+            lessflat[k] = (far && label[k] <= 0) ? 1 : 0;
+        }
+        __syncthreads();
+    }
+}
+
+// ---- per-ring VoxelGrid(0.6) of the less-flat points, batched over rings
+// ringmm: [ring][8] ordered-int min xyz, max xyz, count
+__global__ void k_rot_lf_init(int* ringmm) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ROT_MAX_RINGS * 8) return;
+    int f = t & 7;
+    ringmm[t] = f < 3 ? INT_MAX : (f < 6 ? INT_MIN : 0);
+}
+
+__device__ __forceinline__ int rf2ord(float f) { int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7fffffff; }
+__device__ __forceinline__ float rord2f(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+
+__global__ void k_rot_lf_gather(const Pt32* __restrict__ cloud, const uint32_t* __restrict__ skeys, const int* __restrict__ lessflat,
+                                const int* __restrict__ lfpos, int n, int* __restrict__ lf_src, int* __restrict__ ringmm, int* __restrict__ meta) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k == 0) meta[M_NLF] = lfpos[n];
+    if (k >= n || !lessflat[k]) return;
+    lf_src[lfpos[k]] = k;
+    const int ring = (int)skeys[k];
+    float4 a = cloud[k].a;
+    int* mm = ringmm + ring * 8;
+    atomicMin(&mm[0], rf2ord(a.x)); atomicMin(&mm[1], rf2ord(a.y)); atomicMin(&mm[2], rf2ord(a.z));
+    atomicMax(&mm[3], rf2ord(a.x)); atomicMax(&mm[4], rf2ord(a.y)); atomicMax(&mm[5], rf2ord(a.z));
+    atomicAdd(&mm[6], 1);
+}
+
+__global__ void k_rot_lf_params(const int* __restrict__ ringmm, float leaf, VgParams* __restrict__ prm) {
+    int ring = threadIdx.x;
+    if (ring >= ROT_MAX_RINGS) return;
+    const int* mm = ringmm + ring * 8;
+    VgParams p;
+    p.inv_leaf = 1.0f / leaf;
+    p.n_finite = mm[6];
+    p.overflow = 0;
+    if (p.n_finite == 0) {
+        for (int k = 0; k < 3; ++k) { p.min_b[k] = 0; p.div_b[k] = 1; }
+    } else {
+        long long d[3];
+        for (int k = 0; k < 3; ++k) {
+            float lo = rord2f(mm[k]), hi = rord2f(mm[3 + k]);
+            d[k] = (long long)((hi - lo) * p.inv_leaf) + 1;
+            p.min_b[k] = (int)floorf(lo * p.inv_leaf);
+            p.div_b[k] = (int)floorf(hi * p.inv_leaf) - p.min_b[k] + 1;
+        }
+        if (d[0] * d[1] * d[2] > (long long)INT_MAX) p.overflow = 1;
+    }
+    p.mul[0] = 1; p.mul[1] = p.div_b[0]; p.mul[2] = p.div_b[0] * p.div_b[1];
+    prm[ring] = p;
+}
+
+__global__ void k_rot_lf_keys(const Pt32* __restrict__ cloud, const uint32_t* __restrict__ skeys, const int* __restrict__ lf_src,
+                              const int* __restrict__ meta, const VgParams* __restrict__ prm, unsigned long long* __restrict__ keys,
+                              int* __restrict__ vals, int cap) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= cap) return;
+    unsigned long long key = ~0ull;
+    if (t < meta[M_NLF]) {
+        const int k = lf_src[t];
+        const int ring = (int)skeys[k];
+        const VgParams p = prm[ring];
+        float4 a = cloud[k].a;
+        unsigned idx;
+        if (p.overflow) idx = (unsigned)t;     // PCL returns the input unchanged: every point its own voxel, input order
+        else {
+            int i0 = (int)(floorf(a.x * p.inv_leaf) - (float)p.min_b[0]);
+            int i1 = (int)(floorf(a.y * p.inv_leaf) - (float)p.min_b[1]);
+            int i2 = (int)(floorf(a.z * p.inv_leaf) - (float)p.min_b[2]);
+            idx = (unsigned)(i0 * p.mul[0] + i1 * p.mul[1] + i2 * p.mul[2]);
+        }
+        key = ((unsigned long long)ring << 32) | idx;
+    }
+    keys[t] = key;
+    vals[t] = t;
+}
+
+__global__ void k_rot_lf_heads(const unsigned long long* __restrict__ keys, const int* __restrict__ meta, int cap, int* __restrict__ flags) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t > cap) return;
+    int f = 0;
+    if (t < cap && t < meta[M_NLF]) f = (t == 0 || keys[t] != keys[t - 1]);
+    flags[t] = f;
+}
+
+__global__ void k_rot_lf_centroid(const Pt32* __restrict__ cloud, const int* __restrict__ lf_src, const unsigned long long* __restrict__ keys,
+                                  const int* __restrict__ vals, const int* __restrict__ flags, const int* __restrict__ rank,
+                                  const int* __restrict__ meta, int cap, Pt32* __restrict__ out, int* __restrict__ n_out) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t == 0) *n_out = rank[cap];
+    const int nlf = meta[M_NLF];
+    if (t >= cap || t >= nlf || !flags[t]) return;
+    const unsigned long long key = keys[t];
+    float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
+    int cnt = 0;
+    for (int j = t; j < nlf && keys[j] == key; ++j) {
+        const Pt32 p = cloud[lf_src[vals[j]]];
+        sx += p.a.x; sy += p.a.y; sz += p.a.z; si += p.b.x;
+        ++cnt;
+    }
+    const float fc = (float)cnt;
+    Pt32 o;
+    o.a = make_float4(sx / fc, sy / fc, sz / fc, 1.0f);
+    o.b = make_float4(si / fc, 0.f, 0.f, 0.f);
+    out[rank[t]] = o;
+}
+
+// edge output: segment-major, pick order inside the segment (one block, 64*6 = 384 segments)
+__global__ void __launch_bounds__(384) k_rot_edge_emit(const Pt32* __restrict__ cloud, const int* __restrict__ seg_edge,
+                                                       const int* __restrict__ seg_cnt, int nseg, Pt32* __restrict__ edge, int* __restrict__ meta) {
+    __shared__ int wsum[12];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    int v = t < nseg ? seg_cnt[t] : 0;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    if (t == 0) { int acc = 0; for (int w = 0; w < 12; ++w) { int x = wsum[w]; wsum[w] = acc; acc += x; } meta[M_NEDGE] = acc; }
+    __syncthreads();
+    const int off = inc - v + wsum[warp];
+    for (int e = 0; e < v; ++e) edge[off + e] = cloud[seg_edge[t * 10 + e]];
+}
+
+int rot_extract_dev(liliom_ctx* c, int n, const double q_imu[4], const double q_lb[4], int* n_surf, int* n_edge, int* n_cut) {
+    const int n_scans = c->prm.line_num;
+    if (n_scans != 16 && n_scans != 32 && n_scans != 64) return LILIOM_E_LINES;
+    if (c->prm.ds_rate < 1) return LILIOM_E_ARG;
+    *n_surf = *n_edge = *n_cut = 0;
+    c->n_surf_dev = 0; c->n_rot_cloud = 0;
+    if (n <= 0) return LILIOM_OK;
+    const size_t N = (size_t)n;
+    LILI_CUDA(c, c->rot_keys.ensure(N * 8)); LILI_CUDA(c, c->rot_keys2.ensure(N * 8));
+    LILI_CUDA(c, c->rot_vals.ensure(N * 4)); LILI_CUDA(c, c->rot_vals2.ensure(N * 4));
+    LILI_CUDA(c, c->rot_ring.ensure(N * 4));                 // raw azimuth
+    LILI_CUDA(c, c->rot_cloud.ensure(N * sizeof(Pt32)));
+    LILI_CUDA(c, c->cut.ensure(N * sizeof(Pt32)));
+    LILI_CUDA(c, c->rot_curv.ensure(N * 4)); LILI_CUDA(c, c->rot_label.ensure(N * 4));
+    LILI_CUDA(c, c->rot_lessflat.ensure((N + 2) * 4)); LILI_CUDA(c, c->rot_sort.ensure((N + 2) * 4));
+    LILI_CUDA(c, c->rot_picked.ensure((N + 2) * 4));         // lf_src
+    LILI_CUDA(c, c->rot_meta.ensure((M_SIZE + ROT_MAX_RINGS * 8) * 4 + ROT_MAX_RINGS * sizeof(VgParams)));
+    LILI_CUDA(c, c->rot_seg_edge.ensure((size_t)ROT_MAX_RINGS * 6 * 11 * 4));
+    LILI_CUDA(c, c->surf.ensure(N * sizeof(Pt32)));
+    LILI_CUDA(c, c->edge.ensure((size_t)ROT_MAX_RINGS * 6 * 10 * sizeof(Pt32)));
+    LILI_CUDA(c, c->vg_flags.ensure((N + 2) * 4)); LILI_CUDA(c, c->vg_rank.ensure((N + 2) * 4));
+    LILI_CUDA(c, c->vg_count.ensure(16));
+
+    Q4 qI{q_imu[0], q_imu[1], q_imu[2], q_imu[3]};
+    if (std::isnan(qI.w) || std::isnan(qI.x) || std::isnan(qI.y) || std::isnan(qI.z)) qI = Q4{1, 0, 0, 0};   // :299-301
+    Q4 qL{q_lb[0], q_lb[1], q_lb[2], q_lb[3]};
+    const Pt32* raw = c->raw.as<Pt32>();
+    int* meta = c->rot_meta.as<int>();
+    int* ringmm = meta + M_SIZE;
+    VgParams* rprm = reinterpret_cast<VgParams*>(ringmm + ROT_MAX_RINGS * 8);
+    uint32_t* keys = c->rot_keys.as<uint32_t>(); uint32_t* keys2 = c->rot_keys2.as<uint32_t>();
+    int* vals = c->rot_vals.as<int>(); int* vals2 = c->rot_vals2.as<int>();
+    float* ori = c->rot_ring.as<float>();
+    Pt32* cloud = c->rot_cloud.as<Pt32>();
+    int* seg_edge = c->rot_seg_edge.as<int>();
+    int* seg_cnt = seg_edge + ROT_MAX_RINGS * 6 * 10;
+
+    k_rot_meta_init<<<1, 256, 0, c->stream>>>(meta);
+    LILI_TRY(launch_check(c, "k_rot_meta_init"));
+    k_rot_pre<<<cdiv(n, 256), 256, 0, c->stream>>>(raw, n, n_scans, keys, vals, ori, meta);
+    LILI_TRY(launch_check(c, "k_rot_pre"));
+    k_rot_hp<<<cdiv(n, 256), 256, 0, c->stream>>>(raw, n, keys, ori, meta);
+    LILI_TRY(launch_check(c, "k_rot_hp"));
+    LILI_TRY(sort_pairs_u32(c, keys, keys2, vals, vals2, n, 8));
+    k_rot_build<<<cdiv(n, 128), 128, 0, c->stream>>>(raw, n, keys2, vals2, ori, qI, qL, cloud, meta);
+    LILI_TRY(launch_check(c, "k_rot_build"));
+    k_rot_curv<<<cdiv(n + 1, 256), 256, 0, c->stream>>>(cloud, meta, c->rot_curv.as<float>(), c->rot_label.as<int>(),
+                                                        c->rot_lessflat.as<int>(), n);
+    LILI_TRY(launch_check(c, "k_rot_curv"));
+    static bool attr_set = false;
+    if (!attr_set) {
+        LILI_CUDA(c, cudaFuncSetAttribute(k_rot_ring, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RingSmem)));
+        attr_set = true;
+    }
+    k_rot_ring<<<n_scans, 512, sizeof(RingSmem), c->stream>>>(cloud, c->rot_curv.as<float>(), meta, c->prm.ds_rate, c->rot_label.as<int>(),
+                                                              c->rot_lessflat.as<int>(), seg_edge, seg_cnt);
+    LILI_TRY(launch_check(c, "k_rot_ring"));
+    k_rot_edge_emit<<<1, 384, 0, c->stream>>>(cloud, seg_edge, seg_cnt, n_scans * 6, c->edge.as<Pt32>(), meta);
+    LILI_TRY(launch_check(c, "k_rot_edge_emit"));
+    // less-flat -> per-ring VoxelGrid
+    int* lfpos = c->rot_sort.as<int>();
+    int* lf_src = c->rot_picked.as<int>();
+    LILI_TRY(exclusive_scan_i32(c, c->rot_lessflat.as<int>(), lfpos, n));
+    k_rot_lf_init<<<cdiv(ROT_MAX_RINGS * 8, 256), 256, 0, c->stream>>>(ringmm);
+    LILI_TRY(launch_check(c, "k_rot_lf_init"));
+    k_rot_lf_gather<<<cdiv(n, 256), 256, 0, c->stream>>>(cloud, keys2, c->rot_lessflat.as<int>(), lfpos, n, lf_src, ringmm, meta);
+    LILI_TRY(launch_check(c, "k_rot_lf_gather"));
+    k_rot_lf_params<<<1, 64, 0, c->stream>>>(ringmm, c->prm.rot_ds_leaf, rprm);
+    LILI_TRY(launch_check(c, "k_rot_lf_params"));
+    unsigned long long* k64 = c->rot_keys.as<unsigned long long>();
+    unsigned long long* k64b = c->rot_keys2.as<unsigned long long>();
+    // keys2 (ring ids, sorted) is still needed by k_rot_lf_keys: stash it before reusing the buffers
+    LILI_CUDA(c, c->idx_b.ensure(N * 4));
+    LILI_CUDA(c, cudaMemcpyAsync(c->idx_b.p, keys2, N * 4, cudaMemcpyDeviceToDevice, c->stream));
+    const uint32_t* ring_of = c->idx_b.as<uint32_t>();
+    k_rot_lf_keys<<<cdiv(n, 256), 256, 0, c->stream>>>(cloud, ring_of, lf_src, meta, rprm, k64, vals, n);
+    LILI_TRY(launch_check(c, "k_rot_lf_keys"));
+    LILI_TRY(sort_pairs_u64(c, k64, k64b, vals, vals2, n, 40));
+    k_rot_lf_heads<<<cdiv(n + 1, 256), 256, 0, c->stream>>>(k64b, meta, n, c->vg_flags.as<int>());
+    LILI_TRY(launch_check(c, "k_rot_lf_heads"));
+    LILI_TRY(exclusive_scan_i32(c, c->vg_flags.as<int>(), c->vg_rank.as<int>(), n));
+    k_rot_lf_centroid<<<cdiv(n, 128), 128, 0, c->stream>>>(cloud, lf_src, k64b, vals2, c->vg_flags.as<int>(), c->vg_rank.as<int>(), meta, n,
+                                                           c->surf.as<Pt32>(), c->vg_count.as<int>());
+    LILI_TRY(launch_check(c, "k_rot_lf_centroid"));
+    int* hp = reinterpret_cast<int*>(c->h_pin);
+    LILI_CUDA(c, cudaMemcpyAsync(hp, meta, 8 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    LILI_CUDA(c, cudaMemcpyAsync(hp + 8, c->vg_count.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    LILI_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (hp[M_ERR]) { c->last_error = "ring/segment larger than the shared-memory capacity (16384 / 4096 points)"; return LILIOM_E_CAPACITY; }
+    *n_cut = hp[M_NVALID]; *n_edge = hp[M_NEDGE]; *n_surf = hp[8];
+    c->n_surf_dev = hp[8];
+    c->n_rot_cloud = hp[M_NVALID];
+    return LILIOM_OK;
+}
+
+}  // namespace lili

@@ -1,0 +1,735 @@
+// Scan-to-map on sm_100a: dense 1 m cell grid over the down-sampled map (stand-in for the
+// per-scan FLANN kd-tree, L/src/LidarOdometry.cpp:490) and the fused
+//   transform -> exact 5-NN -> 5x3 QR plane -> gates -> residual + SE(3) Jacobian row ->
+//   Huber -> 21+6 reduction -> 6x6 solve -> pose update
+// kernel replacing findCorrespondingSurfFeatures + the Ceres problem/solve
+// (L/src/LidarOdometry.cpp:352-413, 506-561; L/include/factors/LidarKeyframeFactor.h:111-139).
+//
+// HBM-bound integer/float gather work: no dense contraction, so no tensor cores.  Design:
+//   * map points stored as float4 {x,y,z,orig_index} sorted by cell id (z,y,x order) so the
+//     3 x-adjacent cells of a row are ONE contiguous run: 9 coalesced runs per query;
+//   * 8 lanes ("octet") cooperate on one query: lanes stride through each run with 16-byte
+//     loads, keep a private sorted top-5 in registers, then merge with 3 xor-shuffles;
+//   * a warp finishes 4*R queries, parks the 5 neighbour slots in shared memory, and then every
+//     lane runs the fp64 plane fit / Jacobian of a DIFFERENT query (no redundant fp64 issue);
+//   * 29 fp64 partial sums per block -> fixed-order cross-block sum by the last block (ticket),
+//     which also solves the 6x6 system and updates the pose in HBM: one launch per iteration,
+//     the pose never visits the host inside the loop, results are run-to-run deterministic.
+// Exactness: a query's cell block covers its full `cell`-metre ball and cells are aligned to
+// the integer lattice (floorf(x * 2^-k) is exact), so any point outside the 27 cells is at
+// fp32 distance >= cell >= sqrt(knn_max_sqdist): the accepted 5-NN sets equal the kd-tree's.
+#include "ctx.cuh"
+#include "dev_math.cuh"
+#include "knn_core.cuh"
+
+namespace lili {
+
+// ------------------------------------------------------------------ small utilities
+__global__ void k_repack_f4(const unsigned char* __restrict__ in, int n, int stride, float4* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 v = *reinterpret_cast<const float4*>(in + (size_t)i * stride);
+    v.w = __int_as_float(i);
+    out[i] = v;
+}
+
+int repack_to_f4(liliom_ctx* c, const void* d_in, int n, int stride, float4* d_out) {
+    if (n <= 0) return LILIOM_OK;
+    k_repack_f4<<<cdiv(n, 256), 256, 0, c->stream>>>((const unsigned char*)d_in, n, stride, d_out);
+    return launch_check(c, "k_repack_f4");
+}
+
+__device__ __forceinline__ int f2ord(float f) { int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7fffffff; }
+__device__ __forceinline__ float ord2f(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+
+// mm[0..2] = min xyz (ordered-int encoding), mm[3..5] = max
+__global__ void k_minmax_f4(const float4* __restrict__ p, int n, int* __restrict__ mm) {
+    int lo[3] = {INT_MAX, INT_MAX, INT_MAX}, hi[3] = {INT_MIN, INT_MIN, INT_MIN};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float4 v = p[i];
+        int a = f2ord(v.x), b = f2ord(v.y), cz = f2ord(v.z);
+        lo[0] = min(lo[0], a); hi[0] = max(hi[0], a);
+        lo[1] = min(lo[1], b); hi[1] = max(hi[1], b);
+        lo[2] = min(lo[2], cz); hi[2] = max(hi[2], cz);
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[k] = min(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], o));
+            hi[k] = max(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], o));
+        }
+    }
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { atomicMin(&mm[k], lo[k]); atomicMax(&mm[3 + k], hi[k]); }
+    }
+}
+
+__global__ void k_init_minmax(int* mm) {
+    if (threadIdx.x < 3) mm[threadIdx.x] = INT_MAX;
+    else if (threadIdx.x < 6) mm[threadIdx.x] = INT_MIN;
+}
+
+__global__ void k_cell_keys(const float4* __restrict__ p, int n, GridDesc g, uint32_t* __restrict__ keys, int* __restrict__ vals) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 v = p[i];
+    int cx = cell_coord(v.x, g.inv_cell) - g.org[0];
+    int cy = cell_coord(v.y, g.inv_cell) - g.org[1];
+    int cz = cell_coord(v.z, g.inv_cell) - g.org[2];
+    keys[i] = (uint32_t)((cz * g.dim[1] + cy) * g.dim[0] + cx);
+    vals[i] = i;
+}
+
+__global__ void k_gather_sorted(const float4* __restrict__ p, const int* __restrict__ vals, int n, float4* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int src = vals[i];
+    float4 v = p[src];
+    out[i] = make_float4(v.x, v.y, v.z, v.w);   // w already carries the original index bits
+}
+
+// cell_start[c] = first sorted position whose key >= c; one warp per run boundary fills the gap.
+__global__ void k_cell_bounds(const uint32_t* __restrict__ keys, int n, int ncells, int* __restrict__ cell_start) {
+    int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (w > n) return;
+    // boundary w: between sorted position w-1 and w (w == n: tail)
+    long long prev = (w == 0) ? -1 : (long long)keys[w - 1];
+    long long cur = (w == n) ? (long long)ncells : (long long)keys[w];
+    if (cur == prev) return;
+    for (long long cc = prev + 1 + lane; cc <= cur; cc += 32) cell_start[cc] = w;
+}
+
+int grid_build(liliom_ctx* c, int m) {
+    c->map_ready = false;
+    c->map_n = m;
+    if (m <= 0) { c->grid = GridDesc{}; return LILIOM_OK; }
+    float4* pts = c->map_xyzw.as<float4>();
+    LILI_CUDA(c, c->vg_minmax.ensure(8 * sizeof(int)));
+    int* mm = c->vg_minmax.as<int>();
+    k_init_minmax<<<1, 32, 0, c->stream>>>(mm);
+    LILI_TRY(launch_check(c, "k_init_minmax"));
+    k_minmax_f4<<<min(cdiv(m, 256), c->sm_count * 8), 256, 0, c->stream>>>(pts, m, mm);
+    LILI_TRY(launch_check(c, "k_minmax_f4"));
+    int h[6];
+    LILI_CUDA(c, cudaMemcpyAsync(h, mm, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    LILI_CUDA(c, cudaStreamSynchronize(c->stream));
+    auto dec = [](int i) { int j = i >= 0 ? i : i ^ 0x7fffffff; float f; memcpy(&f, &j, 4); return f; };
+    // cell size: smallest power of two >= sqrt(knn_max_sqdist) (1.0 for the reference's gate)
+    float cell = 1.0f;
+    while ((double)cell * (double)cell < c->prm.knn_max_sqdist) cell *= 2.0f;
+    GridDesc g;
+    g.inv_cell = 1.0f / cell;
+    long long nc = 1;
+    for (int k = 0; k < 3; ++k) {
+        float lo = dec(h[k]), hi = dec(h[3 + k]);
+        if (!(std::isfinite(lo) && std::isfinite(hi))) { c->last_error = "non-finite map point"; return LILIOM_E_ARG; }
+        int clo = (int)floorf(lo * g.inv_cell), chi = (int)floorf(hi * g.inv_cell);
+        g.org[k] = clo;
+        g.dim[k] = chi - clo + 1;
+        nc *= g.dim[k];
+    }
+    if (nc > (1LL << 29)) { c->last_error = "map extent needs more than 2^29 cells"; return LILIOM_E_GRID; }
+    g.ncells = (int)nc;
+    c->grid = g;
+    LILI_CUDA(c, c->grid_keys.ensure((size_t)m * 4));
+    LILI_CUDA(c, c->grid_keys2.ensure((size_t)m * 4));
+    LILI_CUDA(c, c->grid_vals.ensure((size_t)m * 4));
+    LILI_CUDA(c, c->grid_vals2.ensure((size_t)m * 4));
+    LILI_CUDA(c, c->map_sorted.ensure((size_t)m * sizeof(float4)));
+    LILI_CUDA(c, c->cell_start.ensure(((size_t)g.ncells + 2) * 4));
+    k_cell_keys<<<cdiv(m, 256), 256, 0, c->stream>>>(pts, m, g, c->grid_keys.as<uint32_t>(), c->grid_vals.as<int>());
+    LILI_TRY(launch_check(c, "k_cell_keys"));
+    int bits = 1;
+    while ((1LL << bits) < nc) ++bits;
+    LILI_TRY(sort_pairs_u32(c, c->grid_keys.as<uint32_t>(), c->grid_keys2.as<uint32_t>(), c->grid_vals.as<int>(),
+                            c->grid_vals2.as<int>(), m, bits));
+    k_gather_sorted<<<cdiv(m, 256), 256, 0, c->stream>>>(pts, c->grid_vals2.as<int>(), m, c->map_sorted.as<float4>());
+    LILI_TRY(launch_check(c, "k_gather_sorted"));
+    k_cell_bounds<<<cdiv(((long long)m + 1) * 32, 256), 256, 0, c->stream>>>(c->grid_keys2.as<uint32_t>(), m, g.ncells,
+                                                                          c->cell_start.as<int>());
+    LILI_TRY(launch_check(c, "k_cell_bounds"));
+    c->map_ready = true;
+    return LILIOM_OK;
+}
+
+// ------------------------------------------------------------------ the hot kernel
+struct KnnArgs {
+    const float4* feats; int n;
+    const float4* map; const int* cell_start; GridDesc g;
+    const double* pose;                 // 7 doubles in HBM
+    double max_sqd, plane_thres, w_gate, huber_a;
+    unsigned char* valid; float4* plane; int* nn_idx; float* nn_sqd;   // optional outputs
+    double* partials; double* neq; unsigned int* ticket;
+    double* stats;                      // this iteration's stats slot (kStatsDoubles) or null
+    double* pose_out;                   // where the updated pose goes (== pose for GN)
+    unsigned long long* cand_total;     // instrumentation
+    int update_pose;                    // 1: last block performs the GN step
+    int rounds;                         // R: a warp handles 4*R queries per task
+    int nranks, rank;                   // multi-GPU ownership filter (8 m block hash)
+};
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__global__ void __launch_bounds__(kBlock) k_knn_plane(KnnArgs a) {
+    __shared__ Slot slots[kWarps][32];
+    __shared__ double red[kWarps][kNormEq];
+    __shared__ unsigned long long red_cand[kWarps];
+    __shared__ bool is_last;
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int sub = lane & (kLanes - 1);          // lane within the octet
+    const int oct = lane / kLanes;                // octet within the warp (0..3)
+    const unsigned omask = ((1u << kLanes) - 1u) << (oct * kLanes);
+
+    Q4 q{a.pose[0], a.pose[1], a.pose[2], a.pose[3]};
+    D3 t{a.pose[4], a.pose[5], a.pose[6]};
+
+    double acc[kNormEq];
+#pragma unroll
+    for (int k = 0; k < kNormEq; ++k) acc[k] = 0.0;
+    unsigned long long cand = 0;
+
+    const int per_task = 4 * a.rounds;
+    const int ntasks = (a.n + per_task - 1) / per_task;
+    const int gw = blockIdx.x * kWarps + warp;
+    const int nw = gridDim.x * kWarps;
+    const float inf = __int_as_float(0x7f800000);
+
+    for (int task = gw; task < ntasks; task += nw) {
+        // ---------------- phase A: cooperative exact 5-NN, one query per octet per round
+        for (int r = 0; r < a.rounds; ++r) {
+            const int slot = r * 4 + oct;
+            const int qi = task * per_task + slot;
+            Top5 top{inf, inf, inf, inf, inf, -1, -1, -1, -1, -1};
+            float sx = 0.f, sy = 0.f, sz = 0.f;
+            bool live = qi < a.n;
+            if (live) {
+                float4 f = a.feats[qi];
+                D3 pw = qrot_x(q, D3{(double)f.x, (double)f.y, (double)f.z});      // L/src/LidarOdometry.cpp:230-231
+                sx = (float)addx(pw.x, t.x); sy = (float)addx(pw.y, t.y); sz = (float)addx(pw.z, t.z);   // :236-238
+                if (a.nranks > 1 && owner_of(sx, sy, sz, a.nranks) != a.rank) live = false;
+            }
+            if (live) {
+                octet_knn5(sx, sy, sz, a.map, a.cell_start, a.g, sub, omask, top, cand);
+            }
+            // every lane of a warp must reach the shuffles above together: `live` is uniform
+            // inside an octet and the shuffle masks are per-octet, so divergence between octets is safe.
+            if (sub == 0) {
+                Slot& s = slots[warp][slot];
+                bool ok = live && top.p4 >= 0 && ((double)top.d4 < a.max_sqd);      // :365
+                s.pos[0] = ok ? top.p0 : -1; s.pos[1] = top.p1; s.pos[2] = top.p2; s.pos[3] = top.p3; s.pos[4] = top.p4;
+                s.sx = sx; s.sy = sy; s.sz = sz;
+                if (live && a.nn_idx) {
+                    int o5 = qi * 5;
+                    a.nn_idx[o5 + 0] = top.p0 >= 0 ? __float_as_int(a.map[top.p0].w) : -1;
+                    a.nn_idx[o5 + 1] = top.p1 >= 0 ? __float_as_int(a.map[top.p1].w) : -1;
+                    a.nn_idx[o5 + 2] = top.p2 >= 0 ? __float_as_int(a.map[top.p2].w) : -1;
+                    a.nn_idx[o5 + 3] = top.p3 >= 0 ? __float_as_int(a.map[top.p3].w) : -1;
+                    a.nn_idx[o5 + 4] = top.p4 >= 0 ? __float_as_int(a.map[top.p4].w) : -1;
+                }
+                if (live && a.nn_sqd) {
+                    int o5 = qi * 5;
+                    a.nn_sqd[o5 + 0] = top.d0; a.nn_sqd[o5 + 1] = top.d1; a.nn_sqd[o5 + 2] = top.d2;
+                    a.nn_sqd[o5 + 3] = top.d3; a.nn_sqd[o5 + 4] = top.d4;
+                }
+            }
+        }
+        __syncwarp();
+        // ---------------- phase B: one lane per query — plane fit, gates, residual, Jacobian row
+        if (lane < per_task) {
+            const int qi = task * per_task + lane;
+            const Slot s = slots[warp][lane];
+            bool ok = false;
+            float pl0 = 0.f, pl1 = 0.f, pl2 = 0.f, pl3 = 0.f;
+            if (qi < a.n && s.pos[0] >= 0) {
+                double A[5][3], B[5];
+                float4 m[5];
+#pragma unroll
+                for (int j = 0; j < 5; ++j) m[j] = __ldg(a.map + s.pos[j]);
+#pragma unroll
+                for (int j = 0; j < 5; ++j) { A[j][0] = m[j].x; A[j][1] = m[j].y; A[j][2] = m[j].z; B[j] = -1.0; }   // :363,369-371
+                double nv[3];
+                colpiv_qr_solve_5x3(A, B, nv);                                                                        // :375
+                double n2 = nv[0] * nv[0] + nv[1] * nv[1] + nv[2] * nv[2];
+                double nn = sqrt(n2);
+                double normInverse = 1.0 / nn;                                                                        // :376
+                if (n2 > 0) { nv[0] /= nn; nv[1] /= nn; nv[2] /= nn; }                                                // :377
+                bool planeValid = true;
+#pragma unroll
+                for (int j = 0; j < 5; ++j)                                                                            // :386-393
+                    if (fabs(nv[0] * m[j].x + nv[1] * m[j].y + nv[2] * m[j].z + normInverse) > a.plane_thres) planeValid = false;
+                if (planeValid) {
+                    // :397-398 with the reference's mixed widths; exact ops keep the fp32 roundings stable
+                    float pd = (float)addx(addx(addx(mulx(nv[0], (double)s.sx), mulx(nv[1], (double)s.sy)), mulx(nv[2], (double)s.sz)), normInverse);
+                    float rng = __fsqrt_rn(__fsqrt_rn(faddx(faddx(fmulx(s.sx, s.sx), fmulx(s.sy, s.sy)), fmulx(s.sz, s.sz))));
+                    float weight = (float)subx(1.0, mulx(0.9, (double)fabsf(pd)) / (double)rng);
+                    if ((double)weight > a.w_gate) {                                                                  // :400
+                        pl0 = (float)mulx((double)weight, nv[0]);                                                     // :402-405
+                        pl1 = (float)mulx((double)weight, nv[1]);
+                        pl2 = (float)mulx((double)weight, nv[2]);
+                        pl3 = (float)mulx((double)weight, normInverse);
+                        ok = true;
+                    }
+                }
+            }
+            if (qi < a.n) {
+                if (a.valid) a.valid[qi] = ok ? 1 : 0;
+                if (a.plane) a.plane[qi] = make_float4(pl0, pl1, pl2, pl3);
+            }
+            if (ok) {
+                // LidarPlaneNormIncreFactor (LidarKeyframeFactor.h:118-128) in closed form:
+                //   r = n~ . (q*p + t) + d~ ;  row = [ 2 (R p x n~)^T , n~^T ]  
+                float4 f = a.feats[qi];
+                D3 rp = qrot_x(q, D3{(double)f.x, (double)f.y, (double)f.z});
+                double nx = pl0, ny = pl1, nz = pl2;
+                double r = nx * (rp.x + t.x) + ny * (rp.y + t.y) + nz * (rp.z + t.z) + (double)pl3;
+                double J[6];
+                J[0] = 2.0 * (rp.y * nz - rp.z * ny);
+                J[1] = 2.0 * (rp.z * nx - rp.x * nz);
+                J[2] = 2.0 * (rp.x * ny - rp.y * nx);
+                J[3] = nx; J[4] = ny; J[5] = nz;
+                // ceres::HuberLoss(a) + Corrector (rho'' <= 0 branch): scale row and residual by sqrt(rho')
+                double s2 = r * r, rho0, rho1;
+                const double b2 = a.huber_a * a.huber_a;
+                if (s2 > b2) { double rt = sqrt(s2); rho0 = 2.0 * a.huber_a * rt - b2; rho1 = fmax(DBL_MIN, a.huber_a / rt); }
+                else { rho0 = s2; rho1 = 1.0; }
+                double sr = sqrt(rho1);
+#pragma unroll
+                for (int k = 0; k < 6; ++k) J[k] *= sr;
+                r *= sr;
+                int k = 0;
+#pragma unroll
+                for (int i = 0; i < 6; ++i)
+#pragma unroll
+                    for (int j = i; j < 6; ++j) acc[k++] += J[i] * J[j];
+#pragma unroll
+                for (int i = 0; i < 6; ++i) acc[21 + i] += J[i] * r;
+                acc[27] += 0.5 * rho0;
+                acc[28] += 1.0;
+            }
+        }
+        __syncwarp();
+    }
+
+    // ---------------- block reduction of the 29 partial sums (+ candidate counter)
+#pragma unroll
+    for (int k = 0; k < kNormEq; ++k) {
+        double v = warp_sum(acc[k]);
+        if (lane == 0) red[warp][k] = v;
+    }
+    {
+        unsigned long long v = cand;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) red_cand[warp] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < kNormEq) {
+        double v = 0;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) v += red[w][threadIdx.x];
+        a.partials[(size_t)blockIdx.x * kNormEq + threadIdx.x] = v;
+    }
+    if (threadIdx.x == 0) {
+        unsigned long long v = 0;
+        for (int w = 0; w < kWarps; ++w) v += red_cand[w];
+        if (a.cand_total && v) atomicAdd(a.cand_total, v);
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int tk = atomicAdd(a.ticket, 1u);
+        is_last = (tk == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    // ---------------- last block: fixed-order sum over blocks, then the 6x6 step
+    for (int k = warp; k < kNormEq; k += kWarps) {
+        double v = 0;
+        for (int b = lane; b < (int)gridDim.x; b += 32) v += __ldcg(a.partials + (size_t)b * kNormEq + k);
+        v = warp_sum(v);
+        if (lane == 0) red[0][k] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        *a.ticket = 0;
+        double s[kNormEq];
+        for (int k = 0; k < kNormEq; ++k) { s[k] = red[0][k]; a.neq[k] = s[k]; }
+        if (a.update_pose) {
+            double x[7], xn[7], nb[6], d[6];
+            for (int k = 0; k < 7; ++k) x[k] = a.pose[k];
+            for (int k = 0; k < 6; ++k) nb[k] = -s[21 + k];
+            if (s[28] > 0.0 && solve6_ldlt(s, nb, d)) pose_plus(x, d, xn);
+            else for (int k = 0; k < 7; ++k) xn[k] = x[k];
+            if (xn[0] < 0) { xn[0] = -xn[0]; xn[1] = -xn[1]; xn[2] = -xn[2]; xn[3] = -xn[3]; }   // :539-549
+            for (int k = 0; k < 7; ++k) a.pose_out[k] = xn[k];
+            if (a.stats) {
+                a.stats[0] = s[28]; a.stats[1] = 1.0; a.stats[2] = s[27];
+                for (int k = 0; k < 27; ++k) a.stats[3 + k] = s[k];
+                for (int k = 0; k < 7; ++k) a.stats[30 + k] = xn[k];
+            }
+        }
+    }
+}
+
+// GN step for the multi-GPU path: runs after the all-reduce of neq[29], identically on every rank.
+__global__ void k_gn_update(const double* __restrict__ neq, double* __restrict__ pose, double* __restrict__ stats) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double s[kNormEq], x[7], xn[7], nb[6], d[6];
+    for (int k = 0; k < kNormEq; ++k) s[k] = neq[k];
+    for (int k = 0; k < 7; ++k) x[k] = pose[k];
+    for (int k = 0; k < 6; ++k) nb[k] = -s[21 + k];
+    if (s[28] > 0.0 && solve6_ldlt(s, nb, d)) pose_plus(x, d, xn);
+    else for (int k = 0; k < 7; ++k) xn[k] = x[k];
+    if (xn[0] < 0) { xn[0] = -xn[0]; xn[1] = -xn[1]; xn[2] = -xn[2]; xn[3] = -xn[3]; }
+    for (int k = 0; k < 7; ++k) pose[k] = xn[k];
+    if (stats) {
+        stats[0] = s[28]; stats[1] = 1.0; stats[2] = s[27];
+        for (int k = 0; k < 27; ++k) stats[3 + k] = s[k];
+        for (int k = 0; k < 7; ++k) stats[30 + k] = xn[k];
+    }
+}
+
+// ------------------------------------------------------------------ Ceres-faithful LM on frozen correspondences
+// One block: every LM iteration is a pass over the correspondences (cost + 27 scalars at the
+// candidate), a block reduction, and the trust-region bookkeeping of Ceres 2.0's
+// TrustRegionMinimizer + LevenbergMarquardtStrategy on thread 0 (Jacobi scaling fixed at
+// iteration 0, D = sqrt(clamp(diag)/radius), rho-based radius update), with the dense QR on
+// [J; D] replaced by its normal equations (J^T J + D^2) y = J^T r in fp64 (6x6 LDL^T).
+struct LmArgs {
+    const float4* feats; const unsigned char* valid; const float4* plane; int n;
+    double* pose;         // in/out
+    double* stats;        // slot of this outer iteration
+    double huber_a;
+    int max_num_iter;
+    const double* neq0;   // 29 scalars at the linearisation pose (from k_knn_plane)
+    int nranks; void* unused;
+};
+
+constexpr int kLmBlock = 512;
+
+__device__ void lm_eval(const LmArgs& a, const double x[7], double out[kNormEq], double (*red)[kNormEq]) {
+    Q4 q{x[0], x[1], x[2], x[3]};
+    double acc[kNormEq];
+#pragma unroll
+    for (int k = 0; k < kNormEq; ++k) acc[k] = 0.0;
+    for (int i = threadIdx.x; i < a.n; i += blockDim.x) {
+        if (!a.valid[i]) continue;
+        float4 f = a.feats[i];
+        float4 pl = a.plane[i];
+        D3 rp = qrot_x(q, D3{(double)f.x, (double)f.y, (double)f.z});
+        double nx = pl.x, ny = pl.y, nz = pl.z;
+        double r = nx * (rp.x + x[4]) + ny * (rp.y + x[5]) + nz * (rp.z + x[6]) + (double)pl.w;
+        double J[6];
+        J[0] = 2.0 * (rp.y * nz - rp.z * ny);
+        J[1] = 2.0 * (rp.z * nx - rp.x * nz);
+        J[2] = 2.0 * (rp.x * ny - rp.y * nx);
+        J[3] = nx; J[4] = ny; J[5] = nz;
+        double s2 = r * r, rho0, rho1;
+        const double b2 = a.huber_a * a.huber_a;
+        if (s2 > b2) { double rt = sqrt(s2); rho0 = 2.0 * a.huber_a * rt - b2; rho1 = fmax(DBL_MIN, a.huber_a / rt); }
+        else { rho0 = s2; rho1 = 1.0; }
+        double sr = sqrt(rho1);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) J[k] *= sr;
+        r *= sr;
+        int k = 0;
+#pragma unroll
+        for (int i2 = 0; i2 < 6; ++i2)
+#pragma unroll
+            for (int j = i2; j < 6; ++j) acc[k++] += J[i2] * J[j];
+#pragma unroll
+        for (int i2 = 0; i2 < 6; ++i2) acc[21 + i2] += J[i2] * r;
+        acc[27] += 0.5 * rho0;
+        acc[28] += 1.0;
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < kNormEq; ++k) {
+        double v = warp_sum(acc[k]);
+        if (lane == 0) red[warp][k] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < kNormEq) {
+        double v = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) v += red[w][threadIdx.x];
+        red[0][threadIdx.x] = v;
+    }
+    __syncthreads();
+    for (int k = 0; k < kNormEq; ++k) out[k] = red[0][k];
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(kLmBlock) k_lm_solve(LmArgs a) {
+    __shared__ double red[kLmBlock / 32][kNormEq];
+    __shared__ double sh_x[7];
+    __shared__ int sh_cmd;   // 0 = stop, 1 = evaluate candidate in sh_x
+    double x[7];
+    for (int k = 0; k < 7; ++k) x[k] = a.pose[k];
+    double S[kNormEq];
+    lm_eval(a, x, S, red);          // iteration 0: cost, gradient, J^T J at x
+    // --- thread-0 state (replicated arithmetic is avoided: only thread 0 decides) ---
+    double radius = 1e4, decrease_factor = 2.0;
+    bool reuse_diagonal = false, last_successful = false;
+    double diagonal[6], scaling[6];
+    double x_cost = S[27];
+    int iteration = 0, invalid = 0;
+    if (threadIdx.x == 0) {
+        int kk = 0;
+        for (int i = 0; i < 6; ++i) for (int j = i; j < 6; ++j) { if (i == j) scaling[i] = 1.0 / (1.0 + sqrt(S[kk])); ++kk; }
+    }
+    const double count0 = S[28];
+    double step_keep[6];
+    double model_cost_change = 0;
+    for (;;) {
+        if (threadIdx.x == 0) {
+            int cmd = 1;
+            double xc[7];
+            for (;;) {   // loop over invalid steps without evaluation
+                if (count0 <= 0.0) { cmd = 0; break; }
+                if (iteration >= a.max_num_iter) { cmd = 0; break; }
+                if (last_successful) {
+                    double gmax = 0;
+                    for (int k = 0; k < 6; ++k) gmax = fmax(gmax, fabs(S[21 + k]));
+                    if (gmax <= 1e-10) { cmd = 0; break; }
+                }
+                if (radius < 1e-32) { cmd = 0; break; }
+                ++iteration;
+                last_successful = false;
+                // scaled normal equations  Hs = S H S, gs = S g
+                double Hs[21], gs[6];
+                int kk = 0;
+                for (int i = 0; i < 6; ++i) for (int j = i; j < 6; ++j) { Hs[kk] = S[kk] * scaling[i] * scaling[j]; ++kk; }
+                for (int i = 0; i < 6; ++i) gs[i] = S[21 + i] * scaling[i];
+                if (!reuse_diagonal) {
+                    kk = 0;
+                    for (int i = 0; i < 6; ++i) for (int j = i; j < 6; ++j) { if (i == j) diagonal[i] = fmin(fmax(Hs[kk], 1e-6), 1e32); ++kk; }
+                }
+                double Ha[21];
+                kk = 0;
+                for (int i = 0; i < 6; ++i) for (int j = i; j < 6; ++j) { Ha[kk] = Hs[kk] + (i == j ? diagonal[i] / radius : 0.0); ++kk; }
+                double y[6];
+                bool ok = solve6_ldlt(Ha, gs, y);
+                reuse_diagonal = true;
+                double step[6];
+                model_cost_change = 0;
+                if (ok) {
+                    for (int k = 0; k < 6; ++k) step[k] = -y[k];
+                    // -(step.gs + 1/2 step^T Hs step)
+                    double Hfull[6][6];
+                    kk = 0;
+                    for (int i = 0; i < 6; ++i) for (int j = i; j < 6; ++j) { Hfull[i][j] = Hs[kk]; Hfull[j][i] = Hs[kk]; ++kk; }
+                    double sg = 0, shs = 0;
+                    for (int i = 0; i < 6; ++i) {
+                        sg += step[i] * gs[i];
+                        double hv = 0;
+                        for (int j = 0; j < 6; ++j) hv += Hfull[i][j] * step[j];
+                        shs += step[i] * hv;
+                    }
+                    model_cost_change = -(sg + 0.5 * shs);
+                }
+                if (!ok || !(model_cost_change > 0.0)) {
+                    if (++invalid >= 5) { cmd = 0; break; }
+                    radius *= 0.5; reuse_diagonal = false;
+                    continue;
+                }
+                invalid = 0;
+                for (int k = 0; k < 6; ++k) step_keep[k] = step[k] * scaling[k];
+                pose_plus(x, step_keep, xc);
+                for (int k = 0; k < 7; ++k) sh_x[k] = xc[k];
+                cmd = 1;
+                break;
+            }
+            sh_cmd = cmd;
+        }
+        __syncthreads();
+        if (sh_cmd == 0) break;
+        double xc[7];
+        for (int k = 0; k < 7; ++k) xc[k] = sh_x[k];
+        double Sc[kNormEq];
+        lm_eval(a, xc, Sc, red);
+        int stop = 0;
+        if (threadIdx.x == 0) {
+            double candidate_cost = Sc[27];
+            double xn = 0, sn = 0;
+            for (int k = 0; k < 7; ++k) { xn += x[k] * x[k]; sn += (x[k] - xc[k]) * (x[k] - xc[k]); }
+            xn = sqrt(xn); sn = sqrt(sn);
+            double cost_change = x_cost - candidate_cost;
+            if (sn <= 1e-8 * (xn + 1e-8)) stop = 1;                                   // parameter tolerance
+            else if (fabs(cost_change) <= 1e-6 * x_cost) stop = 1;                    // function tolerance
+            else {
+                double relative_decrease = cost_change / model_cost_change;
+                if (relative_decrease > 1e-3) {
+                    for (int k = 0; k < 7; ++k) x[k] = xc[k];
+                    for (int k = 0; k < kNormEq; ++k) S[k] = Sc[k];
+                    x_cost = candidate_cost;
+                    last_successful = true;
+                    double qd = 2.0 * relative_decrease - 1.0;
+                    radius = radius / fmax(1.0 / 3.0, 1.0 - qd * qd * qd);
+                    radius = fmin(1e16, radius);
+                    decrease_factor = 2.0;
+                    reuse_diagonal = false;
+                } else {
+                    radius = radius / decrease_factor;
+                    decrease_factor *= 2.0;
+                    reuse_diagonal = true;
+                }
+            }
+            sh_cmd = stop ? 0 : 1;
+        }
+        __syncthreads();
+        if (sh_cmd == 0) break;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        if (x[0] < 0) { x[0] = -x[0]; x[1] = -x[1]; x[2] = -x[2]; x[3] = -x[3]; }     // :539-549
+        for (int k = 0; k < 7; ++k) a.pose[k] = x[k];
+        if (a.stats) {
+            a.stats[0] = a.neq0[28]; a.stats[1] = (double)iteration; a.stats[2] = a.neq0[27];
+            for (int k = 0; k < 27; ++k) a.stats[3 + k] = a.neq0[k];
+            for (int k = 0; k < 7; ++k) a.stats[30 + k] = x[k];
+        }
+    }
+}
+
+// ------------------------------------------------------------------ host orchestration
+typedef int (*nccl_allreduce_fn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+int nccl_allreduce_sum_f64(liliom_ctx* c, double* buf, int count);   // comm.cu
+
+static int pick_rounds(int n, int sm_count) {
+    // keep >= ~6 warps per SM busy; beyond that amortise the fp64 phase over more lanes
+    long long warps_at_r1 = ((long long)n + 3) / 4;
+    long long target = (long long)sm_count * 6;
+    int r = 1;
+    while (r < 8 && warps_at_r1 / (r * 2) >= target) r *= 2;
+    return r;
+}
+
+int s2m_run(liliom_ctx* c, double pose7[7], int match_cnt, int max_num_iter, int mode, liliom_iter_stats* stats,
+            bool want_corr, double out29[29]) {
+    if (!c->map_ready) return LILIOM_E_NOMAP;
+    if (c->map_n_global < 10) return LILIOM_E_FEWMAP;          // L/src/LidarOdometry.cpp:485-488
+    const int n = c->n_feats;
+    if (match_cnt < 0) return LILIOM_E_ARG;
+    const int iters = match_cnt;
+    const int rounds = pick_rounds(n, c->sm_count);
+    const int per_task = 4 * rounds;
+    const int ntasks = cdiv(n, per_task);
+    int grid = min(max(cdiv(ntasks, kWarps), 1), c->sm_count * 12);
+
+    LILI_CUDA(c, c->pose_dev.ensure(16 * sizeof(double)));
+    LILI_CUDA(c, c->partials.ensure((size_t)grid * kNormEq * sizeof(double)));
+    LILI_CUDA(c, c->neq.ensure(32 * sizeof(double)));
+    LILI_CUDA(c, c->stats_dev.ensure((size_t)(iters + 1) * kStatsDoubles * sizeof(double)));
+    if (!c->counter.p) {
+        LILI_CUDA(c, c->counter.ensure(64));
+        LILI_CUDA(c, cudaMemsetAsync(c->counter.p, 0, 64, c->stream));
+    }
+    const bool need_corr = want_corr || mode == LILIOM_MODE_CERES;
+    if (need_corr) {
+        LILI_CUDA(c, c->corr_valid.ensure((size_t)n + 16));
+        LILI_CUDA(c, c->corr_plane.ensure((size_t)n * sizeof(float4) + 16));
+    }
+    if (want_corr) {
+        LILI_CUDA(c, c->nn_idx.ensure((size_t)n * 5 * sizeof(int) + 16));
+        LILI_CUDA(c, c->nn_sqd.ensure((size_t)n * 5 * sizeof(float) + 16));
+        LILI_CUDA(c, cudaMemsetAsync(c->nn_idx.p, 0xff, (size_t)n * 5 * sizeof(int), c->stream));
+        LILI_CUDA(c, cudaMemsetAsync(c->nn_sqd.p, 0x7f, (size_t)n * 5 * sizeof(float), c->stream));
+    }
+    LILI_CUDA(c, cudaMemcpyAsync(c->pose_dev.p, pose7, 7 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+
+    KnnArgs a{};
+    a.feats = c->feats.as<float4>(); a.n = n;
+    a.map = c->map_sorted.as<float4>(); a.cell_start = c->cell_start.as<int>(); a.g = c->grid;
+    a.pose = c->pose_dev.as<double>(); a.pose_out = c->pose_dev.as<double>();
+    a.max_sqd = c->prm.knn_max_sqdist; a.plane_thres = c->prm.plane_thres; a.w_gate = c->prm.weight_gate; a.huber_a = c->prm.huber_a;
+    a.valid = need_corr ? c->corr_valid.as<unsigned char>() : nullptr;
+    a.plane = need_corr ? c->corr_plane.as<float4>() : nullptr;
+    a.nn_idx = want_corr ? c->nn_idx.as<int>() : nullptr;
+    a.nn_sqd = want_corr ? c->nn_sqd.as<float>() : nullptr;
+    a.partials = c->partials.as<double>(); a.neq = c->neq.as<double>();
+    a.ticket = c->counter.as<unsigned int>();
+    a.cand_total = reinterpret_cast<unsigned long long*>(c->counter.as<unsigned char>() + 16);
+    a.rounds = rounds; a.nranks = c->nranks; a.rank = c->rank;
+
+    const int launches = (iters == 0 && want_corr) ? 1 : iters;
+    for (int it = 0; it < launches; ++it) {
+        a.stats = c->stats_dev.as<double>() + (size_t)it * kStatsDoubles;
+        const bool multi = c->nranks > 1;
+        a.update_pose = (mode == LILIOM_MODE_GN && !multi && iters > 0) ? 1 : 0;
+        size_t ev = 0;
+        if (c->time_kernels) {
+            if (c->ev_used + 2 > c->ev_pool.size()) {
+                for (int k = 0; k < 64; ++k) { cudaEvent_t e; LILI_CUDA(c, cudaEventCreate(&e)); c->ev_pool.push_back(e); }
+            }
+            ev = c->ev_used; c->ev_used += 2;
+            LILI_CUDA(c, cudaEventRecord(c->ev_pool[ev], c->stream));
+        }
+        k_knn_plane<<<grid, kBlock, 0, c->stream>>>(a);
+        LILI_TRY(launch_check(c, "k_knn_plane"));
+        if (c->time_kernels) {
+            LILI_CUDA(c, cudaEventRecord(c->ev_pool[ev + 1], c->stream));
+            c->ev_pending.push_back({ev, (unsigned long long)n});
+        }
+        if (iters == 0) break;
+        if (multi) LILI_TRY(nccl_allreduce_sum_f64(c, c->neq.as<double>(), kNormEq));
+        if (mode == LILIOM_MODE_GN) {
+            if (multi) {
+                k_gn_update<<<1, 32, 0, c->stream>>>(c->neq.as<double>(), c->pose_dev.as<double>(), a.stats);
+                LILI_TRY(launch_check(c, "k_gn_update"));
+            }
+        } else {
+            LmArgs l{};
+            l.feats = a.feats; l.valid = a.valid; l.plane = a.plane; l.n = n;
+            l.pose = c->pose_dev.as<double>(); l.stats = a.stats; l.huber_a = a.huber_a; l.max_num_iter = max_num_iter;
+            l.neq0 = c->neq.as<double>();
+            if (multi) { c->last_error = "CERES mode is single-GPU (the LM solve is one block); use GN mode with a communicator"; return LILIOM_E_ARG; }
+            k_lm_solve<<<1, kLmBlock, 0, c->stream>>>(l);
+            LILI_TRY(launch_check(c, "k_lm_solve"));
+        }
+    }
+    // ---- results: pose + stats in one pinned block
+    double* hp = reinterpret_cast<double*>(c->h_pin);
+    LILI_CUDA(c, cudaMemcpyAsync(hp, c->pose_dev.p, 7 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (out29) LILI_CUDA(c, cudaMemcpyAsync(hp + 8, c->neq.p, kNormEq * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    const bool want_stats = stats && iters > 0;
+    if (want_stats) {
+        size_t bytes = (size_t)iters * kStatsDoubles * sizeof(double);
+        if (64 * sizeof(double) + bytes > c->h_pin_bytes) return LILIOM_E_CAPACITY;
+        LILI_CUDA(c, cudaMemcpyAsync(hp + 64, c->stats_dev.p, bytes, cudaMemcpyDeviceToHost, c->stream));
+    }
+    LILI_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (iters > 0) for (int k = 0; k < 7; ++k) pose7[k] = hp[k];
+    if (out29) for (int k = 0; k < kNormEq; ++k) out29[k] = hp[8 + k];
+    if (want_stats) {
+        for (int it = 0; it < iters; ++it) {
+            const double* s = hp + 64 + (size_t)it * kStatsDoubles;
+            stats[it].n_corr = (int)s[0]; stats[it].lm_iters = (int)s[1]; stats[it].cost = s[2];
+            for (int k = 0; k < 27; ++k) stats[it].jtj_jtr[k] = s[3 + k];
+            for (int k = 0; k < 7; ++k) stats[it].pose7[k] = s[30 + k];
+        }
+    }
+    // fold finished kernel timings into the counters
+    if (c->time_kernels) {
+        for (auto& pr : c->ev_pending) {
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, c->ev_pool[pr.first], c->ev_pool[pr.first + 1]) == cudaSuccess) {
+                c->cnt.knn_ms += ms; c->cnt.knn_launches++; c->cnt.knn_queries += pr.second;
+            }
+        }
+        c->ev_pending.clear();
+        c->ev_used = 0;
+    }
+    return LILIOM_OK;
+}
+
+}  // namespace lili

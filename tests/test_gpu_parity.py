@@ -1,0 +1,263 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on identical inputs.
+Bit-exact for index / label / fp32-cloud outputs, tolerance for fp64 reductions and poses
+(BASELINE.json: pose within 1e-4 m / 1e-4 rad at equal iteration count)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _fields_equal(a, b, fields):
+    assert len(a) == len(b), (len(a), len(b))
+    for f in fields:
+        fa, fb = a[f].view(np.uint32), b[f].view(np.uint32)
+        bad = np.nonzero(fa != fb)[0]
+        assert len(bad) == 0, f"field {f}: {len(bad)} of {len(a)} differ, first at {bad[:5]}: {a[f][bad[:5]]} vs {b[f][bad[:5]]}"
+
+
+def _rot_angle(qa, qb):
+    qa = np.asarray(qa) / np.linalg.norm(qa); qb = np.asarray(qb) / np.linalg.norm(qb)
+    return 2.0 * np.arccos(min(1.0, abs(float(np.dot(qa, qb)))))
+
+
+def _pose_close(a, b, tol_t=1e-4, tol_r=1e-4):
+    assert np.linalg.norm(np.asarray(a)[4:] - np.asarray(b)[4:]) < tol_t, (a, b)
+    assert _rot_angle(a[:4], b[:4]) < tol_r, (a, b)
+
+
+# ---------------------------------------------------------------- VoxelGrid
+@pytest.mark.parametrize("leaf", [0.4, 0.6])
+def test_voxelgrid_pt48_bit_exact(ctx48, oracle, world_small, leaf):
+    surf, _, _ = oracle.extract_horizon(world_small["hz"], world_small["q_hz"])
+    want = oracle.voxelgrid(surf, leaf)
+    got = ctx48.voxelgrid(surf, leaf)
+    _fields_equal(got, want, ["x", "y", "z", "nx", "ny", "nz", "intensity", "curvature"])
+
+
+def test_voxelgrid_pt32_bit_exact(ctx32, oracle, world_small):
+    pts = world_small["hdl"][:40000]
+    want = oracle.voxelgrid(pts, 0.6)
+    got = ctx32.voxelgrid(pts, 0.6)
+    _fields_equal(got, want, ["x", "y", "z", "intensity"])
+
+
+def test_voxelgrid_edge_cases(ctx48, oracle):
+    import liliom_b200 as L
+    assert len(ctx48.voxelgrid(np.zeros(0, L.PT48), 0.4)) == 0
+    one = np.zeros(1, L.PT48); one["x"] = 1.5; one["nx"] = 2.0; one["intensity"] = 3.0
+    _fields_equal(ctx48.voxelgrid(one, 0.4), oracle.voxelgrid(one, 0.4), ["x", "y", "z", "nx", "intensity"])
+    # overflow of the int32 voxel index: PCL returns the input unchanged
+    far = np.zeros(3, L.PT48); far["x"] = [0.0, 1e6, -1e6]; far["y"] = [0, 1e6, 5]; far["z"] = [0, 3e5, 9]
+    got, want = ctx48.voxelgrid(far, 0.01), oracle.voxelgrid(far, 0.01)
+    assert len(want) == 3
+    _fields_equal(got, want, ["x", "y", "z"])
+    # non-finite points are dropped
+    nf = np.zeros(4, L.PT48); nf["x"] = [0.1, np.nan, 0.2, np.inf]
+    _fields_equal(ctx48.voxelgrid(nf, 0.4), oracle.voxelgrid(nf, 0.4), ["x", "y", "z"])
+
+
+# ---------------------------------------------------------------- scan-to-map
+@pytest.fixture(scope="module")
+def s2m_case(ctx48, oracle, world_small):
+    surf, _, _ = oracle.extract_horizon(world_small["hz"], world_small["q_hz"])
+    ds = oracle.voxelgrid(surf, 0.4)
+    tree = oracle.KdTree(world_small["map"])
+    ctx48.map_set_points(world_small["map"])
+    return dict(surf=surf, ds=ds, tree=tree)
+
+
+def test_map_download_roundtrip(ctx48, world_small, s2m_case):
+    got = ctx48.map_download()
+    assert got.shape == world_small["map"].shape
+    assert np.array_equal(got[:, :3].view(np.uint32), world_small["map"][:, :3].view(np.uint32))
+
+
+@pytest.mark.parametrize("which", ["ds", "surf"])
+def test_knn_and_correspondences_exact(ctx48, oracle, world_small, s2m_case, which):
+    feats = s2m_case[which]
+    pose = world_small["guess"]
+    cnt, valid_o, plane_o, idx_o, pw_o = oracle.find_surf_corr(s2m_case["tree"], feats, pose)
+    valid, plane, idx, sqd, s29 = ctx48.find_surf_corr(feats, pose)
+    # (a) 5-NN index sets: exact wherever the oracle's 5th neighbour is inside the 1 m ball
+    _, sqd_o = s2m_case["tree"].knn5(pw_o)
+    inside = sqd_o[:, 4] < 1.0
+    assert inside.sum() > 0.5 * len(feats)
+    assert np.array_equal(idx[inside], idx_o[inside])
+    assert np.array_equal(sqd[inside].view(np.uint32), sqd_o[inside].view(np.uint32))
+    # (b) accept/reject decisions and weighted planes
+    assert np.array_equal(valid, valid_o)
+    assert int(valid.sum()) == cnt and cnt > 100
+    np.testing.assert_allclose(plane, plane_o, rtol=2e-6, atol=1e-7)
+    # (c) the 27 normal-equation scalars + cost + count (fp64 reduction order differs)
+    want = oracle.normal_equations(feats, valid_o, plane_o, pose)
+    np.testing.assert_allclose(s29, want, rtol=1e-9, atol=1e-9)
+
+
+def test_scan_to_map_gn_pose(ctx48, oracle, world_small, s2m_case):
+    rc, pose_o, st_o = oracle.scan_to_map_gn(s2m_case["tree"], s2m_case["ds"], world_small["guess"], 10)
+    pose, st = ctx48.scan_to_map(s2m_case["ds"], world_small["guess"], 10, mode=1)
+    assert rc == 0
+    for a, b in zip(st, st_o):
+        assert abs(a.n_corr - b.n_corr) <= 2
+        _pose_close(np.array(a.pose7), np.array(b.pose7))
+    np.testing.assert_allclose(np.array(st[0].jtj_jtr), np.array(st_o[0].jtj_jtr), rtol=1e-9, atol=1e-9)
+    _pose_close(pose, pose_o)
+    _pose_close(pose, world_small["T"], tol_t=0.02, tol_r=0.01)   # and it is the right answer
+
+
+def test_scan_to_map_ceres_pose(ctx48, oracle, world_small, s2m_case):
+    rc, pose_o, st_o = oracle.scan_to_map_ceres(s2m_case["tree"], s2m_case["ds"], world_small["guess"], 2, 15)
+    pose, st = ctx48.scan_to_map(s2m_case["ds"], world_small["guess"], 2, max_num_iter=15, mode=0)
+    assert [s.lm_iters for s in st] == [s.lm_iters for s in st_o]
+    assert [s.n_corr for s in st] == [s.n_corr for s in st_o]
+    _pose_close(pose, pose_o)
+
+
+def test_few_map_points_leaves_pose(ctx48, world_small):
+    import liliom_b200 as L
+    c = L.Context(variant=0)
+    c.map_set_points(world_small["map"][:5])
+    with pytest.raises(L.LiliomError) as e:
+        c.scan_to_map(world_small["map"][:100], world_small["guess"], 2)
+    assert e.value.code == -3
+    c.close()
+
+
+def test_map_lifecycle_matches_reference_pipeline(oracle, world_small):
+    """push_frame (transformCloud) + FIFO + VoxelGrid(0.4) == oracle concat + voxelgrid."""
+    import liliom_b200 as L
+    c = L.Context(variant=0)
+    c.params.max_map_frames  # default 20
+    surf, _, _ = oracle.extract_horizon(world_small["hz"], world_small["q_hz"])
+    ds = oracle.voxelgrid(surf, 0.4)
+    rng = np.random.default_rng(5)
+    frames = []
+    for k in range(23):
+        pose = np.array(world_small["T"]); pose[4] += 0.3 * k; pose[5] += 0.05 * k
+        sub = ds[rng.permutation(len(ds))[: len(ds) // 2]]
+        c.map_push_frame(sub, pose)
+        frames.append(oracle.transform_cloud(sub, pose))
+    m = c.map_rebuild()
+    want = oracle.voxelgrid(np.concatenate(frames[-20:]), 0.4)
+    got = c.map_download()
+    assert m == len(want) == len(got)
+    assert np.array_equal(got[:, 0].view(np.uint32), want["x"].view(np.uint32))
+    assert np.array_equal(got[:, 2].view(np.uint32), want["z"].view(np.uint32))
+    c.close()
+
+
+# ---------------------------------------------------------------- extractors
+def test_horizon_extract_bit_exact(ctx48, oracle, world_small):
+    surf_o, edge_o, cut_o = oracle.extract_horizon(world_small["hz"], world_small["q_hz"])
+    surf, edge, cut = ctx48.extract_horizon(world_small["hz"], world_small["q_hz"])
+    F = ["x", "y", "z", "nx", "ny", "nz", "intensity", "curvature"]
+    _fields_equal(cut, cut_o, F)
+    _fields_equal(edge, edge_o, F)
+    _fields_equal(surf, surf_o, F)
+    assert len(surf) > 5000 and len(edge) > 10
+
+
+def test_horizon_extract_edge_cases(ctx48, oracle, world_small):
+    import liliom_b200 as L
+    F = ["x", "y", "z", "nx", "ny", "nz", "intensity", "curvature"]
+    pts = world_small["hz"].copy()
+    pts["x"][::97] = np.nan                   # removeNaN
+    pts["x"][5::131] = 0.01; pts["y"][5::131] = 0.0; pts["z"][5::131] = 0.0   # removeClosedPointCloud
+    pts["curvature"][7::53] = 0.0             # reflectivity gate
+    pts["intensity"][11::211] = -1.0          # scan_id < 0
+    pts["intensity"][13::223] = 6.02          # scan_id >= N_SCANS (reference UB, guarded in both)
+    q = np.array([1.0, 0.001, -0.002, 0.01])
+    for a, b in zip(ctx48.extract_horizon(pts, q), oracle.extract_horizon(pts, q)):
+        _fields_equal(a, b, F)
+    empty = np.zeros(0, L.PT48)
+    s, e, c = ctx48.extract_horizon(empty, q)
+    assert len(s) == len(e) == len(c) == 0
+    # NaN q_iMU resets to identity (Preprocessing.cpp:232-234)
+    qn = np.array([np.nan, 0, 0, 0])
+    for a, b in zip(ctx48.extract_horizon(world_small["hz"], qn), oracle.extract_horizon(world_small["hz"], qn)):
+        _fields_equal(a, b, F)
+
+
+@pytest.mark.parametrize("ds_rate", [1, 4])
+def test_rot_extract_bit_exact(oracle, world_small, ds_rate):
+    import liliom_b200 as L
+    p = L.default_params(1)
+    p.ds_rate = ds_rate
+    c = L.Context(p)
+    q_lb = np.array([0.999, 0.01, -0.02, 0.03]); q_lb /= np.linalg.norm(q_lb)
+    rc, surf_o, edge_o, cut_o, lab_o, cur_o = oracle.extract_rot(world_small["hdl"], world_small["q_hdl"], q_lb, 64, ds_rate)
+    surf, edge, cut = c.extract_rot(world_small["hdl"], world_small["q_hdl"], q_lb)
+    lab, cur = c.extract_rot_labels(len(cut))
+    F = ["x", "y", "z", "intensity"]
+    _fields_equal(cut, cut_o, F)
+    assert np.array_equal(cur.view(np.uint32), cur_o.view(np.uint32))
+    assert np.array_equal(lab, lab_o)
+    _fields_equal(edge, edge_o, F)
+    _fields_equal(surf, surf_o, F)
+    assert len(edge) > 50 and len(surf) > 1000
+    c.close()
+
+
+def test_rot_extract_16_lines_and_errors(oracle, world_small):
+    import liliom_b200 as L
+    p = L.default_params(1); p.line_num = 16; p.ds_rate = 1
+    c = L.Context(p)
+    pts = world_small["hdl"][::3].copy()
+    rc, surf_o, edge_o, cut_o, lab_o, cur_o = oracle.extract_rot(pts, world_small["q_hdl"], (1, 0, 0, 0), 16, 1)
+    surf, edge, cut = c.extract_rot(pts, world_small["q_hdl"])
+    F = ["x", "y", "z", "intensity"]
+    _fields_equal(cut, cut_o, F); _fields_equal(edge, edge_o, F); _fields_equal(surf, surf_o, F)
+    c.close()
+    p.line_num = 20
+    c = L.Context(p)
+    with pytest.raises(L.LiliomError) as e:
+        c.extract_rot(pts, world_small["q_hdl"])
+    assert e.value.code == -6
+    c.close()
+
+
+# ---------------------------------------------------------------- backend kernel reuse
+def test_backend_correspondences(ctx48, oracle, world_small, s2m_case):
+    feats = s2m_case["ds"]
+    pose = world_small["guess"]
+    v_o, pl_o, sc_o = oracle.correspond_surf_backend(s2m_case["tree"], feats, pose, 1.0, 0.1, 0.3, 0.5)
+    v, pl, sc = ctx48.correspond_surf(feats, pose, 1.0, 0.1, 0.3, 0.5)
+    assert np.array_equal(v, v_o) and v.sum() > 100
+    np.testing.assert_allclose(pl, pl_o, rtol=2e-6, atol=1e-7)
+    np.testing.assert_allclose(sc, sc_o, rtol=1e-6)
+    for variant in (0, 1):
+        ve_o, pa_o, pb_o = oracle.correspond_edge(s2m_case["tree"], feats, pose, variant)
+        ve, pa, pb = ctx48.correspond_edge(feats, pose, variant)
+        assert np.array_equal(ve, ve_o)
+        np.testing.assert_allclose(pa, pa_o, rtol=1e-6, atol=1e-6)
+        np.testing.assert_allclose(pb, pb_o, rtol=1e-6, atol=1e-6)
+
+
+# ---------------------------------------------------------------- size-independent properties at BASELINE sizes
+def test_full_size_properties():
+    """1 M-point map, dense 20k-query sweep: (i) kNN equals scipy's exact kd-tree, (ii) GN is
+    deterministic run to run, (iii) the pose error shrinks to the noise floor."""
+    import liliom_b200 as L
+    from liliom_b200 import synth
+    from scipy.spatial import cKDTree
+    m, _ = synth.make_map(1_000_000)
+    T = synth.default_true_pose()
+    hz, q = synth.make_horizon_sweep(T)
+    c = L.Context(variant=0)
+    c.map_set_points(m)
+    surf, edge, cut = c.extract_horizon(hz, q)
+    guess = synth.perturbed_pose(T)
+    valid, plane, idx, sqd, s29 = c.find_surf_corr(surf, guess)
+    # transformed queries via the same fp64 expression (numpy) -> fp32
+    qv = np.asarray(guess[:4]); t = np.asarray(guess[4:])
+    p = np.stack([surf["x"], surf["y"], surf["z"]], 1).astype(np.float64)
+    uv = 2.0 * np.cross(qv[1:], p); pw = (p + qv[0] * uv + np.cross(qv[1:], uv) + t).astype(np.float32)
+    d, ii = cKDTree(m[:, :3].astype(np.float64)).query(pw.astype(np.float64), k=5)
+    inside = d[:, 4] < 0.999
+    same = np.sort(idx[inside], 1) == np.sort(ii[inside].astype(np.int32), 1)
+    assert same.all(1).mean() > 0.9999      # fp64 vs fp32 distance ties may reorder a handful
+    p1, _ = c.scan_to_map(surf, guess, 10, mode=1)
+    p2, _ = c.scan_to_map(surf, guess, 10, mode=1)
+    assert np.array_equal(p1, p2)
+    assert np.linalg.norm(p1[4:] - T[4:]) < 0.02
+    c.close()
