@@ -9,6 +9,8 @@
 
 namespace lili {
 
+constexpr int kLanes = 8;
+
 struct BkArgs {
     const float4* feats; int n;
     const float4* map; const int* cell_start; GridDesc g;
@@ -24,17 +26,17 @@ __global__ void __launch_bounds__(kBlock) k_backend_edge(BkArgs a) {
     const unsigned omask = ((1u << kLanes) - 1u) << (oct * kLanes);
     const int qi = (blockIdx.x * blockDim.x + threadIdx.x) / kLanes;
     if (qi >= a.n) return;   // uniform per octet
-    const float inf = __int_as_float(0x7f800000);
     float4 f = a.feats[qi];
     D3 pw = qrot_x(a.q, D3{(double)f.x, (double)f.y, (double)f.z});
     const float sx = (float)addx(pw.x, a.t.x), sy = (float)addx(pw.y, a.t.y), sz = (float)addx(pw.z, a.t.z);
-    Top5 top{inf, inf, inf, inf, inf, -1, -1, -1, -1, -1};
+    Top5 top;
+    top5_init(top);
     unsigned long long cand = 0;
-    octet_knn5(sx, sy, sz, a.map, a.cell_start, a.g, sub, omask, top, cand);
+    group_knn5<kLanes>(sx, sy, sz, a.map, a.cell_start, a.g, sub, omask, top, cand);
     if (sub != 0) return;
     bool ok = false;
     float A3[3] = {0, 0, 0}, B3[3] = {0, 0, 0};
-    if (top.p4 >= 0 && (double)top.d4 < 1.0) {                                        // L:1543
+    if (top.p4 >= 0 && (double)top5_dist(top.k4) < 1.0) {                                        // L:1543
         const int pos[5] = {top.p0, top.p1, top.p2, top.p3, top.p4};
         double px[5], py[5], pz[5], cx = 0, cy = 0, cz = 0;
         for (int j = 0; j < 5; ++j) {
@@ -80,18 +82,18 @@ __global__ void __launch_bounds__(kBlock) k_backend_surf(BkArgs a) {
     const unsigned omask = ((1u << kLanes) - 1u) << (oct * kLanes);
     const int qi = (blockIdx.x * blockDim.x + threadIdx.x) / kLanes;
     if (qi >= a.n) return;
-    const float inf = __int_as_float(0x7f800000);
     float4 f = a.feats[qi];
     D3 pw = qrot_x(a.q, D3{(double)f.x, (double)f.y, (double)f.z});
     const float sx = (float)addx(pw.x, a.t.x), sy = (float)addx(pw.y, a.t.y), sz = (float)addx(pw.z, a.t.z);
-    Top5 top{inf, inf, inf, inf, inf, -1, -1, -1, -1, -1};
+    Top5 top;
+    top5_init(top);
     unsigned long long cand = 0;
-    octet_knn5(sx, sy, sz, a.map, a.cell_start, a.g, sub, omask, top, cand);
+    group_knn5<kLanes>(sx, sy, sz, a.map, a.cell_start, a.g, sub, omask, top, cand);
     if (sub != 0) return;
     bool ok = false;
     float4 pl = make_float4(0, 0, 0, 0);
     double sc = 0;
-    if (top.p4 >= 0 && (double)top.d4 < a.max_sqd) {                                   // R:1476
+    if (top.p4 >= 0 && (double)top5_dist(top.k4) < a.max_sqd) {                                   // R:1476
         const int pos[5] = {top.p0, top.p1, top.p2, top.p3, top.p4};
         double A[5][3], B[5];
         float4 m[5];

@@ -112,6 +112,7 @@ struct liliom_ctx {
     // ---- instrumentation ----
     liliom_counters cnt{};
     bool time_kernels = false;
+    int force_lanes = 0, force_rounds = 0;   // tuning override (LILIOM_KNN_LANES / LILIOM_KNN_ROUNDS)
     std::vector<cudaEvent_t> ev_pool;
     size_t ev_used = 0;
     std::vector<std::pair<size_t, unsigned long long>> ev_pending;  // (event pair index, queries)

@@ -330,30 +330,111 @@ __device__ inline void colpiv_qr_solve_5x3(double A[5][3], double b[5], double x
     }
 }
 
-// 6x6 SPD solve (LDL^T), H given as the 21-scalar upper triangle (row-major), rhs b. Returns false on a non-finite / zero pivot.
-__device__ inline bool solve6_ldlt(const double* s21, const double* rhs, double x[6]) {
+// ---------------------------------------------------------------------------------------
+// Fast path of the same least-squares plane  min || A n + 1 ||  (A = the 5 neighbours):
+// with c = centroid, q_j = p_j - c and S = sum q_j q_j^T,   A^T A = S + 5 c c^T,  A^T 1 = 5 c,
+// so by Sherman-Morrison   n = -5 u / (1 + 5 c.u),   u = S^-1 c.
+// S is built from CENTRED coordinates (differences of fp32 values are exact in fp64), so its
+// conditioning is the patch's own spread ratio (~1e3..1e6) instead of (|p|/spread)^2 of the
+// raw normal equations; a 3x3 LDL^T (stable for SPD without pivoting) then gives the same
+// minimiser as the Householder QR to ~1e-12 relative, in ~1/8 of the fp64 instructions.
+// Returns false when S is numerically singular (collinear / coincident / exactly coplanar
+// neighbours): the caller then takes the rank-revealing QR path, which reproduces Eigen's
+// behaviour for those cases.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ bool plane_fit5_fast(const float4 m[5], double nv[3]) {
+    const double cx = ((double)m[0].x + (double)m[1].x + (double)m[2].x + (double)m[3].x + (double)m[4].x) * 0.2;
+    const double cy = ((double)m[0].y + (double)m[1].y + (double)m[2].y + (double)m[3].y + (double)m[4].y) * 0.2;
+    const double cz = ((double)m[0].z + (double)m[1].z + (double)m[2].z + (double)m[3].z + (double)m[4].z) * 0.2;
+    double s00 = 0, s01 = 0, s02 = 0, s11 = 0, s12 = 0, s22 = 0;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+        const double qx = (double)m[j].x - cx, qy = (double)m[j].y - cy, qz = (double)m[j].z - cz;
+        s00 += qx * qx; s01 += qx * qy; s02 += qx * qz; s11 += qy * qy; s12 += qy * qz; s22 += qz * qz;
+    }
+    const double tr = s00 + s11 + s22;
+    const double tiny = 1e-9 * tr;
+    // LDL^T of S
+    const double d0 = s00;
+    if (!(d0 > tiny)) return false;
+    const double i0 = 1.0 / d0;
+    const double l10 = s01 * i0, l20 = s02 * i0;
+    const double d1 = s11 - l10 * s01;
+    if (!(d1 > tiny)) return false;
+    const double i1 = 1.0 / d1;
+    const double t21 = s12 - l20 * s01;
+    const double l21 = t21 * i1;
+    const double d2 = s22 - l20 * s02 - l21 * t21;
+    if (!(d2 > tiny)) return false;
+    // u = S^-1 c
+    const double y0 = cx, y1 = cy - l10 * y0, y2 = cz - l20 * y0 - l21 * y1;
+    const double z2 = y2 / d2;
+    const double z1 = y1 * i1 - l21 * z2;
+    const double z0 = y0 * i0 - l10 * z1 - l20 * z2;
+    const double den = 1.0 + 5.0 * (cx * z0 + cy * z1 + cz * z2);
+    const double sc = -5.0 / den;
+    nv[0] = sc * z0; nv[1] = sc * z1; nv[2] = sc * z2;
+    return isfinite(nv[0]) && isfinite(nv[1]) && isfinite(nv[2]);
+}
+
+static __device__ __noinline__ void plane_fit5_qr(const float4 m[5], double nv[3]) {
+    double A[5][3], B[5];
+#pragma unroll
+    for (int j = 0; j < 5; ++j) { A[j][0] = m[j].x; A[j][1] = m[j].y; A[j][2] = m[j].z; B[j] = -1.0; }
+    colpiv_qr_solve_5x3(A, B, nv);
+}
+
+// 6x6 SPD solve (LDL^T), H given as the 21-scalar upper triangle (row-major), rhs b.
+// Fully unrolled so that every array lives in registers: this runs on ONE thread at the tail of
+// the iteration kernel, where local-memory round trips would be pure exposed latency.
+// Returns false on a non-finite / zero pivot.
+__device__ __forceinline__ bool solve6_ldlt(const double* s21, const double* rhs, double x[6]) {
     double H[6][6];
-    int k = 0;
-    for (int a = 0; a < 6; ++a) for (int b = a; b < 6; ++b) { H[a][b] = s21[k]; H[b][a] = s21[k]; ++k; }
+    {
+        int k = 0;
+#pragma unroll
+        for (int a = 0; a < 6; ++a)
+#pragma unroll
+            for (int b = a; b < 6; ++b) { H[a][b] = s21[k]; H[b][a] = s21[k]; ++k; }
+    }
     double L[6][6], D[6];
+    bool ok = true;
+#pragma unroll
     for (int j = 0; j < 6; ++j) {
         double d = H[j][j];
+#pragma unroll
         for (int m = 0; m < j; ++m) d -= L[j][m] * L[j][m] * D[m];
-        if (!(fabs(d) > 1e-300) || !isfinite(d)) return false;
+        if (!(fabs(d) > 1e-300) || !isfinite(d)) ok = false;
         D[j] = d;
-        L[j][j] = 1;
+        const double inv = 1.0 / d;
+#pragma unroll
         for (int i = j + 1; i < 6; ++i) {
             double s = H[i][j];
+#pragma unroll
             for (int m = 0; m < j; ++m) s -= L[i][m] * L[j][m] * D[m];
-            L[i][j] = s / d;
+            L[i][j] = s * inv;
         }
     }
     double y[6];
-    for (int i = 0; i < 6; ++i) { double s = rhs[i]; for (int m = 0; m < i; ++m) s -= L[i][m] * y[m]; y[i] = s; }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        double s = rhs[i];
+#pragma unroll
+        for (int m = 0; m < i; ++m) s -= L[i][m] * y[m];
+        y[i] = s;
+    }
+#pragma unroll
     for (int i = 0; i < 6; ++i) y[i] /= D[i];
-    for (int i = 5; i >= 0; --i) { double s = y[i]; for (int m = i + 1; m < 6; ++m) s -= L[m][i] * x[m]; x[i] = s; }
-    for (int i = 0; i < 6; ++i) if (!isfinite(x[i])) return false;
-    return true;
+#pragma unroll
+    for (int i = 5; i >= 0; --i) {
+        double s = y[i];
+#pragma unroll
+        for (int m = i + 1; m < 6; ++m) s -= L[m][i] * x[m];
+        x[i] = s;
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) if (!isfinite(x[i])) ok = false;
+    return ok;
 }
 
 // ceres::QuaternionParameterization::Plus on q, identity on t.

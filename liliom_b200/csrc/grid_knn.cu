@@ -177,90 +177,102 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
-__global__ void __launch_bounds__(kBlock) k_knn_plane(KnnArgs a) {
+// Per-query scratch a warp keeps in shared memory between the phases.
+struct Slot {
+    int   pos[5];            // neighbour positions in the cell-sorted map; pos[0] < 0: no 5-NN inside the radius
+    float sx, sy, sz;        // transformed query (fp32, as the kd-tree saw it)
+};
+struct Row { double J[6]; double r; double half_rho; };   // robustified Jacobian row, residual, rho/2
+
+// scalar k of the 29-vector is  sum_i row.J[kA[k]] * row.X[kB[k]]  (X = J for k<21, r for 21..26)
+__constant__ unsigned char kPairA[27] = {0,0,0,0,0,0, 1,1,1,1,1, 2,2,2,2, 3,3,3, 4,4, 5, 0,1,2,3,4,5};
+__constant__ unsigned char kPairB[27] = {0,1,2,3,4,5, 1,2,3,4,5, 2,3,4,5, 3,4,5, 4,5, 5, 6,6,6,6,6,6};
+
+__device__ __forceinline__ double q_t7(const Q4& q, const D3& t, int k) {
+    return k == 0 ? q.w : k == 1 ? q.x : k == 2 ? q.y : k == 3 ? q.z : k == 4 ? t.x : k == 5 ? t.y : t.z;
+}
+
+template <int LANES>
+__global__ void __launch_bounds__(kBlock, 2) k_knn_plane(KnnArgs a) {
+    constexpr int GROUPS = 32 / LANES;                 // queries a warp searches concurrently
     __shared__ Slot slots[kWarps][32];
+    __shared__ __align__(16) Row rows[kWarps][32];
+    __shared__ unsigned char rvalid[kWarps][32];
     __shared__ double red[kWarps][kNormEq];
     __shared__ unsigned long long red_cand[kWarps];
     __shared__ bool is_last;
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    const int sub = lane & (kLanes - 1);          // lane within the octet
-    const int oct = lane / kLanes;                // octet within the warp (0..3)
-    const unsigned omask = ((1u << kLanes) - 1u) << (oct * kLanes);
+    const int sub = lane & (LANES - 1);
+    const int grp = lane / LANES;
+    const unsigned gmask = (LANES == 32) ? 0xffffffffu : (((1u << LANES) - 1u) << (grp * LANES));
 
-    Q4 q{a.pose[0], a.pose[1], a.pose[2], a.pose[3]};
-    D3 t{a.pose[4], a.pose[5], a.pose[6]};
+    const Q4 q{a.pose[0], a.pose[1], a.pose[2], a.pose[3]};
+    const D3 t{a.pose[4], a.pose[5], a.pose[6]};
 
-    double acc[kNormEq];
-#pragma unroll
-    for (int k = 0; k < kNormEq; ++k) acc[k] = 0.0;
+    // lane k (< 29) owns scalar k of the normal equations: no per-lane 29-vector, no final shuffle tree
+    double acc = 0.0;
+    const int pa = lane < 27 ? kPairA[lane] : 0, pb = lane < 27 ? kPairB[lane] : 0;
     unsigned long long cand = 0;
 
-    const int per_task = 4 * a.rounds;
+    const int per_task = GROUPS * a.rounds;            // <= 32
     const int ntasks = (a.n + per_task - 1) / per_task;
     const int gw = blockIdx.x * kWarps + warp;
     const int nw = gridDim.x * kWarps;
-    const float inf = __int_as_float(0x7f800000);
 
+#pragma unroll 1
     for (int task = gw; task < ntasks; task += nw) {
-        // ---------------- phase A: cooperative exact 5-NN, one query per octet per round
+        // ---------------- phase A: cooperative exact 5-NN, one query per lane group per round
+#pragma unroll 1
         for (int r = 0; r < a.rounds; ++r) {
-            const int slot = r * 4 + oct;
+            const int slot = r * GROUPS + grp;
             const int qi = task * per_task + slot;
-            Top5 top{inf, inf, inf, inf, inf, -1, -1, -1, -1, -1};
+            Top5 top;
+            top5_init(top);
             float sx = 0.f, sy = 0.f, sz = 0.f;
             bool live = qi < a.n;
             if (live) {
-                float4 f = a.feats[qi];
-                D3 pw = qrot_x(q, D3{(double)f.x, (double)f.y, (double)f.z});      // L/src/LidarOdometry.cpp:230-231
+                const float4 f = a.feats[qi];
+                const D3 pw = qrot_x(q, D3{(double)f.x, (double)f.y, (double)f.z});             // L/src/LidarOdometry.cpp:230-231
                 sx = (float)addx(pw.x, t.x); sy = (float)addx(pw.y, t.y); sz = (float)addx(pw.z, t.z);   // :236-238
                 if (a.nranks > 1 && owner_of(sx, sy, sz, a.nranks) != a.rank) live = false;
             }
-            if (live) {
-                octet_knn5(sx, sy, sz, a.map, a.cell_start, a.g, sub, omask, top, cand);
-            }
-            // every lane of a warp must reach the shuffles above together: `live` is uniform
-            // inside an octet and the shuffle masks are per-octet, so divergence between octets is safe.
+            // `live` is uniform inside a lane group and the shuffles are masked per group
+            if (live) group_knn5<LANES>(sx, sy, sz, a.map, a.cell_start, a.g, sub, gmask, top, cand);
             if (sub == 0) {
                 Slot& s = slots[warp][slot];
-                bool ok = live && top.p4 >= 0 && ((double)top.d4 < a.max_sqd);      // :365
+                const bool ok = live && top.p4 >= 0 && ((double)top5_dist(top.k4) < a.max_sqd);  // :365
                 s.pos[0] = ok ? top.p0 : -1; s.pos[1] = top.p1; s.pos[2] = top.p2; s.pos[3] = top.p3; s.pos[4] = top.p4;
                 s.sx = sx; s.sy = sy; s.sz = sz;
                 if (live && a.nn_idx) {
-                    int o5 = qi * 5;
-                    a.nn_idx[o5 + 0] = top.p0 >= 0 ? __float_as_int(a.map[top.p0].w) : -1;
-                    a.nn_idx[o5 + 1] = top.p1 >= 0 ? __float_as_int(a.map[top.p1].w) : -1;
-                    a.nn_idx[o5 + 2] = top.p2 >= 0 ? __float_as_int(a.map[top.p2].w) : -1;
-                    a.nn_idx[o5 + 3] = top.p3 >= 0 ? __float_as_int(a.map[top.p3].w) : -1;
-                    a.nn_idx[o5 + 4] = top.p4 >= 0 ? __float_as_int(a.map[top.p4].w) : -1;
+                    int* o = a.nn_idx + (size_t)qi * 5;
+                    o[0] = top.p0 >= 0 ? top5_orig(top.k0) : -1; o[1] = top.p1 >= 0 ? top5_orig(top.k1) : -1;
+                    o[2] = top.p2 >= 0 ? top5_orig(top.k2) : -1; o[3] = top.p3 >= 0 ? top5_orig(top.k3) : -1;
+                    o[4] = top.p4 >= 0 ? top5_orig(top.k4) : -1;
                 }
                 if (live && a.nn_sqd) {
-                    int o5 = qi * 5;
-                    a.nn_sqd[o5 + 0] = top.d0; a.nn_sqd[o5 + 1] = top.d1; a.nn_sqd[o5 + 2] = top.d2;
-                    a.nn_sqd[o5 + 3] = top.d3; a.nn_sqd[o5 + 4] = top.d4;
+                    float* o = a.nn_sqd + (size_t)qi * 5;
+                    o[0] = top5_dist(top.k0); o[1] = top5_dist(top.k1); o[2] = top5_dist(top.k2); o[3] = top5_dist(top.k3); o[4] = top5_dist(top.k4);
                 }
             }
         }
         __syncwarp();
         // ---------------- phase B: one lane per query — plane fit, gates, residual, Jacobian row
+        bool ok = false;
         if (lane < per_task) {
             const int qi = task * per_task + lane;
             const Slot s = slots[warp][lane];
-            bool ok = false;
             float pl0 = 0.f, pl1 = 0.f, pl2 = 0.f, pl3 = 0.f;
             if (qi < a.n && s.pos[0] >= 0) {
-                double A[5][3], B[5];
                 float4 m[5];
 #pragma unroll
-                for (int j = 0; j < 5; ++j) m[j] = __ldg(a.map + s.pos[j]);
-#pragma unroll
-                for (int j = 0; j < 5; ++j) { A[j][0] = m[j].x; A[j][1] = m[j].y; A[j][2] = m[j].z; B[j] = -1.0; }   // :363,369-371
+                for (int j = 0; j < 5; ++j) m[j] = __ldg(a.map + s.pos[j]);                                          // :369-371
                 double nv[3];
-                colpiv_qr_solve_5x3(A, B, nv);                                                                        // :375
-                double n2 = nv[0] * nv[0] + nv[1] * nv[1] + nv[2] * nv[2];
-                double nn = sqrt(n2);
-                double normInverse = 1.0 / nn;                                                                        // :376
+                if (!plane_fit5_fast(m, nv)) plane_fit5_qr(m, nv);                                                    // :375 (see dev_math.cuh)
+                const double n2 = nv[0] * nv[0] + nv[1] * nv[1] + nv[2] * nv[2];
+                const double nn = sqrt(n2);
+                const double normInverse = 1.0 / nn;                                                                  // :376
                 if (n2 > 0) { nv[0] /= nn; nv[1] /= nn; nv[2] /= nn; }                                                // :377
                 bool planeValid = true;
 #pragma unroll
@@ -268,9 +280,9 @@ __global__ void __launch_bounds__(kBlock) k_knn_plane(KnnArgs a) {
                     if (fabs(nv[0] * m[j].x + nv[1] * m[j].y + nv[2] * m[j].z + normInverse) > a.plane_thres) planeValid = false;
                 if (planeValid) {
                     // :397-398 with the reference's mixed widths; exact ops keep the fp32 roundings stable
-                    float pd = (float)addx(addx(addx(mulx(nv[0], (double)s.sx), mulx(nv[1], (double)s.sy)), mulx(nv[2], (double)s.sz)), normInverse);
-                    float rng = __fsqrt_rn(__fsqrt_rn(faddx(faddx(fmulx(s.sx, s.sx), fmulx(s.sy, s.sy)), fmulx(s.sz, s.sz))));
-                    float weight = (float)subx(1.0, mulx(0.9, (double)fabsf(pd)) / (double)rng);
+                    const float pd = (float)addx(addx(addx(mulx(nv[0], (double)s.sx), mulx(nv[1], (double)s.sy)), mulx(nv[2], (double)s.sz)), normInverse);
+                    const float rng = __fsqrt_rn(__fsqrt_rn(faddx(faddx(fmulx(s.sx, s.sx), fmulx(s.sy, s.sy)), fmulx(s.sz, s.sz))));
+                    const float weight = (float)subx(1.0, mulx(0.9, (double)fabsf(pd)) / (double)rng);
                     if ((double)weight > a.w_gate) {                                                                  // :400
                         pl0 = (float)mulx((double)weight, nv[0]);                                                     // :402-405
                         pl1 = (float)mulx((double)weight, nv[1]);
@@ -287,44 +299,42 @@ __global__ void __launch_bounds__(kBlock) k_knn_plane(KnnArgs a) {
             if (ok) {
                 // LidarPlaneNormIncreFactor (LidarKeyframeFactor.h:118-128) in closed form:
                 //   r = n~ . (q*p + t) + d~ ;  row = [ 2 (R p x n~)^T , n~^T ]  
-                float4 f = a.feats[qi];
-                D3 rp = qrot_x(q, D3{(double)f.x, (double)f.y, (double)f.z});
-                double nx = pl0, ny = pl1, nz = pl2;
+                const float4 f = a.feats[qi];
+                const D3 rp = qrot_x(q, D3{(double)f.x, (double)f.y, (double)f.z});
+                const double nx = pl0, ny = pl1, nz = pl2;
                 double r = nx * (rp.x + t.x) + ny * (rp.y + t.y) + nz * (rp.z + t.z) + (double)pl3;
-                double J[6];
-                J[0] = 2.0 * (rp.y * nz - rp.z * ny);
-                J[1] = 2.0 * (rp.z * nx - rp.x * nz);
-                J[2] = 2.0 * (rp.x * ny - rp.y * nx);
-                J[3] = nx; J[4] = ny; J[5] = nz;
                 // ceres::HuberLoss(a) + Corrector (rho'' <= 0 branch): scale row and residual by sqrt(rho')
-                double s2 = r * r, rho0, rho1;
-                const double b2 = a.huber_a * a.huber_a;
-                if (s2 > b2) { double rt = sqrt(s2); rho0 = 2.0 * a.huber_a * rt - b2; rho1 = fmax(DBL_MIN, a.huber_a / rt); }
-                else { rho0 = s2; rho1 = 1.0; }
-                double sr = sqrt(rho1);
-#pragma unroll
-                for (int k = 0; k < 6; ++k) J[k] *= sr;
-                r *= sr;
-                int k = 0;
-#pragma unroll
-                for (int i = 0; i < 6; ++i)
-#pragma unroll
-                    for (int j = i; j < 6; ++j) acc[k++] += J[i] * J[j];
-#pragma unroll
-                for (int i = 0; i < 6; ++i) acc[21 + i] += J[i] * r;
-                acc[27] += 0.5 * rho0;
-                acc[28] += 1.0;
+                const double s2 = r * r, b2 = a.huber_a * a.huber_a;
+                double rho0 = s2, rho1 = 1.0;
+                if (s2 > b2) { const double rt = sqrt(s2); rho0 = 2.0 * a.huber_a * rt - b2; rho1 = fmax(DBL_MIN, a.huber_a / rt); }
+                const double sr = sqrt(rho1);
+                Row& R = rows[warp][lane];
+                R.J[0] = sr * 2.0 * (rp.y * nz - rp.z * ny);
+                R.J[1] = sr * 2.0 * (rp.z * nx - rp.x * nz);
+                R.J[2] = sr * 2.0 * (rp.x * ny - rp.y * nx);
+                R.J[3] = sr * nx; R.J[4] = sr * ny; R.J[5] = sr * nz;
+                R.r = sr * r;
+                R.half_rho = 0.5 * rho0;
+            }
+            rvalid[warp][lane] = ok ? 1 : 0;
+        }
+        __syncwarp();
+        // ---------------- phase C: lane k accumulates scalar k over the task's rows (fixed slot order)
+        if (lane < kNormEq) {
+#pragma unroll 1
+            for (int sl = 0; sl < per_task; ++sl) {
+                if (!rvalid[warp][sl]) continue;
+                const double* R = reinterpret_cast<const double*>(&rows[warp][sl]);
+                if (lane < 27) acc += R[pa] * R[pb];
+                else if (lane == 27) acc += R[7];
+                else acc += 1.0;
             }
         }
         __syncwarp();
     }
 
-    // ---------------- block reduction of the 29 partial sums (+ candidate counter)
-#pragma unroll
-    for (int k = 0; k < kNormEq; ++k) {
-        double v = warp_sum(acc[k]);
-        if (lane == 0) red[warp][k] = v;
-    }
+    // ---------------- block reduction of the 29 sums (+ candidate counter)
+    if (lane < kNormEq) red[warp][lane] = acc;
     {
         unsigned long long v = cand;
 #pragma unroll
@@ -332,11 +342,12 @@ __global__ void __launch_bounds__(kBlock) k_knn_plane(KnnArgs a) {
         if (lane == 0) red_cand[warp] = v;
     }
     __syncthreads();
+    const int G = gridDim.x;
     if (threadIdx.x < kNormEq) {
         double v = 0;
 #pragma unroll
         for (int w = 0; w < kWarps; ++w) v += red[w][threadIdx.x];
-        a.partials[(size_t)blockIdx.x * kNormEq + threadIdx.x] = v;
+        a.partials[(size_t)threadIdx.x * G + blockIdx.x] = v;          // scalar-major: [29][G]
     }
     if (threadIdx.x == 0) {
         unsigned long long v = 0;
@@ -352,31 +363,62 @@ __global__ void __launch_bounds__(kBlock) k_knn_plane(KnnArgs a) {
     __syncthreads();
     if (!is_last) return;
     __threadfence();
-    // ---------------- last block: fixed-order sum over blocks, then the 6x6 step
-    for (int k = warp; k < kNormEq; k += kWarps) {
-        double v = 0;
-        for (int b = lane; b < (int)gridDim.x; b += 32) v += __ldcg(a.partials + (size_t)b * kNormEq + k);
-        v = warp_sum(v);
-        if (lane == 0) red[0][k] = v;
+    // ---------------- last block: fixed-order sum over blocks, then the 6x6 step.
+    // 8 lanes per scalar, 4 independent loads in flight per lane: the tail is exposed latency (every
+    // other SM is idle by now), so it is laid out for memory-level parallelism, not for work efficiency.
+    {
+        const int sc = threadIdx.x >> 3, l8 = threadIdx.x & 7;
+        double v = 0.0;
+        if (sc < kNormEq) {
+            const double* src = a.partials + (size_t)sc * G;
+            double v0 = 0, v1 = 0, v2 = 0, v3 = 0;
+            int b = l8;
+            for (; b + 24 < G; b += 32) {
+                v0 += __ldcg(src + b); v1 += __ldcg(src + b + 8); v2 += __ldcg(src + b + 16); v3 += __ldcg(src + b + 24);
+            }
+            for (; b < G; b += 8) v0 += __ldcg(src + b);
+            v = (v0 + v1) + (v2 + v3);
+        }
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        if (l8 == 0 && sc < kNormEq) red[0][sc] = v;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
         *a.ticket = 0;
         double s[kNormEq];
-        for (int k = 0; k < kNormEq; ++k) { s[k] = red[0][k]; a.neq[k] = s[k]; }
+#pragma unroll
+        for (int k = 0; k < kNormEq; ++k) s[k] = red[0][k];
         if (a.update_pose) {
             double x[7], xn[7], nb[6], d[6];
-            for (int k = 0; k < 7; ++k) x[k] = a.pose[k];
+#pragma unroll
+            for (int k = 0; k < 7; ++k) x[k] = q_t7(q, t, k);
+#pragma unroll
             for (int k = 0; k < 6; ++k) nb[k] = -s[21 + k];
-            if (s[28] > 0.0 && solve6_ldlt(s, nb, d)) pose_plus(x, d, xn);
-            else for (int k = 0; k < 7; ++k) xn[k] = x[k];
+            const bool solved = solve6_ldlt(s, nb, d);
+            if (s[28] > 0.0 && solved) pose_plus(x, d, xn);
+            else {
+#pragma unroll
+                for (int k = 0; k < 7; ++k) xn[k] = x[k];
+            }
             if (xn[0] < 0) { xn[0] = -xn[0]; xn[1] = -xn[1]; xn[2] = -xn[2]; xn[3] = -xn[3]; }   // :539-549
+#pragma unroll
             for (int k = 0; k < 7; ++k) a.pose_out[k] = xn[k];
             if (a.stats) {
-                a.stats[0] = s[28]; a.stats[1] = 1.0; a.stats[2] = s[27];
-                for (int k = 0; k < 27; ++k) a.stats[3 + k] = s[k];
+#pragma unroll
                 for (int k = 0; k < 7; ++k) a.stats[30 + k] = xn[k];
             }
+        }
+    }
+    // neq + stats are written by the first 29 threads in parallel (off the serial path)
+    if (threadIdx.x < kNormEq) {
+        const double v = red[0][threadIdx.x];
+        a.neq[threadIdx.x] = v;
+        if (a.update_pose && a.stats) {
+            if (threadIdx.x < 27) a.stats[3 + threadIdx.x] = v;
+            else if (threadIdx.x == 27) a.stats[2] = v;
+            else { a.stats[0] = v; a.stats[1] = 1.0; }
         }
     }
 }
@@ -605,13 +647,17 @@ __global__ void __launch_bounds__(kLmBlock) k_lm_solve(LmArgs a) {
 typedef int (*nccl_allreduce_fn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
 int nccl_allreduce_sum_f64(liliom_ctx* c, double* buf, int count);   // comm.cu
 
-static int pick_rounds(int n, int sm_count) {
-    // keep >= ~6 warps per SM busy; beyond that amortise the fp64 phase over more lanes
-    long long warps_at_r1 = ((long long)n + 3) / 4;
-    long long target = (long long)sm_count * 6;
-    int r = 1;
-    while (r < 8 && warps_at_r1 / (r * 2) >= target) r *= 2;
-    return r;
+// Work decomposition.  LANES lanes cooperate on a query and a warp handles (32/LANES)*rounds
+// queries per task.  Small scans (a down-sampled 24k-point sweep leaves 1-3k queries) are latency
+// bound: spread each query over a whole warp and keep one query per warp.  Large query sets are
+// throughput bound: 8 lanes per query and several rounds so that the fp64 phase fills its lanes.
+static void pick_shape(int n, int sm_count, int& lanes, int& rounds) {
+    const long long warp_slots = (long long)sm_count * 16;
+    if ((long long)n <= warp_slots) { lanes = 32; rounds = 1; return; }
+    if ((long long)n <= warp_slots * 2) { lanes = 16; rounds = 1; return; }
+    lanes = 8;
+    rounds = 1;
+    while (rounds < 8 && ((long long)n + 4LL * rounds * 2 - 1) / (4LL * rounds * 2) >= warp_slots) rounds *= 2;
 }
 
 int s2m_run(liliom_ctx* c, double pose7[7], int match_cnt, int max_num_iter, int mode, liliom_iter_stats* stats,
@@ -621,10 +667,12 @@ int s2m_run(liliom_ctx* c, double pose7[7], int match_cnt, int max_num_iter, int
     const int n = c->n_feats;
     if (match_cnt < 0) return LILIOM_E_ARG;
     const int iters = match_cnt;
-    const int rounds = pick_rounds(n, c->sm_count);
-    const int per_task = 4 * rounds;
+    int lanes = 8, rounds = 1;
+    pick_shape(n, c->sm_count, lanes, rounds);
+    if (c->force_lanes) { lanes = c->force_lanes; rounds = c->force_rounds > 0 ? c->force_rounds : 1; }
+    const int per_task = (32 / lanes) * rounds;
     const int ntasks = cdiv(n, per_task);
-    int grid = min(max(cdiv(ntasks, kWarps), 1), c->sm_count * 12);
+    int grid = min(max(cdiv(ntasks, kWarps), 1), c->sm_count * 2);
 
     LILI_CUDA(c, c->pose_dev.ensure(16 * sizeof(double)));
     LILI_CUDA(c, c->partials.ensure((size_t)grid * kNormEq * sizeof(double)));
@@ -674,7 +722,9 @@ int s2m_run(liliom_ctx* c, double pose7[7], int match_cnt, int max_num_iter, int
             ev = c->ev_used; c->ev_used += 2;
             LILI_CUDA(c, cudaEventRecord(c->ev_pool[ev], c->stream));
         }
-        k_knn_plane<<<grid, kBlock, 0, c->stream>>>(a);
+        if (lanes == 32) k_knn_plane<32><<<grid, kBlock, 0, c->stream>>>(a);
+        else if (lanes == 16) k_knn_plane<16><<<grid, kBlock, 0, c->stream>>>(a);
+        else k_knn_plane<8><<<grid, kBlock, 0, c->stream>>>(a);
         LILI_TRY(launch_check(c, "k_knn_plane"));
         if (c->time_kernels) {
             LILI_CUDA(c, cudaEventRecord(c->ev_pool[ev + 1], c->stream));
