@@ -154,7 +154,7 @@ extern "C" int liliom_create(liliom_ctx** out, const liliom_params* p, int devic
     c->h_pin_bytes = 1 << 20;
     e = cudaHostAlloc(&c->h_pin, c->h_pin_bytes, cudaHostAllocDefault);
     if (e != cudaSuccess) { cudaStreamDestroy(c->own_stream); delete c; return LILIOM_E_CUDA; }
-    if (const char* e1 = getenv("LILIOM_KNN_LANES")) { int v = atoi(e1); if (v == 8 || v == 16 || v == 32) c->force_lanes = v; }
+    if (const char* e1 = getenv("LILIOM_KNN_LANES")) { int v = atoi(e1); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16) c->force_lanes = v; }
     if (const char* e2 = getenv("LILIOM_KNN_ROUNDS")) { int v = atoi(e2); if (v >= 1 && v <= 32) c->force_rounds = v; }
     *out = c;
     return LILIOM_OK;

@@ -13,7 +13,7 @@ constexpr int kLanes = 8;
 
 struct BkArgs {
     const float4* feats; int n;
-    const float4* map; const int* cell_start; GridDesc g;
+    const float4* map; const float4* map_orig; const int* cell_start; GridDesc g;
     Q4 q; D3 t;
     int variant;
     double max_sqd, plane_thres, w_gate, lidar_const;
@@ -36,11 +36,11 @@ __global__ void __launch_bounds__(kBlock) k_backend_edge(BkArgs a) {
     if (sub != 0) return;
     bool ok = false;
     float A3[3] = {0, 0, 0}, B3[3] = {0, 0, 0};
-    if (top.p4 >= 0 && (double)top5_dist(top.k4) < 1.0) {                                        // L:1543
-        const int pos[5] = {top.p0, top.p1, top.p2, top.p3, top.p4};
+    if (top.k4 != ~0ull && (double)top5_dist(top.k4) < 1.0) {                                        // L:1543
+        const int pos[5] = {top5_index(top.k0), top5_index(top.k1), top5_index(top.k2), top5_index(top.k3), top5_index(top.k4)};
         double px[5], py[5], pz[5], cx = 0, cy = 0, cz = 0;
         for (int j = 0; j < 5; ++j) {
-            float4 m = a.map[pos[j]];
+            float4 m = a.map_orig[pos[j]];
             px[j] = m.x; py[j] = m.y; pz[j] = m.z;
             cx = addx(cx, px[j]); cy = addx(cy, py[j]); cz = addx(cz, pz[j]);
         }
@@ -93,11 +93,11 @@ __global__ void __launch_bounds__(kBlock) k_backend_surf(BkArgs a) {
     bool ok = false;
     float4 pl = make_float4(0, 0, 0, 0);
     double sc = 0;
-    if (top.p4 >= 0 && (double)top5_dist(top.k4) < a.max_sqd) {                                   // R:1476
-        const int pos[5] = {top.p0, top.p1, top.p2, top.p3, top.p4};
+    if (top.k4 != ~0ull && (double)top5_dist(top.k4) < a.max_sqd) {                                   // R:1476
+        const int pos[5] = {top5_index(top.k0), top5_index(top.k1), top5_index(top.k2), top5_index(top.k3), top5_index(top.k4)};
         double A[5][3], B[5];
         float4 m[5];
-        for (int j = 0; j < 5; ++j) { m[j] = a.map[pos[j]]; A[j][0] = m[j].x; A[j][1] = m[j].y; A[j][2] = m[j].z; B[j] = -1.0; }
+        for (int j = 0; j < 5; ++j) { m[j] = a.map_orig[pos[j]]; A[j][0] = m[j].x; A[j][1] = m[j].y; A[j][2] = m[j].z; B[j] = -1.0; }
         double nv[3];
         colpiv_qr_solve_5x3(A, B, nv);                                                 // R:1484
         double n2 = nv[0] * nv[0] + nv[1] * nv[1] + nv[2] * nv[2];
@@ -154,7 +154,7 @@ extern "C" int liliom_correspond_edge(liliom_ctx* c, const void* feats, int n, i
     LILI_CUDA(c, c->corr_valid.ensure((size_t)n + 16));
     LILI_CUDA(c, c->corr_plane.ensure((size_t)n * 24 + 16));
     BkArgs a{};
-    a.feats = c->feats.as<float4>(); a.n = n; a.map = c->map_sorted.as<float4>(); a.cell_start = c->cell_start.as<int>(); a.g = c->grid;
+    a.feats = c->feats.as<float4>(); a.n = n; a.map = c->map_sorted.as<float4>(); a.map_orig = c->map_xyzw.as<float4>(); a.cell_start = c->cell_start.as<int>(); a.g = c->grid;
     a.q = Q4{pose7[0], pose7[1], pose7[2], pose7[3]}; a.t = D3{pose7[4], pose7[5], pose7[6]};
     a.variant = variant;
     a.valid = c->corr_valid.as<unsigned char>();
@@ -186,7 +186,7 @@ extern "C" int liliom_correspond_surf(liliom_ctx* c, const void* feats, int n, i
     LILI_CUDA(c, c->corr_plane.ensure((size_t)n * 16 + 16));
     LILI_CUDA(c, c->nn_sqd.ensure((size_t)n * 8 + 16));
     BkArgs a{};
-    a.feats = c->feats.as<float4>(); a.n = n; a.map = c->map_sorted.as<float4>(); a.cell_start = c->cell_start.as<int>(); a.g = c->grid;
+    a.feats = c->feats.as<float4>(); a.n = n; a.map = c->map_sorted.as<float4>(); a.map_orig = c->map_xyzw.as<float4>(); a.cell_start = c->cell_start.as<int>(); a.g = c->grid;
     a.q = Q4{pose7[0], pose7[1], pose7[2], pose7[3]}; a.t = D3{pose7[4], pose7[5], pose7[6]};
     a.max_sqd = kd_max_radius; a.plane_thres = surf_dist_thres; a.w_gate = w_gate; a.lidar_const = lidar_const;
     a.valid = c->corr_valid.as<unsigned char>(); a.plane = c->corr_plane.as<float4>(); a.score = c->nn_sqd.as<double>();

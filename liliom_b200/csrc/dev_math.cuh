@@ -397,7 +397,7 @@ __device__ __forceinline__ bool solve6_ldlt(const double* s21, const double* rhs
 #pragma unroll
             for (int b = a; b < 6; ++b) { H[a][b] = s21[k]; H[b][a] = s21[k]; ++k; }
     }
-    double L[6][6], D[6];
+    double L[6][6], D[6], Dinv[6];
     bool ok = true;
 #pragma unroll
     for (int j = 0; j < 6; ++j) {
@@ -407,6 +407,7 @@ __device__ __forceinline__ bool solve6_ldlt(const double* s21, const double* rhs
         if (!(fabs(d) > 1e-300) || !isfinite(d)) ok = false;
         D[j] = d;
         const double inv = 1.0 / d;
+        Dinv[j] = inv;
 #pragma unroll
         for (int i = j + 1; i < 6; ++i) {
             double s = H[i][j];
@@ -424,7 +425,7 @@ __device__ __forceinline__ bool solve6_ldlt(const double* s21, const double* rhs
         y[i] = s;
     }
 #pragma unroll
-    for (int i = 0; i < 6; ++i) y[i] /= D[i];
+    for (int i = 0; i < 6; ++i) y[i] *= Dinv[i];
 #pragma unroll
     for (int i = 5; i >= 0; --i) {
         double s = y[i];

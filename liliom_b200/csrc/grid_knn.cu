@@ -21,6 +21,7 @@
 #include "ctx.cuh"
 #include "dev_math.cuh"
 #include "knn_core.cuh"
+#include <cstdlib>
 
 namespace lili {
 
@@ -87,7 +88,7 @@ __global__ void k_gather_sorted(const float4* __restrict__ p, const int* __restr
     if (i >= n) return;
     int src = vals[i];
     float4 v = p[src];
-    out[i] = make_float4(v.x, v.y, v.z, v.w);   // w already carries the original index bits
+    out[i] = make_float4(v.x, v.y, v.z, __int_as_float(src));   // w = index into the un-sorted map array
 }
 
 // cell_start[c] = first sorted position whose key >= c; one warp per run boundary fills the gap.
@@ -158,7 +159,7 @@ int grid_build(liliom_ctx* c, int m) {
 // ------------------------------------------------------------------ the hot kernel
 struct KnnArgs {
     const float4* feats; int n;
-    const float4* map; const int* cell_start; GridDesc g;
+    const float4* map; const float4* map_orig; const int* cell_start; GridDesc g;   // cell-sorted / download-order map
     const double* pose;                 // 7 doubles in HBM
     double max_sqd, plane_thres, w_gate, huber_a;
     unsigned char* valid; float4* plane; int* nn_idx; float* nn_sqd;   // optional outputs
@@ -167,8 +168,9 @@ struct KnnArgs {
     double* pose_out;                   // where the updated pose goes (== pose for GN)
     unsigned long long* cand_total;     // instrumentation
     int update_pose;                    // 1: last block performs the GN step
-    int rounds;                         // R: a warp handles 4*R queries per task
+    int rounds;                         // a warp handles (32/LANES)*rounds queries per task
     int nranks, rank;                   // multi-GPU ownership filter (8 m block hash)
+    long long* dbg;                     // optional phase timestamps (LILIOM_DEBUG_TIMING)
 };
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -179,7 +181,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 
 // Per-query scratch a warp keeps in shared memory between the phases.
 struct Slot {
-    int   pos[5];            // neighbour positions in the cell-sorted map; pos[0] < 0: no 5-NN inside the radius
+    int   idx[5];            // neighbour indices into map_orig; idx[0] < 0: no 5-NN inside the radius
     float sx, sy, sz;        // transformed query (fp32, as the kd-tree saw it)
 };
 struct Row { double J[6]; double r; double half_rho; };   // robustified Jacobian row, residual, rho/2
@@ -208,6 +210,9 @@ __global__ void __launch_bounds__(kBlock, 2) k_knn_plane(KnnArgs a) {
     const int grp = lane / LANES;
     const unsigned gmask = (LANES == 32) ? 0xffffffffu : (((1u << LANES) - 1u) << (grp * LANES));
 
+#define LILI_STAMP(i) do { if (a.dbg && blockIdx.x == 0 && threadIdx.x == 0) a.dbg[i] = clock64(); } while (0)
+#define LILI_STAMP_LAST(i) do { if (a.dbg && threadIdx.x == 0) a.dbg[i] = clock64(); } while (0)
+    LILI_STAMP(0);
     const Q4 q{a.pose[0], a.pose[1], a.pose[2], a.pose[3]};
     const D3 t{a.pose[4], a.pose[5], a.pose[6]};
 
@@ -239,17 +244,20 @@ __global__ void __launch_bounds__(kBlock, 2) k_knn_plane(KnnArgs a) {
                 if (a.nranks > 1 && owner_of(sx, sy, sz, a.nranks) != a.rank) live = false;
             }
             // `live` is uniform inside a lane group and the shuffles are masked per group
-            if (live) group_knn5<LANES>(sx, sy, sz, a.map, a.cell_start, a.g, sub, gmask, top, cand);
+            LILI_STAMP(8);
+            if (live) group_knn5<LANES>(sx, sy, sz, a.map, a.cell_start, a.g, sub, gmask, top, cand, (a.dbg && blockIdx.x == 0 && threadIdx.x == 0) ? a.dbg : nullptr);
+            LILI_STAMP(11);
             if (sub == 0) {
                 Slot& s = slots[warp][slot];
-                const bool ok = live && top.p4 >= 0 && ((double)top5_dist(top.k4) < a.max_sqd);  // :365
-                s.pos[0] = ok ? top.p0 : -1; s.pos[1] = top.p1; s.pos[2] = top.p2; s.pos[3] = top.p3; s.pos[4] = top.p4;
+                const bool ok = live && top.k4 != ~0ull && ((double)top5_dist(top.k4) < a.max_sqd);  // :365
+                s.idx[0] = ok ? top5_index(top.k0) : -1; s.idx[1] = top5_index(top.k1); s.idx[2] = top5_index(top.k2);
+                s.idx[3] = top5_index(top.k3); s.idx[4] = top5_index(top.k4);
                 s.sx = sx; s.sy = sy; s.sz = sz;
                 if (live && a.nn_idx) {
                     int* o = a.nn_idx + (size_t)qi * 5;
-                    o[0] = top.p0 >= 0 ? top5_orig(top.k0) : -1; o[1] = top.p1 >= 0 ? top5_orig(top.k1) : -1;
-                    o[2] = top.p2 >= 0 ? top5_orig(top.k2) : -1; o[3] = top.p3 >= 0 ? top5_orig(top.k3) : -1;
-                    o[4] = top.p4 >= 0 ? top5_orig(top.k4) : -1;
+                    const u64 kk[5] = {top.k0, top.k1, top.k2, top.k3, top.k4};
+#pragma unroll
+                    for (int j = 0; j < 5; ++j) { const int li = top5_index(kk[j]); o[j] = li >= 0 ? __float_as_int(a.map_orig[li].w) : -1; }
                 }
                 if (live && a.nn_sqd) {
                     float* o = a.nn_sqd + (size_t)qi * 5;
@@ -258,16 +266,17 @@ __global__ void __launch_bounds__(kBlock, 2) k_knn_plane(KnnArgs a) {
             }
         }
         __syncwarp();
+        LILI_STAMP(1);
         // ---------------- phase B: one lane per query — plane fit, gates, residual, Jacobian row
         bool ok = false;
         if (lane < per_task) {
             const int qi = task * per_task + lane;
             const Slot s = slots[warp][lane];
             float pl0 = 0.f, pl1 = 0.f, pl2 = 0.f, pl3 = 0.f;
-            if (qi < a.n && s.pos[0] >= 0) {
+            if (qi < a.n && s.idx[0] >= 0) {
                 float4 m[5];
 #pragma unroll
-                for (int j = 0; j < 5; ++j) m[j] = __ldg(a.map + s.pos[j]);                                          // :369-371
+                for (int j = 0; j < 5; ++j) m[j] = __ldg(a.map_orig + s.idx[j]);                                     // :369-371
                 double nv[3];
                 if (!plane_fit5_fast(m, nv)) plane_fit5_qr(m, nv);                                                    // :375 (see dev_math.cuh)
                 const double n2 = nv[0] * nv[0] + nv[1] * nv[1] + nv[2] * nv[2];
@@ -319,6 +328,7 @@ __global__ void __launch_bounds__(kBlock, 2) k_knn_plane(KnnArgs a) {
             rvalid[warp][lane] = ok ? 1 : 0;
         }
         __syncwarp();
+        LILI_STAMP(2);
         // ---------------- phase C: lane k accumulates scalar k over the task's rows (fixed slot order)
         if (lane < kNormEq) {
 #pragma unroll 1
@@ -333,6 +343,7 @@ __global__ void __launch_bounds__(kBlock, 2) k_knn_plane(KnnArgs a) {
         __syncwarp();
     }
 
+    LILI_STAMP(3);
     // ---------------- block reduction of the 29 sums (+ candidate counter)
     if (lane < kNormEq) red[warp][lane] = acc;
     {
@@ -361,8 +372,10 @@ __global__ void __launch_bounds__(kBlock, 2) k_knn_plane(KnnArgs a) {
         is_last = (tk == gridDim.x - 1);
     }
     __syncthreads();
+    LILI_STAMP(4);
     if (!is_last) return;
     __threadfence();
+    LILI_STAMP_LAST(5);
     // ---------------- last block: fixed-order sum over blocks, then the 6x6 step.
     // 8 lanes per scalar, 4 independent loads in flight per lane: the tail is exposed latency (every
     // other SM is idle by now), so it is laid out for memory-level parallelism, not for work efficiency.
@@ -385,6 +398,7 @@ __global__ void __launch_bounds__(kBlock, 2) k_knn_plane(KnnArgs a) {
         if (l8 == 0 && sc < kNormEq) red[0][sc] = v;
     }
     __syncthreads();
+    LILI_STAMP_LAST(6);
     if (threadIdx.x == 0) {
         *a.ticket = 0;
         double s[kNormEq];
@@ -411,6 +425,7 @@ __global__ void __launch_bounds__(kBlock, 2) k_knn_plane(KnnArgs a) {
             }
         }
     }
+    LILI_STAMP_LAST(7);
     // neq + stats are written by the first 29 threads in parallel (off the serial path)
     if (threadIdx.x < kNormEq) {
         const double v = red[0][threadIdx.x];
@@ -647,17 +662,17 @@ __global__ void __launch_bounds__(kLmBlock) k_lm_solve(LmArgs a) {
 typedef int (*nccl_allreduce_fn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
 int nccl_allreduce_sum_f64(liliom_ctx* c, double* buf, int count);   // comm.cu
 
-// Work decomposition.  LANES lanes cooperate on a query and a warp handles (32/LANES)*rounds
-// queries per task.  Small scans (a down-sampled 24k-point sweep leaves 1-3k queries) are latency
-// bound: spread each query over a whole warp and keep one query per warp.  Large query sets are
-// throughput bound: 8 lanes per query and several rounds so that the fp64 phase fills its lanes.
+// Work decomposition.  LANES lanes cooperate on one query; a warp finishes (32/LANES)*rounds queries
+// per task before the fp64 phase.  Large query sets: one thread per query (every issue slot ranks 32
+// candidates, neighbouring threads share cells in L1).  Small sets (a down-sampled 24k-point sweep
+// leaves 1-3k queries) are latency bound: split each query's 9 runs over 4 or 8 lanes so that the
+// whole GPU is busy and the per-warp critical path is short.
 static void pick_shape(int n, int sm_count, int& lanes, int& rounds) {
-    const long long warp_slots = (long long)sm_count * 16;
-    if ((long long)n <= warp_slots) { lanes = 32; rounds = 1; return; }
-    if ((long long)n <= warp_slots * 2) { lanes = 16; rounds = 1; return; }
-    lanes = 8;
+    const long long w8 = (long long)sm_count * 8;      // warps for ~8 per SM
     rounds = 1;
-    while (rounds < 8 && ((long long)n + 4LL * rounds * 2 - 1) / (4LL * rounds * 2) >= warp_slots) rounds *= 2;
+    if ((long long)n >= w8 * 32) { lanes = 1; return; }
+    if ((long long)n >= w8 * 8) { lanes = 4; rounds = ((long long)n >= w8 * 16) ? 2 : 1; return; }
+    lanes = ((long long)n * 16 / 32 <= w8 * 2) ? 16 : 8;   // tiny scans: one run per lane (9 of 16 lanes)
 }
 
 int s2m_run(liliom_ctx* c, double pose7[7], int match_cnt, int max_num_iter, int mode, liliom_iter_stats* stats,
@@ -670,6 +685,7 @@ int s2m_run(liliom_ctx* c, double pose7[7], int match_cnt, int max_num_iter, int
     int lanes = 8, rounds = 1;
     pick_shape(n, c->sm_count, lanes, rounds);
     if (c->force_lanes) { lanes = c->force_lanes; rounds = c->force_rounds > 0 ? c->force_rounds : 1; }
+    if ((32 / lanes) * rounds > 32) rounds = lanes;   // at most 32 queries per warp task
     const int per_task = (32 / lanes) * rounds;
     const int ntasks = cdiv(n, per_task);
     int grid = min(max(cdiv(ntasks, kWarps), 1), c->sm_count * 2);
@@ -697,7 +713,7 @@ int s2m_run(liliom_ctx* c, double pose7[7], int match_cnt, int max_num_iter, int
 
     KnnArgs a{};
     a.feats = c->feats.as<float4>(); a.n = n;
-    a.map = c->map_sorted.as<float4>(); a.cell_start = c->cell_start.as<int>(); a.g = c->grid;
+    a.map = c->map_sorted.as<float4>(); a.map_orig = c->map_xyzw.as<float4>(); a.cell_start = c->cell_start.as<int>(); a.g = c->grid;
     a.pose = c->pose_dev.as<double>(); a.pose_out = c->pose_dev.as<double>();
     a.max_sqd = c->prm.knn_max_sqdist; a.plane_thres = c->prm.plane_thres; a.w_gate = c->prm.weight_gate; a.huber_a = c->prm.huber_a;
     a.valid = need_corr ? c->corr_valid.as<unsigned char>() : nullptr;
@@ -706,8 +722,14 @@ int s2m_run(liliom_ctx* c, double pose7[7], int match_cnt, int max_num_iter, int
     a.nn_sqd = want_corr ? c->nn_sqd.as<float>() : nullptr;
     a.partials = c->partials.as<double>(); a.neq = c->neq.as<double>();
     a.ticket = c->counter.as<unsigned int>();
-    a.cand_total = reinterpret_cast<unsigned long long*>(c->counter.as<unsigned char>() + 16);
+    a.cand_total = c->time_kernels ? reinterpret_cast<unsigned long long*>(c->counter.as<unsigned char>() + 16) : nullptr;
     a.rounds = rounds; a.nranks = c->nranks; a.rank = c->rank;
+    a.dbg = nullptr;
+    if (getenv("LILIOM_DEBUG_TIMING")) {
+        LILI_CUDA(c, c->lm_state.ensure(64 * sizeof(long long)));
+        LILI_CUDA(c, cudaMemsetAsync(c->lm_state.p, 0, 64 * sizeof(long long), c->stream));
+        a.dbg = c->lm_state.as<long long>();
+    }
 
     const int launches = (iters == 0 && want_corr) ? 1 : iters;
     for (int it = 0; it < launches; ++it) {
@@ -722,8 +744,10 @@ int s2m_run(liliom_ctx* c, double pose7[7], int match_cnt, int max_num_iter, int
             ev = c->ev_used; c->ev_used += 2;
             LILI_CUDA(c, cudaEventRecord(c->ev_pool[ev], c->stream));
         }
-        if (lanes == 32) k_knn_plane<32><<<grid, kBlock, 0, c->stream>>>(a);
-        else if (lanes == 16) k_knn_plane<16><<<grid, kBlock, 0, c->stream>>>(a);
+        if (lanes == 16) k_knn_plane<16><<<grid, kBlock, 0, c->stream>>>(a);
+        else if (lanes == 1) k_knn_plane<1><<<grid, kBlock, 0, c->stream>>>(a);
+        else if (lanes == 2) k_knn_plane<2><<<grid, kBlock, 0, c->stream>>>(a);
+        else if (lanes == 4) k_knn_plane<4><<<grid, kBlock, 0, c->stream>>>(a);
         else k_knn_plane<8><<<grid, kBlock, 0, c->stream>>>(a);
         LILI_TRY(launch_check(c, "k_knn_plane"));
         if (c->time_kernels) {
@@ -767,6 +791,14 @@ int s2m_run(liliom_ctx* c, double pose7[7], int match_cnt, int max_num_iter, int
             for (int k = 0; k < 27; ++k) stats[it].jtj_jtr[k] = s[3 + k];
             for (int k = 0; k < 7; ++k) stats[it].pose7[k] = s[30 + k];
         }
+    }
+    if (a.dbg) {
+        long long h[12];
+        cudaMemcpy(h, a.dbg, sizeof(h), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[phase A detail] pose+feat+transform %lld, first row bounds %lld, candidates+rank %lld, merge %lld, slot %lld\n",
+                h[8] - h[0], h[9] - h[8], h[10] - h[9], h[11] - h[10], h[1] - h[11]);
+        fprintf(stderr, "[knn phases, cycles] blk0: start->A %lld, B %lld, C %lld, loop-end %lld, block-reduce+ticket %lld | last block: reduce %lld, solve %lld (abs tail %lld after blk0 start)\n",
+                h[1] - h[0], h[2] - h[1], h[3] - h[2], 0LL, h[4] - h[3], h[6] - h[5], h[7] - h[6], h[7] - h[0]);
     }
     // fold finished kernel timings into the counters
     if (c->time_kernels) {

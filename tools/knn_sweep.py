@@ -20,7 +20,7 @@ base.close()
 dense = np.concatenate([surf] * 1)
 big = np.concatenate([surf[np.random.default_rng(0).permutation(len(surf))] for _ in range(8)])   # 128k queries, unsorted
 for name, feats in (("ds", ds), ("dense", dense), ("dense_x8_shuffled", big)):
-    for lanes, rounds in ((0, 0), (32, 1), (16, 1), (16, 2), (8, 1), (8, 2), (8, 4), (8, 8)):
+    for lanes, rounds in ((0, 0), (16, 1), (8, 1), (4, 1), (4, 2), (2, 1), (1, 1)):
         if lanes: os.environ["LILIOM_KNN_LANES"] = str(lanes); os.environ["LILIOM_KNN_ROUNDS"] = str(rounds)
         else: os.environ.pop("LILIOM_KNN_LANES", None); os.environ.pop("LILIOM_KNN_ROUNDS", None)
         c = L.Context(variant=0)
