@@ -187,7 +187,7 @@ def make_horizon_sweep(true_pose7, seed: int = 1, omega=(0.0, 0.0, 0.2), dropout
     d_w = _rotate_many(qT, d_start)
     rng_m = _raycast(T[4:], d_w)
     hit = np.isfinite(rng_m) & (rng.uniform(size=len(rng_m)) >= dropout)
-    r = rng_m + rng.normal(0.0, noise, len(rng_m))
+    r = np.where(hit, rng_m, 0.0) + rng.normal(0.0, noise, len(rng_m))
     p = d_s * r[:, None]                                      # raw (distorted) point in the sensor frame at its own time
     out = np.zeros(int(hit.sum()), PT48)
     out["x"] = p[hit, 0]; out["y"] = p[hit, 1]; out["z"] = p[hit, 2]; out["w"] = 1.0
@@ -223,7 +223,7 @@ def make_hdl64_sweep(true_pose7, seed: int = 2, omega=(0.0, 0.0, 0.2), steps: in
     d_w = _rotate_many(np.broadcast_to(T[:4], (len(d_start), 4)), d_start)
     rng_m = _raycast(T[4:], d_w, max_range=120.0)
     hit = np.isfinite(rng_m) & (rng.uniform(size=len(rng_m)) >= dropout)
-    r = rng_m + rng.normal(0.0, noise, len(rng_m))
+    r = np.where(hit, rng_m, 0.0) + rng.normal(0.0, noise, len(rng_m))
     p = d_s * r[:, None]
     out = np.zeros(int(hit.sum()), PT32)
     out["x"] = p[hit, 0]; out["y"] = p[hit, 1]; out["z"] = p[hit, 2]; out["w"] = 1.0

@@ -104,6 +104,11 @@ void orc_pose_relative(const double prev7[7], const double cur7[7], double rel7[
 /* LidarOdometry.cpp:246-278 transformCloud (48 B: rotates normals; 32 B: xyz+intensity only) */
 void orc_transform_cloud(const void* in, int n, int stride, const double pose7[7], void* out);
 
+/* ---- test hooks for the from-knowledge third-party restatements (oracle_math.h) ---- */
+void orc_eigen_sym3(const double a_rowmajor[9], double eval[3], double evec_rowmajor[9]);
+void orc_colpiv_qr_solve(int rows, const double* A_rows_x3, const double* b, double x[3]);
+void orc_slerp_identity(const double q_wxyz[4], double t, double out_wxyz[4]);
+
 #ifdef __cplusplus
 }
 #endif

@@ -469,3 +469,16 @@ extern "C" void orc_pose_relative(const double p[7], const double c[7], double o
     V3 tr = qrot(qi, t2 - t1);
     o[0] = qr.w; o[1] = qr.x; o[2] = qr.y; o[3] = qr.z; o[4] = tr.x; o[5] = tr.y; o[6] = tr.z;
 }
+
+// ---- test hooks -------------------------------------------------------------------------
+extern "C" void orc_eigen_sym3(const double a[9], double eval[3], double evec[9]) {
+    double A[3][3], V[3][3];
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) A[i][j] = a[3 * i + j];
+    eigen_sym3(A, eval, V);
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) evec[3 * i + j] = V[i][j];
+}
+extern "C" void orc_colpiv_qr_solve(int rows, const double* A, const double* b, double x[3]) { colpiv_qr_solve_nx3(rows, A, b, x); }
+extern "C" void orc_slerp_identity(const double q[4], double t, double out[4]) {
+    Quat r = qslerp(Quat{1, 0, 0, 0}, t, Quat{q[0], q[1], q[2], q[3]});
+    out[0] = r.w; out[1] = r.x; out[2] = r.y; out[3] = r.z;
+}

@@ -55,6 +55,9 @@ def lib():
         L.orc_pose_compose.argtypes = [dp, dp, dp]; L.orc_pose_compose.restype = None
         L.orc_pose_relative.argtypes = [dp, dp, dp]; L.orc_pose_relative.restype = None
         L.orc_transform_cloud.argtypes = [vp, C.c_int, C.c_int, dp, vp]; L.orc_transform_cloud.restype = None
+        L.orc_eigen_sym3.argtypes = [dp, dp, dp]; L.orc_eigen_sym3.restype = None
+        L.orc_colpiv_qr_solve.argtypes = [C.c_int, dp, dp, dp]; L.orc_colpiv_qr_solve.restype = None
+        L.orc_slerp_identity.argtypes = [dp, C.c_double, dp]; L.orc_slerp_identity.restype = None
         _lib = L
     return _lib
 
@@ -179,3 +182,31 @@ def transform_cloud(pts, pose7):
     out = np.zeros_like(pts)
     lib().orc_transform_cloud(_p(pts), len(pts), pts.dtype.itemsize, _d(np.asarray(pose7, np.float64)), _p(out))
     return out
+
+
+def eigen_sym3(a):
+    a = np.ascontiguousarray(a, np.float64).reshape(9)
+    ev = np.zeros(3); vec = np.zeros(9)
+    lib().orc_eigen_sym3(_d(a), _d(ev), _d(vec))
+    return ev, vec.reshape(3, 3)
+
+
+def colpiv_qr_solve(A, b):
+    A = np.ascontiguousarray(A, np.float64); b = np.ascontiguousarray(b, np.float64)
+    x = np.zeros(3)
+    lib().orc_colpiv_qr_solve(len(A), _d(A.reshape(-1)), _d(b), _d(x))
+    return x
+
+
+def slerp_identity(q, t):
+    out = np.zeros(4)
+    lib().orc_slerp_identity(_d(np.asarray(q, np.float64)), float(t), _d(out))
+    return out
+
+
+def ceres_solve(feats, valid, plane, pose7, max_num_iter=15):
+    f = _f4(feats)
+    pose = np.array(pose7, np.float64)
+    cost = C.c_double()
+    it = lib().orc_ceres_solve(_p(f), len(f), _p(np.ascontiguousarray(valid)), _p(np.ascontiguousarray(plane)), _d(pose), max_num_iter, C.byref(cost))
+    return it, pose, cost.value

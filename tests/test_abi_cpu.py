@@ -1,0 +1,71 @@
+"""CPU-side checks of the drop-in boundary (no GPU): the C-ABI library loads, exports every symbol
+include/liliom.h declares, and fails loudly (no CPU fallback) when no CUDA device is present."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "liliom.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(liliom_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    import liliom_b200 as L
+    lib = L._binding.lib()
+    decl = _declared_symbols()
+    assert len(decl) >= 25
+    missing = [s for s in decl if not hasattr(lib, s)]
+    assert not missing, missing
+    assert sorted(L.EXPORTS) == decl, (set(decl) ^ set(L.EXPORTS))
+
+
+def test_struct_layouts_match_header():
+    import liliom_b200 as L
+    assert L.PT48.itemsize == 48 and L.PT32.itemsize == 32
+    assert ctypes.sizeof(L.IterStats) == 4 + 4 + 8 + 27 * 8 + 7 * 8
+    assert ctypes.sizeof(L.Counters) == 48
+    p = L.default_params(0)
+    assert (p.abi_version, p.point_stride, p.surf_thres, p.edge_thres) == (1, 48, 0.2, 4.0)
+    assert (p.knn_max_sqdist, p.plane_thres, p.weight_gate, p.huber_a, p.max_map_frames) == (1.0, 0.06, 0.4, 0.1, 20)
+    assert abs(p.leaf_scan - 0.4) < 1e-7 and abs(p.leaf_map - 0.4) < 1e-7
+    r = L.default_params(1)
+    assert (r.point_stride, r.line_num, r.ds_rate) == (32, 64, 4) and abs(r.rot_ds_leaf - 0.6) < 1e-7
+
+
+def test_strerror_and_bad_arguments():
+    import liliom_b200 as L
+    lib = L._binding.lib()
+    assert lib.liliom_strerror(0) == b"ok"
+    assert b"10" in lib.liliom_strerror(-3)            # "< 10" map points, LidarOdometry.cpp:485-488
+    assert lib.liliom_create(None, None, 0) == -1
+    h = ctypes.c_void_p()
+    bad = L.default_params(0); bad.abi_version = 99
+    assert lib.liliom_create(ctypes.byref(h), ctypes.byref(bad), 0) == -1
+    bad = L.default_params(0); bad.point_stride = 40
+    assert lib.liliom_create(ctypes.byref(h), ctypes.byref(bad), 0) == -1
+
+
+def test_no_cpu_fallback_without_a_gpu():
+    import torch
+    import liliom_b200 as L
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(L.LiliomError) as e:
+        L.Context()
+    assert e.value.code == L._binding.E_CUDA
+
+
+def test_product_never_touches_the_oracle():
+    """The oracle is test infrastructure: nothing under liliom_b200/ may import, load or link it."""
+    for dp, _, files in os.walk(os.path.join(ROOT, "liliom_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", "Makefile")):
+                txt = open(os.path.join(dp, f), errors="ignore").read()
+                assert "oracle_lib" not in txt and "liboracle" not in txt and "oracle/" not in txt, os.path.join(dp, f)

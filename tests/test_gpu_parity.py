@@ -261,3 +261,43 @@ def test_full_size_properties():
     assert np.array_equal(p1, p2)
     assert np.linalg.norm(p1[4:] - T[4:]) < 0.02
     c.close()
+
+
+# ---------------------------------------------------------------- committed golden vectors (tests/golden)
+def test_gpu_against_golden_fixtures(ctx48):
+    import os
+    import liliom_b200 as L
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    g = np.load(os.path.join(gold, "horizon_small.npz"))
+    surf, edge, cut = ctx48.extract_horizon(g["pts"].view(L.PT48).reshape(-1), g["q_imu"])
+    assert surf.view(np.uint8).tobytes() == g["surf"].tobytes()
+    assert edge.view(np.uint8).tobytes() == g["edge"].tobytes()
+    assert cut.view(np.uint8).tobytes() == g["cut"].tobytes()
+    assert ctx48.voxelgrid(surf, 0.4).view(np.uint8).tobytes() == g["surf_ds"].tobytes()
+
+    g = np.load(os.path.join(gold, "rot_small.npz"))
+    p = L.default_params(1); p.ds_rate = int(g["ds_rate"]); p.line_num = int(g["line_num"])
+    c = L.Context(p)
+    surf, edge, cut = c.extract_rot(g["pts"].view(L.PT32).reshape(-1), g["q_imu"], g["q_lb"])
+    lab, cur = c.extract_rot_labels(len(cut))
+    assert cut.view(np.uint8).tobytes() == g["cut"].tobytes()
+    assert np.array_equal(lab, g["label"]) and cur.tobytes() == g["curv"].tobytes()
+    assert edge.view(np.uint8).tobytes() == g["edge"].tobytes()
+    assert surf.view(np.uint8).tobytes() == g["surf"].tobytes()
+    c.close()
+
+    g = np.load(os.path.join(gold, "s2m_small.npz"))
+    c = L.Context(variant=0)
+    c.map_set_points(g["map"])
+    valid, plane, idx, sqd, s29 = c.find_surf_corr(g["feats"], g["pose0"])
+    assert np.array_equal(valid, g["valid"])
+    ok = g["valid"] == 1
+    assert np.array_equal(idx[ok], g["nn_idx"][ok])
+    np.testing.assert_allclose(plane, g["plane"], rtol=2e-6, atol=1e-7)
+    np.testing.assert_allclose(s29, g["neq29"], rtol=1e-9, atol=1e-9)
+    pose, _ = c.scan_to_map(g["feats"], g["pose0"], 6, mode=L.MODE_GN)
+    _pose_close(pose, g["pose_gn6"])
+    pose, st = c.scan_to_map(g["feats"], g["pose0"], 2, max_num_iter=15, mode=L.MODE_CERES)
+    _pose_close(pose, g["pose_ceres"])
+    assert [s.lm_iters for s in st] == list(g["ceres_lm_iters"])
+    c.close()

@@ -1,0 +1,219 @@
+"""CPU tests of the oracle (no GPU): the from-knowledge restatements of Eigen / PCL / FLANN / Ceres
+against independent NumPy / SciPy implementations, and the committed golden vectors.
+The reference ships no tests or fixtures ("parity unpinned"): these checks are what pins the oracle."""
+import os
+
+import numpy as np
+import pytest
+from scipy.optimize import least_squares
+from scipy.spatial import cKDTree
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def ceres_plus(x, d):
+    nd = np.linalg.norm(d[:3])
+    out = np.array(x, float)
+    if nd > 0:
+        dq = np.concatenate([[np.cos(nd)], np.sin(nd) / nd * d[:3]])
+        aw, ax, ay, az = dq; bw, bx, by, bz = x[:4]
+        out[:4] = [aw * bw - ax * bx - ay * by - az * bz, aw * bx + ax * bw + ay * bz - az * by,
+                   aw * by + ay * bw + az * bx - ax * bz, aw * bz + az * bw + ax * by - ay * bx]
+    out[4:] = x[4:] + d[3:]
+    return out
+
+
+def test_eigen_sym3_matches_numpy(oracle):
+    rng = np.random.default_rng(0)
+    for k in range(200):
+        B = rng.normal(size=(3, 3)) * 10.0 ** rng.integers(-3, 3)
+        A = B @ B.T if k % 2 else (B + B.T)
+        ev, vec = oracle.eigen_sym3(A)
+        w, v = np.linalg.eigh(A)
+        np.testing.assert_allclose(ev, w, rtol=1e-10, atol=1e-12 * np.abs(w).max())
+        assert np.all(np.diff(ev) >= 0)
+        np.testing.assert_allclose(A @ vec, vec * ev, atol=1e-9 * max(1.0, np.abs(w).max()))
+        np.testing.assert_allclose(vec.T @ vec, np.eye(3), atol=1e-12)
+    ev, vec = oracle.eigen_sym3(np.zeros((3, 3)))
+    assert np.all(ev == 0)
+    ev, vec = oracle.eigen_sym3(np.diag([3.0, 1.0, 2.0]))
+    np.testing.assert_allclose(ev, [1, 2, 3])
+
+
+def test_colpiv_qr_matches_lstsq(oracle):
+    rng = np.random.default_rng(1)
+    for _ in range(200):
+        c = rng.uniform(-300, 300, 3)
+        n = rng.normal(size=3); n /= np.linalg.norm(n)
+        P = c + rng.uniform(-0.6, 0.6, (5, 3))
+        P -= np.outer((P - c) @ n, n) * 0.98          # nearly planar patch far from the origin
+        x = oracle.colpiv_qr_solve(P, -np.ones(5))
+        ref, *_ = np.linalg.lstsq(P, -np.ones(5), rcond=None)
+        np.testing.assert_allclose(x, ref, rtol=1e-6, atol=1e-9)
+    # rank-deficient (collinear) input: solution has a zero component, like Eigen's nonzero_pivots handling
+    t = np.linspace(0, 1, 5)[:, None]
+    P = np.array([10.0, 5.0, 1.0]) + t * np.array([0.0, 0.0, 1.0])
+    x = oracle.colpiv_qr_solve(P, -np.ones(5))
+    assert np.isfinite(x).all() and (x == 0).sum() >= 1
+    np.testing.assert_allclose(P @ x, -1, atol=1e-9)
+
+
+def test_slerp_matches_closed_form(oracle):
+    q = np.array([0.99995, 0.0, 0.0, 0.0099995])
+    for t in (0.0, 0.3, 1.0):
+        out = oracle.slerp_identity(q, t)
+        th = np.arccos(q[0])          # q is (almost) unit
+        np.testing.assert_allclose(out[0], np.sin((1 - t) * th) / np.sin(th) + np.sin(t * th) / np.sin(th) * q[0], rtol=1e-12)
+    np.testing.assert_allclose(oracle.slerp_identity([1, 0, 0, 0], 0.4), [1, 0, 0, 0])
+
+
+def test_voxelgrid_matches_numpy(oracle, world_small):
+    surf, _, _ = oracle.extract_horizon(world_small["hz"], world_small["q_hz"])
+    for leaf in (0.4, 0.6):
+        got = oracle.voxelgrid(surf, leaf)
+        inv = np.float32(1.0) / np.float32(leaf)
+        xyz = np.stack([surf["x"], surf["y"], surf["z"]], 1)
+        ijk = np.floor(xyz * inv).astype(np.int64)
+        mn = ijk.min(0); div = ijk.max(0) - mn + 1
+        idx = (ijk[:, 0] - mn[0]) + (ijk[:, 1] - mn[1]) * div[0] + (ijk[:, 2] - mn[2]) * div[0] * div[1]
+        uniq, inv_idx, counts = np.unique(idx, return_inverse=True, return_counts=True)
+        assert len(got) == len(uniq)
+        for f in ("x", "y", "z", "intensity", "curvature"):
+            acc = np.zeros(len(uniq), np.float32)
+            np.add.at(acc, inv_idx, surf[f])            # sequential fp32 accumulation in index order
+            np.testing.assert_array_equal(got[f], acc / counts.astype(np.float32))
+        nrm = np.sqrt(got["nx"] ** 2 + got["ny"] ** 2 + got["nz"] ** 2)
+        np.testing.assert_allclose(nrm, 1.0, atol=1e-5)
+
+
+def test_kdtree_matches_scipy_and_brute(oracle, world_small):
+    m = world_small["map"][:20000]
+    rng = np.random.default_rng(3)
+    q = m[rng.integers(0, len(m), 500)].copy()
+    q[:, :3] += rng.normal(0, 0.3, (500, 3)).astype(np.float32)
+    tree = oracle.KdTree(m)
+    idx, sqd = tree.knn5(q)
+    bidx, bsqd = oracle.knn5_brute(m, q)
+    assert np.array_equal(idx, bidx) and np.array_equal(sqd.view(np.uint32), bsqd.view(np.uint32))
+    d, ii = cKDTree(m[:, :3].astype(np.float64)).query(q[:, :3].astype(np.float64), k=5)
+    assert (np.sort(idx, 1) == np.sort(ii, 1)).all(1).mean() > 0.995   # fp32-vs-fp64 near-ties only
+    np.testing.assert_allclose(np.sqrt(sqd), d, rtol=1e-4, atol=1e-5)
+    assert np.all(np.diff(sqd, axis=1) >= 0)
+    # fewer than 5 points: padded with -1 / inf
+    t3 = oracle.KdTree(m[:3])
+    i3, d3 = t3.knn5(q[:2])
+    assert (i3[:, 3:] == -1).all() and np.isinf(d3[:, 3:]).all()
+
+
+def test_gradient_matches_finite_differences(oracle, world_small):
+    """J^T r from the closed-form/autodiff-faithful rows == d(cost)/d(delta) through ceres Plus."""
+    surf, _, _ = oracle.extract_horizon(world_small["hz"], world_small["q_hz"])
+    ds = oracle.voxelgrid(surf, 0.4)
+    tree = oracle.KdTree(world_small["map"])
+    pose = world_small["guess"]
+    cnt, valid, plane, idx, pw = oracle.find_surf_corr(tree, ds, pose)
+    s = oracle.normal_equations(ds, valid, plane, pose)
+    g = s[21:27]
+    h = 1e-6
+    for k in range(6):
+        d = np.zeros(6); d[k] = h
+        cp = oracle.normal_equations(ds, valid, plane, ceres_plus(pose, d))[27]
+        cm = oracle.normal_equations(ds, valid, plane, ceres_plus(pose, -d))[27]
+        assert abs((cp - cm) / (2 * h) - g[k]) < 1e-5 * max(1.0, abs(g[k])), (k, (cp - cm) / (2 * h), g[k])
+    assert s[28] == cnt
+
+
+def test_ceres_lm_matches_scipy_huber(oracle, world_small):
+    """ceres::Solve restatement vs scipy least_squares(loss='huber', f_scale=0.1) on the same frozen correspondences."""
+    surf, _, _ = oracle.extract_horizon(world_small["hz"], world_small["q_hz"])
+    ds = oracle.voxelgrid(surf, 0.4)
+    tree = oracle.KdTree(world_small["map"])
+    pose0 = world_small["guess"]
+    cnt, valid, plane, _, _ = oracle.find_surf_corr(tree, ds, pose0)
+    iters, pose_c, cost_c = oracle.ceres_solve(ds, valid, plane, pose0, 50)
+    P = np.stack([ds["x"], ds["y"], ds["z"]], 1).astype(np.float64)[valid == 1]
+    N = plane[valid == 1, :3].astype(np.float64); D = plane[valid == 1, 3].astype(np.float64)
+
+    def res(d):
+        x = ceres_plus(pose0, d)
+        qv = x[1:4]
+        uv = 2.0 * np.cross(qv, P)
+        pw = P + x[0] * uv + np.cross(qv, uv) + x[4:]
+        return (N * pw).sum(1) + D
+    sol = least_squares(res, np.zeros(6), loss="huber", f_scale=0.1, xtol=1e-14, ftol=1e-14, gtol=1e-14)
+    pose_s = ceres_plus(pose0, sol.x)
+    assert np.linalg.norm(pose_c[4:] - pose_s[4:]) < 2e-5
+    assert abs(abs(np.dot(pose_c[:4], pose_s[:4])) - 1.0) < 1e-9
+    assert abs(cost_c - sol.cost) < 1e-6 * max(1.0, sol.cost)
+    assert 1 <= iters <= 50
+
+
+def test_scan_to_map_recovers_true_pose(oracle, world_small):
+    surf, _, _ = oracle.extract_horizon(world_small["hz"], world_small["q_hz"])
+    ds = oracle.voxelgrid(surf, 0.4)
+    tree = oracle.KdTree(world_small["map"])
+    T = world_small["T"]
+    rc, pose, st = oracle.scan_to_map_gn(tree, ds, world_small["guess"], 10)
+    assert rc == 0 and np.linalg.norm(pose[4:] - T[4:]) < 0.02
+    rc, pose2, st2 = oracle.scan_to_map_ceres(tree, ds, world_small["guess"], 2, 15)
+    assert rc == 0 and np.linalg.norm(pose2[4:] - T[4:]) < 0.02 and pose2[0] > 0
+    rc, pose3, _ = oracle.scan_to_map_gn(oracle.KdTree(world_small["map"][:5]), ds, world_small["guess"], 2)
+    assert rc == -1 and np.array_equal(pose3, world_small["guess"])      # < 10 map points: pose untouched
+
+
+def test_horizon_extractor_structure(oracle, world_small):
+    surf, edge, cut = oracle.extract_horizon(world_small["hz"], world_small["q_hz"])
+    assert len(cut) == len(world_small["hz"])
+    assert len(surf) > 5000 and 0 < len(edge) < len(surf)
+    assert (surf["curvature"] > 0).all() and (edge["curvature"] > 0).all()
+    for c in (surf, edge):
+        n = np.sqrt(c["nx"] ** 2 + c["ny"] ** 2 + c["nz"] ** 2)
+        np.testing.assert_allclose(n, 1.0, atol=1e-5)
+    # surf points of one patch share one normal and lie on a plane through the patch
+    line = surf["intensity"].astype(np.int32)
+    assert set(np.unique(line)) <= set(range(6))
+
+
+def test_rot_extractor_structure(oracle, world_small):
+    rc, surf, edge, cut, lab, cur = oracle.extract_rot(world_small["hdl"], world_small["q_hdl"], (1, 0, 0, 0), 64, 1)
+    assert rc == 0 and len(cut) > 80000
+    ring = cut["intensity"].astype(np.int32)
+    assert np.all(np.diff(ring) >= -1) and ring.max() <= 50          # bucketed by ring, rings > 50 dropped
+    assert set(np.unique(lab)) <= {-1, 0, 1, 2}
+    assert (lab == 2).sum() <= 2 * 6 * 51 and (lab == -1).sum() <= 4 * 6 * 51
+    assert (cur[lab > 0] > 2.0).all() and (cur[lab == -1] < 0.1).all()
+    assert len(edge) == (lab > 0).sum()
+    assert oracle.extract_rot(world_small["hdl"], world_small["q_hdl"], (1, 0, 0, 0), 20, 1)[0] == -2
+
+
+# ---------------------------------------------------------------- golden vectors (tests/golden, made by tests/make_golden.py)
+def _same(a, b):
+    assert a.dtype == b.dtype and a.shape == b.shape
+    assert a.tobytes() == b.tobytes()
+
+
+def test_golden_horizon(oracle):
+    g = np.load(os.path.join(GOLD, "horizon_small.npz"))
+    surf, edge, cut = oracle.extract_horizon(g["pts"].view(oracle.PT48).reshape(-1), g["q_imu"], float(g["surf_thres"]), float(g["edge_thres"]))
+    _same(surf.view(np.uint8), g["surf"]); _same(edge.view(np.uint8), g["edge"]); _same(cut.view(np.uint8), g["cut"])
+    _same(oracle.voxelgrid(surf, 0.4).view(np.uint8), g["surf_ds"])
+
+
+def test_golden_rot(oracle):
+    g = np.load(os.path.join(GOLD, "rot_small.npz"))
+    rc, surf, edge, cut, lab, cur = oracle.extract_rot(g["pts"].view(oracle.PT32).reshape(-1), g["q_imu"], g["q_lb"], int(g["line_num"]), int(g["ds_rate"]))
+    _same(surf.view(np.uint8), g["surf"]); _same(edge.view(np.uint8), g["edge"]); _same(cut.view(np.uint8), g["cut"])
+    _same(lab, g["label"]); _same(cur, g["curv"])
+
+
+def test_golden_scan_to_map(oracle):
+    g = np.load(os.path.join(GOLD, "s2m_small.npz"))
+    tree = oracle.KdTree(g["map"])
+    cnt, valid, plane, idx, pw = oracle.find_surf_corr(tree, g["feats"], g["pose0"])
+    _same(valid, g["valid"]); _same(plane, g["plane"]); _same(idx, g["nn_idx"])
+    np.testing.assert_allclose(oracle.normal_equations(g["feats"], valid, plane, g["pose0"]), g["neq29"], rtol=1e-13)
+    rc, pose, st = oracle.scan_to_map_gn(tree, g["feats"], g["pose0"], 6)
+    np.testing.assert_allclose(pose, g["pose_gn6"], rtol=0, atol=1e-12)
+    rc, pose, st = oracle.scan_to_map_ceres(tree, g["feats"], g["pose0"], 2, 15)
+    np.testing.assert_allclose(pose, g["pose_ceres"], rtol=0, atol=1e-12)
+    assert [s.lm_iters for s in st] == list(g["ceres_lm_iters"])
