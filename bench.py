@@ -229,6 +229,8 @@ def main():
         pin_sweeps.append(t.numpy().view(L.PT48))
     cap = max(len(s["pts"]) for s in sweeps)
     out_surf = torch.empty(cap * 48, dtype=torch.uint8).pin_memory().numpy().view(L.PT48)
+    out_edge = torch.empty(cap * 48, dtype=torch.uint8).pin_memory().numpy().view(L.PT48)
+    out_cut = torch.empty(cap * 48, dtype=torch.uint8).pin_memory().numpy().view(L.PT48)
     out_ds = torch.empty(cap * 48, dtype=torch.uint8).pin_memory().numpy().view(L.PT48)
     pose_buf = torch.empty(7, dtype=torch.float64).pin_memory().numpy()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")     # > 126 MB L2
@@ -246,9 +248,10 @@ def main():
 
     def step_e2e(k):
         i = k % len(sweeps)
-        surf, edge, cut = ctx.extract_horizon(pin_sweeps[i], sweeps[i]["q"])          # Preprocessing node call
-        out_surf[:len(surf)] = surf                                                    # (the topic hop, host memory)
-        pose, st, ds = ctx.odometry(out_surf[:len(surf)], sweeps[i]["guess"], ITERS, mode=L.MODE_GN, ds_out=out_ds, pose_out=pose_buf)
+        # Preprocessing node call: H2D raw sweep, D2H the three published clouds (pinned host buffers)
+        surf, edge, cut = ctx.extract_horizon(pin_sweeps[i], sweeps[i]["q"], out=(out_surf, out_edge, out_cut))
+        # LidarOdometry node call on the /surf_features cloud as received (host): H2D, D2H pose + surf_last_ds
+        pose, st, ds = ctx.odometry(surf, sweeps[i]["guess"], ITERS, mode=L.MODE_GN, ds_out=out_ds, pose_out=pose_buf)
         h2d = len(pin_sweeps[i]) * 48 + len(surf) * 48 + 56
         d2h = (len(surf) + len(edge) + len(cut)) * 48 + len(ds) * 48 + 56
         return pose, h2d, d2h

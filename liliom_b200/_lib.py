@@ -157,11 +157,15 @@ class Context:
             raise LiliomError(rc, lib().liliom_last_error(self._h).decode())
 
     # ---- L1 ----
-    def extract_horizon(self, pts: np.ndarray, q_imu):
+    def extract_horizon(self, pts: np.ndarray, q_imu, out=None):
+        """out = optional (surf, edge, cut) caller-owned PT48 arrays (e.g. pinned) to receive the clouds."""
         pts = np.ascontiguousarray(pts, dtype=PT48)
         n = len(pts)
         q = np.asarray(q_imu, dtype=np.float64)
-        surf = np.zeros(max(n, 1), PT48); edge = np.zeros(max(n, 1), PT48); cut = np.zeros(max(n, 1), PT48)
+        if out is None:
+            surf = np.empty(max(n, 1), PT48); edge = np.empty(max(n, 1), PT48); cut = np.empty(max(n, 1), PT48)
+        else:
+            surf, edge, cut = out
         ns, ne, nc = C.c_int(), C.c_int(), C.c_int()
         self._check(lib().liliom_extract_horizon(self._h, _ptr(pts), n, _dptr(q), _ptr(surf), len(surf), C.byref(ns),
                                                  _ptr(edge), len(edge), C.byref(ne), _ptr(cut), len(cut), C.byref(nc)))
@@ -171,7 +175,7 @@ class Context:
         pts = np.ascontiguousarray(pts, dtype=PT32)
         n = len(pts)
         q = np.asarray(q_imu, dtype=np.float64); ql = np.asarray(q_lb, dtype=np.float64)
-        surf = np.zeros(max(n, 1), PT32); edge = np.zeros(max(n, 1), PT32); cut = np.zeros(max(n, 1), PT32)
+        surf = np.empty(max(n, 1), PT32); edge = np.empty(max(n, 1), PT32); cut = np.empty(max(n, 1), PT32)
         ns, ne, nc = C.c_int(), C.c_int(), C.c_int()
         self._check(lib().liliom_extract_rot(self._h, _ptr(pts), n, _dptr(q), _dptr(ql), _ptr(surf), len(surf), C.byref(ns),
                                              _ptr(edge), len(edge), C.byref(ne), _ptr(cut), len(cut), C.byref(nc)))

@@ -76,6 +76,7 @@ static int install_map_from_xyzw(liliom_ctx* c, int m) {
 }
 
 static int upload_feats(liliom_ctx* c, const void* feats, int n, int stride) {
+    c->d_nfeats = nullptr;
     if (n < 0 || (n > 0 && !feats)) return LILIOM_E_ARG;
     if (stride != 16 && stride != 32 && stride != 48) return LILIOM_E_ARG;
     c->n_feats = n;
@@ -414,7 +415,7 @@ extern "C" int liliom_extract_resident(liliom_ctx* c, const double q_imu[4], con
     // the extractors read c->raw: a device-to-device copy keeps the resident sweep reusable across steps
     LILI_CUDA(c, c->raw.ensure((size_t)(n > 0 ? n : 1) * stride));
     if (n > 0) LILI_CUDA(c, cudaMemcpyAsync(c->raw.p, c->raw_scan.p, (size_t)n * stride, cudaMemcpyDeviceToDevice, c->stream));
-    if (stride == 48) return horizon_extract_dev(c, n, q_imu, n_surf, n_edge, n_cut);
+    if (stride == 48) return horizon_extract_dev(c, n, q_imu, n_surf, n_edge, n_cut, /*sync_counts=*/false);
     const double ident[4] = {1, 0, 0, 0};
     return rot_extract_dev(c, n, q_imu, q_lb ? q_lb : ident, n_surf, n_edge, n_cut);
 }
@@ -424,28 +425,45 @@ static int odometry_on_resident_surf(liliom_ctx* c, double pose7[7], int match_c
     if (!c || !pose7 || (mode != LILIOM_MODE_CERES && mode != LILIOM_MODE_GN) || match_cnt < 0) return LILIOM_E_ARG;
     LILI_CUDA(c, cudaSetDevice(c->device));
     const int stride = c->prm.point_stride;
-    const int n = c->n_surf_dev;
-    LILI_CUDA(c, c->vg_out.ensure((size_t)(n > 0 ? n : 1) * stride));
+    // surf count: exact on the host (n_surf_dev >= 0) or only on the device (resident pipeline, no round trip)
+    const int n_max = c->n_surf_dev >= 0 ? c->n_surf_dev : c->n_surf_max;
+    const int* d_n = c->n_surf_dev >= 0 ? nullptr : c->d_nsurf;
+    LILI_CUDA(c, c->vg_out.ensure((size_t)(n_max > 0 ? n_max : 1) * stride));
     LILI_CUDA(c, c->vg_count.ensure(16));
-    int m = n;
+    LILI_CUDA(c, c->feats.ensure((size_t)(n_max > 0 ? n_max : 1) * sizeof(float4)));
     if (c->prm.leaf_scan > 0.0f) {
-        LILI_TRY(voxelgrid_dev(c, c->surf.p, n, stride, c->prm.leaf_scan, c->vg_out.p, c->vg_count.as<int>()));      // L/src/LidarOdometry.cpp:321-322
-        int* hp = reinterpret_cast<int*>(c->h_pin) + 1024;
-        LILI_CUDA(c, cudaMemcpyAsync(hp, c->vg_count.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-        LILI_CUDA(c, cudaStreamSynchronize(c->stream));
-        m = hp[0];
-    } else if (n > 0) {   // leaf_scan == 0: benchmark mode, every surf feature is a query
-        LILI_CUDA(c, cudaMemcpyAsync(c->vg_out.p, c->surf.p, (size_t)n * stride, cudaMemcpyDeviceToDevice, c->stream));
+        // L/src/LidarOdometry.cpp:321-322; the centroid kernel also emits the float4 queries
+        LILI_TRY(voxelgrid_dev2(c, c->surf.p, n_max, d_n, stride, c->prm.leaf_scan, c->vg_out.p, c->vg_count.as<int>(), c->feats.as<float4>()));
+        c->d_nfeats = c->vg_count.as<int>();
+    } else {   // leaf_scan == 0: benchmark mode, every surf feature is a query
+        if (n_max > 0) LILI_CUDA(c, cudaMemcpyAsync(c->vg_out.p, c->surf.p, (size_t)n_max * stride, cudaMemcpyDeviceToDevice, c->stream));
+        LILI_TRY(repack_to_f4(c, c->surf.p, n_max, stride, c->feats.as<float4>(), d_n));
+        c->d_nfeats = d_n;
     }
+    c->n_feats = n_max;
+    int rc = LILIOM_OK;
+    if (!c->map_ready) rc = LILIOM_E_NOMAP;
+    else if (c->map_n_global < 10) rc = LILIOM_E_FEWMAP;
+    if (rc == LILIOM_OK) rc = s2m_run(c, pose7, match_cnt, max_num_iter, mode, stats, false, nullptr);
+    else {   // still report surf_last_ds: read the count back
+        int* hp = reinterpret_cast<int*>(c->h_pin) + 1024;
+        if (c->d_nfeats) {
+            LILI_CUDA(c, cudaMemcpyAsync(hp, c->d_nfeats, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+            LILI_CUDA(c, cudaStreamSynchronize(c->stream));
+            c->n_feats_actual = hp[0] < n_max ? hp[0] : n_max;
+        } else c->n_feats_actual = n_max;
+    }
+    c->d_nfeats = nullptr;
+    const int m = c->n_feats_actual;
     if (n_ds) *n_ds = m;
-    if (ds_out && m > ds_cap) return LILIOM_E_CAPACITY;
-    LILI_CUDA(c, c->feats.ensure((size_t)(m > 0 ? m : 1) * sizeof(float4)));
-    LILI_TRY(repack_to_f4(c, c->vg_out.p, m, stride, c->feats.as<float4>()));
-    c->n_feats = m;
-    if (ds_out && m) LILI_CUDA(c, cudaMemcpyAsync(ds_out, c->vg_out.p, (size_t)m * stride, cudaMemcpyDeviceToHost, c->stream));
-    if (!c->map_ready) { LILI_CUDA(c, cudaStreamSynchronize(c->stream)); return LILIOM_E_NOMAP; }
-    if (c->map_n_global < 10) { LILI_CUDA(c, cudaStreamSynchronize(c->stream)); return LILIOM_E_FEWMAP; }
-    return s2m_run(c, pose7, match_cnt, max_num_iter, mode, stats, false, nullptr);
+    if (ds_out) {
+        if (m > ds_cap) return LILIOM_E_CAPACITY;
+        if (m) {
+            LILI_CUDA(c, cudaMemcpyAsync(ds_out, c->vg_out.p, (size_t)m * stride, cudaMemcpyDeviceToHost, c->stream));
+            LILI_CUDA(c, cudaStreamSynchronize(c->stream));
+        }
+    }
+    return rc;
 }
 
 extern "C" int liliom_odometry_resident(liliom_ctx* c, double pose7[7], int match_cnt, int max_num_iter, int mode, liliom_iter_stats* stats,

@@ -129,6 +129,7 @@ static int backend_prepare(liliom_ctx* c, const void* feats, int n, int stride) 
     if (n < 0 || (n > 0 && !feats)) return LILIOM_E_ARG;
     if (stride != 16 && stride != 32 && stride != 48) return LILIOM_E_ARG;
     c->n_feats = n;
+    c->d_nfeats = nullptr;
     if (n == 0) return LILIOM_OK;
     LILI_CUDA(c, c->feats.ensure((size_t)n * sizeof(float4)));
     if (stride == 16) {

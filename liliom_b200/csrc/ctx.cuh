@@ -72,7 +72,12 @@ struct liliom_ctx {
     lili::DevBuf raw, cut, surf, edge, flags, scan_tmp, idx_a, idx_b;
     lili::DevBuf hz_mat, hz_stage_surf, hz_stage_edge, hz_counts;
     lili::DevBuf rot_keys, rot_keys2, rot_vals, rot_vals2, rot_cloud, rot_curv, rot_label, rot_picked, rot_sort, rot_ring, rot_meta, rot_lessflat, rot_seg_edge;
-    int n_surf_dev = 0;          // surf features resident after the last extract call
+    int n_surf_dev = 0;          // surf features resident after the last extract call (-1: only known on the device)
+    const int* d_nsurf = nullptr; // device-side count of the resident surf features
+    int n_surf_max = 0;          // host upper bound for it
+    const int* d_nfeats = nullptr; // device-side query count for scan-to-map (nullptr: n_feats is exact)
+    int last_n_feats = 0;        // query count of the previous scan (kernel-shape predictor)
+    int n_feats_actual = 0;      // query count read back with the pose
     lili::DevBuf raw_scan;       // resident raw sweep (liliom_upload_scan)
     int n_raw_scan = 0;
     int n_rot_cloud = 0;
@@ -116,6 +121,7 @@ struct liliom_ctx {
     std::vector<cudaEvent_t> ev_pool;
     size_t ev_used = 0;
     std::vector<std::pair<size_t, unsigned long long>> ev_pending;  // (event pair index, queries)
+    std::vector<int> ev_iters;           // kernel-body passes covered by each pending pair
 };
 
 namespace lili {
@@ -155,6 +161,8 @@ int exclusive_scan_i32(liliom_ctx* c, const int* in, int* out, int n);   // out 
 
 // VoxelGrid on device buffers; d_count receives the output count (int, device).
 int voxelgrid_dev(liliom_ctx* c, const void* d_in, int n, int stride, float leaf, void* d_out, int* d_count);
+// n_max = host upper bound, d_n = optional device-side count (<= n_max); d_feats (optional) also receives float4{x,y,z,index}
+int voxelgrid_dev2(liliom_ctx* c, const void* d_in, int n_max, const int* d_n, int stride, float leaf, void* d_out, int* d_count, float4* d_feats);
 
 // grid build from float4 points already on the device (map_xyzw[0..m)).
 int grid_build(liliom_ctx* c, int m);
@@ -162,9 +170,9 @@ int grid_build(liliom_ctx* c, int m);
 int s2m_run(liliom_ctx* c, double pose7[7], int match_cnt, int max_num_iter, int mode, liliom_iter_stats* stats,
             bool want_corr, double out29[29]);
 
-int horizon_extract_dev(liliom_ctx* c, int n, const double q_imu[4], int* n_surf, int* n_edge, int* n_cut);
+int horizon_extract_dev(liliom_ctx* c, int n, const double q_imu[4], int* n_surf, int* n_edge, int* n_cut, bool sync_counts = true);
 int rot_extract_dev(liliom_ctx* c, int n, const double q_imu[4], const double q_lb[4], int* n_surf, int* n_edge, int* n_cut);
 
-int repack_to_f4(liliom_ctx* c, const void* d_in, int n, int stride, float4* d_out);
+int repack_to_f4(liliom_ctx* c, const void* d_in, int n, int stride, float4* d_out, const int* d_n = nullptr);
 
 }  // namespace lili

@@ -245,7 +245,7 @@ __global__ void k_hz_emit(const Pt48* __restrict__ stage_surf, const Pt48* __res
 
 // raw points must already be in c->raw (n x 48 B).  Leaves cut/surf/edge on the device and the
 // three counts in pinned host memory (returned through the pointers after a stream sync).
-int horizon_extract_dev(liliom_ctx* c, int n, const double q_imu[4], int* n_surf, int* n_edge, int* n_cut) {
+int horizon_extract_dev(liliom_ctx* c, int n, const double q_imu[4], int* n_surf, int* n_edge, int* n_cut, bool sync_counts) {
     const size_t npts = (size_t)(n > 0 ? n : 1);
     LILI_CUDA(c, c->cut.ensure(npts * sizeof(Pt48)));
     LILI_CUDA(c, c->surf.ensure((size_t)HZ_PATCHES * 36 * sizeof(Pt48)));
@@ -282,6 +282,13 @@ int horizon_extract_dev(liliom_ctx* c, int n, const double q_imu[4], int* n_surf
     k_hz_emit<<<HZ_PATCHES, 64, 0, c->stream>>>(c->hz_stage_surf.as<Pt48>(), c->hz_stage_edge.as<Pt48>(), counts, offs,
                                                 c->surf.as<Pt48>(), c->edge.as<Pt48>());
     LILI_TRY(launch_check(c, "k_hz_emit"));
+    c->d_nsurf = totals;
+    c->n_surf_max = min(n, HZ_PATCHES * 36);
+    if (!sync_counts) {          // resident pipeline: the counts stay on the device, no host round trip
+        c->n_surf_dev = -1;
+        *n_surf = *n_edge = *n_cut = -1;
+        return LILIOM_OK;
+    }
     int* hp = reinterpret_cast<int*>(c->h_pin);
     LILI_CUDA(c, cudaMemcpyAsync(hp, totals, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     LILI_CUDA(c, cudaMemcpyAsync(hp + 2, cidx + n, sizeof(int), cudaMemcpyDeviceToHost, c->stream));

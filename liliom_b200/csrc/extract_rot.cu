@@ -485,6 +485,8 @@ int rot_extract_dev(liliom_ctx* c, int n, const double q_imu[4], const double q_
     if (hp[M_ERR]) { c->last_error = "ring/segment larger than the shared-memory capacity (16384 / 4096 points)"; return LILIOM_E_CAPACITY; }
     *n_cut = hp[M_NVALID]; *n_edge = hp[M_NEDGE]; *n_surf = hp[8];
     c->n_surf_dev = hp[8];
+    c->d_nsurf = c->vg_count.as<int>();
+    c->n_surf_max = n;
     c->n_rot_cloud = hp[M_NVALID];
     return LILIOM_OK;
 }

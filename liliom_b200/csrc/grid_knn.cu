@@ -26,17 +26,18 @@
 namespace lili {
 
 // ------------------------------------------------------------------ small utilities
-__global__ void k_repack_f4(const unsigned char* __restrict__ in, int n, int stride, float4* __restrict__ out) {
+__global__ void k_repack_f4(const unsigned char* __restrict__ in, int n_max, const int* __restrict__ d_n, int stride, float4* __restrict__ out) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = d_n ? min(*d_n, n_max) : n_max;
     if (i >= n) return;
     float4 v = *reinterpret_cast<const float4*>(in + (size_t)i * stride);
     v.w = __int_as_float(i);
     out[i] = v;
 }
 
-int repack_to_f4(liliom_ctx* c, const void* d_in, int n, int stride, float4* d_out) {
+int repack_to_f4(liliom_ctx* c, const void* d_in, int n, int stride, float4* d_out, const int* d_n) {
     if (n <= 0) return LILIOM_OK;
-    k_repack_f4<<<cdiv(n, 256), 256, 0, c->stream>>>((const unsigned char*)d_in, n, stride, d_out);
+    k_repack_f4<<<cdiv(n, 256), 256, 0, c->stream>>>((const unsigned char*)d_in, n, d_n, stride, d_out);
     return launch_check(c, "k_repack_f4");
 }
 
@@ -158,7 +159,7 @@ int grid_build(liliom_ctx* c, int m) {
 
 // ------------------------------------------------------------------ the hot kernel
 struct KnnArgs {
-    const float4* feats; int n;
+    const float4* feats; int n; const int* n_dev;   // n = host upper bound, n_dev = optional device-side count
     const float4* map; const float4* map_orig; const int* cell_start; GridDesc g;   // cell-sorted / download-order map
     const double* pose;                 // 7 doubles in HBM
     double max_sqd, plane_thres, w_gate, huber_a;
@@ -194,35 +195,35 @@ __device__ __forceinline__ double q_t7(const Q4& q, const D3& t, int k) {
     return k == 0 ? q.w : k == 1 ? q.x : k == 2 ? q.y : k == 3 ? q.z : k == 4 ? t.x : k == 5 ? t.y : t.z;
 }
 
-template <int LANES>
-__global__ void __launch_bounds__(kBlock, 2) k_knn_plane(KnnArgs a) {
-    constexpr int GROUPS = 32 / LANES;                 // queries a warp searches concurrently
-    __shared__ Slot slots[kWarps][32];
-    __shared__ __align__(16) Row rows[kWarps][32];
-    __shared__ unsigned char rvalid[kWarps][32];
-    __shared__ double red[kWarps][kNormEq];
-    __shared__ unsigned long long red_cand[kWarps];
-    __shared__ bool is_last;
+struct KnnSmem {
+    Slot slots[kWarps][32];
+    Row rows[kWarps][32];
+    unsigned char rvalid[kWarps][32];
+    double red[kWarps][kNormEq];
+    unsigned long long red_cand[kWarps];
+    double pose[8];
+    int is_last;
+};
 
+#define LILI_STAMP(i) do { if (a.dbg && blockIdx.x == 0 && threadIdx.x == 0) a.dbg[i] = clock64(); } while (0)
+#define LILI_STAMP_LAST(i) do { if (a.dbg && threadIdx.x == 0) a.dbg[i] = clock64(); } while (0)
+
+// One pass over this block's share of the queries at pose (q,t): phases A (search), B (fit + row), C (lane k
+// accumulates scalar k).  On return lane k < 29 of every warp holds its partial of scalar k in `acc`.
+template <int LANES>
+__device__ __forceinline__ void knn_phases(const KnnArgs& a, const Q4& q, const D3& t, const int n_q, KnnSmem& S,
+                                           double& acc, unsigned long long& cand) {
+    constexpr int GROUPS = 32 / LANES;                 // queries a warp searches concurrently
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int sub = lane & (LANES - 1);
     const int grp = lane / LANES;
     const unsigned gmask = (LANES == 32) ? 0xffffffffu : (((1u << LANES) - 1u) << (grp * LANES));
-
-#define LILI_STAMP(i) do { if (a.dbg && blockIdx.x == 0 && threadIdx.x == 0) a.dbg[i] = clock64(); } while (0)
-#define LILI_STAMP_LAST(i) do { if (a.dbg && threadIdx.x == 0) a.dbg[i] = clock64(); } while (0)
-    LILI_STAMP(0);
-    const Q4 q{a.pose[0], a.pose[1], a.pose[2], a.pose[3]};
-    const D3 t{a.pose[4], a.pose[5], a.pose[6]};
-
     // lane k (< 29) owns scalar k of the normal equations: no per-lane 29-vector, no final shuffle tree
-    double acc = 0.0;
     const int pa = lane < 27 ? kPairA[lane] : 0, pb = lane < 27 ? kPairB[lane] : 0;
-    unsigned long long cand = 0;
 
     const int per_task = GROUPS * a.rounds;            // <= 32
-    const int ntasks = (a.n + per_task - 1) / per_task;
+    const int ntasks = (n_q + per_task - 1) / per_task;
     const int gw = blockIdx.x * kWarps + warp;
     const int nw = gridDim.x * kWarps;
 
@@ -236,7 +237,7 @@ __global__ void __launch_bounds__(kBlock, 2) k_knn_plane(KnnArgs a) {
             Top5 top;
             top5_init(top);
             float sx = 0.f, sy = 0.f, sz = 0.f;
-            bool live = qi < a.n;
+            bool live = qi < n_q;
             if (live) {
                 const float4 f = a.feats[qi];
                 const D3 pw = qrot_x(q, D3{(double)f.x, (double)f.y, (double)f.z});             // L/src/LidarOdometry.cpp:230-231
@@ -248,7 +249,7 @@ __global__ void __launch_bounds__(kBlock, 2) k_knn_plane(KnnArgs a) {
             if (live) group_knn5<LANES>(sx, sy, sz, a.map, a.cell_start, a.g, sub, gmask, top, cand, (a.dbg && blockIdx.x == 0 && threadIdx.x == 0) ? a.dbg : nullptr);
             LILI_STAMP(11);
             if (sub == 0) {
-                Slot& s = slots[warp][slot];
+                Slot& s = S.slots[warp][slot];
                 const bool ok = live && top.k4 != ~0ull && ((double)top5_dist(top.k4) < a.max_sqd);  // :365
                 s.idx[0] = ok ? top5_index(top.k0) : -1; s.idx[1] = top5_index(top.k1); s.idx[2] = top5_index(top.k2);
                 s.idx[3] = top5_index(top.k3); s.idx[4] = top5_index(top.k4);
@@ -271,9 +272,9 @@ __global__ void __launch_bounds__(kBlock, 2) k_knn_plane(KnnArgs a) {
         bool ok = false;
         if (lane < per_task) {
             const int qi = task * per_task + lane;
-            const Slot s = slots[warp][lane];
+            const Slot s = S.slots[warp][lane];
             float pl0 = 0.f, pl1 = 0.f, pl2 = 0.f, pl3 = 0.f;
-            if (qi < a.n && s.idx[0] >= 0) {
+            if (qi < n_q && s.idx[0] >= 0) {
                 float4 m[5];
 #pragma unroll
                 for (int j = 0; j < 5; ++j) m[j] = __ldg(a.map_orig + s.idx[j]);                                     // :369-371
@@ -301,7 +302,7 @@ __global__ void __launch_bounds__(kBlock, 2) k_knn_plane(KnnArgs a) {
                     }
                 }
             }
-            if (qi < a.n) {
+            if (qi < n_q) {
                 if (a.valid) a.valid[qi] = ok ? 1 : 0;
                 if (a.plane) a.plane[qi] = make_float4(pl0, pl1, pl2, pl3);
             }
@@ -317,7 +318,7 @@ __global__ void __launch_bounds__(kBlock, 2) k_knn_plane(KnnArgs a) {
                 double rho0 = s2, rho1 = 1.0;
                 if (s2 > b2) { const double rt = sqrt(s2); rho0 = 2.0 * a.huber_a * rt - b2; rho1 = fmax(DBL_MIN, a.huber_a / rt); }
                 const double sr = sqrt(rho1);
-                Row& R = rows[warp][lane];
+                Row& R = S.rows[warp][lane];
                 R.J[0] = sr * 2.0 * (rp.y * nz - rp.z * ny);
                 R.J[1] = sr * 2.0 * (rp.z * nx - rp.x * nz);
                 R.J[2] = sr * 2.0 * (rp.x * ny - rp.y * nx);
@@ -325,7 +326,7 @@ __global__ void __launch_bounds__(kBlock, 2) k_knn_plane(KnnArgs a) {
                 R.r = sr * r;
                 R.half_rho = 0.5 * rho0;
             }
-            rvalid[warp][lane] = ok ? 1 : 0;
+            S.rvalid[warp][lane] = ok ? 1 : 0;
         }
         __syncwarp();
         LILI_STAMP(2);
@@ -333,8 +334,8 @@ __global__ void __launch_bounds__(kBlock, 2) k_knn_plane(KnnArgs a) {
         if (lane < kNormEq) {
 #pragma unroll 1
             for (int sl = 0; sl < per_task; ++sl) {
-                if (!rvalid[warp][sl]) continue;
-                const double* R = reinterpret_cast<const double*>(&rows[warp][sl]);
+                if (!S.rvalid[warp][sl]) continue;
+                const double* R = reinterpret_cast<const double*>(&S.rows[warp][sl]);
                 if (lane < 27) acc += R[pa] * R[pb];
                 else if (lane == 27) acc += R[7];
                 else acc += 1.0;
@@ -343,80 +344,118 @@ __global__ void __launch_bounds__(kBlock, 2) k_knn_plane(KnnArgs a) {
         __syncwarp();
     }
 
-    LILI_STAMP(3);
-    // ---------------- block reduction of the 29 sums (+ candidate counter)
-    if (lane < kNormEq) red[warp][lane] = acc;
+}
+
+// Block partial -> partials[29][G] (scalar-major) + candidate counter.
+__device__ __forceinline__ void write_block_partials(const KnnArgs& a, KnnSmem& S, double acc, unsigned long long cand) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane < kNormEq) S.red[warp][lane] = acc;
     {
         unsigned long long v = cand;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == 0) red_cand[warp] = v;
+        if (lane == 0) S.red_cand[warp] = v;
     }
     __syncthreads();
     const int G = gridDim.x;
     if (threadIdx.x < kNormEq) {
         double v = 0;
 #pragma unroll
-        for (int w = 0; w < kWarps; ++w) v += red[w][threadIdx.x];
+        for (int w = 0; w < kWarps; ++w) v += S.red[w][threadIdx.x];
         a.partials[(size_t)threadIdx.x * G + blockIdx.x] = v;          // scalar-major: [29][G]
     }
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == 0 && a.cand_total) {
         unsigned long long v = 0;
-        for (int w = 0; w < kWarps; ++w) v += red_cand[w];
-        if (a.cand_total && v) atomicAdd(a.cand_total, v);
+        for (int w = 0; w < kWarps; ++w) v += S.red_cand[w];
+        if (v) atomicAdd(a.cand_total, v);
     }
+}
+
+// Fixed-order sum over the G block partials into S.red[0][0..28]: 8 lanes per scalar, 4 independent loads
+// in flight per lane — this is exposed latency, so it is laid out for memory-level parallelism.
+__device__ __forceinline__ void reduce_partials(const KnnArgs& a, KnnSmem& S) {
+    const int G = gridDim.x;
+    const int sc = threadIdx.x >> 3, l8 = threadIdx.x & 7;
+    double v = 0.0;
+    if (sc < kNormEq) {
+        const double* src = a.partials + (size_t)sc * G;
+        double v0 = 0, v1 = 0, v2 = 0, v3 = 0;
+        int b = l8;
+        for (; b + 24 < G; b += 32) {
+            v0 += __ldcg(src + b); v1 += __ldcg(src + b + 8); v2 += __ldcg(src + b + 16); v3 += __ldcg(src + b + 24);
+        }
+        for (; b < G; b += 8) v0 += __ldcg(src + b);
+        v = (v0 + v1) + (v2 + v3);
+    }
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    if (l8 == 0 && sc < kNormEq) S.red[0][sc] = v;
+    __syncthreads();
+}
+
+// One thread: 6x6 solve of the reduced normal equations in S.red[0], Plus, sign-unify -> xn.
+__device__ __forceinline__ void gn_step(const KnnSmem& S, const Q4& q, const D3& t, double xn[7]) {
+    double s[kNormEq];
+#pragma unroll
+    for (int k = 0; k < kNormEq; ++k) s[k] = S.red[0][k];
+    double x[7], nb[6], d[6];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) x[k] = q_t7(q, t, k);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) nb[k] = -s[21 + k];
+    const bool solved = solve6_ldlt(s, nb, d);
+    if (s[28] > 0.0 && solved) pose_plus(x, d, xn);
+    else {
+#pragma unroll
+        for (int k = 0; k < 7; ++k) xn[k] = x[k];
+    }
+    if (xn[0] < 0) { xn[0] = -xn[0]; xn[1] = -xn[1]; xn[2] = -xn[2]; xn[3] = -xn[3]; }   // :539-549
+}
+
+__device__ __forceinline__ void write_neq_stats(const KnnArgs& a, const KnnSmem& S, double* stats, bool with_stats) {
+    if (threadIdx.x < kNormEq) {
+        const double v = S.red[0][threadIdx.x];
+        a.neq[threadIdx.x] = v;
+        if (with_stats && stats) {
+            if (threadIdx.x < 27) stats[3 + threadIdx.x] = v;
+            else if (threadIdx.x == 27) stats[2] = v;
+            else { stats[0] = v; stats[1] = 1.0; }
+        }
+    }
+}
+
+template <int LANES>
+__global__ void __launch_bounds__(kBlock, 2) k_knn_plane(KnnArgs a) {
+    __shared__ __align__(16) KnnSmem S;
+    LILI_STAMP(0);
+    const Q4 q{a.pose[0], a.pose[1], a.pose[2], a.pose[3]};
+    const D3 t{a.pose[4], a.pose[5], a.pose[6]};
+    const int n_q = a.n_dev ? min(*a.n_dev, a.n) : a.n;
+    double acc = 0.0;
+    unsigned long long cand = 0;
+    knn_phases<LANES>(a, q, t, n_q, S, acc, cand);
+    LILI_STAMP(3);
+    write_block_partials(a, S, acc, cand);
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
-        unsigned int tk = atomicAdd(a.ticket, 1u);
-        is_last = (tk == gridDim.x - 1);
+        const unsigned int tk = atomicAdd(a.ticket, 1u);
+        S.is_last = (tk == gridDim.x - 1);
     }
     __syncthreads();
     LILI_STAMP(4);
-    if (!is_last) return;
+    if (!S.is_last) return;
     __threadfence();
     LILI_STAMP_LAST(5);
-    // ---------------- last block: fixed-order sum over blocks, then the 6x6 step.
-    // 8 lanes per scalar, 4 independent loads in flight per lane: the tail is exposed latency (every
-    // other SM is idle by now), so it is laid out for memory-level parallelism, not for work efficiency.
-    {
-        const int sc = threadIdx.x >> 3, l8 = threadIdx.x & 7;
-        double v = 0.0;
-        if (sc < kNormEq) {
-            const double* src = a.partials + (size_t)sc * G;
-            double v0 = 0, v1 = 0, v2 = 0, v3 = 0;
-            int b = l8;
-            for (; b + 24 < G; b += 32) {
-                v0 += __ldcg(src + b); v1 += __ldcg(src + b + 8); v2 += __ldcg(src + b + 16); v3 += __ldcg(src + b + 24);
-            }
-            for (; b < G; b += 8) v0 += __ldcg(src + b);
-            v = (v0 + v1) + (v2 + v3);
-        }
-        v += __shfl_xor_sync(0xffffffffu, v, 1);
-        v += __shfl_xor_sync(0xffffffffu, v, 2);
-        v += __shfl_xor_sync(0xffffffffu, v, 4);
-        if (l8 == 0 && sc < kNormEq) red[0][sc] = v;
-    }
-    __syncthreads();
+    // ---------------- last block: fixed-order sum over blocks, then the 6x6 step
+    reduce_partials(a, S);
     LILI_STAMP_LAST(6);
     if (threadIdx.x == 0) {
         *a.ticket = 0;
-        double s[kNormEq];
-#pragma unroll
-        for (int k = 0; k < kNormEq; ++k) s[k] = red[0][k];
         if (a.update_pose) {
-            double x[7], xn[7], nb[6], d[6];
-#pragma unroll
-            for (int k = 0; k < 7; ++k) x[k] = q_t7(q, t, k);
-#pragma unroll
-            for (int k = 0; k < 6; ++k) nb[k] = -s[21 + k];
-            const bool solved = solve6_ldlt(s, nb, d);
-            if (s[28] > 0.0 && solved) pose_plus(x, d, xn);
-            else {
-#pragma unroll
-                for (int k = 0; k < 7; ++k) xn[k] = x[k];
-            }
-            if (xn[0] < 0) { xn[0] = -xn[0]; xn[1] = -xn[1]; xn[2] = -xn[2]; xn[3] = -xn[3]; }   // :539-549
+            double xn[7];
+            gn_step(S, q, t, xn);
 #pragma unroll
             for (int k = 0; k < 7; ++k) a.pose_out[k] = xn[k];
             if (a.stats) {
@@ -426,15 +465,64 @@ __global__ void __launch_bounds__(kBlock, 2) k_knn_plane(KnnArgs a) {
         }
     }
     LILI_STAMP_LAST(7);
-    // neq + stats are written by the first 29 threads in parallel (off the serial path)
-    if (threadIdx.x < kNormEq) {
-        const double v = red[0][threadIdx.x];
-        a.neq[threadIdx.x] = v;
-        if (a.update_pose && a.stats) {
-            if (threadIdx.x < 27) a.stats[3 + threadIdx.x] = v;
-            else if (threadIdx.x == 27) a.stats[2] = v;
-            else { a.stats[0] = v; a.stats[1] = 1.0; }
+    write_neq_stats(a, S, a.stats, a.update_pose != 0);
+}
+
+// All GN iterations in ONE cooperative launch (single GPU, GN mode): per iteration the blocks meet at one
+// grid barrier after publishing their partials; then EVERY block sums the partials and solves the 6x6
+// system redundantly (bit-identical), so no second barrier or broadcast is needed.  Removes the launch
+// gap, the drain and the ticket round trip of the per-iteration kernel (~6 us of ~18 per iteration).
+template <int LANES>
+__global__ void __launch_bounds__(kBlock, 2) k_gn_persistent(KnnArgs a, int iters, unsigned int* bar, double* stats_base) {
+    __shared__ __align__(16) KnnSmem S;
+    const int n_q = a.n_dev ? min(*a.n_dev, a.n) : a.n;
+    if (threadIdx.x < 7) S.pose[threadIdx.x] = a.pose[threadIdx.x];
+    __syncthreads();
+    const unsigned int G = gridDim.x;
+#pragma unroll 1
+    for (int it = 0; it < iters; ++it) {
+        const Q4 q{S.pose[0], S.pose[1], S.pose[2], S.pose[3]};
+        const D3 t{S.pose[4], S.pose[5], S.pose[6]};
+        double acc = 0.0;
+        unsigned long long cand = 0;
+        knn_phases<LANES>(a, q, t, n_q, S, acc, cand);
+        write_block_partials(a, S, acc, cand);
+        // ---- grid barrier (generation counter; all blocks are co-resident: cooperative launch)
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned int gen = *reinterpret_cast<volatile unsigned int*>(bar + 1);
+            if (atomicAdd(bar, 1u) == G - 1) {
+                *reinterpret_cast<volatile unsigned int*>(bar) = 0u;
+                __threadfence();
+                atomicAdd(bar + 1, 1u);
+            } else {
+                while (*reinterpret_cast<volatile unsigned int*>(bar + 1) == gen) { }
+            }
+            __threadfence();
         }
+        __syncthreads();
+        reduce_partials(a, S);
+        double* stats = stats_base ? stats_base + (size_t)it * kStatsDoubles : nullptr;
+        if (threadIdx.x == 0) {
+            double xn[7];
+            gn_step(S, q, t, xn);
+#pragma unroll
+            for (int k = 0; k < 7; ++k) S.pose[k] = xn[k];
+            if (blockIdx.x == 0) {
+#pragma unroll
+                for (int k = 0; k < 7; ++k) a.pose_out[k] = xn[k];
+                if (stats) {
+#pragma unroll
+                    for (int k = 0; k < 7; ++k) stats[30 + k] = xn[k];
+                }
+            }
+        }
+        if (blockIdx.x == 0) write_neq_stats(a, S, stats, true);
+        __syncthreads();
+        // the partials of this iteration may only be overwritten after every block has summed them: the next
+        // barrier is behind the next write, so alternate between two partial buffers
+        a.partials = (it & 1) ? a.partials - (size_t)kNormEq * G : a.partials + (size_t)kNormEq * G;
     }
 }
 
@@ -463,7 +551,7 @@ __global__ void k_gn_update(const double* __restrict__ neq, double* __restrict__
 // iteration 0, D = sqrt(clamp(diag)/radius), rho-based radius update), with the dense QR on
 // [J; D] replaced by its normal equations (J^T J + D^2) y = J^T r in fp64 (6x6 LDL^T).
 struct LmArgs {
-    const float4* feats; const unsigned char* valid; const float4* plane; int n;
+    const float4* feats; const unsigned char* valid; const float4* plane; int n; const int* n_dev;
     double* pose;         // in/out
     double* stats;        // slot of this outer iteration
     double huber_a;
@@ -479,7 +567,8 @@ __device__ void lm_eval(const LmArgs& a, const double x[7], double out[kNormEq],
     double acc[kNormEq];
 #pragma unroll
     for (int k = 0; k < kNormEq; ++k) acc[k] = 0.0;
-    for (int i = threadIdx.x; i < a.n; i += blockDim.x) {
+    const int n_c = a.n_dev ? min(*a.n_dev, a.n) : a.n;
+    for (int i = threadIdx.x; i < n_c; i += blockDim.x) {
         if (!a.valid[i]) continue;
         float4 f = a.feats[i];
         float4 pl = a.plane[i];
@@ -682,16 +771,17 @@ int s2m_run(liliom_ctx* c, double pose7[7], int match_cnt, int max_num_iter, int
     const int n = c->n_feats;
     if (match_cnt < 0) return LILIOM_E_ARG;
     const int iters = match_cnt;
+    const int n_est = c->d_nfeats ? (c->last_n_feats > 0 ? min(c->last_n_feats, n) : n) : n;   // device-side count: predict from the last scan
     int lanes = 8, rounds = 1;
-    pick_shape(n, c->sm_count, lanes, rounds);
+    pick_shape(n_est, c->sm_count, lanes, rounds);
     if (c->force_lanes) { lanes = c->force_lanes; rounds = c->force_rounds > 0 ? c->force_rounds : 1; }
     if ((32 / lanes) * rounds > 32) rounds = lanes;   // at most 32 queries per warp task
     const int per_task = (32 / lanes) * rounds;
-    const int ntasks = cdiv(n, per_task);
+    const int ntasks = cdiv(c->d_nfeats ? max(n_est + n_est / 4, 1) : n, per_task);
     int grid = min(max(cdiv(ntasks, kWarps), 1), c->sm_count * 2);
 
     LILI_CUDA(c, c->pose_dev.ensure(16 * sizeof(double)));
-    LILI_CUDA(c, c->partials.ensure((size_t)grid * kNormEq * sizeof(double)));
+    LILI_CUDA(c, c->partials.ensure((size_t)2 * grid * kNormEq * sizeof(double)));   // two buffers (persistent kernel alternates)
     LILI_CUDA(c, c->neq.ensure(32 * sizeof(double)));
     LILI_CUDA(c, c->stats_dev.ensure((size_t)(iters + 1) * kStatsDoubles * sizeof(double)));
     if (!c->counter.p) {
@@ -712,7 +802,7 @@ int s2m_run(liliom_ctx* c, double pose7[7], int match_cnt, int max_num_iter, int
     LILI_CUDA(c, cudaMemcpyAsync(c->pose_dev.p, pose7, 7 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
 
     KnnArgs a{};
-    a.feats = c->feats.as<float4>(); a.n = n;
+    a.feats = c->feats.as<float4>(); a.n = n; a.n_dev = c->d_nfeats;
     a.map = c->map_sorted.as<float4>(); a.map_orig = c->map_xyzw.as<float4>(); a.cell_start = c->cell_start.as<int>(); a.g = c->grid;
     a.pose = c->pose_dev.as<double>(); a.pose_out = c->pose_dev.as<double>();
     a.max_sqd = c->prm.knn_max_sqdist; a.plane_thres = c->prm.plane_thres; a.w_gate = c->prm.weight_gate; a.huber_a = c->prm.huber_a;
@@ -731,7 +821,36 @@ int s2m_run(liliom_ctx* c, double pose7[7], int match_cnt, int max_num_iter, int
         a.dbg = c->lm_state.as<long long>();
     }
 
-    const int launches = (iters == 0 && want_corr) ? 1 : iters;
+    // ---- single-GPU GN: all iterations in one cooperative launch
+    const bool persistent = mode == LILIOM_MODE_GN && c->nranks == 1 && iters > 0 && !want_corr && !a.dbg &&
+                            !getenv("LILIOM_NO_PERSISTENT") && grid <= c->sm_count;
+    if (persistent) {
+        a.update_pose = 1;
+        a.stats = nullptr;
+        int iters_arg = iters;
+        unsigned int* bar = reinterpret_cast<unsigned int*>(c->counter.as<unsigned char>() + 32);
+        double* stats_base = c->stats_dev.as<double>();
+        void* kargs[] = {&a, &iters_arg, &bar, &stats_base};
+        const void* fn = lanes == 16 ? (const void*)k_gn_persistent<16> : lanes == 1 ? (const void*)k_gn_persistent<1>
+                       : lanes == 2 ? (const void*)k_gn_persistent<2> : lanes == 4 ? (const void*)k_gn_persistent<4>
+                                                                                   : (const void*)k_gn_persistent<8>;
+        size_t ev = 0;
+        if (c->time_kernels) {
+            if (c->ev_used + 2 > c->ev_pool.size()) {
+                for (int k = 0; k < 64; ++k) { cudaEvent_t e; LILI_CUDA(c, cudaEventCreate(&e)); c->ev_pool.push_back(e); }
+            }
+            ev = c->ev_used; c->ev_used += 2;
+            LILI_CUDA(c, cudaEventRecord(c->ev_pool[ev], c->stream));
+        }
+        LILI_CUDA(c, cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kBlock), kargs, 0, c->stream));
+        LILI_TRY(launch_check(c, "k_gn_persistent"));
+        if (c->time_kernels) {
+            LILI_CUDA(c, cudaEventRecord(c->ev_pool[ev + 1], c->stream));
+            c->ev_pending.push_back({ev, (unsigned long long)n_est * iters});
+            c->ev_iters.push_back(iters);
+        }
+    }
+    const int launches = persistent ? 0 : ((iters == 0 && want_corr) ? 1 : iters);
     for (int it = 0; it < launches; ++it) {
         a.stats = c->stats_dev.as<double>() + (size_t)it * kStatsDoubles;
         const bool multi = c->nranks > 1;
@@ -752,7 +871,8 @@ int s2m_run(liliom_ctx* c, double pose7[7], int match_cnt, int max_num_iter, int
         LILI_TRY(launch_check(c, "k_knn_plane"));
         if (c->time_kernels) {
             LILI_CUDA(c, cudaEventRecord(c->ev_pool[ev + 1], c->stream));
-            c->ev_pending.push_back({ev, (unsigned long long)n});
+            c->ev_pending.push_back({ev, (unsigned long long)n_est});
+            c->ev_iters.push_back(1);
         }
         if (iters == 0) break;
         if (multi) LILI_TRY(nccl_allreduce_sum_f64(c, c->neq.as<double>(), kNormEq));
@@ -763,7 +883,7 @@ int s2m_run(liliom_ctx* c, double pose7[7], int match_cnt, int max_num_iter, int
             }
         } else {
             LmArgs l{};
-            l.feats = a.feats; l.valid = a.valid; l.plane = a.plane; l.n = n;
+            l.feats = a.feats; l.valid = a.valid; l.plane = a.plane; l.n = n; l.n_dev = c->d_nfeats;
             l.pose = c->pose_dev.as<double>(); l.stats = a.stats; l.huber_a = a.huber_a; l.max_num_iter = max_num_iter;
             l.neq0 = c->neq.as<double>();
             if (multi) { c->last_error = "CERES mode is single-GPU (the LM solve is one block); use GN mode with a communicator"; return LILIOM_E_ARG; }
@@ -775,6 +895,7 @@ int s2m_run(liliom_ctx* c, double pose7[7], int match_cnt, int max_num_iter, int
     double* hp = reinterpret_cast<double*>(c->h_pin);
     LILI_CUDA(c, cudaMemcpyAsync(hp, c->pose_dev.p, 7 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     if (out29) LILI_CUDA(c, cudaMemcpyAsync(hp + 8, c->neq.p, kNormEq * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (c->d_nfeats) LILI_CUDA(c, cudaMemcpyAsync(hp + 40, c->d_nfeats, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     const bool want_stats = stats && iters > 0;
     if (want_stats) {
         size_t bytes = (size_t)iters * kStatsDoubles * sizeof(double);
@@ -782,6 +903,8 @@ int s2m_run(liliom_ctx* c, double pose7[7], int match_cnt, int max_num_iter, int
         LILI_CUDA(c, cudaMemcpyAsync(hp + 64, c->stats_dev.p, bytes, cudaMemcpyDeviceToHost, c->stream));
     }
     LILI_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->n_feats_actual = c->d_nfeats ? min(*reinterpret_cast<int*>(hp + 40), n) : n;
+    c->last_n_feats = c->n_feats_actual;
     if (iters > 0) for (int k = 0; k < 7; ++k) pose7[k] = hp[k];
     if (out29) for (int k = 0; k < kNormEq; ++k) out29[k] = hp[8 + k];
     if (want_stats) {
@@ -802,13 +925,16 @@ int s2m_run(liliom_ctx* c, double pose7[7], int match_cnt, int max_num_iter, int
     }
     // fold finished kernel timings into the counters
     if (c->time_kernels) {
-        for (auto& pr : c->ev_pending) {
+        for (size_t k = 0; k < c->ev_pending.size(); ++k) {
+            auto& pr = c->ev_pending[k];
             float ms = 0;
             if (cudaEventElapsedTime(&ms, c->ev_pool[pr.first], c->ev_pool[pr.first + 1]) == cudaSuccess) {
-                c->cnt.knn_ms += ms; c->cnt.knn_launches++; c->cnt.knn_queries += pr.second;
+                // a persistent launch covers `iters` passes of the kernel body: count each pass as one "launch"
+                c->cnt.knn_ms += ms; c->cnt.knn_launches += (unsigned long long)c->ev_iters[k]; c->cnt.knn_queries += pr.second;
             }
         }
         c->ev_pending.clear();
+        c->ev_iters.clear();
         c->ev_used = 0;
     }
     return LILIOM_OK;
