@@ -76,6 +76,7 @@ typedef struct {
 void liliom_default_params(liliom_params* p, int variant);
 
 int  liliom_create(liliom_ctx** out, const liliom_params* p, int device);
+int  liliom_point_stride(const liliom_ctx* c);          /* 48 or 32, as configured at creation */
 void liliom_destroy(liliom_ctx* c);
 const char* liliom_strerror(int code);
 const char* liliom_last_error(const liliom_ctx* c);   /* detail of the last LILIOM_E_CUDA/NCCL */

@@ -52,8 +52,16 @@ EXPORTS = [
     "liliom_map_download", "liliom_scan_to_map", "liliom_odometry_resident", "liliom_find_surf_corr",
     "liliom_correspond_edge", "liliom_correspond_surf", "liliom_comm_get_unique_id", "liliom_comm_init",
     "liliom_get_counters", "liliom_set_kernel_timing", "liliom_upload_feats", "liliom_scan_to_map_resident",
-    "liliom_odometry", "liliom_set_stream", "liliom_upload_scan", "liliom_extract_resident",
+    "liliom_odometry", "liliom_set_stream", "liliom_upload_scan", "liliom_extract_resident", "liliom_point_stride",
 ]
+NODE_EXPORTS = ["liliom_pre_create", "liliom_pre_destroy", "liliom_pre_imu", "liliom_pre_cloud",
+                "liliom_lo_create", "liliom_lo_destroy", "liliom_lo_edge", "liliom_lo_surf", "liliom_lo_full", "liliom_lo_run"]
+
+
+class LoOutput(C.Structure):
+    _fields_ = [("ran", C.c_int), ("initialized", C.c_int), ("kf", C.c_int), ("n_map", C.c_int), ("n_surf_ds", C.c_int),
+                ("status", C.c_int), ("abs_pose", C.c_double * 7), ("rel_pose", C.c_double * 7), ("stamp", C.c_double)]
+
 
 _lib = None
 
@@ -103,6 +111,16 @@ def lib() -> C.CDLL:
     L.liliom_set_stream.argtypes = [vp, vp]
     L.liliom_upload_scan.argtypes = [vp, vp, C.c_int]
     L.liliom_extract_resident.argtypes = [vp, dp, dp, ip, ip, ip]
+    L.liliom_point_stride.argtypes = [vp]
+    L.liliom_pre_create.argtypes = [vp, C.c_int, dp]; L.liliom_pre_create.restype = vp
+    L.liliom_pre_destroy.argtypes = [vp]; L.liliom_pre_destroy.restype = None
+    L.liliom_pre_imu.argtypes = [vp, C.c_double, dp]; L.liliom_pre_imu.restype = None
+    L.liliom_pre_cloud.argtypes = [vp, C.c_double, vp, C.c_int, vp, C.c_int, ip, vp, C.c_int, ip, vp, C.c_int, ip, dp, dp]
+    L.liliom_lo_create.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int]; L.liliom_lo_create.restype = vp
+    L.liliom_lo_destroy.argtypes = [vp]; L.liliom_lo_destroy.restype = None
+    for f in (L.liliom_lo_edge, L.liliom_lo_surf, L.liliom_lo_full):
+        f.argtypes = [vp, C.c_double, vp, C.c_int]; f.restype = None
+    L.liliom_lo_run.argtypes = [vp, C.POINTER(LoOutput), vp, C.c_int, ip, vp, C.c_int, ip, vp, C.c_int, ip]
     _lib = L
     return L
 
@@ -328,3 +346,61 @@ def comm_get_unique_id() -> bytes:
     if rc != OK:
         raise LiliomError(rc)
     return buf.raw
+
+
+class PreprocessingNode:
+    """Host-side mirror of the reference's Preprocessing node (csrc/host/nodes.cpp) on a Context."""
+
+    def __init__(self, ctx: Context, q_lb=(1.0, 0.0, 0.0, 0.0)):
+        self.ctx = ctx
+        variant = 1 if ctx.stride == 32 else 0
+        self._h = lib().liliom_pre_create(ctx._h, variant, _dptr(np.asarray(q_lb, np.float64)))
+
+    def close(self):
+        if self._h:
+            lib().liliom_pre_destroy(self._h); self._h = None
+
+    def imu(self, stamp: float, gyro):
+        lib().liliom_pre_imu(self._h, float(stamp), _dptr(np.asarray(gyro, np.float64)))
+
+    def cloud(self, stamp: float, pts: np.ndarray):
+        """Returns None while queueing / waiting for IMU, else (stamp, surf, edge, cutted, q_imu)."""
+        pts = np.ascontiguousarray(pts, dtype=self.ctx.dtype)
+        cap = 400000
+        surf = np.empty(cap, self.ctx.dtype); edge = np.empty(cap, self.ctx.dtype); cut = np.empty(cap, self.ctx.dtype)
+        ns, ne, nc = C.c_int(), C.c_int(), C.c_int()
+        st = C.c_double(); q = np.zeros(4)
+        rc = lib().liliom_pre_cloud(self._h, float(stamp), _ptr(pts), len(pts), _ptr(surf), cap, C.byref(ns), _ptr(edge), cap, C.byref(ne),
+                                    _ptr(cut), cap, C.byref(nc), C.byref(st), _dptr(q))
+        if rc < 0:
+            raise LiliomError(rc, lib().liliom_last_error(self.ctx._h).decode())
+        if rc == 0:
+            return None
+        return st.value, surf[:ns.value].copy(), edge[:ne.value].copy(), cut[:nc.value].copy(), q
+
+
+class LidarOdometryNode:
+    """Host-side mirror of the reference's LidarOdometry node (csrc/host/nodes.cpp) on a Context."""
+
+    def __init__(self, ctx: Context, max_num_iter=15, scan_match_cnt=1, if_to_deskew=False, mode=MODE_CERES):
+        self.ctx = ctx
+        self._h = lib().liliom_lo_create(ctx._h, max_num_iter, scan_match_cnt, 1 if if_to_deskew else 0, mode)
+
+    def close(self):
+        if self._h:
+            lib().liliom_lo_destroy(self._h); self._h = None
+
+    def feed(self, stamp: float, edge: np.ndarray, surf: np.ndarray, full: np.ndarray):
+        for fn, a in ((lib().liliom_lo_edge, edge), (lib().liliom_lo_surf, surf), (lib().liliom_lo_full, full)):
+            a = np.ascontiguousarray(a, dtype=self.ctx.dtype)
+            fn(self._h, float(stamp), _ptr(a), len(a))
+
+    def run(self):
+        out = LoOutput()
+        cap = 400000
+        e = np.empty(cap, self.ctx.dtype); s = np.empty(cap, self.ctx.dtype); f = np.empty(cap, self.ctx.dtype)
+        ne, ns, nf = C.c_int(), C.c_int(), C.c_int()
+        rc = lib().liliom_lo_run(self._h, C.byref(out), _ptr(e), cap, C.byref(ne), _ptr(s), cap, C.byref(ns), _ptr(f), cap, C.byref(nf))
+        if rc != OK:
+            raise LiliomError(rc, lib().liliom_last_error(self.ctx._h).decode())
+        return out, e[:ne.value].copy(), s[:ns.value].copy(), f[:nf.value].copy()

@@ -133,6 +133,7 @@ extern "C" const char* liliom_strerror(int code) {
 }
 
 extern "C" const char* liliom_last_error(const liliom_ctx* c) { return c ? c->last_error.c_str() : ""; }
+extern "C" int liliom_point_stride(const liliom_ctx* c) { return c ? c->prm.point_stride : 0; }
 
 extern "C" int liliom_create(liliom_ctx** out, const liliom_params* p, int device) {
     if (!out || !p) return LILIOM_E_ARG;

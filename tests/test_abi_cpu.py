@@ -10,8 +10,8 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _declared_symbols():
-    src = open(os.path.join(ROOT, "include", "liliom.h")).read()
+def _declared_symbols(header="liliom.h"):
+    src = open(os.path.join(ROOT, "include", header)).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     return sorted(set(re.findall(r"\b(liliom_[a-z0-9_]+)\s*\(", src)))
 
@@ -24,6 +24,9 @@ def test_library_exports_every_declared_symbol():
     missing = [s for s in decl if not hasattr(lib, s)]
     assert not missing, missing
     assert sorted(L.EXPORTS) == decl, (set(decl) ^ set(L.EXPORTS))
+    nodes = _declared_symbols("liliom_nodes.h")
+    assert sorted(L.NODE_EXPORTS) == nodes, (set(nodes) ^ set(L.NODE_EXPORTS))
+    assert not [s for s in nodes if not hasattr(lib, s)]
 
 
 def test_struct_layouts_match_header():
