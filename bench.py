@@ -6,8 +6,11 @@ One "step" = one scan through the hot path:
     [5-NN in the voxel map + plane fit + residual/Jacobian + 27-scalar reduce + 6x6 solve + pose update]
 
 N = 1 workload (BASELINE.json configs[1]): 24k-pt Livox-Horizon sweep, 1 M-pt voxel map, 10 GN iterations.
-N > 1 : --multi sharded (default; configs[3]: 5 M-pt map sharded by 8 m block hash, one 29-scalar NCCL
-        all-reduce per iteration, strong scaling) or --multi replicas (independent scan streams, weak scaling).
+N > 1 : --multi replicas (default): every GPU runs the N = 1 workload on its own scan stream — the path is
+        data-parallel over independent sensors/robots, no data-path collective, weak scaling;
+        --multi sharded: ONE scan stream, 5 M-pt map sharded by 16 m block hash (+1 m halo), one 29-scalar NCCL
+        all-reduce per GN iteration (configs[3], strong scaling).  Measured on 2 GPUs the all-reduce latency
+        (~20 us x 10 iterations) outweighs the sharded search for a 1.4k-query scan — see DESIGN.md §4.
 
 value  : scans/s with the sweep already resident in HBM (only the 56-byte pose returns to the host).
 e2e    : scans/s through the reference-facing calls with HOST buffers — Preprocessing node call
@@ -43,7 +46,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--multi", default="sharded", choices=["sharded", "replicas"])
+    ap.add_argument("--multi", default="replicas", choices=["sharded", "replicas"])
     ap.add_argument("--map-points", type=int, default=0, help="override the map size")
     ap.add_argument("--sweeps", type=int, default=8, help="distinct synthetic sweeps cycled through the steps")
     ap.add_argument("--no-cpu-baseline", action="store_true")

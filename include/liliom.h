@@ -126,7 +126,7 @@ int liliom_map_rebuild(liliom_ctx* c, int* n_map_out);
 int liliom_map_clear(liliom_ctx* c);
 /* Install an already down-sampled world-frame map (float4 xyz*, w ignored) — the synthetic
  * 1 M..10 M-point maps of the benchmark configs.  With a communicator (liliom_comm_init) each
- * rank keeps only the 8 m blocks it owns plus a halo. */
+ * rank keeps only the 16 m blocks it owns plus a halo. */
 int liliom_map_set_points(liliom_ctx* c, const liliom_f4* xyzw, int m);
 int liliom_map_size(const liliom_ctx* c);        /* points resident on this rank */
 int liliom_map_download(liliom_ctx* c, liliom_f4* xyzw_out, int cap, int* m_out);  /* surf_from_map_ds */
@@ -183,7 +183,7 @@ int liliom_correspond_surf(liliom_ctx* c, const void* feats_body, int n, int str
 
 /* ===================== multi-GPU (one context per rank) ===================== */
 /* 128-byte NCCL unique id: rank 0 calls get, the launcher broadcasts it, every rank calls init.
- * After init, liliom_map_set_points shards the map by 8 m block hash (+halo) and every
+ * After init, liliom_map_set_points shards the map by 16 m block hash (+halo) and every
  * liliom_scan_to_map / liliom_odometry_resident is COLLECTIVE: per iteration one all-reduce of
  * the 27 J^T J|J^T r scalars (+cost,count) then an identical 6x6 solve on every rank. */
 int liliom_comm_get_unique_id(void* id128);

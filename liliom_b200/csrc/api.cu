@@ -7,7 +7,7 @@
 namespace lili {
 void nccl_destroy(liliom_ctx* c);
 
-// ---- map sharding (multi-GPU): keep a point when any 8 m block touched by its halo box is owned by `rank`
+// ---- map sharding (multi-GPU): keep a point when any 16 m block touched by its halo box is owned by `rank`
 __device__ __forceinline__ unsigned sh_block_hash(int bx, int by, int bz) {
     unsigned h = (unsigned)bx * 73856093u ^ (unsigned)by * 19349663u ^ (unsigned)bz * 83492791u;
     h ^= h >> 15; h *= 0x2c1b3c6du; h ^= h >> 12;
@@ -21,7 +21,7 @@ __global__ void k_shard_flags(const float4* __restrict__ p, int n, float halo, i
         float4 v = p[i];
         for (int c = 0; c < 8 && !f; ++c) {
             float x = v.x + ((c & 1) ? halo : -halo), y = v.y + ((c & 2) ? halo : -halo), z = v.z + ((c & 4) ? halo : -halo);
-            int bx = (int)floorf(x * 0.125f), by = (int)floorf(y * 0.125f), bz = (int)floorf(z * 0.125f);
+            int bx = (int)floorf(x * 0.0625f), by = (int)floorf(y * 0.0625f), bz = (int)floorf(z * 0.0625f);
             if ((int)(sh_block_hash(bx, by, bz) % (unsigned)nranks) == rank) f = 1;
         }
     }

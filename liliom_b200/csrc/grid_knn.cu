@@ -170,7 +170,7 @@ struct KnnArgs {
     unsigned long long* cand_total;     // instrumentation
     int update_pose;                    // 1: last block performs the GN step
     int rounds;                         // a warp handles (32/LANES)*rounds queries per task
-    int nranks, rank;                   // multi-GPU ownership filter (8 m block hash)
+    int nranks, rank;                   // multi-GPU ownership filter (16 m block hash)
     long long* dbg;                     // optional phase timestamps (LILIOM_DEBUG_TIMING)
 };
 

@@ -25,7 +25,7 @@ __device__ __forceinline__ unsigned block_hash(int bx, int by, int bz) {
     return h;
 }
 __device__ __forceinline__ int owner_of(float x, float y, float z, int nranks) {
-    int bx = (int)floorf(x * 0.125f), by = (int)floorf(y * 0.125f), bz = (int)floorf(z * 0.125f);
+    int bx = (int)floorf(x * 0.0625f), by = (int)floorf(y * 0.0625f), bz = (int)floorf(z * 0.0625f);
     return (int)(block_hash(bx, by, bz) % (unsigned)nranks);
 }
 

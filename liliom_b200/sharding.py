@@ -1,5 +1,5 @@
 """Host-side statement of the multi-GPU partition rule implemented in csrc/ (knn_core.cuh
-`owner_of`, api.cu `k_shard_flags`): space is cut into 8 m blocks, a block belongs to rank
+`owner_of`, api.cu `k_shard_flags`): space is cut into 16 m blocks, a block belongs to rank
 hash(block) % nranks, a query is processed by the owner of the block its transformed position
 falls in, and a rank's map shard holds every point whose +-halo box touches a block it owns (so the
 query's whole 1 m search ball is local).  Used by bench.py to report shard sizes and by the gloo tests."""
@@ -21,7 +21,7 @@ def _block_hash(b: np.ndarray) -> np.ndarray:
 
 def owner_of(xyz: np.ndarray, nranks: int) -> np.ndarray:
     xyz = np.asarray(xyz, np.float32)
-    b = np.floor(xyz * np.float32(0.125)).astype(np.int32)
+    b = np.floor(xyz * np.float32(0.0625)).astype(np.int32)
     return (_block_hash(b) % np.uint32(nranks)).astype(np.int32)
 
 
