@@ -146,7 +146,8 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     # pick the faster of 1 thread / all threads on one probe scan (OpenMP over queries can lose on shared hosts)
     best_nt, best_t = 1, None
-    for nt in sorted({1, cores}):
+    os.environ.setdefault("OMP_WAIT_POLICY", "passive")
+    for nt in sorted({1, 2, 4, 8, 16, 32, cores} & set(range(1, cores + 1))):
         t0 = time.perf_counter(); cpu_scan(O, tree, sweeps[0], nt); dt = time.perf_counter() - t0
         if best_t is None or dt < best_t:
             best_nt, best_t = nt, dt

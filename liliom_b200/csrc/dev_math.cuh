@@ -442,9 +442,20 @@ __device__ __forceinline__ bool solve6_ldlt(const double* s21, const double* rhs
 __device__ inline void pose_plus(const double x[7], const double d[6], double out[7]) {
     double nd = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
     if (nd > 0.0) {
-        double sn, cs;
-        sincos(nd, &sn, &cs);
-        double sbd = sn / nd;
+        double sbd, cs;
+        if (nd < 0.25) {
+            // GN steps are small: Taylor series of sin(x)/x and cos(x) to x^16 (truncation < 1e-22 at x = 0.25),
+            // a short FMA chain instead of the generic argument-reduction path on the single-thread tail
+            const double x2 = nd * nd;
+            sbd = 1.0 + x2 * (-1.0 / 6 + x2 * (1.0 / 120 + x2 * (-1.0 / 5040 + x2 * (1.0 / 362880 + x2 * (-1.0 / 39916800 +
+                  x2 * (1.0 / 6227020800.0 + x2 * (-1.0 / 1307674368000.0)))))));
+            cs = 1.0 + x2 * (-0.5 + x2 * (1.0 / 24 + x2 * (-1.0 / 720 + x2 * (1.0 / 40320 + x2 * (-1.0 / 3628800 +
+                 x2 * (1.0 / 479001600 + x2 * (-1.0 / 87178291200.0 + x2 * (1.0 / 20922789888000.0))))))));
+        } else {
+            double sn;
+            sincos(nd, &sn, &cs);
+            sbd = sn / nd;
+        }
         double dw = cs, dx = sbd * d[0], dy = sbd * d[1], dz = sbd * d[2];
         out[0] = dw * x[0] - dx * x[1] - dy * x[2] - dz * x[3];
         out[1] = dw * x[1] + dx * x[0] + dy * x[3] - dz * x[2];

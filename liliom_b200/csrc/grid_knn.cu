@@ -184,6 +184,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 struct Slot {
     int   idx[5];            // neighbour indices into map_orig; idx[0] < 0: no 5-NN inside the radius
     float sx, sy, sz;        // transformed query (fp32, as the kd-tree saw it)
+    float fx, fy, fz;        // body-frame query (phase B re-derives R p from it)
 };
 struct Row { double J[6]; double r; double half_rho; };   // robustified Jacobian row, residual, rho/2
 
@@ -212,7 +213,7 @@ struct KnnSmem {
 // accumulates scalar k).  On return lane k < 29 of every warp holds its partial of scalar k in `acc`.
 template <int LANES>
 __device__ __forceinline__ void knn_phases(const KnnArgs& a, const Q4& q, const D3& t, const int n_q, KnnSmem& S,
-                                           double& acc, unsigned long long& cand) {
+                                           double& acc, unsigned long long& cand, const float4* fpre = nullptr) {
     constexpr int GROUPS = 32 / LANES;                 // queries a warp searches concurrently
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -237,9 +238,10 @@ __device__ __forceinline__ void knn_phases(const KnnArgs& a, const Q4& q, const 
             Top5 top;
             top5_init(top);
             float sx = 0.f, sy = 0.f, sz = 0.f;
+            float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
             bool live = qi < n_q;
             if (live) {
-                const float4 f = a.feats[qi];
+                f = fpre ? *fpre : a.feats[qi];   // (persistent kernel: the query stays in registers across iterations)
                 const D3 pw = qrot_x(q, D3{(double)f.x, (double)f.y, (double)f.z});             // L/src/LidarOdometry.cpp:230-231
                 sx = (float)addx(pw.x, t.x); sy = (float)addx(pw.y, t.y); sz = (float)addx(pw.z, t.z);   // :236-238
                 if (a.nranks > 1 && owner_of(sx, sy, sz, a.nranks) != a.rank) live = false;
@@ -254,6 +256,7 @@ __device__ __forceinline__ void knn_phases(const KnnArgs& a, const Q4& q, const 
                 s.idx[0] = ok ? top5_index(top.k0) : -1; s.idx[1] = top5_index(top.k1); s.idx[2] = top5_index(top.k2);
                 s.idx[3] = top5_index(top.k3); s.idx[4] = top5_index(top.k4);
                 s.sx = sx; s.sy = sy; s.sz = sz;
+                s.fx = f.x; s.fy = f.y; s.fz = f.z;
                 if (live && a.nn_idx) {
                     int* o = a.nn_idx + (size_t)qi * 5;
                     const u64 kk[5] = {top.k0, top.k1, top.k2, top.k3, top.k4};
@@ -309,8 +312,7 @@ __device__ __forceinline__ void knn_phases(const KnnArgs& a, const Q4& q, const 
             if (ok) {
                 // LidarPlaneNormIncreFactor (LidarKeyframeFactor.h:118-128) in closed form:
                 //   r = n~ . (q*p + t) + d~ ;  row = [ 2 (R p x n~)^T , n~^T ]  
-                const float4 f = a.feats[qi];
-                const D3 rp = qrot_x(q, D3{(double)f.x, (double)f.y, (double)f.z});
+                const D3 rp = qrot_x(q, D3{(double)s.fx, (double)s.fy, (double)s.fz});
                 const double nx = pl0, ny = pl1, nz = pl2;
                 double r = nx * (rp.x + t.x) + ny * (rp.y + t.y) + nz * (rp.z + t.z) + (double)pl3;
                 // ceres::HuberLoss(a) + Corrector (rho'' <= 0 branch): scale row and residual by sqrt(rho')
@@ -379,13 +381,19 @@ __device__ __forceinline__ void reduce_partials(const KnnArgs& a, KnnSmem& S) {
     double v = 0.0;
     if (sc < kNormEq) {
         const double* src = a.partials + (size_t)sc * G;
-        double v0 = 0, v1 = 0, v2 = 0, v3 = 0;
-        int b = l8;
-        for (; b + 24 < G; b += 32) {
-            v0 += __ldcg(src + b); v1 += __ldcg(src + b + 8); v2 += __ldcg(src + b + 16); v3 += __ldcg(src + b + 24);
+        // 8 independent accumulators = 8 loads in flight per lane (64 blocks per round trip per scalar)
+        double w0 = 0, w1 = 0, w2 = 0, w3 = 0, w4 = 0, w5 = 0, w6 = 0, w7 = 0;
+        for (int b = l8; b < G; b += 64) {
+            w0 += __ldcg(src + b);
+            if (b + 8 < G) w1 += __ldcg(src + b + 8);
+            if (b + 16 < G) w2 += __ldcg(src + b + 16);
+            if (b + 24 < G) w3 += __ldcg(src + b + 24);
+            if (b + 32 < G) w4 += __ldcg(src + b + 32);
+            if (b + 40 < G) w5 += __ldcg(src + b + 40);
+            if (b + 48 < G) w6 += __ldcg(src + b + 48);
+            if (b + 56 < G) w7 += __ldcg(src + b + 56);
         }
-        for (; b < G; b += 8) v0 += __ldcg(src + b);
-        v = (v0 + v1) + (v2 + v3);
+        v = ((w0 + w1) + (w2 + w3)) + ((w4 + w5) + (w6 + w7));
     }
     v += __shfl_xor_sync(0xffffffffu, v, 1);
     v += __shfl_xor_sync(0xffffffffu, v, 2);
@@ -479,17 +487,36 @@ __global__ void __launch_bounds__(kBlock, 2) k_gn_persistent(KnnArgs a, int iter
     if (threadIdx.x < 7) S.pose[threadIdx.x] = a.pose[threadIdx.x];
     __syncthreads();
     const unsigned int G = gridDim.x;
+    // one task per warp and one round per task (the small-scan shape): each lane group serves the same
+    // query in every iteration, so its body-frame point is loaded once and kept in registers
+    float4 f_keep = make_float4(0.f, 0.f, 0.f, 0.f);
+    bool keep = false;
+    {
+        constexpr int GROUPS = 32 / LANES;
+        const int per_task = GROUPS * a.rounds;
+        const int ntasks = (n_q + per_task - 1) / per_task;
+        const int gw = blockIdx.x * kWarps + (threadIdx.x >> 5), nw = gridDim.x * kWarps;
+        if (a.rounds == 1 && ntasks <= nw) {
+            keep = true;
+            const int qi = gw * per_task + ((threadIdx.x & 31) / LANES);
+            if (qi < n_q) f_keep = a.feats[qi];
+        }
+    }
 #pragma unroll 1
     for (int it = 0; it < iters; ++it) {
         const Q4 q{S.pose[0], S.pose[1], S.pose[2], S.pose[3]};
         const D3 t{S.pose[4], S.pose[5], S.pose[6]};
         double acc = 0.0;
         unsigned long long cand = 0;
-        knn_phases<LANES>(a, q, t, n_q, S, acc, cand);
+        const bool stamp = a.dbg && blockIdx.x == 0 && threadIdx.x == 0 && it == 2;
+        if (stamp) a.dbg[16] = clock64();
+        knn_phases<LANES>(a, q, t, n_q, S, acc, cand, keep ? &f_keep : nullptr);
+        if (stamp) a.dbg[17] = clock64();
         write_block_partials(a, S, acc, cand);
         // ---- grid barrier (generation counter; all blocks are co-resident: cooperative launch)
         __threadfence();
         __syncthreads();
+        if (stamp) a.dbg[18] = clock64();
         if (threadIdx.x == 0) {
             const unsigned int gen = *reinterpret_cast<volatile unsigned int*>(bar + 1);
             if (atomicAdd(bar, 1u) == G - 1) {
@@ -502,11 +529,14 @@ __global__ void __launch_bounds__(kBlock, 2) k_gn_persistent(KnnArgs a, int iter
             __threadfence();
         }
         __syncthreads();
+        if (stamp) a.dbg[19] = clock64();
         reduce_partials(a, S);
+        if (stamp) a.dbg[20] = clock64();
         double* stats = stats_base ? stats_base + (size_t)it * kStatsDoubles : nullptr;
         if (threadIdx.x == 0) {
             double xn[7];
             gn_step(S, q, t, xn);
+            if (stamp) a.dbg[21] = clock64();
 #pragma unroll
             for (int k = 0; k < 7; ++k) S.pose[k] = xn[k];
             if (blockIdx.x == 0) {
@@ -822,7 +852,7 @@ int s2m_run(liliom_ctx* c, double pose7[7], int match_cnt, int max_num_iter, int
     }
 
     // ---- single-GPU GN: all iterations in one cooperative launch
-    const bool persistent = mode == LILIOM_MODE_GN && c->nranks == 1 && iters > 0 && !want_corr && !a.dbg &&
+    const bool persistent = mode == LILIOM_MODE_GN && c->nranks == 1 && iters > 0 && !want_corr &&
                             !getenv("LILIOM_NO_PERSISTENT") && grid <= c->sm_count;
     if (persistent) {
         a.update_pose = 1;
@@ -916,8 +946,10 @@ int s2m_run(liliom_ctx* c, double pose7[7], int match_cnt, int max_num_iter, int
         }
     }
     if (a.dbg) {
-        long long h[12];
+        long long h[24];
         cudaMemcpy(h, a.dbg, sizeof(h), cudaMemcpyDeviceToHost);
+        if (h[16]) fprintf(stderr, "[persistent it=2, cycles] phases %lld, partials+fence %lld, barrier %lld, reduce %lld, solve %lld\n",
+                           h[17] - h[16], h[18] - h[17], h[19] - h[18], h[20] - h[19], h[21] - h[20]);
         fprintf(stderr, "[phase A detail] pose+feat+transform %lld, first row bounds %lld, candidates+rank %lld, merge %lld, slot %lld\n",
                 h[8] - h[0], h[9] - h[8], h[10] - h[9], h[11] - h[10], h[1] - h[11]);
         fprintf(stderr, "[knn phases, cycles] blk0: start->A %lld, B %lld, C %lld, loop-end %lld, block-reduce+ticket %lld | last block: reduce %lld, solve %lld (abs tail %lld after blk0 start)\n",
