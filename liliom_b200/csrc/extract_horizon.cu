@@ -80,20 +80,35 @@ struct HzCell { float x, y, z, curv, inten, depth; };
 constexpr int HZ_WIN = 14;   // columns i-4 .. i+9
 constexpr int HZ_WARPS = 4;
 
+// One warp per patch.  The reference's patch body is a chain of short sequential reductions; every
+// reduction keeps its exact left-to-right order here (bit-exact labels), but independent reductions run
+// on different lanes at the same time: the 36 depth-Laplacians, the 6 per-line arg-max scans, the two
+// centroids (3+3 lanes), the two scatter matrices (6+6 lanes) and the two 3x3 eigen-solves (2 lanes).
+struct HzPatchSmem {
+    HzCell win[HZ_LINES * HZ_WIN];
+    double g1[36];            // depth Laplacian of patch cell e = j*6+k (valid cells only)
+    int    ids_y[HZ_LINES];   // arg-max column offset per line, -1 = none
+    int    list_s[36];        // valid cells in (j,k) order  (indices into win)
+    int    list_e[6];         // edge candidates in line order
+    double cen[6];            // surf centre xyz, edge centre xyz
+    double cov[12];           // surf a00,a10,a20,a11,a21,a22 ; edge likewise
+    double ev[6];             // eigenvalues surf[3], edge[3]
+    float  nrm[6];            // surf normal (evec col 0), edge direction (evec col 2)
+    int    out_s[36], out_e[6];
+    int    ns, ne, num, nedge;
+};
+
 __global__ void __launch_bounds__(HZ_WARPS * 32) k_hz_patch(const Pt48* __restrict__ cut, const int* __restrict__ mat,
                                                            double surf_thres, double edge_thres,
                                                            Pt48* __restrict__ stage_surf, Pt48* __restrict__ stage_edge,
                                                            int* __restrict__ counts) {
-    __shared__ HzCell win[HZ_WARPS][HZ_LINES * HZ_WIN];
-    __shared__ int s_list[HZ_WARPS][36];
-    __shared__ int e_list[HZ_WARPS][6];
-    __shared__ float nrm[HZ_WARPS][6];   // surf normal (0..2), edge direction (3..5)
-    __shared__ int cnts[HZ_WARPS][2];
+    __shared__ HzPatchSmem sm[HZ_WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int patch = blockIdx.x * HZ_WARPS + warp;
     if (patch >= HZ_PATCHES) return;
     const int i0 = 5 + 6 * patch;
-    HzCell* W = win[warp];
+    HzPatchSmem& P = sm[warp];
+    HzCell* W = P.win;
     for (int e = lane; e < HZ_LINES * HZ_WIN; e += 32) {
         int k = e / HZ_WIN, cc = e % HZ_WIN;
         int idx = mat[k * HZ_COLS + (i0 - 4 + cc)];
@@ -106,98 +121,129 @@ __global__ void __launch_bounds__(HZ_WARPS * 32) k_hz_patch(const Pt48* __restri
         W[e] = h;
     }
     __syncwarp();
-    if (lane == 0) {
-        auto C = [&](int k, int j) -> HzCell& { return W[k * HZ_WIN + (j + 4)]; };   // j = column offset from i0 (-4..9)
-        int ns = 0, ne = 0;
-        double cx = 0, cy = 0, cz = 0;
-        int num = 36;
-        for (int j = 0; j < 6; ++j)
-            for (int k = 0; k < HZ_LINES; ++k) {
-                const HzCell& h = C(k, j);
-                if (h.curv <= 0) { num--; continue; }                                            // :276-279
-                cx += (double)h.x; cy += (double)h.y; cz += (double)h.z;
-            }
-        if (num >= 25) {                                                                          // :287
-            cx /= num; cy /= num; cz /= num;
-            double a00 = 0, a01 = 0, a02 = 0, a10 = 0, a11 = 0, a12 = 0, a20 = 0, a21 = 0, a22 = 0;
-            for (int j = 0; j < 6; ++j)
-                for (int k = 0; k < HZ_LINES; ++k) {
-                    const HzCell& h = C(k, j);
-                    if (h.curv <= 0) continue;
-                    double z0 = (double)h.x - cx, z1 = (double)h.y - cy, z2 = (double)h.z - cz;
-                    a00 += z0 * z0; a01 += z0 * z1; a02 += z0 * z2;
-                    a10 += z1 * z0; a11 += z1 * z1; a12 += z1 * z2;
-                    a20 += z2 * z0; a21 += z2 * z1; a22 += z2 * z2;
-                }
-            double ev[3], evec[3][3];
-            eigen_sym3(a00, a10, a20, a11, a21, a22, ev, evec);                                   // :298
-            // per-line depth Laplacian, :302-331
-            int idsx[HZ_LINES], idsy[HZ_LINES], nedge = 0;
-            for (int k = 0; k < HZ_LINES; ++k) {
-                double max_s = 0;
-                int idx = 0;
-                for (int j = 0; j < 6; ++j) {
-                    if (C(k, j).curv <= 0) continue;
-                    double g1 = (double)C(k, j - 4).depth + (double)C(k, j - 3).depth + (double)C(k, j - 2).depth + (double)C(k, j - 1).depth -
-                                8 * (double)C(k, j).depth + (double)C(k, j + 1).depth + (double)C(k, j + 2).depth +
-                                (double)C(k, j + 3).depth + (double)C(k, j + 4).depth;
-                    g1 = g1 / (8 * (double)C(k, j).depth + 1e-3);
-                    if (g1 > 0.06 && g1 > max_s) { max_s = g1; idx = j; }
-                }
-                if (max_s != 0) { idsx[nedge] = k; idsy[nedge] = idx; ++nedge; }
-            }
-            bool flipped[HZ_LINES][6];
-            for (int k = 0; k < HZ_LINES; ++k) for (int j = 0; j < 6; ++j) flipped[k][j] = false;
-            if (nedge > 0) {                                                                      // :333-365
-                double ex = 0, ey = 0, ez = 0;
-                for (int m = 0; m < nedge; ++m) { const HzCell& h = C(idsx[m], idsy[m]); ex += (double)h.x; ey += (double)h.y; ez += (double)h.z; }
-                ex /= nedge; ey /= nedge; ez /= nedge;
-                double b00 = 0, b10 = 0, b20 = 0, b11 = 0, b21 = 0, b22 = 0;
-                for (int m = 0; m < nedge; ++m) {
-                    const HzCell& h = C(idsx[m], idsy[m]);
-                    double z0 = (double)h.x - ex, z1 = (double)h.y - ey, z2 = (double)h.z - ez;
-                    b00 += z0 * z0; b10 += z1 * z0; b20 += z2 * z0; b11 += z1 * z1; b21 += z2 * z1; b22 += z2 * z2;
-                }
-                double eev[3], eevec[3][3];
-                eigen_sym3(b00, b10, b20, b11, b21, b22, eev, eevec);                             // :351
-                if (eev[2] > edge_thres * eev[1] && nedge > 3) {                                  // :353
-                    nrm[warp][3] = (float)eevec[0][2]; nrm[warp][4] = (float)eevec[1][2]; nrm[warp][5] = (float)eevec[2][2];
-                    for (int m = 0; m < nedge; ++m) {
-                        const HzCell& h = C(idsx[m], idsy[m]);
-                        if (h.curv <= 0 && h.inten <= 0) continue;                                // :356
-                        e_list[warp][ne++] = idsx[m] * HZ_WIN + (idsy[m] + 4);
-                        flipped[idsx[m]][idsy[m]] = true;                                         // :363 curvature *= -1
-                    }
-                }
-            }
-            if (ev[0] < surf_thres * ev[1]) {                                                     // :367
-                nrm[warp][0] = (float)evec[0][0]; nrm[warp][1] = (float)evec[1][0]; nrm[warp][2] = (float)evec[2][0];
-                for (int j = 0; j < 6; ++j)
-                    for (int k = 0; k < HZ_LINES; ++k) {
-                        if (C(k, j).curv <= 0 || flipped[k][j]) continue;                         // :371
-                        s_list[warp][ns++] = k * HZ_WIN + (j + 4);
-                    }
-            }
+    auto cell_of = [](int e) { return (e % 6) * HZ_WIN + (e / 6 + 4); };   // patch cell e = j*6+k -> window index (k, j)
+    // ---- (1) validity + depth Laplacian of the 36 patch cells, :276-279 and :310-315
+    for (int e = lane; e < 36; e += 32) {
+        const int k = e % 6, j = e / 6;
+        const HzCell* R = W + k * HZ_WIN + 4;   // R[j] = (k, i0 + j)
+        double g = 0.0;
+        if (R[j].curv > 0) {
+            g = (double)R[j - 4].depth + (double)R[j - 3].depth + (double)R[j - 2].depth + (double)R[j - 1].depth - 8 * (double)R[j].depth +
+                (double)R[j + 1].depth + (double)R[j + 2].depth + (double)R[j + 3].depth + (double)R[j + 4].depth;
+            g = g / (8 * (double)R[j].depth + 1e-3);
         }
-        cnts[warp][0] = ns; cnts[warp][1] = ne;
-        counts[patch] = ns;
-        counts[HZ_PATCHES + 1 + patch] = ne;
+        P.g1[e] = g;
     }
     __syncwarp();
-    const int ns = cnts[warp][0], ne = cnts[warp][1];
-    for (int s = lane; s < ns; s += 32) {
-        const HzCell& h = W[s_list[warp][s]];
+    // ---- (2) per-line arg-max g1 > 0.06, :302-331 (lanes 0..5), and the ordered list of valid cells (lane 6)
+    if (lane < HZ_LINES) {
+        double max_s = 0;
+        int idx = -1;
+        for (int j = 0; j < 6; ++j) {
+            if (W[lane * HZ_WIN + j + 4].curv <= 0) continue;
+            const double g1 = P.g1[j * 6 + lane];
+            if (g1 > 0.06 && g1 > max_s) { max_s = g1; idx = j; }
+        }
+        P.ids_y[lane] = (max_s != 0) ? idx : -1;
+    } else if (lane == 6) {
+        int n = 0;
+        for (int e = 0; e < 36; ++e) if (W[cell_of(e)].curv > 0) P.list_s[n++] = cell_of(e);
+        P.num = n;
+    }
+    __syncwarp();
+    if (lane == 0) {
+        int n = 0;
+        for (int k = 0; k < HZ_LINES; ++k) if (P.ids_y[k] >= 0) P.list_e[n++] = k * HZ_WIN + P.ids_y[k] + 4;
+        P.nedge = n;
+        P.ns = 0; P.ne = 0;
+    }
+    __syncwarp();
+    const int num = P.num, nedge = P.nedge;
+    if (num >= 25) {                                                                              // :287 (else: `continue`, no edge either)
+        // ---- (3) centroids: lanes 0-2 surf xyz (:280-289), lanes 3-5 edge xyz (:335-342); sequential sums
+        if (lane < 6) {
+            const bool is_e = lane >= 3;
+            const int comp = lane % 3;
+            const int* list = is_e ? P.list_e : P.list_s;
+            const int len = is_e ? nedge : num;
+            double acc = 0.0;
+            for (int t = 0; t < len; ++t) {
+                const HzCell& h = W[list[t]];
+                acc += (double)(comp == 0 ? h.x : comp == 1 ? h.y : h.z);
+            }
+            if (len > 0) acc /= len;
+            P.cen[lane] = acc;
+        }
+        __syncwarp();
+        // ---- (4) scatter matrices: lanes 0-5 surf, 6-11 edge; entries (0,0),(1,0),(2,0),(1,1),(2,1),(2,2)  (:291-296, :344-349)
+        if (lane < 12) {
+            const bool is_e = lane >= 6;
+            const int ent = lane % 6;
+            const int r = ent == 0 ? 0 : ent == 1 ? 1 : ent == 2 ? 2 : ent == 3 ? 1 : 2;
+            const int c = ent <= 2 ? 0 : ent == 3 ? 1 : ent == 4 ? 1 : 2;
+            const int* list = is_e ? P.list_e : P.list_s;
+            const int len = is_e ? nedge : num;
+            const double cr = P.cen[(is_e ? 3 : 0) + r], cc = P.cen[(is_e ? 3 : 0) + c];
+            double acc = 0.0;
+            for (int t = 0; t < len; ++t) {
+                const HzCell& h = W[list[t]];
+                const double vr = (double)(r == 0 ? h.x : r == 1 ? h.y : h.z) - cr;
+                const double vc = (double)(c == 0 ? h.x : c == 1 ? h.y : h.z) - cc;
+                acc += vr * vc;
+            }
+            P.cov[lane] = acc;
+        }
+        __syncwarp();
+        // ---- (5) the two eigen-solves side by side (:298, :351)
+        if (lane < 2 && (lane == 0 || nedge > 0)) {
+            const double* M = P.cov + 6 * lane;
+            double ev[3], evec[3][3];
+            eigen_sym3(M[0], M[1], M[2], M[3], M[4], M[5], ev, evec);
+            P.ev[3 * lane] = ev[0]; P.ev[3 * lane + 1] = ev[1]; P.ev[3 * lane + 2] = ev[2];
+            const int col = lane == 0 ? 0 : 2;
+            P.nrm[3 * lane] = (float)evec[0][col]; P.nrm[3 * lane + 1] = (float)evec[1][col]; P.nrm[3 * lane + 2] = (float)evec[2][col];
+        }
+        __syncwarp();
+        // ---- (6) decisions, :353-382
+        if (lane == 0) {
+            int ns = 0, ne = 0;
+            unsigned long long flipped = 0;   // bit = window index of an emitted edge point (:363 curvature *= -1)
+            unsigned long long flipped_hi = 0;
+            if (nedge > 0 && P.ev[5] > edge_thres * P.ev[4] && nedge > 3) {                      // :353
+                for (int m = 0; m < nedge; ++m) {
+                    const int wi = P.list_e[m];
+                    const HzCell& h = W[wi];
+                    if (h.curv <= 0 && h.inten <= 0) continue;                                    // :356
+                    P.out_e[ne++] = wi;
+                    if (wi < 64) flipped |= 1ull << wi; else flipped_hi |= 1ull << (wi - 64);
+                }
+            }
+            if (P.ev[0] < surf_thres * P.ev[1]) {                                                 // :367
+                for (int t = 0; t < num; ++t) {
+                    const int wi = P.list_s[t];
+                    const bool f = wi < 64 ? ((flipped >> wi) & 1ull) : ((flipped_hi >> (wi - 64)) & 1ull);
+                    if (!f) P.out_s[ns++] = wi;                                                   // :371
+                }
+            }
+            P.ns = ns; P.ne = ne;
+        }
+        __syncwarp();
+    }
+    const int ns = P.ns, ne = P.ne;
+    if (lane == 0) { counts[patch] = ns; counts[HZ_PATCHES + 1 + patch] = ne; }
+    for (int s2 = lane; s2 < ns; s2 += 32) {
+        const HzCell& h = W[P.out_s[s2]];
         Pt48 o;
         o.a = make_float4(h.x, h.y, h.z, 1.0f);
-        o.b = make_float4(nrm[warp][0], nrm[warp][1], nrm[warp][2], 0.f);
+        o.b = make_float4(P.nrm[0], P.nrm[1], P.nrm[2], 0.f);
         o.c = make_float4(h.inten, h.curv, 0.f, 0.f);
-        stage_surf[patch * 36 + s] = o;
+        stage_surf[patch * 36 + s2] = o;
     }
     if (lane < ne) {
-        const HzCell& h = W[e_list[warp][lane]];
+        const HzCell& h = W[P.out_e[lane]];
         Pt48 o;
         o.a = make_float4(h.x, h.y, h.z, 1.0f);
-        o.b = make_float4(nrm[warp][3], nrm[warp][4], nrm[warp][5], 0.f);
+        o.b = make_float4(P.nrm[3], P.nrm[4], P.nrm[5], 0.f);
         o.c = make_float4(h.inten, h.curv, 0.f, 0.f);
         stage_edge[patch * 6 + lane] = o;
     }
