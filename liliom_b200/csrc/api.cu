@@ -376,7 +376,7 @@ extern "C" int liliom_scan_to_map(liliom_ctx* c, const void* feats, int n, int s
 }
 
 static int odometry_on_resident_surf(liliom_ctx* c, double pose7[7], int match_cnt, int max_num_iter, int mode, liliom_iter_stats* stats,
-                                     void* ds_out, int ds_cap, int* n_ds);
+                                     void* ds_out, int ds_cap, int* n_ds, bool spec_failed = false);
 
 extern "C" int liliom_odometry(liliom_ctx* c, const void* surf_feats, int n, double pose7[7], int match_cnt, int max_num_iter, int mode,
                                liliom_iter_stats* stats, void* ds_out, int ds_cap, int* n_ds) {
@@ -422,7 +422,7 @@ extern "C" int liliom_extract_resident(liliom_ctx* c, const double q_imu[4], con
 }
 
 static int odometry_on_resident_surf(liliom_ctx* c, double pose7[7], int match_cnt, int max_num_iter, int mode, liliom_iter_stats* stats,
-                                     void* ds_out, int ds_cap, int* n_ds) {
+                                     void* ds_out, int ds_cap, int* n_ds, bool spec_failed) {
     if (!c || !pose7 || (mode != LILIOM_MODE_CERES && mode != LILIOM_MODE_GN) || match_cnt < 0) return LILIOM_E_ARG;
     LILI_CUDA(c, cudaSetDevice(c->device));
     const int stride = c->prm.point_stride;
@@ -434,8 +434,12 @@ static int odometry_on_resident_surf(liliom_ctx* c, double pose7[7], int match_c
     LILI_CUDA(c, c->feats.ensure((size_t)(n_max > 0 ? n_max : 1) * sizeof(float4)));
     if (c->prm.leaf_scan > 0.0f) {
         // L/src/LidarOdometry.cpp:321-322; the centroid kernel also emits the float4 queries
-        LILI_TRY(voxelgrid_dev2(c, c->surf.p, n_max, d_n, stride, c->prm.leaf_scan, c->vg_out.p, c->vg_count.as<int>(), c->feats.as<float4>()));
+        // speculate that the scan's voxel box has < 2^24 cells (a 200 m sweep at 0.4 m: ~2^21-2^23): one radix pass
+        // less.  The box is read back with the pose; on a miss the step is redone with full-width keys.
+        const int key_bits = (n_max > 24576 || spec_failed) ? 32 : 24;
+        LILI_TRY(voxelgrid_dev2(c, c->surf.p, n_max, d_n, stride, c->prm.leaf_scan, c->vg_out.p, c->vg_count.as<int>(), c->feats.as<float4>(), key_bits));
         c->d_nfeats = c->vg_count.as<int>();
+        c->vg_check = key_bits < 32;
     } else {   // leaf_scan == 0: benchmark mode, every surf feature is a query
         if (n_max > 0) LILI_CUDA(c, cudaMemcpyAsync(c->vg_out.p, c->surf.p, (size_t)n_max * stride, cudaMemcpyDeviceToDevice, c->stream));
         LILI_TRY(repack_to_f4(c, c->surf.p, n_max, stride, c->feats.as<float4>(), d_n));
@@ -445,8 +449,18 @@ static int odometry_on_resident_surf(liliom_ctx* c, double pose7[7], int match_c
     int rc = LILIOM_OK;
     if (!c->map_ready) rc = LILIOM_E_NOMAP;
     else if (c->map_n_global < 10) rc = LILIOM_E_FEWMAP;
-    if (rc == LILIOM_OK) rc = s2m_run(c, pose7, match_cnt, max_num_iter, mode, stats, false, nullptr);
-    else {   // still report surf_last_ds: read the count back
+    double pose_in[7];
+    memcpy(pose_in, pose7, sizeof(pose_in));
+    if (rc == LILIOM_OK) {
+        rc = s2m_run(c, pose7, match_cnt, max_num_iter, mode, stats, false, nullptr);
+        if (rc == LILIOM_OK && c->vg_check && !spec_failed && c->vg_ncells >= (1LL << 24) - 1) {   // speculation missed: redo with 32-bit keys
+            c->vg_check = false;
+            c->d_nfeats = nullptr;
+            memcpy(pose7, pose_in, sizeof(pose_in));
+            return odometry_on_resident_surf(c, pose7, match_cnt, max_num_iter, mode, stats, ds_out, ds_cap, n_ds, true);
+        }
+        c->vg_check = false;
+    } else {   // still report surf_last_ds: read the count back
         int* hp = reinterpret_cast<int*>(c->h_pin) + 1024;
         if (c->d_nfeats) {
             LILI_CUDA(c, cudaMemcpyAsync(hp, c->d_nfeats, sizeof(int), cudaMemcpyDeviceToHost, c->stream));

@@ -78,6 +78,8 @@ struct liliom_ctx {
     const int* d_nfeats = nullptr; // device-side query count for scan-to-map (nullptr: n_feats is exact)
     int last_n_feats = 0;        // query count of the previous scan (kernel-shape predictor)
     int n_feats_actual = 0;      // query count read back with the pose
+    bool vg_check = false;       // s2m_run also reads vg_params back (speculative key width of the scan VoxelGrid)
+    long long vg_ncells = 0;     // voxel-box cell count of that VoxelGrid, valid after the sync
     lili::DevBuf raw_scan;       // resident raw sweep (liliom_upload_scan)
     int n_raw_scan = 0;
     int n_rot_cloud = 0;
@@ -162,7 +164,8 @@ int exclusive_scan_i32(liliom_ctx* c, const int* in, int* out, int n);   // out 
 // VoxelGrid on device buffers; d_count receives the output count (int, device).
 int voxelgrid_dev(liliom_ctx* c, const void* d_in, int n, int stride, float leaf, void* d_out, int* d_count);
 // n_max = host upper bound, d_n = optional device-side count (<= n_max); d_feats (optional) also receives float4{x,y,z,index}
-int voxelgrid_dev2(liliom_ctx* c, const void* d_in, int n_max, const int* d_n, int stride, float leaf, void* d_out, int* d_count, float4* d_feats);
+int voxelgrid_dev2(liliom_ctx* c, const void* d_in, int n_max, const int* d_n, int stride, float leaf, void* d_out, int* d_count, float4* d_feats,
+                   int key_bits = 32);
 
 // grid build from float4 points already on the device (map_xyzw[0..m)).
 int grid_build(liliom_ctx* c, int m);

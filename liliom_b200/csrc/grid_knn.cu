@@ -926,6 +926,7 @@ int s2m_run(liliom_ctx* c, double pose7[7], int match_cnt, int max_num_iter, int
     LILI_CUDA(c, cudaMemcpyAsync(hp, c->pose_dev.p, 7 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     if (out29) LILI_CUDA(c, cudaMemcpyAsync(hp + 8, c->neq.p, kNormEq * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     if (c->d_nfeats) LILI_CUDA(c, cudaMemcpyAsync(hp + 40, c->d_nfeats, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    if (c->vg_check) LILI_CUDA(c, cudaMemcpyAsync(hp + 48, c->vg_params.p, sizeof(VgParams), cudaMemcpyDeviceToHost, c->stream));
     const bool want_stats = stats && iters > 0;
     if (want_stats) {
         size_t bytes = (size_t)iters * kStatsDoubles * sizeof(double);
@@ -935,6 +936,10 @@ int s2m_run(liliom_ctx* c, double pose7[7], int match_cnt, int max_num_iter, int
     LILI_CUDA(c, cudaStreamSynchronize(c->stream));
     c->n_feats_actual = c->d_nfeats ? min(*reinterpret_cast<int*>(hp + 40), n) : n;
     c->last_n_feats = c->n_feats_actual;
+    if (c->vg_check) {
+        const VgParams* vp = reinterpret_cast<const VgParams*>(hp + 48);
+        c->vg_ncells = vp->overflow ? 0 : (long long)vp->div_b[0] * vp->div_b[1] * vp->div_b[2];
+    }
     if (iters > 0) for (int k = 0; k < 7; ++k) pose7[k] = hp[k];
     if (out29) for (int k = 0; k < kNormEq; ++k) out29[k] = hp[8 + k];
     if (want_stats) {

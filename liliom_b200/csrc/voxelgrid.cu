@@ -377,7 +377,7 @@ __global__ void __launch_bounds__(VGS_THREADS) k_vg_small(const unsigned char* _
 }
 
 int voxelgrid_dev2(liliom_ctx* c, const void* d_in, int n_max, const int* d_n, int stride, float leaf, void* d_out, int* d_count,
-                   float4* d_feats) {
+                   float4* d_feats, int key_bits) {
     if (stride != 48 && stride != 32) return LILIOM_E_ARG;
     if (n_max <= 0) {
         LILI_CUDA(c, cudaMemsetAsync(d_count, 0, sizeof(int), c->stream));
@@ -421,7 +421,10 @@ int voxelgrid_dev2(liliom_ctx* c, const void* d_in, int n_max, const int* d_n, i
     LILI_TRY(launch_check(c, "k_vg_params"));
     k_vg_keys<<<cdiv(n, 256), 256, 0, c->stream>>>(in, n, d_n, stride, pp, c->vg_keys.as<uint32_t>(), c->vg_vals.as<int>());
     LILI_TRY(launch_check(c, "k_vg_keys"));
-    LILI_TRY(sort_pairs_u32(c, c->vg_keys.as<uint32_t>(), c->vg_keys2.as<uint32_t>(), c->vg_vals.as<int>(), c->vg_vals2.as<int>(), n, 32));
+    // key_bits < 32: the caller speculates that the voxel index fits (one onesweep pass less per 8 bits);
+    // invalid (sentinel) keys are folded to the all-ones key of that width and VgParams::n_finite excludes them.
+    // The caller must check `ncells <= 2^key_bits - 1` afterwards (vg_params stays on the device).
+    LILI_TRY(sort_pairs_u32(c, c->vg_keys.as<uint32_t>(), c->vg_keys2.as<uint32_t>(), c->vg_vals.as<int>(), c->vg_vals2.as<int>(), n, key_bits));
     k_vg_heads<<<cdiv(n + 1, 256), 256, 0, c->stream>>>(c->vg_keys2.as<uint32_t>(), n, pp, c->vg_flags.as<int>());
     LILI_TRY(launch_check(c, "k_vg_heads"));
     LILI_TRY(exclusive_scan_i32(c, c->vg_flags.as<int>(), c->vg_rank.as<int>(), n));
@@ -436,7 +439,7 @@ int voxelgrid_dev2(liliom_ctx* c, const void* d_in, int n_max, const int* d_n, i
 }
 
 int voxelgrid_dev(liliom_ctx* c, const void* d_in, int n, int stride, float leaf, void* d_out, int* d_count) {
-    return voxelgrid_dev2(c, d_in, n, nullptr, stride, leaf, d_out, d_count, nullptr);
+    return voxelgrid_dev2(c, d_in, n, nullptr, stride, leaf, d_out, d_count, nullptr, 32);
 }
 
 }  // namespace lili

@@ -301,3 +301,21 @@ def test_gpu_against_golden_fixtures(ctx48):
     _pose_close(pose, g["pose_ceres"])
     assert [s.lm_iters for s in st] == list(g["ceres_lm_iters"])
     c.close()
+
+
+def test_odometry_call_and_sort_width_speculation(ctx48, oracle, world_small, s2m_case):
+    """liliom_odometry = VoxelGrid(0.4) of the received surf cloud + scan-to-map.  The scan VoxelGrid sorts
+    24-bit keys speculatively; a sweep whose voxel box has >= 2^24 cells must transparently redo with 32."""
+    surf = s2m_case["surf"]
+    for far in (False, True):
+        cloud = surf.copy()
+        if far:   # stretch the bounding box to ~520 x 520 x 80 voxels (> 2^24 cells)
+            extra = np.zeros(4, cloud.dtype)
+            extra["x"] = [-104.0, 104.0, 0.0, 0.0]; extra["y"] = [0.0, 0.0, -104.0, 104.0]; extra["z"] = [-16.0, 16.0, 0.0, 0.0]
+            extra["curvature"] = 1.0
+            cloud = np.concatenate([cloud, extra])
+        ds_o = oracle.voxelgrid(cloud, 0.4)
+        rc, pose_o, _ = oracle.scan_to_map_gn(s2m_case["tree"], ds_o, world_small["guess"], 5)
+        pose, st, ds = ctx48.odometry(cloud, world_small["guess"], 5, mode=1)
+        _fields_equal(ds, ds_o, ["x", "y", "z", "nx", "ny", "nz", "intensity", "curvature"])
+        _pose_close(pose, pose_o)
