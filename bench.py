@@ -247,7 +247,7 @@ def main():
     def step_resident(k):
         sw = sweeps[k % len(sweeps)]
         ns, ne, nc = ctx.extract_resident(sw["q"])
-        pose, st, nds = ctx.odometry_resident(sw["guess"], ITERS, mode=L.MODE_GN)
+        pose, st, nds = ctx.odometry_resident(sw["guess"], ITERS, mode=L.MODE_GN, want_stats=False)
         return pose, nds
 
     def step_e2e(k):
@@ -255,7 +255,7 @@ def main():
         # Preprocessing node call: H2D raw sweep, D2H the three published clouds (pinned host buffers)
         surf, edge, cut = ctx.extract_horizon(pin_sweeps[i], sweeps[i]["q"], out=(out_surf, out_edge, out_cut))
         # LidarOdometry node call on the /surf_features cloud as received (host): H2D, D2H pose + surf_last_ds
-        pose, st, ds = ctx.odometry(surf, sweeps[i]["guess"], ITERS, mode=L.MODE_GN, ds_out=out_ds, pose_out=pose_buf)
+        pose, st, ds = ctx.odometry(surf, sweeps[i]["guess"], ITERS, mode=L.MODE_GN, ds_out=out_ds, pose_out=pose_buf, want_stats=False)
         h2d = len(pin_sweeps[i]) * 48 + len(surf) * 48 + 56
         d2h = (len(surf) + len(edge) + len(cut)) * 48 + len(ds) * 48 + 56
         return pose, h2d, d2h

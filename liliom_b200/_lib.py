@@ -265,26 +265,29 @@ class Context:
         self._check(lib().liliom_scan_to_map_resident(self._h, _dptr(pose), match_cnt, max_num_iter, mode, st))
         return pose, ([st[i] for i in range(match_cnt)] if want_stats else None)
 
-    def odometry_resident(self, pose7, match_cnt: int, max_num_iter: int = 15, mode: int = MODE_GN, want_ds: bool = False, cap: int = 0):
+    def odometry_resident(self, pose7, match_cnt: int, max_num_iter: int = 15, mode: int = MODE_GN, want_ds: bool = False, cap: int = 0,
+                          want_stats: bool = True):
         pose = np.array(pose7, dtype=np.float64)
-        st = (IterStats * max(match_cnt, 1))()
+        st = (IterStats * max(match_cnt, 1))() if want_stats else None
         nds = C.c_int()
         ds = np.zeros(max(cap, 1), self.dtype) if want_ds else None
         self._check(lib().liliom_odometry_resident(self._h, _dptr(pose), match_cnt, max_num_iter, mode, st, _ptr(ds), cap if want_ds else 0, C.byref(nds)))
-        return pose, [st[i] for i in range(match_cnt)], (ds[:nds.value] if want_ds else nds.value)
+        return pose, ([st[i] for i in range(match_cnt)] if want_stats else None), (ds[:nds.value] if want_ds else nds.value)
 
     def odometry(self, surf_feats: np.ndarray, pose7, match_cnt: int, max_num_iter: int = 15, mode: int = MODE_GN,
-                 ds_out: np.ndarray | None = None, pose_out: np.ndarray | None = None):
+                 ds_out: np.ndarray | None = None, pose_out: np.ndarray | None = None, want_stats: bool = True):
         """LidarOdometry node view: un-down-sampled surf cloud in (host), pose + surf_last_ds out."""
-        f = np.ascontiguousarray(surf_feats, dtype=self.dtype) if surf_feats.dtype != self.dtype or not surf_feats.flags.c_contiguous else surf_feats
+        f = surf_feats
+        if f.dtype != self.dtype or not f.flags.c_contiguous:
+            f = np.ascontiguousarray(f, dtype=self.dtype)
         pose = pose_out if pose_out is not None else np.empty(7, np.float64)
         pose[:] = pose7
-        st = (IterStats * max(match_cnt, 1))()
+        st = (IterStats * max(match_cnt, 1))() if want_stats else None
         nds = C.c_int()
         if ds_out is None:
-            ds_out = np.zeros(max(len(f), 1), self.dtype)
+            ds_out = np.empty(max(len(f), 1), self.dtype)
         self._check(lib().liliom_odometry(self._h, _ptr(f), len(f), _dptr(pose), match_cnt, max_num_iter, mode, st, _ptr(ds_out), len(ds_out), C.byref(nds)))
-        return pose, [st[i] for i in range(match_cnt)], ds_out[:nds.value]
+        return pose, ([st[i] for i in range(match_cnt)] if want_stats else None), ds_out[:nds.value]
 
     def set_stream(self, cuda_stream: int | None):
         self._check(lib().liliom_set_stream(self._h, C.c_void_p(cuda_stream) if cuda_stream else None))

@@ -111,6 +111,7 @@ struct liliom_ctx {
     lili::DevBuf stats_dev;              // iterations x kStatsDoubles
     lili::DevBuf counter;                // last-block ticket + scratch ints
     lili::DevBuf lm_state;
+    unsigned int bar_arrivals = 0;       // total grid-barrier arrivals issued so far (persistent GN kernel)
 
     // ---- multi-GPU ----
     void* nccl_comm = nullptr;

@@ -172,6 +172,7 @@ struct KnnArgs {
     int rounds;                         // a warp handles (32/LANES)*rounds queries per task
     int nranks, rank;                   // multi-GPU ownership filter (16 m block hash)
     long long* dbg;                     // optional phase timestamps (LILIOM_DEBUG_TIMING)
+    int interleave;                     // 1: deal tasks to warps block-cyclically (load balance for small scans)
 };
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -225,7 +226,9 @@ __device__ __forceinline__ void knn_phases(const KnnArgs& a, const Q4& q, const 
 
     const int per_task = GROUPS * a.rounds;            // <= 32
     const int ntasks = (n_q + per_task - 1) / per_task;
-    const int gw = blockIdx.x * kWarps + warp;
+    // queries arrive in voxel order (spatially sorted): dealing neighbouring tasks to different blocks evens out the
+    // per-block work (dense vs sparse regions) at the grid barrier; large scans keep neighbours together for L1 reuse
+    const int gw = a.interleave ? warp * (int)gridDim.x + (int)blockIdx.x : (int)blockIdx.x * kWarps + warp;
     const int nw = gridDim.x * kWarps;
 
 #pragma unroll 1
@@ -481,12 +484,13 @@ __global__ void __launch_bounds__(kBlock, 2) k_knn_plane(KnnArgs a) {
 // system redundantly (bit-identical), so no second barrier or broadcast is needed.  Removes the launch
 // gap, the drain and the ticket round trip of the per-iteration kernel (~6 us of ~18 per iteration).
 template <int LANES>
-__global__ void __launch_bounds__(kBlock, 2) k_gn_persistent(KnnArgs a, int iters, unsigned int* bar, double* stats_base) {
+__global__ void __launch_bounds__(kBlock, 2) k_gn_persistent(KnnArgs a, int iters, unsigned int* bar, double* stats_base, unsigned int bar_base) {
     __shared__ __align__(16) KnnSmem S;
     const int n_q = a.n_dev ? min(*a.n_dev, a.n) : a.n;
     if (threadIdx.x < 7) S.pose[threadIdx.x] = a.pose[threadIdx.x];
     __syncthreads();
     const unsigned int G = gridDim.x;
+    // bar_base = arrivals of all previous launches on this context (tracked by the host, advanced by iters*G per launch)
     // one task per warp and one round per task (the small-scan shape): each lane group serves the same
     // query in every iteration, so its body-frame point is loaded once and kept in registers
     float4 f_keep = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -495,7 +499,8 @@ __global__ void __launch_bounds__(kBlock, 2) k_gn_persistent(KnnArgs a, int iter
         constexpr int GROUPS = 32 / LANES;
         const int per_task = GROUPS * a.rounds;
         const int ntasks = (n_q + per_task - 1) / per_task;
-        const int gw = blockIdx.x * kWarps + (threadIdx.x >> 5), nw = gridDim.x * kWarps;
+        const int gw = a.interleave ? (threadIdx.x >> 5) * (int)gridDim.x + (int)blockIdx.x : (int)blockIdx.x * kWarps + (threadIdx.x >> 5);
+        const int nw = gridDim.x * kWarps;
         if (a.rounds == 1 && ntasks <= nw) {
             keep = true;
             const int qi = gw * per_task + ((threadIdx.x & 31) / LANES);
@@ -518,14 +523,10 @@ __global__ void __launch_bounds__(kBlock, 2) k_gn_persistent(KnnArgs a, int iter
         __syncthreads();
         if (stamp) a.dbg[18] = clock64();
         if (threadIdx.x == 0) {
-            const unsigned int gen = *reinterpret_cast<volatile unsigned int*>(bar + 1);
-            if (atomicAdd(bar, 1u) == G - 1) {
-                *reinterpret_cast<volatile unsigned int*>(bar) = 0u;
-                __threadfence();
-                atomicAdd(bar + 1, 1u);
-            } else {
-                while (*reinterpret_cast<volatile unsigned int*>(bar + 1) == gen) { }
-            }
+            // monotonic arrival counter: no generation read, no reset inside the loop — one fire-and-forget RED plus polls
+            atomicAdd(bar, 1u);
+            const unsigned int target = bar_base + (unsigned int)(it + 1) * G;
+            while ((int)(*reinterpret_cast<volatile unsigned int*>(bar) - target) < 0) { }
             __threadfence();
         }
         __syncthreads();
@@ -844,6 +845,7 @@ int s2m_run(liliom_ctx* c, double pose7[7], int match_cnt, int max_num_iter, int
     a.ticket = c->counter.as<unsigned int>();
     a.cand_total = c->time_kernels ? reinterpret_cast<unsigned long long*>(c->counter.as<unsigned char>() + 16) : nullptr;
     a.rounds = rounds; a.nranks = c->nranks; a.rank = c->rank;
+    a.interleave = (lanes >= 8 && !getenv("LILIOM_NO_INTERLEAVE")) ? 1 : 0;
     a.dbg = nullptr;
     if (getenv("LILIOM_DEBUG_TIMING")) {
         LILI_CUDA(c, c->lm_state.ensure(64 * sizeof(long long)));
@@ -860,7 +862,8 @@ int s2m_run(liliom_ctx* c, double pose7[7], int match_cnt, int max_num_iter, int
         int iters_arg = iters;
         unsigned int* bar = reinterpret_cast<unsigned int*>(c->counter.as<unsigned char>() + 32);
         double* stats_base = c->stats_dev.as<double>();
-        void* kargs[] = {&a, &iters_arg, &bar, &stats_base};
+        unsigned int bar_base = c->bar_arrivals;
+        void* kargs[] = {&a, &iters_arg, &bar, &stats_base, &bar_base};
         const void* fn = lanes == 16 ? (const void*)k_gn_persistent<16> : lanes == 1 ? (const void*)k_gn_persistent<1>
                        : lanes == 2 ? (const void*)k_gn_persistent<2> : lanes == 4 ? (const void*)k_gn_persistent<4>
                                                                                    : (const void*)k_gn_persistent<8>;
@@ -874,6 +877,7 @@ int s2m_run(liliom_ctx* c, double pose7[7], int match_cnt, int max_num_iter, int
         }
         LILI_CUDA(c, cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kBlock), kargs, 0, c->stream));
         LILI_TRY(launch_check(c, "k_gn_persistent"));
+        c->bar_arrivals += (unsigned int)iters * (unsigned int)grid;
         if (c->time_kernels) {
             LILI_CUDA(c, cudaEventRecord(c->ev_pool[ev + 1], c->stream));
             c->ev_pending.push_back({ev, (unsigned long long)n_est * iters});
