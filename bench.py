@@ -50,6 +50,8 @@ def parse():
     ap.add_argument("--map-points", type=int, default=0, help="override the map size")
     ap.add_argument("--sweeps", type=int, default=8, help="distinct synthetic sweeps cycled through the steps")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e", default="two-nodes", choices=["two-nodes", "sequential"],
+                    help="e2e leg: two concurrent node threads (reference architecture, default) or one thread calling both nodes in turn")
     ap.add_argument("--dense-queries", action="store_true", help="roofline micro-run: every surf feature is a query (no scan DS)")
     return ap.parse_args()
 
@@ -108,6 +110,59 @@ class ClockSampler:
                 pass
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
                 "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_two_stage_pipeline(total, warmup, nbuf, stage_a, stage_b, on_start, on_end, timeout_s=120.0):
+    """Two host threads joined by a bounded queue (nbuf buffers in flight).  stage_a(k, buf) -> item,
+    stage_b(k, buf, item).  on_start() runs on thread A after both stages have fully drained the `warmup`
+    steps; on_end() runs on thread B after the last step.  Any exception / timeout is re-raised in the caller."""
+    import queue
+    free_q, work_q = queue.Queue(), queue.Queue()
+    for b in range(nbuf):
+        free_q.put(b)
+    gate = threading.Barrier(2, timeout=timeout_s)
+    errors = []
+
+    def a_thread():
+        try:
+            for k in range(total):
+                if k == warmup:
+                    gate.wait()          # thread B arrives here after finishing step warmup-1
+                    on_start()
+                b = free_q.get(timeout=timeout_s)
+                work_q.put((k, b, stage_a(k, b)))
+        except BaseException as e:       # noqa: BLE001
+            errors.append(e)
+            gate.abort()
+        finally:
+            work_q.put(None)
+
+    def b_thread():
+        try:
+            if warmup == 0:
+                gate.wait()
+            while True:
+                item = work_q.get(timeout=timeout_s)
+                if item is None:
+                    break
+                k, b, payload = item
+                stage_b(k, b, payload)
+                free_q.put(b)
+                if k == warmup - 1:
+                    gate.wait()
+            on_end()
+        except BaseException as e:       # noqa: BLE001
+            errors.append(e)
+            gate.abort()
+            free_q.put(0)
+
+    ta = threading.Thread(target=a_thread, daemon=True); tb = threading.Thread(target=b_thread, daemon=True)
+    ta.start(); tb.start()
+    ta.join(timeout_s * 4); tb.join(timeout_s * 4)
+    if errors:
+        raise errors[0]
+    if ta.is_alive() or tb.is_alive():
+        raise RuntimeError("two-stage pipeline did not finish")
 
 
 def make_workload(n_map: int, n_sweeps: int, variant: int = 0):
@@ -260,6 +315,43 @@ def main():
         d2h = (len(surf) + len(edge) + len(cut)) * 48 + len(ds) * 48 + 56
         return pose, h2d, d2h
 
+    def e2e_two_nodes(steps, warmup):
+        """The reference runs Preprocessing and LidarOdometry as two concurrent single-threaded nodes; so does this
+        leg: one host thread + context + CUDA stream per node, the /surf_features hop through pinned host memory.
+        L2 is flushed before every scan on the Preprocessing stream INSIDE the timed region (conservative)."""
+        ctx_pre = L.Context(prm, device=local_rank)
+        s_pre = torch.cuda.Stream(); ctx_pre.set_stream(s_pre.cuda_stream)
+        nbuf = 3
+        sets = [[torch.empty(cap * 48, dtype=torch.uint8).pin_memory().numpy().view(L.PT48) for _ in range(3)] for _ in range(nbuf)]
+        ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
+        result = {}
+
+        def stage_a(k, b):
+            i = k % len(sweeps)
+            with torch.cuda.stream(s_pre):
+                flush.fill_(k & 0xff)
+            surf, edge, cut = ctx_pre.extract_horizon(pin_sweeps[i], sweeps[i]["q"], out=tuple(sets[b]))
+            return (len(surf), len(edge), len(cut))
+
+        def stage_b(k, b, item):
+            ns, ne, nc = item
+            i = k % len(sweeps)
+            pose, st, ds = ctx.odometry(sets[b][0][:ns], sweeps[i]["guess"], ITERS, mode=L.MODE_GN, ds_out=out_ds, pose_out=pose_buf, want_stats=False)
+            result.update(pose=np.array(pose), h2d=len(pin_sweeps[i]) * 48 + ns * 48 + 56, d2h=(ns + ne + nc) * 48 + len(ds) * 48 + 56)
+
+        barrier()
+        run_two_stage_pipeline(warmup + steps, warmup, nbuf, stage_a, stage_b,
+                               on_start=lambda: ev0.record(s_pre), on_end=lambda: ev1.record(stream))
+        torch.cuda.synchronize()
+        ms = ev0.elapsed_time(ev1)
+        barrier()
+        if multi:
+            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        ctx_pre.close()
+        return ms, (result["pose"], result["h2d"], result["d2h"])
+
     def timed(fn, steps, warmup, prep=None):
         for k in range(warmup):
             if prep: prep(k)
@@ -293,7 +385,11 @@ def main():
         ms_res, last = timed(step_resident, args.steps, max(args.warmup, 3), prep_resident)
         cnt = ctx.counters(reset=True)
         # ---- timed region 2: end to end with host buffers
-        ms_e2e, last_e2e = timed(step_e2e, args.steps, max(args.warmup, 3))
+        ms_seq, last_seq = timed(step_e2e, args.steps, max(args.warmup, 3))
+        if args.e2e == "sequential" or sharded:
+            ms_e2e, last_e2e = ms_seq, last_seq
+        else:
+            ms_e2e, last_e2e = e2e_two_nodes(args.steps, max(args.warmup, 3))
     clocks = clk.summary()
     cnt_e2e = ctx.counters(reset=True)
 
@@ -341,7 +437,12 @@ def main():
         "gpu_launches": int(cnt.launches),
         "lib_calls": int(cnt.lib_launches),
         "e2e": {"value": e2e_val, "unit": "scans/s", "ms_per_step": ms_e2e / args.steps,
-                "h2d_bytes_per_step": int(last_e2e[1]), "d2h_bytes_per_step": int(last_e2e[2])},
+                "h2d_bytes_per_step": int(last_e2e[1]), "d2h_bytes_per_step": int(last_e2e[2]),
+                "mode": ("sequential: one host thread calls the Preprocessing-node entry point then the LidarOdometry-node entry point"
+                         if (args.e2e == "sequential" or sharded) else
+                         "two-nodes: Preprocessing and LidarOdometry contexts on two host threads / CUDA streams, as the reference's two ROS "
+                         "nodes; /surf_features hop through pinned host memory; 256 MB L2 flush before every scan inside the timed region"),
+                "sequential_value": scans_total / (ms_seq * 1e-3), "sequential_ms_per_step": ms_seq / args.steps},
         "clocks": clocks,
         "roofline": roof,
         "cpu_baseline": cpu,

@@ -357,6 +357,8 @@ class PreprocessingNode:
     def __init__(self, ctx: Context, q_lb=(1.0, 0.0, 0.0, 0.0)):
         self.ctx = ctx
         variant = 1 if ctx.stride == 32 else 0
+        self._cap = 0
+        self._bufs = None
         self._h = lib().liliom_pre_create(ctx._h, variant, _dptr(np.asarray(q_lb, np.float64)))
 
     def close(self):
@@ -369,8 +371,11 @@ class PreprocessingNode:
     def cloud(self, stamp: float, pts: np.ndarray):
         """Returns None while queueing / waiting for IMU, else (stamp, surf, edge, cutted, q_imu)."""
         pts = np.ascontiguousarray(pts, dtype=self.ctx.dtype)
-        cap = 400000
-        surf = np.empty(cap, self.ctx.dtype); edge = np.empty(cap, self.ctx.dtype); cut = np.empty(cap, self.ctx.dtype)
+        cap = max(self._cap, len(pts))
+        if cap > self._cap or self._bufs is None:
+            self._cap = cap
+            self._bufs = [np.empty(cap, self.ctx.dtype) for _ in range(3)]
+        surf, edge, cut = self._bufs
         ns, ne, nc = C.c_int(), C.c_int(), C.c_int()
         st = C.c_double(); q = np.zeros(4)
         rc = lib().liliom_pre_cloud(self._h, float(stamp), _ptr(pts), len(pts), _ptr(surf), cap, C.byref(ns), _ptr(edge), cap, C.byref(ne),
@@ -387,6 +392,8 @@ class LidarOdometryNode:
 
     def __init__(self, ctx: Context, max_num_iter=15, scan_match_cnt=1, if_to_deskew=False, mode=MODE_CERES):
         self.ctx = ctx
+        self._cap = 0
+        self._bufs = None
         self._h = lib().liliom_lo_create(ctx._h, max_num_iter, scan_match_cnt, 1 if if_to_deskew else 0, mode)
 
     def close(self):
@@ -396,14 +403,22 @@ class LidarOdometryNode:
     def feed(self, stamp: float, edge: np.ndarray, surf: np.ndarray, full: np.ndarray):
         for fn, a in ((lib().liliom_lo_edge, edge), (lib().liliom_lo_surf, surf), (lib().liliom_lo_full, full)):
             a = np.ascontiguousarray(a, dtype=self.ctx.dtype)
+            self._cap = max(self._cap, len(a))
             fn(self._h, float(stamp), _ptr(a), len(a))
 
-    def run(self):
+    def run(self, want_clouds: bool = True):
         out = LoOutput()
-        cap = 400000
-        e = np.empty(cap, self.ctx.dtype); s = np.empty(cap, self.ctx.dtype); f = np.empty(cap, self.ctx.dtype)
         ne, ns, nf = C.c_int(), C.c_int(), C.c_int()
-        rc = lib().liliom_lo_run(self._h, C.byref(out), _ptr(e), cap, C.byref(ne), _ptr(s), cap, C.byref(ns), _ptr(f), cap, C.byref(nf))
+        if not want_clouds:
+            rc = lib().liliom_lo_run(self._h, C.byref(out), None, 0, C.byref(ne), None, 0, C.byref(ns), None, 0, C.byref(nf))
+            if rc != OK:
+                raise LiliomError(rc, lib().liliom_last_error(self.ctx._h).decode())
+            return out, None, None, None
+        cap = max(self._cap, 1)
+        if self._bufs is None or len(self._bufs[0]) < cap:
+            self._bufs = [np.empty(cap, self.ctx.dtype) for _ in range(3)]
+        e, s, f = self._bufs
+        rc = lib().liliom_lo_run(self._h, C.byref(out), _ptr(e), len(e), C.byref(ne), _ptr(s), len(s), C.byref(ns), _ptr(f), len(f), C.byref(nf))
         if rc != OK:
             raise LiliomError(rc, lib().liliom_last_error(self.ctx._h).decode())
         return out, e[:ne.value].copy(), s[:ns.value].copy(), f[:nf.value].copy()
