@@ -181,6 +181,15 @@ int liliom_correspond_surf(liliom_ctx* c, const void* feats_body, int n, int str
                            double kd_max_radius, double surf_dist_thres, double w_gate, double lidar_const,
                            unsigned char* valid, float* plane, double* score);
 
+/* Horizon backend variant, L/src/BackendFusion.cpp:1601-1681: rows of the plane fit weighted by
+ * 1/|reflectivity difference| (the `curvature` channel, L/src/FormatConvert.cpp:21), candidates rejected when the summed
+ * difference exceeds reflect_thres (:1628), score = lidar_const*(w + exp(-sum)) (:1676).  The map must have been installed
+ * with liliom_map_set_cloud (keeps the reflectivity channel); feats are 48-byte points. */
+int liliom_map_set_cloud(liliom_ctx* c, const void* pts, int m, int stride);
+int liliom_correspond_surf_refl(liliom_ctx* c, const void* feats48, int n, const double pose7[7], double kd_max_radius,
+                                double surf_dist_thres, double w_gate, double lidar_const, double reflect_thres,
+                                unsigned char* valid, float* plane, double* score);
+
 /* ===================== multi-GPU (one context per rank) ===================== */
 /* 128-byte NCCL unique id: rank 0 calls get, the launcher broadcasts it, every rank calls init.
  * After init, liliom_map_set_points shards the map by 16 m block hash (+halo) and every

@@ -53,6 +53,7 @@ EXPORTS = [
     "liliom_correspond_edge", "liliom_correspond_surf", "liliom_comm_get_unique_id", "liliom_comm_init",
     "liliom_get_counters", "liliom_set_kernel_timing", "liliom_upload_feats", "liliom_scan_to_map_resident",
     "liliom_odometry", "liliom_set_stream", "liliom_upload_scan", "liliom_extract_resident", "liliom_point_stride",
+    "liliom_map_set_cloud", "liliom_correspond_surf_refl",
 ]
 NODE_EXPORTS = ["liliom_pre_create", "liliom_pre_destroy", "liliom_pre_imu", "liliom_pre_cloud",
                 "liliom_lo_create", "liliom_lo_destroy", "liliom_lo_edge", "liliom_lo_surf", "liliom_lo_full", "liliom_lo_run"]
@@ -112,6 +113,8 @@ def lib() -> C.CDLL:
     L.liliom_upload_scan.argtypes = [vp, vp, C.c_int]
     L.liliom_extract_resident.argtypes = [vp, dp, dp, ip, ip, ip]
     L.liliom_point_stride.argtypes = [vp]
+    L.liliom_map_set_cloud.argtypes = [vp, vp, C.c_int, C.c_int]
+    L.liliom_correspond_surf_refl.argtypes = [vp, vp, C.c_int, dp, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, vp, vp, vp]
     L.liliom_pre_create.argtypes = [vp, C.c_int, dp]; L.liliom_pre_create.restype = vp
     L.liliom_pre_destroy.argtypes = [vp]; L.liliom_pre_destroy.restype = None
     L.liliom_pre_imu.argtypes = [vp, C.c_double, dp]; L.liliom_pre_imu.restype = None
@@ -327,6 +330,19 @@ class Context:
         valid = np.zeros(max(n, 1), np.uint8); plane = np.zeros((max(n, 1), 4), np.float32); score = np.zeros(max(n, 1), np.float64)
         self._check(lib().liliom_correspond_surf(self._h, _ptr(f), n, stride, _dptr(pose), kd_max_radius, surf_dist_thres, w_gate,
                                                  lidar_const, _ptr(valid), _ptr(plane), _ptr(score)))
+        return valid[:n], plane[:n], score[:n]
+
+    def map_set_cloud(self, pts: np.ndarray):
+        pts = np.ascontiguousarray(pts)
+        self._check(lib().liliom_map_set_cloud(self._h, _ptr(pts), len(pts), pts.dtype.itemsize))
+
+    def correspond_surf_refl(self, feats: np.ndarray, pose7, kd_max_radius=1.0, surf_dist_thres=0.1, w_gate=0.2, lidar_const=1.0, reflect_thres=10.0):
+        f = np.ascontiguousarray(feats, dtype=PT48)
+        n = len(f)
+        pose = np.array(pose7, dtype=np.float64)
+        valid = np.zeros(max(n, 1), np.uint8); plane = np.zeros((max(n, 1), 4), np.float32); score = np.zeros(max(n, 1), np.float64)
+        self._check(lib().liliom_correspond_surf_refl(self._h, _ptr(f), n, _dptr(pose), kd_max_radius, surf_dist_thres, w_gate, lidar_const,
+                                                      reflect_thres, _ptr(valid), _ptr(plane), _ptr(score)))
         return valid[:n], plane[:n], score[:n]
 
     # ---- multi-GPU / instrumentation ----

@@ -6,6 +6,7 @@
 
 namespace lili {
 void nccl_destroy(liliom_ctx* c);
+int nccl_allreduce_sum_f64(liliom_ctx* c, double* buf, int count);
 
 // ---- map sharding (multi-GPU): keep a point when any 16 m block touched by its halo box is owned by `rank`
 __device__ __forceinline__ unsigned sh_block_hash(int bx, int by, int bz) {
@@ -27,6 +28,31 @@ __global__ void k_shard_flags(const float4* __restrict__ p, int n, float halo, i
     }
     flags[i] = f;
 }
+// same rule on PCL-layout points (stride bytes): used by the sharded liliom_map_push_frame
+__global__ void k_shard_flags_strided(const unsigned char* __restrict__ p, int n, int stride, float halo, int nranks, int rank, int* __restrict__ flags) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n) return;
+    int f = 0;
+    if (i < n) {
+        const float4 v = *reinterpret_cast<const float4*>(p + (size_t)i * stride);
+        for (int c = 0; c < 8 && !f; ++c) {
+            float x = v.x + ((c & 1) ? halo : -halo), y = v.y + ((c & 2) ? halo : -halo), z = v.z + ((c & 4) ? halo : -halo);
+            int bx = (int)floorf(x * 0.0625f), by = (int)floorf(y * 0.0625f), bz = (int)floorf(z * 0.0625f);
+            if ((int)(sh_block_hash(bx, by, bz) % (unsigned)nranks) == rank) f = 1;
+        }
+    }
+    flags[i] = f;
+}
+__global__ void k_compact_strided(const unsigned char* __restrict__ in, const int* __restrict__ flags, const int* __restrict__ pos, int n, int stride,
+                                  unsigned char* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || !flags[i]) return;
+    const float4* src = reinterpret_cast<const float4*>(in + (size_t)i * stride);
+    float4* dst = reinterpret_cast<float4*>(out + (size_t)pos[i] * stride);
+    for (int k = 0; k < stride / 16; ++k) dst[k] = src[k];
+}
+__global__ void k_int_to_double(const int* __restrict__ in, double* __restrict__ out) { if (threadIdx.x == 0) out[0] = (double)in[0]; }
+
 __global__ void k_compact_f4(const float4* __restrict__ in, const int* __restrict__ flags, const int* __restrict__ pos, int n, float4* __restrict__ out) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n && flags[i]) out[pos[i]] = in[i];
@@ -50,6 +76,11 @@ __global__ void k_transform_cloud(const unsigned char* __restrict__ in, int n, i
         const float4 b = *reinterpret_cast<const float4*>(in + (size_t)i * stride + 16);
         *reinterpret_cast<float4*>(out + (size_t)i * stride + 16) = make_float4(b.x, 0.f, 0.f, 0.f);
     }
+}
+
+__global__ void k_gather_refl48(const unsigned char* __restrict__ pts, int n, float* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = reinterpret_cast<const float*>(pts + (size_t)i * 48)[9];
 }
 
 static int install_map_from_xyzw(liliom_ctx* c, int m) {
@@ -173,7 +204,7 @@ extern "C" void liliom_destroy(liliom_ctx* c) {
                       &c->vg_keys2, &c->vg_vals, &c->vg_vals2, &c->vg_flags, &c->vg_rank, &c->vg_params, &c->vg_out, &c->vg_minmax, &c->vg_count,
                       &c->cub_tmp, &c->map_raw, &c->map_ds, &c->map_xyzw, &c->map_sorted, &c->cell_start, &c->grid_keys, &c->grid_keys2,
                       &c->grid_vals, &c->grid_vals2, &c->feats, &c->corr_valid, &c->corr_plane, &c->nn_idx, &c->nn_sqd, &c->pose_dev,
-                      &c->partials, &c->neq, &c->stats_dev, &c->counter, &c->lm_state, &c->raw_scan};
+                      &c->partials, &c->neq, &c->stats_dev, &c->counter, &c->lm_state, &c->raw_scan, &c->map_refl};
     for (DevBuf* b : bufs) b->release();
     for (auto& f : c->frames) f.buf.release();
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
@@ -281,9 +312,33 @@ extern "C" int liliom_map_push_frame(liliom_ctx* c, const void* surf_ds_body, in
         LILI_CUDA(c, cudaMemcpyAsync(c->raw.p, surf_ds_body, (size_t)n * stride, cudaMemcpyHostToDevice, c->stream));
         Q4 q{pose7[0], pose7[1], pose7[2], pose7[3]};
         D3 t{pose7[4], pose7[5], pose7[6]};
-        k_transform_cloud<<<cdiv(n, 256), 256, 0, c->stream>>>((const unsigned char*)c->raw.p, n, stride, q, t, (unsigned char*)f.buf.p);
-        LILI_TRY(launch_check(c, "k_transform_cloud"));
-        LILI_CUDA(c, cudaStreamSynchronize(c->stream));
+        if (c->nranks == 1) {
+            k_transform_cloud<<<cdiv(n, 256), 256, 0, c->stream>>>((const unsigned char*)c->raw.p, n, stride, q, t, (unsigned char*)f.buf.p);
+            LILI_TRY(launch_check(c, "k_transform_cloud"));
+            LILI_CUDA(c, cudaStreamSynchronize(c->stream));
+        } else {
+            // sharded map maintenance: every rank receives the frame, keeps the points within (search radius + one voxel
+            // diagonal) of a block it owns — every voxel that can reach an owned query's 1 m ball is then complete locally —
+            // and voxel-filters / indexes only its shard.  No inter-rank traffic.
+            LILI_CUDA(c, c->map_ds.ensure((size_t)n * stride));
+            LILI_CUDA(c, c->flags.ensure(((size_t)n + 2) * 4));
+            LILI_CUDA(c, c->idx_a.ensure(((size_t)n + 2) * 4));
+            k_transform_cloud<<<cdiv(n, 256), 256, 0, c->stream>>>((const unsigned char*)c->raw.p, n, stride, q, t, (unsigned char*)c->map_ds.p);
+            LILI_TRY(launch_check(c, "k_transform_cloud"));
+            float cell = 1.0f;
+            while ((double)cell * (double)cell < c->prm.knn_max_sqdist) cell *= 2.0f;
+            const float halo = cell + 1.7320508f * c->prm.leaf_map + 0.05f;
+            k_shard_flags_strided<<<cdiv(n + 1, 256), 256, 0, c->stream>>>((const unsigned char*)c->map_ds.p, n, stride, halo, c->nranks, c->rank, c->flags.as<int>());
+            LILI_TRY(launch_check(c, "k_shard_flags_strided"));
+            LILI_TRY(exclusive_scan_i32(c, c->flags.as<int>(), c->idx_a.as<int>(), n));
+            k_compact_strided<<<cdiv(n, 256), 256, 0, c->stream>>>((const unsigned char*)c->map_ds.p, c->flags.as<int>(), c->idx_a.as<int>(), n, stride,
+                                                                  (unsigned char*)f.buf.p);
+            LILI_TRY(launch_check(c, "k_compact_strided"));
+            int local = 0;
+            LILI_CUDA(c, cudaMemcpyAsync(&local, c->idx_a.as<int>() + n, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+            LILI_CUDA(c, cudaStreamSynchronize(c->stream));
+            f.n = local;
+        }
     }
     c->frames.push_back(f);
     return LILIOM_OK;
@@ -297,25 +352,38 @@ extern "C" int liliom_map_rebuild(liliom_ctx* c, int* n_map_out) {
     for (auto& f : c->frames) total += (size_t)f.n;
     c->map_ready = false; c->map_n = 0; c->map_n_global = 0;
     if (n_map_out) *n_map_out = 0;
-    if (total == 0) { c->map_ready = true; return LILIOM_OK; }
-    LILI_CUDA(c, c->map_raw.ensure(total * stride));
-    LILI_CUDA(c, c->map_ds.ensure(total * stride));
+    if (total == 0 && c->nranks == 1) { c->map_ready = true; return LILIOM_OK; }
+    LILI_CUDA(c, c->map_raw.ensure((total > 0 ? total : 1) * stride));
+    LILI_CUDA(c, c->map_ds.ensure((total > 0 ? total : 1) * stride));
     LILI_CUDA(c, c->vg_count.ensure(16));
     size_t off = 0;
     for (auto& f : c->frames) {                                                    // :301-302 concatenation, oldest first
         if (f.n) LILI_CUDA(c, cudaMemcpyAsync((unsigned char*)c->map_raw.p + off * stride, f.buf.p, (size_t)f.n * stride, cudaMemcpyDeviceToDevice, c->stream));
         off += (size_t)f.n;
     }
-    LILI_TRY(voxelgrid_dev(c, c->map_raw.p, (int)total, stride, c->prm.leaf_map, c->map_ds.p, c->vg_count.as<int>()));   // :316-317
-    int* hp = reinterpret_cast<int*>(c->h_pin);
-    LILI_CUDA(c, cudaMemcpyAsync(hp, c->vg_count.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    LILI_CUDA(c, cudaStreamSynchronize(c->stream));
-    const int m = hp[0];
+    int m = 0;
+    if (total > 0) {
+        LILI_TRY(voxelgrid_dev(c, c->map_raw.p, (int)total, stride, c->prm.leaf_map, c->map_ds.p, c->vg_count.as<int>()));   // :316-317
+        int* hp = reinterpret_cast<int*>(c->h_pin);
+        LILI_CUDA(c, cudaMemcpyAsync(hp, c->vg_count.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        LILI_CUDA(c, cudaStreamSynchronize(c->stream));
+        m = hp[0];
+    }
     LILI_CUDA(c, c->map_xyzw.ensure((size_t)(m > 0 ? m : 1) * sizeof(float4)));
     LILI_TRY(repack_to_f4(c, c->map_ds.p, m, stride, c->map_xyzw.as<float4>()));
     c->map_n_global = m;
-    if (c->nranks > 1) LILI_TRY(install_map_from_xyzw(c, m));
-    else LILI_TRY(grid_build(c, m));
+    if (c->nranks > 1) {
+        LILI_TRY(install_map_from_xyzw(c, m));          // drops the (possibly incomplete) voxels beyond the 1-cell halo
+        // the "< 10 map points" guard (L/src/LidarOdometry.cpp:485-488) is about the whole map: sum the owned-voxel counts
+        LILI_CUDA(c, c->neq.ensure(32 * sizeof(double)));
+        double mine = (double)c->map_n;
+        LILI_CUDA(c, cudaMemcpyAsync(c->neq.p, &mine, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        LILI_TRY(nccl_allreduce_sum_f64(c, c->neq.as<double>(), 1));
+        double tot = 0;
+        LILI_CUDA(c, cudaMemcpyAsync(&tot, c->neq.p, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        LILI_CUDA(c, cudaStreamSynchronize(c->stream));
+        c->map_n_global = (int)tot;                     // halo voxels are counted on several ranks: an upper bound >= the true size
+    } else LILI_TRY(grid_build(c, m));
     LILI_CUDA(c, cudaStreamSynchronize(c->stream));
     if (n_map_out) *n_map_out = m;
     return LILIOM_OK;
@@ -324,12 +392,35 @@ extern "C" int liliom_map_rebuild(liliom_ctx* c, int* n_map_out) {
 extern "C" int liliom_map_set_points(liliom_ctx* c, const liliom_f4* xyzw, int m) {
     if (!c || m < 0 || (m > 0 && !xyzw)) return LILIOM_E_ARG;
     LILI_CUDA(c, cudaSetDevice(c->device));
+    c->map_refl.release();
     c->map_ready = false;
     LILI_CUDA(c, c->map_xyzw.ensure((size_t)(m > 0 ? m : 1) * sizeof(float4)));
     LILI_CUDA(c, c->raw.ensure((size_t)(m > 0 ? m : 1) * sizeof(float4)));
     if (m > 0) {
         LILI_CUDA(c, cudaMemcpyAsync(c->raw.p, xyzw, (size_t)m * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
         LILI_TRY(repack_to_f4(c, c->raw.p, m, 16, c->map_xyzw.as<float4>()));
+    }
+    LILI_TRY(install_map_from_xyzw(c, m));
+    LILI_CUDA(c, cudaStreamSynchronize(c->stream));
+    return LILIOM_OK;
+}
+
+// Install a PCL-layout cloud as the map, keeping its reflectivity channel for the Horizon backend variant.
+extern "C" int liliom_map_set_cloud(liliom_ctx* c, const void* pts, int m, int stride) {
+    if (!c || m < 0 || (m > 0 && !pts) || (stride != 48 && stride != 32)) return LILIOM_E_ARG;
+    LILI_CUDA(c, cudaSetDevice(c->device));
+    if (c->nranks > 1) { c->last_error = "liliom_map_set_cloud is single-GPU"; return LILIOM_E_ARG; }
+    c->map_ready = false;
+    LILI_CUDA(c, c->map_xyzw.ensure((size_t)(m > 0 ? m : 1) * sizeof(float4)));
+    LILI_CUDA(c, c->map_refl.ensure((size_t)(m > 0 ? m : 1) * sizeof(float)));
+    LILI_CUDA(c, c->raw.ensure((size_t)(m > 0 ? m : 1) * stride));
+    if (m > 0) {
+        LILI_CUDA(c, cudaMemcpyAsync(c->raw.p, pts, (size_t)m * stride, cudaMemcpyHostToDevice, c->stream));
+        LILI_TRY(repack_to_f4(c, c->raw.p, m, stride, c->map_xyzw.as<float4>()));
+        if (stride == 48) {
+            k_gather_refl48<<<cdiv(m, 256), 256, 0, c->stream>>>((const unsigned char*)c->raw.p, m, c->map_refl.as<float>());
+            LILI_TRY(launch_check(c, "k_gather_refl48"));
+        } else LILI_CUDA(c, cudaMemsetAsync(c->map_refl.p, 0, (size_t)m * sizeof(float), c->stream));
     }
     LILI_TRY(install_map_from_xyzw(c, m));
     LILI_CUDA(c, cudaStreamSynchronize(c->stream));

@@ -18,6 +18,7 @@ struct BkArgs {
     int variant;
     double max_sqd, plane_thres, w_gate, lidar_const;
     unsigned char* valid; float* pa; float* pb; float4* plane; double* score;
+    const float* map_refl; const float* feat_refl; double reflect_thres;   // Horizon backend variant (L:1617-1638), nullptr = ROT variant
 };
 
 __global__ void __launch_bounds__(kBlock) k_backend_edge(BkArgs a) {
@@ -98,8 +99,25 @@ __global__ void __launch_bounds__(kBlock) k_backend_surf(BkArgs a) {
         double A[5][3], B[5];
         float4 m[5];
         for (int j = 0; j < 5; ++j) { m[j] = a.map_orig[pos[j]]; A[j][0] = m[j].x; A[j][1] = m[j].y; A[j][2] = m[j].z; B[j] = -1.0; }
-        double nv[3];
-        colpiv_qr_solve_5x3(A, B, nv);                                                 // R:1484
+        double sum_w = 0.0;
+        bool skip = false;
+        if (a.map_refl) {                                                              // L:1617-1638: rows weighted by 1/|d reflectivity| / sum
+            double vw[5];
+            const float fr = a.feat_refl[qi];
+            for (int j = 0; j < 5; ++j) {
+                const double tmp_w = (double)fabsf(fsubx(fr, a.map_refl[pos[j]]));
+                sum_w = addx(sum_w, tmp_w);
+                vw[j] = 1.0 / tmp_w;          // +inf when the reflectivities coincide, as in the reference
+            }
+            if (sum_w > a.reflect_thres) skip = true;                                  // L:1628
+            for (int j = 0; j < 5; ++j) {
+                const double w = vw[j] / sum_w;
+                A[j][0] = mulx(w, (double)m[j].x); A[j][1] = mulx(w, (double)m[j].y); A[j][2] = mulx(w, (double)m[j].z);
+                B[j] = mulx(B[j], w);
+            }
+        }
+        double nv[3] = {0, 0, 0};
+        if (!skip) colpiv_qr_solve_5x3(A, B, nv);                                      // R:1484 / L:1641
         double n2 = nv[0] * nv[0] + nv[1] * nv[1] + nv[2] * nv[2];
         double nn = sqrt(n2);
         double normInverse = 1.0 / nn;
@@ -107,6 +125,7 @@ __global__ void __launch_bounds__(kBlock) k_backend_surf(BkArgs a) {
         bool planeValid = true;
         for (int j = 0; j < 5; ++j)                                                    // R:1489-1497
             if (fabs(nv[0] * m[j].x + nv[1] * m[j].y + nv[2] * m[j].z + normInverse) > a.plane_thres) planeValid = false;
+        if (skip) planeValid = false;
         if (planeValid) {
             float pd = (float)addx(addx(addx(mulx(nv[0], (double)sx), mulx(nv[1], (double)sy)), mulx(nv[2], (double)sz)), normInverse);
             float rng = __fsqrt_rn(__fsqrt_rn(faddx(faddx(fmulx(sx, sx), fmulx(sy, sy)), fmulx(sz, sz))));
@@ -114,7 +133,8 @@ __global__ void __launch_bounds__(kBlock) k_backend_surf(BkArgs a) {
             if ((double)weight > a.w_gate) {                                           // R:1504
                 pl = make_float4((float)mulx((double)weight, nv[0]), (float)mulx((double)weight, nv[1]),
                                  (float)mulx((double)weight, nv[2]), (float)mulx((double)weight, normInverse));
-                sc = a.lidar_const * (double)weight;                                   // R:1515
+                sc = a.map_refl ? a.lidar_const * ((double)weight + exp(-sum_w))          // L:1676
+                                : a.lidar_const * (double)weight;                             // R:1515
                 ok = true;
             }
         }
@@ -122,6 +142,12 @@ __global__ void __launch_bounds__(kBlock) k_backend_surf(BkArgs a) {
     a.valid[qi] = ok ? 1 : 0;
     a.plane[qi] = pl;
     a.score[qi] = sc;
+}
+
+// curvature (= 0.1 * reflectivity, L/src/FormatConvert.cpp:21) of 48-byte points
+__global__ void k_gather_refl(const unsigned char* __restrict__ pts, int n, float* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = reinterpret_cast<const float*>(pts + (size_t)i * 48)[9];
 }
 
 static int backend_prepare(liliom_ctx* c, const void* feats, int n, int stride) {
@@ -169,9 +195,9 @@ extern "C" int liliom_correspond_edge(liliom_ctx* c, const void* feats, int n, i
     return LILIOM_OK;
 }
 
-extern "C" int liliom_correspond_surf(liliom_ctx* c, const void* feats, int n, int stride, const double pose7[7], double kd_max_radius,
-                                      double surf_dist_thres, double w_gate, double lidar_const, unsigned char* valid, float* plane,
-                                      double* score) {
+static int correspond_surf_impl(liliom_ctx* c, const void* feats, int n, int stride, const double pose7[7], double kd_max_radius,
+                                double surf_dist_thres, double w_gate, double lidar_const, bool refl, double reflect_thres,
+                                unsigned char* valid, float* plane, double* score) {
     if (!c || !pose7 || !valid || !plane || !score) return LILIOM_E_ARG;
     LILI_CUDA(c, cudaSetDevice(c->device));
     {   // the grid's cell size bounds the exact search radius
@@ -190,6 +216,13 @@ extern "C" int liliom_correspond_surf(liliom_ctx* c, const void* feats, int n, i
     a.feats = c->feats.as<float4>(); a.n = n; a.map = c->map_sorted.as<float4>(); a.map_orig = c->map_xyzw.as<float4>(); a.cell_start = c->cell_start.as<int>(); a.g = c->grid;
     a.q = Q4{pose7[0], pose7[1], pose7[2], pose7[3]}; a.t = D3{pose7[4], pose7[5], pose7[6]};
     a.max_sqd = kd_max_radius; a.plane_thres = surf_dist_thres; a.w_gate = w_gate; a.lidar_const = lidar_const;
+    if (refl) {
+        if (stride != 48 || !c->map_refl.p) { c->last_error = "reflectivity variant needs 48-byte features and a map installed with liliom_map_set_cloud"; return LILIOM_E_ARG; }
+        LILI_CUDA(c, c->nn_idx.ensure((size_t)n * 4 + 16));
+        k_gather_refl<<<cdiv(n, 256), 256, 0, c->stream>>>((const unsigned char*)c->raw.p, n, c->nn_idx.as<float>());
+        LILI_TRY(launch_check(c, "k_gather_refl"));
+        a.map_refl = c->map_refl.as<float>(); a.feat_refl = c->nn_idx.as<float>(); a.reflect_thres = reflect_thres;
+    }
     a.valid = c->corr_valid.as<unsigned char>(); a.plane = c->corr_plane.as<float4>(); a.score = c->nn_sqd.as<double>();
     k_backend_surf<<<cdiv((long long)n * kLanes, kBlock), kBlock, 0, c->stream>>>(a);
     LILI_TRY(launch_check(c, "k_backend_surf"));
@@ -198,4 +231,16 @@ extern "C" int liliom_correspond_surf(liliom_ctx* c, const void* feats, int n, i
     LILI_CUDA(c, cudaMemcpyAsync(score, a.score, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
     LILI_CUDA(c, cudaStreamSynchronize(c->stream));
     return LILIOM_OK;
+}
+
+extern "C" int liliom_correspond_surf(liliom_ctx* c, const void* feats, int n, int stride, const double pose7[7], double kd_max_radius,
+                                      double surf_dist_thres, double w_gate, double lidar_const, unsigned char* valid, float* plane,
+                                      double* score) {
+    return correspond_surf_impl(c, feats, n, stride, pose7, kd_max_radius, surf_dist_thres, w_gate, lidar_const, false, 0.0, valid, plane, score);
+}
+
+extern "C" int liliom_correspond_surf_refl(liliom_ctx* c, const void* feats48, int n, const double pose7[7], double kd_max_radius,
+                                           double surf_dist_thres, double w_gate, double lidar_const, double reflect_thres,
+                                           unsigned char* valid, float* plane, double* score) {
+    return correspond_surf_impl(c, feats48, n, 48, pose7, kd_max_radius, surf_dist_thres, w_gate, lidar_const, true, reflect_thres, valid, plane, score);
 }

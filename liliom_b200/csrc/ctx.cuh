@@ -93,6 +93,7 @@ struct liliom_ctx {
     lili::DevBuf map_raw;                // concatenated frames (stride bytes)
     lili::DevBuf map_ds;                 // VoxelGrid output (stride bytes) or installed float4
     lili::DevBuf map_xyzw;               // float4 in map_download order (w = index)
+    lili::DevBuf map_refl;               // optional per-point reflectivity channel (liliom_map_set_cloud)
     lili::DevBuf map_sorted;             // float4 sorted by cell, w = original index bits
     lili::DevBuf cell_start;             // ncells + 1
     lili::DevBuf grid_keys, grid_keys2, grid_vals, grid_vals2;

@@ -107,7 +107,18 @@ __global__ void k_cell_bounds(const uint32_t* __restrict__ keys, int n, int ncel
 int grid_build(liliom_ctx* c, int m) {
     c->map_ready = false;
     c->map_n = m;
-    if (m <= 0) { c->grid = GridDesc{}; return LILIOM_OK; }
+    if (m <= 0) {   // empty (shard of the) map: a 1-cell grid with no points, so that collective callers still run every launch
+        GridDesc g{};
+        g.inv_cell = 1.0f; g.dim[0] = g.dim[1] = g.dim[2] = 1; g.ncells = 1;
+        c->grid = g;
+        LILI_CUDA(c, c->cell_start.ensure(4 * sizeof(int)));
+        LILI_CUDA(c, cudaMemsetAsync(c->cell_start.p, 0, 4 * sizeof(int), c->stream));
+        LILI_CUDA(c, c->map_sorted.ensure(sizeof(float4)));
+        LILI_CUDA(c, c->map_xyzw.ensure(sizeof(float4)));
+        c->map_n = 0;
+        c->map_ready = true;
+        return LILIOM_OK;
+    }
     float4* pts = c->map_xyzw.as<float4>();
     LILI_CUDA(c, c->vg_minmax.ensure(8 * sizeof(int)));
     int* mm = c->vg_minmax.as<int>();

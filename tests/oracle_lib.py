@@ -169,11 +169,14 @@ def correspond_edge(tree: KdTree, feats, pose7, variant=0):
     return valid[:n], pa[:n], pb[:n]
 
 
-def correspond_surf_backend(tree: KdTree, feats, pose7, kd_max_radius=1.0, surf_dist_thres=0.06, w_gate=0.3, lidar_const=1.0):
+def correspond_surf_backend(tree: KdTree, feats, pose7, kd_max_radius=1.0, surf_dist_thres=0.06, w_gate=0.3, lidar_const=1.0,
+                            map_refl=None, feat_refl=None, reflect_thres=0.0):
     f = _f4(feats); n = len(f)
     valid = np.zeros(max(n, 1), np.uint8); plane = np.zeros((max(n, 1), 4), np.float32); score = np.zeros(max(n, 1), np.float64)
+    mr = None if map_refl is None else np.ascontiguousarray(map_refl, np.float32)
+    fr = None if feat_refl is None else np.ascontiguousarray(feat_refl, np.float32)
     lib().orc_correspond_surf_backend(tree.h, _p(tree.map), len(tree.map), _p(f), n, _d(np.asarray(pose7, np.float64)), kd_max_radius,
-                                      surf_dist_thres, w_gate, lidar_const, None, None, 0.0, _p(valid), _p(plane), _p(score))
+                                      surf_dist_thres, w_gate, lidar_const, _p(mr), _p(fr), reflect_thres, _p(valid), _p(plane), _p(score))
     return valid[:n], plane[:n], score[:n]
 
 

@@ -319,3 +319,30 @@ def test_odometry_call_and_sort_width_speculation(ctx48, oracle, world_small, s2
         pose, st, ds = ctx48.odometry(cloud, world_small["guess"], 5, mode=1)
         _fields_equal(ds, ds_o, ["x", "y", "z", "nx", "ny", "nz", "intensity", "curvature"])
         _pose_close(pose, pose_o)
+
+
+def test_backend_reflectivity_weighted_planes(oracle, world_small, s2m_case):
+    """Horizon BackendFusion variant (L/src/BackendFusion.cpp:1601-1681): reflectivity-weighted plane rows."""
+    import liliom_b200 as L
+    rng = np.random.default_rng(9)
+    # a surf local map in the PCL layout with a reflectivity channel: the down-sampled features of the sweep, at the true pose
+    ds = s2m_case["ds"].copy()
+    map_cloud = oracle.transform_cloud(ds, world_small["T"])
+    map_cloud["curvature"] = rng.uniform(1.0, 20.0, len(map_cloud)).astype(np.float32)
+    map_cloud["curvature"][::17] = 5.0                                 # exact reflectivity ties -> 1/0 rows, as in the reference
+    feats = ds.copy()
+    feats["curvature"] = rng.uniform(1.0, 20.0, len(feats)).astype(np.float32)
+    feats["curvature"][::17] = 5.0
+    m4 = np.ones((len(map_cloud), 4), np.float32); m4[:, 0] = map_cloud["x"]; m4[:, 1] = map_cloud["y"]; m4[:, 2] = map_cloud["z"]
+    tree = oracle.KdTree(m4)
+    pose = world_small["guess"]
+    c = L.Context(variant=0)
+    c.map_set_cloud(map_cloud)
+    for thres in (40.0, 25.0):
+        v_o, pl_o, sc_o = oracle.correspond_surf_backend(tree, feats, pose, 1.0, 0.18, 0.2, 0.8, map_cloud["curvature"], feats["curvature"], thres)
+        v, pl, sc = c.correspond_surf_refl(feats, pose, 1.0, 0.18, 0.2, 0.8, thres)
+        assert np.array_equal(v, v_o)
+        np.testing.assert_allclose(pl, pl_o, rtol=5e-6, atol=1e-6)
+        np.testing.assert_allclose(sc, sc_o, rtol=1e-6, atol=1e-9)
+    assert v_o.sum() > 20
+    c.close()
