@@ -112,6 +112,7 @@ struct liliom_ctx {
     lili::DevBuf stats_dev;              // iterations x kStatsDoubles
     lili::DevBuf counter;                // last-block ticket + scratch ints
     lili::DevBuf lm_state;
+    lili::DevBuf slots_buf;              // search -> fit hand-off of the split path (48 B per query)
     unsigned int bar_arrivals = 0;       // total grid-barrier arrivals issued so far (persistent GN kernel)
 
     // ---- multi-GPU ----

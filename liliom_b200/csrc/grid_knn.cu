@@ -184,6 +184,8 @@ struct KnnArgs {
     int nranks, rank;                   // multi-GPU ownership filter (16 m block hash)
     long long* dbg;                     // optional phase timestamps (LILIOM_DEBUG_TIMING)
     int interleave;                     // 1: deal tasks to warps block-cyclically (load balance for small scans)
+    struct Slot* slots_g;               // split path (large query sets): search kernel -> fit kernel hand-off, 48 B per query
+    int fit_only;                       // 1: phase A is skipped, slots come from slots_g (written by k_knn_search)
 };
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -197,6 +199,7 @@ struct Slot {
     int   idx[5];            // neighbour indices into map_orig; idx[0] < 0: no 5-NN inside the radius
     float sx, sy, sz;        // transformed query (fp32, as the kd-tree saw it)
     float fx, fy, fz;        // body-frame query (phase B re-derives R p from it)
+    int   pad;               // 48 bytes: three 16-byte stores in the split path
 };
 struct Row { double J[6]; double r; double half_rho; };   // robustified Jacobian row, residual, rho/2
 
@@ -245,6 +248,12 @@ __device__ __forceinline__ void knn_phases(const KnnArgs& a, const Q4& q, const 
 #pragma unroll 1
     for (int task = gw; task < ntasks; task += nw) {
         // ---------------- phase A: cooperative exact 5-NN, one query per lane group per round
+        if (a.fit_only) {
+            if (lane < per_task) {
+                const int qi = task * per_task + lane;
+                if (qi < n_q) S.slots[warp][lane] = a.slots_g[qi];
+            }
+        } else
 #pragma unroll 1
         for (int r = 0; r < a.rounds; ++r) {
             const int slot = r * GROUPS + grp;
@@ -444,6 +453,40 @@ __device__ __forceinline__ void write_neq_stats(const KnnArgs& a, const KnnSmem&
             else if (threadIdx.x == 27) stats[2] = v;
             else { stats[0] = v; stats[1] = 1.0; }
         }
+    }
+}
+
+
+// ---- split path for large query sets (opt-in, LILIOM_SPLIT=1): the search needs ~60 registers, the fp64 fit ~128, so
+// two kernels let the search run at twice the occupancy.  It did not pay on B200 (81 vs 75.6 us at 128k queries): the
+// ranking is bound by dependent integer compare/select chains, not by exposed memory latency.
+__global__ void __launch_bounds__(kBlock, 4) k_knn_search(KnnArgs a) {
+    const int n_q = a.n_dev ? min(*a.n_dev, a.n) : a.n;
+    const Q4 q{a.pose[0], a.pose[1], a.pose[2], a.pose[3]};
+    const D3 t{a.pose[4], a.pose[5], a.pose[6]};
+    unsigned long long cand = 0;
+    for (int qi = blockIdx.x * blockDim.x + threadIdx.x; qi < n_q; qi += gridDim.x * blockDim.x) {
+        const float4 f = a.feats[qi];
+        const D3 pw = qrot_x(q, D3{(double)f.x, (double)f.y, (double)f.z});
+        const float sx = (float)addx(pw.x, t.x), sy = (float)addx(pw.y, t.y), sz = (float)addx(pw.z, t.z);
+        Top5 top;
+        top5_init(top);
+        const bool live = !(a.nranks > 1 && owner_of(sx, sy, sz, a.nranks) != a.rank);
+        if (live) group_knn5<1, 4>(sx, sy, sz, a.map, a.cell_start, a.g, 0, 1u << (threadIdx.x & 31), top, cand);
+        const bool ok = live && top.k4 != ~0ull && ((double)top5_dist(top.k4) < a.max_sqd);
+        Slot s;
+        s.idx[0] = ok ? top5_index(top.k0) : -1; s.idx[1] = top5_index(top.k1); s.idx[2] = top5_index(top.k2);
+        s.idx[3] = top5_index(top.k3); s.idx[4] = top5_index(top.k4);
+        s.sx = sx; s.sy = sy; s.sz = sz; s.fx = f.x; s.fy = f.y; s.fz = f.z;
+        int4* dst = reinterpret_cast<int4*>(a.slots_g + qi);
+        dst[0] = make_int4(s.idx[0], s.idx[1], s.idx[2], s.idx[3]);
+        dst[1] = make_int4(s.idx[4], __float_as_int(sx), __float_as_int(sy), __float_as_int(sz));
+        dst[2] = make_int4(__float_as_int(f.x), __float_as_int(f.y), __float_as_int(f.z), 0);
+    }
+    if (a.cand_total) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) cand += __shfl_xor_sync(0xffffffffu, cand, o);
+        if ((threadIdx.x & 31) == 0 && cand) atomicAdd(a.cand_total, cand);
     }
 }
 
@@ -896,6 +939,11 @@ int s2m_run(liliom_ctx* c, double pose7[7], int match_cnt, int max_num_iter, int
         }
     }
     const int launches = persistent ? 0 : ((iters == 0 && want_corr) ? 1 : iters);
+    // measured on B200 (128k queries): fused 75.6 us, split 81.0 us — the search is issue-bound, not occupancy-bound; opt-in only
+    const bool split = lanes == 1 && !want_corr && getenv("LILIOM_SPLIT");
+    if (split) LILI_CUDA(c, c->slots_buf.ensure((size_t)n * sizeof(Slot)));
+    a.slots_g = split ? c->slots_buf.as<Slot>() : nullptr;
+    a.fit_only = 0;
     for (int it = 0; it < launches; ++it) {
         a.stats = c->stats_dev.as<double>() + (size_t)it * kStatsDoubles;
         const bool multi = c->nranks > 1;
@@ -908,7 +956,16 @@ int s2m_run(liliom_ctx* c, double pose7[7], int match_cnt, int max_num_iter, int
             ev = c->ev_used; c->ev_used += 2;
             LILI_CUDA(c, cudaEventRecord(c->ev_pool[ev], c->stream));
         }
-        if (lanes == 16) k_knn_plane<16><<<grid, kBlock, 0, c->stream>>>(a);
+        if (split) {
+            KnnArgs sa = a;
+            k_knn_search<<<min(cdiv(n, kBlock), c->sm_count * 4), kBlock, 0, c->stream>>>(sa);
+            LILI_TRY(launch_check(c, "k_knn_search"));
+            a.fit_only = 1;
+            a.cand_total = nullptr;
+            k_knn_plane<1><<<grid, kBlock, 0, c->stream>>>(a);
+            a.fit_only = 0;
+            a.cand_total = sa.cand_total;
+        } else if (lanes == 16) k_knn_plane<16><<<grid, kBlock, 0, c->stream>>>(a);
         else if (lanes == 1) k_knn_plane<1><<<grid, kBlock, 0, c->stream>>>(a);
         else if (lanes == 2) k_knn_plane<2><<<grid, kBlock, 0, c->stream>>>(a);
         else if (lanes == 4) k_knn_plane<4><<<grid, kBlock, 0, c->stream>>>(a);

@@ -71,7 +71,7 @@ __device__ __forceinline__ u64 make_key(float sx, float sy, float sz, const floa
 // whole query: consecutive queries are spatial neighbours (VoxelGrid output order), so the warp's
 // loads hit the same cells in L1.  On return every lane of the group holds the merged top-5.
 // `cand` accumulates the number of map points this lane examined.
-template <int LANES>
+template <int LANES, int BATCH = 8>
 __device__ __forceinline__ void group_knn5(float sx, float sy, float sz, const float4* __restrict__ map,
                                            const int* __restrict__ cell_start, const GridDesc& g, int sub, unsigned gmask,
                                            Top5& top, unsigned long long& cand, long long* dbg = nullptr) {
@@ -99,12 +99,12 @@ __device__ __forceinline__ void group_knn5(float sx, float sy, float sz, const f
         row_range(row + LANES, nb, ne);          // next run's bounds are in flight while this run is ranked
         cand += (unsigned long long)(e - b);
 #pragma unroll 1
-        for (int p0 = b; p0 < e; p0 += 8) {
-            float4 c[8];
+        for (int p0 = b; p0 < e; p0 += BATCH) {
+            float4 c[BATCH];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) if (p0 + i < e) c[i] = __ldg(map + p0 + i);
+            for (int i = 0; i < BATCH; ++i) if (p0 + i < e) c[i] = __ldg(map + p0 + i);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) if (p0 + i < e) top5_insert(top, make_key(sx, sy, sz, c[i]));
+            for (int i = 0; i < BATCH; ++i) if (p0 + i < e) top5_insert(top, make_key(sx, sy, sz, c[i]));
         }
         b = nb; e = ne;
     }

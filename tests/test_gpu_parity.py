@@ -346,3 +346,71 @@ def test_backend_reflectivity_weighted_planes(oracle, world_small, s2m_case):
         np.testing.assert_allclose(sc, sc_o, rtol=1e-6, atol=1e-9)
     assert v_o.sum() > 20
     c.close()
+
+
+# ---------------------------------------------------------------- ROT package end to end (BASELINE configs[2] as a parity case)
+def test_rot_pipeline_extract_downsample_scan_to_map(ctx32, oracle, world_small):
+    """HDL-64E sweep -> LiLi-OM-ROT extractor -> VoxelGrid(0.4) -> scan-to-map on 32-byte points
+    (R/src/Preprocessing.cpp + R/src/LidarOdometry.cpp), GN and Ceres-faithful modes."""
+    import liliom_b200 as L
+    rc, surf_o, edge_o, cut_o, lab_o, cur_o = oracle.extract_rot(world_small["hdl"], world_small["q_hdl"], (1, 0, 0, 0), 64, 4)
+    surf, edge, cut = ctx32.extract_rot(world_small["hdl"], world_small["q_hdl"])
+    _fields_equal(surf, surf_o, ["x", "y", "z", "intensity"])
+    ctx32.map_set_points(world_small["map"])
+    tree = oracle.KdTree(world_small["map"])
+    ds_o = oracle.voxelgrid(surf_o, 0.4)
+    for mode, run_o in ((1, lambda: oracle.scan_to_map_gn(tree, ds_o, world_small["guess"], 6)),
+                        (0, lambda: oracle.scan_to_map_ceres(tree, ds_o, world_small["guess"], 2, 12))):
+        rc, pose_o, st_o = run_o()
+        pose, st, ds = ctx32.odometry(surf, world_small["guess"], 6 if mode == 1 else 2, max_num_iter=12, mode=mode)
+        _fields_equal(ds, ds_o, ["x", "y", "z", "intensity"])
+        _pose_close(pose, pose_o)
+        assert [s.n_corr for s in st] == [s.n_corr for s in st_o] or mode == 1
+    _pose_close(pose, world_small["T"], tol_t=0.03, tol_r=0.01)
+
+
+# ---------------------------------------------------------------- ragged / degenerate inputs
+def test_scan_to_map_edge_cases(ctx48, oracle, world_small, s2m_case):
+    import liliom_b200 as L
+    guess = world_small["guess"]
+    # no features: the pose is returned unchanged in both modes
+    for mode in (0, 1):
+        pose, st = ctx48.scan_to_map(np.zeros((0, 4), np.float32), guess, 3, mode=mode)
+        assert np.array_equal(pose, guess) and all(s.n_corr == 0 for s in st)
+    # one feature, and features that are nowhere near the map (every 5th neighbour beyond 1 m): no correspondence, no step
+    far = np.ones((64, 4), np.float32); far[:, :3] += 5000.0
+    pose, st = ctx48.scan_to_map(far, guess, 2, mode=1)
+    assert np.array_equal(pose, guess) and st[0].n_corr == 0
+    one = s2m_case["ds"][:1]
+    rc, pose_o, _ = oracle.scan_to_map_gn(s2m_case["tree"], one, guess, 2)
+    pose, st = ctx48.scan_to_map(one, guess, 2, mode=1)
+    assert np.all(np.isfinite(pose))
+    # a map with exact duplicate points and a collinear run (rank-deficient plane fits take the QR path)
+    m = world_small["map"][:20000].copy()
+    m = np.concatenate([m, m[:500], np.stack([np.linspace(0, 30, 400), np.full(400, 3.0), np.full(400, 1.0), np.ones(400)], 1).astype(np.float32)])
+    c = L.Context(variant=0)
+    c.map_set_points(m)
+    tree = oracle.KdTree(m)
+    q = np.ones((300, 4), np.float32)
+    q[:, 0] = np.linspace(0.2, 29.7, 300); q[:, 1] = 3.02; q[:, 2] = 1.01
+    ident = np.array([1.0, 0, 0, 0, 0, 0, 0])
+    cnt, valid_o, plane_o, idx_o, pw_o = oracle.find_surf_corr(tree, q, ident)
+    valid, plane, idx, sqd, s29 = c.find_surf_corr(q, ident)
+    _, sqd_o = tree.knn5(pw_o)
+    inside = sqd_o[:, 4] < 1.0
+    assert inside.sum() > 200 and np.array_equal(idx[inside], idx_o[inside])
+    assert np.array_equal(valid, valid_o)
+    ok = valid_o == 1
+    np.testing.assert_allclose(plane[ok], plane_o[ok], rtol=1e-4, atol=1e-5)
+    c.close()
+
+
+def test_map_too_large_for_dense_grid():
+    import liliom_b200 as L
+    c = L.Context(variant=0)
+    m = np.ones((16, 4), np.float32)
+    m[:, 0] = np.linspace(-4e5, 4e5, 16); m[:, 1] = np.linspace(-4e5, 4e5, 16)
+    with pytest.raises(L.LiliomError) as e:
+        c.map_set_points(m)
+    assert e.value.code == -5           # LILIOM_E_GRID: extent needs more than 2^29 one-metre cells
+    c.close()
