@@ -443,11 +443,8 @@ int rot_extract_dev(liliom_ctx* c, int n, const double q_imu[4], const double q_
     k_rot_curv<<<cdiv(n + 1, 256), 256, 0, c->stream>>>(cloud, meta, c->rot_curv.as<float>(), c->rot_label.as<int>(),
                                                         c->rot_lessflat.as<int>(), n);
     LILI_TRY(launch_check(c, "k_rot_curv"));
-    static bool attr_set = false;
-    if (!attr_set) {
-        LILI_CUDA(c, cudaFuncSetAttribute(k_rot_ring, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RingSmem)));
-        attr_set = true;
-    }
+    // per-device function attribute (cheap; a process may hold contexts on several GPUs)
+    LILI_CUDA(c, cudaFuncSetAttribute(k_rot_ring, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RingSmem)));
     k_rot_ring<<<n_scans, 512, sizeof(RingSmem), c->stream>>>(cloud, c->rot_curv.as<float>(), meta, c->prm.ds_rate, c->rot_label.as<int>(),
                                                               c->rot_lessflat.as<int>(), seg_edge, seg_cnt);
     LILI_TRY(launch_check(c, "k_rot_ring"));

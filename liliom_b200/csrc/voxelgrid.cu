@@ -390,12 +390,8 @@ int voxelgrid_dev2(liliom_ctx* c, const void* d_in, int n_max, const int* d_n, i
     const unsigned char* in = (const unsigned char*)d_in;
     if (n_max <= VGS_CAP && getenv("LILIOM_VG_SMALL")) {   // opt-in: a single SM sorts 16k keys in ~300 us, the multi-CTA chain below in ~50
         // scan-sized input: the whole filter in ONE persistent CTA (no host-visible intermediate, 1 launch instead of ~12)
-        static bool attr = false;
-        if (!attr) {
-            LILI_CUDA(c, cudaFuncSetAttribute(k_vg_small<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(VgSmallSmem)));
-            LILI_CUDA(c, cudaFuncSetAttribute(k_vg_small<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(VgSmallSmem)));
-            attr = true;
-        }
+        LILI_CUDA(c, cudaFuncSetAttribute(k_vg_small<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(VgSmallSmem)));
+        LILI_CUDA(c, cudaFuncSetAttribute(k_vg_small<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(VgSmallSmem)));
         if (stride == 48)
             k_vg_small<48><<<1, VGS_THREADS, sizeof(VgSmallSmem), c->stream>>>(in, n_max, d_n, leaf, c->vg_keys2.as<uint32_t>(), c->vg_vals2.as<int>(),
                                                                                 c->vg_rank.as<int>(), (unsigned char*)d_out, d_count, d_feats);
