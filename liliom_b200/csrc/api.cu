@@ -184,6 +184,11 @@ extern "C" int liliom_create(liliom_ctx** out, const liliom_params* p, int devic
     cudaError_t e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete c; return LILIOM_E_CUDA; }
     c->stream = c->own_stream;
+    if (cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_ready, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_copied, cudaEventDisableTiming) != cudaSuccess) {
+        cudaStreamDestroy(c->own_stream); delete c; return LILIOM_E_CUDA;
+    }
     c->h_pin_bytes = 1 << 20;
     e = cudaHostAlloc(&c->h_pin, c->h_pin_bytes, cudaHostAllocDefault);
     if (e != cudaSuccess) { cudaStreamDestroy(c->own_stream); delete c; return LILIOM_E_CUDA; }
@@ -202,13 +207,16 @@ extern "C" void liliom_destroy(liliom_ctx* c) {
                       &c->hz_stage_edge, &c->hz_counts, &c->rot_keys, &c->rot_keys2, &c->rot_vals, &c->rot_vals2, &c->rot_cloud, &c->rot_curv,
                       &c->rot_label, &c->rot_picked, &c->rot_sort, &c->rot_ring, &c->rot_meta, &c->rot_lessflat, &c->rot_seg_edge, &c->vg_keys,
                       &c->vg_keys2, &c->vg_vals, &c->vg_vals2, &c->vg_flags, &c->vg_rank, &c->vg_params, &c->vg_out, &c->vg_minmax, &c->vg_count,
-                      &c->cub_tmp, &c->map_raw, &c->map_ds, &c->map_xyzw, &c->map_sorted, &c->cell_start, &c->grid_keys, &c->grid_keys2,
+                      &c->cub_tmp, &c->vg_coop, &c->map_raw, &c->map_ds, &c->map_xyzw, &c->map_sorted, &c->cell_start, &c->grid_keys, &c->grid_keys2,
                       &c->grid_vals, &c->grid_vals2, &c->feats, &c->corr_valid, &c->corr_plane, &c->nn_idx, &c->nn_sqd, &c->pose_dev,
                       &c->partials, &c->neq, &c->stats_dev, &c->counter, &c->lm_state, &c->raw_scan, &c->map_refl, &c->slots_buf};
     for (DevBuf* b : bufs) b->release();
     for (auto& f : c->frames) f.buf.release();
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     if (c->h_pin) cudaFreeHost(c->h_pin);
+    if (c->ev_ready) cudaEventDestroy(c->ev_ready);
+    if (c->ev_copied) cudaEventDestroy(c->ev_copied);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }
@@ -223,12 +231,22 @@ extern "C" int liliom_extract_horizon(liliom_ctx* c, const liliom_pt48* pts, int
     LILI_CUDA(c, c->raw.ensure((size_t)(n > 0 ? n : 1) * 48));
     if (n > 0) LILI_CUDA(c, cudaMemcpyAsync(c->raw.p, pts, (size_t)n * 48, cudaMemcpyHostToDevice, c->stream));
     int ns = 0, ne = 0, nc = 0;
-    LILI_TRY(horizon_extract_dev(c, n, q_imu, &ns, &ne, &nc));
-    if ((surf_out && ns > surf_cap) || (edge_out && ne > edge_cap) || (cut_out && nc > cut_cap)) return LILIOM_E_CAPACITY;
-    if (surf_out && ns) LILI_CUDA(c, cudaMemcpyAsync(surf_out, c->surf.p, (size_t)ns * 48, cudaMemcpyDeviceToHost, c->stream));
-    if (edge_out && ne) LILI_CUDA(c, cudaMemcpyAsync(edge_out, c->edge.p, (size_t)ne * 48, cudaMemcpyDeviceToHost, c->stream));
-    if (cut_out && nc) LILI_CUDA(c, cudaMemcpyAsync(cut_out, c->cut.p, (size_t)nc * 48, cudaMemcpyDeviceToHost, c->stream));
+    // The cutted cloud is complete after the de-skew kernel: its D2H runs on the copy stream under the patch kernels.
+    // It is issued before the count is known, so min(n, cut_cap) slots are copied; slots past *n_cut are unspecified.
+    c->early_cut_dst = cut_out; c->early_cut_cap = cut_cap; c->early_cut_issued = false;
+    const int rc_x = horizon_extract_dev(c, n, q_imu, &ns, &ne, &nc);
+    c->early_cut_dst = nullptr;
+    if (rc_x != LILIOM_OK) { if (c->early_cut_issued) cudaStreamSynchronize(c->copy_stream); return rc_x; }
+    const bool over = (surf_out && ns > surf_cap) || (edge_out && ne > edge_cap) || (cut_out && nc > cut_cap);
+    if (!over) {
+        if (surf_out && ns) LILI_CUDA(c, cudaMemcpyAsync(surf_out, c->surf.p, (size_t)ns * 48, cudaMemcpyDeviceToHost, c->stream));
+        if (edge_out && ne) LILI_CUDA(c, cudaMemcpyAsync(edge_out, c->edge.p, (size_t)ne * 48, cudaMemcpyDeviceToHost, c->stream));
+        if (cut_out && nc && !c->early_cut_issued)
+            LILI_CUDA(c, cudaMemcpyAsync(cut_out, c->cut.p, (size_t)nc * 48, cudaMemcpyDeviceToHost, c->stream));
+    }
     LILI_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (c->early_cut_issued) LILI_CUDA(c, cudaStreamSynchronize(c->copy_stream));   // c->cut is reused by the next call
+    if (over) return LILIOM_E_CAPACITY;
     *n_surf = ns; *n_edge = ne; *n_cut = nc;
     return LILIOM_OK;
 }
@@ -273,10 +291,20 @@ extern "C" int liliom_voxelgrid(liliom_ctx* c, const void* pts, int n, int strid
     LILI_CUDA(c, c->vg_out.ensure((size_t)n * stride));
     LILI_CUDA(c, c->vg_count.ensure(16));
     LILI_CUDA(c, cudaMemcpyAsync(c->raw.p, pts, (size_t)n * stride, cudaMemcpyHostToDevice, c->stream));
-    LILI_TRY(voxelgrid_dev(c, c->raw.p, n, stride, leaf, c->vg_out.p, c->vg_count.as<int>()));
+    bool coop = false;
+    LILI_TRY(voxelgrid_coop(c, c->raw.p, n, nullptr, stride, leaf, c->vg_out.p, c->vg_count.as<int>(), nullptr, &coop));
     int* hp = reinterpret_cast<int*>(c->h_pin);
-    LILI_CUDA(c, cudaMemcpyAsync(hp, c->vg_count.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    LILI_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (coop) {      // the cooperative filter may decline the input: its verdict comes back with the count
+        LILI_CUDA(c, cudaMemcpyAsync(hp, c->vg_count.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        LILI_CUDA(c, cudaMemcpyAsync(hp + 16, c->vg_params.p, sizeof(VgParams), cudaMemcpyDeviceToHost, c->stream));
+        LILI_CUDA(c, cudaStreamSynchronize(c->stream));
+        if (reinterpret_cast<const VgParams*>(hp + 16)->bail) coop = false;
+    }
+    if (!coop) {
+        LILI_TRY(voxelgrid_dev(c, c->raw.p, n, stride, leaf, c->vg_out.p, c->vg_count.as<int>()));
+        LILI_CUDA(c, cudaMemcpyAsync(hp, c->vg_count.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        LILI_CUDA(c, cudaStreamSynchronize(c->stream));
+    }
     const int m = hp[0];
     if (out && m > cap) return LILIOM_E_CAPACITY;
     if (out && m) {
@@ -528,9 +556,16 @@ static int odometry_on_resident_surf(liliom_ctx* c, double pose7[7], int match_c
         // speculate that the scan's voxel box has < 2^24 cells (a 200 m sweep at 0.4 m: ~2^21-2^23): one radix pass
         // less.  The box is read back with the pose; on a miss the step is redone with full-width keys.
         const int key_bits = (n_max > 24576 || spec_failed) ? 32 : 24;
-        LILI_TRY(voxelgrid_dev2(c, c->surf.p, n_max, d_n, stride, c->prm.leaf_scan, c->vg_out.p, c->vg_count.as<int>(), c->feats.as<float4>(), key_bits));
+        // scan-sized clouds take the single-launch cooperative filter; it may decline (VgParams::bail, read back with the pose)
+        bool coop = false;
+        if (!spec_failed)
+            LILI_TRY(voxelgrid_coop(c, c->surf.p, n_max, d_n, stride, c->prm.leaf_scan, c->vg_out.p, c->vg_count.as<int>(), c->feats.as<float4>(), &coop));
+        if (!coop)
+            LILI_TRY(voxelgrid_dev2(c, c->surf.p, n_max, d_n, stride, c->prm.leaf_scan, c->vg_out.p, c->vg_count.as<int>(), c->feats.as<float4>(), key_bits));
         c->d_nfeats = c->vg_count.as<int>();
-        c->vg_check = key_bits < 32;
+        c->vg_used24 = !coop && key_bits < 32;
+        c->vg_check = coop || key_bits < 32;
+        c->vg_bail = false;
     } else {   // leaf_scan == 0: benchmark mode, every surf feature is a query
         if (n_max > 0) LILI_CUDA(c, cudaMemcpyAsync(c->vg_out.p, c->surf.p, (size_t)n_max * stride, cudaMemcpyDeviceToDevice, c->stream));
         LILI_TRY(repack_to_f4(c, c->surf.p, n_max, stride, c->feats.as<float4>(), d_n));
@@ -544,7 +579,8 @@ static int odometry_on_resident_surf(liliom_ctx* c, double pose7[7], int match_c
     memcpy(pose_in, pose7, sizeof(pose_in));
     if (rc == LILIOM_OK) {
         rc = s2m_run(c, pose7, match_cnt, max_num_iter, mode, stats, false, nullptr);
-        if (rc == LILIOM_OK && c->vg_check && !spec_failed && c->vg_ncells >= (1LL << 24) - 1) {   // speculation missed: redo with 32-bit keys
+        if (rc == LILIOM_OK && c->vg_check && !spec_failed &&
+            (c->vg_bail || (c->vg_used24 && c->vg_ncells >= (1LL << 24) - 1))) {   // speculation missed: redo with the sort chain, 32-bit keys
             c->vg_check = false;
             c->d_nfeats = nullptr;
             memcpy(pose7, pose_in, sizeof(pose_in));

@@ -36,6 +36,7 @@ struct VgParams {
     int   mul[3];
     int   overflow;    // PCL: "Leaf size is too small" -> output = input
     int   n_finite;
+    int   bail;        // cooperative single-launch filter declined this input (see k_vg_coop): redo with the sort chain
 };
 
 // Dense cell grid over the down-sampled map (the kd-tree's stand-in).
@@ -61,6 +62,11 @@ struct liliom_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;       // stream all work is issued on (own_stream unless liliom_set_stream)
     cudaStream_t own_stream = nullptr;
+    cudaStream_t copy_stream = nullptr;  // D2H of a finished output while later kernels of the same call still run
+    cudaEvent_t  ev_ready = nullptr, ev_copied = nullptr;
+    void*  early_cut_dst = nullptr;      // host destination for the cutted cloud (set per call by the API layer)
+    int    early_cut_cap = 0;
+    bool   early_cut_issued = false;
     std::string last_error;
     int sm_count = 148;
 
@@ -79,6 +85,10 @@ struct liliom_ctx {
     int last_n_feats = 0;        // query count of the previous scan (kernel-shape predictor)
     int n_feats_actual = 0;      // query count read back with the pose
     bool vg_check = false;       // s2m_run also reads vg_params back (speculative key width of the scan VoxelGrid)
+    bool vg_used24 = false;      // ... the sort chain ran with 24-bit keys
+    bool vg_bail = false;        // ... the cooperative filter declined (valid after the sync)
+    unsigned int vg_coop_calls = 0;   // launches of k_vg_coop so far (selects the rotating control slot)
+    lili::DevBuf vg_coop;        // hash table + scratch of the cooperative filter
     long long vg_ncells = 0;     // voxel-box cell count of that VoxelGrid, valid after the sync
     lili::DevBuf raw_scan;       // resident raw sweep (liliom_upload_scan)
     int n_raw_scan = 0;
@@ -167,6 +177,8 @@ int exclusive_scan_i32(liliom_ctx* c, const int* in, int* out, int n);   // out 
 // VoxelGrid on device buffers; d_count receives the output count (int, device).
 int voxelgrid_dev(liliom_ctx* c, const void* d_in, int n, int stride, float leaf, void* d_out, int* d_count);
 // n_max = host upper bound, d_n = optional device-side count (<= n_max); d_feats (optional) also receives float4{x,y,z,index}
+int voxelgrid_coop(liliom_ctx* c, const void* d_in, int n_max, const int* d_n, int stride, float leaf, void* d_out, int* d_count, float4* d_feats,
+                   bool* used);
 int voxelgrid_dev2(liliom_ctx* c, const void* d_in, int n_max, const int* d_n, int stride, float leaf, void* d_out, int* d_count, float4* d_feats,
                    int key_bits = 32);
 

@@ -319,6 +319,14 @@ int horizon_extract_dev(liliom_ctx* c, int n, const double q_imu[4], int* n_surf
     if (n > 0) {
         k_hz_deskew_bin<<<cdiv(n, 128), 128, 0, c->stream>>>(raw, n, flags, cidx, q, c->cut.as<Pt48>(), mat);
         LILI_TRY(launch_check(c, "k_hz_deskew_bin"));
+        if (c->early_cut_dst && c->early_cut_cap > 0) {
+            const size_t cnt = (size_t)min(n, c->early_cut_cap);
+            LILI_CUDA(c, cudaEventRecord(c->ev_ready, c->stream));
+            LILI_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_ready, 0));
+            LILI_CUDA(c, cudaMemcpyAsync(c->early_cut_dst, c->cut.p, cnt * sizeof(Pt48), cudaMemcpyDeviceToHost, c->copy_stream));
+            LILI_CUDA(c, cudaEventRecord(c->ev_copied, c->copy_stream));
+            c->early_cut_issued = true;
+        }
     }
     k_hz_patch<<<cdiv(HZ_PATCHES, HZ_WARPS), HZ_WARPS * 32, 0, c->stream>>>(c->cut.as<Pt48>(), mat, c->prm.surf_thres, c->prm.edge_thres,
                                                                             c->hz_stage_surf.as<Pt48>(), c->hz_stage_edge.as<Pt48>(), counts);

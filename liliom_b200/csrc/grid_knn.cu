@@ -1011,6 +1011,7 @@ int s2m_run(liliom_ctx* c, double pose7[7], int match_cnt, int max_num_iter, int
     if (c->vg_check) {
         const VgParams* vp = reinterpret_cast<const VgParams*>(hp + 48);
         c->vg_ncells = vp->overflow ? 0 : (long long)vp->div_b[0] * vp->div_b[1] * vp->div_b[2];
+        c->vg_bail = vp->bail != 0;
     }
     if (iters > 0) for (int k = 0; k < 7; ++k) pose7[k] = hp[k];
     if (out29) for (int k = 0; k < kNormEq; ++k) out29[k] = hp[8 + k];

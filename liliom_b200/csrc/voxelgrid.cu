@@ -58,6 +58,7 @@ __global__ void k_vg_params(const int* __restrict__ mm, float leaf, VgParams* __
     p.inv_leaf = 1.0f / leaf;                       // Eigen::Array4f::Ones() / leaf_size_
     p.n_finite = mm[6];
     p.overflow = 0;
+    p.bail = 0;
     if (p.n_finite == 0) {
         for (int k = 0; k < 3; ++k) { p.min_b[k] = 0; p.div_b[k] = 1; }
     } else {
@@ -243,6 +244,7 @@ __global__ void __launch_bounds__(VGS_THREADS) k_vg_small(const unsigned char* _
         p.inv_leaf = 1.0f / leaf;
         p.n_finite = mm[6];
         p.overflow = 0;
+        p.bail = 0;
         if (p.n_finite == 0) {
             for (int k = 0; k < 3; ++k) { p.min_b[k] = 0; p.div_b[k] = 1; }
         } else {
@@ -374,6 +376,331 @@ __global__ void __launch_bounds__(VGS_THREADS) k_vg_small(const unsigned char* _
             *reinterpret_cast<float4*>(dst + 16) = make_float4(si / fc, 0.0f, 0.0f, 0.0f);
         }
     }
+}
+
+// ---------------------------------------------------------------------------------------
+// Scan-sized VoxelGrid in ONE cooperative launch, without a sort (n <= VGC_NCAP points).
+// The sort chain above costs ~13 dependent launches (~95 us for a 13k-point /surf_features cloud, almost
+// all of it launch latency and three onesweep passes).  PCL only needs (a) which points share a voxel,
+// (b) the voxels in ascending index order, (c) each voxel's members summed in a fixed order.  With
+// idx = i + j*dx + k*dx*dy and 0 <= i < dx, 0 <= j < dy, ascending idx is lexicographic (k, j, i) order, and
+// i/j/k differ from the absolute cell coordinate floor(p*inv_leaf) only by the box minimum (exact in fp32
+// below 2^24), so neither (a) nor (b) needs the bounding box:
+//   phase 1  every point inserts its absolute (kz, jy, ix) key into a hash table (64-bit CAS), the first
+//            writer appends the key to a dense list; per-slot member count by atomicAdd; box partials
+//   phase 2  output rank of a voxel = number of listed keys below its key (all pairs, one warp per voxel,
+//            the list is a few KB and L1-resident); member segment start by atomicAdd (scratch order)
+//   phase 3  every point drops its index into its voxel's segment
+//   phase 4  one warp per voxel: members ordered by original index (rank by counting), fp32 sums in that
+//            order — the order of the sort chain and of the oracle — centroid written at the voxel's rank
+// Three grid barriers instead of twelve launch boundaries.  Inputs it declines (|cell coordinate| >= 2^20,
+// PCL's index overflow, a voxel with more than VGC_VCAP members) set VgParams::bail and an output count
+// of 0; the caller re-runs the sort chain.  Semantics otherwise identical to k_vg_* above.
+// ---------------------------------------------------------------------------------------
+constexpr int VGC_NCAP = 32768;
+constexpr int VGC_T = 65536;          // hash slots (load factor <= 0.5)
+constexpr int VGC_THREADS = 256;
+constexpr int VGC_WARPS = VGC_THREADS / 32;
+constexpr int VGC_VCAP = 256;         // members per voxel handled in shared memory
+constexpr unsigned long long VGC_EMPTY = ~0ull;
+
+struct VgCoopBufs {
+    unsigned long long* hkey;   // [T]   voxel key per slot (VGC_EMPTY when free; restored by the kernel itself)
+    int* hcnt;                  // [T]   members per slot (0 when free; restored by the kernel itself)
+    int* hoff;                  // [T]   start of the slot's member segment
+    unsigned long long* ukey;   // [NCAP] dense list of occupied keys (arbitrary order)
+    int* uslot;                 // [NCAP] their slots
+    int* urank;                 // [NCAP] their output ranks
+    int* pslot;                 // [NCAP] slot of point i (-1: not finite)
+    int* ppos;                  // [NCAP] arrival number of point i inside its voxel
+    int* members;               // [NCAP] point indices grouped by voxel
+    int* mmpart;                // [7][grid] per-block box partials
+    unsigned int* ctl;          // [4][4] rotating {barrier arrivals, bail flag, #voxels, segment cursor}; slot = call & 3
+};
+
+static size_t vgc_layout(VgCoopBufs& B, unsigned char* base, int grid) {
+    size_t off = 0;
+    auto take = [&](size_t bytes) { unsigned char* p = base ? base + off : nullptr; off += (bytes + 255) & ~(size_t)255; return p; };
+    B.hkey = (unsigned long long*)take((size_t)VGC_T * 8);
+    B.hcnt = (int*)take((size_t)VGC_T * 4);
+    B.hoff = (int*)take((size_t)VGC_T * 4);
+    B.ukey = (unsigned long long*)take((size_t)VGC_NCAP * 8);
+    B.uslot = (int*)take((size_t)VGC_NCAP * 4);
+    B.urank = (int*)take((size_t)VGC_NCAP * 4);
+    B.pslot = (int*)take((size_t)VGC_NCAP * 4);
+    B.ppos = (int*)take((size_t)VGC_NCAP * 4);
+    B.members = (int*)take((size_t)VGC_NCAP * 4);
+    B.mmpart = (int*)take((size_t)7 * grid * 4);
+    B.ctl = (unsigned int*)take(16 * 4);
+    return off;
+}
+
+__device__ __forceinline__ void vgc_barrier(unsigned int* bar, unsigned int target) {
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        atomicAdd(bar, 1u);
+        while ((int)(*reinterpret_cast<volatile unsigned int*>(bar) - target) < 0) { }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+struct VgCoopSmem {
+    int   red[7][VGC_WARPS];
+    int   sidx[VGC_WARPS][VGC_VCAP];
+    float stage[VGC_WARPS][32][8];
+};
+
+template <int STRIDE>
+__global__ void __launch_bounds__(VGC_THREADS) k_vg_coop(const unsigned char* __restrict__ pts, int n_max, const int* __restrict__ d_n, float leaf,
+                                                         VgCoopBufs B, unsigned int call, VgParams* __restrict__ pp,
+                                                         unsigned char* __restrict__ out, int* __restrict__ count_out, float4* __restrict__ feats_out) {
+    __shared__ VgCoopSmem S;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned int G = gridDim.x;
+    const int gtid = blockIdx.x * VGC_THREADS + tid, gthreads = G * VGC_THREADS;
+    const int gwarp = blockIdx.x * VGC_WARPS + warp, gwarps = G * VGC_WARPS;
+    unsigned int* ctl = B.ctl + 4 * (call & 3u);          // [0] barrier, [1] bail, [2] #voxels, [3] segment cursor
+    if (blockIdx.x == 0 && tid < 4) B.ctl[4 * ((call + 1u) & 3u) + tid] = 0u;   // the next launch's slot (nobody uses it now)
+    const int n = d_n ? min(*d_n, n_max) : n_max;
+    const float inv_leaf = 1.0f / leaf;
+
+    // ---- phase 1: hash insert + bounding box partials
+    int lo[3] = {INT_MAX, INT_MAX, INT_MAX}, hi[3] = {INT_MIN, INT_MIN, INT_MIN}, cnt = 0;
+    for (int i = gtid; i < n; i += gthreads) {
+        const float4 v = *reinterpret_cast<const float4*>(pts + (size_t)i * STRIDE);
+        int slot = -1, pos = 0;
+        if (isfinite(v.x) && isfinite(v.y) && isfinite(v.z)) {
+            ++cnt;
+            const int a = vg_f2ord(v.x), b = vg_f2ord(v.y), c = vg_f2ord(v.z);
+            lo[0] = min(lo[0], a); hi[0] = max(hi[0], a);
+            lo[1] = min(lo[1], b); hi[1] = max(hi[1], b);
+            lo[2] = min(lo[2], c); hi[2] = max(hi[2], c);
+            const float fx = floorf(v.x * inv_leaf), fy = floorf(v.y * inv_leaf), fz = floorf(v.z * inv_leaf);
+            const float lim = 1048576.0f;
+            if (!(fabsf(fx) < lim && fabsf(fy) < lim && fabsf(fz) < lim)) {
+                atomicOr(&ctl[1], 1u);
+            } else {
+                const unsigned long long key = ((unsigned long long)((int)fz + (1 << 20)) << 42) | ((unsigned long long)((int)fy + (1 << 20)) << 21) |
+                                               (unsigned long long)((int)fx + (1 << 20));
+                unsigned int s = (unsigned int)((key * 0x9E3779B97F4A7C15ull) >> 48) & (VGC_T - 1);
+                while (true) {
+                    const unsigned long long prev = atomicCAS(&B.hkey[s], VGC_EMPTY, key);
+                    if (prev == VGC_EMPTY) {
+                        const unsigned int u = atomicAdd(&ctl[2], 1u);
+                        B.ukey[u] = key; B.uslot[u] = (int)s;
+                        break;
+                    }
+                    if (prev == key) break;
+                    s = (s + 1) & (VGC_T - 1);
+                }
+                slot = (int)s;
+                pos = atomicAdd(&B.hcnt[s], 1);
+            }
+        }
+        B.pslot[i] = slot; B.ppos[i] = pos;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            lo[k] = min(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], o));
+            hi[k] = max(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], o));
+        }
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { S.red[k][warp] = lo[k]; S.red[3 + k][warp] = hi[k]; }
+        S.red[6][warp] = cnt;
+    }
+    __syncthreads();
+    if (tid < 7) {
+        int v = S.red[tid][0];
+        for (int w = 1; w < VGC_WARPS; ++w) v = tid < 3 ? min(v, S.red[tid][w]) : tid < 6 ? max(v, S.red[tid][w]) : v + S.red[tid][w];
+        B.mmpart[tid * G + blockIdx.x] = v;
+    }
+    vgc_barrier(&ctl[0], G);
+
+    int U = (int)*reinterpret_cast<volatile unsigned int*>(&ctl[2]);
+    unsigned int bail = *reinterpret_cast<volatile unsigned int*>(&ctl[1]);
+    if (!bail) {
+        // ---- phase 2: box parameters (block 0), output ranks and member segments
+        if (blockIdx.x == 0 && warp == 0) {
+            int mm[7] = {INT_MAX, INT_MAX, INT_MAX, INT_MIN, INT_MIN, INT_MIN, 0};
+            for (unsigned int b = lane; b < G; b += 32) {
+#pragma unroll
+                for (int k = 0; k < 7; ++k) {
+                    const int v = __ldcg(&B.mmpart[k * G + b]);
+                    mm[k] = k < 3 ? min(mm[k], v) : k < 6 ? max(mm[k], v) : mm[k] + v;
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                for (int k = 0; k < 7; ++k) {
+                    const int v = __shfl_xor_sync(0xffffffffu, mm[k], o);
+                    mm[k] = k < 3 ? min(mm[k], v) : k < 6 ? max(mm[k], v) : mm[k] + v;
+                }
+            }
+            if (lane == 0) {
+                VgParams p;
+                p.inv_leaf = inv_leaf;
+                p.n_finite = mm[6];
+                p.overflow = 0;
+                p.bail = 0;
+                if (p.n_finite == 0) {
+                    for (int k = 0; k < 3; ++k) { p.min_b[k] = 0; p.div_b[k] = 1; }
+                } else {
+                    long long d[3];
+                    for (int k = 0; k < 3; ++k) {
+                        const float flo = vg_ord2f(mm[k]), fhi = vg_ord2f(mm[3 + k]);
+                        d[k] = (long long)((fhi - flo) * p.inv_leaf) + 1;
+                        p.min_b[k] = (int)floorf(flo * p.inv_leaf);
+                        const int max_b = (int)floorf(fhi * p.inv_leaf);
+                        p.div_b[k] = max_b - p.min_b[k] + 1;
+                    }
+                    if (d[0] * d[1] * d[2] > (long long)INT_MAX) { p.overflow = 1; p.bail = 1; atomicOr(&ctl[1], 4u); }   // PCL copies the input: sort chain
+                }
+                p.mul[0] = 1; p.mul[1] = p.div_b[0]; p.mul[2] = p.div_b[0] * p.div_b[1];
+                *pp = p;
+                *count_out = p.bail ? 0 : U;
+            }
+        }
+        for (int u = gwarp; u < U; u += gwarps) {
+            const unsigned long long my = __ldcg(&B.ukey[u]);
+            int below = 0;
+#pragma unroll 4
+            for (int v = lane; v < U; v += 32) below += (__ldcg(&B.ukey[v]) < my) ? 1 : 0;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) below += __shfl_xor_sync(0xffffffffu, below, o);
+            if (lane == 0) {
+                const int s = __ldcg(&B.uslot[u]);
+                const int c = __ldcg(&B.hcnt[s]);
+                if (c > VGC_VCAP) atomicOr(&ctl[1], 2u);
+                B.hoff[s] = (int)atomicAdd(&ctl[3], (unsigned int)c);
+                B.urank[u] = below;
+            }
+        }
+        vgc_barrier(&ctl[0], 2u * G);
+        bail = *reinterpret_cast<volatile unsigned int*>(&ctl[1]);
+    }
+    if (bail) {
+        // declined: leave the table clean for the next launch and report an empty result with the bail mark
+        for (int s = gtid; s < VGC_T; s += gthreads) { B.hkey[s] = VGC_EMPTY; B.hcnt[s] = 0; }
+        if (blockIdx.x == 0 && tid == 0) {
+            VgParams p;
+            p.inv_leaf = inv_leaf;
+            for (int k = 0; k < 3; ++k) { p.min_b[k] = 0; p.div_b[k] = 1; p.mul[k] = 1; }
+            p.overflow = 0; p.n_finite = 0; p.bail = 1;
+            *pp = p;
+            *count_out = 0;
+        }
+        return;
+    }
+
+    // ---- phase 3: group the point indices by voxel
+    for (int i = gtid; i < n; i += gthreads) {
+        const int s = __ldcg(&B.pslot[i]);
+        if (s >= 0) B.members[__ldcg(&B.hoff[s]) + __ldcg(&B.ppos[i])] = i;
+    }
+    vgc_barrier(&ctl[0], 3u * G);
+
+    // ---- phase 4: one warp per voxel — members in ascending original index, sequential fp32 sums
+    constexpr int NF = STRIDE == 48 ? 8 : 4;
+    for (int u = gwarp; u < U; u += gwarps) {
+        const int s = __ldcg(&B.uslot[u]);
+        const int c = __ldcg(&B.hcnt[s]);
+        const int off = __ldcg(&B.hoff[s]);
+        const int o = __ldcg(&B.urank[u]);
+        // order by counting (indices are distinct)
+        for (int j = lane; j < c; j += 32) {
+            const int m = __ldcg(&B.members[off + j]);
+            int below = 0;
+            for (int k = 0; k < c; ++k) below += (__ldcg(&B.members[off + k]) < m) ? 1 : 0;
+            S.sidx[warp][below] = m;
+        }
+        __syncwarp();
+        float acc = 0.f;       // lane f < NF owns field f
+        for (int base = 0; base < c; base += 32) {
+            const int j = base + lane;
+            if (j < c) {
+                const unsigned char* src = pts + (size_t)S.sidx[warp][j] * STRIDE;
+                const float4 A = *reinterpret_cast<const float4*>(src);
+                const float4 Bv = *reinterpret_cast<const float4*>(src + 16);
+                float* st = S.stage[warp][lane];
+                st[0] = A.x; st[1] = A.y; st[2] = A.z;
+                if (STRIDE == 48) {
+                    const float4 Cv = *reinterpret_cast<const float4*>(src + 32);
+                    st[3] = Bv.x; st[4] = Bv.y; st[5] = Bv.z; st[6] = Cv.x; st[7] = Cv.y;
+                } else {
+                    st[3] = Bv.x;
+                }
+            }
+            __syncwarp();
+            if (lane < NF) {
+                const int m = min(32, c - base);
+                for (int k = 0; k < m; ++k) acc += S.stage[warp][k][lane];
+            }
+            __syncwarp();
+        }
+        float f[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) f[k] = __shfl_sync(0xffffffffu, acc, k);
+        if (lane == 0) {
+            const float fc = (float)c;
+            const float sx = f[0], sy = f[1], sz = f[2];
+            unsigned char* dst = out + (size_t)o * STRIDE;
+            *reinterpret_cast<float4*>(dst) = make_float4(sx / fc, sy / fc, sz / fc, 1.0f);
+            if (feats_out) feats_out[o] = make_float4(sx / fc, sy / fc, sz / fc, __int_as_float(o));
+            if (STRIDE == 48) {
+                float snx = f[3], sny = f[4], snz = f[5];
+                const float si = f[6], sc = f[7];
+                float n2 = snx * snx + sny * sny + snz * snz;
+                if (n2 > 0.0f) { float nn = sqrtf(n2); snx = snx / nn; sny = sny / nn; snz = snz / nn; }
+                *reinterpret_cast<float4*>(dst + 16) = make_float4(snx, sny, snz, 0.0f);
+                *reinterpret_cast<float4*>(dst + 32) = make_float4(si / fc, sc / fc, 0.0f, 0.0f);
+            } else {
+                const float si = f[3];
+                *reinterpret_cast<float4*>(dst + 16) = make_float4(si / fc, 0.0f, 0.0f, 0.0f);
+            }
+            B.hkey[s] = VGC_EMPTY;      // hand the slot back
+            B.hcnt[s] = 0;
+        }
+        __syncwarp();
+    }
+}
+
+// Returns LILIOM_OK after enqueueing the cooperative filter; the caller must look at VgParams::bail (vg_params)
+// after its next sync and fall back to voxelgrid_dev2 when it is set.  *used = false: not applicable, nothing enqueued.
+int voxelgrid_coop(liliom_ctx* c, const void* d_in, int n_max, const int* d_n, int stride, float leaf, void* d_out, int* d_count,
+                   float4* d_feats, bool* used) {
+    *used = false;
+    if ((stride != 48 && stride != 32) || n_max <= 0 || n_max > VGC_NCAP || getenv("LILIOM_NO_VG_COOP")) return LILIOM_OK;
+    const int grid = c->sm_count;
+    VgCoopBufs B;
+    const size_t bytes = vgc_layout(B, nullptr, grid);
+    if (!c->vg_coop.p) {
+        LILI_CUDA(c, c->vg_coop.ensure(bytes));
+        vgc_layout(B, (unsigned char*)c->vg_coop.p, grid);
+        LILI_CUDA(c, cudaMemsetAsync(c->vg_coop.p, 0, c->vg_coop.cap, c->stream));
+        LILI_CUDA(c, cudaMemsetAsync(B.hkey, 0xff, (size_t)VGC_T * 8, c->stream));
+        c->vg_coop_calls = 0;
+    }
+    vgc_layout(B, (unsigned char*)c->vg_coop.p, grid);
+    LILI_CUDA(c, c->vg_params.ensure(sizeof(VgParams)));
+    const unsigned char* in = (const unsigned char*)d_in;
+    unsigned char* outp = (unsigned char*)d_out;
+    VgParams* pp = c->vg_params.as<VgParams>();
+    unsigned int call = c->vg_coop_calls;
+    void* kargs[] = {&in, &n_max, &d_n, &leaf, &B, &call, &pp, &outp, &d_count, &d_feats};
+    const void* fn = stride == 48 ? (const void*)k_vg_coop<48> : (const void*)k_vg_coop<32>;
+    LILI_CUDA(c, cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(VGC_THREADS), kargs, 0, c->stream));
+    LILI_TRY(launch_check(c, "k_vg_coop"));
+    c->vg_coop_calls++;
+    *used = true;
+    return LILIOM_OK;
 }
 
 int voxelgrid_dev2(liliom_ctx* c, const void* d_in, int n_max, const int* d_n, int stride, float leaf, void* d_out, int* d_count,

@@ -321,6 +321,37 @@ def test_odometry_call_and_sort_width_speculation(ctx48, oracle, world_small, s2
         _pose_close(pose, pose_o)
 
 
+def test_voxelgrid_cooperative_filter_paths(ctx48, ctx32, oracle, world_small, s2m_case):
+    """Clouds of <= 32768 points take the single-launch cooperative filter (hash + rank by counting, no sort).
+    It must give the sort chain's / oracle's bits, keep its hash table clean across calls, and hand inputs it
+    declines (a voxel with > 256 members, cell coordinates beyond 2^20, PCL's index overflow) to the sort chain."""
+    import liliom_b200 as L
+    F48 = ["x", "y", "z", "nx", "ny", "nz", "intensity", "curvature"]
+    rng = np.random.default_rng(5)
+    surf = s2m_case["surf"]
+    hdl = world_small["hdl"][:30000]
+    dense = np.zeros(3000, L.PT48)                      # 3000 points in a handful of voxels: > 256 members each
+    dense["x"] = rng.uniform(0.0, 0.8, 3000).astype(np.float32); dense["y"] = rng.uniform(0.0, 0.4, 3000).astype(np.float32)
+    dense["z"] = rng.uniform(0.0, 0.4, 3000).astype(np.float32); dense["intensity"] = rng.uniform(0, 255, 3000).astype(np.float32)
+    dense["nx"] = rng.normal(size=3000).astype(np.float32); dense["curvature"] = rng.uniform(0, 1, 3000).astype(np.float32)
+    farpt = surf[:2000].copy(); farpt["x"][::7] += 600000.0      # |floor(x / 0.4)| > 2^20 for some points
+    shifted = surf[:3000].copy(); shifted["x"] += np.float32(600000.0)   # small box, but cell coordinates beyond 2^20
+    sparse = np.zeros(5000, L.PT48)                     # every point its own voxel, with NaNs sprinkled in
+    sparse["x"] = rng.uniform(-80, 80, 5000).astype(np.float32); sparse["y"] = rng.uniform(-80, 80, 5000).astype(np.float32)
+    sparse["z"] = rng.uniform(-5, 5, 5000).astype(np.float32); sparse["x"][::97] = np.nan; sparse["z"][5::131] = np.inf
+    for rep in range(3):                                # alternate inputs: rotating control slots, table hand-back
+        for cloud, leaf in ((surf, 0.4), (dense, 0.4), (sparse, 0.4), (farpt, 0.4), (shifted, 0.4), (surf, 0.2), (dense, 0.05)):
+            _fields_equal(ctx48.voxelgrid(cloud, leaf), oracle.voxelgrid(cloud, leaf), F48)
+        _fields_equal(ctx32.voxelgrid(hdl, 0.6), oracle.voxelgrid(hdl, 0.6), ["x", "y", "z", "intensity"])
+    # the odometry entry point: declined inputs are redone transparently, then the next call is cooperative again
+    for cloud in (surf, np.concatenate([surf, dense]), farpt, surf):
+        ds_o = oracle.voxelgrid(cloud, 0.4)
+        rc, pose_o, _ = oracle.scan_to_map_gn(s2m_case["tree"], ds_o, world_small["guess"], 3)
+        pose, st, ds = ctx48.odometry(cloud, world_small["guess"], 3, mode=1)
+        _fields_equal(ds, ds_o, F48)
+        _pose_close(pose, pose_o)
+
+
 def test_backend_reflectivity_weighted_planes(oracle, world_small, s2m_case):
     """Horizon BackendFusion variant (L/src/BackendFusion.cpp:1601-1681): reflectivity-weighted plane rows."""
     import liliom_b200 as L
