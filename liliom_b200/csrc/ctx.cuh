@@ -89,6 +89,8 @@ struct liliom_ctx {
     bool vg_bail = false;        // ... the cooperative filter declined (valid after the sync)
     unsigned int vg_coop_calls = 0;   // launches of k_vg_coop so far (selects the rotating control slot)
     lili::DevBuf vg_coop;        // hash table + scratch of the cooperative filter
+    lili::DevBuf hz_ctl;         // barrier words + per-block counts of the cooperative Horizon extractor
+    unsigned int hz_coop_calls = 0;
     long long vg_ncells = 0;     // voxel-box cell count of that VoxelGrid, valid after the sync
     lili::DevBuf raw_scan;       // resident raw sweep (liliom_upload_scan)
     int n_raw_scan = 0;

@@ -24,20 +24,20 @@ constexpr int HZ_EMPTY = INT_MAX;
 
 struct Pt48 { float4 a, b, c; };  // {x,y,z,1} {nx,ny,nz,0} {intensity,curvature,0,0}
 
+__device__ __forceinline__ int hz_keep(const Pt48* __restrict__ pts, int i) {
+    float4 a = pts[i].a;
+    float inten = pts[i].c.x;
+    const float thres = 0.1f;
+    bool fin = isfinite(a.x) && isfinite(a.y) && isfinite(a.z);
+    bool close = (a.x * a.x + a.y * a.y + a.z * a.z) < thres * thres;
+    int scan_id = (int)inten;
+    return fin && !close && scan_id >= 0;
+}
+
 __global__ void k_hz_flags(const Pt48* __restrict__ pts, int n, int* __restrict__ flags) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i > n) return;
-    int f = 0;
-    if (i < n) {
-        float4 a = pts[i].a;
-        float inten = pts[i].c.x;
-        const float thres = 0.1f;
-        bool fin = isfinite(a.x) && isfinite(a.y) && isfinite(a.z);
-        bool close = (a.x * a.x + a.y * a.y + a.z * a.z) < thres * thres;
-        int scan_id = (int)inten;
-        f = fin && !close && scan_id >= 0;
-    }
-    flags[i] = f;
+    flags[i] = i < n ? hz_keep(pts, i) : 0;
 }
 
 __global__ void k_hz_fill(int* __restrict__ mat, int n, int v) {
@@ -45,10 +45,9 @@ __global__ void k_hz_fill(int* __restrict__ mat, int n, int v) {
     if (i < n) mat[i] = v;
 }
 
-__global__ void k_hz_deskew_bin(const Pt48* __restrict__ pts, int n, const int* __restrict__ flags, const int* __restrict__ cidx,
-                                Q4 q_imu, Pt48* __restrict__ cut, int* __restrict__ mat) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n || !flags[i]) return;
+// one kept point: undistort, write it at position ci of the cutted cloud, claim its (line, column) cell
+__device__ __forceinline__ void hz_deskew_bin_point(const Pt48* __restrict__ pts, int i, int ci, const Q4& q_imu, Pt48* __restrict__ cut,
+                                                    int* __restrict__ mat) {
     const float4 a = pts[i].a;
     const float intensity = pts[i].c.x, curvature = pts[i].c.y;
     const int scan_id = (int)intensity;
@@ -60,7 +59,6 @@ __global__ void k_hz_deskew_bin(const Pt48* __restrict__ pts, int n, const int* 
     Q4 q_si = qslerp_x(Q4{1, 0, 0, 0}, ratio_i, q_imu);
     D3 ps = qrot_x(q_si, D3{(double)a.x, (double)a.y, (double)a.z});
     const float ux = (float)ps.x, uy = (float)ps.y, uz = (float)ps.z;
-    const int ci = cidx[i];
     Pt48 o;
     o.a = make_float4(ux, uy, uz, 1.0f);
     o.b = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -73,6 +71,13 @@ __global__ void k_hz_deskew_bin(const Pt48* __restrict__ pts, int n, const int* 
     if (col >= HZ_COLS || col < 0) return;
     if (scan_id >= HZ_LINES) return;   // the reference indexes mat[] out of bounds here (UB); guarded
     atomicMin(&mat[scan_id * HZ_COLS + col], ci);                                                // :265-267 first writer wins
+}
+
+__global__ void k_hz_deskew_bin(const Pt48* __restrict__ pts, int n, const int* __restrict__ flags, const int* __restrict__ cidx,
+                                Q4 q_imu, Pt48* __restrict__ cut, int* __restrict__ mat) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || !flags[i]) return;
+    hz_deskew_bin_point(pts, i, cidx[i], q_imu, cut, mat);
 }
 
 struct HzCell { float x, y, z, curv, inten, depth; };
@@ -98,23 +103,19 @@ struct HzPatchSmem {
     int    ns, ne, num, nedge;
 };
 
-__global__ void __launch_bounds__(HZ_WARPS * 32) k_hz_patch(const Pt48* __restrict__ cut, const int* __restrict__ mat,
-                                                           double surf_thres, double edge_thres,
-                                                           Pt48* __restrict__ stage_surf, Pt48* __restrict__ stage_edge,
-                                                           int* __restrict__ counts) {
-    __shared__ HzPatchSmem sm[HZ_WARPS];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int patch = blockIdx.x * HZ_WARPS + warp;
-    if (patch >= HZ_PATCHES) return;
+// Evaluates one patch with one warp: fills P (window, lists, normals, out_s/out_e, ns/ne).
+template <bool COHERENT>
+__device__ __forceinline__ void hz_patch_eval(HzPatchSmem& P, const Pt48* __restrict__ cut, const int* __restrict__ mat, int patch, int lane,
+                                              double surf_thres, double edge_thres) {
     const int i0 = 5 + 6 * patch;
-    HzPatchSmem& P = sm[warp];
     HzCell* W = P.win;
     for (int e = lane; e < HZ_LINES * HZ_WIN; e += 32) {
         int k = e / HZ_WIN, cc = e % HZ_WIN;
-        int idx = mat[k * HZ_COLS + (i0 - 4 + cc)];
+        // COHERENT: mat / cut were produced earlier in the same (cooperative) launch by other SMs -> bypass L1
+        int idx = COHERENT ? __ldcg(&mat[k * HZ_COLS + (i0 - 4 + cc)]) : mat[k * HZ_COLS + (i0 - 4 + cc)];
         HzCell h{0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         if (idx != HZ_EMPTY) {
-            float4 a = cut[idx].a, c = cut[idx].c;
+            float4 a = COHERENT ? __ldcg(&cut[idx].a) : cut[idx].a, c = COHERENT ? __ldcg(&cut[idx].c) : cut[idx].c;
             h.x = a.x; h.y = a.y; h.z = a.z; h.inten = c.x; h.curv = c.y;
             h.depth = sqrtf(a.x * a.x + a.y * a.y + a.z * a.z);                                   // getDepth :99-102
         }
@@ -229,15 +230,19 @@ __global__ void __launch_bounds__(HZ_WARPS * 32) k_hz_patch(const Pt48* __restri
         }
         __syncwarp();
     }
+}
+
+// Writes the patch's selected cells (P.out_s / P.out_e) as published points starting at dst_s / dst_e.
+__device__ __forceinline__ void hz_patch_emit(const HzPatchSmem& P, int lane, Pt48* __restrict__ dst_s, Pt48* __restrict__ dst_e) {
+    const HzCell* W = P.win;
     const int ns = P.ns, ne = P.ne;
-    if (lane == 0) { counts[patch] = ns; counts[HZ_PATCHES + 1 + patch] = ne; }
     for (int s2 = lane; s2 < ns; s2 += 32) {
         const HzCell& h = W[P.out_s[s2]];
         Pt48 o;
         o.a = make_float4(h.x, h.y, h.z, 1.0f);
         o.b = make_float4(P.nrm[0], P.nrm[1], P.nrm[2], 0.f);
         o.c = make_float4(h.inten, h.curv, 0.f, 0.f);
-        stage_surf[patch * 36 + s2] = o;
+        dst_s[s2] = o;
     }
     if (lane < ne) {
         const HzCell& h = W[P.out_e[lane]];
@@ -245,8 +250,22 @@ __global__ void __launch_bounds__(HZ_WARPS * 32) k_hz_patch(const Pt48* __restri
         o.a = make_float4(h.x, h.y, h.z, 1.0f);
         o.b = make_float4(P.nrm[3], P.nrm[4], P.nrm[5], 0.f);
         o.c = make_float4(h.inten, h.curv, 0.f, 0.f);
-        stage_edge[patch * 6 + lane] = o;
+        dst_e[lane] = o;
     }
+}
+
+__global__ void __launch_bounds__(HZ_WARPS * 32) k_hz_patch(const Pt48* __restrict__ cut, const int* __restrict__ mat,
+                                                           double surf_thres, double edge_thres,
+                                                           Pt48* __restrict__ stage_surf, Pt48* __restrict__ stage_edge,
+                                                           int* __restrict__ counts) {
+    __shared__ HzPatchSmem sm[HZ_WARPS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int patch = blockIdx.x * HZ_WARPS + warp;
+    if (patch >= HZ_PATCHES) return;
+    HzPatchSmem& P = sm[warp];
+    hz_patch_eval<false>(P, cut, mat, patch, lane, surf_thres, edge_thres);
+    if (lane == 0) { counts[patch] = P.ns; counts[HZ_PATCHES + 1 + patch] = P.ne; }
+    hz_patch_emit(P, lane, stage_surf + patch * 36, stage_edge + patch * 6);
 }
 
 // counts layout: [0..663] surf counts, [664] spare, [665..1328] edge counts, [1329] spare.
@@ -289,6 +308,98 @@ __global__ void k_hz_emit(const Pt48* __restrict__ stage_surf, const Pt48* __res
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// The whole extractor as ONE cooperative launch (8 launches + a CUB scan otherwise, most of their ~75 us
+// launch latency): three grid barriers separate the four dependent stages.
+//   A  keep-flags counted per block (block b owns the contiguous points [b*chunk, (b+1)*chunk)); mat := EMPTY
+//   B  block prefix = sum of the preceding blocks' counts -> stable compaction index; de-skew, cutted cloud,
+//      first-writer-wins cell claims (atomicMin), exactly as k_hz_deskew_bin
+//   C  one warp per patch (hz_patch_eval, L1 bypassed for data written in B); per-patch counts published
+//   D  every warp sums the counts of the patches before its own (patch-major order of the reference) and
+//      writes its selected cells straight from shared memory — no staging copy
+// Same device functions as the multi-launch chain, so the bits are the chain's.
+// ---------------------------------------------------------------------------------------
+constexpr int HZC_THREADS = 256;
+constexpr int HZC_WARPS = HZC_THREADS / 32;
+
+__device__ __forceinline__ void hz_grid_barrier(unsigned int* bar, unsigned int target) {
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        atomicAdd(bar, 1u);
+        while ((int)(*reinterpret_cast<volatile unsigned int*>(bar) - target) < 0) { }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(HZC_THREADS) k_hz_coop(const Pt48* __restrict__ pts, int n, Q4 q_imu, double surf_thres, double edge_thres,
+                                                         Pt48* __restrict__ cut, int* __restrict__ mat, int* __restrict__ blockcnt,
+                                                         int* __restrict__ counts, int* __restrict__ totals, int* __restrict__ ncut_out,
+                                                         Pt48* __restrict__ surf, Pt48* __restrict__ edge, unsigned int* __restrict__ ctl,
+                                                         unsigned int call) {
+    __shared__ HzPatchSmem sm[HZC_WARPS];
+    __shared__ int wsum[HZC_WARPS];
+    __shared__ int s_bpre;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int G = gridDim.x, b = blockIdx.x;
+    unsigned int* bar = ctl + (call & 3u);
+    if (b == 0 && tid == 0) ctl[(call + 1u) & 3u] = 0u;      // the next launch's barrier word
+    // ---- A
+    for (int e = b * HZC_THREADS + tid; e < HZ_LINES * HZ_COLS; e += G * HZC_THREADS) mat[e] = HZ_EMPTY;
+    const int chunk = (n + G - 1) / G;
+    const int ipt = (chunk + HZC_THREADS - 1) / HZC_THREADS;
+    const int j0 = tid * ipt, j1 = min(j0 + ipt, chunk);
+    int mine = 0;
+    for (int j = j0; j < j1; ++j) {
+        const int i = b * chunk + j;
+        if (i < n) mine += hz_keep(pts, i);
+    }
+    int inc = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    int tpre = inc - mine;
+    for (int w = 0; w < warp; ++w) tpre += wsum[w];
+    if (tid == HZC_THREADS - 1) blockcnt[b] = tpre + mine;
+    hz_grid_barrier(bar, (unsigned int)G);
+    // ---- B
+    if (warp == 0) {
+        int pre = 0, tot = 0;
+        for (int k = lane; k < G; k += 32) { const int v = __ldcg(&blockcnt[k]); tot += v; if (k < b) pre += v; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { pre += __shfl_xor_sync(0xffffffffu, pre, o); tot += __shfl_xor_sync(0xffffffffu, tot, o); }
+        if (lane == 0) { s_bpre = pre; if (b == 0) *ncut_out = tot; }
+    }
+    __syncthreads();
+    {
+        int ci = s_bpre + tpre;
+        for (int j = j0; j < j1; ++j) {
+            const int i = b * chunk + j;
+            if (i < n && hz_keep(pts, i)) { hz_deskew_bin_point(pts, i, ci, q_imu, cut, mat); ++ci; }
+        }
+    }
+    hz_grid_barrier(bar, 2u * (unsigned int)G);
+    // ---- C  (host guarantees G * HZC_WARPS >= HZ_PATCHES: one patch per warp)
+    const int patch = b * HZC_WARPS + warp;
+    HzPatchSmem& P = sm[warp];
+    if (patch < HZ_PATCHES) {
+        hz_patch_eval<true>(P, cut, mat, patch, lane, surf_thres, edge_thres);
+        if (lane == 0) { counts[patch] = P.ns; counts[HZ_PATCHES + 1 + patch] = P.ne; }
+    }
+    hz_grid_barrier(bar, 3u * (unsigned int)G);
+    // ---- D
+    if (patch < HZ_PATCHES) {
+        int os = 0, oe = 0;
+        for (int k = lane; k < patch; k += 32) { os += __ldcg(&counts[k]); oe += __ldcg(&counts[HZ_PATCHES + 1 + k]); }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { os += __shfl_xor_sync(0xffffffffu, os, o); oe += __shfl_xor_sync(0xffffffffu, oe, o); }
+        hz_patch_emit(P, lane, surf + os, edge + oe);
+        if (patch == HZ_PATCHES - 1 && lane == 0) { totals[0] = os + P.ns; totals[1] = oe + P.ne; }
+    }
+}
+
 // raw points must already be in c->raw (n x 48 B).  Leaves cut/surf/edge on the device and the
 // three counts in pinned host memory (returned through the pointers after a stream sync).
 int horizon_extract_dev(liliom_ctx* c, int n, const double q_imu[4], int* n_surf, int* n_edge, int* n_cut, bool sync_counts) {
@@ -311,31 +422,52 @@ int horizon_extract_dev(liliom_ctx* c, int n, const double q_imu[4], int* n_surf
     int* counts = c->hz_counts.as<int>();
     int* offs = counts + 2 * (HZ_PATCHES + 1);
     int* totals = counts + 4 * (HZ_PATCHES + 1);
-    k_hz_flags<<<cdiv(n + 1, 256), 256, 0, c->stream>>>(raw, n, flags);
-    LILI_TRY(launch_check(c, "k_hz_flags"));
-    LILI_TRY(exclusive_scan_i32(c, flags, cidx, n));
-    k_hz_fill<<<cdiv(HZ_LINES * HZ_COLS, 256), 256, 0, c->stream>>>(mat, HZ_LINES * HZ_COLS, HZ_EMPTY);
-    LILI_TRY(launch_check(c, "k_hz_fill"));
-    if (n > 0) {
-        k_hz_deskew_bin<<<cdiv(n, 128), 128, 0, c->stream>>>(raw, n, flags, cidx, q, c->cut.as<Pt48>(), mat);
-        LILI_TRY(launch_check(c, "k_hz_deskew_bin"));
-        if (c->early_cut_dst && c->early_cut_cap > 0) {
-            const size_t cnt = (size_t)min(n, c->early_cut_cap);
-            LILI_CUDA(c, cudaEventRecord(c->ev_ready, c->stream));
-            LILI_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_ready, 0));
-            LILI_CUDA(c, cudaMemcpyAsync(c->early_cut_dst, c->cut.p, cnt * sizeof(Pt48), cudaMemcpyDeviceToHost, c->copy_stream));
-            LILI_CUDA(c, cudaEventRecord(c->ev_copied, c->copy_stream));
-            c->early_cut_issued = true;
+    const bool coop = c->sm_count * HZC_WARPS >= HZ_PATCHES && n > 0 && !getenv("LILIOM_NO_HZ_COOP");
+    if (coop) {
+        // one cooperative launch; scratch: per-block counts behind the patch counts, barrier words in their own buffer
+        if (!c->hz_ctl.p) {
+            LILI_CUDA(c, c->hz_ctl.ensure(64 + (size_t)c->sm_count * sizeof(int)));
+            LILI_CUDA(c, cudaMemsetAsync(c->hz_ctl.p, 0, c->hz_ctl.cap, c->stream));
+            c->hz_coop_calls = 0;
         }
+        unsigned int* ctl = c->hz_ctl.as<unsigned int>();
+        int* blockcnt = reinterpret_cast<int*>(c->hz_ctl.as<unsigned char>() + 64);
+        int* ncut_out = cidx + n;
+        const Pt48* raw_c = raw;
+        Pt48* cutp = c->cut.as<Pt48>(); Pt48* surfp = c->surf.as<Pt48>(); Pt48* edgep = c->edge.as<Pt48>();
+        double st = c->prm.surf_thres, et = c->prm.edge_thres;
+        unsigned int call = c->hz_coop_calls;
+        void* kargs[] = {&raw_c, &n, &q, &st, &et, &cutp, &mat, &blockcnt, &counts, &totals, &ncut_out, &surfp, &edgep, &ctl, &call};
+        LILI_CUDA(c, cudaLaunchCooperativeKernel((const void*)k_hz_coop, dim3(c->sm_count), dim3(HZC_THREADS), kargs, 0, c->stream));
+        LILI_TRY(launch_check(c, "k_hz_coop"));
+        c->hz_coop_calls++;
+    } else {
+        k_hz_flags<<<cdiv(n + 1, 256), 256, 0, c->stream>>>(raw, n, flags);
+        LILI_TRY(launch_check(c, "k_hz_flags"));
+        LILI_TRY(exclusive_scan_i32(c, flags, cidx, n));
+        k_hz_fill<<<cdiv(HZ_LINES * HZ_COLS, 256), 256, 0, c->stream>>>(mat, HZ_LINES * HZ_COLS, HZ_EMPTY);
+        LILI_TRY(launch_check(c, "k_hz_fill"));
+        if (n > 0) {
+            k_hz_deskew_bin<<<cdiv(n, 128), 128, 0, c->stream>>>(raw, n, flags, cidx, q, c->cut.as<Pt48>(), mat);
+            LILI_TRY(launch_check(c, "k_hz_deskew_bin"));
+            if (c->early_cut_dst && c->early_cut_cap > 0) {
+                const size_t cnt = (size_t)min(n, c->early_cut_cap);
+                LILI_CUDA(c, cudaEventRecord(c->ev_ready, c->stream));
+                LILI_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_ready, 0));
+                LILI_CUDA(c, cudaMemcpyAsync(c->early_cut_dst, c->cut.p, cnt * sizeof(Pt48), cudaMemcpyDeviceToHost, c->copy_stream));
+                LILI_CUDA(c, cudaEventRecord(c->ev_copied, c->copy_stream));
+                c->early_cut_issued = true;
+            }
+        }
+        k_hz_patch<<<cdiv(HZ_PATCHES, HZ_WARPS), HZ_WARPS * 32, 0, c->stream>>>(c->cut.as<Pt48>(), mat, c->prm.surf_thres, c->prm.edge_thres,
+                                                                                c->hz_stage_surf.as<Pt48>(), c->hz_stage_edge.as<Pt48>(), counts);
+        LILI_TRY(launch_check(c, "k_hz_patch"));
+        k_hz_offsets<<<1, 1024, 0, c->stream>>>(counts, offs, totals);
+        LILI_TRY(launch_check(c, "k_hz_offsets"));
+        k_hz_emit<<<HZ_PATCHES, 64, 0, c->stream>>>(c->hz_stage_surf.as<Pt48>(), c->hz_stage_edge.as<Pt48>(), counts, offs,
+                                                    c->surf.as<Pt48>(), c->edge.as<Pt48>());
+        LILI_TRY(launch_check(c, "k_hz_emit"));
     }
-    k_hz_patch<<<cdiv(HZ_PATCHES, HZ_WARPS), HZ_WARPS * 32, 0, c->stream>>>(c->cut.as<Pt48>(), mat, c->prm.surf_thres, c->prm.edge_thres,
-                                                                            c->hz_stage_surf.as<Pt48>(), c->hz_stage_edge.as<Pt48>(), counts);
-    LILI_TRY(launch_check(c, "k_hz_patch"));
-    k_hz_offsets<<<1, 1024, 0, c->stream>>>(counts, offs, totals);
-    LILI_TRY(launch_check(c, "k_hz_offsets"));
-    k_hz_emit<<<HZ_PATCHES, 64, 0, c->stream>>>(c->hz_stage_surf.as<Pt48>(), c->hz_stage_edge.as<Pt48>(), counts, offs,
-                                                c->surf.as<Pt48>(), c->edge.as<Pt48>());
-    LILI_TRY(launch_check(c, "k_hz_emit"));
     c->d_nsurf = totals;
     c->n_surf_max = min(n, HZ_PATCHES * 36);
     if (!sync_counts) {          // resident pipeline: the counts stay on the device, no host round trip

@@ -178,6 +178,22 @@ def test_horizon_extract_edge_cases(ctx48, oracle, world_small):
         _fields_equal(a, b, F)
 
 
+def test_horizon_extract_single_launch_shapes(ctx48, oracle, world_small):
+    """The extractor runs as one cooperative launch; block b owns a contiguous slice of the sweep.  Sweeps longer than
+    grid x 256 points give every thread several points (the stable compaction order must survive), tiny sweeps leave
+    most blocks empty, and back-to-back calls alternate the barrier words."""
+    F = ["x", "y", "z", "nx", "ny", "nz", "intensity", "curvature"]
+    base = world_small["hz"]
+    rng = np.random.default_rng(11)
+    big = np.concatenate([base, base, base, base])       # ~4x the returns: later duplicates lose every cell claim
+    big["x"][len(base):] += rng.normal(0, 0.01, len(big) - len(base)).astype(np.float32)
+    big["x"][3::41] = np.nan
+    q = world_small["q_hz"]
+    for pts in (big, base[:700], base[:1], big[:50001], base):
+        for a, b in zip(ctx48.extract_horizon(pts, q), oracle.extract_horizon(pts, q)):
+            _fields_equal(a, b, F)
+
+
 @pytest.mark.parametrize("ds_rate", [1, 4])
 def test_rot_extract_bit_exact(oracle, world_small, ds_rate):
     import liliom_b200 as L
