@@ -217,3 +217,32 @@ def test_golden_scan_to_map(oracle):
     rc, pose, st = oracle.scan_to_map_ceres(tree, g["feats"], g["pose0"], 2, 15)
     np.testing.assert_allclose(pose, g["pose_ceres"], rtol=0, atol=1e-12)
     assert [s.lm_iters for s in st] == list(g["ceres_lm_iters"])
+
+
+def test_kdtree_matches_real_flann_kdtree_single(oracle, world_small):
+    """Third-party pin: OpenCV vendors the FLANN sources (cv::flann), including the very index class PCL's KdTreeFLANN
+    instantiates — KDTreeSingleIndex (algorithm 4), leaf_max_size 15 by default in PCL, SearchParams(checks=-1, eps=0,
+    sorted=true) (L/src/LidarOdometry.cpp:490,360 through pcl::KdTreeFLANN).  The oracle's from-knowledge kd-tree must
+    return the same neighbours in the same order with bit-identical fp32 squared distances, except where FLANN's own
+    tie order (equal distances) is unspecified."""
+    cv2 = pytest.importorskip("cv2")
+    if not hasattr(cv2, "flann_Index"):
+        pytest.skip("this OpenCV build has no flann module")
+    m = world_small["map"][:60000]
+    xyz = np.ascontiguousarray(m[:, :3], dtype=np.float32)
+    rng = np.random.default_rng(11)
+    q = m[rng.integers(0, len(m), 3000)].copy()
+    q[:, :3] += rng.normal(0, 0.35, (3000, 3)).astype(np.float32)
+    index = cv2.flann_Index(xyz, dict(algorithm=4, leaf_max_size=15, reorder=True))       # FLANN_INDEX_KDTREE_SINGLE
+    fi, fd = index.knnSearch(np.ascontiguousarray(q[:, :3]), 5, params=dict(checks=-1, eps=0.0, sorted=True))
+    idx, sqd = oracle.KdTree(m).knn5(q)
+    # distances: FLANN's L2 functor accumulates (dx*dx + dy*dy) + dz*dz in fp32 — same bits as the oracle
+    assert np.array_equal(sqd.view(np.uint32), fd.astype(np.float32).view(np.uint32))
+    same = (idx == fi)
+    tie = np.zeros_like(same)
+    tie[:, 1:] |= sqd[:, 1:] == sqd[:, :-1]
+    tie[:, :-1] |= sqd[:, :-1] == sqd[:, 1:]
+    assert (same | tie).all()
+    assert same.mean() > 0.999
+    # the 5th-neighbour gate (:365) therefore decides identically
+    assert np.array_equal(sqd[:, 4] < 1.0, fd[:, 4] < 1.0)
