@@ -190,6 +190,36 @@ int liliom_correspond_surf_refl(liliom_ctx* c, const void* feats48, int n, const
                                 double surf_dist_thres, double w_gate, double lidar_const, double reflect_thres,
                                 unsigned char* valid, float* plane, double* score);
 
+/* ---- the LiDAR residual blocks of ONE window keyframe, reduced on the device ----
+ * L/src/BackendFusion.cpp:919-979 adds, per keyframe of the sliding window, one LidarEdgeFactor
+ * (L/include/factors/LidarKeyframeFactor.h:12-62) per edge correspondence and one LidarPlaneNormFactor (:65-108) per
+ * surf correspondence on the parameter blocks (tmpTrans, tmpQuat) under ceres::CauchyLoss(1.0) (:845) and
+ * QuaternionParameterization; the same factors are evaluated again for the marginalisation (:1087-1148).
+ * These calls evaluate those rows at pose7_body = [qw,qx,qy,qz,tx,ty,tz] of the keyframe on the correspondences the
+ * preceding liliom_correspond_edge / liliom_correspond_surf(_refl) call left resident in `c`, and return the keyframe's
+ * normal-equation block: out29 = upper triangle of J^T J (21, row-major) | J^T r (6) | cost = 1/2 sum rho | count, with
+ * the robustified rows sqrt(rho')[dr/dt, dr/dq * PlusJacobian] — tangent order [t(3), rot(3)] (the parameter-block order).
+ * They can be called repeatedly at different poses (LM iterations on frozen correspondences).
+ * edge: s_weight = the factor's `s` (pt.intensity = lidar_const, :1581); the extrinsics are not applied (:38).
+ * surf: point_w = q * (q_lb^-1 * (p - t_lb)) + t (:87-88), residual score*(n~.point_w + d~). */
+int liliom_backend_edge_block(liliom_ctx* c, const double pose7_body[7], double s_weight, double cauchy_b, double out29[29]);
+int liliom_backend_surf_block(liliom_ctx* c, const double pose7_body[7], const double q_lb_wxyz[4], const double t_lb[3],
+                              double cauchy_b, double out29[29]);
+
+/* ---- wire format on the sensor side — FormatConvert's livoxLidarHandler on the device ----
+ * L/src/FormatConvert.cpp:11-24: livox_ros_driver::CustomPoint {uint32 offset_time; float x,y,z; uint8 reflectivity,
+ * tag, line} -> pcl::PointXYZINormal with intensity = line + 0.1*float(offset_time/(float)time_end) (:19-20),
+ * curvature = 0.1*reflectivity (:21), time_end = points.back().offset_time (:13).
+ * stride = 20 (the C++ message struct in memory) or 19 (serialised wire bytes).
+ * liliom_convert_livox leaves the converted sweep resident (as liliom_upload_scan does) and optionally downloads it;
+ * liliom_extract_horizon_livox = convert + liliom_extract_horizon without the 48-byte host cloud in between
+ * (H2D traffic 19-20 B/point instead of 48). */
+int liliom_convert_livox(liliom_ctx* c, const void* custom_pts, int n, int stride, liliom_pt48* out, int cap);
+int liliom_extract_horizon_livox(liliom_ctx* c, const void* custom_pts, int n, int stride, const double q_imu_wxyz[4],
+                                 liliom_pt48* surf_out, int surf_cap, int* n_surf,
+                                 liliom_pt48* edge_out, int edge_cap, int* n_edge,
+                                 liliom_pt48* cutted_out, int cut_cap, int* n_cut);
+
 /* ===================== multi-GPU (one context per rank) ===================== */
 /* 128-byte NCCL unique id: rank 0 calls get, the launcher broadcasts it, every rank calls init.
  * After init, liliom_map_set_points shards the map by 16 m block hash (+halo) and every

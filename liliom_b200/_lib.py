@@ -19,7 +19,10 @@ PT48 = np.dtype([("x", "f4"), ("y", "f4"), ("z", "f4"), ("w", "f4"),
                  ("intensity", "f4"), ("curvature", "f4"), ("p0", "f4"), ("p1", "f4")])
 PT32 = np.dtype([("x", "f4"), ("y", "f4"), ("z", "f4"), ("w", "f4"),
                  ("intensity", "f4"), ("p0", "f4"), ("p1", "f4"), ("p2", "f4")])
-assert PT48.itemsize == 48 and PT32.itemsize == 32
+# livox_ros_driver::CustomPoint as laid out in the C++ message struct (20 bytes; the wire layout is the first 19)
+LIVOX20 = np.dtype([("offset_time", "<u4"), ("x", "<f4"), ("y", "<f4"), ("z", "<f4"),
+                    ("reflectivity", "u1"), ("tag", "u1"), ("line", "u1"), ("pad", "u1")])
+assert PT48.itemsize == 48 and PT32.itemsize == 32 and LIVOX20.itemsize == 20
 
 OK, E_ARG, E_CUDA, E_FEWMAP, E_CAPACITY, E_GRID, E_LINES, E_NCCL, E_NOMAP = 0, -1, -2, -3, -4, -5, -6, -7, -8
 MODE_CERES, MODE_GN = 0, 1
@@ -54,6 +57,7 @@ EXPORTS = [
     "liliom_get_counters", "liliom_set_kernel_timing", "liliom_upload_feats", "liliom_scan_to_map_resident",
     "liliom_odometry", "liliom_set_stream", "liliom_upload_scan", "liliom_extract_resident", "liliom_point_stride",
     "liliom_map_set_cloud", "liliom_correspond_surf_refl",
+    "liliom_backend_edge_block", "liliom_backend_surf_block", "liliom_convert_livox", "liliom_extract_horizon_livox",
 ]
 NODE_EXPORTS = ["liliom_pre_create", "liliom_pre_destroy", "liliom_pre_imu", "liliom_pre_cloud",
                 "liliom_lo_create", "liliom_lo_destroy", "liliom_lo_edge", "liliom_lo_surf", "liliom_lo_full", "liliom_lo_run"]
@@ -115,6 +119,10 @@ def lib() -> C.CDLL:
     L.liliom_point_stride.argtypes = [vp]
     L.liliom_map_set_cloud.argtypes = [vp, vp, C.c_int, C.c_int]
     L.liliom_correspond_surf_refl.argtypes = [vp, vp, C.c_int, dp, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, vp, vp, vp]
+    L.liliom_backend_edge_block.argtypes = [vp, dp, C.c_double, C.c_double, dp]
+    L.liliom_backend_surf_block.argtypes = [vp, dp, dp, dp, C.c_double, dp]
+    L.liliom_convert_livox.argtypes = [vp, vp, C.c_int, C.c_int, vp, C.c_int]
+    L.liliom_extract_horizon_livox.argtypes = [vp, vp, C.c_int, C.c_int, dp, vp, C.c_int, ip, vp, C.c_int, ip, vp, C.c_int, ip]
     L.liliom_pre_create.argtypes = [vp, C.c_int, dp]; L.liliom_pre_create.restype = vp
     L.liliom_pre_destroy.argtypes = [vp]; L.liliom_pre_destroy.restype = None
     L.liliom_pre_imu.argtypes = [vp, C.c_double, dp]; L.liliom_pre_imu.restype = None
@@ -344,6 +352,46 @@ class Context:
         self._check(lib().liliom_correspond_surf_refl(self._h, _ptr(f), n, _dptr(pose), kd_max_radius, surf_dist_thres, w_gate, lidar_const,
                                                       reflect_thres, _ptr(valid), _ptr(plane), _ptr(score)))
         return valid[:n], plane[:n], score[:n]
+
+    def backend_edge_block(self, pose7_body, s_weight: float, cauchy_b: float = 1.0):
+        """(f1) 29 scalars of the LidarEdgeFactor rows on the correspondences of the last correspond_edge call."""
+        out = np.zeros(29)
+        self._check(lib().liliom_backend_edge_block(self._h, _dptr(np.asarray(pose7_body, np.float64)), float(s_weight), float(cauchy_b), _dptr(out)))
+        return out
+
+    def backend_surf_block(self, pose7_body, q_lb=(1.0, 0.0, 0.0, 0.0), t_lb=(0.0, 0.0, 0.0), cauchy_b: float = 1.0):
+        """(f1) 29 scalars of the LidarPlaneNormFactor rows on the correspondences of the last correspond_surf* call."""
+        out = np.zeros(29)
+        self._check(lib().liliom_backend_surf_block(self._h, _dptr(np.asarray(pose7_body, np.float64)), _dptr(np.asarray(q_lb, np.float64)),
+                                                    _dptr(np.asarray(t_lb, np.float64)), float(cauchy_b), _dptr(out)))
+        return out
+
+    # ---- wire formats (f3) ----
+    @staticmethod
+    def _livox(custom_pts, stride):
+        a = np.ascontiguousarray(custom_pts)
+        if stride is None:
+            stride = a.dtype.itemsize
+            return a, len(a), stride
+        return a, a.size * a.dtype.itemsize // stride, stride
+
+    def convert_livox(self, custom_pts: np.ndarray, stride: int | None = None, download: bool = True):
+        a, n, stride = self._livox(custom_pts, stride)
+        out = np.zeros(max(n, 1), PT48) if download else None
+        self._check(lib().liliom_convert_livox(self._h, _ptr(a), n, stride, _ptr(out), len(out) if download else 0))
+        return out[:n] if download else n
+
+    def extract_horizon_livox(self, custom_pts: np.ndarray, q_imu, stride: int | None = None, out=None):
+        a, n, stride = self._livox(custom_pts, stride)
+        q = np.asarray(q_imu, dtype=np.float64)
+        if out is None:
+            surf = np.empty(max(n, 1), PT48); edge = np.empty(max(n, 1), PT48); cut = np.empty(max(n, 1), PT48)
+        else:
+            surf, edge, cut = out
+        ns, ne, nc = C.c_int(), C.c_int(), C.c_int()
+        self._check(lib().liliom_extract_horizon_livox(self._h, _ptr(a), n, stride, _dptr(q), _ptr(surf), len(surf), C.byref(ns),
+                                                       _ptr(edge), len(edge), C.byref(ne), _ptr(cut), len(cut), C.byref(nc)))
+        return surf[:ns.value], edge[:ne.value], cut[:nc.value]
 
     # ---- multi-GPU / instrumentation ----
     def comm_init(self, unique_id: bytes, nranks: int, rank: int):

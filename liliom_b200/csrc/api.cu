@@ -209,7 +209,7 @@ extern "C" void liliom_destroy(liliom_ctx* c) {
                       &c->vg_keys2, &c->vg_vals, &c->vg_vals2, &c->vg_flags, &c->vg_rank, &c->vg_params, &c->vg_out, &c->vg_minmax, &c->vg_count,
                       &c->cub_tmp, &c->vg_coop, &c->hz_ctl, &c->map_raw, &c->map_ds, &c->map_xyzw, &c->map_sorted, &c->cell_start, &c->grid_keys, &c->grid_keys2,
                       &c->grid_vals, &c->grid_vals2, &c->feats, &c->corr_valid, &c->corr_plane, &c->nn_idx, &c->nn_sqd, &c->pose_dev,
-                      &c->partials, &c->neq, &c->stats_dev, &c->counter, &c->lm_state, &c->raw_scan, &c->map_refl, &c->slots_buf};
+                      &c->partials, &c->neq, &c->stats_dev, &c->counter, &c->lm_state, &c->raw_scan, &c->map_refl, &c->slots_buf, &c->livox_in};
     for (DevBuf* b : bufs) b->release();
     for (auto& f : c->frames) f.buf.release();
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
@@ -222,14 +222,10 @@ extern "C" void liliom_destroy(liliom_ctx* c) {
 }
 
 // ===================== L1 =====================
-extern "C" int liliom_extract_horizon(liliom_ctx* c, const liliom_pt48* pts, int n, const double q_imu[4],
-                                      liliom_pt48* surf_out, int surf_cap, int* n_surf, liliom_pt48* edge_out, int edge_cap, int* n_edge,
-                                      liliom_pt48* cut_out, int cut_cap, int* n_cut) {
-    if (!c || n < 0 || (n > 0 && !pts) || !q_imu || !n_surf || !n_edge || !n_cut) return LILIOM_E_ARG;
-    if (c->prm.point_stride != 48) return LILIOM_E_ARG;
-    LILI_CUDA(c, cudaSetDevice(c->device));
-    LILI_CUDA(c, c->raw.ensure((size_t)(n > 0 ? n : 1) * 48));
-    if (n > 0) LILI_CUDA(c, cudaMemcpyAsync(c->raw.p, pts, (size_t)n * 48, cudaMemcpyHostToDevice, c->stream));
+// Shared tail of the Horizon entry points: c->raw holds n 48-byte points (upload already queued on the stream).
+static int extract_horizon_from_raw(liliom_ctx* c, int n, const double q_imu[4],
+                                    liliom_pt48* surf_out, int surf_cap, int* n_surf, liliom_pt48* edge_out, int edge_cap, int* n_edge,
+                                    liliom_pt48* cut_out, int cut_cap, int* n_cut) {
     int ns = 0, ne = 0, nc = 0;
     // The cutted cloud is complete after the de-skew kernel: its D2H runs on the copy stream under the patch kernels.
     // It is issued before the count is known, so min(n, cut_cap) slots are copied; slots past *n_cut are unspecified.
@@ -249,6 +245,68 @@ extern "C" int liliom_extract_horizon(liliom_ctx* c, const liliom_pt48* pts, int
     if (over) return LILIOM_E_CAPACITY;
     *n_surf = ns; *n_edge = ne; *n_cut = nc;
     return LILIOM_OK;
+}
+
+extern "C" int liliom_extract_horizon(liliom_ctx* c, const liliom_pt48* pts, int n, const double q_imu[4],
+                                      liliom_pt48* surf_out, int surf_cap, int* n_surf, liliom_pt48* edge_out, int edge_cap, int* n_edge,
+                                      liliom_pt48* cut_out, int cut_cap, int* n_cut) {
+    if (!c || n < 0 || (n > 0 && !pts) || !q_imu || !n_surf || !n_edge || !n_cut) return LILIOM_E_ARG;
+    if (c->prm.point_stride != 48) return LILIOM_E_ARG;
+    LILI_CUDA(c, cudaSetDevice(c->device));
+    LILI_CUDA(c, c->raw.ensure((size_t)(n > 0 ? n : 1) * 48));
+    if (n > 0) LILI_CUDA(c, cudaMemcpyAsync(c->raw.p, pts, (size_t)n * 48, cudaMemcpyHostToDevice, c->stream));
+    return extract_horizon_from_raw(c, n, q_imu, surf_out, surf_cap, n_surf, edge_out, edge_cap, n_edge, cut_out, cut_cap, n_cut);
+}
+
+// ---- (f3) FormatConvert on the device: livox_ros_driver::CustomPoint[] -> pcl::PointXYZINormal[] (L/src/FormatConvert.cpp:11-24)
+namespace lili {
+__global__ void k_livox_to_pt48(const unsigned char* __restrict__ in, int n, int stride, float4* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    auto rd32 = [](const unsigned char* p) { return (unsigned)p[0] | ((unsigned)p[1] << 8) | ((unsigned)p[2] << 16) | ((unsigned)p[3] << 24); };
+    const unsigned time_end = rd32(in + (size_t)(n - 1) * stride);                       // :13 points.back().offset_time
+    const unsigned char* p = in + (size_t)i * stride;
+    const unsigned off = rd32(p);
+    const float x = __uint_as_float(rd32(p + 4)), y = __uint_as_float(rd32(p + 8)), z = __uint_as_float(rd32(p + 12));
+    const unsigned refl = p[16], line = p[18];
+    const float s = __fdiv_rn(__uint2float_rn(off), __uint2float_rn(time_end));          // :19 float(offset_time / (float)time_end)
+    const float intensity = (float)addx((double)line, mulx((double)s, 0.1));            // :20
+    const float curvature = (float)mulx(0.1, (double)refl);                             // :21
+    out[3 * (size_t)i] = make_float4(x, y, z, 1.0f);                                    // pcl::PointXYZINormal default ctor: data[3] = 1
+    out[3 * (size_t)i + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    out[3 * (size_t)i + 2] = make_float4(intensity, curvature, 0.f, 0.f);
+}
+static int livox_to_dev(liliom_ctx* c, const void* custom_pts, int n, int stride, void* d_out48) {
+    if (n <= 0) return LILIOM_OK;
+    LILI_CUDA(c, c->livox_in.ensure((size_t)n * stride));
+    LILI_CUDA(c, cudaMemcpyAsync(c->livox_in.p, custom_pts, (size_t)n * stride, cudaMemcpyHostToDevice, c->stream));
+    k_livox_to_pt48<<<cdiv(n, 256), 256, 0, c->stream>>>((const unsigned char*)c->livox_in.p, n, stride, (float4*)d_out48);
+    return launch_check(c, "k_livox_to_pt48");
+}
+}  // namespace lili
+
+extern "C" int liliom_convert_livox(liliom_ctx* c, const void* custom_pts, int n, int stride, liliom_pt48* out, int cap) {
+    if (!c || n < 0 || (n > 0 && !custom_pts) || (stride != 19 && stride != 20)) return LILIOM_E_ARG;
+    if (c->prm.point_stride != 48) return LILIOM_E_ARG;
+    if (out && n > cap) return LILIOM_E_CAPACITY;
+    LILI_CUDA(c, cudaSetDevice(c->device));
+    LILI_CUDA(c, c->raw_scan.ensure((size_t)(n > 0 ? n : 1) * 48));
+    LILI_TRY(livox_to_dev(c, custom_pts, n, stride, c->raw_scan.p));
+    c->n_raw_scan = n;
+    if (out && n) LILI_CUDA(c, cudaMemcpyAsync(out, c->raw_scan.p, (size_t)n * 48, cudaMemcpyDeviceToHost, c->stream));
+    LILI_CUDA(c, cudaStreamSynchronize(c->stream));
+    return LILIOM_OK;
+}
+
+extern "C" int liliom_extract_horizon_livox(liliom_ctx* c, const void* custom_pts, int n, int stride, const double q_imu[4],
+                                            liliom_pt48* surf_out, int surf_cap, int* n_surf, liliom_pt48* edge_out, int edge_cap, int* n_edge,
+                                            liliom_pt48* cut_out, int cut_cap, int* n_cut) {
+    if (!c || n < 0 || (n > 0 && !custom_pts) || (stride != 19 && stride != 20) || !q_imu || !n_surf || !n_edge || !n_cut) return LILIOM_E_ARG;
+    if (c->prm.point_stride != 48) return LILIOM_E_ARG;
+    LILI_CUDA(c, cudaSetDevice(c->device));
+    LILI_CUDA(c, c->raw.ensure((size_t)(n > 0 ? n : 1) * 48));
+    LILI_TRY(livox_to_dev(c, custom_pts, n, stride, c->raw.p));
+    return extract_horizon_from_raw(c, n, q_imu, surf_out, surf_cap, n_surf, edge_out, edge_cap, n_edge, cut_out, cut_cap, n_cut);
 }
 
 extern "C" int liliom_extract_rot(liliom_ctx* c, const liliom_pt32* pts, int n, const double q_imu[4], const double q_lb[4],

@@ -156,6 +156,7 @@ static int backend_prepare(liliom_ctx* c, const void* feats, int n, int stride) 
     if (stride != 16 && stride != 32 && stride != 48) return LILIOM_E_ARG;
     c->n_feats = n;
     c->d_nfeats = nullptr;
+    c->bk_kind = 0; c->bk_n = 0;
     if (n == 0) return LILIOM_OK;
     LILI_CUDA(c, c->feats.ensure((size_t)n * sizeof(float4)));
     if (stride == 16) {
@@ -168,6 +169,134 @@ static int backend_prepare(liliom_ctx* c, const void* feats, int n, int stride) 
     return LILIOM_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------
+// the LiDAR residual blocks of one window keyframe (L/src/BackendFusion.cpp:919-979) reduced on the
+// device to that keyframe's 6x6 normal-equation block.  Rows are the closed forms of SURVEY.md Appendix A:
+//   LidarEdgeFactor      (LidarKeyframeFactor.h:12-62):  r = s |u x v| / |a-b|, u = p_w-a, v = p_w-b, p_w = q p + t
+//                                                        g = dr/dp_w = s ((a-b) x c^) / |a-b|
+//   LidarPlaneNormFactor (LidarKeyframeFactor.h:65-108): r = score (n~ . p_w + d~), p_w = q (q_lb^-1 (p - t_lb)) + t, g = score n~
+//   row = sqrt(rho') [ g^T , 2 (R p' x g)^T ]   (parameter blocks t, q -> tangent order [t, rot]),  CauchyLoss(b) (:845)
+// Works on the correspondences the last liliom_correspond_* call left resident in this context.
+// ---------------------------------------------------------------------------------------
+struct BlkArgs {
+    const float4* feats; int n;
+    const unsigned char* valid;
+    const float* pa; const float* pb;          // edge
+    const float4* plane; const double* score;  // surf
+    Q4 q; D3 t; Q4 qlb_inv; D3 tlb;
+    double s_weight, cauchy_b;
+    double* partials;                          // [gridDim.x][29]
+};
+
+constexpr int kBlkThreads = 256;
+
+template <bool EDGE>
+__global__ void __launch_bounds__(kBlkThreads) k_backend_block(BlkArgs a) {
+    __shared__ double red[kBlkThreads / 32][kNormEq];
+    double acc[kNormEq];
+#pragma unroll
+    for (int k = 0; k < kNormEq; ++k) acc[k] = 0.0;
+    const double b2 = a.cauchy_b * a.cauchy_b, c2 = 1.0 / b2;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += gridDim.x * blockDim.x) {
+        if (!a.valid[i]) continue;
+        const float4 f = a.feats[i];
+        D3 pr, g;        // the point the keyframe rotation acts on, and dr/dp_w
+        double r;
+        if (EDGE) {
+            pr = D3{(double)f.x, (double)f.y, (double)f.z};
+            const D3 rp = qrot_x(a.q, pr);
+            const D3 lp{rp.x + a.t.x, rp.y + a.t.y, rp.z + a.t.z};
+            const D3 A{(double)a.pa[3 * (size_t)i], (double)a.pa[3 * (size_t)i + 1], (double)a.pa[3 * (size_t)i + 2]};
+            const D3 B{(double)a.pb[3 * (size_t)i], (double)a.pb[3 * (size_t)i + 1], (double)a.pb[3 * (size_t)i + 2]};
+            const D3 u{lp.x - A.x, lp.y - A.y, lp.z - A.z}, v{lp.x - B.x, lp.y - B.y, lp.z - B.z};
+            const D3 nu = cross_x(u, v);
+            const D3 de{A.x - B.x, A.y - B.y, A.z - B.z};
+            const double nn = sqrt(nu.x * nu.x + nu.y * nu.y + nu.z * nu.z);
+            const double dn = sqrt(de.x * de.x + de.y * de.y + de.z * de.z);
+            r = nn / dn * a.s_weight;
+            g = D3{0, 0, 0};
+            if (nn > 0) {    // a zero cross product has no derivative (the reference's autodiff yields NaN there)
+                const D3 cx = cross_x(de, nu);
+                const double k = a.s_weight / (dn * nn);
+                g = D3{k * cx.x, k * cx.y, k * cx.z};
+            }
+        } else {
+            const D3 d{(double)f.x - a.tlb.x, (double)f.y - a.tlb.y, (double)f.z - a.tlb.z};
+            pr = qrot_x(a.qlb_inv, d);
+            const D3 rp = qrot_x(a.q, pr);
+            const float4 pl = a.plane[i];
+            const double sc = a.score[i];
+            r = sc * ((double)pl.x * (rp.x + a.t.x) + (double)pl.y * (rp.y + a.t.y) + (double)pl.z * (rp.z + a.t.z) + (double)pl.w);
+            g = D3{sc * (double)pl.x, sc * (double)pl.y, sc * (double)pl.z};
+        }
+        const D3 rp = qrot_x(a.q, pr);
+        double J[6];
+        J[0] = g.x; J[1] = g.y; J[2] = g.z;
+        J[3] = 2.0 * (rp.y * g.z - rp.z * g.y);
+        J[4] = 2.0 * (rp.z * g.x - rp.x * g.z);
+        J[5] = 2.0 * (rp.x * g.y - rp.y * g.x);
+        // ceres::CauchyLoss(b) + Corrector (rho'' < 0 branch)
+        const double sum = 1.0 + r * r * c2;
+        const double rho0 = b2 * log(sum);
+        const double sr = sqrt(fmax(DBL_MIN, 1.0 / sum));
+#pragma unroll
+        for (int k = 0; k < 6; ++k) J[k] *= sr;
+        r *= sr;
+        int k = 0;
+#pragma unroll
+        for (int i2 = 0; i2 < 6; ++i2)
+#pragma unroll
+            for (int j = i2; j < 6; ++j) acc[k++] += J[i2] * J[j];
+#pragma unroll
+        for (int i2 = 0; i2 < 6; ++i2) acc[21 + i2] += J[i2] * r;
+        acc[27] += 0.5 * rho0;
+        acc[28] += 1.0;
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < kNormEq; ++k) {
+        double v = acc[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) red[warp][k] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < kNormEq) {
+        double v = 0;
+#pragma unroll
+        for (int w = 0; w < kBlkThreads / 32; ++w) v += red[w][threadIdx.x];
+        a.partials[(size_t)blockIdx.x * kNormEq + threadIdx.x] = v;
+    }
+}
+
+// fixed-order sum over the block partials (run-to-run deterministic)
+__global__ void k_backend_block_sum(const double* __restrict__ partials, int nblocks, double* __restrict__ out29) {
+    if (threadIdx.x >= kNormEq) return;
+    double v = 0;
+    for (int b = 0; b < nblocks; ++b) v += partials[(size_t)b * kNormEq + threadIdx.x];
+    out29[threadIdx.x] = v;
+}
+
+static int backend_block_run(liliom_ctx* c, bool edge, BlkArgs& a, double out29[29]) {
+    const int n = c->bk_n;
+    const int nblocks = n > 0 ? min(cdiv(n, kBlkThreads), 64) : 1;
+    LILI_CUDA(c, c->partials.ensure((size_t)64 * kNormEq * sizeof(double)));
+    LILI_CUDA(c, c->neq.ensure(32 * sizeof(double)));
+    a.feats = c->feats.as<float4>(); a.n = n; a.valid = c->corr_valid.as<unsigned char>();
+    a.partials = c->partials.as<double>();
+    if (edge) k_backend_block<true><<<nblocks, kBlkThreads, 0, c->stream>>>(a);
+    else k_backend_block<false><<<nblocks, kBlkThreads, 0, c->stream>>>(a);
+    LILI_TRY(launch_check(c, "k_backend_block"));
+    k_backend_block_sum<<<1, 32, 0, c->stream>>>(a.partials, nblocks, c->neq.as<double>());
+    LILI_TRY(launch_check(c, "k_backend_block_sum"));
+    double* hp = reinterpret_cast<double*>(c->h_pin);
+    LILI_CUDA(c, cudaMemcpyAsync(hp, c->neq.p, kNormEq * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    LILI_CUDA(c, cudaStreamSynchronize(c->stream));
+    for (int k = 0; k < kNormEq; ++k) out29[k] = hp[k];
+    return LILIOM_OK;
+}
+
 }  // namespace lili
 
 using namespace lili;
@@ -177,7 +306,7 @@ extern "C" int liliom_correspond_edge(liliom_ctx* c, const void* feats, int n, i
     if (!c || !pose7 || !valid || !pa || !pb || (variant != 0 && variant != 1)) return LILIOM_E_ARG;
     LILI_CUDA(c, cudaSetDevice(c->device));
     LILI_TRY(backend_prepare(c, feats, n, stride));
-    if (n == 0) return LILIOM_OK;
+    if (n == 0) { c->bk_kind = 1; return LILIOM_OK; }
     LILI_CUDA(c, c->corr_valid.ensure((size_t)n + 16));
     LILI_CUDA(c, c->corr_plane.ensure((size_t)n * 24 + 16));
     BkArgs a{};
@@ -188,6 +317,7 @@ extern "C" int liliom_correspond_edge(liliom_ctx* c, const void* feats, int n, i
     a.pa = c->corr_plane.as<float>(); a.pb = a.pa + 3 * (size_t)n;
     k_backend_edge<<<cdiv((long long)n * kLanes, kBlock), kBlock, 0, c->stream>>>(a);
     LILI_TRY(launch_check(c, "k_backend_edge"));
+    c->bk_kind = 1; c->bk_n = n;
     LILI_CUDA(c, cudaMemcpyAsync(valid, a.valid, (size_t)n, cudaMemcpyDeviceToHost, c->stream));
     LILI_CUDA(c, cudaMemcpyAsync(pa, a.pa, (size_t)n * 12, cudaMemcpyDeviceToHost, c->stream));
     LILI_CUDA(c, cudaMemcpyAsync(pb, a.pb, (size_t)n * 12, cudaMemcpyDeviceToHost, c->stream));
@@ -208,7 +338,7 @@ static int correspond_surf_impl(liliom_ctx* c, const void* feats, int n, int str
         }
     }
     LILI_TRY(backend_prepare(c, feats, n, stride));
-    if (n == 0) return LILIOM_OK;
+    if (n == 0) { c->bk_kind = 2; return LILIOM_OK; }
     LILI_CUDA(c, c->corr_valid.ensure((size_t)n + 16));
     LILI_CUDA(c, c->corr_plane.ensure((size_t)n * 16 + 16));
     LILI_CUDA(c, c->nn_sqd.ensure((size_t)n * 8 + 16));
@@ -226,6 +356,7 @@ static int correspond_surf_impl(liliom_ctx* c, const void* feats, int n, int str
     a.valid = c->corr_valid.as<unsigned char>(); a.plane = c->corr_plane.as<float4>(); a.score = c->nn_sqd.as<double>();
     k_backend_surf<<<cdiv((long long)n * kLanes, kBlock), kBlock, 0, c->stream>>>(a);
     LILI_TRY(launch_check(c, "k_backend_surf"));
+    c->bk_kind = 2; c->bk_n = n;
     LILI_CUDA(c, cudaMemcpyAsync(valid, a.valid, (size_t)n, cudaMemcpyDeviceToHost, c->stream));
     LILI_CUDA(c, cudaMemcpyAsync(plane, a.plane, (size_t)n * 16, cudaMemcpyDeviceToHost, c->stream));
     LILI_CUDA(c, cudaMemcpyAsync(score, a.score, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
@@ -243,4 +374,31 @@ extern "C" int liliom_correspond_surf_refl(liliom_ctx* c, const void* feats48, i
                                            double surf_dist_thres, double w_gate, double lidar_const, double reflect_thres,
                                            unsigned char* valid, float* plane, double* score) {
     return correspond_surf_impl(c, feats48, n, 48, pose7, kd_max_radius, surf_dist_thres, w_gate, lidar_const, true, reflect_thres, valid, plane, score);
+}
+
+extern "C" int liliom_backend_edge_block(liliom_ctx* c, const double pose7_body[7], double s_weight, double cauchy_b, double out29[29]) {
+    if (!c || !pose7_body || !out29 || !(cauchy_b > 0)) return LILIOM_E_ARG;
+    LILI_CUDA(c, cudaSetDevice(c->device));
+    if (c->bk_kind != 1) { c->last_error = "liliom_backend_edge_block needs the correspondences of a preceding liliom_correspond_edge call"; return LILIOM_E_ARG; }
+    BlkArgs a{};
+    a.q = Q4{pose7_body[0], pose7_body[1], pose7_body[2], pose7_body[3]}; a.t = D3{pose7_body[4], pose7_body[5], pose7_body[6]};
+    a.pa = c->corr_plane.as<float>(); a.pb = a.pa + 3 * (size_t)c->bk_n;
+    a.s_weight = s_weight; a.cauchy_b = cauchy_b;
+    return backend_block_run(c, true, a, out29);
+}
+
+extern "C" int liliom_backend_surf_block(liliom_ctx* c, const double pose7_body[7], const double q_lb_wxyz[4], const double t_lb[3],
+                                         double cauchy_b, double out29[29]) {
+    if (!c || !pose7_body || !q_lb_wxyz || !t_lb || !out29 || !(cauchy_b > 0)) return LILIOM_E_ARG;
+    LILI_CUDA(c, cudaSetDevice(c->device));
+    if (c->bk_kind != 2) { c->last_error = "liliom_backend_surf_block needs the correspondences of a preceding liliom_correspond_surf* call"; return LILIOM_E_ARG; }
+    BlkArgs a{};
+    a.q = Q4{pose7_body[0], pose7_body[1], pose7_body[2], pose7_body[3]}; a.t = D3{pose7_body[4], pose7_body[5], pose7_body[6]};
+    // Eigen::Quaternion::inverse(): conjugate / squared norm (zero quaternion for a zero input)
+    const double n2 = q_lb_wxyz[0] * q_lb_wxyz[0] + q_lb_wxyz[1] * q_lb_wxyz[1] + q_lb_wxyz[2] * q_lb_wxyz[2] + q_lb_wxyz[3] * q_lb_wxyz[3];
+    a.qlb_inv = n2 > 0 ? Q4{q_lb_wxyz[0] / n2, -q_lb_wxyz[1] / n2, -q_lb_wxyz[2] / n2, -q_lb_wxyz[3] / n2} : Q4{0, 0, 0, 0};
+    a.tlb = D3{t_lb[0], t_lb[1], t_lb[2]};
+    a.plane = c->corr_plane.as<float4>(); a.score = c->nn_sqd.as<double>();
+    a.cauchy_b = cauchy_b;
+    return backend_block_run(c, false, a, out29);
 }

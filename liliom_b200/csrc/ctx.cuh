@@ -92,7 +92,8 @@ struct liliom_ctx {
     lili::DevBuf hz_ctl;         // barrier words + per-block counts of the cooperative Horizon extractor
     unsigned int hz_coop_calls = 0;
     long long vg_ncells = 0;     // voxel-box cell count of that VoxelGrid, valid after the sync
-    lili::DevBuf raw_scan;       // resident raw sweep (liliom_upload_scan)
+    lili::DevBuf raw_scan;       // resident raw sweep (liliom_upload_scan / liliom_convert_livox)
+    lili::DevBuf livox_in;       // staged livox CustomPoint records (19/20 bytes each)
     int n_raw_scan = 0;
     int n_rot_cloud = 0;
 
@@ -125,6 +126,7 @@ struct liliom_ctx {
     lili::DevBuf counter;                // last-block ticket + scratch ints
     lili::DevBuf lm_state;
     lili::DevBuf slots_buf;              // search -> fit hand-off of the split path (48 B per query)
+    int bk_kind = 0, bk_n = 0;           // backend correspondences resident from the last liliom_correspond_* call (1 edge, 2 surf)
     unsigned int bar_arrivals = 0;       // total grid-barrier arrivals issued so far (persistent GN kernel)
 
     // ---- multi-GPU ----

@@ -95,6 +95,21 @@ int orc_correspond_surf_backend(const void* tree, const float* map_xyzw, int m, 
                                 double lidar_const, const float* map_refl, const float* feat_refl, double reflect_thres,
                                 unsigned char* valid, float* plane, double* score);
 
+
+/* ---- (f1) backend LiDAR residual blocks of one window keyframe, LiLi-OM/src/BackendFusion.cpp:919-979 ----
+ * LidarEdgeFactor / LidarPlaneNormFactor (LidarKeyframeFactor.h:12-108) under CauchyLoss(cauchy_b), reduced to the
+ * keyframe's normal-equation block.  Tangent order [t(3), rot(3)] (parameter blocks t, q); out29 = 21 + 6 + cost + count.
+ * feats/valid/pa/pb/plane/score are the outputs of the correspondence searches above; pose7_body = [qw..qz, tx..tz] of the
+ * keyframe (tmpQuat/tmpTrans), NOT the lidar pose the search ran at. */
+void orc_backend_edge_block(const float* feats_xyzw, int n, const unsigned char* valid, const float* pa, const float* pb,
+                            double s_weight, const double pose7_body[7], double cauchy_b, double out29[29]);
+void orc_backend_surf_block(const float* feats_xyzw, int n, const unsigned char* valid, const float* plane, const double* score,
+                            const double pose7_body[7], const double q_lb[4], const double t_lb[3], double cauchy_b,
+                            double out29[29]);
+
+/* ---- (f3) FormatConvert, LiLi-OM/src/FormatConvert.cpp:11-24: livox CustomPoint[] -> PointXYZINormal[] ---- */
+void orc_convert_livox(const unsigned char* custom_pts, int n, int stride, orc_pt48* out);
+
 /* ---- host glue restated for tests of the node mirror ----
  * math_tools.h:125-138 deltaQ + Preprocessing.cpp:129-133 solveRotation: q <- q * deltaQ(0.5*(g0+g1)*dt) */
 void orc_solve_rotation(double q_wxyz[4], const double gyr0[3], const double gyr1[3], double dt);

@@ -123,3 +123,131 @@ extern "C" int orc_correspond_surf_backend(const void* tree, const float* map_xy
     }
     return cnt;
 }
+
+// ---------------------------------------------------------------------------------------
+// the LiDAR residual blocks one window keyframe contributes to the backend problem,
+// LiLi-OM/src/BackendFusion.cpp:919-979 — LidarEdgeFactor (LidarKeyframeFactor.h:12-62) and LidarPlaneNormFactor
+// (:65-108), AutoDiffCostFunction<.,1,3,4> on the parameter blocks (t, q) with QuaternionParameterization on q and
+// ceres::CauchyLoss(1.0) (:845).  What Ceres feeds its linear solver for such a block is, per residual, the row
+// sqrt(rho') * [dr/dt , dr/dq * PlusJacobian(q)] and the residual sqrt(rho') * r (Corrector, rho'' <= 0 branch); the
+// functions below reduce those rows to the keyframe's 6x6 normal-equation block.
+// Tangent order follows the parameter-block order: [t(3), rot(3)].  out29 = 21 (upper triangle, row-major) + 6 + cost + count.
+// ---------------------------------------------------------------------------------------
+namespace {
+
+// d(q*v)/dq_k for Eigen's q*v expression (uv = qv x v; uv += uv; v + w uv + qv x uv), then the from-knowledge
+// ceres::QuaternionParameterization::ComputeJacobian (4x3) — same construction as plane_row() in oracle_s2m.cpp.
+inline void rot_tangent_rows(const double x[4], V3 v, V3 g, double Jrot[3]) {
+    const double w = x[0];
+    V3 qv{x[1], x[2], x[3]};
+    V3 uv = cross(qv, v); uv = uv + uv;
+    double jq[4];
+    jq[0] = dot(g, uv);
+    const V3 e[3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+    for (int k = 0; k < 3; ++k) {
+        V3 duv = 2.0 * cross(e[k], v);
+        V3 df = w * duv + cross(e[k], uv) + cross(qv, duv);
+        jq[k + 1] = dot(g, df);
+    }
+    const double P[4][3] = {{-x[1], -x[2], -x[3]}, {x[0], x[3], -x[2]}, {-x[3], x[0], x[1]}, {x[2], -x[1], x[0]}};
+    for (int c = 0; c < 3; ++c) Jrot[c] = jq[0] * P[0][c] + jq[1] * P[1][c] + jq[2] * P[2][c] + jq[3] * P[3][c];
+}
+
+// from-knowledge ceres::CauchyLoss(b)::Evaluate: rho = b^2 log(1 + s/b^2), rho' = 1/(1 + s/b^2), rho'' < 0, then the
+// Corrector's rho'' <= 0 branch: row and residual scaled by sqrt(rho').
+inline void add_row(double J[6], double r, double cauchy_b, double out29[29]) {
+    const double s = r * r, b2 = cauchy_b * cauchy_b, c2 = 1.0 / b2;
+    const double sum = 1.0 + s * c2;
+    const double inv = 1.0 / sum;
+    const double rho0 = b2 * std::log(sum);
+    const double rho1 = std::max(std::numeric_limits<double>::min(), inv);
+    const double sr = std::sqrt(rho1);
+    for (int c = 0; c < 6; ++c) J[c] *= sr;
+    r *= sr;
+    int k = 0;
+    for (int a = 0; a < 6; ++a)
+        for (int b = a; b < 6; ++b) out29[k++] += J[a] * J[b];
+    for (int a = 0; a < 6; ++a) out29[21 + a] += J[a] * r;
+    out29[27] += 0.5 * rho0;
+    out29[28] += 1.0;
+}
+
+}  // namespace
+
+extern "C" void orc_backend_edge_block(const float* feats_xyzw, int n, const unsigned char* valid, const float* pa, const float* pb,
+                                       double s_weight, const double pose7_body[7], double cauchy_b, double out29[29]) {
+    for (int k = 0; k < 29; ++k) out29[k] = 0;
+    Quat q{pose7_body[0], pose7_body[1], pose7_body[2], pose7_body[3]};
+    V3 t{pose7_body[4], pose7_body[5], pose7_body[6]};
+    for (int i = 0; i < n; ++i) {
+        if (!valid[i]) continue;
+        const float* f = feats_xyzw + 4 * (size_t)i;
+        V3 cp{f[0], f[1], f[2]};
+        V3 a{pa[3 * (size_t)i], pa[3 * (size_t)i + 1], pa[3 * (size_t)i + 2]};
+        V3 b{pb[3 * (size_t)i], pb[3 * (size_t)i + 1], pb[3 * (size_t)i + 2]};
+        V3 lp = qrot(q, cp) + t;                                 // LidarKeyframeFactor.h:38 (the extrinsics are NOT applied)
+        V3 nu = cross(lp - a, lp - b);                           // :40
+        V3 de = a - b;                                           // :41
+        const double nn = norm(nu), dn = norm(de);
+        double r = nn / dn;                                      // :43
+        r *= s_weight;                                           // :44
+        // dr/dlp = s ((a-b) x nu^) / |a-b|; a zero cross product has no derivative (autodiff yields NaN): row dropped to 0
+        V3 g{0, 0, 0};
+        if (nn > 0) g = (s_weight / (dn * nn)) * cross(de, nu);
+        double J[6];
+        J[0] = g.x; J[1] = g.y; J[2] = g.z;
+        rot_tangent_rows(pose7_body, cp, g, J + 3);
+        add_row(J, r, cauchy_b, out29);
+    }
+}
+
+extern "C" void orc_backend_surf_block(const float* feats_xyzw, int n, const unsigned char* valid, const float* plane, const double* score,
+                                       const double pose7_body[7], const double q_lb[4], const double t_lb[3], double cauchy_b,
+                                       double out29[29]) {
+    for (int k = 0; k < 29; ++k) out29[k] = 0;
+    Quat q{pose7_body[0], pose7_body[1], pose7_body[2], pose7_body[3]};
+    V3 t{pose7_body[4], pose7_body[5], pose7_body[6]};
+    Quat qlbi = qinv(Quat{q_lb[0], q_lb[1], q_lb[2], q_lb[3]});
+    V3 tlb{t_lb[0], t_lb[1], t_lb[2]};
+    for (int i = 0; i < n; ++i) {
+        if (!valid[i]) continue;
+        const float* f = feats_xyzw + 4 * (size_t)i;
+        const float* pl = plane + 4 * (size_t)i;
+        V3 cp{f[0], f[1], f[2]};
+        V3 pbody = qrot(qlbi, cp - tlb);                         // LidarKeyframeFactor.h:87
+        V3 pw = qrot(q, pbody) + t;                              // :88
+        V3 nrm{pl[0], pl[1], pl[2]};
+        const double sc = score[i];
+        const double r = sc * (dot(nrm, pw) + (double)pl[3]);    // :91
+        V3 g = sc * nrm;
+        double J[6];
+        J[0] = g.x; J[1] = g.y; J[2] = g.z;
+        rot_tangent_rows(pose7_body, pbody, g, J + 3);
+        add_row(J, r, cauchy_b, out29);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// FormatConvert's livoxLidarHandler, LiLi-OM/src/FormatConvert.cpp:11-24, on the in-memory
+// livox_ros_driver::CustomPoint {uint32 offset_time; float x,y,z; uint8 reflectivity, tag, line} (stride bytes per
+// point: 20 for the C++ message struct, 19 for the serialised wire layout).  Output: pcl::PointXYZINormal as
+// push_back'ed there (data[3] = 1, normals/curvature pads 0).
+// ---------------------------------------------------------------------------------------
+extern "C" void orc_convert_livox(const unsigned char* custom_pts, int n, int stride, orc_pt48* out) {
+    if (n <= 0) return;
+    unsigned int time_end;
+    std::memcpy(&time_end, custom_pts + (size_t)(n - 1) * stride, 4);       // :13 points.back().offset_time
+    for (int i = 0; i < n; ++i) {
+        const unsigned char* p = custom_pts + (size_t)i * stride;
+        unsigned int off; float xyz[3];
+        std::memcpy(&off, p, 4); std::memcpy(xyz, p + 4, 12);
+        const unsigned char refl = p[16], line = p[18];
+        orc_pt48 pt;
+        std::memset(&pt, 0, sizeof(pt));
+        pt.x = xyz[0]; pt.y = xyz[1]; pt.z = xyz[2]; pt.w = 1.0f;
+        float s = float(off / (float)time_end);                              // :19 (uint32 -> float, fp32 division)
+        pt.intensity = line + s * 0.1;                                       // :20 (double arithmetic, narrowed)
+        pt.curvature = 0.1 * refl;                                           // :21
+        out[i] = pt;
+    }
+}

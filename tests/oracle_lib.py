@@ -51,6 +51,9 @@ def lib():
         L.orc_correspond_edge.argtypes = [vp, vp, C.c_int, vp, C.c_int, dp, C.c_int, vp, vp, vp]
         L.orc_correspond_surf_backend.argtypes = [vp, vp, C.c_int, vp, C.c_int, dp, C.c_double, C.c_double, C.c_double, C.c_double,
                                                   vp, vp, C.c_double, vp, vp, vp]
+        L.orc_backend_edge_block.argtypes = [vp, C.c_int, vp, vp, vp, C.c_double, dp, C.c_double, dp]; L.orc_backend_edge_block.restype = None
+        L.orc_backend_surf_block.argtypes = [vp, C.c_int, vp, vp, vp, dp, dp, dp, C.c_double, dp]; L.orc_backend_surf_block.restype = None
+        L.orc_convert_livox.argtypes = [vp, C.c_int, C.c_int, vp]; L.orc_convert_livox.restype = None
         L.orc_solve_rotation.argtypes = [dp, dp, dp, C.c_double]; L.orc_solve_rotation.restype = None
         L.orc_pose_compose.argtypes = [dp, dp, dp]; L.orc_pose_compose.restype = None
         L.orc_pose_relative.argtypes = [dp, dp, dp]; L.orc_pose_relative.restype = None
@@ -213,3 +216,38 @@ def ceres_solve(feats, valid, plane, pose7, max_num_iter=15):
     cost = C.c_double()
     it = lib().orc_ceres_solve(_p(f), len(f), _p(np.ascontiguousarray(valid)), _p(np.ascontiguousarray(plane)), _d(pose), max_num_iter, C.byref(cost))
     return it, pose, cost.value
+
+
+def backend_edge_block(feats, valid, pa, pb, s_weight, pose7_body, cauchy_b=1.0):
+    """(f1) LidarEdgeFactor rows of one keyframe reduced to [21 | 6 | cost | count], tangent order [t, rot]."""
+    f = _f4(feats)
+    out = np.zeros(29)
+    lib().orc_backend_edge_block(_p(f), len(f), _p(np.ascontiguousarray(valid, np.uint8)), _p(np.ascontiguousarray(pa, np.float32)),
+                                 _p(np.ascontiguousarray(pb, np.float32)), float(s_weight), _d(np.asarray(pose7_body, np.float64)), float(cauchy_b), _d(out))
+    return out
+
+
+def backend_surf_block(feats, valid, plane, score, pose7_body, q_lb=(1.0, 0, 0, 0), t_lb=(0.0, 0, 0), cauchy_b=1.0):
+    """(f1) LidarPlaneNormFactor rows of one keyframe reduced to [21 | 6 | cost | count], tangent order [t, rot]."""
+    f = _f4(feats)
+    out = np.zeros(29)
+    lib().orc_backend_surf_block(_p(f), len(f), _p(np.ascontiguousarray(valid, np.uint8)), _p(np.ascontiguousarray(plane, np.float32)),
+                                 _p(np.ascontiguousarray(score, np.float64)), _d(np.asarray(pose7_body, np.float64)),
+                                 _d(np.asarray(q_lb, np.float64)), _d(np.asarray(t_lb, np.float64)), float(cauchy_b), _d(out))
+    return out
+
+
+LIVOX20 = np.dtype([("offset_time", "<u4"), ("x", "<f4"), ("y", "<f4"), ("z", "<f4"), ("reflectivity", "u1"), ("tag", "u1"), ("line", "u1"), ("pad", "u1")])
+
+
+def convert_livox(custom_pts, stride=None):
+    """(f3) FormatConvert::livoxLidarHandler on an array of livox CustomPoint (LIVOX20 records or raw bytes + stride)."""
+    a = np.ascontiguousarray(custom_pts)
+    if stride is None:
+        stride = a.dtype.itemsize
+        n = len(a)
+    else:
+        n = a.size // stride
+    out = np.zeros(max(n, 1), PT48)
+    lib().orc_convert_livox(_p(a), n, stride, _p(out))
+    return out[:n]

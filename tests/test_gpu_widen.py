@@ -1,0 +1,121 @@
+"""GPU parity for the SURVEY.md §8 (f) rows: (f1) backend LiDAR factor blocks, (f3) Livox CustomMsg ingest.
+Same bar as tests/test_gpu_parity.py: the CUDA path through the C ABI against the CPU oracle on identical inputs."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _f4(cloud):
+    out = np.ones((len(cloud), 4), np.float32)
+    out[:, 0] = cloud["x"]; out[:, 1] = cloud["y"]; out[:, 2] = cloud["z"]
+    return out
+
+
+def _livox_sweep(world_small, L):
+    """The synthetic Horizon sweep re-encoded as the livox CustomPoint records FormatConvert receives."""
+    pts = world_small["hz"]
+    n = len(pts)
+    a = np.zeros(n, L.LIVOX20)
+    line = np.floor(pts["intensity"]).astype(np.int64)
+    frac = (pts["intensity"].astype(np.float64) - line) / 0.1
+    a["offset_time"] = np.clip(np.round(frac * 99_000_000.0), 0, 99_000_000).astype(np.uint32)
+    a["offset_time"][-1] = 99_000_000                                   # points.back() defines time_end
+    a["x"], a["y"], a["z"] = pts["x"], pts["y"], pts["z"]
+    a["reflectivity"] = np.clip(np.round(pts["curvature"].astype(np.float64) * 10.0), 0, 255).astype(np.uint8)
+    a["line"] = line.astype(np.uint8)
+    a["tag"] = 0x10
+    return a
+
+
+# ---------------------------------------------------------------- (f3) FormatConvert on the device
+@pytest.mark.parametrize("stride", [20, 19])
+def test_convert_livox_bit_exact(ctx48, oracle, world_small, stride):
+    import liliom_b200 as L
+    a = _livox_sweep(world_small, L)
+    raw = a if stride == 20 else np.ascontiguousarray(a.view(np.uint8).reshape(len(a), 20)[:, :19]).reshape(-1)
+    ref = oracle.convert_livox(raw, stride=stride if stride == 19 else None)
+    got = ctx48.convert_livox(raw, stride=stride if stride == 19 else None)
+    assert got.tobytes() == ref.tobytes()
+    assert len(ctx48.convert_livox(a[:0])) == 0
+
+
+def test_extract_horizon_from_livox_records(ctx48, oracle, world_small):
+    import liliom_b200 as L
+    a = _livox_sweep(world_small, L)
+    cloud = oracle.convert_livox(a)
+    surf_o, edge_o, cut_o = oracle.extract_horizon(cloud, world_small["q_hz"])
+    surf, edge, cut = ctx48.extract_horizon_livox(a, world_small["q_hz"])
+    assert len(surf_o) > 3000
+    for got, ref in ((surf, surf_o), (edge, edge_o), (cut, cut_o)):
+        assert len(got) == len(ref) and got.tobytes() == ref.tobytes()
+    # resident flow: convert -> extract_resident gives the same counts
+    n = ctx48.convert_livox(a, download=False)
+    ns, ne, nc = ctx48.extract_resident(world_small["q_hz"])
+    assert n == len(a) and nc == len(cut_o)
+    pose, st, ds = ctx48.odometry_resident(world_small["guess"], 0, want_ds=True, cap=len(a))     # surf count is device-side there
+    assert len(ds) == len(oracle.voxelgrid(surf_o, 0.4))
+
+
+# ---------------------------------------------------------------- (f1) backend LiDAR factor blocks
+def test_backend_surf_block_matches_oracle(oracle, world_small):
+    import liliom_b200 as L
+    surf_o, edge_o, _ = oracle.extract_horizon(world_small["hz"], world_small["q_hz"])
+    ds = oracle.voxelgrid(surf_o, 0.4)
+    tree = oracle.KdTree(world_small["map"])
+    pose_l = world_small["guess"]
+    q_lb = np.array([0.9990482, 0.0, 0.0436194, 0.0]); t_lb = np.array([0.05, -0.02, 0.10])
+    c = L.Context(variant=0)
+    c.map_set_points(world_small["map"])
+    v_o, pl_o, sc_o = oracle.correspond_surf_backend(tree, ds, pose_l, 1.0, 0.06, 0.2, 0.6)
+    v, pl, sc = c.correspond_surf(ds, pose_l, 1.0, 0.06, 0.2, 0.6)
+    assert np.array_equal(v, v_o) and v.sum() > 200
+    for k, pose_b in enumerate((pose_l, world_small["T"])):           # the block may be evaluated at any pose (LM iterations)
+        ref = oracle.backend_surf_block(ds, v, pl, sc, pose_b, q_lb, t_lb, 1.0)
+        got = c.backend_surf_block(pose_b, q_lb, t_lb, 1.0)
+        assert got[28] == ref[28] == v.sum()
+        np.testing.assert_allclose(got, ref, rtol=1e-9, atol=1e-9 * np.abs(ref[:21]).max())
+    # the wrong kind resident -> argument error, not garbage
+    with pytest.raises(L.LiliomError):
+        c.backend_edge_block(pose_l, 0.6)
+    c.close()
+
+
+def test_backend_edge_block_matches_oracle(oracle, world_small):
+    import liliom_b200 as L
+    rng = np.random.default_rng(21)
+    # an edge local map: points along vertical poles and horizontal rails (line-like 5-NN sets), 0.2 m spacing + noise
+    poles = []
+    for px in range(-30, 31, 6):
+        for py in (-8.0, 8.0):
+            z = np.arange(0.0, 6.0, 0.2)
+            poles.append(np.stack([np.full_like(z, px), np.full_like(z, py), z], 1))
+        x = np.arange(px, px + 6.0, 0.2)
+        poles.append(np.stack([x, np.full_like(x, 10.0), np.full_like(x, 3.0)], 1))
+    m = np.concatenate(poles).astype(np.float32)
+    m += rng.normal(0, 0.01, m.shape).astype(np.float32)
+    m4 = np.ones((len(m), 4), np.float32); m4[:, :3] = m
+    pose = np.array([0.9990482, 0.0, 0.0, 0.0436194, 0.4, -0.3, 0.1])
+    # features: map points pulled into the body frame with noise
+    sel = m[rng.integers(0, len(m), 1500)].astype(np.float64) + rng.normal(0, 0.08, (1500, 3))
+    qw, qx, qy, qz = pose[:4]
+    R = np.array([[1 - 2 * (qy * qy + qz * qz), 2 * (qx * qy - qw * qz), 2 * (qx * qz + qw * qy)],
+                  [2 * (qx * qy + qw * qz), 1 - 2 * (qx * qx + qz * qz), 2 * (qy * qz - qw * qx)],
+                  [2 * (qx * qz - qw * qy), 2 * (qy * qz + qw * qx), 1 - 2 * (qx * qx + qy * qy)]])
+    feats = np.ones((1500, 4), np.float32); feats[:, :3] = (sel - pose[4:]) @ R
+    tree = oracle.KdTree(m4)
+    c = L.Context(variant=0)
+    c.map_set_points(m4)
+    for variant in (0, 1):
+        v_o, pa_o, pb_o = oracle.correspond_edge(tree, feats, pose, variant)
+        v, pa, pb = c.correspond_edge(feats, pose, variant)
+        assert np.array_equal(v, v_o) and v.sum() > 300
+        pose_b = pose.copy(); pose_b[4:] += (0.02, -0.01, 0.03)
+        ref = oracle.backend_edge_block(feats, v, pa, pb, 0.6, pose_b, 1.0)
+        got = c.backend_edge_block(pose_b, 0.6, 1.0)
+        assert got[28] == ref[28] == v.sum()
+        np.testing.assert_allclose(got, ref, rtol=1e-8, atol=1e-9 * np.abs(ref[:21]).max())
+    # empty feature set: zero block
+    c.correspond_edge(feats[:0], pose, 0)
+    assert not c.backend_edge_block(pose, 0.6).any()
+    c.close()
