@@ -137,6 +137,11 @@ struct liliom_ctx {
     liliom_counters cnt{};
     bool time_kernels = false;
     int force_lanes = 0, force_rounds = 0;   // tuning override (LILIOM_KNN_LANES / LILIOM_KNN_ROUNDS)
+    int knn_flat = 0;                    // 16-lane search shape: 0 = one run per lane, 1 = round-robin candidates, 2 = + per-iteration cache (LILIOM_KNN_FLAT)
+    int gn_ll = 0;                       // persistent GN kernel: 1 = flag-in-data exchange of the block partials instead of the counter barrier (LILIOM_GN_LL)
+    lili::DevBuf ll_buf;                 // two epoch-parity buffers of [29][2*sm_count] {epoch|lo32, epoch|hi32}
+    unsigned int ll_epoch = 0;           // last epoch issued
+    bool gn_smem_set = false;            // cudaFuncAttributeMaxDynamicSharedMemorySize raised for k_gn_persistent<16> on this device
     std::vector<cudaEvent_t> ev_pool;
     size_t ev_used = 0;
     std::vector<std::pair<size_t, unsigned long long>> ev_pending;  // (event pair index, queries)

@@ -186,6 +186,8 @@ struct KnnArgs {
     int interleave;                     // 1: deal tasks to warps block-cyclically (load balance for small scans)
     struct Slot* slots_g;               // split path (large query sets): search kernel -> fit kernel hand-off, 48 B per query
     int fit_only;                       // 1: phase A is skipped, slots come from slots_g (written by k_knn_search)
+    int flat;                           // LANES >= 16 only: 1 = deal the 27-cell candidate list round-robin over the lanes (group_knn5_flat),
+                                        // 2 = also keep each lane's batch across the GN iterations of the persistent kernel
 };
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -215,6 +217,8 @@ struct KnnSmem {
     Slot slots[kWarps][32];
     Row rows[kWarps][32];
     unsigned char rvalid[kWarps][32];
+    float4 nb[kWarps][2][5];     // FLAT shape (two queries per warp task): the 5 neighbours handed over by the search
+    int nb_flag[kWarps][2];
     double red[kWarps][kNormEq];
     unsigned long long red_cand[kWarps];
     double pose[8];
@@ -226,9 +230,10 @@ struct KnnSmem {
 
 // One pass over this block's share of the queries at pose (q,t): phases A (search), B (fit + row), C (lane k
 // accumulates scalar k).  On return lane k < 29 of every warp holds its partial of scalar k in `acc`.
-template <int LANES>
+template <int LANES, bool FLAT = false>
 __device__ __forceinline__ void knn_phases(const KnnArgs& a, const Q4& q, const D3& t, const int n_q, KnnSmem& S,
-                                           double& acc, unsigned long long& cand, const float4* fpre = nullptr) {
+                                           double& acc, unsigned long long& cand, const float4* fpre = nullptr,
+                                           float4* cc = nullptr, int cc_stride = 0, int4* cc_tag = nullptr) {
     constexpr int GROUPS = 32 / LANES;                 // queries a warp searches concurrently
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -271,7 +276,14 @@ __device__ __forceinline__ void knn_phases(const KnnArgs& a, const Q4& q, const 
             }
             // `live` is uniform inside a lane group and the shuffles are masked per group
             LILI_STAMP(8);
-            if (live) group_knn5<LANES>(sx, sy, sz, a.map, a.cell_start, a.g, sub, gmask, top, cand, (a.dbg && blockIdx.x == 0 && threadIdx.x == 0) ? a.dbg : nullptr);
+            if (live) {
+                if constexpr (FLAT) {
+                    const bool hand = per_task <= 2;       // rounds == 1: slot == grp
+                    group_knn5_flat<LANES>(sx, sy, sz, a.map, a.cell_start, a.g, sub, gmask, top, cand, cc, cc_stride, cc_tag,
+                                           hand ? &S.nb[warp][slot & 1][0] : nullptr, hand ? &S.nb_flag[warp][slot & 1] : nullptr);
+                }
+                else group_knn5<LANES>(sx, sy, sz, a.map, a.cell_start, a.g, sub, gmask, top, cand, (a.dbg && blockIdx.x == 0 && threadIdx.x == 0) ? a.dbg : nullptr);
+            }
             LILI_STAMP(11);
             if (sub == 0) {
                 Slot& s = S.slots[warp][slot];
@@ -280,6 +292,8 @@ __device__ __forceinline__ void knn_phases(const KnnArgs& a, const Q4& q, const 
                 s.idx[3] = top5_index(top.k3); s.idx[4] = top5_index(top.k4);
                 s.sx = sx; s.sy = sy; s.sz = sz;
                 s.fx = f.x; s.fy = f.y; s.fz = f.z;
+                s.pad = 0;
+                if constexpr (FLAT) { if (live && per_task <= 2) s.pad = 2; }    // neighbours may be in S.nb (see nb_flag)
                 if (live && a.nn_idx) {
                     int* o = a.nn_idx + (size_t)qi * 5;
                     const u64 kk[5] = {top.k0, top.k1, top.k2, top.k3, top.k4};
@@ -302,8 +316,15 @@ __device__ __forceinline__ void knn_phases(const KnnArgs& a, const Q4& q, const 
             float pl0 = 0.f, pl1 = 0.f, pl2 = 0.f, pl3 = 0.f;
             if (qi < n_q && s.idx[0] >= 0) {
                 float4 m[5];
+                bool from_smem = false;
+                if constexpr (FLAT) from_smem = s.pad == 2 && S.nb_flag[warp][lane & 1] == 1;
+                if (from_smem) {
 #pragma unroll
-                for (int j = 0; j < 5; ++j) m[j] = __ldg(a.map_orig + s.idx[j]);                                     // :369-371
+                    for (int j = 0; j < 5; ++j) m[j] = S.nb[warp][lane & 1][j];
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 5; ++j) m[j] = __ldg(a.map_orig + s.idx[j]);                                 // :369-371
+                }
                 double nv[3];
                 if (!plane_fit5_fast(m, nv)) plane_fit5_qr(m, nv);                                                    // :375 (see dev_math.cuh)
                 const double n2 = nv[0] * nv[0] + nv[1] * nv[1] + nv[2] * nv[2];
@@ -396,27 +417,114 @@ __device__ __forceinline__ void write_block_partials(const KnnArgs& a, KnnSmem& 
     }
 }
 
-// Fixed-order sum over the G block partials into S.red[0][0..28]: 8 lanes per scalar, 4 independent loads
-// in flight per lane — this is exposed latency, so it is laid out for memory-level parallelism.
+// Fixed-order sum over the G block partials into S.red[0][0..28]: 8 lanes per scalar.  This is exposed latency, so
+// every load of a lane is issued before the first add: ONE L2 round trip for up to 8*kRedLoads = 160 blocks (the
+// persistent kernel never has more than one block per SM); larger grids take another trip per 160 blocks.
+constexpr int kRedLoads = 20;
 __device__ __forceinline__ void reduce_partials(const KnnArgs& a, KnnSmem& S) {
     const int G = gridDim.x;
     const int sc = threadIdx.x >> 3, l8 = threadIdx.x & 7;
     double v = 0.0;
     if (sc < kNormEq) {
         const double* src = a.partials + (size_t)sc * G;
-        // 8 independent accumulators = 8 loads in flight per lane (64 blocks per round trip per scalar)
-        double w0 = 0, w1 = 0, w2 = 0, w3 = 0, w4 = 0, w5 = 0, w6 = 0, w7 = 0;
-        for (int b = l8; b < G; b += 64) {
-            w0 += __ldcg(src + b);
-            if (b + 8 < G) w1 += __ldcg(src + b + 8);
-            if (b + 16 < G) w2 += __ldcg(src + b + 16);
-            if (b + 24 < G) w3 += __ldcg(src + b + 24);
-            if (b + 32 < G) w4 += __ldcg(src + b + 32);
-            if (b + 40 < G) w5 += __ldcg(src + b + 40);
-            if (b + 48 < G) w6 += __ldcg(src + b + 48);
-            if (b + 56 < G) w7 += __ldcg(src + b + 56);
+#pragma unroll 1
+        for (int base = l8; base < G; base += 8 * kRedLoads) {
+            double w[kRedLoads];
+#pragma unroll
+            for (int j = 0; j < kRedLoads; ++j) w[j] = (base + 8 * j < G) ? __ldcg(src + base + 8 * j) : 0.0;
+            // fixed pairwise tree (deterministic, short dependency chain)
+#pragma unroll
+            for (int j = 0; j < 10; ++j) w[j] += w[j + 10];
+#pragma unroll
+            for (int j = 0; j < 5; ++j) w[j] += w[j + 5];
+            v += ((w[0] + w[1]) + (w[2] + w[3])) + w[4];
         }
-        v = ((w0 + w1) + (w2 + w3)) + ((w4 + w5) + (w6 + w7));
+    }
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    if (l8 == 0 && sc < kNormEq) S.red[0][sc] = v;
+    __syncthreads();
+}
+
+// ---- flag-in-data exchange of the block partials (persistent kernel, opt-out: LILIOM_GN_LL=0) -------------------
+// The counter barrier costs three dependent L2 round trips per pass on top of the arrival skew: partial stores ->
+// __threadfence -> atomic arrival -> poll -> partial loads (measured: fence 2.1k + barrier 4.2k + reduce 2.3k of a
+// 24k-cycle pass).  Here every 8-byte word a block publishes carries the pass's epoch in its upper half (a double
+// travels as {epoch|lo32, epoch|hi32}, NCCL's "LL" scheme): an aligned 8-byte store is single-copy atomic, so a
+// reader that sees the epoch sees the data — no fence, no counter, and the wait IS the load of the data.  Two
+// buffers alternate by epoch parity: a block can only publish pass e+1 after it has read every block's pass e, i.e.
+// after every block has finished reading pass e-1, so the buffer of pass e-1 is free.  Epochs increase monotonically
+// across launches (host-tracked), the buffer is zeroed once at allocation and epochs start at 1, so a stale word never
+// matches.  The summation order is the fixed tree of reduce_partials: every block computes bit-identical sums.
+__device__ __forceinline__ void ll_store(ulonglong2* p, double v, unsigned int epoch) {
+    const u64 w0 = ((u64)epoch << 32) | (u64)(unsigned)__double2loint(v);
+    const u64 w1 = ((u64)epoch << 32) | (u64)(unsigned)__double2hiint(v);
+    asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(w0), "l"(w1) : "memory");
+}
+__device__ __forceinline__ void ll_load(const ulonglong2* p, u64& w0, u64& w1) {
+    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(p) : "memory");
+}
+
+__device__ __forceinline__ void write_block_partials_ll(const KnnArgs& a, KnnSmem& S, double acc, unsigned long long cand,
+                                                        ulonglong2* ll, unsigned int epoch) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane < kNormEq) S.red[warp][lane] = acc;
+    {
+        unsigned long long v = cand;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) S.red_cand[warp] = v;
+    }
+    __syncthreads();
+    const int G = gridDim.x;
+    if (threadIdx.x < kNormEq) {
+        double v = 0;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) v += S.red[w][threadIdx.x];
+        ll_store(ll + (size_t)threadIdx.x * G + blockIdx.x, v, epoch);      // scalar-major: [29][G]
+    }
+    if (threadIdx.x == 0 && a.cand_total) {
+        unsigned long long v = 0;
+        for (int w = 0; w < kWarps; ++w) v += S.red_cand[w];
+        if (v) atomicAdd(a.cand_total, v);
+    }
+    __syncthreads();       // S.red[0] is rewritten by reduce_ll
+}
+
+// Poll-and-sum: same 8-lanes-per-scalar layout and summation tree as reduce_partials; a lane re-loads only the words
+// whose epoch has not arrived yet.  The spin is capped (~seconds) so that a protocol bug shows up as a wrong result
+// in a test, never as a hung GPU.
+__device__ __forceinline__ void reduce_ll(const ulonglong2* ll, unsigned int epoch, KnnSmem& S) {
+    const int G = gridDim.x;
+    const int sc = threadIdx.x >> 3, l8 = threadIdx.x & 7;
+    double v = 0.0;
+    if (sc < kNormEq) {
+        const ulonglong2* src = ll + (size_t)sc * G;
+#pragma unroll 1
+        for (int base = l8; base < G; base += 8 * kRedLoads) {
+            u64 w0[kRedLoads], w1[kRedLoads];
+            unsigned int pending = 0;
+#pragma unroll
+            for (int j = 0; j < kRedLoads; ++j) { w0[j] = 0; w1[j] = 0; if (base + 8 * j < G) pending |= 1u << j; }
+            unsigned int spins = 0;
+            while (pending) {
+#pragma unroll
+                for (int j = 0; j < kRedLoads; ++j) if (pending & (1u << j)) ll_load(src + base + 8 * j, w0[j], w1[j]);
+#pragma unroll
+                for (int j = 0; j < kRedLoads; ++j)
+                    if ((pending & (1u << j)) && (unsigned int)(w0[j] >> 32) == epoch && (unsigned int)(w1[j] >> 32) == epoch) pending &= ~(1u << j);
+                if (++spins > (1u << 21)) pending = 0;      // safety valve (never taken in a correct run)
+            }
+            double w[kRedLoads];
+#pragma unroll
+            for (int j = 0; j < kRedLoads; ++j) w[j] = (base + 8 * j < G) ? __hiloint2double((int)(unsigned int)w1[j], (int)(unsigned int)w0[j]) : 0.0;
+#pragma unroll
+            for (int j = 0; j < 10; ++j) w[j] += w[j + 10];
+#pragma unroll
+            for (int j = 0; j < 5; ++j) w[j] += w[j + 5];
+            v += ((w[0] + w[1]) + (w[2] + w[3])) + w[4];
+        }
     }
     v += __shfl_xor_sync(0xffffffffu, v, 1);
     v += __shfl_xor_sync(0xffffffffu, v, 2);
@@ -490,7 +598,7 @@ __global__ void __launch_bounds__(kBlock, 4) k_knn_search(KnnArgs a) {
     }
 }
 
-template <int LANES>
+template <int LANES, bool FLAT = false>
 __global__ void __launch_bounds__(kBlock, 2) k_knn_plane(KnnArgs a) {
     __shared__ __align__(16) KnnSmem S;
     LILI_STAMP(0);
@@ -499,7 +607,7 @@ __global__ void __launch_bounds__(kBlock, 2) k_knn_plane(KnnArgs a) {
     const int n_q = a.n_dev ? min(*a.n_dev, a.n) : a.n;
     double acc = 0.0;
     unsigned long long cand = 0;
-    knn_phases<LANES>(a, q, t, n_q, S, acc, cand);
+    knn_phases<LANES, FLAT>(a, q, t, n_q, S, acc, cand);
     LILI_STAMP(3);
     write_block_partials(a, S, acc, cand);
     __threadfence();
@@ -537,9 +645,11 @@ __global__ void __launch_bounds__(kBlock, 2) k_knn_plane(KnnArgs a) {
 // grid barrier after publishing their partials; then EVERY block sums the partials and solves the 6x6
 // system redundantly (bit-identical), so no second barrier or broadcast is needed.  Removes the launch
 // gap, the drain and the ticket round trip of the per-iteration kernel (~6 us of ~18 per iteration).
-template <int LANES>
-__global__ void __launch_bounds__(kBlock, 2) k_gn_persistent(KnnArgs a, int iters, unsigned int* bar, double* stats_base, unsigned int bar_base) {
+template <int LANES, bool FLAT = false>
+__global__ void __launch_bounds__(kBlock, 2) k_gn_persistent(KnnArgs a, int iters, unsigned int* bar, double* stats_base, unsigned int bar_base,
+                                                             ulonglong2* ll, unsigned int ll_epoch0, unsigned int ll_stride) {
     __shared__ __align__(16) KnnSmem S;
+    extern __shared__ __align__(16) unsigned char dyn_smem[];   // flat == 2: [kFlatBatch][kBlock] float4 candidates + [kBlock] int4 tags
     const int n_q = a.n_dev ? min(*a.n_dev, a.n) : a.n;
     if (threadIdx.x < 7) S.pose[threadIdx.x] = a.pose[threadIdx.x];
     __syncthreads();
@@ -561,6 +671,13 @@ __global__ void __launch_bounds__(kBlock, 2) k_gn_persistent(KnnArgs a, int iter
             if (qi < n_q) f_keep = a.feats[qi];
         }
     }
+    // candidate cache (see group_knn5_flat): only when a lane group serves the same query in every iteration
+    float4* cc = nullptr; int4* cc_tag = nullptr;
+    if (FLAT && a.flat == 2 && keep) {
+        cc = reinterpret_cast<float4*>(dyn_smem) + threadIdx.x;
+        cc_tag = reinterpret_cast<int4*>(dyn_smem + (size_t)kFlatBatch * kBlock * sizeof(float4)) + threadIdx.x;
+        *cc_tag = make_int4(0, 0, 0, -1);
+    }
 #pragma unroll 1
     for (int it = 0; it < iters; ++it) {
         const Q4 q{S.pose[0], S.pose[1], S.pose[2], S.pose[3]};
@@ -569,23 +686,32 @@ __global__ void __launch_bounds__(kBlock, 2) k_gn_persistent(KnnArgs a, int iter
         unsigned long long cand = 0;
         const bool stamp = a.dbg && blockIdx.x == 0 && threadIdx.x == 0 && it == 2;
         if (stamp) a.dbg[16] = clock64();
-        knn_phases<LANES>(a, q, t, n_q, S, acc, cand, keep ? &f_keep : nullptr);
+        knn_phases<LANES, FLAT>(a, q, t, n_q, S, acc, cand, keep ? &f_keep : nullptr, cc, kBlock, cc_tag);
         if (stamp) a.dbg[17] = clock64();
-        write_block_partials(a, S, acc, cand);
-        // ---- grid barrier (generation counter; all blocks are co-resident: cooperative launch)
-        __threadfence();
-        __syncthreads();
-        if (stamp) a.dbg[18] = clock64();
-        if (threadIdx.x == 0) {
-            // monotonic arrival counter: no generation read, no reset inside the loop — one fire-and-forget RED plus polls
-            atomicAdd(bar, 1u);
-            const unsigned int target = bar_base + (unsigned int)(it + 1) * G;
-            while ((int)(*reinterpret_cast<volatile unsigned int*>(bar) - target) < 0) { }
+        if (ll) {
+            // ---- flag-in-data exchange: publishing is the arrival, polling is the load (see ll_store)
+            const unsigned int epoch = ll_epoch0 + (unsigned int)it;
+            ulonglong2* buf = ll + (size_t)(epoch & 1u) * ll_stride;
+            write_block_partials_ll(a, S, acc, cand, buf, epoch);
+            if (stamp) { a.dbg[18] = clock64(); a.dbg[19] = a.dbg[18]; }
+            reduce_ll(buf, epoch, S);
+        } else {
+            write_block_partials(a, S, acc, cand);
+            // ---- grid barrier (generation counter; all blocks are co-resident: cooperative launch)
             __threadfence();
+            __syncthreads();
+            if (stamp) a.dbg[18] = clock64();
+            if (threadIdx.x == 0) {
+                // monotonic arrival counter: no generation read, no reset inside the loop — one fire-and-forget RED plus polls
+                atomicAdd(bar, 1u);
+                const unsigned int target = bar_base + (unsigned int)(it + 1) * G;
+                while ((int)(*reinterpret_cast<volatile unsigned int*>(bar) - target) < 0) { }
+                __threadfence();
+            }
+            __syncthreads();
+            if (stamp) a.dbg[19] = clock64();
+            reduce_partials(a, S);
         }
-        __syncthreads();
-        if (stamp) a.dbg[19] = clock64();
-        reduce_partials(a, S);
         if (stamp) a.dbg[20] = clock64();
         double* stats = stats_base ? stats_base + (size_t)it * kStatsDoubles : nullptr;
         if (threadIdx.x == 0) {
@@ -900,6 +1026,7 @@ int s2m_run(liliom_ctx* c, double pose7[7], int match_cnt, int max_num_iter, int
     a.cand_total = c->time_kernels ? reinterpret_cast<unsigned long long*>(c->counter.as<unsigned char>() + 16) : nullptr;
     a.rounds = rounds; a.nranks = c->nranks; a.rank = c->rank;
     a.interleave = (lanes >= 8 && !getenv("LILIOM_NO_INTERLEAVE")) ? 1 : 0;
+    a.flat = lanes >= 16 ? c->knn_flat : 0;
     a.dbg = nullptr;
     if (getenv("LILIOM_DEBUG_TIMING")) {
         LILI_CUDA(c, c->lm_state.ensure(64 * sizeof(long long)));
@@ -917,8 +1044,21 @@ int s2m_run(liliom_ctx* c, double pose7[7], int match_cnt, int max_num_iter, int
         unsigned int* bar = reinterpret_cast<unsigned int*>(c->counter.as<unsigned char>() + 32);
         double* stats_base = c->stats_dev.as<double>();
         unsigned int bar_base = c->bar_arrivals;
-        void* kargs[] = {&a, &iters_arg, &bar, &stats_base, &bar_base};
-        const void* fn = lanes == 16 ? (const void*)k_gn_persistent<16> : lanes == 1 ? (const void*)k_gn_persistent<1>
+        ulonglong2* ll = nullptr;
+        unsigned int ll_epoch0 = 0, ll_stride = (unsigned int)kNormEq * (unsigned int)(2 * c->sm_count);
+        if (c->gn_ll) {
+            if (!c->ll_buf.p) {      // zeroed once: epochs start at 1 and only grow, a stale word never matches
+                LILI_CUDA(c, c->ll_buf.ensure((size_t)2 * ll_stride * sizeof(ulonglong2)));
+                LILI_CUDA(c, cudaMemsetAsync(c->ll_buf.p, 0, c->ll_buf.cap, c->stream));
+                c->ll_epoch = 0;
+            }
+            ll = c->ll_buf.as<ulonglong2>();
+            ll_epoch0 = c->ll_epoch + 1u;
+            c->ll_epoch += (unsigned int)iters;
+        }
+        void* kargs[] = {&a, &iters_arg, &bar, &stats_base, &bar_base, &ll, &ll_epoch0, &ll_stride};
+        const void* fn = (lanes == 16 && a.flat) ? (const void*)k_gn_persistent<16, true>
+                       : lanes == 16 ? (const void*)k_gn_persistent<16> : lanes == 1 ? (const void*)k_gn_persistent<1>
                        : lanes == 2 ? (const void*)k_gn_persistent<2> : lanes == 4 ? (const void*)k_gn_persistent<4>
                                                                                    : (const void*)k_gn_persistent<8>;
         size_t ev = 0;
@@ -929,9 +1069,17 @@ int s2m_run(liliom_ctx* c, double pose7[7], int match_cnt, int max_num_iter, int
             ev = c->ev_used; c->ev_used += 2;
             LILI_CUDA(c, cudaEventRecord(c->ev_pool[ev], c->stream));
         }
-        LILI_CUDA(c, cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kBlock), kargs, 0, c->stream));
+        size_t dyn = 0;
+        if (a.flat == 2) {
+            dyn = (size_t)kFlatBatch * kBlock * sizeof(float4) + (size_t)kBlock * sizeof(int4);
+            if (!c->gn_smem_set) {
+                LILI_CUDA(c, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+                c->gn_smem_set = true;
+            }
+        }
+        LILI_CUDA(c, cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kBlock), kargs, dyn, c->stream));
         LILI_TRY(launch_check(c, "k_gn_persistent"));
-        c->bar_arrivals += (unsigned int)iters * (unsigned int)grid;
+        if (!ll) c->bar_arrivals += (unsigned int)iters * (unsigned int)grid;
         if (c->time_kernels) {
             LILI_CUDA(c, cudaEventRecord(c->ev_pool[ev + 1], c->stream));
             c->ev_pending.push_back({ev, (unsigned long long)n_est * iters});
@@ -965,7 +1113,8 @@ int s2m_run(liliom_ctx* c, double pose7[7], int match_cnt, int max_num_iter, int
             k_knn_plane<1><<<grid, kBlock, 0, c->stream>>>(a);
             a.fit_only = 0;
             a.cand_total = sa.cand_total;
-        } else if (lanes == 16) k_knn_plane<16><<<grid, kBlock, 0, c->stream>>>(a);
+        } else if (lanes == 16 && a.flat) k_knn_plane<16, true><<<grid, kBlock, 0, c->stream>>>(a);
+        else if (lanes == 16) k_knn_plane<16><<<grid, kBlock, 0, c->stream>>>(a);
         else if (lanes == 1) k_knn_plane<1><<<grid, kBlock, 0, c->stream>>>(a);
         else if (lanes == 2) k_knn_plane<2><<<grid, kBlock, 0, c->stream>>>(a);
         else if (lanes == 4) k_knn_plane<4><<<grid, kBlock, 0, c->stream>>>(a);

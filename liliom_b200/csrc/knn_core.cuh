@@ -133,4 +133,117 @@ __device__ __forceinline__ void group_knn5(float sx, float sy, float sz, const f
     }
 }
 
+
+// ---- flat variant for the latency-bound small-scan shape (LANES == 16: two queries per warp) -------------------
+// group_knn5 gives lane r the whole run r, so a query costs max-run-length ranking steps and lanes 9..15 idle
+// (measured on B200, 1.7k queries: 5.3k of a 13k-cycle pass in "candidates + rank").  Here the 9 run bounds are
+// shared through shuffles and the concatenated candidate list is dealt round-robin: lane `sub` ranks candidates
+// sub, sub+LANES, ... — ceil(T/LANES) steps instead of the longest run, one batch of independent 16-byte loads per
+// lane for T <= 8*LANES, consecutive lanes reading consecutive map points.  The candidate SET is unchanged, so the
+// merged top-5 is bit-identical to group_knn5's.
+// `cc` (optional, per-thread slots in shared memory): a lane's batch is kept across the GN iterations of the
+// persistent kernel; while the transformed query stays in the same cell the bounds + candidate loads (two dependent
+// L2 round trips) are skipped.  cc_tag holds the cell the cache was filled for (tag.w < 0: empty / not cacheable).
+constexpr int kFlatBatch = 8;
+
+template <int LANES>
+__device__ __forceinline__ void group_knn5_flat(float sx, float sy, float sz, const float4* __restrict__ map,
+                                                const int* __restrict__ cell_start, const GridDesc& g, int sub, unsigned gmask,
+                                                Top5& top, unsigned long long& cand, float4* cc, int cc_stride, int4* cc_tag,
+                                                float4* nb_out = nullptr, int* nb_flag = nullptr) {
+    static_assert(LANES >= 16, "one lane per (y,z) row of the 3x3x3 block");
+    const int cx = cell_coord(sx, g.inv_cell) - g.org[0];
+    const int cy = cell_coord(sy, g.inv_cell) - g.org[1];
+    const int cz = cell_coord(sz, g.inv_cell) - g.org[2];
+    float4 c[kFlatBatch];
+    int nmine = 0, T = 0;
+    int rb[9], pre[10];
+    const bool reuse = cc_tag && cc_tag->w >= 0 && cc_tag->x == cx && cc_tag->y == cy && cc_tag->z == cz;   // uniform in the group
+    if (reuse) {
+        nmine = cc_tag->w;
+#pragma unroll
+        for (int i = 0; i < kFlatBatch; ++i) if (i < nmine) c[i] = cc[i * cc_stride];
+    } else {
+        const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.dim[0] - 1);
+        int b = 0, len = 0;
+        if (sub < 9 && x0 <= x1) {
+            const int y = cy + (sub % 3) - 1, z = cz + (sub / 3) - 1;
+            if (y >= 0 && y < g.dim[1] && z >= 0 && z < g.dim[2]) {
+                const int base = (z * g.dim[1] + y) * g.dim[0];
+                b = __ldg(cell_start + base + x0);
+                len = __ldg(cell_start + base + x1 + 1) - b;
+            }
+        }
+        pre[0] = 0;
+#pragma unroll
+        for (int r = 0; r < 9; ++r) {
+            rb[r] = __shfl_sync(gmask, b, r, LANES);
+            pre[r + 1] = pre[r] + __shfl_sync(gmask, len, r, LANES);
+        }
+        T = pre[9];
+    }
+#pragma unroll 1
+    for (int j0 = sub;; j0 += LANES * kFlatBatch) {
+        if (!reuse) {
+            nmine = 0;
+#pragma unroll
+            for (int i = 0; i < kFlatBatch; ++i) {
+                const int j = j0 + i * LANES;
+                if (j < T) {
+                    int pos = rb[0] + j;
+#pragma unroll
+                    for (int r = 1; r < 9; ++r) if (j >= pre[r]) pos = rb[r] + (j - pre[r]);   // last row whose prefix <= j
+                    c[i] = __ldg(map + pos);
+                    nmine = i + 1;
+                }
+            }
+            if (cc_tag && j0 == sub) {      // first batch: cacheable when it is also the only one
+                if (T <= LANES * kFlatBatch) {
+#pragma unroll
+                    for (int i = 0; i < kFlatBatch; ++i) if (i < nmine) cc[i * cc_stride] = c[i];
+                    *cc_tag = make_int4(cx, cy, cz, nmine);
+                } else cc_tag->w = -1;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < kFlatBatch; ++i) if (i < nmine) top5_insert(top, make_key(sx, sy, sz, c[i]));
+        cand += (unsigned long long)nmine;
+        if (reuse || j0 - sub + LANES * kFlatBatch >= T) break;     // group-uniform: T and reuse are
+    }
+    // merge (same as group_knn5)
+    Top5 res;
+#define LILI_MERGE_ROUND(KJ)                                                              \
+    {                                                                                     \
+        u64 mn = top.k0;                                                                  \
+        _Pragma("unroll")                                                                 \
+        for (int o = 1; o < LANES; o <<= 1) { const u64 other = __shfl_xor_sync(gmask, mn, o); mn = other < mn ? other : mn; } \
+        KJ = mn;                                                                          \
+        if (top.k0 == mn && mn != ~0ull) { top.k0 = top.k1; top.k1 = top.k2; top.k2 = top.k3; top.k3 = top.k4; top.k4 = ~0ull; } \
+    }
+    LILI_MERGE_ROUND(res.k0)
+    LILI_MERGE_ROUND(res.k1)
+    LILI_MERGE_ROUND(res.k2)
+    LILI_MERGE_ROUND(res.k3)
+    LILI_MERGE_ROUND(res.k4)
+#undef LILI_MERGE_ROUND
+    top = res;
+    // Hand the winners' coordinates to the plane fit through shared memory: the lane that loaded a winning candidate
+    // still holds it in registers (single-batch case), so the fit does not have to fetch the 5 neighbours from L2 again
+    // (the cell-sorted copy and map_download order hold the same coordinates).  nb_flag = 1 tells phase B to use them.
+    if (nb_out) {
+        const bool single = reuse || T <= LANES * kFlatBatch;      // group-uniform
+        if (single) {
+#pragma unroll
+            for (int i = 0; i < kFlatBatch; ++i) {
+                if (i < nmine) {
+                    const u64 k = make_key(sx, sy, sz, c[i]);
+                    const int j = k == res.k0 ? 0 : k == res.k1 ? 1 : k == res.k2 ? 2 : k == res.k3 ? 3 : k == res.k4 ? 4 : -1;
+                    if (j >= 0) nb_out[j] = c[i];
+                }
+            }
+        }
+        if (sub == 0) *nb_flag = single ? 1 : 0;
+    }
+}
+
 }  // namespace lili

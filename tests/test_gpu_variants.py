@@ -1,0 +1,78 @@
+"""The latency variants of the small-scan GN kernel must not change a single bit:
+  LILIOM_KNN_FLAT = 0 one run per lane | 1 candidates dealt round-robin over the 16 lanes | 2 + per-iteration candidate cache
+  LILIOM_GN_LL    = 0 counter grid barrier | 1 flag-in-data exchange of the block partials
+Same candidate sets, same per-row arithmetic, same summation trees -> identical poses, correspondences and sums."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+VARIANTS = [(0, 0), (1, 0), (2, 0), (0, 1), (1, 1), (2, 1)]
+
+
+def _ctx(flat, ll):
+    import liliom_b200 as L
+    old = {k: os.environ.get(k) for k in ("LILIOM_KNN_FLAT", "LILIOM_GN_LL")}
+    os.environ["LILIOM_KNN_FLAT"] = str(flat); os.environ["LILIOM_GN_LL"] = str(ll)
+    try:
+        return L.Context(variant=0)          # the switches are read at liliom_create
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+def test_gn_variants_bit_identical(oracle, world_small):
+    import liliom_b200 as L
+    surf, _, _ = oracle.extract_horizon(world_small["hz"], world_small["q_hz"])
+    ds = oracle.voxelgrid(surf, 0.4)
+    guess = world_small["guess"]
+    # scans of different sizes back to back: the grid size (and the LL layout stride) changes between launches,
+    # the last one is large enough to leave the 16-lane shape (flat does not apply there)
+    scans = [ds, ds[: len(ds) // 3], ds[::2], ds[:40], surf[:6000], ds]
+    ref = None
+    for flat, ll in VARIANTS:
+        c = _ctx(flat, ll)
+        c.map_set_points(world_small["map"])
+        out = []
+        for f in scans:
+            for iters in (10, 3):
+                pose, st = c.scan_to_map(f, guess, iters, mode=L.MODE_GN)
+                out.append((pose.copy(), [np.array(s.jtj_jtr) for s in st], [s.n_corr for s in st], [s.cost for s in st]))
+        v, pl, idx, sqd, s29 = c.find_surf_corr(ds, guess)          # k_knn_plane<16> (ticket path), flat or not
+        out.append((s29.copy(), [pl.copy()], [idx.copy(), v.copy()], [sqd.copy()]))
+        c.close()
+        if ref is None:
+            ref = out
+            rc, pose_o, _ = oracle.scan_to_map_gn(oracle.KdTree(world_small["map"]), ds, guess, 10)
+            assert np.linalg.norm(out[0][0][4:] - pose_o[4:]) < 1e-4
+            continue
+        for k, (a, b) in enumerate(zip(out, ref)):
+            assert a[0].tobytes() == b[0].tobytes(), (flat, ll, k, a[0], b[0])
+            for x, y in zip(a[1] + a[3], b[1] + b[3]):
+                assert np.asarray(x).tobytes() == np.asarray(y).tobytes(), (flat, ll, k)
+            for x, y in zip(a[2], b[2]):
+                assert np.array_equal(x, y), (flat, ll, k)
+
+
+def test_gn_variants_resident_pipeline(oracle, world_small):
+    """Through the node-facing call (extract -> VoxelGrid -> persistent GN with the device-side query count)."""
+    import liliom_b200 as L
+    ref = None
+    for flat, ll in VARIANTS:
+        c = _ctx(flat, ll)
+        c.map_set_points(world_small["map"])
+        poses = []
+        for k in range(4):
+            surf, edge, cut = c.extract_horizon(world_small["hz"], world_small["q_hz"])
+            pose, st, ds = c.odometry_resident(world_small["guess"], 10, mode=L.MODE_GN, want_ds=True, cap=len(surf))
+            poses.append(pose.copy())
+        c.close()
+        assert all(p.tobytes() == poses[0].tobytes() for p in poses)            # run-to-run deterministic
+        if ref is None:
+            ref = poses[0]
+        assert poses[0].tobytes() == ref.tobytes(), (flat, ll)
