@@ -11,7 +11,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libliliom_b200.so")
+# LILIOM_LIB: tuning builds of the same CUDA library (tools/ab_variants.py); the product is libliliom_b200.so
+LIB_PATH = os.environ.get("LILIOM_LIB") or os.path.join(_HERE, "libliliom_b200.so")
 
 # numpy mirrors of the PCL layouts (include/liliom.h)
 PT48 = np.dtype([("x", "f4"), ("y", "f4"), ("z", "f4"), ("w", "f4"),

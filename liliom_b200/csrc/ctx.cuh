@@ -138,7 +138,7 @@ struct liliom_ctx {
     bool time_kernels = false;
     int force_lanes = 0, force_rounds = 0;   // tuning override (LILIOM_KNN_LANES / LILIOM_KNN_ROUNDS)
     int knn_flat = 0;                    // 16-lane search shape: 0 = one run per lane, 1 = round-robin candidates, 2 = + per-iteration cache (LILIOM_KNN_FLAT)
-    int gn_ll = 0;                       // persistent GN kernel: 1 = flag-in-data exchange of the block partials instead of the counter barrier (LILIOM_GN_LL)
+    int gn_ll = 0;                       // persistent GN kernel grid sync (LILIOM_GN_SYNC): 0 counter barrier | 1 flag-in-data exchange | 2 same, staged poll | 3 counter, release-only
     lili::DevBuf ll_buf;                 // two epoch-parity buffers of [29][2*sm_count] {epoch|lo32, epoch|hi32}
     unsigned int ll_epoch = 0;           // last epoch issued
     bool gn_smem_set = false;            // cudaFuncAttributeMaxDynamicSharedMemorySize raised for k_gn_persistent<16> on this device

@@ -492,6 +492,25 @@ __device__ __forceinline__ void write_block_partials_ll(const KnnArgs& a, KnnSme
     __syncthreads();       // S.red[0] is rewritten by reduce_ll
 }
 
+// Staged variant (LILIOM_GN_SYNC=2): with every thread of every block polling, ~0.5 M 16-byte loads per round hit the L2
+// while the slowest blocks still need it for their search (measured: slower than the counter barrier).  Stage 1: thread b
+// watches ONE word of block b (the last scalar) with a short back-off; when all have shown up, stage 2 is reduce_ll, whose
+// per-word epoch check still covers words that became visible out of order.
+__device__ __forceinline__ void ll_wait_arrivals(const ulonglong2* ll, unsigned int epoch) {
+    const int G = gridDim.x;
+    for (int b = threadIdx.x; b < G; b += blockDim.x) {
+        const ulonglong2* p = ll + (size_t)(kNormEq - 1) * G + b;
+        u64 w0, w1;
+        unsigned int spins = 0;
+        while (true) {
+            ll_load(p, w0, w1);
+            if (((unsigned int)(w0 >> 32) == epoch && (unsigned int)(w1 >> 32) == epoch) || ++spins > (1u << 20)) break;
+            __nanosleep(40);
+        }
+    }
+    __syncthreads();
+}
+
 // Poll-and-sum: same 8-lanes-per-scalar layout and summation tree as reduce_partials; a lane re-loads only the words
 // whose epoch has not arrived yet.  The spin is capped (~seconds) so that a protocol bug shows up as a wrong result
 // in a test, never as a hung GPU.
@@ -645,9 +664,17 @@ __global__ void __launch_bounds__(kBlock, 2) k_knn_plane(KnnArgs a) {
 // grid barrier after publishing their partials; then EVERY block sums the partials and solves the 6x6
 // system redundantly (bit-identical), so no second barrier or broadcast is needed.  Removes the launch
 // gap, the drain and the ticket round trip of the per-iteration kernel (~6 us of ~18 per iteration).
+// The persistent kernel never runs more than one block per SM (grid <= sm_count).  LILI_GN_MAXNREG (build-time experiment)
+// trades the 128-register cap of __launch_bounds__(256, 2) for a higher one: no spills, while a 64-register block of the
+// Preprocessing node's cooperative kernel still fits beside it (176 * 256 + 64 * 256 <= 65536 registers).
+#ifdef LILI_GN_MAXNREG
+#define LILI_GN_BOUNDS __maxnreg__(LILI_GN_MAXNREG)
+#else
+#define LILI_GN_BOUNDS __launch_bounds__(kBlock, 2)
+#endif
 template <int LANES, bool FLAT = false>
-__global__ void __launch_bounds__(kBlock, 2) k_gn_persistent(KnnArgs a, int iters, unsigned int* bar, double* stats_base, unsigned int bar_base,
-                                                             ulonglong2* ll, unsigned int ll_epoch0, unsigned int ll_stride) {
+__global__ void LILI_GN_BOUNDS k_gn_persistent(KnnArgs a, int iters, unsigned int* bar, double* stats_base, unsigned int bar_base,
+                                                             ulonglong2* ll, unsigned int ll_epoch0, unsigned int ll_stride, int sync_mode) {
     __shared__ __align__(16) KnnSmem S;
     extern __shared__ __align__(16) unsigned char dyn_smem[];   // flat == 2: [kFlatBatch][kBlock] float4 candidates + [kBlock] int4 tags
     const int n_q = a.n_dev ? min(*a.n_dev, a.n) : a.n;
@@ -693,8 +720,27 @@ __global__ void __launch_bounds__(kBlock, 2) k_gn_persistent(KnnArgs a, int iter
             const unsigned int epoch = ll_epoch0 + (unsigned int)it;
             ulonglong2* buf = ll + (size_t)(epoch & 1u) * ll_stride;
             write_block_partials_ll(a, S, acc, cand, buf, epoch);
-            if (stamp) { a.dbg[18] = clock64(); a.dbg[19] = a.dbg[18]; }
+            if (stamp) a.dbg[18] = clock64();
+            if (sync_mode == 2) ll_wait_arrivals(buf, epoch);
+            if (stamp) a.dbg[19] = clock64();
             reduce_ll(buf, epoch, S);
+        } else if (sync_mode == 3) {
+            // ---- counter barrier with the minimum of fences (experiment): one release by thread 0 after the block barrier
+            // (cumulative over bar.sync, as in cooperative groups' grid.sync) and NO acquire fence after the poll.  The acquire
+            // would only invalidate L1; everything this kernel reads through L1 (map, cell table, features) is immutable for
+            // the launch, and the partials are read with L2-scope loads (__ldcg).
+            write_block_partials(a, S, acc, cand);
+            __syncthreads();
+            if (stamp) a.dbg[18] = clock64();
+            if (threadIdx.x == 0) {
+                asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(bar), "r"(1u) : "memory");
+                const unsigned int target = bar_base + (unsigned int)(it + 1) * G;
+                unsigned int v;
+                do { asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory"); } while ((int)(v - target) < 0);
+            }
+            __syncthreads();
+            if (stamp) a.dbg[19] = clock64();
+            reduce_partials(a, S);
         } else {
             write_block_partials(a, S, acc, cand);
             // ---- grid barrier (generation counter; all blocks are co-resident: cooperative launch)
@@ -1046,7 +1092,8 @@ int s2m_run(liliom_ctx* c, double pose7[7], int match_cnt, int max_num_iter, int
         unsigned int bar_base = c->bar_arrivals;
         ulonglong2* ll = nullptr;
         unsigned int ll_epoch0 = 0, ll_stride = (unsigned int)kNormEq * (unsigned int)(2 * c->sm_count);
-        if (c->gn_ll) {
+        int sync_mode = c->gn_ll;      // 0 counter barrier | 1 flag-in-data, all threads poll | 2 flag-in-data, staged poll | 3 counter, release-only
+        if (sync_mode == 1 || sync_mode == 2) {
             if (!c->ll_buf.p) {      // zeroed once: epochs start at 1 and only grow, a stale word never matches
                 LILI_CUDA(c, c->ll_buf.ensure((size_t)2 * ll_stride * sizeof(ulonglong2)));
                 LILI_CUDA(c, cudaMemsetAsync(c->ll_buf.p, 0, c->ll_buf.cap, c->stream));
@@ -1056,7 +1103,7 @@ int s2m_run(liliom_ctx* c, double pose7[7], int match_cnt, int max_num_iter, int
             ll_epoch0 = c->ll_epoch + 1u;
             c->ll_epoch += (unsigned int)iters;
         }
-        void* kargs[] = {&a, &iters_arg, &bar, &stats_base, &bar_base, &ll, &ll_epoch0, &ll_stride};
+        void* kargs[] = {&a, &iters_arg, &bar, &stats_base, &bar_base, &ll, &ll_epoch0, &ll_stride, &sync_mode};
         const void* fn = (lanes == 16 && a.flat) ? (const void*)k_gn_persistent<16, true>
                        : lanes == 16 ? (const void*)k_gn_persistent<16> : lanes == 1 ? (const void*)k_gn_persistent<1>
                        : lanes == 2 ? (const void*)k_gn_persistent<2> : lanes == 4 ? (const void*)k_gn_persistent<4>

@@ -1,6 +1,6 @@
 """The latency variants of the small-scan GN kernel must not change a single bit:
   LILIOM_KNN_FLAT = 0 one run per lane | 1 candidates dealt round-robin over the 16 lanes | 2 + per-iteration candidate cache
-  LILIOM_GN_LL    = 0 counter grid barrier | 1 flag-in-data exchange of the block partials
+  LILIOM_GN_SYNC  = 0 counter grid barrier | 1 flag-in-data exchange of the block partials | 2 same with a staged poll | 3 counter barrier, release-only
 Same candidate sets, same per-row arithmetic, same summation trees -> identical poses, correspondences and sums."""
 import os
 
@@ -9,13 +9,13 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
-VARIANTS = [(0, 0), (1, 0), (2, 0), (0, 1), (1, 1), (2, 1)]
+VARIANTS = [(0, 0), (1, 0), (2, 0), (0, 1), (2, 1), (0, 2), (2, 2), (0, 3), (1, 3)]
 
 
 def _ctx(flat, ll):
     import liliom_b200 as L
-    old = {k: os.environ.get(k) for k in ("LILIOM_KNN_FLAT", "LILIOM_GN_LL")}
-    os.environ["LILIOM_KNN_FLAT"] = str(flat); os.environ["LILIOM_GN_LL"] = str(ll)
+    old = {k: os.environ.get(k) for k in ("LILIOM_KNN_FLAT", "LILIOM_GN_SYNC")}
+    os.environ["LILIOM_KNN_FLAT"] = str(flat); os.environ["LILIOM_GN_SYNC"] = str(ll)
     try:
         return L.Context(variant=0)          # the switches are read at liliom_create
     finally:
