@@ -53,6 +53,9 @@ def parse():
     ap.add_argument("--e2e", default="two-nodes", choices=["two-nodes", "sequential"],
                     help="e2e leg: two concurrent node threads (reference architecture, default) or one thread calling both nodes in turn")
     ap.add_argument("--dense-queries", action="store_true", help="roofline micro-run: every surf feature is a query (no scan DS)")
+    ap.add_argument("--workload", default="horizon", choices=["horizon", "rot"],
+                    help="horizon: BASELINE configs[1] (24k-pt Livox sweep, 1 M-pt map; the metric's config, default); "
+                         "rot: configs[2] (130k-pt HDL-64E sweep through the LiLi-OM-ROT extractor, 2 M-pt map)")
     return ap.parse_args()
 
 
@@ -180,9 +183,18 @@ def make_workload(n_map: int, n_sweeps: int, variant: int = 0):
     return m, sweeps
 
 
+def workload_name(rot, n_returns, n_map):
+    if rot:
+        return f"130k-pt HDL-64E sweep ({n_returns} returns, LiLi-OM-ROT extractor, ds_rate 4) vs {n_map}-pt voxel map, {ITERS} GN iters"
+    return f"24k-pt Livox-Horizon sweep ({n_returns} returns) vs {n_map}-pt voxel map, {ITERS} GN iters"
+
+
 # ---------------------------------------------------------------------------------------------- CPU oracle legs
 def cpu_scan(O, tree, sw, nthreads):
-    surf, edge, cut = O.extract_horizon(sw["pts"], sw["q"])
+    if sw["pts"].dtype.itemsize == 32:      # ROT package (configs[2])
+        rc, surf, edge, cut, _, _ = O.extract_rot(sw["pts"], sw["q"], (1.0, 0, 0, 0), 64, 4)
+    else:
+        surf, edge, cut = O.extract_horizon(sw["pts"], sw["q"])
     ds = O.voxelgrid(surf, 0.4)
     rc, pose, st = O.scan_to_map_gn(tree, ds, sw["guess"], ITERS, nthreads)
     return pose, len(ds)
@@ -195,8 +207,9 @@ def run_reference(args):
         return
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib as O
-    n_map = args.map_points or 1_000_000
-    m, sweeps = make_workload(n_map, min(args.sweeps, 4))
+    rot = args.workload == "rot"
+    n_map = args.map_points or (2_000_000 if rot else 1_000_000)
+    m, sweeps = make_workload(n_map, min(args.sweeps, 4), 1 if rot else 0)
     t0 = time.perf_counter(); tree = O.KdTree(m); t_build = time.perf_counter() - t0
     cores = os.cpu_count() or 1
     # pick the faster of 1 thread / all threads on one probe scan (OpenMP over queries can lose on shared hosts)
@@ -219,7 +232,7 @@ def run_reference(args):
             "warmup": min(args.warmup, 2), "ms_per_step": 1e3 * dt / steps, "higher_is_better": True,
             "scaling": "strong" if args.multi == "sharded" else "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"24k-pt Livox-Horizon sweep ({len(sweeps[0]['pts'])} returns) vs {n_map}-pt voxel map, {ITERS} GN iters",
+            "config": {"workload": workload_name(rot, len(sweeps[0]['pts']), n_map),
                        "map_points": n_map, "iters": ITERS,
                        "impl_note": "CPU oracle port of the reference path (oracle/): the reference itself needs ROS/PCL/Eigen/Ceres and cannot be "
                                     "built in this image; best of {1,2,4,8,16,32,all} OpenMP threads over the queries"},
@@ -265,13 +278,16 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     sharded = multi and args.multi == "sharded"
-    n_map = args.map_points or (5_000_000 if sharded else 1_000_000)
+    rot = args.workload == "rot"
+    n_map = args.map_points or (5_000_000 if sharded else 2_000_000 if rot else 1_000_000)
 
-    m, sweeps = make_workload(n_map, args.sweeps)
+    m, sweeps = make_workload(n_map, args.sweeps, 1 if rot else 0)
     if multi and not sharded:     # replicas: every rank gets its own scan stream
         sweeps = sweeps[rank % len(sweeps):] + sweeps[:rank % len(sweeps)]
 
-    prm = L.default_params(0)
+    prm = L.default_params(1 if rot else 0)
+    PT = L.PT32 if rot else L.PT48
+    psz = PT.itemsize
     if args.dense_queries:
         prm.leaf_scan = 0.0        # no scan down-sampling: every surf feature is a query (roofline micro-run)
     ctx = L.Context(prm, device=local_rank)
@@ -288,12 +304,17 @@ def main():
     pin_sweeps = []
     for sw in sweeps:
         t = torch.from_numpy(sw["pts"].view(np.uint8).reshape(-1)).pin_memory()
-        pin_sweeps.append(t.numpy().view(L.PT48))
+        pin_sweeps.append(t.numpy().view(PT))
     cap = max(len(s["pts"]) for s in sweeps)
-    out_surf = torch.empty(cap * 48, dtype=torch.uint8).pin_memory().numpy().view(L.PT48)
-    out_edge = torch.empty(cap * 48, dtype=torch.uint8).pin_memory().numpy().view(L.PT48)
-    out_cut = torch.empty(cap * 48, dtype=torch.uint8).pin_memory().numpy().view(L.PT48)
-    out_ds = torch.empty(cap * 48, dtype=torch.uint8).pin_memory().numpy().view(L.PT48)
+    out_surf = torch.empty(cap * psz, dtype=torch.uint8).pin_memory().numpy().view(PT)
+    out_edge = torch.empty(cap * psz, dtype=torch.uint8).pin_memory().numpy().view(PT)
+    out_cut = torch.empty(cap * psz, dtype=torch.uint8).pin_memory().numpy().view(PT)
+    out_ds = torch.empty(cap * psz, dtype=torch.uint8).pin_memory().numpy().view(PT)
+
+    def extract_host(cx, i, out):
+        if rot:
+            return cx.extract_rot(pin_sweeps[i], sweeps[i]["q"], out=out)
+        return cx.extract_horizon(pin_sweeps[i], sweeps[i]["q"], out=out)
     pose_buf = torch.empty(7, dtype=torch.float64).pin_memory().numpy()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")     # > 126 MB L2
 
@@ -311,11 +332,11 @@ def main():
     def step_e2e(k):
         i = k % len(sweeps)
         # Preprocessing node call: H2D raw sweep, D2H the three published clouds (pinned host buffers)
-        surf, edge, cut = ctx.extract_horizon(pin_sweeps[i], sweeps[i]["q"], out=(out_surf, out_edge, out_cut))
+        surf, edge, cut = extract_host(ctx, i, (out_surf, out_edge, out_cut))
         # LidarOdometry node call on the /surf_features cloud as received (host): H2D, D2H pose + surf_last_ds
         pose, st, ds = ctx.odometry(surf, sweeps[i]["guess"], ITERS, mode=L.MODE_GN, ds_out=out_ds, pose_out=pose_buf, want_stats=False)
-        h2d = len(pin_sweeps[i]) * 48 + len(surf) * 48 + 56
-        d2h = (len(surf) + len(edge) + len(cut)) * 48 + len(ds) * 48 + 56
+        h2d = len(pin_sweeps[i]) * psz + len(surf) * psz + 56
+        d2h = (len(surf) + len(edge) + len(cut)) * psz + len(ds) * psz + 56
         return pose, h2d, d2h
 
     def e2e_two_nodes(steps, warmup):
@@ -332,7 +353,7 @@ def main():
         s_lo = torch.cuda.Stream(priority=-1) if os.environ.get("LILIOM_BENCH_PRIO", "1") == "1" else stream
         ctx.set_stream(s_lo.cuda_stream)
         nbuf = 3
-        sets = [[torch.empty(cap * 48, dtype=torch.uint8).pin_memory().numpy().view(L.PT48) for _ in range(3)] for _ in range(nbuf)]
+        sets = [[torch.empty(cap * psz, dtype=torch.uint8).pin_memory().numpy().view(PT) for _ in range(3)] for _ in range(nbuf)]
         ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
         result = {}
 
@@ -347,7 +368,7 @@ def main():
                 with torch.cuda.stream(s_flush if flush_mode == "side" else s_pre):
                     flush.fill_(k & 0xff)
             t1 = time.perf_counter()
-            surf, edge, cut = ctx_pre.extract_horizon(pin_sweeps[i], sweeps[i]["q"], out=tuple(sets[b]))
+            surf, edge, cut = extract_host(ctx_pre, i, tuple(sets[b]))
             diag["fill"] += t1 - t0; diag["a"] += time.perf_counter() - t1
             return (len(surf), len(edge), len(cut))
 
@@ -361,7 +382,7 @@ def main():
             if want_diag:
                 eb.record(s_lo); ev_pairs.append((ea, eb))
             diag["b"] += time.perf_counter() - t0
-            result.update(pose=np.array(pose), h2d=len(pin_sweeps[i]) * 48 + ns * 48 + 56, d2h=(ns + ne + nc) * 48 + len(ds) * 48 + 56)
+            result.update(pose=np.array(pose), h2d=len(pin_sweeps[i]) * psz + ns * psz + 56, d2h=(ns + ne + nc) * psz + len(ds) * psz + 56)
 
         barrier()
         run_two_stage_pipeline(warmup + steps, warmup, nbuf, stage_a, stage_b,
@@ -453,13 +474,13 @@ def main():
         if multi:
             dist.destroy_process_group()
         return
-    cpu = None if args.no_cpu_baseline or multi else cpu_baseline_leg(m if n_map <= 1_000_000 else m[:1_000_000], sweeps[:4])
+    cpu = None if args.no_cpu_baseline or multi else cpu_baseline_leg(m, sweeps[:4])
     pose, nq = last
     line = {
         "metric": METRIC, "value": value, "unit": "scans/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_res / args.steps, "higher_is_better": True,
         "scaling": "strong" if args.multi == "sharded" else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": (f"24k-pt Livox-Horizon sweep ({len(sweeps[0]['pts'])} returns) vs {n_map}-pt voxel map, {ITERS} GN iters"
+        "config": {"workload": (workload_name(rot, len(sweeps[0]['pts']), n_map)
                                 + (", map sharded by 8 m block hash + 29-scalar NCCL all-reduce per iteration" if sharded else "")
                                 + (", independent scan stream per GPU" if (multi and not sharded) else "")),
                    "map_points": n_map, "iters": ITERS, "queries_per_scan": int(nq), "dense_queries": bool(args.dense_queries),

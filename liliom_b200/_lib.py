@@ -201,11 +201,14 @@ class Context:
                                                  _ptr(edge), len(edge), C.byref(ne), _ptr(cut), len(cut), C.byref(nc)))
         return surf[:ns.value], edge[:ne.value], cut[:nc.value]
 
-    def extract_rot(self, pts: np.ndarray, q_imu, q_lb=(1.0, 0.0, 0.0, 0.0)):
+    def extract_rot(self, pts: np.ndarray, q_imu, q_lb=(1.0, 0.0, 0.0, 0.0), out=None):
         pts = np.ascontiguousarray(pts, dtype=PT32)
         n = len(pts)
         q = np.asarray(q_imu, dtype=np.float64); ql = np.asarray(q_lb, dtype=np.float64)
-        surf = np.empty(max(n, 1), PT32); edge = np.empty(max(n, 1), PT32); cut = np.empty(max(n, 1), PT32)
+        if out is None:
+            surf = np.empty(max(n, 1), PT32); edge = np.empty(max(n, 1), PT32); cut = np.empty(max(n, 1), PT32)
+        else:
+            surf, edge, cut = out
         ns, ne, nc = C.c_int(), C.c_int(), C.c_int()
         self._check(lib().liliom_extract_rot(self._h, _ptr(pts), n, _dptr(q), _dptr(ql), _ptr(surf), len(surf), C.byref(ns),
                                              _ptr(edge), len(edge), C.byref(ne), _ptr(cut), len(cut), C.byref(nc)))

@@ -138,9 +138,8 @@ struct liliom_ctx {
     bool time_kernels = false;
     int force_lanes = 0, force_rounds = 0;   // tuning override (LILIOM_KNN_LANES / LILIOM_KNN_ROUNDS)
     int knn_flat = 0;                    // 16-lane search shape: 0 = one run per lane, 1 = round-robin candidates, 2 = + per-iteration cache (LILIOM_KNN_FLAT)
-    int gn_ll = 0;                       // persistent GN kernel grid sync (LILIOM_GN_SYNC): 0 counter barrier | 1 flag-in-data exchange | 2 same, staged poll | 3 counter, release-only
-    lili::DevBuf ll_buf;                 // two epoch-parity buffers of [29][2*sm_count] {epoch|lo32, epoch|hi32}
-    unsigned int ll_epoch = 0;           // last epoch issued
+    int gn_sync = 3;                     // persistent GN kernel grid barrier (LILIOM_GN_SYNC): 3 = release-only arrival, no acquire fence (default),
+                                         // 0 = full fences on both sides
     bool gn_smem_set = false;            // cudaFuncAttributeMaxDynamicSharedMemorySize raised for k_gn_persistent<16> on this device
     std::vector<cudaEvent_t> ev_pool;
     size_t ev_used = 0;

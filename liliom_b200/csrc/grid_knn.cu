@@ -447,111 +447,6 @@ __device__ __forceinline__ void reduce_partials(const KnnArgs& a, KnnSmem& S) {
     __syncthreads();
 }
 
-// ---- flag-in-data exchange of the block partials (persistent kernel, opt-out: LILIOM_GN_LL=0) -------------------
-// The counter barrier costs three dependent L2 round trips per pass on top of the arrival skew: partial stores ->
-// __threadfence -> atomic arrival -> poll -> partial loads (measured: fence 2.1k + barrier 4.2k + reduce 2.3k of a
-// 24k-cycle pass).  Here every 8-byte word a block publishes carries the pass's epoch in its upper half (a double
-// travels as {epoch|lo32, epoch|hi32}, NCCL's "LL" scheme): an aligned 8-byte store is single-copy atomic, so a
-// reader that sees the epoch sees the data — no fence, no counter, and the wait IS the load of the data.  Two
-// buffers alternate by epoch parity: a block can only publish pass e+1 after it has read every block's pass e, i.e.
-// after every block has finished reading pass e-1, so the buffer of pass e-1 is free.  Epochs increase monotonically
-// across launches (host-tracked), the buffer is zeroed once at allocation and epochs start at 1, so a stale word never
-// matches.  The summation order is the fixed tree of reduce_partials: every block computes bit-identical sums.
-__device__ __forceinline__ void ll_store(ulonglong2* p, double v, unsigned int epoch) {
-    const u64 w0 = ((u64)epoch << 32) | (u64)(unsigned)__double2loint(v);
-    const u64 w1 = ((u64)epoch << 32) | (u64)(unsigned)__double2hiint(v);
-    asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(w0), "l"(w1) : "memory");
-}
-__device__ __forceinline__ void ll_load(const ulonglong2* p, u64& w0, u64& w1) {
-    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(p) : "memory");
-}
-
-__device__ __forceinline__ void write_block_partials_ll(const KnnArgs& a, KnnSmem& S, double acc, unsigned long long cand,
-                                                        ulonglong2* ll, unsigned int epoch) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (lane < kNormEq) S.red[warp][lane] = acc;
-    {
-        unsigned long long v = cand;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == 0) S.red_cand[warp] = v;
-    }
-    __syncthreads();
-    const int G = gridDim.x;
-    if (threadIdx.x < kNormEq) {
-        double v = 0;
-#pragma unroll
-        for (int w = 0; w < kWarps; ++w) v += S.red[w][threadIdx.x];
-        ll_store(ll + (size_t)threadIdx.x * G + blockIdx.x, v, epoch);      // scalar-major: [29][G]
-    }
-    if (threadIdx.x == 0 && a.cand_total) {
-        unsigned long long v = 0;
-        for (int w = 0; w < kWarps; ++w) v += S.red_cand[w];
-        if (v) atomicAdd(a.cand_total, v);
-    }
-    __syncthreads();       // S.red[0] is rewritten by reduce_ll
-}
-
-// Staged variant (LILIOM_GN_SYNC=2): with every thread of every block polling, ~0.5 M 16-byte loads per round hit the L2
-// while the slowest blocks still need it for their search (measured: slower than the counter barrier).  Stage 1: thread b
-// watches ONE word of block b (the last scalar) with a short back-off; when all have shown up, stage 2 is reduce_ll, whose
-// per-word epoch check still covers words that became visible out of order.
-__device__ __forceinline__ void ll_wait_arrivals(const ulonglong2* ll, unsigned int epoch) {
-    const int G = gridDim.x;
-    for (int b = threadIdx.x; b < G; b += blockDim.x) {
-        const ulonglong2* p = ll + (size_t)(kNormEq - 1) * G + b;
-        u64 w0, w1;
-        unsigned int spins = 0;
-        while (true) {
-            ll_load(p, w0, w1);
-            if (((unsigned int)(w0 >> 32) == epoch && (unsigned int)(w1 >> 32) == epoch) || ++spins > (1u << 20)) break;
-            __nanosleep(40);
-        }
-    }
-    __syncthreads();
-}
-
-// Poll-and-sum: same 8-lanes-per-scalar layout and summation tree as reduce_partials; a lane re-loads only the words
-// whose epoch has not arrived yet.  The spin is capped (~seconds) so that a protocol bug shows up as a wrong result
-// in a test, never as a hung GPU.
-__device__ __forceinline__ void reduce_ll(const ulonglong2* ll, unsigned int epoch, KnnSmem& S) {
-    const int G = gridDim.x;
-    const int sc = threadIdx.x >> 3, l8 = threadIdx.x & 7;
-    double v = 0.0;
-    if (sc < kNormEq) {
-        const ulonglong2* src = ll + (size_t)sc * G;
-#pragma unroll 1
-        for (int base = l8; base < G; base += 8 * kRedLoads) {
-            u64 w0[kRedLoads], w1[kRedLoads];
-            unsigned int pending = 0;
-#pragma unroll
-            for (int j = 0; j < kRedLoads; ++j) { w0[j] = 0; w1[j] = 0; if (base + 8 * j < G) pending |= 1u << j; }
-            unsigned int spins = 0;
-            while (pending) {
-#pragma unroll
-                for (int j = 0; j < kRedLoads; ++j) if (pending & (1u << j)) ll_load(src + base + 8 * j, w0[j], w1[j]);
-#pragma unroll
-                for (int j = 0; j < kRedLoads; ++j)
-                    if ((pending & (1u << j)) && (unsigned int)(w0[j] >> 32) == epoch && (unsigned int)(w1[j] >> 32) == epoch) pending &= ~(1u << j);
-                if (++spins > (1u << 21)) pending = 0;      // safety valve (never taken in a correct run)
-            }
-            double w[kRedLoads];
-#pragma unroll
-            for (int j = 0; j < kRedLoads; ++j) w[j] = (base + 8 * j < G) ? __hiloint2double((int)(unsigned int)w1[j], (int)(unsigned int)w0[j]) : 0.0;
-#pragma unroll
-            for (int j = 0; j < 10; ++j) w[j] += w[j + 10];
-#pragma unroll
-            for (int j = 0; j < 5; ++j) w[j] += w[j + 5];
-            v += ((w[0] + w[1]) + (w[2] + w[3])) + w[4];
-        }
-    }
-    v += __shfl_xor_sync(0xffffffffu, v, 1);
-    v += __shfl_xor_sync(0xffffffffu, v, 2);
-    v += __shfl_xor_sync(0xffffffffu, v, 4);
-    if (l8 == 0 && sc < kNormEq) S.red[0][sc] = v;
-    __syncthreads();
-}
-
 // One thread: 6x6 solve of the reduced normal equations in S.red[0], Plus, sign-unify -> xn.
 __device__ __forceinline__ void gn_step(const KnnSmem& S, const Q4& q, const D3& t, double xn[7]) {
     double s[kNormEq];
@@ -664,17 +559,19 @@ __global__ void __launch_bounds__(kBlock, 2) k_knn_plane(KnnArgs a) {
 // grid barrier after publishing their partials; then EVERY block sums the partials and solves the 6x6
 // system redundantly (bit-identical), so no second barrier or broadcast is needed.  Removes the launch
 // gap, the drain and the ticket round trip of the per-iteration kernel (~6 us of ~18 per iteration).
-// The persistent kernel never runs more than one block per SM (grid <= sm_count).  LILI_GN_MAXNREG (build-time experiment)
-// trades the 128-register cap of __launch_bounds__(256, 2) for a higher one: no spills, while a 64-register block of the
-// Preprocessing node's cooperative kernel still fits beside it (176 * 256 + 64 * 256 <= 65536 registers).
-#ifdef LILI_GN_MAXNREG
-#define LILI_GN_BOUNDS __maxnreg__(LILI_GN_MAXNREG)
-#else
-#define LILI_GN_BOUNDS __launch_bounds__(kBlock, 2)
+// The persistent kernel never runs more than one block per SM (grid <= sm_count), so it takes a 176-register cap instead
+// of the 128 of __launch_bounds__(256, 2): the spills (200-600 B per thread in the fp64 fit) disappear, while a
+// 64-register block of the Preprocessing node's cooperative kernel still fits beside it (176*256 + 64*256 <= 65536
+// registers), which the two-node e2e leg relies on.  Measured on B200 (1.5k-query scans, A/B in one process,
+// tools/ab_variants.py): 12.70 -> 12.32 us per pass; with the release-only barrier below 11.04 us.
+// (__maxnreg__ and __launch_bounds__ cannot be combined; the block size is fixed by the host code.)
+#ifndef LILI_GN_MAXNREG
+#define LILI_GN_MAXNREG 176
 #endif
+#define LILI_GN_BOUNDS __maxnreg__(LILI_GN_MAXNREG)
 template <int LANES, bool FLAT = false>
 __global__ void LILI_GN_BOUNDS k_gn_persistent(KnnArgs a, int iters, unsigned int* bar, double* stats_base, unsigned int bar_base,
-                                                             ulonglong2* ll, unsigned int ll_epoch0, unsigned int ll_stride, int sync_mode) {
+                                                             int sync_mode) {
     __shared__ __align__(16) KnnSmem S;
     extern __shared__ __align__(16) unsigned char dyn_smem[];   // flat == 2: [kFlatBatch][kBlock] float4 candidates + [kBlock] int4 tags
     const int n_q = a.n_dev ? min(*a.n_dev, a.n) : a.n;
@@ -715,20 +612,14 @@ __global__ void LILI_GN_BOUNDS k_gn_persistent(KnnArgs a, int iters, unsigned in
         if (stamp) a.dbg[16] = clock64();
         knn_phases<LANES, FLAT>(a, q, t, n_q, S, acc, cand, keep ? &f_keep : nullptr, cc, kBlock, cc_tag);
         if (stamp) a.dbg[17] = clock64();
-        if (ll) {
-            // ---- flag-in-data exchange: publishing is the arrival, polling is the load (see ll_store)
-            const unsigned int epoch = ll_epoch0 + (unsigned int)it;
-            ulonglong2* buf = ll + (size_t)(epoch & 1u) * ll_stride;
-            write_block_partials_ll(a, S, acc, cand, buf, epoch);
-            if (stamp) a.dbg[18] = clock64();
-            if (sync_mode == 2) ll_wait_arrivals(buf, epoch);
-            if (stamp) a.dbg[19] = clock64();
-            reduce_ll(buf, epoch, S);
-        } else if (sync_mode == 3) {
-            // ---- counter barrier with the minimum of fences (experiment): one release by thread 0 after the block barrier
-            // (cumulative over bar.sync, as in cooperative groups' grid.sync) and NO acquire fence after the poll.  The acquire
-            // would only invalidate L1; everything this kernel reads through L1 (map, cell table, features) is immutable for
-            // the launch, and the partials are read with L2-scope loads (__ldcg).
+        if (sync_mode == 3) {
+            // ---- counter barrier with the minimum of fences (default; measured 12.70 -> 11.99 us per pass against mode 0):
+            // one release by thread 0 after the block barrier (cumulative over bar.sync, as in cooperative groups' grid.sync;
+            // SASS: MEMBAR.ALL.GPU + RED, no L1 invalidate) and NO acquire fence after the poll.  An acquire (mode 0's
+            // __threadfence: MEMBAR.SC + CCTL.IVALL) would only add an L1 invalidation: everything this kernel reads through
+            // L1 (map, cell table, features) is immutable for the launch, and the partials are read with L2-scope loads
+            // (__ldcg) issued after the poll's control dependency and a bar.sync.  The PTX model formally asks for the acquire;
+            // LILIOM_GN_SYNC=0 restores it, and tests/test_gpu_variants.py pins both to the same bits.
             write_block_partials(a, S, acc, cand);
             __syncthreads();
             if (stamp) a.dbg[18] = clock64();
@@ -1090,20 +981,8 @@ int s2m_run(liliom_ctx* c, double pose7[7], int match_cnt, int max_num_iter, int
         unsigned int* bar = reinterpret_cast<unsigned int*>(c->counter.as<unsigned char>() + 32);
         double* stats_base = c->stats_dev.as<double>();
         unsigned int bar_base = c->bar_arrivals;
-        ulonglong2* ll = nullptr;
-        unsigned int ll_epoch0 = 0, ll_stride = (unsigned int)kNormEq * (unsigned int)(2 * c->sm_count);
-        int sync_mode = c->gn_ll;      // 0 counter barrier | 1 flag-in-data, all threads poll | 2 flag-in-data, staged poll | 3 counter, release-only
-        if (sync_mode == 1 || sync_mode == 2) {
-            if (!c->ll_buf.p) {      // zeroed once: epochs start at 1 and only grow, a stale word never matches
-                LILI_CUDA(c, c->ll_buf.ensure((size_t)2 * ll_stride * sizeof(ulonglong2)));
-                LILI_CUDA(c, cudaMemsetAsync(c->ll_buf.p, 0, c->ll_buf.cap, c->stream));
-                c->ll_epoch = 0;
-            }
-            ll = c->ll_buf.as<ulonglong2>();
-            ll_epoch0 = c->ll_epoch + 1u;
-            c->ll_epoch += (unsigned int)iters;
-        }
-        void* kargs[] = {&a, &iters_arg, &bar, &stats_base, &bar_base, &ll, &ll_epoch0, &ll_stride, &sync_mode};
+        int sync_mode = c->gn_sync;    // 3: release-only counter barrier (default) | 0: counter barrier with full fences
+        void* kargs[] = {&a, &iters_arg, &bar, &stats_base, &bar_base, &sync_mode};
         const void* fn = (lanes == 16 && a.flat) ? (const void*)k_gn_persistent<16, true>
                        : lanes == 16 ? (const void*)k_gn_persistent<16> : lanes == 1 ? (const void*)k_gn_persistent<1>
                        : lanes == 2 ? (const void*)k_gn_persistent<2> : lanes == 4 ? (const void*)k_gn_persistent<4>
@@ -1126,7 +1005,7 @@ int s2m_run(liliom_ctx* c, double pose7[7], int match_cnt, int max_num_iter, int
         }
         LILI_CUDA(c, cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kBlock), kargs, dyn, c->stream));
         LILI_TRY(launch_check(c, "k_gn_persistent"));
-        if (!ll) c->bar_arrivals += (unsigned int)iters * (unsigned int)grid;
+        c->bar_arrivals += (unsigned int)iters * (unsigned int)grid;
         if (c->time_kernels) {
             LILI_CUDA(c, cudaEventRecord(c->ev_pool[ev + 1], c->stream));
             c->ev_pending.push_back({ev, (unsigned long long)n_est * iters});

@@ -96,6 +96,7 @@ def test_backend_edge_block_matches_oracle(oracle, world_small):
     m += rng.normal(0, 0.01, m.shape).astype(np.float32)
     m4 = np.ones((len(m), 4), np.float32); m4[:, :3] = m
     pose = np.array([0.9990482, 0.0, 0.0, 0.0436194, 0.4, -0.3, 0.1])
+    pose[:4] /= np.linalg.norm(pose[:4])      # unit like every pose Ceres' QuaternionParameterization produces (the closed-form row assumes it)
     # features: map points pulled into the body frame with noise
     sel = m[rng.integers(0, len(m), 1500)].astype(np.float64) + rng.normal(0, 0.08, (1500, 3))
     qw, qx, qy, qz = pose[:4]

@@ -13,7 +13,7 @@ import liliom_b200 as L
 from liliom_b200 import synth
 
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 150
-cfgs = [tuple(int(x) for x in a.split(":")) for a in sys.argv[2:]] or [(0, 0), (0, 3), (0, 2), (0, 1), (1, 0), (1, 3), (2, 3), (2, 2)]
+cfgs = [tuple(int(x) for x in a.split(":")) for a in sys.argv[2:]] or [(0, 3), (0, 0), (1, 3), (1, 0), (2, 3)]
 m, _ = synth.make_map(1_000_000)
 T0 = synth.default_true_pose()
 sweeps = []
