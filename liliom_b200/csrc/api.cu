@@ -592,12 +592,16 @@ extern "C" int liliom_extract_resident(liliom_ctx* c, const double q_imu[4], con
     LILI_CUDA(c, cudaSetDevice(c->device));
     const int stride = c->prm.point_stride;
     const int n = c->n_raw_scan;
-    // the extractors read c->raw: a device-to-device copy keeps the resident sweep reusable across steps
-    LILI_CUDA(c, c->raw.ensure((size_t)(n > 0 ? n : 1) * stride));
-    if (n > 0) LILI_CUDA(c, cudaMemcpyAsync(c->raw.p, c->raw_scan.p, (size_t)n * stride, cudaMemcpyDeviceToDevice, c->stream));
-    if (stride == 48) return horizon_extract_dev(c, n, q_imu, n_surf, n_edge, n_cut, /*sync_counts=*/false);
-    const double ident[4] = {1, 0, 0, 0};
-    return rot_extract_dev(c, n, q_imu, q_lb ? q_lb : ident, n_surf, n_edge, n_cut);
+    // the extractors only read their input: they take the resident sweep in place (no device-to-device copy)
+    c->raw_src = n > 0 ? c->raw_scan.p : nullptr;
+    int rc;
+    if (stride == 48) rc = horizon_extract_dev(c, n, q_imu, n_surf, n_edge, n_cut, /*sync_counts=*/false);
+    else {
+        const double ident[4] = {1, 0, 0, 0};
+        rc = rot_extract_dev(c, n, q_imu, q_lb ? q_lb : ident, n_surf, n_edge, n_cut);
+    }
+    c->raw_src = nullptr;
+    return rc;
 }
 
 static int odometry_on_resident_surf(liliom_ctx* c, double pose7[7], int match_cnt, int max_num_iter, int mode, liliom_iter_stats* stats,

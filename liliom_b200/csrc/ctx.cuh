@@ -95,6 +95,7 @@ struct liliom_ctx {
     lili::DevBuf raw_scan;       // resident raw sweep (liliom_upload_scan / liliom_convert_livox)
     lili::DevBuf livox_in;       // staged livox CustomPoint records (19/20 bytes each)
     int n_raw_scan = 0;
+    const void* raw_src = nullptr; // when set, the extractors read the sweep from here instead of c->raw (resident pipeline: no copy)
     int n_rot_cloud = 0;
 
     // ---- voxel grid scratch ----

@@ -415,7 +415,7 @@ int horizon_extract_dev(liliom_ctx* c, int n, const double q_imu[4], int* n_surf
     LILI_CUDA(c, c->hz_counts.ensure((size_t)(4 * (HZ_PATCHES + 1) + 8) * sizeof(int)));
     Q4 q{q_imu[0], q_imu[1], q_imu[2], q_imu[3]};
     if (std::isnan(q.w) || std::isnan(q.x) || std::isnan(q.y) || std::isnan(q.z)) q = Q4{1, 0, 0, 0};   // :232-234
-    const Pt48* raw = c->raw.as<Pt48>();
+    const Pt48* raw = c->raw_src ? reinterpret_cast<const Pt48*>(c->raw_src) : c->raw.as<Pt48>();   // read-only input
     int* flags = c->flags.as<int>();
     int* cidx = c->idx_a.as<int>();
     int* mat = c->hz_mat.as<int>();

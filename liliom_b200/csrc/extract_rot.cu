@@ -420,7 +420,7 @@ int rot_extract_dev(liliom_ctx* c, int n, const double q_imu[4], const double q_
     Q4 qI{q_imu[0], q_imu[1], q_imu[2], q_imu[3]};
     if (std::isnan(qI.w) || std::isnan(qI.x) || std::isnan(qI.y) || std::isnan(qI.z)) qI = Q4{1, 0, 0, 0};   // :299-301
     Q4 qL{q_lb[0], q_lb[1], q_lb[2], q_lb[3]};
-    const Pt32* raw = c->raw.as<Pt32>();
+    const Pt32* raw = c->raw_src ? reinterpret_cast<const Pt32*>(c->raw_src) : c->raw.as<Pt32>();   // read-only input
     int* meta = c->rot_meta.as<int>();
     int* ringmm = meta + M_SIZE;
     VgParams* rprm = reinterpret_cast<VgParams*>(ringmm + ROT_MAX_RINGS * 8);
