@@ -33,7 +33,7 @@ def test_gn_variants_bit_identical(oracle, world_small):
     guess = world_small["guess"]
     # scans of different sizes back to back: the grid size (and the LL layout stride) changes between launches,
     # the last one is large enough to leave the 16-lane shape (flat does not apply there)
-    scans = [ds, ds[: len(ds) // 3], ds[::2], ds[:40], surf[:6000], ds]
+    scans = [ds, ds[: len(ds) // 3], ds[::2], ds[:40], surf[:6000], surf[:3000], ds]     # 3000: two search rounds per warp task
     ref = None
     for flat, ll in VARIANTS:
         c = _ctx(flat, ll)
@@ -50,6 +50,8 @@ def test_gn_variants_bit_identical(oracle, world_small):
             ref = out
             rc, pose_o, _ = oracle.scan_to_map_gn(oracle.KdTree(world_small["map"]), ds, guess, 10)
             assert np.linalg.norm(out[0][0][4:] - pose_o[4:]) < 1e-4
+            rc, pose_o, _ = oracle.scan_to_map_gn(oracle.KdTree(world_small["map"]), surf[:3000], guess, 10)
+            assert np.linalg.norm(out[10][0][4:] - pose_o[4:]) < 1e-4 and abs(abs(np.dot(out[10][0][:4], pose_o[:4])) - 1) < 1e-9
             continue
         for k, (a, b) in enumerate(zip(out, ref)):
             assert a[0].tobytes() == b[0].tobytes(), (flat, ll, k, a[0], b[0])
