@@ -220,6 +220,16 @@ int liliom_extract_horizon_livox(liliom_ctx* c, const void* custom_pts, int n, i
                                  liliom_pt48* edge_out, int edge_cap, int* n_edge,
                                  liliom_pt48* cutted_out, int cut_cap, int* n_cut);
 
+/* ---- SURVEY §8 (f3), publishing side: the PointCloud2 layout pcl::toROSMsg gives these clouds ----
+ * L/src/Preprocessing.cpp:385-401, L/src/LidarOdometry.cpp:634-649: pcl::toROSMsg copies the point array verbatim into
+ * sensor_msgs::PointCloud2::data (point_step = sizeof(PointT), is_dense as in the cloud, height 1) and lists the fields
+ * PCL registers for the point type.  The buffers this library returns ARE that payload: a node can pass msg.data.data()
+ * (resized to n * point_step) as the output pointer and fill the header from this table — no intermediate PCL cloud.
+ * datatype follows sensor_msgs::PointField (7 = FLOAT32).  Returns the number of fields (8 for stride 48, 4 for 32),
+ * or LILIOM_E_ARG / LILIOM_E_CAPACITY. */
+typedef struct { char name[16]; unsigned int offset; unsigned char datatype; unsigned int count; } liliom_pc2_field;
+int liliom_pc2_layout(int point_stride, liliom_pc2_field* fields, int cap, int* point_step);
+
 /* ===================== multi-GPU (one context per rank) ===================== */
 /* 128-byte NCCL unique id: rank 0 calls get, the launcher broadcasts it, every rank calls init.
  * After init, liliom_map_set_points shards the map by 16 m block hash (+halo) and every

@@ -59,9 +59,24 @@ EXPORTS = [
     "liliom_odometry", "liliom_set_stream", "liliom_upload_scan", "liliom_extract_resident", "liliom_point_stride",
     "liliom_map_set_cloud", "liliom_correspond_surf_refl",
     "liliom_backend_edge_block", "liliom_backend_surf_block", "liliom_convert_livox", "liliom_extract_horizon_livox",
+    "liliom_pc2_layout",
 ]
 NODE_EXPORTS = ["liliom_pre_create", "liliom_pre_destroy", "liliom_pre_imu", "liliom_pre_cloud",
                 "liliom_lo_create", "liliom_lo_destroy", "liliom_lo_edge", "liliom_lo_surf", "liliom_lo_full", "liliom_lo_run"]
+
+
+class Pc2Field(C.Structure):
+    _fields_ = [("name", C.c_char * 16), ("offset", C.c_uint), ("datatype", C.c_ubyte), ("count", C.c_uint)]
+
+
+def pc2_layout(point_stride: int):
+    """(fields, point_step) of the sensor_msgs/PointCloud2 pcl::toROSMsg builds for the 48 / 32-byte clouds."""
+    f = (Pc2Field * 8)()
+    step = C.c_int()
+    n = lib().liliom_pc2_layout(point_stride, f, 8, C.byref(step))
+    if n < 0:
+        raise LiliomError(n)
+    return [(f[i].name.decode(), f[i].offset, f[i].datatype, f[i].count) for i in range(n)], step.value
 
 
 class LoOutput(C.Structure):
@@ -124,6 +139,7 @@ def lib() -> C.CDLL:
     L.liliom_backend_surf_block.argtypes = [vp, dp, dp, dp, C.c_double, dp]
     L.liliom_convert_livox.argtypes = [vp, vp, C.c_int, C.c_int, vp, C.c_int]
     L.liliom_extract_horizon_livox.argtypes = [vp, vp, C.c_int, C.c_int, dp, vp, C.c_int, ip, vp, C.c_int, ip, vp, C.c_int, ip]
+    L.liliom_pc2_layout.argtypes = [C.c_int, vp, C.c_int, ip]
     L.liliom_pre_create.argtypes = [vp, C.c_int, dp]; L.liliom_pre_create.restype = vp
     L.liliom_pre_destroy.argtypes = [vp]; L.liliom_pre_destroy.restype = None
     L.liliom_pre_imu.argtypes = [vp, C.c_double, dp]; L.liliom_pre_imu.restype = None

@@ -698,6 +698,26 @@ extern "C" int liliom_find_surf_corr(liliom_ctx* c, const void* feats, int n, in
     return LILIOM_OK;
 }
 
+// ===================== wire format, publishing side =====================
+// from-knowledge: POINT_CLOUD_REGISTER_POINT_STRUCT of pcl::PointXYZINormal / pcl::PointXYZI (PCL 1.8-1.10) as pcl::toROSMsg lists them
+extern "C" int liliom_pc2_layout(int point_stride, liliom_pc2_field* fields, int cap, int* point_step) {
+    struct F { const char* name; unsigned int off; };
+    static const F f48[] = {{"x", 0}, {"y", 4}, {"z", 8}, {"normal_x", 16}, {"normal_y", 20}, {"normal_z", 24}, {"intensity", 32}, {"curvature", 36}};
+    static const F f32[] = {{"x", 0}, {"y", 4}, {"z", 8}, {"intensity", 16}};
+    if (point_stride != 48 && point_stride != 32) return LILIOM_E_ARG;
+    const F* src = point_stride == 48 ? f48 : f32;
+    const int n = point_stride == 48 ? 8 : 4;
+    if (point_step) *point_step = point_stride;
+    if (!fields) return n;
+    if (cap < n) return LILIOM_E_CAPACITY;
+    for (int i = 0; i < n; ++i) {
+        memset(&fields[i], 0, sizeof(fields[i]));
+        strncpy(fields[i].name, src[i].name, sizeof(fields[i].name) - 1);
+        fields[i].offset = src[i].off; fields[i].datatype = 7; fields[i].count = 1;
+    }
+    return n;
+}
+
 // ===================== instrumentation =====================
 extern "C" int liliom_get_counters(liliom_ctx* c, liliom_counters* out, int reset) {
     if (!c || !out) return LILIOM_E_ARG;

@@ -72,3 +72,19 @@ def test_product_never_touches_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", "Makefile")):
                 txt = open(os.path.join(dp, f), errors="ignore").read()
                 assert "oracle_lib" not in txt and "liboracle" not in txt and "oracle/" not in txt, os.path.join(dp, f)
+
+
+def test_pointcloud2_layout_matches_the_point_dtypes():
+    """liliom_pc2_layout (pcl::toROSMsg's field table) against the numpy mirrors of the PCL structs."""
+    import liliom_b200 as L
+    f48, step48 = L.pc2_layout(48)
+    assert step48 == 48 and [x[0] for x in f48] == ["x", "y", "z", "normal_x", "normal_y", "normal_z", "intensity", "curvature"]
+    names48 = {"normal_x": "nx", "normal_y": "ny", "normal_z": "nz"}
+    for name, off, dt, cnt in f48:
+        assert (dt, cnt) == (7, 1) and L.PT48.fields[names48.get(name, name)][1] == off
+    f32, step32 = L.pc2_layout(32)
+    assert step32 == 32 and [(n, o) for n, o, _, _ in f32] == [("x", 0), ("y", 4), ("z", 8), ("intensity", 16)]
+    for name, off, dt, cnt in f32:
+        assert L.PT32.fields[name][1] == off
+    assert L._binding.lib().liliom_pc2_layout(40, None, 0, None) == L._binding.E_ARG
+    assert L._binding.lib().liliom_pc2_layout(48, (L._binding.Pc2Field * 2)(), 2, None) == L._binding.E_CAPACITY
