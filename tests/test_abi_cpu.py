@@ -88,3 +88,28 @@ def test_pointcloud2_layout_matches_the_point_dtypes():
         assert L.PT32.fields[name][1] == off
     assert L._binding.lib().liliom_pc2_layout(40, None, 0, None) == L._binding.E_ARG
     assert L._binding.lib().liliom_pc2_layout(48, (L._binding.Pc2Field * 2)(), 2, None) == L._binding.E_CAPACITY
+
+
+def test_headers_are_plain_c_and_link_from_c(tmp_path):
+    """The drop-in boundary is a C ABI: both headers must compile as strict C99 and as C++14 (the reference's dialect,
+    L/CMakeLists.txt:6), and a C program must link against the library and call it without any CUDA/torch type."""
+    import shutil
+    import subprocess
+    gcc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else shutil.which("gcc")
+    gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else shutil.which("g++")
+    if not gcc or not gxx:
+        pytest.skip("no host compiler")
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "liliom.h"\n#include "liliom_nodes.h"\n'
+                   'int main(void) { liliom_params p; liliom_pc2_field f[8]; int step = 0;\n'
+                   '  liliom_default_params(&p, 1);\n'
+                   '  if (p.abi_version != LILIOM_ABI_VERSION || p.point_stride != 32) return 1;\n'
+                   '  if (liliom_pc2_layout(48, f, 8, &step) != 8 || step != 48) return 2;\n'
+                   '  return liliom_strerror(LILIOM_E_FEWMAP)[0] ? 0 : 3; }\n')
+    inc = os.path.join(ROOT, "include")
+    libdir = os.path.join(ROOT, "liliom_b200")
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", inc, "-c", str(src), "-o", str(tmp_path / "a.o")], check=True)
+    subprocess.run([gxx, "-std=c++14", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", inc, "-x", "c++", "-c", str(src), "-o", str(tmp_path / "b.o")], check=True)
+    exe = tmp_path / "hdr_bin"
+    subprocess.run([gcc, "-std=c99", "-I", inc, str(src), "-o", str(exe), "-L", libdir, "-lliliom_b200", f"-Wl,-rpath,{libdir}"], check=True)
+    assert subprocess.run([str(exe)]).returncode == 0
