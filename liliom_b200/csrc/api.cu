@@ -193,6 +193,7 @@ extern "C" int liliom_create(liliom_ctx** out, const liliom_params* p, int devic
     e = cudaHostAlloc(&c->h_pin, c->h_pin_bytes, cudaHostAllocDefault);
     if (e != cudaSuccess) { cudaStreamDestroy(c->own_stream); delete c; return LILIOM_E_CUDA; }
     if (const char* e1 = getenv("LILIOM_KNN_LANES")) { int v = atoi(e1); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16) c->force_lanes = v; }
+    if (const char* e7 = getenv("LILIOM_FAST_IO")) c->fast_io = atoi(e7) != 0;
     if (const char* e6 = getenv("LILIOM_COOP_SYNC")) c->coop_rel = atoi(e6) == 3;
     if (const char* e5 = getenv("LILIOM_GN_SYNC")) { int v = atoi(e5); if (v == 0 || v == 3) c->gn_sync = v; }
     if (const char* e3 = getenv("LILIOM_KNN_FLAT")) { int v = atoi(e3); if (v >= 0 && v <= 2) c->knn_flat = v; }
@@ -212,7 +213,7 @@ extern "C" void liliom_destroy(liliom_ctx* c) {
                       &c->vg_keys2, &c->vg_vals, &c->vg_vals2, &c->vg_flags, &c->vg_rank, &c->vg_params, &c->vg_out, &c->vg_minmax, &c->vg_count,
                       &c->cub_tmp, &c->vg_coop, &c->hz_ctl, &c->map_raw, &c->map_ds, &c->map_xyzw, &c->map_sorted, &c->cell_start, &c->grid_keys, &c->grid_keys2,
                       &c->grid_vals, &c->grid_vals2, &c->feats, &c->corr_valid, &c->corr_plane, &c->nn_idx, &c->nn_sqd, &c->pose_dev,
-                      &c->partials, &c->neq, &c->stats_dev, &c->counter, &c->lm_state, &c->raw_scan, &c->map_refl, &c->slots_buf, &c->livox_in};
+                      &c->partials, &c->neq, &c->stats_dev, &c->counter, &c->lm_state, &c->raw_scan, &c->map_refl, &c->slots_buf, &c->livox_in, &c->result_dev};
     for (DevBuf* b : bufs) b->release();
     for (auto& f : c->frames) f.buf.release();
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);

@@ -141,6 +141,8 @@ struct liliom_ctx {
     int knn_flat = 0;                    // 16-lane search shape: 0 = one run per lane, 1 = round-robin candidates, 2 = + per-iteration cache (LILIOM_KNN_FLAT)
     int gn_sync = 3;                     // persistent GN kernel grid barrier (LILIOM_GN_SYNC): 3 = release-only arrival, no acquire fence (default),
                                          // 0 = full fences on both sides
+    bool fast_io = false;                // LILIOM_FAST_IO=1: pose in the launch parameters, one read-back block (opt-in until measured)
+    lili::DevBuf result_dev;             // {pose7 | n_feats | VgParams} written by block 0 of the persistent kernel
     bool coop_rel = false;               // release-only grid barriers in the cooperative extract / VoxelGrid kernels (LILIOM_COOP_SYNC=3, opt-in)
     bool gn_smem_set = false;            // cudaFuncAttributeMaxDynamicSharedMemorySize raised for k_gn_persistent<16> on this device
     std::vector<cudaEvent_t> ev_pool;

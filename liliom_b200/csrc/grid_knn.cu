@@ -186,6 +186,8 @@ struct KnnArgs {
     int interleave;                     // 1: deal tasks to warps block-cyclically (load balance for small scans)
     struct Slot* slots_g;               // split path (large query sets): search kernel -> fit kernel hand-off, 48 B per query
     int fit_only;                       // 1: phase A is skipped, slots come from slots_g (written by k_knn_search)
+    double pose0[7]; int pose_by_value; // persistent kernel, LILIOM_FAST_IO: the start pose travels in the launch parameters (no H2D copy)
+    double* result; const VgParams* vgp; // ... and block 0 leaves {pose7 | n_feats | VgParams} in one block for a single D2H copy
     int flat;                           // LANES >= 16 only: 1 = deal the 27-cell candidate list round-robin over the lanes (group_knn5_flat),
                                         // 2 = also keep each lane's batch across the GN iterations of the persistent kernel
 };
@@ -575,7 +577,7 @@ __global__ void LILI_GN_BOUNDS k_gn_persistent(KnnArgs a, int iters, unsigned in
     __shared__ __align__(16) KnnSmem S;
     extern __shared__ __align__(16) unsigned char dyn_smem[];   // flat == 2: [kFlatBatch][kBlock] float4 candidates + [kBlock] int4 tags
     const int n_q = a.n_dev ? min(*a.n_dev, a.n) : a.n;
-    if (threadIdx.x < 7) S.pose[threadIdx.x] = a.pose[threadIdx.x];
+    if (threadIdx.x < 7) S.pose[threadIdx.x] = a.pose_by_value ? a.pose0[threadIdx.x] : a.pose[threadIdx.x];
     __syncthreads();
     const unsigned int G = gridDim.x;
     // bar_base = arrivals of all previous launches on this context (tracked by the host, advanced by iters*G per launch)
@@ -671,6 +673,16 @@ __global__ void LILI_GN_BOUNDS k_gn_persistent(KnnArgs a, int iters, unsigned in
         // the partials of this iteration may only be overwritten after every block has summed them: the next
         // barrier is behind the next write, so alternate between two partial buffers
         a.partials = (it & 1) ? a.partials - (size_t)kNormEq * G : a.partials + (size_t)kNormEq * G;
+    }
+    if (a.result && blockIdx.x == 0 && threadIdx.x == 0) {      // same layout as the pinned read-back block of s2m_run
+#pragma unroll
+        for (int k = 0; k < 7; ++k) a.result[k] = S.pose[k];
+        *reinterpret_cast<int*>(a.result + 40) = n_q;
+        if (a.vgp) {
+            const int* src = reinterpret_cast<const int*>(a.vgp);
+            int* dst = reinterpret_cast<int*>(a.result + 48);
+            for (int k = 0; k < (int)(sizeof(VgParams) / sizeof(int)); ++k) dst[k] = __ldcg(src + k);
+        }
     }
 }
 
@@ -955,8 +967,6 @@ int s2m_run(liliom_ctx* c, double pose7[7], int match_cnt, int max_num_iter, int
         LILI_CUDA(c, cudaMemsetAsync(c->nn_idx.p, 0xff, (size_t)n * 5 * sizeof(int), c->stream));
         LILI_CUDA(c, cudaMemsetAsync(c->nn_sqd.p, 0x7f, (size_t)n * 5 * sizeof(float), c->stream));
     }
-    LILI_CUDA(c, cudaMemcpyAsync(c->pose_dev.p, pose7, 7 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-
     KnnArgs a{};
     a.feats = c->feats.as<float4>(); a.n = n; a.n_dev = c->d_nfeats;
     a.map = c->map_sorted.as<float4>(); a.map_orig = c->map_xyzw.as<float4>(); a.cell_start = c->cell_start.as<int>(); a.g = c->grid;
@@ -982,6 +992,18 @@ int s2m_run(liliom_ctx* c, double pose7[7], int match_cnt, int max_num_iter, int
     // ---- single-GPU GN: all iterations in one cooperative launch
     const bool persistent = mode == LILIOM_MODE_GN && c->nranks == 1 && iters > 0 && !want_corr &&
                             !getenv("LILIOM_NO_PERSISTENT") && grid <= c->sm_count;
+    // LILIOM_FAST_IO=1 (opt-in until measured): the persistent launch carries the start pose in its parameters and leaves
+    // pose, query count and VoxelGrid verdict in one device block, so the call needs no H2D copy and one D2H copy of 432 B
+    // instead of three small ones (each a separate ~2 us DMA on the critical path of a ~220 us scan).
+    const bool fast_io = persistent && c->fast_io;
+    if (!fast_io) LILI_CUDA(c, cudaMemcpyAsync(c->pose_dev.p, pose7, 7 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    if (fast_io) {
+        LILI_CUDA(c, c->result_dev.ensure(64 * sizeof(double)));
+        for (int k = 0; k < 7; ++k) a.pose0[k] = pose7[k];
+        a.pose_by_value = 1;
+        a.result = c->result_dev.as<double>();
+        a.vgp = c->vg_check ? c->vg_params.as<VgParams>() : nullptr;
+    }
     if (persistent) {
         a.update_pose = 1;
         a.stats = nullptr;
@@ -1078,10 +1100,14 @@ int s2m_run(liliom_ctx* c, double pose7[7], int match_cnt, int max_num_iter, int
     }
     // ---- results: pose + stats in one pinned block
     double* hp = reinterpret_cast<double*>(c->h_pin);
-    LILI_CUDA(c, cudaMemcpyAsync(hp, c->pose_dev.p, 7 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    if (out29) LILI_CUDA(c, cudaMemcpyAsync(hp + 8, c->neq.p, kNormEq * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    if (c->d_nfeats) LILI_CUDA(c, cudaMemcpyAsync(hp + 40, c->d_nfeats, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    if (c->vg_check) LILI_CUDA(c, cudaMemcpyAsync(hp + 48, c->vg_params.p, sizeof(VgParams), cudaMemcpyDeviceToHost, c->stream));
+    if (fast_io) {
+        LILI_CUDA(c, cudaMemcpyAsync(hp, c->result_dev.p, 48 * sizeof(double) + sizeof(VgParams), cudaMemcpyDeviceToHost, c->stream));
+    } else {
+        LILI_CUDA(c, cudaMemcpyAsync(hp, c->pose_dev.p, 7 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        if (out29) LILI_CUDA(c, cudaMemcpyAsync(hp + 8, c->neq.p, kNormEq * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        if (c->d_nfeats) LILI_CUDA(c, cudaMemcpyAsync(hp + 40, c->d_nfeats, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        if (c->vg_check) LILI_CUDA(c, cudaMemcpyAsync(hp + 48, c->vg_params.p, sizeof(VgParams), cudaMemcpyDeviceToHost, c->stream));
+    }
     const bool want_stats = stats && iters > 0;
     if (want_stats) {
         size_t bytes = (size_t)iters * kStatsDoubles * sizeof(double);
