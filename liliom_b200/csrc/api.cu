@@ -194,7 +194,6 @@ extern "C" int liliom_create(liliom_ctx** out, const liliom_params* p, int devic
     if (e != cudaSuccess) { cudaStreamDestroy(c->own_stream); delete c; return LILIOM_E_CUDA; }
     if (const char* e1 = getenv("LILIOM_KNN_LANES")) { int v = atoi(e1); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16) c->force_lanes = v; }
     if (const char* e7 = getenv("LILIOM_FAST_IO")) c->fast_io = atoi(e7) != 0;
-    if (const char* e6 = getenv("LILIOM_COOP_SYNC")) c->coop_rel = atoi(e6) == 3;
     if (const char* e5 = getenv("LILIOM_GN_SYNC")) { int v = atoi(e5); if (v == 0 || v == 3) c->gn_sync = v; }
     if (const char* e3 = getenv("LILIOM_KNN_FLAT")) { int v = atoi(e3); if (v >= 0 && v <= 2) c->knn_flat = v; }
     if (const char* e2 = getenv("LILIOM_KNN_ROUNDS")) { int v = atoi(e2); if (v >= 1 && v <= 32) c->force_rounds = v; }

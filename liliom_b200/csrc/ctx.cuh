@@ -143,7 +143,6 @@ struct liliom_ctx {
                                          // 0 = full fences on both sides
     bool fast_io = false;                // LILIOM_FAST_IO=1: pose in the launch parameters, one read-back block (opt-in until measured)
     lili::DevBuf result_dev;             // {pose7 | n_feats | VgParams} written by block 0 of the persistent kernel
-    bool coop_rel = false;               // release-only grid barriers in the cooperative extract / VoxelGrid kernels (LILIOM_COOP_SYNC=3, opt-in)
     bool gn_smem_set = false;            // cudaFuncAttributeMaxDynamicSharedMemorySize raised for k_gn_persistent<16> on this device
     std::vector<cudaEvent_t> ev_pool;
     size_t ev_used = 0;

@@ -322,20 +322,10 @@ __global__ void k_hz_emit(const Pt48* __restrict__ stage_surf, const Pt48* __res
 constexpr int HZC_THREADS = 256;
 constexpr int HZC_WARPS = HZC_THREADS / 32;
 
-// rel = true (opt-in, LILIOM_COOP_SYNC=3; to be A/B-measured like the GN kernel's barrier, grid_knn.cu): one cumulative
-// release by thread 0 and no acquire fence — valid here because every read of data another block produced in this launch
-// (blockcnt, mat, cut, counts) is an L2-scope load (__ldcg / COHERENT) and the raw sweep is immutable.
-__device__ __forceinline__ void hz_grid_barrier(unsigned int* bar, unsigned int target, bool rel) {
-    if (rel) {
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(bar), "r"(1u) : "memory");
-            unsigned int v;
-            do { asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory"); } while ((int)(v - target) < 0);
-        }
-        __syncthreads();
-        return;
-    }
+// (A release-only variant of this barrier — one cumulative red.release by thread 0, no acquire fence; legal here because
+// every cross-block read is an L2-scope load — was measured in round 1 and changed nothing: 4586/4629 vs 4653/4563 scans/s.
+// These kernels spend their time in the stages, not in the three fences.)
+__device__ __forceinline__ void hz_grid_barrier(unsigned int* bar, unsigned int target) {
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -356,8 +346,6 @@ __global__ void __launch_bounds__(HZC_THREADS) k_hz_coop(const Pt48* __restrict_
     __shared__ int s_bpre;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int G = gridDim.x, b = blockIdx.x;
-    const bool rel = (call >> 31) != 0u;                     // bit 31 of `call`: release-only barrier
-    call &= 0x7fffffffu;
     unsigned int* bar = ctl + (call & 3u);
     if (b == 0 && tid == 0) ctl[(call + 1u) & 3u] = 0u;      // the next launch's barrier word
     // ---- A
@@ -378,7 +366,7 @@ __global__ void __launch_bounds__(HZC_THREADS) k_hz_coop(const Pt48* __restrict_
     int tpre = inc - mine;
     for (int w = 0; w < warp; ++w) tpre += wsum[w];
     if (tid == HZC_THREADS - 1) blockcnt[b] = tpre + mine;
-    hz_grid_barrier(bar, (unsigned int)G, rel);
+    hz_grid_barrier(bar, (unsigned int)G);
     // ---- B
     if (warp == 0) {
         int pre = 0, tot = 0;
@@ -395,7 +383,7 @@ __global__ void __launch_bounds__(HZC_THREADS) k_hz_coop(const Pt48* __restrict_
             if (i < n && hz_keep(pts, i)) { hz_deskew_bin_point(pts, i, ci, q_imu, cut, mat); ++ci; }
         }
     }
-    hz_grid_barrier(bar, 2u * (unsigned int)G, rel);
+    hz_grid_barrier(bar, 2u * (unsigned int)G);
     // ---- C  (host guarantees G * HZC_WARPS >= HZ_PATCHES: one patch per warp)
     const int patch = b * HZC_WARPS + warp;
     HzPatchSmem& P = sm[warp];
@@ -403,7 +391,7 @@ __global__ void __launch_bounds__(HZC_THREADS) k_hz_coop(const Pt48* __restrict_
         hz_patch_eval<true>(P, cut, mat, patch, lane, surf_thres, edge_thres);
         if (lane == 0) { counts[patch] = P.ns; counts[HZ_PATCHES + 1 + patch] = P.ne; }
     }
-    hz_grid_barrier(bar, 3u * (unsigned int)G, rel);
+    hz_grid_barrier(bar, 3u * (unsigned int)G);
     // ---- D
     if (patch < HZ_PATCHES) {
         int os = 0, oe = 0;
@@ -451,7 +439,7 @@ int horizon_extract_dev(liliom_ctx* c, int n, const double q_imu[4], int* n_surf
         const Pt48* raw_c = raw;
         Pt48* cutp = c->cut.as<Pt48>(); Pt48* surfp = c->surf.as<Pt48>(); Pt48* edgep = c->edge.as<Pt48>();
         double st = c->prm.surf_thres, et = c->prm.edge_thres;
-        unsigned int call = (c->hz_coop_calls & 0x7fffffffu) | (c->coop_rel ? 0x80000000u : 0u);
+        unsigned int call = c->hz_coop_calls;
         void* kargs[] = {&raw_c, &n, &q, &st, &et, &cutp, &mat, &blockcnt, &counts, &totals, &ncut_out, &surfp, &edgep, &ctl, &call};
         LILI_CUDA(c, cudaLaunchCooperativeKernel((const void*)k_hz_coop, dim3(c->sm_count), dim3(HZC_THREADS), kargs, 0, c->stream));
         LILI_TRY(launch_check(c, "k_hz_coop"));

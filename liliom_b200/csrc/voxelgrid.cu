@@ -435,18 +435,7 @@ static size_t vgc_layout(VgCoopBufs& B, unsigned char* base, int grid) {
     return off;
 }
 
-// rel: see hz_grid_barrier (extract_horizon.cu) — every cross-block read in this kernel is an L2-scope load or an atomic.
-__device__ __forceinline__ void vgc_barrier(unsigned int* bar, unsigned int target, bool rel) {
-    if (rel) {
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(bar), "r"(1u) : "memory");
-            unsigned int v;
-            do { asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory"); } while ((int)(v - target) < 0);
-        }
-        __syncthreads();
-        return;
-    }
+__device__ __forceinline__ void vgc_barrier(unsigned int* bar, unsigned int target) {
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -472,8 +461,6 @@ __global__ void __launch_bounds__(VGC_THREADS) k_vg_coop(const unsigned char* __
     const unsigned int G = gridDim.x;
     const int gtid = blockIdx.x * VGC_THREADS + tid, gthreads = G * VGC_THREADS;
     const int gwarp = blockIdx.x * VGC_WARPS + warp, gwarps = G * VGC_WARPS;
-    const bool rel = (call >> 31) != 0u;                  // bit 31 of `call`: release-only barrier
-    call &= 0x7fffffffu;
     unsigned int* ctl = B.ctl + 4 * (call & 3u);          // [0] barrier, [1] bail, [2] #voxels, [3] segment cursor
     if (blockIdx.x == 0 && tid < 4) B.ctl[4 * ((call + 1u) & 3u) + tid] = 0u;   // the next launch's slot (nobody uses it now)
     const int n = d_n ? min(*d_n, n_max) : n_max;
@@ -534,7 +521,7 @@ __global__ void __launch_bounds__(VGC_THREADS) k_vg_coop(const unsigned char* __
         for (int w = 1; w < VGC_WARPS; ++w) v = tid < 3 ? min(v, S.red[tid][w]) : tid < 6 ? max(v, S.red[tid][w]) : v + S.red[tid][w];
         B.mmpart[tid * G + blockIdx.x] = v;
     }
-    vgc_barrier(&ctl[0], G, rel);
+    vgc_barrier(&ctl[0], G);
 
     int U = (int)*reinterpret_cast<volatile unsigned int*>(&ctl[2]);
     unsigned int bail = *reinterpret_cast<volatile unsigned int*>(&ctl[1]);
@@ -596,7 +583,7 @@ __global__ void __launch_bounds__(VGC_THREADS) k_vg_coop(const unsigned char* __
                 B.urank[u] = below;
             }
         }
-        vgc_barrier(&ctl[0], 2u * G, rel);
+        vgc_barrier(&ctl[0], 2u * G);
         bail = *reinterpret_cast<volatile unsigned int*>(&ctl[1]);
     }
     if (bail) {
@@ -618,7 +605,7 @@ __global__ void __launch_bounds__(VGC_THREADS) k_vg_coop(const unsigned char* __
         const int s = __ldcg(&B.pslot[i]);
         if (s >= 0) B.members[__ldcg(&B.hoff[s]) + __ldcg(&B.ppos[i])] = i;
     }
-    vgc_barrier(&ctl[0], 3u * G, rel);
+    vgc_barrier(&ctl[0], 3u * G);
 
     // ---- phase 4: one warp per voxel — members in ascending original index, sequential fp32 sums
     constexpr int NF = STRIDE == 48 ? 8 : 4;
@@ -706,7 +693,7 @@ int voxelgrid_coop(liliom_ctx* c, const void* d_in, int n_max, const int* d_n, i
     const unsigned char* in = (const unsigned char*)d_in;
     unsigned char* outp = (unsigned char*)d_out;
     VgParams* pp = c->vg_params.as<VgParams>();
-    unsigned int call = (c->vg_coop_calls & 0x7fffffffu) | (c->coop_rel ? 0x80000000u : 0u);
+    unsigned int call = c->vg_coop_calls;
     void* kargs[] = {&in, &n_max, &d_n, &leaf, &B, &call, &pp, &outp, &d_count, &d_feats};
     const void* fn = stride == 48 ? (const void*)k_vg_coop<48> : (const void*)k_vg_coop<32>;
     LILI_CUDA(c, cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(VGC_THREADS), kargs, 0, c->stream));

@@ -14,7 +14,7 @@ from liliom_b200 import synth
 
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 150
 cfgs = [tuple(int(x) for x in a.split(":")) for a in sys.argv[2:]] or [(0, 3), (0, 0), (1, 3), (1, 0), (2, 3)]
-cfgs = [c if len(c) == 3 else c + (0,) for c in cfgs]      # optional third field: LILIOM_COOP_SYNC (3 = release-only barriers in the extract / VoxelGrid kernels)
+cfgs = [c if len(c) == 3 else c + (0,) for c in cfgs]      # optional third field: LILIOM_FAST_IO (pose in the launch parameters, one read-back block)
 m, _ = synth.make_map(1_000_000)
 T0 = synth.default_true_pose()
 sweeps = []
@@ -27,7 +27,7 @@ stream = torch.cuda.Stream()
 ref = None
 print(f"lib: {L.LIB_PATH}")
 for flat, sync, coop in cfgs:
-    os.environ["LILIOM_KNN_FLAT"] = str(flat); os.environ["LILIOM_GN_SYNC"] = str(sync); os.environ["LILIOM_COOP_SYNC"] = str(coop)
+    os.environ["LILIOM_KNN_FLAT"] = str(flat); os.environ["LILIOM_GN_SYNC"] = str(sync); os.environ["LILIOM_FAST_IO"] = str(coop)
     c = L.Context(variant=0)
     c.set_stream(stream.cuda_stream)
     c.map_set_points(m)
@@ -55,4 +55,4 @@ for flat, sync, coop in cfgs:
     same = "ref" if ref is None else ("bit-identical" if all(a.tobytes() == b.tobytes() for a, b in zip(poses, ref)) else "DIFFERENT POSES")
     if ref is None:
         ref = poses
-    print(f"flat={flat} sync={sync} coop={coop}: {steps / (tot * 1e-3):7.0f} scans/s  step {1e3 * tot / steps:6.1f} us  GN {1e3 * cnt.knn_ms / max(cnt.knn_launches, 1):6.2f} us/pass  [{same}]", flush=True)
+    print(f"flat={flat} sync={sync} fast_io={coop}: {steps / (tot * 1e-3):7.0f} scans/s  step {1e3 * tot / steps:6.1f} us  GN {1e3 * cnt.knn_ms / max(cnt.knn_launches, 1):6.2f} us/pass  [{same}]", flush=True)
