@@ -465,7 +465,7 @@ def main():
                 traffic = json.load(open(tp)).get("dram_bytes_per_launch")
             except Exception:
                 traffic = None
-        roof = {"bound": "hbm", "kernel": "k_knn_plane", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+        roof = {"bound": "hbm", "kernel": "k_gn_persistent / k_knn_plane (one GN pass of the kNN+plane+Jacobian+reduce+solve kernel body)", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                 "traffic": traffic, "peak_source": peak_src, "queries_per_launch": qpl, "candidates_per_query": cbar,
                 "algorithmic_bytes_per_launch": bytes_per_launch, "us_per_launch": t_launch * 1e6,
                 "min_bytes_per_launch": qpl * 96.0}
