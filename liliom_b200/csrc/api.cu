@@ -193,6 +193,7 @@ extern "C" int liliom_create(liliom_ctx** out, const liliom_params* p, int devic
     e = cudaHostAlloc(&c->h_pin, c->h_pin_bytes, cudaHostAllocDefault);
     if (e != cudaSuccess) { cudaStreamDestroy(c->own_stream); delete c; return LILIOM_E_CUDA; }
     if (const char* e1 = getenv("LILIOM_KNN_LANES")) { int v = atoi(e1); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16) c->force_lanes = v; }
+    c->dbg_timing = getenv("LILIOM_DEBUG_TIMING") != nullptr;
     if (const char* e7 = getenv("LILIOM_FAST_IO")) c->fast_io = atoi(e7) != 0;
     if (const char* e5 = getenv("LILIOM_GN_SYNC")) { int v = atoi(e5); if (v == 0 || v == 3) c->gn_sync = v; }
     if (const char* e3 = getenv("LILIOM_KNN_FLAT")) { int v = atoi(e3); if (v >= 0 && v <= 2) c->knn_flat = v; }

@@ -346,6 +346,10 @@ __global__ void __launch_bounds__(HZC_THREADS) k_hz_coop(const Pt48* __restrict_
     __shared__ int s_bpre;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int G = gridDim.x, b = blockIdx.x;
+    // bit 31 of `call` (LILIOM_DEBUG_TIMING): block 0 leaves clock64 stamps of the stage boundaries in the spare control words
+    long long* stamp = ((call >> 31) != 0u && b == 0 && tid == 0) ? reinterpret_cast<long long*>(ctl + 4) : nullptr;
+    call &= 0x7fffffffu;
+    if (stamp) stamp[0] = clock64();
     unsigned int* bar = ctl + (call & 3u);
     if (b == 0 && tid == 0) ctl[(call + 1u) & 3u] = 0u;      // the next launch's barrier word
     // ---- A
@@ -367,6 +371,7 @@ __global__ void __launch_bounds__(HZC_THREADS) k_hz_coop(const Pt48* __restrict_
     for (int w = 0; w < warp; ++w) tpre += wsum[w];
     if (tid == HZC_THREADS - 1) blockcnt[b] = tpre + mine;
     hz_grid_barrier(bar, (unsigned int)G);
+    if (stamp) stamp[1] = clock64();
     // ---- B
     if (warp == 0) {
         int pre = 0, tot = 0;
@@ -384,6 +389,7 @@ __global__ void __launch_bounds__(HZC_THREADS) k_hz_coop(const Pt48* __restrict_
         }
     }
     hz_grid_barrier(bar, 2u * (unsigned int)G);
+    if (stamp) stamp[2] = clock64();
     // ---- C  (host guarantees G * HZC_WARPS >= HZ_PATCHES: one patch per warp)
     const int patch = b * HZC_WARPS + warp;
     HzPatchSmem& P = sm[warp];
@@ -392,6 +398,7 @@ __global__ void __launch_bounds__(HZC_THREADS) k_hz_coop(const Pt48* __restrict_
         if (lane == 0) { counts[patch] = P.ns; counts[HZ_PATCHES + 1 + patch] = P.ne; }
     }
     hz_grid_barrier(bar, 3u * (unsigned int)G);
+    if (stamp) stamp[3] = clock64();
     // ---- D
     if (patch < HZ_PATCHES) {
         int os = 0, oe = 0;
@@ -401,6 +408,7 @@ __global__ void __launch_bounds__(HZC_THREADS) k_hz_coop(const Pt48* __restrict_
         hz_patch_emit(P, lane, surf + os, edge + oe);
         if (patch == HZ_PATCHES - 1 && lane == 0) { totals[0] = os + P.ns; totals[1] = oe + P.ne; }
     }
+    if (stamp) stamp[4] = clock64();
 }
 
 // raw points must already be in c->raw (n x 48 B).  Leaves cut/surf/edge on the device and the
@@ -439,7 +447,7 @@ int horizon_extract_dev(liliom_ctx* c, int n, const double q_imu[4], int* n_surf
         const Pt48* raw_c = raw;
         Pt48* cutp = c->cut.as<Pt48>(); Pt48* surfp = c->surf.as<Pt48>(); Pt48* edgep = c->edge.as<Pt48>();
         double st = c->prm.surf_thres, et = c->prm.edge_thres;
-        unsigned int call = c->hz_coop_calls;
+        unsigned int call = (c->hz_coop_calls & 0x7fffffffu) | (c->dbg_timing ? 0x80000000u : 0u);
         void* kargs[] = {&raw_c, &n, &q, &st, &et, &cutp, &mat, &blockcnt, &counts, &totals, &ncut_out, &surfp, &edgep, &ctl, &call};
         LILI_CUDA(c, cudaLaunchCooperativeKernel((const void*)k_hz_coop, dim3(c->sm_count), dim3(HZC_THREADS), kargs, 0, c->stream));
         LILI_TRY(launch_check(c, "k_hz_coop"));

@@ -1132,6 +1132,16 @@ int s2m_run(liliom_ctx* c, double pose7[7], int match_cnt, int max_num_iter, int
             for (int k = 0; k < 7; ++k) stats[it].pose7[k] = s[30 + k];
         }
     }
+    if (a.dbg && c->dbg_timing) {       // stage clocks of the two cooperative kernels that ran before this call (resident pipeline)
+        long long t[5];
+        if (c->hz_ctl.p && cudaMemcpy(t, c->hz_ctl.as<unsigned char>() + 16, sizeof(t), cudaMemcpyDeviceToHost) == cudaSuccess && t[4] > t[0])
+            fprintf(stderr, "[k_hz_coop, cycles, block 0] A keep-flags+barrier %lld, B de-skew/bin+barrier %lld, C patches+barrier %lld, D emit %lld\n",
+                    t[1] - t[0], t[2] - t[1], t[3] - t[2], t[4] - t[3]);
+        const long long* vs = vg_coop_stamps(c);
+        if (vs && cudaMemcpy(t, vs, sizeof(t), cudaMemcpyDeviceToHost) == cudaSuccess && t[4] > t[0])
+            fprintf(stderr, "[k_vg_coop, cycles, block 0] 1 hash insert+barrier %lld, 2 ranks+barrier %lld, 3 group+barrier %lld, 4 centroids %lld\n",
+                    t[1] - t[0], t[2] - t[1], t[3] - t[2], t[4] - t[3]);
+    }
     if (a.dbg) {
         long long h[24];
         cudaMemcpy(h, a.dbg, sizeof(h), cudaMemcpyDeviceToHost);

@@ -461,6 +461,10 @@ __global__ void __launch_bounds__(VGC_THREADS) k_vg_coop(const unsigned char* __
     const unsigned int G = gridDim.x;
     const int gtid = blockIdx.x * VGC_THREADS + tid, gthreads = G * VGC_THREADS;
     const int gwarp = blockIdx.x * VGC_WARPS + warp, gwarps = G * VGC_WARPS;
+    // bit 31 of `call` (LILIOM_DEBUG_TIMING): block 0 leaves clock64 stamps of the phase boundaries behind the 16 control words
+    long long* stamp = ((call >> 31) != 0u && blockIdx.x == 0 && tid == 0) ? reinterpret_cast<long long*>(B.ctl + 16) : nullptr;
+    call &= 0x7fffffffu;
+    if (stamp) stamp[0] = clock64();
     unsigned int* ctl = B.ctl + 4 * (call & 3u);          // [0] barrier, [1] bail, [2] #voxels, [3] segment cursor
     if (blockIdx.x == 0 && tid < 4) B.ctl[4 * ((call + 1u) & 3u) + tid] = 0u;   // the next launch's slot (nobody uses it now)
     const int n = d_n ? min(*d_n, n_max) : n_max;
@@ -522,6 +526,7 @@ __global__ void __launch_bounds__(VGC_THREADS) k_vg_coop(const unsigned char* __
         B.mmpart[tid * G + blockIdx.x] = v;
     }
     vgc_barrier(&ctl[0], G);
+    if (stamp) stamp[1] = clock64();
 
     int U = (int)*reinterpret_cast<volatile unsigned int*>(&ctl[2]);
     unsigned int bail = *reinterpret_cast<volatile unsigned int*>(&ctl[1]);
@@ -584,6 +589,7 @@ __global__ void __launch_bounds__(VGC_THREADS) k_vg_coop(const unsigned char* __
             }
         }
         vgc_barrier(&ctl[0], 2u * G);
+        if (stamp) stamp[2] = clock64();
         bail = *reinterpret_cast<volatile unsigned int*>(&ctl[1]);
     }
     if (bail) {
@@ -606,6 +612,7 @@ __global__ void __launch_bounds__(VGC_THREADS) k_vg_coop(const unsigned char* __
         if (s >= 0) B.members[__ldcg(&B.hoff[s]) + __ldcg(&B.ppos[i])] = i;
     }
     vgc_barrier(&ctl[0], 3u * G);
+    if (stamp) stamp[3] = clock64();
 
     // ---- phase 4: one warp per voxel — members in ascending original index, sequential fp32 sums
     constexpr int NF = STRIDE == 48 ? 8 : 4;
@@ -670,6 +677,15 @@ __global__ void __launch_bounds__(VGC_THREADS) k_vg_coop(const unsigned char* __
         }
         __syncwarp();
     }
+    if (stamp) stamp[4] = clock64();
+}
+
+// stage stamps of the last k_vg_coop launch (LILIOM_DEBUG_TIMING); nullptr before the first launch
+const long long* vg_coop_stamps(liliom_ctx* c) {
+    if (!c->vg_coop.p) return nullptr;
+    VgCoopBufs B;
+    vgc_layout(B, (unsigned char*)c->vg_coop.p, c->sm_count);
+    return reinterpret_cast<const long long*>(B.ctl + 16);
 }
 
 // Returns LILIOM_OK after enqueueing the cooperative filter; the caller must look at VgParams::bail (vg_params)
@@ -693,7 +709,7 @@ int voxelgrid_coop(liliom_ctx* c, const void* d_in, int n_max, const int* d_n, i
     const unsigned char* in = (const unsigned char*)d_in;
     unsigned char* outp = (unsigned char*)d_out;
     VgParams* pp = c->vg_params.as<VgParams>();
-    unsigned int call = c->vg_coop_calls;
+    unsigned int call = (c->vg_coop_calls & 0x7fffffffu) | (c->dbg_timing ? 0x80000000u : 0u);
     void* kargs[] = {&in, &n_max, &d_n, &leaf, &B, &call, &pp, &outp, &d_count, &d_feats};
     const void* fn = stride == 48 ? (const void*)k_vg_coop<48> : (const void*)k_vg_coop<32>;
     LILI_CUDA(c, cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(VGC_THREADS), kargs, 0, c->stream));
