@@ -344,3 +344,16 @@ def test_convert_livox_matches_formula(oracle):
     assert out19.tobytes() == out.tobytes()
     # the converted cloud is what the Horizon extractor expects: line = int(intensity), frac in [0, 0.1]
     assert ((out["intensity"] - np.floor(out["intensity"])) <= 0.1 + 1e-6).all()
+
+
+def test_golden_backend_blocks_and_livox(oracle):
+    g = np.load(os.path.join(GOLD, "backend_small.npz")); s2m = np.load(os.path.join(GOLD, "s2m_small.npz"))
+    tree = oracle.KdTree(s2m["map"]); feats = s2m["feats"]
+    sv, plane, score = oracle.correspond_surf_backend(tree, feats, g["pose_l"], 1.0, 0.06, 0.2, 0.6)
+    _same(sv, g["surf_valid"]); _same(plane, g["surf_plane"]); _same(score, g["surf_score"])
+    np.testing.assert_allclose(oracle.backend_surf_block(feats, sv, plane, score, g["pose_b"], g["q_lb"], g["t_lb"], 1.0), g["surf_block"], rtol=1e-13)
+    ev, pa, pb = oracle.correspond_edge(tree, feats, g["pose_l"], 0)
+    _same(ev, g["edge_valid"]); _same(pa, g["edge_pa"]); _same(pb, g["edge_pb"])
+    np.testing.assert_allclose(oracle.backend_edge_block(feats, ev, pa, pb, 0.6, g["pose_b"], 1.0), g["edge_block"], rtol=1e-13)
+    lv = np.load(os.path.join(GOLD, "livox_small.npz"))
+    _same(oracle.convert_livox(lv["records"].view(oracle.LIVOX20).reshape(-1)).view(np.uint8), lv["cloud"])
