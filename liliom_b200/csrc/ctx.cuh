@@ -141,6 +141,7 @@ struct liliom_ctx {
     int knn_flat = 0;                    // 16-lane search shape: 0 = one run per lane, 1 = round-robin candidates, 2 = + per-iteration cache (LILIOM_KNN_FLAT)
     int gn_sync = 3;                     // persistent GN kernel grid barrier (LILIOM_GN_SYNC): 3 = release-only arrival, no acquire fence (default),
                                          // 0 = full fences on both sides
+    bool map_coop = false;               // LILIOM_MAP_COOP=1: liliom_map_rebuild voxel-filters the 20-frame map with the cooperative single-launch filter
     bool dbg_timing = false;             // LILIOM_DEBUG_TIMING at create: stage clocks of the cooperative kernels, printed by s2m_run
     bool fast_io = false;                // LILIOM_FAST_IO=1: pose in the launch parameters, one read-back block (opt-in until measured)
     lili::DevBuf result_dev;             // {pose7 | n_feats | VgParams} written by block 0 of the persistent kernel
