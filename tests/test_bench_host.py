@@ -45,3 +45,15 @@ def test_two_stage_pipeline_propagates_errors():
         raise ValueError("stage b failed")
     with pytest.raises(ValueError):
         bench.run_two_stage_pipeline(6, 2, 2, lambda k, b: k, boom, lambda: None, lambda: None, timeout_s=5.0)
+
+
+def test_tools_and_entry_points_compile():
+    """Every script a GPU session runs (tools/, bench.py, __graft_entry__.py, fixture generators) must at least parse."""
+    import glob
+    import py_compile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    files = glob.glob(os.path.join(root, "tools", "*.py")) + [os.path.join(root, f) for f in ("bench.py", "__graft_entry__.py")] + \
+        glob.glob(os.path.join(root, "tests", "make_golden*.py"))
+    assert len(files) >= 8
+    for f in files:
+        py_compile.compile(f, doraise=True)
