@@ -297,6 +297,10 @@ def main():
         uid = [L.comm_get_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         ctx.comm_init(uid[0], world, rank)
+        if os.environ.get("LILIOM_PEER"):     # fused exchange over NVLink peer memory (one launch per scan and rank) instead of NCCL per iteration
+            hs = [None] * world
+            dist.all_gather_object(hs, ctx.comm_peer_export())
+            ctx.comm_peer_attach(hs, rank)
     ctx.map_set_points(m)
     ctx.set_kernel_timing(True)
 

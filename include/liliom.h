@@ -238,6 +238,15 @@ int liliom_pc2_layout(int point_stride, liliom_pc2_field* fields, int cap, int* 
 int liliom_comm_get_unique_id(void* id128);
 int liliom_comm_init(liliom_ctx* c, const void* id128, int nranks, int rank);
 
+/* Fused exchange over peer memory (single node, NVLink / NVSwitch; optional, after liliom_comm_init): every rank exports the
+ * 64-byte cudaIpcMemHandle of its exchange buffer, the launcher all-gathers them, every rank attaches all of them in rank
+ * order.  From then on a GN-mode scan-to-map runs all its iterations in ONE cooperative launch per rank: after the local
+ * reduction each rank stores its 29 sums directly into every peer's buffer (flag-in-data words) and reads the others' from
+ * its own — no ncclAllReduce, no per-iteration launches.  Sums are added in rank order on every rank: identical poses.
+ * nranks == 1 is accepted (self-exchange; exercises the protocol on one GPU). */
+int liliom_comm_peer_export(liliom_ctx* c, void* handle64);
+int liliom_comm_peer_attach(liliom_ctx* c, const void* handles /* nranks * 64 bytes, rank order */, int nranks, int rank);
+
 /* ===================== instrumentation ===================== */
 typedef struct {
     unsigned long long launches;      /* kernels of this library launched since create/reset */

@@ -59,7 +59,7 @@ EXPORTS = [
     "liliom_odometry", "liliom_set_stream", "liliom_upload_scan", "liliom_extract_resident", "liliom_point_stride",
     "liliom_map_set_cloud", "liliom_correspond_surf_refl",
     "liliom_backend_edge_block", "liliom_backend_surf_block", "liliom_convert_livox", "liliom_extract_horizon_livox",
-    "liliom_pc2_layout",
+    "liliom_pc2_layout", "liliom_comm_peer_export", "liliom_comm_peer_attach",
 ]
 NODE_EXPORTS = ["liliom_pre_create", "liliom_pre_destroy", "liliom_pre_imu", "liliom_pre_cloud",
                 "liliom_lo_create", "liliom_lo_destroy", "liliom_lo_edge", "liliom_lo_surf", "liliom_lo_full", "liliom_lo_run"]
@@ -140,6 +140,8 @@ def lib() -> C.CDLL:
     L.liliom_convert_livox.argtypes = [vp, vp, C.c_int, C.c_int, vp, C.c_int]
     L.liliom_extract_horizon_livox.argtypes = [vp, vp, C.c_int, C.c_int, dp, vp, C.c_int, ip, vp, C.c_int, ip, vp, C.c_int, ip]
     L.liliom_pc2_layout.argtypes = [C.c_int, vp, C.c_int, ip]
+    L.liliom_comm_peer_export.argtypes = [vp, vp]
+    L.liliom_comm_peer_attach.argtypes = [vp, vp, C.c_int, C.c_int]
     L.liliom_pre_create.argtypes = [vp, C.c_int, dp]; L.liliom_pre_create.restype = vp
     L.liliom_pre_destroy.argtypes = [vp]; L.liliom_pre_destroy.restype = None
     L.liliom_pre_imu.argtypes = [vp, C.c_double, dp]; L.liliom_pre_imu.restype = None
@@ -417,6 +419,18 @@ class Context:
     def comm_init(self, unique_id: bytes, nranks: int, rank: int):
         buf = C.create_string_buffer(unique_id, 128)
         self._check(lib().liliom_comm_init(self._h, buf, nranks, rank))
+
+    def comm_peer_export(self) -> bytes:
+        """64-byte IPC handle of this rank's exchange buffer (fused multi-GPU exchange, include/liliom.h)."""
+        buf = C.create_string_buffer(64)
+        self._check(lib().liliom_comm_peer_export(self._h, buf))
+        return buf.raw
+
+    def comm_peer_attach(self, handles, rank: int):
+        """handles: the exported handles of all ranks in rank order (e.g. from dist.all_gather_object)."""
+        blob = b"".join(handles)
+        buf = C.create_string_buffer(blob, len(blob))
+        self._check(lib().liliom_comm_peer_attach(self._h, buf, len(handles), rank))
 
     def counters(self, reset: bool = False) -> Counters:
         c = Counters()

@@ -55,6 +55,12 @@ int nccl_allreduce_sum_f64(liliom_ctx* c, double* buf, int count) {
 void nccl_destroy(liliom_ctx* c) {
     if (c->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->nccl_comm);
     c->nccl_comm = nullptr;
+    for (int p = 0; p < kMaxPeers; ++p) {      // peer mappings of the fused exchange (own buffer is a DevBuf)
+        if (c->peer_ptrs[p] && c->peer_ptrs[p] != c->peer_buf.p) cudaIpcCloseMemHandle(c->peer_ptrs[p]);
+        c->peer_ptrs[p] = nullptr;
+    }
+    c->peer_ready = false;
+    c->peer_buf.release();
 }
 
 }  // namespace lili
@@ -82,5 +88,47 @@ extern "C" int liliom_comm_init(liliom_ctx* c, const void* id128, int nranks, in
     c->nccl_comm = comm;
     c->nranks = nranks;
     c->rank = rank;
+    return LILIOM_OK;
+}
+
+// ---- fused exchange over NVLink / NVSwitch peer memory (SURVEY.md §8 e, "one kernel that does both") -------------------------
+// The NCCL path costs, per GN iteration, a kernel, an all-reduce of 232 bytes (~20 us of latency on 2 B200s, more than the
+// sharded search saves at 1.4k queries) and an update kernel.  Here every rank runs its persistent GN kernel; after the local
+// grid reduction block 0 stores the rank's 29 sums straight into EVERY peer's exchange buffer (flag-in-data words, system scope)
+// and all blocks read the ranks' sums from their own buffer: all iterations of a scan in one launch per rank, no collective call.
+static size_t peer_buf_bytes() { return (size_t)2 * lili::kMaxPeers * 32 * sizeof(ulonglong2); }
+
+extern "C" int liliom_comm_peer_export(liliom_ctx* c, void* handle64) {
+    if (!c || !handle64) return LILIOM_E_ARG;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    LILI_CUDA(c, cudaSetDevice(c->device));
+    if (!c->peer_buf.p) {
+        LILI_CUDA(c, c->peer_buf.ensure(peer_buf_bytes()));
+        LILI_CUDA(c, cudaMemset(c->peer_buf.p, 0, c->peer_buf.cap));      // epochs start at 1: a zero word never matches
+        c->peer_epoch = 0;
+    }
+    cudaIpcMemHandle_t h;
+    LILI_CUDA(c, cudaIpcGetMemHandle(&h, c->peer_buf.p));
+    memcpy(handle64, &h, 64);
+    return LILIOM_OK;
+}
+
+extern "C" int liliom_comm_peer_attach(liliom_ctx* c, const void* handles, int nranks, int rank) {
+    if (!c || !handles || nranks < 1 || nranks > lili::kMaxPeers || rank < 0 || rank >= nranks) return LILIOM_E_ARG;
+    LILI_CUDA(c, cudaSetDevice(c->device));
+    if (!c->peer_buf.p) { c->last_error = "liliom_comm_peer_attach: call liliom_comm_peer_export first"; return LILIOM_E_ARG; }
+    if (c->nranks != nranks || c->rank != rank) {
+        if (nranks > 1 && !c->nccl_comm) { c->last_error = "liliom_comm_peer_attach: call liliom_comm_init first (map sharding and the map-size guard use it)"; return LILIOM_E_ARG; }
+        if (nranks > 1) { c->last_error = "liliom_comm_peer_attach: nranks/rank differ from liliom_comm_init"; return LILIOM_E_ARG; }
+    }
+    for (int p = 0; p < nranks; ++p) {
+        if (p == rank) { c->peer_ptrs[p] = c->peer_buf.p; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char*)handles + (size_t)p * 64, 64);
+        void* ptr = nullptr;
+        LILI_CUDA(c, cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+        c->peer_ptrs[p] = ptr;
+    }
+    c->peer_ready = true;
     return LILIOM_OK;
 }

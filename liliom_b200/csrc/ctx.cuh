@@ -47,6 +47,16 @@ struct GridDesc {
     int   ncells;
 };
 
+// Fused multi-GPU exchange (single node): pointers to every rank's exchange buffer (own entry = own buffer), see
+// peer_exchange() in grid_knn.cu.  Passed to the persistent GN kernel by value.
+constexpr int kMaxPeers = 16;
+struct PeerArgs {
+    ulonglong2* buf[kMaxPeers];
+    int nranks, rank;
+    unsigned int epoch0;       // epoch of iteration 0 of this launch (monotonic across launches, identical on all ranks)
+    int enabled;
+};
+
 constexpr int kStatsDoubles = 40;   // per outer iteration on the device: n_corr, lm_iters, cost, 27, pose7, pad
 constexpr int kNormEq = 29;         // 21 + 6 + cost + count
 
@@ -133,6 +143,10 @@ struct liliom_ctx {
     // ---- multi-GPU ----
     void* nccl_comm = nullptr;
     int nranks = 1, rank = 0;
+    lili::DevBuf peer_buf;               // this rank's exchange buffer: [2 parities][kMaxPeers][32] {epoch|lo32, epoch|hi32}
+    void* peer_ptrs[lili::kMaxPeers] = {};   // every rank's buffer as mapped into this process (cudaIpcOpenMemHandle)
+    bool peer_ready = false;
+    unsigned int peer_epoch = 0;         // last epoch issued
 
     // ---- instrumentation ----
     liliom_counters cnt{};

@@ -222,6 +222,7 @@ struct KnnSmem {
     float4 nb[kWarps][2][5];     // FLAT shape (two queries per warp task): the 5 neighbours handed over by the search
     int nb_flag[kWarps][2];
     double red[kWarps][kNormEq];
+    double xch[kMaxPeers][kNormEq];   // fused multi-GPU exchange: every rank's 29 sums before they are added in rank order
     unsigned long long red_cand[kWarps];
     double pose[8];
     int is_last;
@@ -449,6 +450,47 @@ __device__ __forceinline__ void reduce_partials(const KnnArgs& a, KnnSmem& S) {
     __syncthreads();
 }
 
+// ---- fused multi-GPU exchange (persistent kernel; liliom_comm_peer_attach) -----------------------------------------------
+// Every 8-byte word carries the pass's epoch in its upper half (a double travels as {epoch|lo32, epoch|hi32}): an aligned 8-byte
+// store is single-copy atomic, so a reader that sees the epoch sees the data — no fence and no flag word.  Stores and loads are
+// system scope (the writer is another GPU over NVLink).  Two buffers alternate by epoch parity: a rank can publish pass e+1 only
+// after it has read every rank's pass e, i.e. after every block of every rank has finished reading pass e-1 (they pass their own
+// grid barrier of pass e before their block 0 publishes).  Epochs grow monotonically across launches and the buffers are zeroed
+// once, so a stale word never matches.  On entry S.red[0][0..28] holds this rank's sums (identical in every block); on return it
+// holds the sums over all ranks, added in rank order (bit-identical on every rank).
+__device__ __forceinline__ void peer_exchange(const PeerArgs& pa, unsigned int epoch, KnnSmem& S) {
+    const size_t base = (size_t)(epoch & 1u) * kMaxPeers * 32;
+    if (blockIdx.x == 0 && threadIdx.x < kNormEq) {
+        const double v = S.red[0][threadIdx.x];
+        const u64 w0 = ((u64)epoch << 32) | (u64)(unsigned)__double2loint(v);
+        const u64 w1 = ((u64)epoch << 32) | (u64)(unsigned)__double2hiint(v);
+        for (int p = 0; p < pa.nranks; ++p) {
+            ulonglong2* dst = pa.buf[p] + base + (size_t)pa.rank * 32 + threadIdx.x;
+            asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(dst), "l"(w0), "l"(w1) : "memory");
+        }
+    }
+    for (int t = threadIdx.x; t < pa.nranks * kNormEq; t += blockDim.x) {
+        const int r = t / kNormEq, k = t - r * kNormEq;
+        const ulonglong2* src = pa.buf[pa.rank] + base + (size_t)r * 32 + k;
+        u64 w0 = 0, w1 = 0;
+        unsigned int spins = 0;
+        while (true) {
+            asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(src) : "memory");
+            if ((unsigned int)(w0 >> 32) == epoch && (unsigned int)(w1 >> 32) == epoch) break;
+            if (++spins > (1u << 24)) { w0 = w1 = 0x7ff8000000000000ull; break; }   // a lost peer must end in a NaN pose, never in a hung GPU
+            __nanosleep(20);
+        }
+        S.xch[r][k] = __hiloint2double((int)(unsigned int)w1, (int)(unsigned int)w0);
+    }
+    __syncthreads();
+    if (threadIdx.x < kNormEq) {
+        double v = 0.0;
+        for (int r = 0; r < pa.nranks; ++r) v += S.xch[r][threadIdx.x];
+        S.red[0][threadIdx.x] = v;
+    }
+    __syncthreads();
+}
+
 // One thread: 6x6 solve of the reduced normal equations in S.red[0], Plus, sign-unify -> xn.
 __device__ __forceinline__ void gn_step(const KnnSmem& S, const Q4& q, const D3& t, double xn[7]) {
     double s[kNormEq];
@@ -573,7 +615,7 @@ __global__ void __launch_bounds__(kBlock, 2) k_knn_plane(KnnArgs a) {
 #define LILI_GN_BOUNDS __maxnreg__(LILI_GN_MAXNREG)
 template <int LANES, bool FLAT = false>
 __global__ void LILI_GN_BOUNDS k_gn_persistent(KnnArgs a, int iters, unsigned int* bar, double* stats_base, unsigned int bar_base,
-                                                             int sync_mode) {
+                                                             int sync_mode, PeerArgs pa) {
     __shared__ __align__(16) KnnSmem S;
     extern __shared__ __align__(16) unsigned char dyn_smem[];   // flat == 2: [kFlatBatch][kBlock] float4 candidates + [kBlock] int4 tags
     const int n_q = a.n_dev ? min(*a.n_dev, a.n) : a.n;
@@ -651,6 +693,7 @@ __global__ void LILI_GN_BOUNDS k_gn_persistent(KnnArgs a, int iters, unsigned in
             if (stamp) a.dbg[19] = clock64();
             reduce_partials(a, S);
         }
+        if (pa.enabled) peer_exchange(pa, pa.epoch0 + (unsigned int)it, S);     // multi-GPU: this rank's sums -> sums over all ranks
         if (stamp) a.dbg[20] = clock64();
         double* stats = stats_base ? stats_base + (size_t)it * kStatsDoubles : nullptr;
         if (threadIdx.x == 0) {
@@ -990,7 +1033,8 @@ int s2m_run(liliom_ctx* c, double pose7[7], int match_cnt, int max_num_iter, int
     }
 
     // ---- single-GPU GN: all iterations in one cooperative launch
-    const bool persistent = mode == LILIOM_MODE_GN && c->nranks == 1 && iters > 0 && !want_corr &&
+    const bool peer = c->peer_ready && c->peer_ptrs[c->rank] != nullptr;       // fused exchange instead of ncclAllReduce + k_gn_update
+    const bool persistent = mode == LILIOM_MODE_GN && (c->nranks == 1 || peer) && iters > 0 && !want_corr &&
                             !getenv("LILIOM_NO_PERSISTENT") && grid <= c->sm_count;
     // LILIOM_FAST_IO=1 (opt-in until measured): the persistent launch carries the start pose in its parameters and leaves
     // pose, query count and VoxelGrid verdict in one device block, so the call needs no H2D copy and one D2H copy of 432 B
@@ -1012,7 +1056,14 @@ int s2m_run(liliom_ctx* c, double pose7[7], int match_cnt, int max_num_iter, int
         double* stats_base = c->stats_dev.as<double>();
         unsigned int bar_base = c->bar_arrivals;
         int sync_mode = c->gn_sync;    // 3: release-only counter barrier (default) | 0: counter barrier with full fences
-        void* kargs[] = {&a, &iters_arg, &bar, &stats_base, &bar_base, &sync_mode};
+        PeerArgs pa{};
+        if (peer) {
+            for (int p = 0; p < c->nranks; ++p) pa.buf[p] = reinterpret_cast<ulonglong2*>(c->peer_ptrs[p]);
+            pa.nranks = c->nranks; pa.rank = c->rank; pa.enabled = 1;
+            pa.epoch0 = c->peer_epoch + 1u;          // every rank makes the same sequence of calls: same epochs everywhere
+            c->peer_epoch += (unsigned int)iters;
+        }
+        void* kargs[] = {&a, &iters_arg, &bar, &stats_base, &bar_base, &sync_mode, &pa};
         const void* fn = (lanes == 16 && a.flat) ? (const void*)k_gn_persistent<16, true>
                        : lanes == 16 ? (const void*)k_gn_persistent<16> : lanes == 1 ? (const void*)k_gn_persistent<1>
                        : lanes == 2 ? (const void*)k_gn_persistent<2> : lanes == 4 ? (const void*)k_gn_persistent<4>

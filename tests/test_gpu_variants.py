@@ -13,7 +13,7 @@ VARIANTS = [(0, 3), (0, 0), (1, 3), (1, 0), (2, 3), (2, 0)]
 # switches that have not been measured on a B200 yet (written after the round's GPU budget was spent) join the matrix only on request
 EXTRA = {}
 if os.environ.get("LILIOM_TEST_EXPERIMENTAL"):
-    VARIANTS += [(0, 13), (1, 10)]                  # +10: LILIOM_FAST_IO=1 on top of the sync mode
+    VARIANTS += [(0, 13), (1, 10), (0, 23)]         # +10: LILIOM_FAST_IO=1 on top of the sync mode; +20: fused peer exchange with itself
     EXTRA = {"LILIOM_FAST_IO": "1"}
 
 
@@ -22,9 +22,12 @@ def _ctx(flat, ll):
     keys = ("LILIOM_KNN_FLAT", "LILIOM_GN_SYNC", "LILIOM_FAST_IO")
     old = {k: os.environ.get(k) for k in keys}
     os.environ["LILIOM_KNN_FLAT"] = str(flat); os.environ["LILIOM_GN_SYNC"] = str(ll % 10)
-    os.environ["LILIOM_FAST_IO"] = "1" if ll >= 10 else "0"
+    os.environ["LILIOM_FAST_IO"] = "1" if 10 <= ll < 20 else "0"
     try:
-        return L.Context(variant=0)          # the switches are read at liliom_create
+        c = L.Context(variant=0)             # the switches are read at liliom_create
+        if ll >= 20:                         # one rank exchanging with itself: the whole protocol on a single GPU
+            c.comm_peer_attach([c.comm_peer_export()], 0)
+        return c
     finally:
         for k, v in old.items():
             if v is None:

@@ -26,6 +26,10 @@ ctx = L.Context(variant=0, device=lr)
 uid = [L.comm_get_unique_id() if rank == 0 else None]
 dist.broadcast_object_list(uid, src=0)
 ctx.comm_init(uid[0], world, rank)
+if os.environ.get("LILIOM_PEER"):      # fused exchange over peer memory instead of ncclAllReduce + update kernel per iteration
+    hs = [None] * world
+    dist.all_gather_object(hs, ctx.comm_peer_export())
+    ctx.comm_peer_attach(hs, rank)
 ctx.map_set_points(m)
 pose, st = ctx.scan_to_map(ds, guess, 10, mode=L.MODE_GN)
 dt = np.linalg.norm(pose[4:] - pose_ref[4:]); dq = 1 - abs(np.dot(pose[:4], pose_ref[:4]))
@@ -57,6 +61,10 @@ shard = L.Context(variant=0, device=lr)
 uid2 = [L.comm_get_unique_id() if rank == 0 else None]
 dist.broadcast_object_list(uid2, src=0)
 shard.comm_init(uid2[0], world, rank)
+if os.environ.get("LILIOM_PEER"):
+    hs2 = [None] * world
+    dist.all_gather_object(hs2, shard.comm_peer_export())
+    shard.comm_peer_attach(hs2, rank)
 p_shard, m_shard = run_sequence(shard)
 d = float(np.abs(p_shard - p_single).max())
 allp = [None] * world
