@@ -458,9 +458,10 @@ __device__ __forceinline__ void reduce_partials(const KnnArgs& a, KnnSmem& S) {
 // grid barrier of pass e before their block 0 publishes).  Epochs grow monotonically across launches and the buffers are zeroed
 // once, so a stale word never matches.  On entry S.red[0][0..28] holds this rank's sums (identical in every block); on return it
 // holds the sums over all ranks, added in rank order (bit-identical on every rank).
-__device__ __forceinline__ void peer_exchange(const PeerArgs& pa, unsigned int epoch, KnnSmem& S) {
+// `writer`: the block that publishes (block 0 of the persistent kernel; the last block of the per-iteration kernel, the only caller there).
+__device__ __forceinline__ void peer_exchange(const PeerArgs& pa, unsigned int epoch, KnnSmem& S, bool writer) {
     const size_t base = (size_t)(epoch & 1u) * kMaxPeers * 32;
-    if (blockIdx.x == 0 && threadIdx.x < kNormEq) {
+    if (writer && threadIdx.x < kNormEq) {
         const double v = S.red[0][threadIdx.x];
         const u64 w0 = ((u64)epoch << 32) | (u64)(unsigned)__double2loint(v);
         const u64 w1 = ((u64)epoch << 32) | (u64)(unsigned)__double2hiint(v);
@@ -557,7 +558,7 @@ __global__ void __launch_bounds__(kBlock, 4) k_knn_search(KnnArgs a) {
 }
 
 template <int LANES, bool FLAT = false>
-__global__ void __launch_bounds__(kBlock, 2) k_knn_plane(KnnArgs a) {
+__global__ void __launch_bounds__(kBlock, 2) k_knn_plane(KnnArgs a, PeerArgs pa) {
     __shared__ __align__(16) KnnSmem S;
     LILI_STAMP(0);
     const Q4 q{a.pose[0], a.pose[1], a.pose[2], a.pose[3]};
@@ -581,6 +582,7 @@ __global__ void __launch_bounds__(kBlock, 2) k_knn_plane(KnnArgs a) {
     LILI_STAMP_LAST(5);
     // ---------------- last block: fixed-order sum over blocks, then the 6x6 step
     reduce_partials(a, S);
+    if (pa.enabled) peer_exchange(pa, pa.epoch0, S, true);      // multi-GPU, one launch per iteration: the last block trades sums with the peers
     LILI_STAMP_LAST(6);
     if (threadIdx.x == 0) {
         *a.ticket = 0;
@@ -693,7 +695,7 @@ __global__ void LILI_GN_BOUNDS k_gn_persistent(KnnArgs a, int iters, unsigned in
             if (stamp) a.dbg[19] = clock64();
             reduce_partials(a, S);
         }
-        if (pa.enabled) peer_exchange(pa, pa.epoch0 + (unsigned int)it, S);     // multi-GPU: this rank's sums -> sums over all ranks
+        if (pa.enabled) peer_exchange(pa, pa.epoch0 + (unsigned int)it, S, blockIdx.x == 0);     // multi-GPU: this rank's sums -> sums over all ranks
         if (stamp) a.dbg[20] = clock64();
         double* stats = stats_base ? stats_base + (size_t)it * kStatsDoubles : nullptr;
         if (threadIdx.x == 0) {
@@ -1102,7 +1104,16 @@ int s2m_run(liliom_ctx* c, double pose7[7], int match_cnt, int max_num_iter, int
     for (int it = 0; it < launches; ++it) {
         a.stats = c->stats_dev.as<double>() + (size_t)it * kStatsDoubles;
         const bool multi = c->nranks > 1;
-        a.update_pose = (mode == LILIOM_MODE_GN && !multi && iters > 0) ? 1 : 0;
+        // fused exchange, one launch per iteration (large scans: grid > one block per SM): the last block trades the sums with the
+        // peers and performs the GN step itself — no ncclAllReduce, no update kernel
+        const bool peer_iter = peer && multi && mode == LILIOM_MODE_GN && iters > 0;
+        PeerArgs pit{};
+        if (peer_iter) {
+            for (int p = 0; p < c->nranks; ++p) pit.buf[p] = reinterpret_cast<ulonglong2*>(c->peer_ptrs[p]);
+            pit.nranks = c->nranks; pit.rank = c->rank; pit.enabled = 1;
+            pit.epoch0 = ++c->peer_epoch;
+        }
+        a.update_pose = (mode == LILIOM_MODE_GN && (!multi || peer_iter) && iters > 0) ? 1 : 0;
         size_t ev = 0;
         if (c->time_kernels) {
             if (c->ev_used + 2 > c->ev_pool.size()) {
@@ -1117,15 +1128,15 @@ int s2m_run(liliom_ctx* c, double pose7[7], int match_cnt, int max_num_iter, int
             LILI_TRY(launch_check(c, "k_knn_search"));
             a.fit_only = 1;
             a.cand_total = nullptr;
-            k_knn_plane<1><<<grid, kBlock, 0, c->stream>>>(a);
+            k_knn_plane<1><<<grid, kBlock, 0, c->stream>>>(a, pit);
             a.fit_only = 0;
             a.cand_total = sa.cand_total;
-        } else if (lanes == 16 && a.flat) k_knn_plane<16, true><<<grid, kBlock, 0, c->stream>>>(a);
-        else if (lanes == 16) k_knn_plane<16><<<grid, kBlock, 0, c->stream>>>(a);
-        else if (lanes == 1) k_knn_plane<1><<<grid, kBlock, 0, c->stream>>>(a);
-        else if (lanes == 2) k_knn_plane<2><<<grid, kBlock, 0, c->stream>>>(a);
-        else if (lanes == 4) k_knn_plane<4><<<grid, kBlock, 0, c->stream>>>(a);
-        else k_knn_plane<8><<<grid, kBlock, 0, c->stream>>>(a);
+        } else if (lanes == 16 && a.flat) k_knn_plane<16, true><<<grid, kBlock, 0, c->stream>>>(a, pit);
+        else if (lanes == 16) k_knn_plane<16><<<grid, kBlock, 0, c->stream>>>(a, pit);
+        else if (lanes == 1) k_knn_plane<1><<<grid, kBlock, 0, c->stream>>>(a, pit);
+        else if (lanes == 2) k_knn_plane<2><<<grid, kBlock, 0, c->stream>>>(a, pit);
+        else if (lanes == 4) k_knn_plane<4><<<grid, kBlock, 0, c->stream>>>(a, pit);
+        else k_knn_plane<8><<<grid, kBlock, 0, c->stream>>>(a, pit);
         LILI_TRY(launch_check(c, "k_knn_plane"));
         if (c->time_kernels) {
             LILI_CUDA(c, cudaEventRecord(c->ev_pool[ev + 1], c->stream));
@@ -1133,9 +1144,9 @@ int s2m_run(liliom_ctx* c, double pose7[7], int match_cnt, int max_num_iter, int
             c->ev_iters.push_back(1);
         }
         if (iters == 0) break;
-        if (multi) LILI_TRY(nccl_allreduce_sum_f64(c, c->neq.as<double>(), kNormEq));
+        if (multi && !peer_iter) LILI_TRY(nccl_allreduce_sum_f64(c, c->neq.as<double>(), kNormEq));
         if (mode == LILIOM_MODE_GN) {
-            if (multi) {
+            if (multi && !peer_iter) {
                 k_gn_update<<<1, 32, 0, c->stream>>>(c->neq.as<double>(), c->pose_dev.as<double>(), a.stats);
                 LILI_TRY(launch_check(c, "k_gn_update"));
             }
