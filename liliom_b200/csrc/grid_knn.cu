@@ -558,7 +558,7 @@ __global__ void __launch_bounds__(kBlock, 4) k_knn_search(KnnArgs a) {
 }
 
 template <int LANES, bool FLAT = false>
-__global__ void __launch_bounds__(kBlock, 2) k_knn_plane(KnnArgs a, PeerArgs pa) {
+__global__ void __launch_bounds__(kBlock, 2) k_knn_plane(KnnArgs a, const __grid_constant__ PeerArgs pa) {
     __shared__ __align__(16) KnnSmem S;
     LILI_STAMP(0);
     const Q4 q{a.pose[0], a.pose[1], a.pose[2], a.pose[3]};
@@ -617,11 +617,16 @@ __global__ void __launch_bounds__(kBlock, 2) k_knn_plane(KnnArgs a, PeerArgs pa)
 #define LILI_GN_BOUNDS __maxnreg__(LILI_GN_MAXNREG)
 template <int LANES, bool FLAT = false>
 __global__ void LILI_GN_BOUNDS k_gn_persistent(KnnArgs a, int iters, unsigned int* bar, double* stats_base, unsigned int bar_base,
-                                                             int sync_mode, PeerArgs pa) {
+                                                             int sync_mode, const __grid_constant__ PeerArgs pa) {
     __shared__ __align__(16) KnnSmem S;
     extern __shared__ __align__(16) unsigned char dyn_smem[];   // flat == 2: [kFlatBatch][kBlock] float4 candidates + [kBlock] int4 tags
     const int n_q = a.n_dev ? min(*a.n_dev, a.n) : a.n;
-    if (threadIdx.x < 7) S.pose[threadIdx.x] = a.pose_by_value ? a.pose0[threadIdx.x] : a.pose[threadIdx.x];
+    if (threadIdx.x < 7) {
+        // static indices only: a dynamically indexed kernel parameter would be copied to local memory as a whole
+        const int k = threadIdx.x;
+        const double byval = k == 0 ? a.pose0[0] : k == 1 ? a.pose0[1] : k == 2 ? a.pose0[2] : k == 3 ? a.pose0[3] : k == 4 ? a.pose0[4] : k == 5 ? a.pose0[5] : a.pose0[6];
+        S.pose[k] = a.pose_by_value ? byval : a.pose[k];
+    }
     __syncthreads();
     const unsigned int G = gridDim.x;
     // bar_base = arrivals of all previous launches on this context (tracked by the host, advanced by iters*G per launch)
