@@ -53,6 +53,7 @@ def parse():
     ap.add_argument("--e2e", default="two-nodes", choices=["two-nodes", "sequential"],
                     help="e2e leg: two concurrent node threads (reference architecture, default) or one thread calling both nodes in turn")
     ap.add_argument("--dense-queries", action="store_true", help="roofline micro-run: every surf feature is a query (no scan DS)")
+    ap.add_argument("--no-dense-probe", action="store_true", help="skip the short dense-query probe that annotates roofline.dense_probe")
     ap.add_argument("--workload", default="horizon", choices=["horizon", "rot"],
                     help="horizon: BASELINE configs[1] (24k-pt Livox sweep, 1 M-pt map; the metric's config, default); "
                          "rot: configs[2] (130k-pt HDL-64E sweep through the LiLi-OM-ROT extractor, 2 M-pt map)")
@@ -473,6 +474,38 @@ def main():
                 "traffic": traffic, "peak_source": peak_src, "queries_per_launch": qpl, "candidates_per_query": cbar,
                 "algorithmic_bytes_per_launch": bytes_per_launch, "us_per_launch": t_launch * 1e6,
                 "min_bytes_per_launch": qpl * 96.0}
+
+    # ---- the same kernel where it is less latency-bound: every surf feature as a query (no scan down-sampling), a second
+    # short resident run on its own context (N = 1, rank 0, default workload only).  Informational: `roofline` above is the
+    # headline workload's; this shows how the fraction moves with the query count.  Never allowed to break the bench line.
+    if roof is not None and not multi and not args.dense_queries and not rot and not args.no_dense_probe:
+        try:
+            dprm = L.default_params(0); dprm.leaf_scan = 0.0
+            dctx = L.Context(dprm, device=local_rank)
+            dctx.set_stream(stream.cuda_stream)
+            dctx.map_set_points(m)
+            dctx.set_kernel_timing(True)
+            with torch.cuda.stream(stream):
+                for k in range(24):
+                    sw = sweeps[k % len(sweeps)]
+                    dctx.upload_scan(sw["pts"])
+                    flush.fill_(k & 0xff)
+                    dctx.extract_resident(sw["q"])
+                    dctx.odometry_resident(sw["guess"], ITERS, mode=L.MODE_GN, want_stats=False)
+                    if k == 3:
+                        dctx.counters(reset=True)
+            dc = dctx.counters()
+            dctx.close()
+            if dc.knn_launches:
+                dq = dc.knn_queries / dc.knn_launches
+                dcb = dc.knn_candidates / max(dc.knn_queries, 1)
+                db = dq * (16 + 27 * 8 + 16 * dcb)
+                dt_l = dc.knn_ms * 1e-3 / dc.knn_launches
+                roof["dense_probe"] = {"what": "same kernel, every surf feature a query (leaf_scan = 0), 20 scans", "queries_per_launch": dq,
+                                       "candidates_per_query": dcb, "us_per_launch": dt_l * 1e6, "achieved": db / dt_l / 1e9,
+                                       "frac": db / dt_l / 1e9 / peak}
+        except Exception as e:      # noqa: BLE001
+            roof["dense_probe"] = {"error": str(e)[:200]}
 
     if rank != 0:
         if multi:
