@@ -475,13 +475,14 @@ __device__ __forceinline__ void peer_exchange(const PeerArgs& pa, unsigned int e
         const ulonglong2* src = pa.buf[pa.rank] + base + (size_t)r * 32 + k;
         u64 w0 = 0, w1 = 0;
         unsigned int spins = 0;
+        bool lost = false;
         while (true) {
             asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(src) : "memory");
             if ((unsigned int)(w0 >> 32) == epoch && (unsigned int)(w1 >> 32) == epoch) break;
-            if (++spins > (1u << 24)) { w0 = w1 = 0x7ff8000000000000ull; break; }   // a lost peer must end in a NaN pose, never in a hung GPU
+            if (++spins > (1u << 23)) { lost = true; break; }      // ~6 s: a lost peer must end in a NaN pose, never in a hung GPU
             __nanosleep(20);
         }
-        S.xch[r][k] = __hiloint2double((int)(unsigned int)w1, (int)(unsigned int)w0);
+        S.xch[r][k] = lost ? __longlong_as_double(0x7ff8000000000000ll) : __hiloint2double((int)(unsigned int)w1, (int)(unsigned int)w0);
     }
     __syncthreads();
     if (threadIdx.x < kNormEq) {

@@ -31,6 +31,7 @@ if os.environ.get("LILIOM_PEER"):      # fused exchange over peer memory instead
     dist.all_gather_object(hs, ctx.comm_peer_export())
     ctx.comm_peer_attach(hs, rank)
 ctx.map_set_points(m)
+dist.barrier()          # collective call below: with the fused exchange a rank's kernel waits (bounded) for its peers' kernels
 pose, st = ctx.scan_to_map(ds, guess, 10, mode=L.MODE_GN)
 dt = np.linalg.norm(pose[4:] - pose_ref[4:]); dq = 1 - abs(np.dot(pose[:4], pose_ref[:4]))
 sizes = [None] * world
