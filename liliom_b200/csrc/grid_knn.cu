@@ -226,6 +226,7 @@ struct KnnSmem {
     unsigned long long red_cand[kWarps];
     double pose[8];
     int is_last;
+    int peer_lost;               // fused exchange: a peer did not publish within the wait bound -> the pose is poisoned (NaN), the host reports it
 };
 
 #define LILI_STAMP(i) do { if (a.dbg && blockIdx.x == 0 && threadIdx.x == 0) a.dbg[i] = clock64(); } while (0)
@@ -479,7 +480,7 @@ __device__ __forceinline__ void peer_exchange(const PeerArgs& pa, unsigned int e
         while (true) {
             asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(src) : "memory");
             if ((unsigned int)(w0 >> 32) == epoch && (unsigned int)(w1 >> 32) == epoch) break;
-            if (++spins > (1u << 23)) { lost = true; break; }      // ~6 s: a lost peer must end in a NaN pose, never in a hung GPU
+            if (++spins > (1u << 23)) { lost = true; S.peer_lost = 1; break; }      // ~6 s: a lost peer must end in a NaN pose, never in a hung GPU
             __nanosleep(20);
         }
         S.xch[r][k] = lost ? __longlong_as_double(0x7ff8000000000000ll) : __hiloint2double((int)(unsigned int)w1, (int)(unsigned int)w0);
@@ -510,6 +511,10 @@ __device__ __forceinline__ void gn_step(const KnnSmem& S, const Q4& q, const D3&
         for (int k = 0; k < 7; ++k) xn[k] = x[k];
     }
     if (xn[0] < 0) { xn[0] = -xn[0]; xn[1] = -xn[1]; xn[2] = -xn[2]; xn[3] = -xn[3]; }   // :539-549
+    if (S.peer_lost) {
+#pragma unroll
+        for (int k = 0; k < 7; ++k) xn[k] = __longlong_as_double(0x7ff8000000000000ll);
+    }
 }
 
 __device__ __forceinline__ void write_neq_stats(const KnnArgs& a, const KnnSmem& S, double* stats, bool with_stats) {
@@ -561,6 +566,7 @@ __global__ void __launch_bounds__(kBlock, 4) k_knn_search(KnnArgs a) {
 template <int LANES, bool FLAT = false>
 __global__ void __launch_bounds__(kBlock, 2) k_knn_plane(KnnArgs a, const __grid_constant__ PeerArgs pa) {
     __shared__ __align__(16) KnnSmem S;
+    if (threadIdx.x == 0) S.peer_lost = 0;
     LILI_STAMP(0);
     const Q4 q{a.pose[0], a.pose[1], a.pose[2], a.pose[3]};
     const D3 t{a.pose[4], a.pose[5], a.pose[6]};
@@ -622,6 +628,7 @@ __global__ void LILI_GN_BOUNDS k_gn_persistent(KnnArgs a, int iters, unsigned in
     __shared__ __align__(16) KnnSmem S;
     extern __shared__ __align__(16) unsigned char dyn_smem[];   // flat == 2: [kFlatBatch][kBlock] float4 candidates + [kBlock] int4 tags
     const int n_q = a.n_dev ? min(*a.n_dev, a.n) : a.n;
+    if (threadIdx.x == 32) S.peer_lost = 0;
     if (threadIdx.x < 7) {
         // static indices only: a dynamically indexed kernel parameter would be copied to local memory as a whole
         const int k = threadIdx.x;
@@ -1189,6 +1196,10 @@ int s2m_run(liliom_ctx* c, double pose7[7], int match_cnt, int max_num_iter, int
         const VgParams* vp = reinterpret_cast<const VgParams*>(hp + 48);
         c->vg_ncells = vp->overflow ? 0 : (long long)vp->div_b[0] * vp->div_b[1] * vp->div_b[2];
         c->vg_bail = vp->bail != 0;
+    }
+    if (iters > 0 && peer && std::isnan(hp[0])) {
+        c->last_error = "fused exchange: a peer rank did not publish its sums within the wait bound (collective call not entered on every rank?)";
+        return LILIOM_E_NCCL;
     }
     if (iters > 0) for (int k = 0; k < 7; ++k) pose7[k] = hp[k];
     if (out29) for (int k = 0; k < kNormEq; ++k) out29[k] = hp[8 + k];
