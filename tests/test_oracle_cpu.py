@@ -357,3 +357,63 @@ def test_golden_backend_blocks_and_livox(oracle):
     np.testing.assert_allclose(oracle.backend_edge_block(feats, ev, pa, pb, 0.6, g["pose_b"], 1.0), g["edge_block"], rtol=1e-13)
     lv = np.load(os.path.join(GOLD, "livox_small.npz"))
     _same(oracle.convert_livox(lv["records"].view(oracle.LIVOX20).reshape(-1)).view(np.uint8), lv["cloud"])
+
+
+def test_incremental_local_map_is_bit_exact(oracle, world_small):
+    """Design check for SURVEY §8 (f2): a local map maintained INCREMENTALLY (append the newest frame's points to their
+    voxels, drop the oldest frame's, re-sum only the voxels whose membership changed from the front) equals
+    pcl::VoxelGrid of the concatenated <= 20 frames bit for bit, because (i) PCL's voxel of a point is floor(p/leaf)
+    whatever the bounding box, (ii) its output order (ascending i + j*dx + k*dx*dy) is the lexicographic (k, j, i) order of
+    those absolute coordinates, (iii) the centroid is a sequential fp32 sum in concatenation order, which an append extends."""
+    rng = np.random.default_rng(4)
+    surf, _, _ = oracle.extract_horizon(world_small["hz"], world_small["q_hz"])
+    base = oracle.voxelgrid(surf, 0.4)
+    leaf = np.float32(0.4); inv = np.float32(1.0) / leaf
+    frames = []                       # (frame cloud) oldest first
+    vox = {}                          # (kz, ky, kx) -> list of [frame_serial, running fp32 sums per field..., count]; kept as member lists
+    fields = ["x", "y", "z", "nx", "ny", "nz", "intensity", "curvature"]
+
+    def keys_of(cloud):
+        k = np.floor(np.stack([cloud["x"], cloud["y"], cloud["z"]], 1) * inv).astype(np.int64)
+        return [tuple(r[::-1]) for r in k]                     # (kz, ky, kx)
+
+    members = {}                      # key -> list of (serial, point record), concatenation order
+    serial = 0
+    for step in range(26):
+        f = base.copy()
+        f["x"] += np.float32(0.11 * step) + rng.normal(0, 0.02, len(f)).astype(np.float32)
+        f["y"] += np.float32(-0.03 * step)
+        if len(frames) >= 20:                                   # FIFO eviction (LidarOdometry.cpp:290-299)
+            old = frames.pop(0)
+            for kk in set(keys_of(old[1])):
+                members[kk] = [mm for mm in members[kk] if mm[0] != old[0]]
+                if not members[kk]:
+                    del members[kk]
+        frames.append((serial, f))
+        for kk, rec in zip(keys_of(f), f):
+            members.setdefault(kk, []).append((serial, rec))
+        serial += 1
+        if step % 5 != 0 and step < 24:
+            continue
+        ref = oracle.voxelgrid(np.concatenate([c for _, c in frames]), float(leaf))
+        order = sorted(members)
+        assert len(order) == len(ref)
+        got = np.zeros(len(order), oracle.PT48)
+        for o, kk in enumerate(order):
+            acc = {fl: np.float32(0) for fl in fields}
+            for _, rec in members[kk]:
+                for fl in fields:
+                    acc[fl] = np.float32(acc[fl] + rec[fl])
+            n = np.float32(len(members[kk]))
+            for fl in ("x", "y", "z", "intensity", "curvature"):
+                got[fl][o] = acc[fl] / n
+            got["w"][o] = 1.0
+            nx, ny, nz = acc["nx"], acc["ny"], acc["nz"]
+            n2 = np.float32(np.float32(nx * nx + ny * ny) + nz * nz)
+            if n2 > 0:
+                nn = np.sqrt(n2)
+                nx, ny, nz = nx / nn, ny / nn, nz / nn
+            got["nx"][o], got["ny"][o], got["nz"][o] = nx, ny, nz
+        for fl in ("x", "y", "z", "intensity", "curvature"):
+            assert got[fl].tobytes() == ref[fl].tobytes(), (step, fl)
+        np.testing.assert_allclose(np.stack([got["nx"], got["ny"], got["nz"]], 1), np.stack([ref["nx"], ref["ny"], ref["nz"]], 1), atol=2e-7)
