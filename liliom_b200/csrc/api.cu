@@ -78,6 +78,18 @@ __global__ void k_transform_cloud(const unsigned char* __restrict__ in, int n, i
     }
 }
 
+// Concatenation of the FIFO frames (L/src/LidarOdometry.cpp:301-302) in one launch: thread i copies the i-th 16-byte word of the
+// concatenated cloud; off[] are the frames' start offsets in 16-byte words (off[nframes] = total).
+constexpr int kConcatMax = 32;
+struct ConcatTab { const float4* src[kConcatMax]; int off[kConcatMax + 1]; };
+__global__ void k_concat_frames(const __grid_constant__ ConcatTab tab, int nframes, int n16, float4* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n16) return;
+    int f = 0;
+    for (int k = 1; k < nframes; ++k) if (i >= tab.off[k]) f = k;
+    out[i] = tab.src[f][i - tab.off[f]];
+}
+
 __global__ void k_gather_refl48(const unsigned char* __restrict__ pts, int n, float* __restrict__ out) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = reinterpret_cast<const float*>(pts + (size_t)i * 48)[9];
@@ -448,6 +460,15 @@ extern "C" int liliom_map_rebuild(liliom_ctx* c, int* n_map_out) {
     LILI_CUDA(c, c->map_ds.ensure((total > 0 ? total : 1) * stride));
     LILI_CUDA(c, c->vg_count.ensure(16));
     size_t off = 0;
+    if (c->map_coop && c->frames.size() <= (size_t)kConcatMax && total > 0) {      // one gather launch instead of <= 20 small copies
+        ConcatTab tab{};
+        int k = 0;
+        for (auto& f : c->frames) { tab.src[k] = (const float4*)f.buf.p; tab.off[k] = (int)(off * (stride / 16)); off += (size_t)f.n; ++k; }
+        for (; k <= kConcatMax; ++k) tab.off[k] = (int)(off * (stride / 16));
+        const int n16 = (int)(total * (stride / 16));
+        k_concat_frames<<<cdiv(n16, 256), 256, 0, c->stream>>>(tab, (int)c->frames.size(), n16, (float4*)c->map_raw.p);
+        LILI_TRY(launch_check(c, "k_concat_frames"));
+    } else
     for (auto& f : c->frames) {                                                    // :301-302 concatenation, oldest first
         if (f.n) LILI_CUDA(c, cudaMemcpyAsync((unsigned char*)c->map_raw.p + off * stride, f.buf.p, (size_t)f.n * stride, cudaMemcpyDeviceToDevice, c->stream));
         off += (size_t)f.n;
