@@ -417,3 +417,194 @@ def test_incremental_local_map_is_bit_exact(oracle, world_small):
         for fl in ("x", "y", "z", "intensity", "curvature"):
             assert got[fl].tobytes() == ref[fl].tobytes(), (step, fl)
         np.testing.assert_allclose(np.stack([got["nx"], got["ny"], got["nz"]], 1), np.stack([ref["nx"], ref["ny"], ref["nz"]], 1), atol=2e-7)
+
+
+def test_horizon_extractor_second_restatement(oracle, world_small):
+    """An independent NumPy restatement of the binning + patch classifier (L/src/Preprocessing.cpp:238-383), written from the
+    reference source and not from oracle_horizon.cpp, must select the same surf / edge points in the same order.  It starts
+    from the oracle's de-skewed cloud (the slerp is covered elsewhere) and uses numpy's eigvalsh for the two PCA gates, so
+    only a ratio within rounding of a threshold could differ (none does on these sweeps)."""
+    from liliom_b200 import synth
+    for seed in (1, 7):
+        T = np.array(world_small["T"]); T[4] += 0.9 * seed
+        pts, q = synth.make_horizon_sweep(T, seed=seed)
+        surf_o, edge_o, cut_o = oracle.extract_horizon(pts, q, 0.2, 4.0)
+        N_SCANS, H_SCANS = 6, 4000
+        t_interval = 0.1 / (H_SCANS - 1)
+        mat = np.zeros((N_SCANS, H_SCANS), oracle.PT48)                       # zero-initialised like PointXYZINormal mat[][] (+ curvature 0 = empty)
+        for p in cut_o:                                                       # :242-268 (scan_id >= 0 always for the synthetic sweep)
+            scan_id = int(p["intensity"])
+            dep = np.float32(np.float32(p["x"] * p["x"] + p["y"] * p["y"]) + p["z"] * p["z"])       # float products, summed in float (:259)
+            if dep > 40000.0 or dep < 4.0 or p["curvature"] < 0.05 or p["curvature"] > 25.45:
+                continue
+            col = int(np.round(float(np.float32(p["intensity"] - np.float32(scan_id))) / t_interval))   # float - int -> float, / double
+            if col >= H_SCANS or col < 0:
+                continue
+            if mat[scan_id, col]["curvature"] != 0:
+                continue
+            mat[scan_id, col] = p
+        depth = np.sqrt((mat["x"] * mat["x"] + mat["y"] * mat["y"] + mat["z"] * mat["z"]).astype(np.float32)).astype(np.float64)   # getDepth: float
+        curv = mat["curvature"].copy()
+        xyz = np.stack([mat["x"], mat["y"], mat["z"]], -1).astype(np.float64)
+        surf_sel, edge_sel = [], []
+        for i in range(5, H_SCANS - 12, 6):
+            cells = [(k, i + j) for j in range(6) for k in range(N_SCANS) if curv[k, i + j] > 0]
+            if len(cells) < 25:
+                continue
+            P = np.array([xyz[c] for c in cells]); ctr = P.mean(0)
+            ev = np.linalg.eigvalsh((P - ctr).T @ (P - ctr))
+            ids = []
+            for k in range(N_SCANS):
+                max_s, idx = 0.0, i
+                for j in range(6):
+                    if curv[k, i + j] <= 0:
+                        continue
+                    d = depth[k]
+                    g1 = d[i + j - 4] + d[i + j - 3] + d[i + j - 2] + d[i + j - 1] - 8 * d[i + j] + d[i + j + 1] + d[i + j + 2] + d[i + j + 3] + d[i + j + 4]
+                    g1 = g1 / (8 * d[i + j] + 1e-3)
+                    if g1 > 0.06 and g1 > max_s:
+                        max_s, idx = g1, i + j
+                if max_s != 0:
+                    ids.append((k, idx))
+            if len(ids) > 3:
+                E = np.array([xyz[c] for c in ids]); ce = E.mean(0)
+                eve = np.linalg.eigvalsh((E - ce).T @ (E - ce))
+                if eve[2] > 4.0 * eve[1]:
+                    for c in ids:
+                        if curv[c] <= 0 and mat[c]["intensity"] <= 0:
+                            continue
+                        edge_sel.append(c); curv[c] *= -1
+            if ev[0] < 0.2 * ev[1]:
+                for j in range(6):
+                    for k in range(N_SCANS):
+                        if curv[k, i + j] > 0:
+                            surf_sel.append((k, i + j)); curv[k, i + j] *= -1
+        assert len(surf_sel) == len(surf_o) and len(edge_sel) == len(edge_o), (len(surf_sel), len(surf_o), len(edge_sel), len(edge_o))
+        for sel, out in ((surf_sel, surf_o), (edge_sel, edge_o)):
+            got = np.array([[mat[c]["x"], mat[c]["y"], mat[c]["z"]] for c in sel], np.float32).reshape(-1, 3)
+            ref = np.stack([out["x"], out["y"], out["z"]], 1)
+            assert got.tobytes() == ref.tobytes()
+
+
+def test_rot_labelling_second_restatement(oracle, world_small):
+    """Independent NumPy restatement of the ROT curvature / per-segment sort / greedy labelling (R/src/Preprocessing.cpp:377-500),
+    written from the reference source, on the oracle's ring-bucketed de-skewed cloud: curvature and labels bit-exact, the edge
+    cloud (cornerPointsLessSharp) in the same order.  std::sort's tie order is defined as (curvature, index), as everywhere."""
+    for ds_rate in (1, 4):
+        rc, surf_o, edge_o, cut, lab_o, cur_o = oracle.extract_rot(world_small["hdl"], world_small["q_hdl"], (1, 0, 0, 0), 64, ds_rate)
+        assert rc == 0
+        n = len(cut)
+        x, y, z = cut["x"], cut["y"], cut["z"]
+        ring = cut["intensity"].astype(np.int32)
+        N_SCANS = 64
+        counts = np.bincount(ring, minlength=N_SCANS)
+        ends = np.cumsum(counts); starts = ends - counts
+        scanStart = starts + 5; scanEnd = ends - 6                                     # :378-382
+
+        def stencil(a):
+            i = np.arange(5, n - 5)
+            s = a[i - 5] + a[i - 4]; s = s + a[i - 3]; s = s + a[i - 2]; s = s + a[i - 1]
+            s = s - np.float32(10) * a[i]
+            for k in (1, 2, 3, 4, 5):
+                s = s + a[i + k]
+            return s
+        dx, dy, dz = stencil(x), stencil(y), stencil(z)
+        curv = np.zeros(n, np.float32)
+        curv[5:n - 5] = (dx * dx + dy * dy) + dz * dz                                  # :391
+        picked = np.zeros(n + 8, np.int32); label = np.zeros(n, np.int32)
+        r2 = (x * x + y * y) + z * z
+
+        def gap2(a, b):
+            ddx = x[a] - x[b]; ddy = y[a] - y[b]; ddz = z[a] - z[b]
+            return np.float32(np.float32(ddx * ddx + ddy * ddy) + ddz * ddz)
+
+        def suppress(ind):
+            for l in range(1, 6):
+                if gap2(ind + l, ind + l - 1) > 0.05:
+                    break
+                picked[ind + l] = 1
+            for l in range(-1, -6, -1):
+                if gap2(ind + l, ind + l + 1) > 0.05:
+                    break
+                picked[ind + l] = 1
+        edge_order = []
+        for i in range(N_SCANS):
+            if scanEnd[i] - scanStart[i] < 6 or i % ds_rate != 0:
+                continue
+            for j in range(6):
+                sp = scanStart[i] + (scanEnd[i] - scanStart[i]) * j // 6
+                ep = scanStart[i] + (scanEnd[i] - scanStart[i]) * (j + 1) // 6 - 1
+                seg = np.arange(sp, ep + 1)
+                order = seg[np.lexsort((seg, curv[seg]))]
+                big = 0
+                for ind in order[::-1]:
+                    if picked[ind] == 0 and curv[ind] > 2.0:
+                        big += 1
+                        if big <= 2:
+                            label[ind] = 2
+                        elif big <= 10:
+                            label[ind] = 1
+                        else:
+                            break
+                        edge_order.append(ind)
+                        picked[ind] = 1
+                        suppress(ind)
+                small = 0
+                for ind in order:
+                    if r2[ind] < 0.25:
+                        continue
+                    if picked[ind] == 0 and curv[ind] < 0.1:
+                        label[ind] = -1
+                        small += 1
+                        if small >= 4:
+                            break
+                        picked[ind] = 1
+                        suppress(ind)
+        assert curv.tobytes() == cur_o.tobytes()
+        assert np.array_equal(label, lab_o), int((label != lab_o).sum())
+        got = np.stack([x[edge_order], y[edge_order], z[edge_order]], 1)
+        assert got.tobytes() == np.stack([edge_o["x"], edge_o["y"], edge_o["z"]], 1).tobytes()
+
+
+def test_find_surf_corr_second_restatement_on_real_flann(oracle, world_small):
+    """findCorrespondingSurfFeatures (L/src/LidarOdometry.cpp:352-413) restated a second time, from the reference source, on top
+    of third-party code only: the 5-NN come from a real FLANN KDTreeSingleIndex (OpenCV's vendored FLANN, the class PCL wraps),
+    the plane from numpy's least squares.  Accept flags must equal the oracle's, planes agree to fp32 rounding."""
+    cv2 = pytest.importorskip("cv2")
+    if not hasattr(cv2, "flann_Index"):
+        pytest.skip("this OpenCV build has no flann module")
+    surf, _, _ = oracle.extract_horizon(world_small["hz"], world_small["q_hz"])
+    ds = oracle.voxelgrid(surf, 0.4)
+    m = world_small["map"]
+    pose = world_small["guess"]
+    cnt, valid_o, plane_o, idx_o, pw_o = oracle.find_surf_corr(oracle.KdTree(m), ds, pose)
+    # transformPoint (:221-244): Eigen q*p + t in double, stored as float
+    P = np.stack([ds["x"], ds["y"], ds["z"]], 1).astype(np.float64)
+    qv = pose[1:4]; uv = 2.0 * np.cross(qv, P)
+    sel = (P + pose[0] * uv + np.cross(qv, uv) + pose[4:]).astype(np.float32)
+    index = cv2.flann_Index(np.ascontiguousarray(m[:, :3]), dict(algorithm=4, leaf_max_size=15, reorder=True))
+    nn, sqd = index.knnSearch(np.ascontiguousarray(sel), 5, params=dict(checks=-1, eps=0.0, sorted=True))
+    valid = np.zeros(len(sel), np.uint8); plane = np.zeros((len(sel), 4), np.float32)
+    for i in range(len(sel)):
+        if not sqd[i, 4] < 1.0:                                                        # :365
+            continue
+        A = m[nn[i], :3].astype(np.float64)
+        norm, *_ = np.linalg.lstsq(A, -np.ones(5), rcond=None)                         # :375
+        nrm = np.linalg.norm(norm)
+        if not nrm > 0:
+            continue
+        normInverse = 1.0 / nrm; norm = norm / nrm
+        if (np.abs(A @ norm + normInverse) > 0.06).any():                              # :386-393
+            continue
+        s = sel[i]
+        pd = np.float32(norm[0] * s[0] + norm[1] * s[1] + norm[2] * s[2] + normInverse)
+        rng = np.sqrt(np.sqrt(np.float32(np.float32(s[0] * s[0] + s[1] * s[1]) + s[2] * s[2])))   # float overloads (SURVEY App. C.1)
+        weight = np.float32(1 - 0.9 * abs(float(pd)) / float(rng))
+        if weight > 0.4:
+            valid[i] = 1
+            plane[i] = [weight * norm[0], weight * norm[1], weight * norm[2], weight * normInverse]
+    # identical decisions except where a gate sits within rounding of its threshold (different LS solver) or FLANN's tie order differs
+    assert (valid != valid_o).sum() <= 2, int((valid != valid_o).sum())
+    both = (valid == 1) & (valid_o == 1)
+    assert both.sum() > 1000
+    np.testing.assert_allclose(plane[both], plane_o[both], rtol=5e-6, atol=5e-7)
