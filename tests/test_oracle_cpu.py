@@ -608,3 +608,51 @@ def test_find_surf_corr_second_restatement_on_real_flann(oracle, world_small):
     both = (valid == 1) & (valid_o == 1)
     assert both.sum() > 1000
     np.testing.assert_allclose(plane[both], plane_o[both], rtol=5e-6, atol=5e-7)
+
+
+def test_backend_edge_corr_second_restatement_on_real_flann(oracle):
+    """findCorrespondingCornerFeatures (L/src/BackendFusion.cpp:1531-1599; ROT variant adds the dist < 0.1 gate, R:1435-1443)
+    restated from the reference source on real FLANN + numpy.linalg.eigh: same accept flags, same line end points to fp32."""
+    cv2 = pytest.importorskip("cv2")
+    if not hasattr(cv2, "flann_Index"):
+        pytest.skip("this OpenCV build has no flann module")
+    rng = np.random.default_rng(31)
+    segs = []
+    for px in range(-30, 31, 6):
+        for py in (-8.0, 8.0):
+            zz = np.arange(0.0, 6.0, 0.2)
+            segs.append(np.stack([np.full_like(zz, px), np.full_like(zz, py), zz], 1))
+        xx = np.arange(px, px + 6.0, 0.2)
+        segs.append(np.stack([xx, np.full_like(xx, 10.0), np.full_like(xx, 3.0)], 1))
+    m = np.concatenate(segs).astype(np.float32) + rng.normal(0, 0.01, (sum(len(s) for s in segs), 3)).astype(np.float32)
+    m4 = np.ones((len(m), 4), np.float32); m4[:, :3] = m
+    pose = np.array([1.0, 0, 0, 0, 0.0, 0.0, 0.0])
+    feats = np.ones((1200, 4), np.float32)
+    feats[:, :3] = m[rng.integers(0, len(m), 1200)] + rng.normal(0, 0.08, (1200, 3)).astype(np.float32)
+    tree = oracle.KdTree(m4)
+    index = cv2.flann_Index(np.ascontiguousarray(m), dict(algorithm=4, leaf_max_size=15, reorder=True))
+    nn, sqd = index.knnSearch(np.ascontiguousarray(feats[:, :3]), 5, params=dict(checks=-1, eps=0.0, sorted=True))
+    for variant in (0, 1):
+        v_o, pa_o, pb_o = oracle.correspond_edge(tree, feats, pose, variant)
+        v = np.zeros(len(feats), np.uint8); pa = np.zeros((len(feats), 3), np.float32); pb = np.zeros((len(feats), 3), np.float32)
+        for i in range(len(feats)):
+            if not sqd[i, 4] < 1.0:
+                continue
+            P = m[nn[i]].astype(np.float64)
+            c = P.sum(0) / 5.0
+            w, vec = np.linalg.eigh((P - c).T @ (P - c))
+            if not w[2] > 3 * w[1]:
+                continue
+            u = vec[:, 2]
+            A, B = c + 0.1 * u, c - 0.1 * u
+            if variant == 1:
+                lp = feats[i, :3].astype(np.float64)
+                if not np.linalg.norm(np.cross(lp - A, lp - B)) / np.linalg.norm(A - B) < 0.1:
+                    continue
+            v[i] = 1; pa[i] = A; pb[i] = B
+        assert (v != v_o).sum() <= 2 and v.sum() > 300
+        both = (v == 1) & (v_o == 1)
+        # the eigenvector's sign is arbitrary: the end points may be swapped
+        same = np.abs(pa[both] - pa_o[both]).max(1) < 1e-5
+        swapped = np.abs(pa[both] - pb_o[both]).max(1) < 1e-5
+        assert (same | swapped).all()
