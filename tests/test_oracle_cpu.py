@@ -656,3 +656,36 @@ def test_backend_edge_corr_second_restatement_on_real_flann(oracle):
         same = np.abs(pa[both] - pa_o[both]).max(1) < 1e-5
         swapped = np.abs(pa[both] - pb_o[both]).max(1) < 1e-5
         assert (same | swapped).all()
+
+
+def test_voxelgrid_adversarial_inputs_match_numpy(oracle):
+    """pcl::VoxelGrid restatement on inputs the sweeps never produce: negative coordinates, points exactly on voxel faces,
+    duplicates, non-finite points (dropped from the box and from the output), a single point, both strides."""
+    rng = np.random.default_rng(8)
+    for dt, leaf in ((oracle.PT48, 0.4), (oracle.PT32, 0.6), (oracle.PT48, 0.25)):
+        n = 3000
+        c = np.zeros(n, dt)
+        xyz = rng.uniform(-7, 7, (n, 3)).astype(np.float32)
+        xyz[:300] = np.round(xyz[:300] / np.float32(leaf)) * np.float32(leaf)        # exactly on voxel faces
+        xyz[300:400] = xyz[:100]                                                     # duplicates
+        c["x"], c["y"], c["z"] = xyz.T
+        c["intensity"] = rng.uniform(0, 50, n).astype(np.float32)
+        if dt is oracle.PT48:
+            c["curvature"] = rng.uniform(0, 25, n).astype(np.float32)
+        bad = rng.choice(n, 40, replace=False)
+        c["x"][bad[:15]] = np.nan; c["y"][bad[15:30]] = np.inf; c["z"][bad[30:]] = -np.inf
+        got = oracle.voxelgrid(c, leaf)
+        ok = np.isfinite(c["x"]) & np.isfinite(c["y"]) & np.isfinite(c["z"])
+        f = c[ok]
+        inv = np.float32(1.0) / np.float32(leaf)
+        ijk = np.floor(np.stack([f["x"], f["y"], f["z"]], 1) * inv).astype(np.int64)
+        mn = ijk.min(0); div = ijk.max(0) - mn + 1
+        idx = (ijk[:, 0] - mn[0]) + (ijk[:, 1] - mn[1]) * div[0] + (ijk[:, 2] - mn[2]) * div[0] * div[1]
+        uniq, inv_idx, counts = np.unique(idx, return_inverse=True, return_counts=True)
+        assert len(got) == len(uniq)
+        for fld in ("x", "y", "z", "intensity"):
+            acc = np.zeros(len(uniq), np.float32)
+            np.add.at(acc, inv_idx, f[fld])
+            np.testing.assert_array_equal(got[fld], acc / counts.astype(np.float32))
+    one = np.zeros(1, oracle.PT48); one["x"] = 1.5; one["curvature"] = 3
+    assert len(oracle.voxelgrid(one, 0.4)) == 1 and len(oracle.voxelgrid(one[:0], 0.4)) == 0
