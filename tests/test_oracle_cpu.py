@@ -689,3 +689,30 @@ def test_voxelgrid_adversarial_inputs_match_numpy(oracle):
             np.testing.assert_array_equal(got[fld], acc / counts.astype(np.float32))
     one = np.zeros(1, oracle.PT48); one["x"] = 1.5; one["curvature"] = 3
     assert len(oracle.voxelgrid(one, 0.4)) == 1 and len(oracle.voxelgrid(one[:0], 0.4)) == 0
+
+
+def test_horizon_deskew_second_restatement(oracle, world_small):
+    """undistortion (L/src/Preprocessing.cpp:104-127) restated in NumPy from the reference source: slerp(Identity -> q_iMU) by the
+    fractional part of `intensity` over 0.1 s, Eigen's un-normalised q * v.  The oracle's cutted cloud must agree to fp32 rounding
+    (numpy's acos / sin are not glibc's bit for bit, so this is a 1-ulp-of-fp32 check, not a bit-exact one)."""
+    pts, q = world_small["hz"], np.asarray(world_small["q_hz"], np.float64)
+    _, _, cut = oracle.extract_horizon(pts, q)
+    assert len(cut) == len(pts)                                   # no NaN / closer-than-0.1 m points in the synthetic sweep
+    inten = pts["intensity"].astype(np.float64)
+    ratio = np.minimum((inten - np.floor(inten)) / 0.1, 1.0)       # float intensity - int line, in double (:106-112)
+    d = q[0]                                                       # Identity . q_iMU
+    absd = abs(d)
+    if absd >= 1.0 - np.finfo(np.float64).eps:
+        s0, s1 = 1.0 - ratio, ratio
+    else:
+        th = np.arccos(absd); sth = np.sin(th)
+        s0 = np.sin((1.0 - ratio) * th) / sth; s1 = np.sin(ratio * th) / sth
+    if d < 0:
+        s1 = -s1
+    qs = np.stack([s0 + s1 * q[0], s1 * q[1], s1 * q[2], s1 * q[3]], 1)             # s0 * Identity + s1 * q_iMU, not re-normalised
+    P = np.stack([pts["x"], pts["y"], pts["z"]], 1).astype(np.float64)
+    uv = 2.0 * np.cross(qs[:, 1:], P)
+    out = (P + qs[:, :1] * uv + np.cross(qs[:, 1:], uv)).astype(np.float32)
+    ref = np.stack([cut["x"], cut["y"], cut["z"]], 1)
+    assert np.abs(out.view(np.int32) - ref.view(np.int32)).max() <= 1              # within one fp32 ulp
+    assert np.array_equal(cut["intensity"], pts["intensity"]) and np.array_equal(cut["curvature"], pts["curvature"])
