@@ -771,3 +771,46 @@ def test_rot_ring_and_time_assignment_on_glibc(oracle, world_small):
     got = np.array([v for b in buckets for v in b], np.float32)
     assert len(got) == len(cut)
     assert got.tobytes() == cut["intensity"].tobytes()
+
+
+def test_pose_glue_second_restatement(oracle):
+    """poseInitialization / computeRelative / transformCloud (L/src/LidarOdometry.cpp:415-480, 246-278) against plain NumPy
+    quaternion algebra written from the reference source (Hamilton product, Eigen's q*v, inverse = conjugate / squared norm)."""
+    import ctypes as C
+    rng = np.random.default_rng(12)
+
+    def qmul(a, b):
+        return np.array([a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3], a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2],
+                         a[0] * b[2] + a[2] * b[0] + a[3] * b[1] - a[1] * b[3], a[0] * b[3] + a[3] * b[0] + a[1] * b[2] - a[2] * b[1]])
+
+    def qrot(q, v):
+        uv = 2.0 * np.cross(q[1:], v)
+        return v + q[0] * uv + np.cross(q[1:], uv)
+    L = oracle.lib()
+    for _ in range(50):
+        a = rng.normal(size=7); a[:4] /= np.linalg.norm(a[:4]) * rng.uniform(0.999, 1.001)     # almost-unit, as accumulated in the node
+        r = rng.normal(size=7); r[:4] /= np.linalg.norm(r[:4])
+        out = np.zeros(7)
+        L.orc_pose_compose(oracle._d(a), oracle._d(r), oracle._d(out))                          # t0 = q0*dt + t0 ; q0 = q0*dq
+        np.testing.assert_allclose(out[:4], qmul(a[:4], r[:4]), rtol=0, atol=1e-15)
+        np.testing.assert_allclose(out[4:], qrot(a[:4], r[4:]) + a[4:], rtol=0, atol=1e-14)
+        rel = np.zeros(7)
+        L.orc_pose_relative(oracle._d(a), oracle._d(out), oracle._d(rel))                       # q1^-1 * q2 ; q1^-1 * (t2 - t1)
+        qi = np.array([a[0], -a[1], -a[2], -a[3]]) / np.dot(a[:4], a[:4])
+        np.testing.assert_allclose(rel[:4], qmul(qi, out[:4]), rtol=0, atol=1e-14)
+        np.testing.assert_allclose(rel[4:], qrot(qi, out[4:] - a[4:]), rtol=0, atol=1e-13)
+    # transformCloud: xyz rotated + translated (double, stored float), normals rotated only (48-byte layout)
+    c = np.zeros(200, oracle.PT48)
+    c["x"], c["y"], c["z"] = rng.uniform(-30, 30, (3, 200)).astype(np.float32)
+    nrm = rng.normal(size=(200, 3)); nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    c["nx"], c["ny"], c["nz"] = nrm.T.astype(np.float32)
+    c["intensity"] = 3.5; c["curvature"] = 1.25
+    pose = rng.normal(size=7); pose[:4] /= np.linalg.norm(pose[:4])
+    t = oracle.transform_cloud(c, pose)
+    P = np.stack([c["x"], c["y"], c["z"]], 1).astype(np.float64)
+    N = np.stack([c["nx"], c["ny"], c["nz"]], 1).astype(np.float64)
+    ref_p = np.array([qrot(pose[:4], p) + pose[4:] for p in P]).astype(np.float32)
+    ref_n = np.array([qrot(pose[:4], v) for v in N]).astype(np.float32)
+    assert np.abs(np.stack([t["x"], t["y"], t["z"]], 1).view(np.int32) - ref_p.view(np.int32)).max() <= 1
+    np.testing.assert_allclose(np.stack([t["nx"], t["ny"], t["nz"]], 1), ref_n, atol=1e-6)
+    assert (t["intensity"] == 3.5).all() and (t["curvature"] == 1.25).all()
