@@ -1,6 +1,7 @@
 // C ABI of libliliom_b200.so (see include/liliom.h for the contract and reference citations).
 #include "ctx.cuh"
 #include "dev_math.cuh"
+#include "knn_core.cuh"
 #include <new>
 #include <cstdlib>
 
@@ -8,13 +9,9 @@ namespace lili {
 void nccl_destroy(liliom_ctx* c);
 int nccl_allreduce_sum_f64(liliom_ctx* c, double* buf, int count);
 
-// ---- map sharding (multi-GPU): keep a point when any 16 m block touched by its halo box is owned by `rank`
-__device__ __forceinline__ unsigned sh_block_hash(int bx, int by, int bz) {
-    unsigned h = (unsigned)bx * 73856093u ^ (unsigned)by * 19349663u ^ (unsigned)bz * 83492791u;
-    h ^= h >> 15; h *= 0x2c1b3c6du; h ^= h >> 12;
-    return h;
-}
-__global__ void k_shard_flags(const float4* __restrict__ p, int n, float halo, int nranks, int rank, int* __restrict__ flags) {
+// ---- map sharding (multi-GPU): keep a point when any shard block (cube of 1/inv_block metres, default 16 m) touched by its
+// halo box is owned by `rank` (same hash as owner_of() in knn_core.cuh)
+__global__ void k_shard_flags(const float4* __restrict__ p, int n, float halo, float inv_block, int nranks, int rank, int* __restrict__ flags) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i > n) return;
     int f = 0;
@@ -22,14 +19,14 @@ __global__ void k_shard_flags(const float4* __restrict__ p, int n, float halo, i
         float4 v = p[i];
         for (int c = 0; c < 8 && !f; ++c) {
             float x = v.x + ((c & 1) ? halo : -halo), y = v.y + ((c & 2) ? halo : -halo), z = v.z + ((c & 4) ? halo : -halo);
-            int bx = (int)floorf(x * 0.0625f), by = (int)floorf(y * 0.0625f), bz = (int)floorf(z * 0.0625f);
-            if ((int)(sh_block_hash(bx, by, bz) % (unsigned)nranks) == rank) f = 1;
+            if (owner_of(x, y, z, nranks, inv_block) == rank) f = 1;
         }
     }
     flags[i] = f;
 }
 // same rule on PCL-layout points (stride bytes): used by the sharded liliom_map_push_frame
-__global__ void k_shard_flags_strided(const unsigned char* __restrict__ p, int n, int stride, float halo, int nranks, int rank, int* __restrict__ flags) {
+__global__ void k_shard_flags_strided(const unsigned char* __restrict__ p, int n, int stride, float halo, float inv_block, int nranks, int rank,
+                                      int* __restrict__ flags) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i > n) return;
     int f = 0;
@@ -37,8 +34,7 @@ __global__ void k_shard_flags_strided(const unsigned char* __restrict__ p, int n
         const float4 v = *reinterpret_cast<const float4*>(p + (size_t)i * stride);
         for (int c = 0; c < 8 && !f; ++c) {
             float x = v.x + ((c & 1) ? halo : -halo), y = v.y + ((c & 2) ? halo : -halo), z = v.z + ((c & 4) ? halo : -halo);
-            int bx = (int)floorf(x * 0.0625f), by = (int)floorf(y * 0.0625f), bz = (int)floorf(z * 0.0625f);
-            if ((int)(sh_block_hash(bx, by, bz) % (unsigned)nranks) == rank) f = 1;
+            if (owner_of(x, y, z, nranks, inv_block) == rank) f = 1;
         }
     }
     flags[i] = f;
@@ -104,7 +100,7 @@ static int install_map_from_xyzw(liliom_ctx* c, int m) {
         LILI_CUDA(c, c->map_ds.ensure((size_t)m * sizeof(float4)));
         float cell = 1.0f;
         while ((double)cell * (double)cell < c->prm.knn_max_sqdist) cell *= 2.0f;
-        k_shard_flags<<<cdiv(m + 1, 256), 256, 0, c->stream>>>(c->map_xyzw.as<float4>(), m, cell, c->nranks, c->rank, c->flags.as<int>());
+        k_shard_flags<<<cdiv(m + 1, 256), 256, 0, c->stream>>>(c->map_xyzw.as<float4>(), m, cell, c->shard_inv_block, c->nranks, c->rank, c->flags.as<int>());
         LILI_TRY(launch_check(c, "k_shard_flags"));
         LILI_TRY(exclusive_scan_i32(c, c->flags.as<int>(), c->idx_a.as<int>(), m));
         k_compact_f4<<<cdiv(m, 256), 256, 0, c->stream>>>(c->map_xyzw.as<float4>(), c->flags.as<int>(), c->idx_a.as<int>(), m, c->map_ds.as<float4>());
@@ -208,8 +204,11 @@ extern "C" int liliom_create(liliom_ctx** out, const liliom_params* p, int devic
     c->dbg_timing = getenv("LILIOM_DEBUG_TIMING") != nullptr;
     if (const char* e9 = getenv("LILIOM_MAP_COOP")) c->map_coop = atoi(e9) != 0;
     if (const char* e7 = getenv("LILIOM_FAST_IO")) c->fast_io = atoi(e7) != 0;
-    if (const char* e5 = getenv("LILIOM_GN_SYNC")) { int v = atoi(e5); if (v == 0 || v == 3) c->gn_sync = v; }
-    if (const char* e3 = getenv("LILIOM_KNN_FLAT")) { int v = atoi(e3); if (v >= 0 && v <= 2) c->knn_flat = v; }
+    if (const char* e5 = getenv("LILIOM_GN_SYNC")) { int v = atoi(e5); if (v == 0 || v == 1 || v == 3) c->gn_sync = v; }
+    if (const char* e4 = getenv("LILIOM_SHARD_BLOCK")) {      // shard block edge in metres (power of two, 8..256): larger blocks = thinner halos
+        int v = atoi(e4);
+        if (v >= 8 && v <= 256 && (v & (v - 1)) == 0) c->shard_inv_block = 1.0f / (float)v;
+    }
     if (const char* e2 = getenv("LILIOM_KNN_ROUNDS")) { int v = atoi(e2); if (v >= 1 && v <= 32) c->force_rounds = v; }
     *out = c;
     return LILIOM_OK;
@@ -226,7 +225,7 @@ extern "C" void liliom_destroy(liliom_ctx* c) {
                       &c->vg_keys2, &c->vg_vals, &c->vg_vals2, &c->vg_flags, &c->vg_rank, &c->vg_params, &c->vg_out, &c->vg_minmax, &c->vg_count,
                       &c->cub_tmp, &c->vg_coop, &c->hz_ctl, &c->map_raw, &c->map_ds, &c->map_xyzw, &c->map_sorted, &c->cell_start, &c->grid_keys, &c->grid_keys2,
                       &c->grid_vals, &c->grid_vals2, &c->feats, &c->corr_valid, &c->corr_plane, &c->nn_idx, &c->nn_sqd, &c->pose_dev,
-                      &c->partials, &c->neq, &c->stats_dev, &c->counter, &c->lm_state, &c->raw_scan, &c->map_refl, &c->slots_buf, &c->livox_in, &c->result_dev};
+                      &c->partials, &c->neq, &c->stats_dev, &c->counter, &c->lm_state, &c->raw_scan, &c->map_refl, &c->livox_in, &c->result_dev};
     for (DevBuf* b : bufs) b->release();
     for (auto& f : c->frames) f.buf.release();
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
@@ -431,7 +430,7 @@ extern "C" int liliom_map_push_frame(liliom_ctx* c, const void* surf_ds_body, in
             float cell = 1.0f;
             while ((double)cell * (double)cell < c->prm.knn_max_sqdist) cell *= 2.0f;
             const float halo = cell + 1.7320508f * c->prm.leaf_map + 0.05f;
-            k_shard_flags_strided<<<cdiv(n + 1, 256), 256, 0, c->stream>>>((const unsigned char*)c->map_ds.p, n, stride, halo, c->nranks, c->rank, c->flags.as<int>());
+            k_shard_flags_strided<<<cdiv(n + 1, 256), 256, 0, c->stream>>>((const unsigned char*)c->map_ds.p, n, stride, halo, c->shard_inv_block, c->nranks, c->rank, c->flags.as<int>());
             LILI_TRY(launch_check(c, "k_shard_flags_strided"));
             LILI_TRY(exclusive_scan_i32(c, c->flags.as<int>(), c->idx_a.as<int>(), n));
             k_compact_strided<<<cdiv(n, 256), 256, 0, c->stream>>>((const unsigned char*)c->map_ds.p, c->flags.as<int>(), c->idx_a.as<int>(), n, stride,
@@ -759,16 +758,17 @@ extern "C" int liliom_pc2_layout(int point_stride, liliom_pc2_field* fields, int
 extern "C" int liliom_get_counters(liliom_ctx* c, liliom_counters* out, int reset) {
     if (!c || !out) return LILIOM_E_ARG;
     LILI_CUDA(c, cudaSetDevice(c->device));
-    unsigned long long cand = 0;
+    unsigned long long dev[2] = {0, 0};       // examined candidates, searched queries: counted by the kernels themselves
     if (c->counter.p) {
-        LILI_CUDA(c, cudaMemcpyAsync(&cand, c->counter.as<unsigned char>() + 16, sizeof(cand), cudaMemcpyDeviceToHost, c->stream));
+        LILI_CUDA(c, cudaMemcpyAsync(dev, c->counter.as<unsigned char>() + 16, sizeof(dev), cudaMemcpyDeviceToHost, c->stream));
         LILI_CUDA(c, cudaStreamSynchronize(c->stream));
     }
-    c->cnt.knn_candidates = cand;
+    c->cnt.knn_candidates = dev[0];
+    c->cnt.knn_queries = dev[1];
     *out = c->cnt;
     if (reset) {
         c->cnt = liliom_counters{};
-        if (c->counter.p) LILI_CUDA(c, cudaMemsetAsync(c->counter.as<unsigned char>() + 16, 0, 8, c->stream));
+        if (c->counter.p) LILI_CUDA(c, cudaMemsetAsync(c->counter.as<unsigned char>() + 16, 0, 16, c->stream));
     }
     return LILIOM_OK;
 }

@@ -17,6 +17,7 @@ struct BkArgs {
     Q4 q; D3 t;
     int variant;
     double max_sqd, plane_thres, w_gate, lidar_const;
+    float tau0;        // largest fp32 distance inside the gate (search pruning, knn_core.cuh)
     unsigned char* valid; float* pa; float* pb; float4* plane; double* score;
     const float* map_refl; const float* feat_refl; double reflect_thres;   // Horizon backend variant (L:1617-1638), nullptr = ROT variant
 };
@@ -33,7 +34,7 @@ __global__ void __launch_bounds__(kBlock) k_backend_edge(BkArgs a) {
     Top5 top;
     top5_init(top);
     unsigned long long cand = 0;
-    group_knn5<kLanes>(sx, sy, sz, a.map, a.cell_start, a.g, sub, omask, top, cand);
+    group_knn5<kLanes>(sx, sy, sz, a.map, a.cell_start, a.g, sub, omask, a.tau0, top, cand);
     if (sub != 0) return;
     bool ok = false;
     float A3[3] = {0, 0, 0}, B3[3] = {0, 0, 0};
@@ -89,7 +90,7 @@ __global__ void __launch_bounds__(kBlock) k_backend_surf(BkArgs a) {
     Top5 top;
     top5_init(top);
     unsigned long long cand = 0;
-    group_knn5<kLanes>(sx, sy, sz, a.map, a.cell_start, a.g, sub, omask, top, cand);
+    group_knn5<kLanes>(sx, sy, sz, a.map, a.cell_start, a.g, sub, omask, a.tau0, top, cand);
     if (sub != 0) return;
     bool ok = false;
     float4 pl = make_float4(0, 0, 0, 0);
@@ -313,6 +314,7 @@ extern "C" int liliom_correspond_edge(liliom_ctx* c, const void* feats, int n, i
     a.feats = c->feats.as<float4>(); a.n = n; a.map = c->map_sorted.as<float4>(); a.map_orig = c->map_xyzw.as<float4>(); a.cell_start = c->cell_start.as<int>(); a.g = c->grid;
     a.q = Q4{pose7[0], pose7[1], pose7[2], pose7[3]}; a.t = D3{pose7[4], pose7[5], pose7[6]};
     a.variant = variant;
+    a.tau0 = knn_gate_tau(1.0);                                                   // L:1543 sqdist[4] < 1.0
     a.valid = c->corr_valid.as<unsigned char>();
     a.pa = c->corr_plane.as<float>(); a.pb = a.pa + 3 * (size_t)n;
     k_backend_edge<<<cdiv((long long)n * kLanes, kBlock), kBlock, 0, c->stream>>>(a);
@@ -345,6 +347,7 @@ static int correspond_surf_impl(liliom_ctx* c, const void* feats, int n, int str
     BkArgs a{};
     a.feats = c->feats.as<float4>(); a.n = n; a.map = c->map_sorted.as<float4>(); a.map_orig = c->map_xyzw.as<float4>(); a.cell_start = c->cell_start.as<int>(); a.g = c->grid;
     a.q = Q4{pose7[0], pose7[1], pose7[2], pose7[3]}; a.t = D3{pose7[4], pose7[5], pose7[6]};
+    a.tau0 = knn_gate_tau(kd_max_radius);
     a.max_sqd = kd_max_radius; a.plane_thres = surf_dist_thres; a.w_gate = w_gate; a.lidar_const = lidar_const;
     if (refl) {
         if (stride != 48 || !c->map_refl.p) { c->last_error = "reflectivity variant needs 48-byte features and a map installed with liliom_map_set_cloud"; return LILIOM_E_ARG; }

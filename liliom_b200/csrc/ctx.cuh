@@ -136,13 +136,13 @@ struct liliom_ctx {
     lili::DevBuf stats_dev;              // iterations x kStatsDoubles
     lili::DevBuf counter;                // last-block ticket + scratch ints
     lili::DevBuf lm_state;
-    lili::DevBuf slots_buf;              // search -> fit hand-off of the split path (48 B per query)
     int bk_kind = 0, bk_n = 0;           // backend correspondences resident from the last liliom_correspond_* call (1 edge, 2 surf)
     unsigned int bar_arrivals = 0;       // total grid-barrier arrivals issued so far (persistent GN kernel)
 
     // ---- multi-GPU ----
     void* nccl_comm = nullptr;
     int nranks = 1, rank = 0;
+    float shard_inv_block = 0.0625f;     // 1 / shard block edge (LILIOM_SHARD_BLOCK, metres, power of two; must agree on all ranks)
     lili::DevBuf peer_buf;               // this rank's exchange buffer: [2 parities][kMaxPeers][32] {epoch|lo32, epoch|hi32}
     void* peer_ptrs[lili::kMaxPeers] = {};   // every rank's buffer as mapped into this process (cudaIpcOpenMemHandle)
     bool peer_ready = false;
@@ -152,14 +152,13 @@ struct liliom_ctx {
     liliom_counters cnt{};
     bool time_kernels = false;
     int force_lanes = 0, force_rounds = 0;   // tuning override (LILIOM_KNN_LANES / LILIOM_KNN_ROUNDS)
-    int knn_flat = 0;                    // 16-lane search shape: 0 = one run per lane, 1 = round-robin candidates, 2 = + per-iteration cache (LILIOM_KNN_FLAT)
     int gn_sync = 3;                     // persistent GN kernel grid barrier (LILIOM_GN_SYNC): 3 = release-only arrival, no acquire fence (default),
                                          // 0 = full fences on both sides
     bool map_coop = false;               // LILIOM_MAP_COOP=1: liliom_map_rebuild voxel-filters the 20-frame map with the cooperative single-launch filter
     bool dbg_timing = false;             // LILIOM_DEBUG_TIMING at create: stage clocks of the cooperative kernels, printed by s2m_run
+    bool knn1_smem_set = false;          // dynamic shared memory limit raised for the one-thread-per-query kernels on this device
     bool fast_io = false;                // LILIOM_FAST_IO=1: pose in the launch parameters, one read-back block (opt-in until measured)
     lili::DevBuf result_dev;             // {pose7 | n_feats | VgParams} written by block 0 of the persistent kernel
-    bool gn_smem_set = false;            // cudaFuncAttributeMaxDynamicSharedMemorySize raised for k_gn_persistent<16> on this device
     std::vector<cudaEvent_t> ev_pool;
     size_t ev_used = 0;
     std::vector<std::pair<size_t, unsigned long long>> ev_pending;  // (event pair index, queries)

@@ -387,8 +387,9 @@ static __device__ __noinline__ void plane_fit5_qr(const float4 m[5], double nv[3
 // 6x6 SPD solve (LDL^T), H given as the 21-scalar upper triangle (row-major), rhs b.
 // Fully unrolled so that every array lives in registers: this runs on ONE thread at the tail of
 // the iteration kernel, where local-memory round trips would be pure exposed latency.
-// Returns false on a non-finite / zero pivot.
-__device__ __forceinline__ bool solve6_ldlt(const double* s21, const double* rhs, double x[6]) {
+// Returns false on a non-finite / zero pivot.  `lambda` is added to every diagonal entry (Levenberg damping); with
+// piv_min >= 0 a pivot that is not above piv_min also fails (relative conditioning test of the GN step, see gn_safe_step).
+__device__ __forceinline__ bool solve6_ldlt(const double* s21, const double* rhs, double x[6], double lambda = 0.0, double piv_min = -1.0) {
     double H[6][6];
     {
         int k = 0;
@@ -401,10 +402,10 @@ __device__ __forceinline__ bool solve6_ldlt(const double* s21, const double* rhs
     bool ok = true;
 #pragma unroll
     for (int j = 0; j < 6; ++j) {
-        double d = H[j][j];
+        double d = H[j][j] + lambda;
 #pragma unroll
         for (int m = 0; m < j; ++m) d -= L[j][m] * L[j][m] * D[m];
-        if (!(fabs(d) > 1e-300) || !isfinite(d)) ok = false;
+        if (!(fabs(d) > 1e-300) || !isfinite(d) || (piv_min >= 0.0 && !(d > piv_min))) ok = false;
         D[j] = d;
         const double inv = 1.0 / d;
         Dinv[j] = inv;
@@ -436,6 +437,33 @@ __device__ __forceinline__ bool solve6_ldlt(const double* s21, const double* rhs
 #pragma unroll
     for (int i = 0; i < 6; ++i) if (!isfinite(x[i])) ok = false;
     return ok;
+}
+
+// Gauss-Newton step of LILIOM_MODE_GN with the two safeguards an undamped step lacks (the reference's own solver is
+// Ceres' trust-region LM, L/src/LidarOdometry.cpp:527-537 = LILIOM_MODE_CERES):
+//   (1) conditioning: when a pivot of H = J^T J falls below 1e-10 * max diag(H) the scan does not constrain some direction
+//       (a narrow-FoV sweep facing one wall, a corridor); the step is then taken from the Levenberg-damped system
+//       (H + 1e-6 * max diag * I) d = -g, which moves the constrained directions and leaves the others (nearly) alone;
+//   (2) trust region: a step of more than kGnMaxRot rad / kGnMaxTrans m is scaled back onto that bound.
+// Neither triggers on a well-posed scan, where the step is the plain LDL^T solution.  oracle_s2m.cpp::gn_safe_step is the same.
+constexpr double kGnPivotRel = 1e-10, kGnDampRel = 1e-6, kGnMaxRot = 0.35, kGnMaxTrans = 5.0;
+__device__ __forceinline__ bool gn_safe_step(const double* s21, const double* rhs, double d[6]) {
+    const double maxd = fmax(fmax(fmax(s21[0], s21[6]), fmax(s21[11], s21[15])), fmax(s21[18], s21[20]));
+    if (!(maxd > 0.0) || !isfinite(maxd)) return false;
+    bool ok = false;
+#pragma unroll 1
+    for (int attempt = 0; attempt < 2 && !ok; ++attempt)
+        ok = solve6_ldlt(s21, rhs, d, attempt == 0 ? 0.0 : kGnDampRel * maxd, attempt == 0 ? kGnPivotRel * maxd : 0.0);
+    if (!ok) return false;
+    const double rot = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]), tr = sqrt(d[3] * d[3] + d[4] * d[4] + d[5] * d[5]);
+    double sc = 1.0;
+    if (rot > kGnMaxRot) sc = kGnMaxRot / rot;
+    if (tr * sc > kGnMaxTrans) sc = kGnMaxTrans / tr;
+    if (sc < 1.0) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) d[k] *= sc;
+    }
+    return true;
 }
 
 // ceres::QuaternionParameterization::Plus on q, identity on t.

@@ -461,7 +461,7 @@ int horizon_extract_dev(liliom_ctx* c, int n, const double q_imu[4], int* n_surf
         if (n > 0) {
             k_hz_deskew_bin<<<cdiv(n, 128), 128, 0, c->stream>>>(raw, n, flags, cidx, q, c->cut.as<Pt48>(), mat);
             LILI_TRY(launch_check(c, "k_hz_deskew_bin"));
-            if (c->early_cut_dst && c->early_cut_cap > 0) {
+            if (c->early_cut_dst && c->early_cut_cap >= n) {      // only when no count can overflow the caller's buffer: an error return leaves it untouched
                 const size_t cnt = (size_t)min(n, c->early_cut_cap);
                 LILI_CUDA(c, cudaEventRecord(c->ev_ready, c->stream));
                 LILI_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_ready, 0));

@@ -184,13 +184,16 @@ struct KnnArgs {
     int nranks, rank;                   // multi-GPU ownership filter (16 m block hash)
     long long* dbg;                     // optional phase timestamps (LILIOM_DEBUG_TIMING)
     int interleave;                     // 1: deal tasks to warps block-cyclically (load balance for small scans)
-    struct Slot* slots_g;               // split path (large query sets): search kernel -> fit kernel hand-off, 48 B per query
-    int fit_only;                       // 1: phase A is skipped, slots come from slots_g (written by k_knn_search)
+    float tau0;                         // largest fp32 distance inside the gate (knn_gate_tau(max_sqd)): search pruning threshold
+    float inv_block;                    // 1 / shard block edge (multi-GPU ownership)
+    unsigned long long* queries_total;  // instrumentation: queries processed (device-side count), one add per pass
     double pose0[7]; int pose_by_value; // persistent kernel, LILIOM_FAST_IO: the start pose travels in the launch parameters (no H2D copy)
     double* result; const VgParams* vgp; // ... and block 0 leaves {pose7 | n_feats | VgParams} in one block for a single D2H copy
-    int flat;                           // LANES >= 16 only: 1 = deal the 27-cell candidate list round-robin over the lanes (group_knn5_flat),
-                                        // 2 = also keep each lane's batch across the GN iterations of the persistent kernel
 };
+
+// per-thread instrumentation word: examined candidates in the low 40 bits, searched queries above (summed per block)
+constexpr int kCandBits = 40;
+constexpr unsigned long long kCandMask = (1ull << kCandBits) - 1ull;
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -203,7 +206,7 @@ struct Slot {
     int   idx[5];            // neighbour indices into map_orig; idx[0] < 0: no 5-NN inside the radius
     float sx, sy, sz;        // transformed query (fp32, as the kd-tree saw it)
     float fx, fy, fz;        // body-frame query (phase B re-derives R p from it)
-    int   pad;               // 48 bytes: three 16-byte stores in the split path
+    int   pad;               // 48 bytes
 };
 struct Row { double J[6]; double r; double half_rho; };   // robustified Jacobian row, residual, rho/2
 
@@ -219,8 +222,6 @@ struct KnnSmem {
     Slot slots[kWarps][32];
     Row rows[kWarps][32];
     unsigned char rvalid[kWarps][32];
-    float4 nb[kWarps][2][5];     // FLAT shape (two queries per warp task): the 5 neighbours handed over by the search
-    int nb_flag[kWarps][2];
     double red[kWarps][kNormEq];
     double xch[kMaxPeers][kNormEq];   // fused multi-GPU exchange: every rank's 29 sums before they are added in rank order
     unsigned long long red_cand[kWarps];
@@ -234,11 +235,12 @@ struct KnnSmem {
 
 // One pass over this block's share of the queries at pose (q,t): phases A (search), B (fit + row), C (lane k
 // accumulates scalar k).  On return lane k < 29 of every warp holds its partial of scalar k in `acc`.
-template <int LANES, bool FLAT = false>
+template <int LANES>
 __device__ __forceinline__ void knn_phases(const KnnArgs& a, const Q4& q, const D3& t, const int n_q, KnnSmem& S,
-                                           double& acc, unsigned long long& cand, const float4* fpre = nullptr,
-                                           float4* cc = nullptr, int cc_stride = 0, int4* cc_tag = nullptr) {
+                                           double& acc, unsigned long long& cand, const float4* fpre = nullptr) {
     constexpr int GROUPS = 32 / LANES;                 // queries a warp searches concurrently
+    extern __shared__ __align__(16) unsigned char dyn_smem[];      // LANES == 1: [kRunCap][kBlock] int4 run lists (thread_knn5)
+    int4* runs = reinterpret_cast<int4*>(dyn_smem) + threadIdx.x;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int sub = lane & (LANES - 1);
@@ -257,12 +259,6 @@ __device__ __forceinline__ void knn_phases(const KnnArgs& a, const Q4& q, const 
 #pragma unroll 1
     for (int task = gw; task < ntasks; task += nw) {
         // ---------------- phase A: cooperative exact 5-NN, one query per lane group per round
-        if (a.fit_only) {
-            if (lane < per_task) {
-                const int qi = task * per_task + lane;
-                if (qi < n_q) S.slots[warp][lane] = a.slots_g[qi];
-            }
-        } else
 #pragma unroll 1
         for (int r = 0; r < a.rounds; ++r) {
             const int slot = r * GROUPS + grp;
@@ -276,17 +272,14 @@ __device__ __forceinline__ void knn_phases(const KnnArgs& a, const Q4& q, const 
                 f = fpre ? *fpre : a.feats[qi];   // (persistent kernel: the query stays in registers across iterations)
                 const D3 pw = qrot_x(q, D3{(double)f.x, (double)f.y, (double)f.z});             // L/src/LidarOdometry.cpp:230-231
                 sx = (float)addx(pw.x, t.x); sy = (float)addx(pw.y, t.y); sz = (float)addx(pw.z, t.z);   // :236-238
-                if (a.nranks > 1 && owner_of(sx, sy, sz, a.nranks) != a.rank) live = false;
+                if (a.nranks > 1 && owner_of(sx, sy, sz, a.nranks, a.inv_block) != a.rank) live = false;
             }
             // `live` is uniform inside a lane group and the shuffles are masked per group
             LILI_STAMP(8);
             if (live) {
-                if constexpr (FLAT) {
-                    const bool hand = per_task <= 2;       // rounds == 1: slot == grp
-                    group_knn5_flat<LANES>(sx, sy, sz, a.map, a.cell_start, a.g, sub, gmask, top, cand, cc, cc_stride, cc_tag,
-                                           hand ? &S.nb[warp][slot & 1][0] : nullptr, hand ? &S.nb_flag[warp][slot & 1] : nullptr);
-                }
-                else group_knn5<LANES>(sx, sy, sz, a.map, a.cell_start, a.g, sub, gmask, top, cand, (a.dbg && blockIdx.x == 0 && threadIdx.x == 0) ? a.dbg : nullptr);
+                if (sub == 0) cand += 1ull << kCandBits;
+                if constexpr (LANES == 1) thread_knn5(sx, sy, sz, a.map, a.cell_start, a.g, a.tau0, runs, kBlock, top, cand);
+                else group_knn5<LANES>(sx, sy, sz, a.map, a.cell_start, a.g, sub, gmask, a.tau0, top, cand, (a.dbg && blockIdx.x == 0 && threadIdx.x == 0) ? a.dbg : nullptr);
             }
             LILI_STAMP(11);
             if (sub == 0) {
@@ -297,7 +290,6 @@ __device__ __forceinline__ void knn_phases(const KnnArgs& a, const Q4& q, const 
                 s.sx = sx; s.sy = sy; s.sz = sz;
                 s.fx = f.x; s.fy = f.y; s.fz = f.z;
                 s.pad = 0;
-                if constexpr (FLAT) { if (live && per_task <= 2) s.pad = 2; }    // neighbours may be in S.nb (see nb_flag)
                 if (live && a.nn_idx) {
                     int* o = a.nn_idx + (size_t)qi * 5;
                     const u64 kk[5] = {top.k0, top.k1, top.k2, top.k3, top.k4};
@@ -320,15 +312,8 @@ __device__ __forceinline__ void knn_phases(const KnnArgs& a, const Q4& q, const 
             float pl0 = 0.f, pl1 = 0.f, pl2 = 0.f, pl3 = 0.f;
             if (qi < n_q && s.idx[0] >= 0) {
                 float4 m[5];
-                bool from_smem = false;
-                if constexpr (FLAT) from_smem = s.pad == 2 && S.nb_flag[warp][lane & 1] == 1;
-                if (from_smem) {
 #pragma unroll
-                    for (int j = 0; j < 5; ++j) m[j] = S.nb[warp][lane & 1][j];
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 5; ++j) m[j] = __ldg(a.map_orig + s.idx[j]);                                 // :369-371
-                }
+                for (int j = 0; j < 5; ++j) m[j] = __ldg(a.map_orig + s.idx[j]);                                     // :369-371
                 double nv[3];
                 if (!plane_fit5_fast(m, nv)) plane_fit5_qr(m, nv);                                                    // :375 (see dev_math.cuh)
                 const double n2 = nv[0] * nv[0] + nv[1] * nv[1] + nv[2] * nv[2];
@@ -414,10 +399,11 @@ __device__ __forceinline__ void write_block_partials(const KnnArgs& a, KnnSmem& 
         for (int w = 0; w < kWarps; ++w) v += S.red[w][threadIdx.x];
         a.partials[(size_t)threadIdx.x * G + blockIdx.x] = v;          // scalar-major: [29][G]
     }
-    if (threadIdx.x == 0 && a.cand_total) {
+    if (threadIdx.x == 0 && a.cand_total) {     // instrumentation (liliom_set_kernel_timing): examined candidates | searched queries
         unsigned long long v = 0;
         for (int w = 0; w < kWarps; ++w) v += S.red_cand[w];
-        if (v) atomicAdd(a.cand_total, v);
+        if (v & kCandMask) atomicAdd(a.cand_total, v & kCandMask);
+        if (v >> kCandBits) atomicAdd(a.queries_total, v >> kCandBits);
     }
 }
 
@@ -462,6 +448,7 @@ __device__ __forceinline__ void reduce_partials(const KnnArgs& a, KnnSmem& S) {
 // `writer`: the block that publishes (block 0 of the persistent kernel; the last block of the per-iteration kernel, the only caller there).
 __device__ __forceinline__ void peer_exchange(const PeerArgs& pa, unsigned int epoch, KnnSmem& S, bool writer) {
     const size_t base = (size_t)(epoch & 1u) * kMaxPeers * 32;
+    const bool already_lost = S.peer_lost != 0;     // block-uniform (written before the previous exchange's closing barrier): no second wait
     if (writer && threadIdx.x < kNormEq) {
         const double v = S.red[0][threadIdx.x];
         const u64 w0 = ((u64)epoch << 32) | (u64)(unsigned)__double2loint(v);
@@ -476,8 +463,8 @@ __device__ __forceinline__ void peer_exchange(const PeerArgs& pa, unsigned int e
         const ulonglong2* src = pa.buf[pa.rank] + base + (size_t)r * 32 + k;
         u64 w0 = 0, w1 = 0;
         unsigned int spins = 0;
-        bool lost = false;
-        while (true) {
+        bool lost = already_lost;
+        while (!already_lost) {
             asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(src) : "memory");
             if ((unsigned int)(w0 >> 32) == epoch && (unsigned int)(w1 >> 32) == epoch) break;
             if (++spins > (1u << 23)) { lost = true; S.peer_lost = 1; break; }      // ~6 s: a lost peer must end in a NaN pose, never in a hung GPU
@@ -504,7 +491,7 @@ __device__ __forceinline__ void gn_step(const KnnSmem& S, const Q4& q, const D3&
     for (int k = 0; k < 7; ++k) x[k] = q_t7(q, t, k);
 #pragma unroll
     for (int k = 0; k < 6; ++k) nb[k] = -s[21 + k];
-    const bool solved = solve6_ldlt(s, nb, d);
+    const bool solved = gn_safe_step(s, nb, d);
     if (s[28] > 0.0 && solved) pose_plus(x, d, xn);
     else {
 #pragma unroll
@@ -530,40 +517,7 @@ __device__ __forceinline__ void write_neq_stats(const KnnArgs& a, const KnnSmem&
 }
 
 
-// ---- split path for large query sets (opt-in, LILIOM_SPLIT=1): the search needs ~60 registers, the fp64 fit ~128, so
-// two kernels let the search run at twice the occupancy.  It did not pay on B200 (81 vs 75.6 us at 128k queries): the
-// ranking is bound by dependent integer compare/select chains, not by exposed memory latency.
-__global__ void __launch_bounds__(kBlock, 4) k_knn_search(KnnArgs a) {
-    const int n_q = a.n_dev ? min(*a.n_dev, a.n) : a.n;
-    const Q4 q{a.pose[0], a.pose[1], a.pose[2], a.pose[3]};
-    const D3 t{a.pose[4], a.pose[5], a.pose[6]};
-    unsigned long long cand = 0;
-    for (int qi = blockIdx.x * blockDim.x + threadIdx.x; qi < n_q; qi += gridDim.x * blockDim.x) {
-        const float4 f = a.feats[qi];
-        const D3 pw = qrot_x(q, D3{(double)f.x, (double)f.y, (double)f.z});
-        const float sx = (float)addx(pw.x, t.x), sy = (float)addx(pw.y, t.y), sz = (float)addx(pw.z, t.z);
-        Top5 top;
-        top5_init(top);
-        const bool live = !(a.nranks > 1 && owner_of(sx, sy, sz, a.nranks) != a.rank);
-        if (live) group_knn5<1, 4>(sx, sy, sz, a.map, a.cell_start, a.g, 0, 1u << (threadIdx.x & 31), top, cand);
-        const bool ok = live && top.k4 != ~0ull && ((double)top5_dist(top.k4) < a.max_sqd);
-        Slot s;
-        s.idx[0] = ok ? top5_index(top.k0) : -1; s.idx[1] = top5_index(top.k1); s.idx[2] = top5_index(top.k2);
-        s.idx[3] = top5_index(top.k3); s.idx[4] = top5_index(top.k4);
-        s.sx = sx; s.sy = sy; s.sz = sz; s.fx = f.x; s.fy = f.y; s.fz = f.z;
-        int4* dst = reinterpret_cast<int4*>(a.slots_g + qi);
-        dst[0] = make_int4(s.idx[0], s.idx[1], s.idx[2], s.idx[3]);
-        dst[1] = make_int4(s.idx[4], __float_as_int(sx), __float_as_int(sy), __float_as_int(sz));
-        dst[2] = make_int4(__float_as_int(f.x), __float_as_int(f.y), __float_as_int(f.z), 0);
-    }
-    if (a.cand_total) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) cand += __shfl_xor_sync(0xffffffffu, cand, o);
-        if ((threadIdx.x & 31) == 0 && cand) atomicAdd(a.cand_total, cand);
-    }
-}
-
-template <int LANES, bool FLAT = false>
+template <int LANES>
 __global__ void __launch_bounds__(kBlock, 2) k_knn_plane(KnnArgs a, const __grid_constant__ PeerArgs pa) {
     __shared__ __align__(16) KnnSmem S;
     if (threadIdx.x == 0) S.peer_lost = 0;
@@ -573,7 +527,7 @@ __global__ void __launch_bounds__(kBlock, 2) k_knn_plane(KnnArgs a, const __grid
     const int n_q = a.n_dev ? min(*a.n_dev, a.n) : a.n;
     double acc = 0.0;
     unsigned long long cand = 0;
-    knn_phases<LANES, FLAT>(a, q, t, n_q, S, acc, cand);
+    knn_phases<LANES>(a, q, t, n_q, S, acc, cand);
     LILI_STAMP(3);
     write_block_partials(a, S, acc, cand);
     __threadfence();
@@ -598,6 +552,7 @@ __global__ void __launch_bounds__(kBlock, 2) k_knn_plane(KnnArgs a, const __grid
             gn_step(S, q, t, xn);
 #pragma unroll
             for (int k = 0; k < 7; ++k) a.pose_out[k] = xn[k];
+            if (pa.enabled) a.pose_out[7] = S.peer_lost ? 1.0 : 0.0;
             if (a.stats) {
 #pragma unroll
                 for (int k = 0; k < 7; ++k) a.stats[30 + k] = xn[k];
@@ -622,11 +577,10 @@ __global__ void __launch_bounds__(kBlock, 2) k_knn_plane(KnnArgs a, const __grid
 #define LILI_GN_MAXNREG 176
 #endif
 #define LILI_GN_BOUNDS __maxnreg__(LILI_GN_MAXNREG)
-template <int LANES, bool FLAT = false>
+template <int LANES>
 __global__ void LILI_GN_BOUNDS k_gn_persistent(KnnArgs a, int iters, unsigned int* bar, double* stats_base, unsigned int bar_base,
                                                              int sync_mode, const __grid_constant__ PeerArgs pa) {
     __shared__ __align__(16) KnnSmem S;
-    extern __shared__ __align__(16) unsigned char dyn_smem[];   // flat == 2: [kFlatBatch][kBlock] float4 candidates + [kBlock] int4 tags
     const int n_q = a.n_dev ? min(*a.n_dev, a.n) : a.n;
     if (threadIdx.x == 32) S.peer_lost = 0;
     if (threadIdx.x < 7) {
@@ -654,13 +608,6 @@ __global__ void LILI_GN_BOUNDS k_gn_persistent(KnnArgs a, int iters, unsigned in
             if (qi < n_q) f_keep = a.feats[qi];
         }
     }
-    // candidate cache (see group_knn5_flat): only when a lane group serves the same query in every iteration
-    float4* cc = nullptr; int4* cc_tag = nullptr;
-    if (FLAT && a.flat == 2 && keep) {
-        cc = reinterpret_cast<float4*>(dyn_smem) + threadIdx.x;
-        cc_tag = reinterpret_cast<int4*>(dyn_smem + (size_t)kFlatBatch * kBlock * sizeof(float4)) + threadIdx.x;
-        *cc_tag = make_int4(0, 0, 0, -1);
-    }
 #pragma unroll 1
     for (int it = 0; it < iters; ++it) {
         const Q4 q{S.pose[0], S.pose[1], S.pose[2], S.pose[3]};
@@ -669,9 +616,9 @@ __global__ void LILI_GN_BOUNDS k_gn_persistent(KnnArgs a, int iters, unsigned in
         unsigned long long cand = 0;
         const bool stamp = a.dbg && blockIdx.x == 0 && threadIdx.x == 0 && it == 2;
         if (stamp) a.dbg[16] = clock64();
-        knn_phases<LANES, FLAT>(a, q, t, n_q, S, acc, cand, keep ? &f_keep : nullptr, cc, kBlock, cc_tag);
+        knn_phases<LANES>(a, q, t, n_q, S, acc, cand, keep ? &f_keep : nullptr);
         if (stamp) a.dbg[17] = clock64();
-        if (sync_mode == 3) {
+        if (sync_mode == 3 || sync_mode == 1) {
             // ---- counter barrier with the minimum of fences (default; measured 12.70 -> 11.99 us per pass against mode 0):
             // one release by thread 0 after the block barrier (cumulative over bar.sync, as in cooperative groups' grid.sync;
             // SASS: MEMBAR.ALL.GPU + RED, no L1 invalidate) and NO acquire fence after the poll.  An acquire (mode 0's
@@ -686,7 +633,11 @@ __global__ void LILI_GN_BOUNDS k_gn_persistent(KnnArgs a, int iters, unsigned in
                 asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(bar), "r"(1u) : "memory");
                 const unsigned int target = bar_base + (unsigned int)(it + 1) * G;
                 unsigned int v;
-                do { asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory"); } while ((int)(v - target) < 0);
+                if (sync_mode == 1) {       // formally complete: the poll is an acquire load (pairs with the release RED), bar.sync orders the block behind it
+                    do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory"); } while ((int)(v - target) < 0);
+                } else {
+                    do { asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory"); } while ((int)(v - target) < 0);
+                }
             }
             __syncthreads();
             if (stamp) a.dbg[19] = clock64();
@@ -720,6 +671,7 @@ __global__ void LILI_GN_BOUNDS k_gn_persistent(KnnArgs a, int iters, unsigned in
             if (blockIdx.x == 0) {
 #pragma unroll
                 for (int k = 0; k < 7; ++k) a.pose_out[k] = xn[k];
+                if (pa.enabled) a.pose_out[7] = S.peer_lost ? 1.0 : 0.0;      // explicit loss flag for the host (the pose is NaN as well)
                 if (stats) {
 #pragma unroll
                     for (int k = 0; k < 7; ++k) stats[30 + k] = xn[k];
@@ -751,7 +703,7 @@ __global__ void k_gn_update(const double* __restrict__ neq, double* __restrict__
     for (int k = 0; k < kNormEq; ++k) s[k] = neq[k];
     for (int k = 0; k < 7; ++k) x[k] = pose[k];
     for (int k = 0; k < 6; ++k) nb[k] = -s[21 + k];
-    if (s[28] > 0.0 && solve6_ldlt(s, nb, d)) pose_plus(x, d, xn);
+    if (s[28] > 0.0 && gn_safe_step(s, nb, d)) pose_plus(x, d, xn);
     else for (int k = 0; k < 7; ++k) xn[k] = x[k];
     if (xn[0] < 0) { xn[0] = -xn[0]; xn[1] = -xn[1]; xn[2] = -xn[2]; xn[3] = -xn[3]; }
     for (int k = 0; k < 7; ++k) pose[k] = xn[k];
@@ -988,6 +940,8 @@ int s2m_run(liliom_ctx* c, double pose7[7], int match_cnt, int max_num_iter, int
     if (c->map_n_global < 10) return LILIOM_E_FEWMAP;          // L/src/LidarOdometry.cpp:485-488
     const int n = c->n_feats;
     if (match_cnt < 0) return LILIOM_E_ARG;
+    // the per-iteration stats come back through the pinned block: check its capacity before anything is enqueued
+    if (stats && match_cnt > 0 && 64 * sizeof(double) + (size_t)match_cnt * kStatsDoubles * sizeof(double) > c->h_pin_bytes) return LILIOM_E_CAPACITY;
     const int iters = match_cnt;
     const int n_est = c->d_nfeats ? (c->last_n_feats > 0 ? min(c->last_n_feats, n) : n) : n;   // device-side count: predict from the last scan
     int lanes = 8, rounds = 1;
@@ -1037,9 +991,11 @@ int s2m_run(liliom_ctx* c, double pose7[7], int match_cnt, int max_num_iter, int
     a.partials = c->partials.as<double>(); a.neq = c->neq.as<double>();
     a.ticket = c->counter.as<unsigned int>();
     a.cand_total = c->time_kernels ? reinterpret_cast<unsigned long long*>(c->counter.as<unsigned char>() + 16) : nullptr;
+    a.queries_total = c->time_kernels ? reinterpret_cast<unsigned long long*>(c->counter.as<unsigned char>() + 24) : nullptr;
+    a.tau0 = knn_gate_tau(c->prm.knn_max_sqdist);
+    a.inv_block = c->shard_inv_block;
     a.rounds = rounds; a.nranks = c->nranks; a.rank = c->rank;
     a.interleave = (lanes >= 8 && !getenv("LILIOM_NO_INTERLEAVE")) ? 1 : 0;
-    a.flat = lanes >= 16 ? c->knn_flat : 0;
     a.dbg = nullptr;
     if (getenv("LILIOM_DEBUG_TIMING")) {
         LILI_CUDA(c, c->lm_state.ensure(64 * sizeof(long long)));
@@ -1047,6 +1003,13 @@ int s2m_run(liliom_ctx* c, double pose7[7], int match_cnt, int max_num_iter, int
         a.dbg = c->lm_state.as<long long>();
     }
 
+    // one thread per query: per-thread run lists in dynamic shared memory (thread_knn5); static + dynamic exceed 48 KB
+    const size_t dyn_smem = lanes == 1 ? (size_t)kRunCap * kBlock * sizeof(int4) : 0;
+    if (lanes == 1 && !c->knn1_smem_set) {
+        LILI_CUDA(c, cudaFuncSetAttribute((const void*)k_knn_plane<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
+        LILI_CUDA(c, cudaFuncSetAttribute((const void*)k_gn_persistent<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
+        c->knn1_smem_set = true;
+    }
     // ---- single-GPU GN: all iterations in one cooperative launch
     const bool peer = c->peer_ready && c->peer_ptrs[c->rank] != nullptr;       // fused exchange instead of ncclAllReduce + k_gn_update
     const bool persistent = mode == LILIOM_MODE_GN && (c->nranks == 1 || peer) && iters > 0 && !want_corr &&
@@ -1055,7 +1018,12 @@ int s2m_run(liliom_ctx* c, double pose7[7], int match_cnt, int max_num_iter, int
     // pose, query count and VoxelGrid verdict in one device block, so the call needs no H2D copy and one D2H copy of 432 B
     // instead of three small ones (each a separate ~2 us DMA on the critical path of a ~220 us scan).
     const bool fast_io = persistent && c->fast_io;
-    if (!fast_io) LILI_CUDA(c, cudaMemcpyAsync(c->pose_dev.p, pose7, 7 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    if (!fast_io) {
+        double p8[8] = {pose7[0], pose7[1], pose7[2], pose7[3], pose7[4], pose7[5], pose7[6], 0.0};      // [7]: peer-loss flag, cleared
+        double* pin = reinterpret_cast<double*>(c->h_pin) + 56;      // pinned staging (slots 56..63 of the small block; results land in 0..55)
+        memcpy(pin, p8, sizeof(p8));
+        LILI_CUDA(c, cudaMemcpyAsync(c->pose_dev.p, pin, 8 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    }
     if (fast_io) {
         LILI_CUDA(c, c->result_dev.ensure(64 * sizeof(double)));
         for (int k = 0; k < 7; ++k) a.pose0[k] = pose7[k];
@@ -1079,8 +1047,7 @@ int s2m_run(liliom_ctx* c, double pose7[7], int match_cnt, int max_num_iter, int
             c->peer_epoch += (unsigned int)iters;
         }
         void* kargs[] = {&a, &iters_arg, &bar, &stats_base, &bar_base, &sync_mode, &pa};
-        const void* fn = (lanes == 16 && a.flat) ? (const void*)k_gn_persistent<16, true>
-                       : lanes == 16 ? (const void*)k_gn_persistent<16> : lanes == 1 ? (const void*)k_gn_persistent<1>
+        const void* fn = lanes == 16 ? (const void*)k_gn_persistent<16> : lanes == 1 ? (const void*)k_gn_persistent<1>
                        : lanes == 2 ? (const void*)k_gn_persistent<2> : lanes == 4 ? (const void*)k_gn_persistent<4>
                                                                                    : (const void*)k_gn_persistent<8>;
         size_t ev = 0;
@@ -1091,15 +1058,7 @@ int s2m_run(liliom_ctx* c, double pose7[7], int match_cnt, int max_num_iter, int
             ev = c->ev_used; c->ev_used += 2;
             LILI_CUDA(c, cudaEventRecord(c->ev_pool[ev], c->stream));
         }
-        size_t dyn = 0;
-        if (a.flat == 2) {
-            dyn = (size_t)kFlatBatch * kBlock * sizeof(float4) + (size_t)kBlock * sizeof(int4);
-            if (!c->gn_smem_set) {
-                LILI_CUDA(c, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-                c->gn_smem_set = true;
-            }
-        }
-        LILI_CUDA(c, cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kBlock), kargs, dyn, c->stream));
+        LILI_CUDA(c, cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kBlock), kargs, dyn_smem, c->stream));
         LILI_TRY(launch_check(c, "k_gn_persistent"));
         c->bar_arrivals += (unsigned int)iters * (unsigned int)grid;
         if (c->time_kernels) {
@@ -1109,11 +1068,6 @@ int s2m_run(liliom_ctx* c, double pose7[7], int match_cnt, int max_num_iter, int
         }
     }
     const int launches = persistent ? 0 : ((iters == 0 && want_corr) ? 1 : iters);
-    // measured on B200 (128k queries): fused 75.6 us, split 81.0 us — the search is issue-bound, not occupancy-bound; opt-in only
-    const bool split = lanes == 1 && !want_corr && getenv("LILIOM_SPLIT");
-    if (split) LILI_CUDA(c, c->slots_buf.ensure((size_t)n * sizeof(Slot)));
-    a.slots_g = split ? c->slots_buf.as<Slot>() : nullptr;
-    a.fit_only = 0;
     for (int it = 0; it < launches; ++it) {
         a.stats = c->stats_dev.as<double>() + (size_t)it * kStatsDoubles;
         const bool multi = c->nranks > 1;
@@ -1135,18 +1089,8 @@ int s2m_run(liliom_ctx* c, double pose7[7], int match_cnt, int max_num_iter, int
             ev = c->ev_used; c->ev_used += 2;
             LILI_CUDA(c, cudaEventRecord(c->ev_pool[ev], c->stream));
         }
-        if (split) {
-            KnnArgs sa = a;
-            k_knn_search<<<min(cdiv(n, kBlock), c->sm_count * 4), kBlock, 0, c->stream>>>(sa);
-            LILI_TRY(launch_check(c, "k_knn_search"));
-            a.fit_only = 1;
-            a.cand_total = nullptr;
-            k_knn_plane<1><<<grid, kBlock, 0, c->stream>>>(a, pit);
-            a.fit_only = 0;
-            a.cand_total = sa.cand_total;
-        } else if (lanes == 16 && a.flat) k_knn_plane<16, true><<<grid, kBlock, 0, c->stream>>>(a, pit);
-        else if (lanes == 16) k_knn_plane<16><<<grid, kBlock, 0, c->stream>>>(a, pit);
-        else if (lanes == 1) k_knn_plane<1><<<grid, kBlock, 0, c->stream>>>(a, pit);
+        if (lanes == 16) k_knn_plane<16><<<grid, kBlock, 0, c->stream>>>(a, pit);
+        else if (lanes == 1) k_knn_plane<1><<<grid, kBlock, dyn_smem, c->stream>>>(a, pit);
         else if (lanes == 2) k_knn_plane<2><<<grid, kBlock, 0, c->stream>>>(a, pit);
         else if (lanes == 4) k_knn_plane<4><<<grid, kBlock, 0, c->stream>>>(a, pit);
         else k_knn_plane<8><<<grid, kBlock, 0, c->stream>>>(a, pit);
@@ -1178,7 +1122,7 @@ int s2m_run(liliom_ctx* c, double pose7[7], int match_cnt, int max_num_iter, int
     if (fast_io) {
         LILI_CUDA(c, cudaMemcpyAsync(hp, c->result_dev.p, 48 * sizeof(double) + sizeof(VgParams), cudaMemcpyDeviceToHost, c->stream));
     } else {
-        LILI_CUDA(c, cudaMemcpyAsync(hp, c->pose_dev.p, 7 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        LILI_CUDA(c, cudaMemcpyAsync(hp, c->pose_dev.p, 8 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));     // pose + peer-loss flag
         if (out29) LILI_CUDA(c, cudaMemcpyAsync(hp + 8, c->neq.p, kNormEq * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
         if (c->d_nfeats) LILI_CUDA(c, cudaMemcpyAsync(hp + 40, c->d_nfeats, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
         if (c->vg_check) LILI_CUDA(c, cudaMemcpyAsync(hp + 48, c->vg_params.p, sizeof(VgParams), cudaMemcpyDeviceToHost, c->stream));
@@ -1186,7 +1130,6 @@ int s2m_run(liliom_ctx* c, double pose7[7], int match_cnt, int max_num_iter, int
     const bool want_stats = stats && iters > 0;
     if (want_stats) {
         size_t bytes = (size_t)iters * kStatsDoubles * sizeof(double);
-        if (64 * sizeof(double) + bytes > c->h_pin_bytes) return LILIOM_E_CAPACITY;
         LILI_CUDA(c, cudaMemcpyAsync(hp + 64, c->stats_dev.p, bytes, cudaMemcpyDeviceToHost, c->stream));
     }
     LILI_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -1197,7 +1140,7 @@ int s2m_run(liliom_ctx* c, double pose7[7], int match_cnt, int max_num_iter, int
         c->vg_ncells = vp->overflow ? 0 : (long long)vp->div_b[0] * vp->div_b[1] * vp->div_b[2];
         c->vg_bail = vp->bail != 0;
     }
-    if (iters > 0 && peer && std::isnan(hp[0])) {
+    if (iters > 0 && peer && !fast_io && hp[7] != 0.0) {
         c->last_error = "fused exchange: a peer rank did not publish its sums within the wait bound (collective call not entered on every rank?)";
         return LILIOM_E_NCCL;
     }
@@ -1238,7 +1181,7 @@ int s2m_run(liliom_ctx* c, double pose7[7], int match_cnt, int max_num_iter, int
             float ms = 0;
             if (cudaEventElapsedTime(&ms, c->ev_pool[pr.first], c->ev_pool[pr.first + 1]) == cudaSuccess) {
                 // a persistent launch covers `iters` passes of the kernel body: count each pass as one "launch"
-                c->cnt.knn_ms += ms; c->cnt.knn_launches += (unsigned long long)c->ev_iters[k]; c->cnt.knn_queries += pr.second;
+                c->cnt.knn_ms += ms; c->cnt.knn_launches += (unsigned long long)c->ev_iters[k];
             }
         }
         c->ev_pending.clear();

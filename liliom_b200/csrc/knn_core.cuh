@@ -1,16 +1,29 @@
-// Lane-group-cooperative exact 5-NN over the dense cell grid (shared by the scan-to-map kernel
-// and the backend correspondence kernels).  See grid_knn.cu for the design notes.
+// Exact 5-NN over the dense cell grid (shared by the scan-to-map kernel and the backend correspondence kernels).
+// See grid_knn.cu for the design notes.
 //
 // Candidate ordering is (fp32 squared distance, map index).  Both live in one 64-bit key
 //     key = (bits(d) << 32) | index             (d >= +0, so the bit pattern orders like the value)
 // so a single unsigned compare implements FLANN's distance order plus our index tie-break with
 // no branches and no extra loads.
+//
+// Pruning (round 2; profiles/r01_knn_dense_lanes1_ncu.txt had 57 % of the issued instructions in the 64-bit ranking
+// chain and every query ranking all ~63 points of its 27 cells).  A correspondence needs its FIFTH neighbour inside the
+// gate (d5 < knn_max_sqdist, L/src/LidarOdometry.cpp:365), so a candidate at or beyond the gate can never be part of an
+// accepted set, and once five candidates are held nothing beyond the current fifth distance can enter the set either:
+//   * every candidate is tested against the running threshold `tau` with ONE fp32 compare before its key is built;
+//   * whole cells are skipped when their lower bound exceeds `tau`.  The bound is the candidate distance expression itself,
+//     ((dx*dx) + dy*dy) + dz*dz in round-to-nearest fp32, evaluated at the faces of the query's own cell: every point of the
+//     skipped cell has |coordinate difference| >= the face distance per axis in exact arithmetic, fp32 subtraction,
+//     multiplication and addition are monotonic, hence its computed distance is >= the bound.  The accepted sets and
+//     their order are bit-identical to the exhaustive search (and to the oracle's kd-tree); a query that ends with
+//     fewer than five candidates inside the gate is rejected by both.
 // Loops are deliberately NOT unrolled: the first version of this kernel was 11.7k SASS
 // instructions and spent 47 % of its issue slots in stall_no_inst (instruction-cache misses,
 // profiles/r01_knn_v1_ncu.txt).
 #pragma once
 #include "ctx.cuh"
 #include "dev_math.cuh"
+#include <cmath>
 
 namespace lili {
 
@@ -19,17 +32,27 @@ __device__ __forceinline__ int cell_coord(float v, float inv_cell) { return (int
 constexpr int kBlock = 256;
 constexpr int kWarps = kBlock / 32;
 
-__device__ __forceinline__ unsigned block_hash(int bx, int by, int bz) {
+__host__ __device__ __forceinline__ unsigned block_hash(int bx, int by, int bz) {
     unsigned h = (unsigned)bx * 73856093u ^ (unsigned)by * 19349663u ^ (unsigned)bz * 83492791u;
     h ^= h >> 15; h *= 0x2c1b3c6du; h ^= h >> 12;
     return h;
 }
-__device__ __forceinline__ int owner_of(float x, float y, float z, int nranks) {
-    int bx = (int)floorf(x * 0.0625f), by = (int)floorf(y * 0.0625f), bz = (int)floorf(z * 0.0625f);
+// Ownership of a point for the sharded map: space is cut into cubes of 1/inv_block metres (a power of two, default 16 m),
+// the cube's hash picks the rank (SURVEY.md §8 e).
+__device__ __forceinline__ int owner_of(float x, float y, float z, int nranks, float inv_block) {
+    int bx = (int)floorf(x * inv_block), by = (int)floorf(y * inv_block), bz = (int)floorf(z * inv_block);
     return (int)(block_hash(bx, by, bz) % (unsigned)nranks);
 }
 
 typedef unsigned long long u64;
+
+// Largest float t with (double)t < max_sqd: "d <= t" is then the reference's gate "(double)d < max_sqd".
+inline float knn_gate_tau(double max_sqd) {
+    float f = (float)max_sqd;
+    while ((double)f >= max_sqd) f = nextafterf(f, -INFINITY);
+    while ((double)nextafterf(f, INFINITY) < max_sqd) f = nextafterf(f, INFINITY);
+    return f;
+}
 
 // Sorted (ascending) list of the five best keys.  The low word of a key is the neighbour's index in
 // the un-sorted map array (map_download order), which is also where phase B fetches its coordinates
@@ -56,38 +79,83 @@ __device__ __forceinline__ void top5_insert(Top5& t, u64 k) {
     }
 }
 
-__device__ __forceinline__ u64 make_key(float sx, float sy, float sz, const float4& m) {
-    // FLANN L2_Simple<float>: ((dx*dx) + dy*dy) + dz*dz with no contraction (exact-op intrinsics)
+// FLANN L2_Simple<float>: ((dx*dx) + dy*dy) + dz*dz with no contraction (exact-op intrinsics)
+__device__ __forceinline__ float cand_dist(float sx, float sy, float sz, const float4& m) {
     const float dx = fsubx(sx, m.x), dy = fsubx(sy, m.y), dz = fsubx(sz, m.z);
-    const float d = faddx(faddx(fmulx(dx, dx), fmulx(dy, dy)), fmulx(dz, dz));
+    return faddx(faddx(fmulx(dx, dx), fmulx(dy, dy)), fmulx(dz, dz));
+}
+__device__ __forceinline__ u64 make_key(float d, const float4& m) {
     return ((u64)__float_as_uint(d) << 32) | (u64)(unsigned)__float_as_int(m.w);
 }
 
-// LANES (1, 2, 4, 8 or 16) lanes — mask `gmask`, lane-in-group `sub` — search the 3x3x3 cell block around
-// (sx,sy,sz).  The three x-adjacent cells of a (y,z) row are ONE contiguous run of the cell-sorted
-// map, so the block is 9 runs; lane `sub` walks rows sub, sub+LANES, ...  Each lane pulls its run in
-// batches of 8 independent 16-byte loads (memory-level parallelism without occupancy), ranks them into
-// a private sorted top-5, and the group merges with 5 REDUX.MIN rounds.  With LANES == 1 a thread owns a
-// whole query: consecutive queries are spatial neighbours (VoxelGrid output order), so the warp's
-// loads hit the same cells in L1.  On return every lane of the group holds the merged top-5.
+// One candidate: cheap fp32 reject against the running threshold, then the ranked insert.  tau is the largest distance that
+// can still enter the set: the gate until five candidates are held, then the fifth distance (ties go on to the index compare).
+__device__ __forceinline__ void consider(float sx, float sy, float sz, const float4& m, Top5& top, float& tau) {
+    const float d = cand_dist(sx, sy, sz, m);
+    if (d <= tau) {
+        top5_insert(top, make_key(d, m));
+        tau = fminf(tau, top5_dist(top.k4));        // k4 == ~0 decodes to NaN: fminf keeps tau
+    }
+}
+
+// The query's cell and the distances to its six faces (>= 0; 0 is always a valid lower bound).
+struct QCell {
+    int cx, cy, cz;                     // grid-relative cell coordinates (may lie outside the grid)
+    float xl, xh, yl, yh, zl, zh;       // sx - lo_x, hi_x - sx, ...
+};
+__device__ __forceinline__ QCell query_cell(float sx, float sy, float sz, const GridDesc& g) {
+    QCell q;
+    const float cell = 1.0f / g.inv_cell;                      // power of two: all products below are exact
+    const float fx = floorf(sx * g.inv_cell), fy = floorf(sy * g.inv_cell), fz = floorf(sz * g.inv_cell);
+    q.cx = (int)fx - g.org[0]; q.cy = (int)fy - g.org[1]; q.cz = (int)fz - g.org[2];
+    const float lx = fx * cell, ly = fy * cell, lz = fz * cell;
+    q.xl = fmaxf(fsubx(sx, lx), 0.f); q.xh = fmaxf(fsubx(faddx(lx, cell), sx), 0.f);
+    q.yl = fmaxf(fsubx(sy, ly), 0.f); q.yh = fmaxf(fsubx(faddx(ly, cell), sy), 0.f);
+    q.zl = fmaxf(fsubx(sz, lz), 0.f); q.zh = fmaxf(fsubx(faddx(lz, cell), sz), 0.f);
+    return q;
+}
+// lower bound of the candidate distance over a cell at offset (ox, oy, oz) in {-1,0,1}^3, same expression and rounding
+__device__ __forceinline__ float cell_bound(const QCell& q, int ox, int oy, int oz) {
+    const float bx = ox < 0 ? q.xl : ox > 0 ? q.xh : 0.f;
+    const float by = oy < 0 ? q.yl : oy > 0 ? q.yh : 0.f;
+    const float bz = oz < 0 ? q.zl : oz > 0 ? q.zh : 0.f;
+    return faddx(faddx(fmulx(bx, bx), fmulx(by, by)), fmulx(bz, bz));
+}
+
+// Run of the cell-sorted map covering the cells of row (oy, oz) that can still hold a neighbour: the three x-adjacent
+// cells are ONE contiguous run, its ends are trimmed by the bound.  Returns false when nothing is left.
+__device__ __forceinline__ bool row_cells(const QCell& q, const GridDesc& g, int oy, int oz, float tau, int& idx_b, int& idx_e) {
+    const int y = q.cy + oy, z = q.cz + oz;
+    if (y < 0 || y >= g.dim[1] || z < 0 || z >= g.dim[2]) return false;
+    if (cell_bound(q, 0, oy, oz) > tau) return false;
+    int xs = q.cx - 1, xe = q.cx + 1;
+    if (cell_bound(q, -1, oy, oz) > tau) xs = q.cx;
+    if (cell_bound(q, +1, oy, oz) > tau) xe = q.cx;
+    xs = max(xs, 0); xe = min(xe, g.dim[0] - 1);
+    if (xs > xe) return false;
+    const int base = (z * g.dim[1] + y) * g.dim[0];
+    idx_b = base + xs; idx_e = base + xe + 1;
+    return true;
+}
+
+// LANES (2, 4, 8 or 16) lanes — mask `gmask`, lane-in-group `sub` — search the 3x3x3 cell block around
+// (sx,sy,sz); lane `sub` walks rows sub, sub+LANES, ...  Each lane pulls its run in batches of independent 16-byte
+// loads (memory-level parallelism without occupancy), ranks them into a private sorted top-5, and the group merges with
+// 5 min-butterflies.  On return every lane of the group holds the merged top-5.
 // `cand` accumulates the number of map points this lane examined.
 template <int LANES, int BATCH = 8>
 __device__ __forceinline__ void group_knn5(float sx, float sy, float sz, const float4* __restrict__ map,
-                                           const int* __restrict__ cell_start, const GridDesc& g, int sub, unsigned gmask,
+                                           const int* __restrict__ cell_start, const GridDesc& g, int sub, unsigned gmask, float tau0,
                                            Top5& top, unsigned long long& cand, long long* dbg = nullptr) {
-    const int cx = cell_coord(sx, g.inv_cell) - g.org[0];
-    const int cy = cell_coord(sy, g.inv_cell) - g.org[1];
-    const int cz = cell_coord(sz, g.inv_cell) - g.org[2];
-    const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.dim[0] - 1);
+    static_assert(LANES > 1, "one thread per query: thread_knn5");
+    const QCell qc = query_cell(sx, sy, sz, g);
+    float tau = tau0;
     auto row_range = [&](int row, int& b, int& e) {
         b = 0; e = 0;
-        if (row < 9 && x0 <= x1) {
-            const int y = cy + (row % 3) - 1, z = cz + (row / 3) - 1;
-            if (y >= 0 && y < g.dim[1] && z >= 0 && z < g.dim[2]) {
-                const int base = (z * g.dim[1] + y) * g.dim[0];
-                b = __ldg(cell_start + base + x0);
-                e = __ldg(cell_start + base + x1 + 1);
-            }
+        int ib, ie;
+        if (row < 9 && row_cells(qc, g, (row % 3) - 1, (row / 3) - 1, tau, ib, ie)) {
+            b = __ldg(cell_start + ib);
+            e = __ldg(cell_start + ie);
         }
     };
     int b, e;
@@ -104,113 +172,15 @@ __device__ __forceinline__ void group_knn5(float sx, float sy, float sz, const f
 #pragma unroll
             for (int i = 0; i < BATCH; ++i) if (p0 + i < e) c[i] = __ldg(map + p0 + i);
 #pragma unroll
-            for (int i = 0; i < BATCH; ++i) if (p0 + i < e) top5_insert(top, make_key(sx, sy, sz, c[i]));
+            for (int i = 0; i < BATCH; ++i) if (p0 + i < e) consider(sx, sy, sz, c[i], top, tau);
         }
         b = nb; e = ne;
     }
     if (dbg) dbg[10] = clock64() + (long long)(top.k0 & 0);
-    if (LANES > 1) {
-        // merge: 5 rounds of "group-wide minimum of the list heads, winner pops".  The minimum is an xor
-        // butterfly of 64-bit keys (REDUX.MIN on a partial lane mask measured ~350 cycles per call on
-        // B200, the shuffle butterfly ~35 cycles per step).  Keys are unique — a map point lives in
-        // exactly one lane's list — so exactly one lane pops per round.
-        Top5 res;
-#define LILI_MERGE_ROUND(KJ)                                                              \
-        {                                                                                 \
-            u64 mn = top.k0;                                                              \
-            _Pragma("unroll")                                                             \
-            for (int o = 1; o < LANES; o <<= 1) { const u64 other = __shfl_xor_sync(gmask, mn, o); mn = other < mn ? other : mn; } \
-            KJ = mn;                                                                      \
-            if (top.k0 == mn && mn != ~0ull) { top.k0 = top.k1; top.k1 = top.k2; top.k2 = top.k3; top.k3 = top.k4; top.k4 = ~0ull; } \
-        }
-        LILI_MERGE_ROUND(res.k0)
-        LILI_MERGE_ROUND(res.k1)
-        LILI_MERGE_ROUND(res.k2)
-        LILI_MERGE_ROUND(res.k3)
-        LILI_MERGE_ROUND(res.k4)
-#undef LILI_MERGE_ROUND
-        top = res;
-    }
-}
-
-
-// ---- flat variant for the latency-bound small-scan shape (LANES == 16: two queries per warp) -------------------
-// group_knn5 gives lane r the whole run r, so a query costs max-run-length ranking steps and lanes 9..15 idle
-// (measured on B200, 1.7k queries: 5.3k of a 13k-cycle pass in "candidates + rank").  Here the 9 run bounds are
-// shared through shuffles and the concatenated candidate list is dealt round-robin: lane `sub` ranks candidates
-// sub, sub+LANES, ... — ceil(T/LANES) steps instead of the longest run, one batch of independent 16-byte loads per
-// lane for T <= 8*LANES, consecutive lanes reading consecutive map points.  The candidate SET is unchanged, so the
-// merged top-5 is bit-identical to group_knn5's.
-// `cc` (optional, per-thread slots in shared memory): a lane's batch is kept across the GN iterations of the
-// persistent kernel; while the transformed query stays in the same cell the bounds + candidate loads (two dependent
-// L2 round trips) are skipped.  cc_tag holds the cell the cache was filled for (tag.w < 0: empty / not cacheable).
-constexpr int kFlatBatch = 8;
-
-template <int LANES>
-__device__ __forceinline__ void group_knn5_flat(float sx, float sy, float sz, const float4* __restrict__ map,
-                                                const int* __restrict__ cell_start, const GridDesc& g, int sub, unsigned gmask,
-                                                Top5& top, unsigned long long& cand, float4* cc, int cc_stride, int4* cc_tag,
-                                                float4* nb_out = nullptr, int* nb_flag = nullptr) {
-    static_assert(LANES >= 16, "one lane per (y,z) row of the 3x3x3 block");
-    const int cx = cell_coord(sx, g.inv_cell) - g.org[0];
-    const int cy = cell_coord(sy, g.inv_cell) - g.org[1];
-    const int cz = cell_coord(sz, g.inv_cell) - g.org[2];
-    float4 c[kFlatBatch];
-    int nmine = 0, T = 0;
-    int rb[9], pre[10];
-    const bool reuse = cc_tag && cc_tag->w >= 0 && cc_tag->x == cx && cc_tag->y == cy && cc_tag->z == cz;   // uniform in the group
-    if (reuse) {
-        nmine = cc_tag->w;
-#pragma unroll
-        for (int i = 0; i < kFlatBatch; ++i) if (i < nmine) c[i] = cc[i * cc_stride];
-    } else {
-        const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.dim[0] - 1);
-        int b = 0, len = 0;
-        if (sub < 9 && x0 <= x1) {
-            const int y = cy + (sub % 3) - 1, z = cz + (sub / 3) - 1;
-            if (y >= 0 && y < g.dim[1] && z >= 0 && z < g.dim[2]) {
-                const int base = (z * g.dim[1] + y) * g.dim[0];
-                b = __ldg(cell_start + base + x0);
-                len = __ldg(cell_start + base + x1 + 1) - b;
-            }
-        }
-        pre[0] = 0;
-#pragma unroll
-        for (int r = 0; r < 9; ++r) {
-            rb[r] = __shfl_sync(gmask, b, r, LANES);
-            pre[r + 1] = pre[r] + __shfl_sync(gmask, len, r, LANES);
-        }
-        T = pre[9];
-    }
-#pragma unroll 1
-    for (int j0 = sub;; j0 += LANES * kFlatBatch) {
-        if (!reuse) {
-            nmine = 0;
-#pragma unroll
-            for (int i = 0; i < kFlatBatch; ++i) {
-                const int j = j0 + i * LANES;
-                if (j < T) {
-                    int pos = rb[0] + j;
-#pragma unroll
-                    for (int r = 1; r < 9; ++r) if (j >= pre[r]) pos = rb[r] + (j - pre[r]);   // last row whose prefix <= j
-                    c[i] = __ldg(map + pos);
-                    nmine = i + 1;
-                }
-            }
-            if (cc_tag && j0 == sub) {      // first batch: cacheable when it is also the only one
-                if (T <= LANES * kFlatBatch) {
-#pragma unroll
-                    for (int i = 0; i < kFlatBatch; ++i) if (i < nmine) cc[i * cc_stride] = c[i];
-                    *cc_tag = make_int4(cx, cy, cz, nmine);
-                } else cc_tag->w = -1;
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < kFlatBatch; ++i) if (i < nmine) top5_insert(top, make_key(sx, sy, sz, c[i]));
-        cand += (unsigned long long)nmine;
-        if (reuse || j0 - sub + LANES * kFlatBatch >= T) break;     // group-uniform: T and reuse are
-    }
-    // merge (same as group_knn5)
+    // merge: 5 rounds of "group-wide minimum of the list heads, winner pops".  The minimum is an xor
+    // butterfly of 64-bit keys (REDUX.MIN on a partial lane mask measured ~350 cycles per call on
+    // B200, the shuffle butterfly ~35 cycles per step).  Keys are unique — a map point lives in
+    // exactly one lane's list — so exactly one lane pops per round.
     Top5 res;
 #define LILI_MERGE_ROUND(KJ)                                                              \
     {                                                                                     \
@@ -227,22 +197,77 @@ __device__ __forceinline__ void group_knn5_flat(float sx, float sy, float sz, co
     LILI_MERGE_ROUND(res.k4)
 #undef LILI_MERGE_ROUND
     top = res;
-    // Hand the winners' coordinates to the plane fit through shared memory: the lane that loaded a winning candidate
-    // still holds it in registers (single-batch case), so the fit does not have to fetch the 5 neighbours from L2 again
-    // (the cell-sorted copy and map_download order hold the same coordinates).  nb_flag = 1 tells phase B to use them.
-    if (nb_out) {
-        const bool single = reuse || T <= LANES * kFlatBatch;      // group-uniform
-        if (single) {
+}
+
+// One thread per query (large query sets: every issue slot ranks 32 candidates; consecutive queries are spatial
+// neighbours, so the warp's loads hit the same cells in L1).  Three steps:
+//   1. the centre row (the query's own (y,z) row, three x-adjacent cells, ~1/3 of the block's points and nearly always
+//      the five nearest among them) — after it `tau` is at or near the final fifth distance;
+//   2. the eight other rows are bounded against that tau; the survivors' trimmed runs go to a per-thread list in shared
+//      memory, all their cell-table loads in flight together;
+//   3. ONE loop over the concatenated list.  A warp's trip count is then the maximum over its lanes of the total number of
+//      batches — not the sum over rows of the per-row maxima, which is what cost the first version of this kernel twice
+//      the mean (profiles/r01_knn_dense_lanes1_ncu.txt).
+// `runs`: this thread's slots of a [kRunCap][run_stride] int4 array in shared memory {begin, end, bound bits, -}.
+constexpr int kRunCap = 8;
+template <int BATCH1 = 8, int BATCH3 = 4>
+__device__ __forceinline__ void thread_knn5(float sx, float sy, float sz, const float4* __restrict__ map,
+                                            const int* __restrict__ cell_start, const GridDesc& g, float tau0, int4* runs, int run_stride,
+                                            Top5& top, unsigned long long& cand) {
+    const QCell qc = query_cell(sx, sy, sz, g);
+    float tau = tau0;
+    {   // 1. centre row
+        int ib, ie, b = 0, e = 0;
+        if (row_cells(qc, g, 0, 0, tau, ib, ie)) { b = __ldg(cell_start + ib); e = __ldg(cell_start + ie); }
+        cand += (unsigned long long)(e - b);
+#pragma unroll 1
+        for (int p0 = b; p0 < e; p0 += BATCH1) {
+            float4 c[BATCH1];
 #pragma unroll
-            for (int i = 0; i < kFlatBatch; ++i) {
-                if (i < nmine) {
-                    const u64 k = make_key(sx, sy, sz, c[i]);
-                    const int j = k == res.k0 ? 0 : k == res.k1 ? 1 : k == res.k2 ? 2 : k == res.k3 ? 3 : k == res.k4 ? 4 : -1;
-                    if (j >= 0) nb_out[j] = c[i];
-                }
-            }
+            for (int i = 0; i < BATCH1; ++i) if (p0 + i < e) c[i] = __ldg(map + p0 + i);
+#pragma unroll
+            for (int i = 0; i < BATCH1; ++i) if (p0 + i < e) consider(sx, sy, sz, c[i], top, tau);
         }
-        if (sub == 0) *nb_flag = single ? 1 : 0;
+    }
+    // 2. surviving rows: faces first (they hold the nearer cells), then corners
+    int nruns = 0;
+    {
+        int rb[kRunCap], re[kRunCap];
+        float bnd[kRunCap];
+#pragma unroll
+        for (int k = 0; k < kRunCap; ++k) {
+            const int oy = k == 0 ? -1 : k == 1 ? 1 : k == 2 ? 0 : k == 3 ? 0 : (k & 1) ? 1 : -1;
+            const int oz = k == 0 ? 0 : k == 1 ? 0 : k == 2 ? -1 : k == 3 ? 1 : k < 6 ? -1 : 1;
+            int ib, ie;
+            rb[k] = 0; re[k] = 0;
+            bnd[k] = cell_bound(qc, 0, oy, oz);
+            if (row_cells(qc, g, oy, oz, tau, ib, ie)) { rb[k] = __ldg(cell_start + ib); re[k] = __ldg(cell_start + ie); }
+        }
+#pragma unroll
+        for (int k = 0; k < kRunCap; ++k) {
+            if (re[k] > rb[k]) { runs[nruns * run_stride] = make_int4(rb[k], re[k], __float_as_int(bnd[k]), 0); ++nruns; }
+        }
+    }
+    // 3. one flat loop over the listed runs
+    int k = 0, p = 0, e = 0;
+#pragma unroll 1
+    while (true) {
+        if (p >= e) {
+            bool have = false;
+            while (k < nruns) {
+                const int4 r = runs[k * run_stride];
+                ++k;
+                if (__int_as_float(r.z) <= tau) { p = r.x; e = r.y; have = true; break; }   // tau has shrunk since step 2
+            }
+            if (!have) break;
+        }
+        float4 c[BATCH3];
+#pragma unroll
+        for (int i = 0; i < BATCH3; ++i) if (p + i < e) c[i] = __ldg(map + p + i);
+#pragma unroll
+        for (int i = 0; i < BATCH3; ++i) if (p + i < e) consider(sx, sy, sz, c[i], top, tau);
+        cand += (unsigned long long)(min(e - p, BATCH3));
+        p += BATCH3;
     }
 }
 

@@ -172,13 +172,14 @@ static void unpack_sym(const double s[27], double H[6][6], double g[6]) {
     for (int a = 0; a < 6; ++a) g[a] = s[21 + a];
 }
 
-// dense symmetric positive (semi)definite 6x6 solve by LDL^T with a tiny-pivot guard
-static bool solve6(const double Hin[6][6], const double bin[6], double x[6]) {
+// dense symmetric positive (semi)definite 6x6 solve by LDL^T with a tiny-pivot guard; lambda is added to the diagonal,
+// piv_min >= 0 additionally rejects pivots that are not above it
+static bool solve6(const double Hin[6][6], const double bin[6], double x[6], double lambda = 0.0, double piv_min = -1.0) {
     double L[6][6] = {{0}}, D[6];
     for (int j = 0; j < 6; ++j) {
-        double d = Hin[j][j];
+        double d = Hin[j][j] + lambda;
         for (int k = 0; k < j; ++k) d -= L[j][k] * L[j][k] * D[k];
-        if (!(std::fabs(d) > 1e-300)) return false;
+        if (!(std::fabs(d) > 1e-300) || !std::isfinite(d) || (piv_min >= 0.0 && !(d > piv_min))) return false;
         D[j] = d;
         L[j][j] = 1;
         for (int i = j + 1; i < 6; ++i) {
@@ -191,6 +192,23 @@ static bool solve6(const double Hin[6][6], const double bin[6], double x[6]) {
     for (int i = 0; i < 6; ++i) { double s = bin[i]; for (int k = 0; k < i; ++k) s -= L[i][k] * y[k]; y[i] = s; }
     for (int i = 0; i < 6; ++i) y[i] /= D[i];
     for (int i = 5; i >= 0; --i) { double s = y[i]; for (int k = i + 1; k < 6; ++k) s -= L[k][i] * x[k]; x[i] = s; }
+    for (int i = 0; i < 6; ++i) if (!std::isfinite(x[i])) return false;
+    return true;
+}
+
+// The GN mode's step (NOT the reference's solver, which is Ceres LM = orc_scan_to_map_ceres): plain LDL^T solution of
+// H d = -g, with (1) a Levenberg-damped re-solve when a pivot is below 1e-10 * max diag(H) (unconstrained direction) and
+// (2) a trust region of 0.35 rad / 5 m on the step.  Same constants as dev_math.cuh::gn_safe_step.
+static bool gn_safe_step(const double H[6][6], const double nb[6], double d[6]) {
+    double maxd = 0;
+    for (int k = 0; k < 6; ++k) maxd = std::fmax(maxd, H[k][k]);
+    if (!(maxd > 0.0) || !std::isfinite(maxd)) return false;
+    if (!solve6(H, nb, d, 0.0, 1e-10 * maxd) && !solve6(H, nb, d, 1e-6 * maxd, 0.0)) return false;
+    const double rot = std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]), tr = std::sqrt(d[3] * d[3] + d[4] * d[4] + d[5] * d[5]);
+    double sc = 1.0;
+    if (rot > 0.35) sc = 0.35 / rot;
+    if (tr * sc > 5.0) sc = 5.0 / tr;
+    if (sc < 1.0) for (int k = 0; k < 6; ++k) d[k] *= sc;
     return true;
 }
 
@@ -209,7 +227,7 @@ extern "C" int orc_scan_to_map_gn(const void* tree, const float* map_xyzw, int m
         unpack_sym(s29, H, g);
         for (int k = 0; k < 6; ++k) nb[k] = -g[k];
         double xn[7];
-        if (nc > 0 && solve6(H, nb, d)) pose_plus(x, d, xn); else std::memcpy(xn, x, sizeof(xn));
+        if (nc > 0 && gn_safe_step(H, nb, d)) pose_plus(x, d, xn); else std::memcpy(xn, x, sizeof(xn));
         unify(xn);
         if (stats) {
             stats[it].n_corr = nc; stats[it].lm_iters = 1; stats[it].cost = s29[27];

@@ -141,8 +141,18 @@ def test_map_lifecycle_matches_reference_pipeline(oracle, world_small):
     want = oracle.voxelgrid(np.concatenate(frames[-20:]), 0.4)
     got = c.map_download()
     assert m == len(want) == len(got)
-    assert np.array_equal(got[:, 0].view(np.uint32), want["x"].view(np.uint32))
-    assert np.array_equal(got[:, 2].view(np.uint32), want["z"].view(np.uint32))
+    for k, f in enumerate(("x", "y", "z")):                       # every channel the search reads; w carries the point's index
+        assert np.array_equal(got[:, k].view(np.uint32), want[f].view(np.uint32)), f
+    assert np.array_equal(got[:, 3].view(np.int32), np.arange(m, dtype=np.int32))
+    # ... and the map a scan is matched against is that cloud: same correspondences as the oracle's kd-tree over it
+    m4 = np.ones((m, 4), np.float32); m4[:, 0] = want["x"]; m4[:, 1] = want["y"]; m4[:, 2] = want["z"]
+    tree = oracle.KdTree(m4)
+    cnt, valid_o, plane_o, idx_o, pw_o = oracle.find_surf_corr(tree, ds, world_small["guess"])
+    valid, plane, idx, sqd, s29 = c.find_surf_corr(ds, world_small["guess"])
+    assert np.array_equal(valid, valid_o) and cnt > 100
+    _, sqd_o = tree.knn5(pw_o)
+    inside = sqd_o[:, 4] < 1.0
+    assert np.array_equal(idx[inside], idx_o[inside])
     c.close()
 
 

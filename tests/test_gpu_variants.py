@@ -1,6 +1,8 @@
-"""The latency variants of the small-scan GN kernel must not change a single bit:
-  LILIOM_KNN_FLAT = 0 one run per lane | 1 candidates dealt round-robin over the 16 lanes | 2 + per-iteration candidate cache
-  LILIOM_GN_SYNC  = 3 counter grid barrier with a release-only arrival (default) | 0 full fences on both sides
+"""The switches of the small-scan GN kernel must not change a single bit:
+  LILIOM_GN_SYNC  = 3 counter grid barrier with a release-only arrival and a relaxed poll (default) | 1 release arrival +
+                    acquire poll | 0 full fences on both sides
+  LILIOM_FAST_IO  = 1 start pose in the launch parameters, one read-back block
+  fused peer exchange of one rank with itself (the whole NVLink protocol on a single GPU)
 Same candidate sets, same per-row arithmetic, same summation trees -> identical poses, correspondences and sums."""
 import os
 
@@ -9,19 +11,15 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
-VARIANTS = [(0, 3), (0, 0), (1, 3), (1, 0), (2, 3), (2, 0)]
-# switches that have not been measured on a B200 yet (written after the round's GPU budget was spent) join the matrix only on request
-EXTRA = {}
-if os.environ.get("LILIOM_TEST_EXPERIMENTAL"):
-    VARIANTS += [(0, 13), (1, 10), (0, 23)]         # +10: LILIOM_FAST_IO=1 on top of the sync mode; +20: fused peer exchange with itself
-    EXTRA = {"LILIOM_FAST_IO": "1"}
+# (unused, mode): mode % 10 = LILIOM_GN_SYNC; +10: LILIOM_FAST_IO=1; +20: fused peer exchange with itself
+VARIANTS = [(0, 3), (0, 1), (0, 0), (0, 13), (0, 23)]
 
 
 def _ctx(flat, ll):
     import liliom_b200 as L
-    keys = ("LILIOM_KNN_FLAT", "LILIOM_GN_SYNC", "LILIOM_FAST_IO")
+    keys = ("LILIOM_GN_SYNC", "LILIOM_FAST_IO")
     old = {k: os.environ.get(k) for k in keys}
-    os.environ["LILIOM_KNN_FLAT"] = str(flat); os.environ["LILIOM_GN_SYNC"] = str(ll % 10)
+    os.environ["LILIOM_GN_SYNC"] = str(ll % 10)
     os.environ["LILIOM_FAST_IO"] = "1" if 10 <= ll < 20 else "0"
     try:
         c = L.Context(variant=0)             # the switches are read at liliom_create
@@ -41,8 +39,7 @@ def test_gn_variants_bit_identical(oracle, world_small):
     surf, _, _ = oracle.extract_horizon(world_small["hz"], world_small["q_hz"])
     ds = oracle.voxelgrid(surf, 0.4)
     guess = world_small["guess"]
-    # scans of different sizes back to back: the grid size (and the LL layout stride) changes between launches,
-    # the last one is large enough to leave the 16-lane shape (flat does not apply there)
+    # scans of different sizes back to back: the grid size changes between launches, the larger ones leave the 16-lane shape
     scans = [ds, ds[: len(ds) // 3], ds[::2], ds[:40], surf[:6000], surf[:3000], ds]     # 3000: two search rounds per warp task
     ref = None
     for flat, ll in VARIANTS:
@@ -53,7 +50,7 @@ def test_gn_variants_bit_identical(oracle, world_small):
             for iters in (10, 3):
                 pose, st = c.scan_to_map(f, guess, iters, mode=L.MODE_GN)
                 out.append((pose.copy(), [np.array(s.jtj_jtr) for s in st], [s.n_corr for s in st], [s.cost for s in st]))
-        v, pl, idx, sqd, s29 = c.find_surf_corr(ds, guess)          # k_knn_plane<16> (ticket path), flat or not
+        v, pl, idx, sqd, s29 = c.find_surf_corr(ds, guess)          # k_knn_plane<16> (ticket path)
         out.append((s29.copy(), [pl.copy()], [idx.copy(), v.copy()], [sqd.copy()]))
         c.close()
         if ref is None:
