@@ -4,22 +4,29 @@
 One "step" = one scan through the hot path:
     feature extraction (raw sweep) -> VoxelGrid(0.4) of the surf features -> ITERS x
     [5-NN in the voxel map + plane fit + residual/Jacobian + 27-scalar reduce + 6x6 solve + pose update]
+    (+ per-scan map maintenance in the streamed workload: push a frame, re-filter and re-index the local map)
 
-N = 1 workload (BASELINE.json configs[1]): 24k-pt Livox-Horizon sweep, 1 M-pt voxel map, 10 GN iterations.
-N > 1 : --multi replicas (default): every GPU runs the N = 1 workload on its own scan stream — the path is
-        data-parallel over independent sensors/robots, no data-path collective, weak scaling;
-        --multi sharded: ONE scan stream, 5 M-pt map sharded by 16 m block hash (+1 m halo), one 29-scalar NCCL
-        all-reduce per GN iteration (configs[3], strong scaling).  Measured on 2 GPUs the all-reduce latency
-        (~20 us x 10 iterations) outweighs the sharded search for a 1.4k-query scan — see DESIGN.md §4.
+N = 1 : BASELINE.json configs[1] — 24k-pt Livox-Horizon sweep, 1 M-pt voxel map, 10 GN iterations, map pre-built
+        (--workload rot: configs[2], 130k-pt HDL-64E sweep through the LiLi-OM-ROT extractor, 2 M-pt map).
+N > 1 : BASELINE.json configs[4] (--multi sharded, default) — ONE scan stream: 130k-pt HDL-64E sweep, 10 M-pt local map kept as a
+        FIFO of 20 frames and SHARDED by voxel-block hash across the GPUs (halo replicated), 10 GN iterations with one exchange
+        of the 29 normal-equation scalars per iteration (fused into the GN kernel over NVLink peer memory; NCCL all-reduce
+        with LILIOM_BENCH_NCCL=1), and the reference's per-scan map maintenance INSIDE the step (L/src/LidarOdometry.cpp:
+        280-323, 490: push the frame, concatenate, VoxelGrid(0.4), rebuild the search structure) — the part that shards.
+        Strong scaling: the line also carries the same workload on one GPU, measured in the same run (`same_workload_1gpu`).
+        --multi replicas: every GPU runs the N = 1 workload on its own scan stream (no collective, weak scaling); the
+        sharded line reports it as a secondary key (`replicas`).
 
 value  : scans/s with the sweep already resident in HBM (only the 56-byte pose returns to the host).
-e2e    : scans/s through the reference-facing calls with HOST buffers — Preprocessing node call
-         (H2D raw sweep, D2H the three published clouds) + LidarOdometry node call (H2D surf cloud,
-         D2H pose + surf_last_ds).
-roofline: kNN+Jacobian kernel, algorithmic bytes (SURVEY.md §8 d) / CUDA-event duration / measured HBM peak.
-cpu_baseline: the CPU oracle (restatement of the reference, oracle/) on the host cores, bounded sample.
---impl reference: the same workload on the CPU oracle with all host threads (the reference itself cannot
-         be built here: needs ROS/PCL/Eigen/Ceres).
+e2e    : scans/s through the reference-facing calls with HOST (pinned) buffers — Preprocessing node call (H2D raw sweep,
+         D2H the three published clouds) + LidarOdometry node call (H2D surf cloud, D2H pose + surf_last_ds)
+         (+ H2D of the pushed frame in the streamed workload).
+roofline: kNN+Jacobian kernel — algorithmic bytes per SURVEY.md §8(d), B_q = 16 + 27*8 + 16*C-bar per query and pass with
+         C-bar = points in the query's 27 cells (counted by liliom_knn_block_stats), over the CUDA-event duration of a pass,
+         against the measured HBM peak.  The search prunes; `examined` carries the same figure on the bytes actually fetched.
+cpu_baseline: the CPU oracle (restatement of the reference, oracle/) on the host cores, bounded sample, 1 thread.
+--impl reference: the same workload on the CPU oracle with the host threads (the reference itself cannot be built here:
+         needs ROS/PCL/Eigen/Ceres).
 """
 from __future__ import annotations
 
@@ -37,6 +44,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 ITERS = 10
+N_FRAMES = 20
 METRIC = "scans/sec (24k-pt sweep vs 1M-pt map); kNN+Jacobian HBM GB/s vs peak"
 
 
@@ -46,17 +54,18 @@ def parse():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--multi", default="replicas", choices=["sharded", "replicas"])
+    ap.add_argument("--multi", default="sharded", choices=["sharded", "replicas"])
     ap.add_argument("--map-points", type=int, default=0, help="override the map size")
     ap.add_argument("--sweeps", type=int, default=8, help="distinct synthetic sweeps cycled through the steps")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e", default="two-nodes", choices=["two-nodes", "sequential"],
-                    help="e2e leg: two concurrent node threads (reference architecture, default) or one thread calling both nodes in turn")
+                    help="e2e leg at N = 1: two concurrent node threads (reference architecture, default) or one thread calling both nodes in turn")
     ap.add_argument("--dense-queries", action="store_true", help="roofline micro-run: every surf feature is a query (no scan DS)")
-    ap.add_argument("--no-dense-probe", action="store_true", help="skip the short dense-query probe that annotates roofline.dense_probe")
-    ap.add_argument("--workload", default="horizon", choices=["horizon", "rot"],
-                    help="horizon: BASELINE configs[1] (24k-pt Livox sweep, 1 M-pt map; the metric's config, default); "
-                         "rot: configs[2] (130k-pt HDL-64E sweep through the LiLi-OM-ROT extractor, 2 M-pt map)")
+    ap.add_argument("--no-dense-probe", action="store_true", help="skip the dense-query probes that annotate roofline.dense_probe")
+    ap.add_argument("--no-extra-legs", action="store_true", help="N > 1: skip the same-workload-on-one-GPU and replicas legs")
+    ap.add_argument("--workload", default="", choices=["", "horizon", "rot", "stream"],
+                    help="horizon: configs[1] (default at N = 1); rot: configs[2]; stream: configs[4]'s streamed workload "
+                         "(130k sweep, 10 M-pt map as 20 frames, map maintenance in the step; default at N > 1, also runs at N = 1)")
     return ap.parse_args()
 
 
@@ -71,10 +80,12 @@ def measured_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (recipe's clocks line)."""
+    """nvidia-smi clocks / throttle reasons during the timed region (recipe's clocks line).  Rank 0 only: one poller per
+    node is enough, and N pollers forking nvidia-smi at 10 Hz compete with the ranks' own host threads."""
 
-    def __init__(self, index: int):
+    def __init__(self, index: int, enabled: bool = True):
         self.index = index
+        self.enabled = enabled
         self.rows = []
         self._stop = threading.Event()
         self._t = None
@@ -90,16 +101,18 @@ class ClockSampler:
                     self.rows.append([x.strip() for x in out.split(",")])
             except Exception:
                 pass
-            self._stop.wait(0.1)
+            self._stop.wait(0.2)
 
     def __enter__(self):
-        self._t = threading.Thread(target=self._run, daemon=True)
-        self._t.start()
+        if self.enabled:
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
         return self
 
     def __exit__(self, *a):
         self._stop.set()
-        self._t.join(timeout=6)
+        if self._t:
+            self._t.join(timeout=6)
 
     def summary(self):
         sm, mx, reasons = [], [], set()
@@ -169,14 +182,23 @@ def run_two_stage_pipeline(total, warmup, nbuf, stage_a, stage_b, on_start, on_e
         raise RuntimeError("two-stage pipeline did not finish")
 
 
-def make_workload(n_map: int, n_sweeps: int, variant: int = 0):
+# ---------------------------------------------------------------------------------------------- workloads
+def resolve_workload(args, world):
+    """(kind, n_map): horizon = configs[1], rot = configs[2], stream = configs[4]'s streamed workload."""
+    sharded = world > 1 and args.multi == "sharded"
+    kind = args.workload or ("stream" if sharded else "horizon")
+    n_map = args.map_points or {"horizon": 1_000_000, "rot": 2_000_000, "stream": 10_000_000}[kind]
+    return kind, n_map
+
+
+def make_workload(kind: str, n_map: int, n_sweeps: int):
     from liliom_b200 import synth
     m, _ = synth.make_map(n_map)
     T0 = synth.default_true_pose()
     sweeps = []
     for k in range(n_sweeps):
         T = np.array(T0); T[4] += 0.7 * k; T[5] += 0.15 * k       # sensor advancing through the block
-        if variant == 0:
+        if kind == "horizon":
             pts, q = synth.make_horizon_sweep(T, seed=1 + k)
         else:
             pts, q = synth.make_hdl64_sweep(T, seed=2 + k)
@@ -184,21 +206,77 @@ def make_workload(n_map: int, n_sweeps: int, variant: int = 0):
     return m, sweeps
 
 
-def workload_name(rot, n_returns, n_map):
-    if rot:
+def make_frames(m, PT):
+    """The streamed workload's local map as the reference holds it: a FIFO of N_FRAMES world-frame clouds (here: equal
+    slabs of the synthetic map along x, oldest first) whose concatenation, VoxelGrid-filtered, is the map."""
+    order = np.argsort(m[:, 0], kind="stable")
+    frames = []
+    per = (len(m) + N_FRAMES - 1) // N_FRAMES
+    for k in range(N_FRAMES):
+        idx = order[k * per:(k + 1) * per]
+        f = np.zeros(len(idx), PT)
+        f["x"] = m[idx, 0]; f["y"] = m[idx, 1]; f["z"] = m[idx, 2]; f["w"] = 1.0
+        frames.append(f)
+    return frames
+
+
+def workload_name(kind, n_returns, n_map):
+    if kind == "rot":
         return f"130k-pt HDL-64E sweep ({n_returns} returns, LiLi-OM-ROT extractor, ds_rate 4) vs {n_map}-pt voxel map, {ITERS} GN iters"
+    if kind == "stream":
+        return (f"streamed: 130k-pt HDL-64E sweep ({n_returns} returns, LiLi-OM-ROT extractor, ds_rate 4) vs {n_map}-pt local map held as "
+                f"{N_FRAMES} frames, {ITERS} GN iters, then per-scan map maintenance (push frame, concatenate, VoxelGrid 0.4, re-index) inside the step")
     return f"24k-pt Livox-Horizon sweep ({n_returns} returns) vs {n_map}-pt voxel map, {ITERS} GN iters"
 
 
+def config_dict(kind, n_returns, n_map, world, multi):
+    """The `config` object — the SAME keys and values in both arms (ours / reference)."""
+    return {"workload": workload_name(kind, n_returns, n_map), "kind": kind, "map_points": n_map, "iters": ITERS,
+            "map_frames": N_FRAMES if kind == "stream" else 0,
+            "multi": ("single" if world == 1 else multi), "n_gpus": world,
+            "l2": "GPU arm: a 256 MB buffer is written between timed steps (L2 flushed), each step timed with its own CUDA-event pair on the "
+                  "launch stream; CPU arm: wall clock around the timed steps"}
+
+
 # ---------------------------------------------------------------------------------------------- CPU oracle legs
-def cpu_scan(O, tree, sw, nthreads):
-    if sw["pts"].dtype.itemsize == 32:      # ROT package (configs[2])
-        rc, surf, edge, cut, _, _ = O.extract_rot(sw["pts"], sw["q"], (1.0, 0, 0, 0), 64, 4)
-    else:
-        surf, edge, cut = O.extract_horizon(sw["pts"], sw["q"])
-    ds = O.voxelgrid(surf, 0.4)
-    rc, pose, st = O.scan_to_map_gn(tree, ds, sw["guess"], ITERS, nthreads)
-    return pose, len(ds)
+class CpuWorkload:
+    """The oracle (oracle/, test infrastructure) running one scan of the workload — the cpu_baseline leg and --impl reference."""
+
+    def __init__(self, kind, m, sweeps):
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle_lib as O
+        self.O, self.kind, self.sweeps = O, kind, sweeps
+        t0 = time.perf_counter()
+        if kind == "stream":
+            self.frames = make_frames(m, O.PT32)
+            self.map4 = self._filter_and_index()          # as the reference: VoxelGrid of the concatenation, kd-tree over it
+        else:
+            self.map4 = m
+            self.tree = O.KdTree(m)
+        self.t_setup = time.perf_counter() - t0
+
+    def _filter_and_index(self):
+        O = self.O
+        ds = O.voxelgrid(np.concatenate(self.frames), 0.4)                 # L/src/LidarOdometry.cpp:301-302, 316-317
+        m4 = np.ones((len(ds), 4), np.float32)
+        m4[:, 0] = ds["x"]; m4[:, 1] = ds["y"]; m4[:, 2] = ds["z"]
+        self.tree = O.KdTree(m4)                                           # :490
+        return m4
+
+    def scan(self, k, nthreads):
+        O, sw = self.O, self.sweeps[k % len(self.sweeps)]
+        if sw["pts"].dtype.itemsize == 32:      # ROT package
+            rc, surf, edge, cut, _, _ = O.extract_rot(sw["pts"], sw["q"], (1.0, 0, 0, 0), 64, 4)
+        else:
+            surf, edge, cut = O.extract_horizon(sw["pts"], sw["q"])
+        ds = O.voxelgrid(surf, 0.4)
+        rc, pose, st = O.scan_to_map_gn(self.tree, ds, sw["guess"], ITERS, nthreads)
+        if self.kind == "stream":               # per-scan map maintenance: pop the oldest frame, push one, re-filter, re-index
+            ident = np.array([1.0, 0, 0, 0, 0, 0, 0])
+            f = self.frames.pop(0)
+            self.frames.append(O.transform_cloud(f, ident))                # :246-278 on the pushed frame
+            self.map4 = self._filter_and_index()
+        return pose, len(ds)
 
 
 def run_reference(args):
@@ -206,57 +284,66 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import oracle_lib as O
-    rot = args.workload == "rot"
-    n_map = args.map_points or (2_000_000 if rot else 1_000_000)
-    m, sweeps = make_workload(n_map, min(args.sweeps, 4), 1 if rot else 0)
-    t0 = time.perf_counter(); tree = O.KdTree(m); t_build = time.perf_counter() - t0
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    kind, n_map = resolve_workload(args, world)
+    m, sweeps = make_workload(kind, n_map, min(args.sweeps, 4))
+    W = CpuWorkload(kind, m, sweeps)
     cores = os.cpu_count() or 1
-    # pick the faster of 1 thread / all threads on one probe scan (OpenMP over queries can lose on shared hosts)
-    best_nt, best_t = 1, None
     os.environ.setdefault("OMP_WAIT_POLICY", "passive")
-    for nt in sorted({1, 2, 4, 8, 16, 32, cores} & set(range(1, cores + 1))):
-        t0 = time.perf_counter(); cpu_scan(O, tree, sweeps[0], nt); dt = time.perf_counter() - t0
-        if best_t is None or dt < best_t:
-            best_nt, best_t = nt, dt
-    steps = max(1, min(args.steps, int(60.0 / max(best_t, 1e-3))))
-    for k in range(min(args.warmup, 2)):
-        cpu_scan(O, tree, sweeps[k % len(sweeps)], best_nt)
+    # thread count: median of PROBE scans per candidate (OpenMP over the queries can lose on shared hosts); 1 thread is the
+    # reference's own architecture and is always reported beside the best
+    heavy = kind == "stream"
+    PROBE = 1 if heavy else 5
+    cands = sorted({1, 4, 8, 16, 32, cores} & set(range(1, cores + 1))) if not heavy else sorted({1, min(16, cores)})
+    probe = {}
+    W.scan(0, 1)                                            # first-touch warm-up, not timed
+    for nt in cands:
+        ts = []
+        for k in range(PROBE):
+            t0 = time.perf_counter(); W.scan(k, nt); ts.append(time.perf_counter() - t0)
+        probe[nt] = float(np.median(ts))
+    best_nt = min(probe, key=probe.get)
+    warm = max(args.warmup, 3) if not heavy else 1
+    steps = max(1, min(args.steps, int(45.0 / max(probe[best_nt], 1e-3))))
+    for k in range(warm):
+        W.scan(k, best_nt)
     t0 = time.perf_counter()
     for k in range(steps):
-        cpu_scan(O, tree, sweeps[k % len(sweeps)], best_nt)
+        W.scan(k, best_nt)
     dt = time.perf_counter() - t0
     val = steps / dt
-    sample = f"{steps} scans (extract + VoxelGrid + {ITERS} GN iters, kd-tree prebuilt in {t_build:.2f}s, excluded)"
+    sample = (f"{steps} scans (extract + VoxelGrid + {ITERS} GN iters" + (", + map maintenance: VoxelGrid of the 20-frame concatenation and kd-tree build per scan" if heavy else
+              f", kd-tree prebuilt in {W.t_setup:.2f}s, excluded — the reference rebuilds it per scan, L/src/LidarOdometry.cpp:490") + ")")
+    cfg = config_dict(kind, len(sweeps[0]["pts"]), n_map, world, args.multi)
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "scans/s", "n_gpus": args.gpus, "steps": steps,
-            "warmup": min(args.warmup, 2), "ms_per_step": 1e3 * dt / steps, "higher_is_better": True,
-            "scaling": "strong" if args.multi == "sharded" else "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(rot, len(sweeps[0]['pts']), n_map),
-                       "map_points": n_map, "iters": ITERS,
-                       "impl_note": "CPU oracle port of the reference path (oracle/): the reference itself needs ROS/PCL/Eigen/Ceres and cannot be "
-                                    "built in this image; best of {1,2,4,8,16,32,all} OpenMP threads over the queries"},
+            "warmup": warm, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True,
+            "scaling": "strong" if (world > 1 and args.multi == "sharded") else "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
+            "impl_note": "CPU oracle port of the reference path (oracle/): the reference itself needs ROS/PCL/Eigen/Ceres and cannot be built in "
+                         "this image; OpenMP over the queries, thread count = best median of the probe scans; extraction and VoxelGrid are "
+                         "single-threaded as in the reference",
+            "threads_probe_s_per_scan": {str(k): v for k, v in probe.items()},
+            "one_thread_value": 1.0 / probe[1],
             "cpu_baseline": {"value": val, "unit": "scans/s", "cores": best_nt, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
-def cpu_baseline_leg(m, sweeps):
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import oracle_lib as O
-    tree = O.KdTree(m)
-    cpu_scan(O, tree, sweeps[0], 1)
+def cpu_baseline_leg(kind, m, sweeps):
+    W = CpuWorkload(kind, m, sweeps)
+    W.scan(0, 1)
     n = 0
     t0 = time.perf_counter()
     while True:
-        cpu_scan(O, tree, sweeps[n % len(sweeps)], 1)
+        W.scan(n, 1)
         n += 1
         if time.perf_counter() - t0 > 10.0:
             break
     dt = time.perf_counter() - t0
     return {"value": n / dt, "unit": "scans/s", "cores": 1, "kind": "port",
-            "sample": f"{n} scans in {dt:.1f}s, 1 thread (the reference nodes are single-threaded), kd-tree build excluded"}
+            "sample": f"{n} scans in {dt:.1f}s, 1 thread (the reference nodes are single-threaded)"
+                      + (", map maintenance (VoxelGrid + kd-tree build) included" if kind == "stream" else
+                         ", kd-tree build EXCLUDED (the reference rebuilds it per scan, L/src/LidarOdometry.cpp:490: with it the CPU figure is lower)")}
 
 
 # ---------------------------------------------------------------------------------------------- GPU legs
@@ -279,10 +366,13 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     sharded = multi and args.multi == "sharded"
-    rot = args.workload == "rot"
-    n_map = args.map_points or (5_000_000 if sharded else 2_000_000 if rot else 1_000_000)
+    kind, n_map = resolve_workload(args, world)
+    stream_wl = kind == "stream"
+    rot = kind != "horizon"
+    steps = args.steps
+    warmup = max(args.warmup, 3)
 
-    m, sweeps = make_workload(n_map, args.sweeps, 1 if rot else 0)
+    m, sweeps = make_workload(kind, n_map, args.sweeps)
     if multi and not sharded:     # replicas: every rank gets its own scan stream
         sweeps = sweeps[rank % len(sweeps):] + sweeps[:rank % len(sweeps)]
 
@@ -291,18 +381,43 @@ def main():
     psz = PT.itemsize
     if args.dense_queries:
         prm.leaf_scan = 0.0        # no scan down-sampling: every surf feature is a query (roofline micro-run)
-    ctx = L.Context(prm, device=local_rank)
     stream = torch.cuda.Stream()
-    ctx.set_stream(stream.cuda_stream)
-    if sharded:
-        uid = [L.comm_get_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(uid, src=0)
-        ctx.comm_init(uid[0], world, rank)
-        if os.environ.get("LILIOM_PEER"):     # fused exchange over NVLink peer memory (one launch per scan and rank) instead of NCCL per iteration
-            hs = [None] * world
-            dist.all_gather_object(hs, ctx.comm_peer_export())
-            ctx.comm_peer_attach(hs, rank)
-    ctx.map_set_points(m)
+    ident = np.array([1.0, 0, 0, 0, 0, 0, 0])
+    use_nccl_exchange = bool(os.environ.get("LILIOM_BENCH_NCCL"))
+
+    def new_context(with_comm: bool):
+        cx = L.Context(prm, device=local_rank)
+        cx.set_stream(stream.cuda_stream)
+        if with_comm:
+            uid = [L.comm_get_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(uid, src=0)
+            cx.comm_init(uid[0], world, rank)
+            if not use_nccl_exchange:     # fused exchange over NVLink peer memory: one launch per scan and rank, no collective call per iteration
+                hs = [None] * world
+                dist.all_gather_object(hs, cx.comm_peer_export())
+                cx.comm_peer_attach(hs, rank)
+        return cx
+
+    # ---- the streamed workload's frames: device-resident (resident leg) and pinned host (e2e leg)
+    frames_host, frames_dev = [], []
+    if stream_wl:
+        for f in make_frames(m, PT):
+            th = torch.from_numpy(f.view(np.uint8).reshape(-1)).pin_memory()
+            frames_host.append(th.numpy().view(PT))
+            frames_dev.append(th.to("cuda", non_blocking=True))
+        torch.cuda.synchronize()
+
+    def install_map(cx):
+        if stream_wl:
+            cx.map_clear()
+            for fd in frames_dev:
+                cx.map_push_frame_device(fd.data_ptr(), fd.numel() // psz, ident)
+            return cx.map_rebuild()
+        cx.map_set_points(m)
+        return len(m)
+
+    ctx = new_context(sharded)
+    n_map_installed = install_map(ctx)
     ctx.set_kernel_timing(True)
 
     # pinned host buffers for the e2e leg (the contract: inputs come from pinned host memory)
@@ -328,23 +443,38 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step_resident(k):
-        sw = sweeps[k % len(sweeps)]
-        ns, ne, nc = ctx.extract_resident(sw["q"])
-        pose, st, nds = ctx.odometry_resident(sw["guess"], ITERS, mode=L.MODE_GN, want_stats=False)
-        return pose, nds
+    def make_steps(cx):
+        """The two step functions on context cx.  Streamed workload: frame k % N_FRAMES is the oldest in the FIFO at step k
+        (it was pushed N_FRAMES pushes ago); pushing it again keeps the map's content — and the step's work — constant."""
+        def step_resident(k):
+            sw = sweeps[k % len(sweeps)]
+            cx.extract_resident(sw["q"])
+            pose, st, nds = cx.odometry_resident(sw["guess"], ITERS, mode=L.MODE_GN, want_stats=False)
+            if stream_wl:
+                fd = frames_dev[k % N_FRAMES]
+                cx.map_push_frame_device(fd.data_ptr(), fd.numel() // psz, ident)
+                cx.map_rebuild()
+            return pose, nds
 
-    def step_e2e(k):
-        i = k % len(sweeps)
-        # Preprocessing node call: H2D raw sweep, D2H the three published clouds (pinned host buffers)
-        surf, edge, cut = extract_host(ctx, i, (out_surf, out_edge, out_cut))
-        # LidarOdometry node call on the /surf_features cloud as received (host): H2D, D2H pose + surf_last_ds
-        pose, st, ds = ctx.odometry(surf, sweeps[i]["guess"], ITERS, mode=L.MODE_GN, ds_out=out_ds, pose_out=pose_buf, want_stats=False)
-        h2d = len(pin_sweeps[i]) * psz + len(surf) * psz + 56
-        d2h = (len(surf) + len(edge) + len(cut)) * psz + len(ds) * psz + 56
-        return pose, h2d, d2h
+        def step_e2e(k):
+            i = k % len(sweeps)
+            # Preprocessing node call: H2D raw sweep, D2H the three published clouds (pinned host buffers)
+            surf, edge, cut = extract_host(cx, i, (out_surf, out_edge, out_cut))
+            # LidarOdometry node call on the /surf_features cloud as received (host): H2D, D2H pose + surf_last_ds
+            pose, st, ds = cx.odometry(surf, sweeps[i]["guess"], ITERS, mode=L.MODE_GN, ds_out=out_ds, pose_out=pose_buf, want_stats=False)
+            h2d = len(pin_sweeps[i]) * psz + len(surf) * psz + 56
+            d2h = (len(surf) + len(edge) + len(cut)) * psz + len(ds) * psz + 56
+            if stream_wl:
+                fh = frames_host[k % N_FRAMES]
+                cx.map_push_frame(fh, ident)                  # buildLocalMap's push: the frame arrives from the host
+                cx.map_rebuild()
+                h2d += len(fh) * psz + 56
+            return pose, h2d, d2h
+        return step_resident, step_e2e
 
-    def e2e_two_nodes(steps, warmup):
+    step_resident, step_e2e = make_steps(ctx)
+
+    def e2e_two_nodes(n_steps, n_warm):
         """The reference runs Preprocessing and LidarOdometry as two concurrent single-threaded nodes; so does this
         leg: one host thread + context + CUDA stream per node, the /surf_features hop through pinned host memory.
         A 256 MB L2-evicting write is issued per scan on a third stream INSIDE the timed region; in a pipelined steady
@@ -355,69 +485,49 @@ def main():
         s_flush = torch.cuda.Stream()
         # The LidarOdometry stream gets the higher priority: its cooperative GN kernel needs every CTA resident and meets
         # at 10 grid barriers, so queueing behind the other node's CTAs (or the flush) costs it far more than it costs them.
-        s_lo = torch.cuda.Stream(priority=-1) if os.environ.get("LILIOM_BENCH_PRIO", "1") == "1" else stream
+        s_lo = torch.cuda.Stream(priority=-1)
         ctx.set_stream(s_lo.cuda_stream)
         nbuf = 3
         sets = [[torch.empty(cap * psz, dtype=torch.uint8).pin_memory().numpy().view(PT) for _ in range(3)] for _ in range(nbuf)]
         ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
         result = {}
 
-        diag = {"a": 0.0, "b": 0.0, "fill": 0.0}
-        want_diag = bool(os.environ.get("LILIOM_BENCH_DIAG")); ev_pairs = []
-        flush_mode = os.environ.get("LILIOM_BENCH_FLUSH", "side")      # diagnosis only: side | pre | none
-
         def stage_a(k, b):
             i = k % len(sweeps)
-            t0 = time.perf_counter()
-            if flush_mode != "none":
-                with torch.cuda.stream(s_flush if flush_mode == "side" else s_pre):
-                    flush.fill_(k & 0xff)
-            t1 = time.perf_counter()
+            with torch.cuda.stream(s_flush):
+                flush.fill_(k & 0xff)
             surf, edge, cut = extract_host(ctx_pre, i, tuple(sets[b]))
-            diag["fill"] += t1 - t0; diag["a"] += time.perf_counter() - t1
             return (len(surf), len(edge), len(cut))
 
         def stage_b(k, b, item):
             ns, ne, nc = item
             i = k % len(sweeps)
-            t0 = time.perf_counter()
-            if want_diag:
-                ea = torch.cuda.Event(enable_timing=True); eb = torch.cuda.Event(enable_timing=True); ea.record(s_lo)
             pose, st, ds = ctx.odometry(sets[b][0][:ns], sweeps[i]["guess"], ITERS, mode=L.MODE_GN, ds_out=out_ds, pose_out=pose_buf, want_stats=False)
-            if want_diag:
-                eb.record(s_lo); ev_pairs.append((ea, eb))
-            diag["b"] += time.perf_counter() - t0
             result.update(pose=np.array(pose), h2d=len(pin_sweeps[i]) * psz + ns * psz + 56, d2h=(ns + ne + nc) * psz + len(ds) * psz + 56)
 
         barrier()
-        run_two_stage_pipeline(warmup + steps, warmup, nbuf, stage_a, stage_b,
+        run_two_stage_pipeline(n_warm + n_steps, n_warm, nbuf, stage_a, stage_b,
                                on_start=lambda: ev0.record(s_pre), on_end=lambda: ev1.record(s_lo))
         torch.cuda.synchronize()
         ms = ev0.elapsed_time(ev1)
         barrier()
-        if multi:
-            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
         ctx_pre.close()
         ctx.set_stream(stream.cuda_stream)
-        if os.environ.get("LILIOM_BENCH_DIAG"):
-            tot = warmup + steps
-            gpu_b = sum(a.elapsed_time(b) for a, b in ev_pairs) / max(len(ev_pairs), 1)
-            print(f"[diag] LidarOdometry call, GPU-side first-to-last op: {1e3 * gpu_b:.0f} us", file=sys.stderr)
-            print(f"[diag] two-nodes host wall per scan: fill {1e6 * diag['fill'] / tot:.0f} us, Preprocessing call {1e6 * diag['a'] / tot:.0f} us, "
-                  f"LidarOdometry call {1e6 * diag['b'] / tot:.0f} us, pipeline {1e3 * ms / steps:.0f} us", file=sys.stderr)
         return ms, (result["pose"], result["h2d"], result["d2h"])
 
-    def timed(fn, steps, warmup, prep=None):
-        for k in range(warmup):
+    def timed(fn, n_steps, n_warm, prep=None, after_warmup=None, collective=True):
+        """n_warm untimed steps, then n_steps steps each bracketed by its own CUDA-event pair on the launch stream, a 256 MB
+        L2-evicting write between them.  Returns (this rank's total ms, last result)."""
+        for k in range(n_warm):
             if prep: prep(k)
             fn(k)
-        barrier()
+        if after_warmup: after_warmup()
+        if collective: barrier()
+        else: torch.cuda.synchronize()
         tot_ms = 0.0
         last = None
         with torch.cuda.stream(stream):
-            for k in range(steps):
+            for k in range(n_steps):
                 if prep: prep(k)
                 flush.fill_(k & 0xff)                       # evict L2 between steps (cold-cache scans)
                 e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
@@ -426,59 +536,88 @@ def main():
                 e1.record(stream)
                 e1.synchronize()
                 tot_ms += e0.elapsed_time(e1)
-        barrier()
-        if multi:
-            t = torch.tensor([tot_ms], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            tot_ms = float(t.item())
+        if collective: barrier()
+        else: torch.cuda.synchronize()
         return tot_ms, last
 
-    def prep_resident(k):
-        ctx.upload_scan(sweeps[k % len(sweeps)]["pts"])     # untimed: the sweep is resident when the step starts
+    def over_ranks(ms):
+        """(max over ranks, per-rank list) of a rank-local time."""
+        if not multi:
+            return ms, [ms]
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        allt = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        per = [float(x.item()) for x in allt]
+        return max(per), per
 
-    # ---- timed region 1: device-resident
-    ctx.counters(reset=True)
-    with ClockSampler(local_rank) as clk:
-        ms_res, last = timed(step_resident, args.steps, max(args.warmup, 3), prep_resident)
+    def prep_for(cx):
+        def prep(k):
+            cx.upload_scan(sweeps[k % len(sweeps)]["pts"])     # untimed: the sweep is resident when the step starts
+        return prep
+
+    # ---- timed region 1: device-resident; counters cover exactly the timed steps
+    cnt_box = {}
+    with ClockSampler(local_rank, enabled=(rank == 0)) as clk:
+        ms_res_local, last = timed(step_resident, steps, warmup, prep_for(ctx), after_warmup=lambda: ctx.counters(reset=True))
         cnt = ctx.counters(reset=True)
+        ms_res, ms_res_ranks = over_ranks(ms_res_local)
         # ---- timed region 2: end to end with host buffers
-        ms_seq, last_seq = timed(step_e2e, args.steps, max(args.warmup, 3))
-        if args.e2e == "sequential" or sharded:
+        ms_seq_local, last_seq = timed(step_e2e, steps, warmup)
+        ms_seq, _ = over_ranks(ms_seq_local)
+        if args.e2e == "sequential" or sharded or stream_wl:
             ms_e2e, last_e2e = ms_seq, last_seq
         else:
-            ms_e2e, last_e2e = e2e_two_nodes(args.steps, max(args.warmup, 3))
+            ms_e2e_local, last_e2e = e2e_two_nodes(steps, warmup)
+            ms_e2e, _ = over_ranks(ms_e2e_local)
     clocks = clk.summary()
-    cnt_e2e = ctx.counters(reset=True)
+    ctx.counters(reset=True)
 
-    scans_total = args.steps * (world if (multi and not sharded) else 1)
+    replicas = multi and not sharded
+    scans_total = steps * (world if replicas else 1)
     value = scans_total / (ms_res * 1e-3)
     e2e_val = scans_total / (ms_e2e * 1e-3)
 
     # ---- roofline of the kNN+Jacobian kernel (algorithmic bytes per SURVEY.md §8 d)
     peak, peak_src = measured_peak()
-    roof = None
-    if cnt.knn_launches:
-        qpl = cnt.knn_queries / cnt.knn_launches
-        cbar = cnt.knn_candidates / max(cnt.knn_queries, 1)
-        bytes_per_launch = qpl * (16 + 27 * 8 + 16 * cbar)
-        t_launch = cnt.knn_ms * 1e-3 / cnt.knn_launches
-        ach = bytes_per_launch / t_launch / 1e9
-        traffic = None
+
+    def roofline_from(cx, cn, pose_for_stats):
+        if not cn.knn_launches:
+            return None
+        nq, c27 = cx.knn_block_stats(pose_for_stats)          # resident queries of the last scan, at its start pose
+        cbar27 = c27 / max(nq, 1)
+        qpl = cn.knn_queries / cn.knn_launches                # device-side count: queries searched per pass
+        cex = cn.knn_candidates / max(cn.knn_queries, 1)      # candidates examined per query after pruning
+        t_launch = cn.knn_ms * 1e-3 / cn.knn_launches
+        b8d = qpl * (16 + 27 * 8 + 16 * cbar27)
+        bex = qpl * (16 + 27 * 8 + 16 * cex)
+        return {"queries_per_launch": qpl, "candidates_per_query": cbar27, "examined_per_query": cex,
+                "algorithmic_bytes_per_launch": b8d, "us_per_launch": t_launch * 1e6, "achieved": b8d / t_launch / 1e9,
+                "frac": b8d / t_launch / 1e9 / peak,
+                "examined": {"bytes_per_launch": bex, "achieved": bex / t_launch / 1e9, "frac": bex / t_launch / 1e9 / peak},
+                "min_bytes_per_launch": qpl * 96.0, "passes_timed": int(cn.knn_launches)}
+
+    roof = roofline_from(ctx, cnt, sweeps[(steps - 1) % len(sweeps)]["guess"])
+    if roof is not None:
+        traffic, traffic_src = None, None
         tp = os.path.join(ROOT, "profiles", "knn_traffic.json")
         if os.path.exists(tp):
             try:
-                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+                tj = json.load(open(tp))
+                traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("source")
             except Exception:
-                traffic = None
-        roof = {"bound": "hbm", "kernel": "k_gn_persistent / k_knn_plane (one GN pass of the kNN+plane+Jacobian+reduce+solve kernel body)", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": traffic, "peak_source": peak_src, "queries_per_launch": qpl, "candidates_per_query": cbar,
-                "algorithmic_bytes_per_launch": bytes_per_launch, "us_per_launch": t_launch * 1e6,
-                "min_bytes_per_launch": qpl * 96.0}
+                pass
+        roof = {"bound": "hbm", "kernel": "k_gn_persistent / k_knn_plane (one GN pass of the kNN+plane+Jacobian+reduce+solve kernel body)",
+                "unit": "GB/s", "peak": peak, "peak_source": peak_src, "traffic": traffic, "traffic_source": traffic_src,
+                "accounting": "achieved = SURVEY §8(d) bytes (16 + 27*8 + 16*C-bar per query, C-bar = points in the query's 27 cells, "
+                              "queries counted on the device) / CUDA-event time of one pass over the timed steps; `examined` = the same with the "
+                              "candidates the pruned search actually fetched",
+                **roof}
 
-    # ---- the same kernel where it is less latency-bound: every surf feature as a query (no scan down-sampling), a second
-    # short resident run on its own context (N = 1, rank 0, default workload only).  Informational: `roofline` above is the
-    # headline workload's; this shows how the fraction moves with the query count.  Never allowed to break the bench line.
-    if roof is not None and not multi and not args.dense_queries and not rot and not args.no_dense_probe:
+    # ---- the same kernel where it is less latency-bound (N = 1, default workload only; never allowed to break the bench line):
+    # (a) every surf feature of the 24k sweep a query (leaf_scan = 0) against the 1 M-pt map,
+    # (b) every return of a 130k-pt HDL-64E sweep a query against a 10 M-pt (HBM-resident) map, one thread per query.
+    if roof is not None and not multi and kind == "horizon" and not args.dense_queries and not args.no_dense_probe:
+        probes = {}
         try:
             dprm = L.default_params(0); dprm.leaf_scan = 0.0
             dctx = L.Context(dprm, device=local_rank)
@@ -494,50 +633,131 @@ def main():
                     dctx.odometry_resident(sw["guess"], ITERS, mode=L.MODE_GN, want_stats=False)
                     if k == 3:
                         dctx.counters(reset=True)
-            dc = dctx.counters()
+            r = roofline_from(dctx, dctx.counters(), sweeps[23 % len(sweeps)]["guess"])
             dctx.close()
-            if dc.knn_launches:
-                dq = dc.knn_queries / dc.knn_launches
-                dcb = dc.knn_candidates / max(dc.knn_queries, 1)
-                db = dq * (16 + 27 * 8 + 16 * dcb)
-                dt_l = dc.knn_ms * 1e-3 / dc.knn_launches
-                roof["dense_probe"] = {"what": "same kernel, every surf feature a query (leaf_scan = 0), 20 scans", "queries_per_launch": dq,
-                                       "candidates_per_query": dcb, "us_per_launch": dt_l * 1e6, "achieved": db / dt_l / 1e9,
-                                       "frac": db / dt_l / 1e9 / peak}
+            if r:
+                probes["surf_24k_vs_1M"] = {"what": "every surf feature of the 24k sweep a query (leaf_scan = 0), 1 M-pt map, 20 scans", **r}
         except Exception as e:      # noqa: BLE001
-            roof["dense_probe"] = {"error": str(e)[:200]}
+            probes["surf_24k_vs_1M"] = {"error": str(e)[:200]}
+        try:
+            from liliom_b200 import synth
+            big, _ = synth.make_map(10_000_000)
+            T = synth.default_true_pose()
+            hdl, _q = synth.make_hdl64_sweep(T)
+            feats = np.ones((len(hdl), 4), np.float32)
+            feats[:, 0] = hdl["x"]; feats[:, 1] = hdl["y"]; feats[:, 2] = hdl["z"]
+            bctx = L.Context(L.default_params(0), device=local_rank)
+            bctx.set_stream(stream.cuda_stream)
+            bctx.map_set_points(big)
+            del big
+            bctx.upload_feats(feats)
+            bctx.set_kernel_timing(True)
+            g = synth.perturbed_pose(T)
+            with torch.cuda.stream(stream):
+                for k in range(8):
+                    flush.fill_(k & 0xff)
+                    pz, _ = bctx.scan_to_map_resident(g, ITERS, mode=L.MODE_GN)
+                    if k == 2:
+                        bctx.counters(reset=True)
+            r = roofline_from(bctx, bctx.counters(), g)
+            bctx.close()
+            if r:
+                probes["hdl_130k_vs_10M"] = {"what": "every return of a 130k-pt HDL-64E sweep a query, 10 M-pt map (HBM-resident), 5 scans x 10 passes",
+                                             "pose_err_m": float(np.linalg.norm(pz[4:] - T[4:])), **r}
+        except Exception as e:      # noqa: BLE001
+            probes["hdl_130k_vs_10M"] = {"error": str(e)[:200]}
+        roof["dense_probe"] = probes
+
+    # ---- N > 1, sharded: the SAME workload on one GPU (rank 0, fewer steps), and the replicas number as a secondary key
+    same1, repl = None, None
+    if sharded and not args.no_extra_legs:
+        if rank == 0:
+            try:
+                c1 = new_context(False)
+                install_map(c1)
+                s1_res, _ = make_steps(c1)
+                k1 = max(3, min(steps, 20))
+                ms1, last1 = timed(s1_res, k1, 3, prep_for(c1), collective=False)
+                c1.close()
+                same1 = {"value": k1 / (ms1 * 1e-3), "unit": "scans/s", "ms_per_step": ms1 / k1, "steps": k1,
+                         "pose_max_abs_diff_vs_sharded": float(np.abs(np.asarray(last1[0]) - np.asarray(last[0])).max())
+                         if (k1 - 1) % len(sweeps) == (steps - 1) % len(sweeps) else None,
+                         "what": "the same streamed workload (full map, no sharding) on ONE GPU, measured by rank 0 in this run"}
+            except Exception as e:      # noqa: BLE001
+                same1 = {"error": str(e)[:200]}
+        barrier()
+        try:
+            from liliom_b200 import synth
+            rprm = L.default_params(0)
+            rc = L.Context(rprm, device=local_rank)
+            rc.set_stream(stream.cuda_stream)
+            m1, _ = synth.make_map(1_000_000)
+            rc.map_set_points(m1)
+            T0 = synth.default_true_pose()
+            rs = []
+            for k in range(4):
+                T = np.array(T0); T[4] += 0.7 * (k + rank); T[5] += 0.15 * (k + rank)
+                p_, q_ = synth.make_horizon_sweep(T, seed=1 + k + rank)
+                rs.append((p_, q_, synth.perturbed_pose(T)))
+
+            def rstep(k):
+                p_, q_, g_ = rs[k % len(rs)]
+                rc.extract_resident(q_)
+                return rc.odometry_resident(g_, ITERS, mode=L.MODE_GN, want_stats=False)
+
+            def rprep(k):
+                rc.upload_scan(rs[k % len(rs)][0])
+            kr = max(10, min(steps, 100))
+            msr_local, _ = timed(rstep, kr, 5, rprep)
+            msr, msr_ranks = over_ranks(msr_local)
+            rc.close()
+            repl = {"value": kr * world / (msr * 1e-3), "unit": "scans/s", "steps": kr, "ms_per_step_ranks": [x / kr for x in msr_ranks],
+                    "what": "independent scan streams, one per GPU, each the N = 1 workload (24k-pt Horizon sweep vs 1 M-pt map): weak scaling, no collective"}
+        except Exception as e:      # noqa: BLE001
+            repl = {"error": str(e)[:200]}
 
     if rank != 0:
         if multi:
             dist.destroy_process_group()
         return
-    cpu = None if args.no_cpu_baseline or multi else cpu_baseline_leg(m, sweeps[:4])
+    cpu = None if (args.no_cpu_baseline or multi) else cpu_baseline_leg(kind, m, sweeps[:4])
     pose, nq = last
+    per_rank = [x / steps for x in ms_res_ranks]
+    cfg = config_dict(kind, len(sweeps[0]["pts"]), n_map, world, args.multi)
+    run = {"queries_per_scan": int(nq), "dense_queries": bool(args.dense_queries), "map_points_installed": int(n_map_installed),
+                "exchange": (None if not sharded else "29 fp64 sums per GN iteration: " +
+                             ("ncclAllReduce + update kernel per iteration" if use_nccl_exchange else
+                              "fused into the persistent GN kernel over NVLink peer memory (one launch per scan and rank)") +
+                             "; map maintenance: one 2-scalar ncclAllReduce per rebuild (map-size guard)")}
     line = {
-        "metric": METRIC, "value": value, "unit": "scans/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": ms_res / args.steps, "higher_is_better": True,
-        "scaling": "strong" if args.multi == "sharded" else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": (workload_name(rot, len(sweeps[0]['pts']), n_map)
-                                + (", map sharded by 8 m block hash + 29-scalar NCCL all-reduce per iteration" if sharded else "")
-                                + (", independent scan stream per GPU" if (multi and not sharded) else "")),
-                   "map_points": n_map, "iters": ITERS, "queries_per_scan": int(nq), "dense_queries": bool(args.dense_queries),
-                   "l2": "256 MB buffer written between timed steps (L2 flushed); each step timed with its own CUDA-event pair on the launch stream",
-                   "multi": args.multi if multi else "single"},
+        "metric": METRIC, "value": value, "unit": "scans/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+        "ms_per_step": ms_res / steps, "higher_is_better": True,
+        "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": cfg, "run": run,
         "gpu_launches": int(cnt.launches),
         "lib_calls": int(cnt.lib_launches),
-        "e2e": {"value": e2e_val, "unit": "scans/s", "ms_per_step": ms_e2e / args.steps,
+        "e2e": {"value": e2e_val, "unit": "scans/s", "ms_per_step": ms_e2e / steps,
                 "h2d_bytes_per_step": int(last_e2e[1]), "d2h_bytes_per_step": int(last_e2e[2]),
-                "mode": ("sequential: one host thread calls the Preprocessing-node entry point then the LidarOdometry-node entry point"
-                         if (args.e2e == "sequential" or sharded) else
+                "mode": ("sequential: one host thread calls the Preprocessing-node entry point, the LidarOdometry-node entry point"
+                         + (" and the map maintenance" if stream_wl else "") + " in turn"
+                         if (args.e2e == "sequential" or sharded or stream_wl) else
                          "two-nodes: Preprocessing and LidarOdometry contexts on two host threads / CUDA streams, as the reference's two ROS "
                          "nodes; /surf_features hop through pinned host memory; one 256 MB L2-evicting write per scan on a third stream inside "
-                         "the timed region (sequential_value: one thread, flush strictly between scans)"),
-                "sequential_value": scans_total / (ms_seq * 1e-3), "sequential_ms_per_step": ms_seq / args.steps},
+                         "the timed region (sequential_value: one thread, flush strictly between scans — the like-for-like figure against "
+                         "the strictly sequential reference arm)"),
+                "sequential_value": scans_total / (ms_seq * 1e-3), "sequential_ms_per_step": ms_seq / steps},
         "clocks": clocks,
         "roofline": roof,
         "cpu_baseline": cpu,
-        "pose_err_m": float(np.linalg.norm(np.asarray(pose)[4:] - sweeps[(args.steps - 1) % len(sweeps)]["T"][4:])),
+        "pose_err_m": float(np.linalg.norm(np.asarray(pose)[4:] - sweeps[(steps - 1) % len(sweeps)]["T"][4:])),
     }
+    if multi:
+        line["ms_per_step_ranks"] = {"min": min(per_rank), "median": float(np.median(per_rank)), "max": max(per_rank), "all": per_rank}
+    if sharded:
+        line["same_workload_1gpu"] = same1
+        line["replicas"] = repl
+        if same1 and "value" in same1:
+            line["speedup_vs_1gpu_same_workload"] = value / same1["value"]
     print(json.dumps(line), flush=True)
     if multi:
         dist.destroy_process_group()

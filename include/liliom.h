@@ -123,6 +123,9 @@ int liliom_voxelgrid(liliom_ctx* c, const void* pts, int n, int stride, float le
  * n_map_out (optional) = surf_from_map_ds size. */
 int liliom_map_push_frame(liliom_ctx* c, const void* surf_ds_body, int n, const double pose7[7]);
 int liliom_map_rebuild(liliom_ctx* c, int* n_map_out);
+/* push_frame for pipelines that keep surf_last_ds on the device (both nodes in one process): d_surf_ds_body is a DEVICE
+ * pointer to n points of point_stride bytes, valid until the call returns.  Same semantics otherwise. */
+int liliom_map_push_frame_device(liliom_ctx* c, const void* d_surf_ds_body, int n, const double pose7[7]);
 int liliom_map_clear(liliom_ctx* c);
 /* Install an already down-sampled world-frame map (float4 xyz*, w ignored) — the synthetic
  * 1 M..10 M-point maps of the benchmark configs.  With a communicator (liliom_comm_init) each
@@ -253,10 +256,15 @@ typedef struct {
     unsigned long long lib_launches;  /* CUB sort/scan calls issued (library plumbing) */
     double knn_ms;                    /* sum of CUDA-event durations of the kNN+Jacobian kernel */
     unsigned long long knn_launches;  /* number of timed launches in knn_ms */
-    unsigned long long knn_queries;   /* queries processed by those launches */
-    unsigned long long knn_candidates;/* map points examined by those launches (sum of block sizes) */
+    unsigned long long knn_queries;   /* queries searched by those launches, summed over passes (counted on the device) */
+    unsigned long long knn_candidates;/* map points examined by those launches after pruning (counted on the device) */
 } liliom_counters;
 int liliom_get_counters(liliom_ctx* c, liliom_counters* out, int reset);
+/* The C-bar of the algorithmic-bytes figure (SURVEY.md §8 d: B_q = 16 + 27*8 + 16*C-bar per query and pass): for the
+ * queries resident after the last scan-to-map / odometry call, transformed by pose7, out2[0] = queries (owned by this
+ * rank when the map is sharded), out2[1] = map points in their full 3x3x3 cell blocks.  The search itself examines fewer
+ * (pruning; knn_candidates above counts those).  Not on the hot path. */
+int liliom_knn_block_stats(liliom_ctx* c, const double pose7[7], unsigned long long out2[2]);
 /* 1: bracket every kNN+Jacobian launch with CUDA events on the context stream (default 0). */
 int liliom_set_kernel_timing(liliom_ctx* c, int on);
 /* Run all library work on a caller-owned CUDA stream (cudaStream_t passed as void*; NULL restores the

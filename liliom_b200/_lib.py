@@ -60,6 +60,7 @@ EXPORTS = [
     "liliom_map_set_cloud", "liliom_correspond_surf_refl",
     "liliom_backend_edge_block", "liliom_backend_surf_block", "liliom_convert_livox", "liliom_extract_horizon_livox",
     "liliom_pc2_layout", "liliom_comm_peer_export", "liliom_comm_peer_attach",
+    "liliom_map_push_frame_device", "liliom_knn_block_stats",
 ]
 NODE_EXPORTS = ["liliom_pre_create", "liliom_pre_destroy", "liliom_pre_imu", "liliom_pre_cloud",
                 "liliom_lo_create", "liliom_lo_destroy", "liliom_lo_edge", "liliom_lo_surf", "liliom_lo_full", "liliom_lo_run"]
@@ -142,6 +143,8 @@ def lib() -> C.CDLL:
     L.liliom_pc2_layout.argtypes = [C.c_int, vp, C.c_int, ip]
     L.liliom_comm_peer_export.argtypes = [vp, vp]
     L.liliom_comm_peer_attach.argtypes = [vp, vp, C.c_int, C.c_int]
+    L.liliom_map_push_frame_device.argtypes = [vp, vp, C.c_int, dp]
+    L.liliom_knn_block_stats.argtypes = [vp, dp, C.POINTER(C.c_ulonglong)]
     L.liliom_pre_create.argtypes = [vp, C.c_int, dp]; L.liliom_pre_create.restype = vp
     L.liliom_pre_destroy.argtypes = [vp]; L.liliom_pre_destroy.restype = None
     L.liliom_pre_imu.argtypes = [vp, C.c_double, dp]; L.liliom_pre_imu.restype = None
@@ -254,6 +257,11 @@ class Context:
         pts = np.ascontiguousarray(pts, dtype=self.dtype)
         p = np.asarray(pose7, dtype=np.float64)
         self._check(lib().liliom_map_push_frame(self._h, _ptr(pts), len(pts), _dptr(p)))
+
+    def map_push_frame_device(self, dev_ptr: int, n: int, pose7):
+        """push_frame from a DEVICE buffer of n points (point_stride bytes each), e.g. a torch CUDA tensor's data_ptr()."""
+        p = np.asarray(pose7, dtype=np.float64)
+        self._check(lib().liliom_map_push_frame_device(self._h, C.c_void_p(dev_ptr), n, _dptr(p)))
 
     def map_rebuild(self) -> int:
         m = C.c_int()
@@ -436,6 +444,13 @@ class Context:
         c = Counters()
         self._check(lib().liliom_get_counters(self._h, C.byref(c), 1 if reset else 0))
         return c
+
+    def knn_block_stats(self, pose7):
+        """(queries, points in their full 27-cell blocks) for the resident queries at pose7: the C-bar of SURVEY.md §8(d)."""
+        p = np.asarray(pose7, dtype=np.float64)
+        out = (C.c_ulonglong * 2)()
+        self._check(lib().liliom_knn_block_stats(self._h, _dptr(p), out))
+        return int(out[0]), int(out[1])
 
     def set_kernel_timing(self, on: bool):
         self._check(lib().liliom_set_kernel_timing(self._h, 1 if on else 0))

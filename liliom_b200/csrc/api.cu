@@ -398,9 +398,8 @@ extern "C" int liliom_map_clear(liliom_ctx* c) {
     return LILIOM_OK;
 }
 
-extern "C" int liliom_map_push_frame(liliom_ctx* c, const void* surf_ds_body, int n, const double pose7[7]) {
-    if (!c || n < 0 || (n > 0 && !surf_ds_body) || !pose7) return LILIOM_E_ARG;
-    LILI_CUDA(c, cudaSetDevice(c->device));
+// Shared body of the two push_frame entry points: d_src = n body-frame points of point_stride bytes ON THE DEVICE.
+static int push_frame_from_device(liliom_ctx* c, const void* d_src, int n, const double pose7[7]) {
     const int stride = c->prm.point_stride;
     if ((int)c->frames.size() >= c->prm.max_map_frames && !c->frames.empty()) {      // L/src/LidarOdometry.cpp:293-296 pop_front
         c->frames.front().buf.release();
@@ -408,24 +407,25 @@ extern "C" int liliom_map_push_frame(liliom_ctx* c, const void* surf_ds_body, in
     }
     Frame f;
     f.n = n;
+    int rc = LILIOM_OK;
     if (n > 0) {
-        LILI_CUDA(c, f.buf.ensure((size_t)n * stride));
-        LILI_CUDA(c, c->raw.ensure((size_t)n * stride));
-        LILI_CUDA(c, cudaMemcpyAsync(c->raw.p, surf_ds_body, (size_t)n * stride, cudaMemcpyHostToDevice, c->stream));
         Q4 q{pose7[0], pose7[1], pose7[2], pose7[3]};
         D3 t{pose7[4], pose7[5], pose7[6]};
-        if (c->nranks == 1) {
-            k_transform_cloud<<<cdiv(n, 256), 256, 0, c->stream>>>((const unsigned char*)c->raw.p, n, stride, q, t, (unsigned char*)f.buf.p);
-            LILI_TRY(launch_check(c, "k_transform_cloud"));
-            LILI_CUDA(c, cudaStreamSynchronize(c->stream));
-        } else {
+        auto body = [&]() -> int {
+            LILI_CUDA(c, f.buf.ensure((size_t)n * stride));
+            if (c->nranks == 1) {
+                k_transform_cloud<<<cdiv(n, 256), 256, 0, c->stream>>>((const unsigned char*)d_src, n, stride, q, t, (unsigned char*)f.buf.p);
+                LILI_TRY(launch_check(c, "k_transform_cloud"));
+                LILI_CUDA(c, cudaStreamSynchronize(c->stream));
+                return LILIOM_OK;
+            }
             // sharded map maintenance: every rank receives the frame, keeps the points within (search radius + one voxel
             // diagonal) of a block it owns — every voxel that can reach an owned query's 1 m ball is then complete locally —
             // and voxel-filters / indexes only its shard.  No inter-rank traffic.
             LILI_CUDA(c, c->map_ds.ensure((size_t)n * stride));
             LILI_CUDA(c, c->flags.ensure(((size_t)n + 2) * 4));
             LILI_CUDA(c, c->idx_a.ensure(((size_t)n + 2) * 4));
-            k_transform_cloud<<<cdiv(n, 256), 256, 0, c->stream>>>((const unsigned char*)c->raw.p, n, stride, q, t, (unsigned char*)c->map_ds.p);
+            k_transform_cloud<<<cdiv(n, 256), 256, 0, c->stream>>>((const unsigned char*)d_src, n, stride, q, t, (unsigned char*)c->map_ds.p);
             LILI_TRY(launch_check(c, "k_transform_cloud"));
             float cell = 1.0f;
             while ((double)cell * (double)cell < c->prm.knn_max_sqdist) cell *= 2.0f;
@@ -436,14 +436,34 @@ extern "C" int liliom_map_push_frame(liliom_ctx* c, const void* surf_ds_body, in
             k_compact_strided<<<cdiv(n, 256), 256, 0, c->stream>>>((const unsigned char*)c->map_ds.p, c->flags.as<int>(), c->idx_a.as<int>(), n, stride,
                                                                   (unsigned char*)f.buf.p);
             LILI_TRY(launch_check(c, "k_compact_strided"));
-            int local = 0;
-            LILI_CUDA(c, cudaMemcpyAsync(&local, c->idx_a.as<int>() + n, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+            int* hp = reinterpret_cast<int*>(c->h_pin) + 1024;
+            LILI_CUDA(c, cudaMemcpyAsync(hp, c->idx_a.as<int>() + n, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
             LILI_CUDA(c, cudaStreamSynchronize(c->stream));
-            f.n = local;
-        }
+            f.n = hp[0];
+            return LILIOM_OK;
+        };
+        rc = body();
     }
+    if (rc != LILIOM_OK) { f.buf.release(); return rc; }      // no leak on the error paths (DevBuf has no destructor)
     c->frames.push_back(f);
     return LILIOM_OK;
+}
+
+extern "C" int liliom_map_push_frame(liliom_ctx* c, const void* surf_ds_body, int n, const double pose7[7]) {
+    if (!c || n < 0 || (n > 0 && !surf_ds_body) || !pose7) return LILIOM_E_ARG;
+    LILI_CUDA(c, cudaSetDevice(c->device));
+    const int stride = c->prm.point_stride;
+    if (n > 0) {
+        LILI_CUDA(c, c->raw.ensure((size_t)n * stride));
+        LILI_CUDA(c, cudaMemcpyAsync(c->raw.p, surf_ds_body, (size_t)n * stride, cudaMemcpyHostToDevice, c->stream));
+    }
+    return push_frame_from_device(c, c->raw.p, n, pose7);
+}
+
+extern "C" int liliom_map_push_frame_device(liliom_ctx* c, const void* d_surf_ds_body, int n, const double pose7[7]) {
+    if (!c || n < 0 || (n > 0 && !d_surf_ds_body) || !pose7) return LILIOM_E_ARG;
+    LILI_CUDA(c, cudaSetDevice(c->device));
+    return push_frame_from_device(c, d_surf_ds_body, n, pose7);
 }
 
 extern "C" int liliom_map_rebuild(liliom_ctx* c, int* n_map_out) {
@@ -498,16 +518,21 @@ extern "C" int liliom_map_rebuild(liliom_ctx* c, int* n_map_out) {
     LILI_TRY(repack_to_f4(c, c->map_ds.p, m, stride, c->map_xyzw.as<float4>()));
     c->map_n_global = m;
     if (c->nranks > 1) {
-        LILI_TRY(install_map_from_xyzw(c, m));          // drops the (possibly incomplete) voxels beyond the 1-cell halo
+        // Every rank ENTERS the all-reduce whatever happened locally (a rank that returned early would leave its peers waiting
+        // in the collective): the local status travels as a second scalar and all ranks fail together.
+        const int rc_local = install_map_from_xyzw(c, m);          // drops the (possibly incomplete) voxels beyond the 1-cell halo
         // the "< 10 map points" guard (L/src/LidarOdometry.cpp:485-488) is about the whole map: sum the owned-voxel counts
         LILI_CUDA(c, c->neq.ensure(32 * sizeof(double)));
-        double mine = (double)c->map_n;
-        LILI_CUDA(c, cudaMemcpyAsync(c->neq.p, &mine, sizeof(double), cudaMemcpyHostToDevice, c->stream));
-        LILI_TRY(nccl_allreduce_sum_f64(c, c->neq.as<double>(), 1));
-        double tot = 0;
-        LILI_CUDA(c, cudaMemcpyAsync(&tot, c->neq.p, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        double* pin = reinterpret_cast<double*>(c->h_pin) + 56;
+        pin[0] = rc_local == LILIOM_OK ? (double)c->map_n : 0.0;
+        pin[1] = rc_local == LILIOM_OK ? 0.0 : 1.0;
+        LILI_CUDA(c, cudaMemcpyAsync(c->neq.p, pin, 2 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        LILI_TRY(nccl_allreduce_sum_f64(c, c->neq.as<double>(), 2));
+        LILI_CUDA(c, cudaMemcpyAsync(pin + 2, c->neq.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
         LILI_CUDA(c, cudaStreamSynchronize(c->stream));
-        c->map_n_global = (int)tot;                     // halo voxels are counted on several ranks: an upper bound >= the true size
+        if (rc_local != LILIOM_OK) return rc_local;
+        if (pin[3] != 0.0) { c->map_ready = false; c->last_error = "liliom_map_rebuild failed on another rank"; return LILIOM_E_NCCL; }
+        c->map_n_global = (int)pin[2];                  // halo voxels are counted on several ranks: an upper bound >= the true size
     } else LILI_TRY(grid_build(c, m));
     LILI_CUDA(c, cudaStreamSynchronize(c->stream));
     if (n_map_out) *n_map_out = m;
@@ -771,6 +796,12 @@ extern "C" int liliom_get_counters(liliom_ctx* c, liliom_counters* out, int rese
         if (c->counter.p) LILI_CUDA(c, cudaMemsetAsync(c->counter.as<unsigned char>() + 16, 0, 16, c->stream));
     }
     return LILIOM_OK;
+}
+
+extern "C" int liliom_knn_block_stats(liliom_ctx* c, const double pose7[7], unsigned long long out2[2]) {
+    if (!c || !pose7 || !out2) return LILIOM_E_ARG;
+    LILI_CUDA(c, cudaSetDevice(c->device));
+    return block27_stats(c, pose7, out2);
 }
 
 extern "C" int liliom_set_kernel_timing(liliom_ctx* c, int on) {

@@ -917,6 +917,54 @@ __global__ void __launch_bounds__(kLmBlock) k_lm_solve(LmArgs a) {
     }
 }
 
+// ------------------------------------------------------------------ instrumentation: the C-bar of SURVEY.md §8(d)
+// Points in the full 3x3x3 cell block of every (owned) query at pose (q,t): the candidate count the algorithmic-bytes figure
+// B_q = 16 + 27*8 + 16*C-bar is defined on.  The search kernels examine fewer (pruning, knn_core.cuh) and count those
+// separately (liliom_counters::knn_candidates).  out[0] += queries, out[1] += block points.
+__global__ void k_block27_count(const float4* __restrict__ feats, int n, Q4 q, D3 t, const int* __restrict__ cell_start, GridDesc g,
+                                int nranks, int rank, float inv_block, unsigned long long* __restrict__ out) {
+    unsigned long long cnt = 0, nq = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4 f = feats[i];
+        const D3 pw = qrot_x(q, D3{(double)f.x, (double)f.y, (double)f.z});
+        const float sx = (float)addx(pw.x, t.x), sy = (float)addx(pw.y, t.y), sz = (float)addx(pw.z, t.z);
+        if (nranks > 1 && owner_of(sx, sy, sz, nranks, inv_block) != rank) continue;
+        ++nq;
+        const int cx = cell_coord(sx, g.inv_cell) - g.org[0], cy = cell_coord(sy, g.inv_cell) - g.org[1], cz = cell_coord(sz, g.inv_cell) - g.org[2];
+        const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.dim[0] - 1);
+        if (x0 > x1) continue;
+        for (int row = 0; row < 9; ++row) {
+            const int y = cy + (row % 3) - 1, z = cz + (row / 3) - 1;
+            if (y < 0 || y >= g.dim[1] || z < 0 || z >= g.dim[2]) continue;
+            const int base = (z * g.dim[1] + y) * g.dim[0];
+            cnt += (unsigned long long)(__ldg(cell_start + base + x1 + 1) - __ldg(cell_start + base + x0));
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { cnt += __shfl_xor_sync(0xffffffffu, cnt, o); nq += __shfl_xor_sync(0xffffffffu, nq, o); }
+    if ((threadIdx.x & 31) == 0) { if (nq) atomicAdd(out, nq); if (cnt) atomicAdd(out + 1, cnt); }
+}
+
+int block27_stats(liliom_ctx* c, const double pose7[7], unsigned long long out[2]) {
+    out[0] = out[1] = 0;
+    if (!c->map_ready) return LILIOM_E_NOMAP;
+    const int n = c->n_feats_actual;
+    if (n <= 0) return LILIOM_OK;
+    LILI_CUDA(c, c->lm_state.ensure(64 * sizeof(long long)));
+    unsigned long long* d = c->lm_state.as<unsigned long long>();
+    LILI_CUDA(c, cudaMemsetAsync(d, 0, 16, c->stream));
+    const Q4 q{pose7[0], pose7[1], pose7[2], pose7[3]};
+    const D3 t{pose7[4], pose7[5], pose7[6]};
+    k_block27_count<<<min(cdiv(n, 256), c->sm_count * 4), 256, 0, c->stream>>>(c->feats.as<float4>(), n, q, t, c->cell_start.as<int>(), c->grid,
+                                                                              c->nranks, c->rank, c->shard_inv_block, d);
+    LILI_TRY(launch_check(c, "k_block27_count"));
+    unsigned long long* hp = reinterpret_cast<unsigned long long*>(c->h_pin) + 56;
+    LILI_CUDA(c, cudaMemcpyAsync(hp, d, 16, cudaMemcpyDeviceToHost, c->stream));
+    LILI_CUDA(c, cudaStreamSynchronize(c->stream));
+    out[0] = hp[0]; out[1] = hp[1];
+    return LILIOM_OK;
+}
+
 // ------------------------------------------------------------------ host orchestration
 typedef int (*nccl_allreduce_fn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
 int nccl_allreduce_sum_f64(liliom_ctx* c, double* buf, int count);   // comm.cu
