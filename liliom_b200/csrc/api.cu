@@ -204,6 +204,7 @@ extern "C" int liliom_create(liliom_ctx** out, const liliom_params* p, int devic
     c->dbg_timing = getenv("LILIOM_DEBUG_TIMING") != nullptr;
     if (const char* e9 = getenv("LILIOM_MAP_COOP")) c->map_coop = atoi(e9) != 0;
     if (const char* e7 = getenv("LILIOM_FAST_IO")) c->fast_io = atoi(e7) != 0;
+    if (const char* e6 = getenv("LILIOM_GN_GRID")) c->gn_full_grid = strcmp(e6, "full") == 0;
     if (const char* e5 = getenv("LILIOM_GN_SYNC")) { int v = atoi(e5); if (v == 0 || v == 1 || v == 3) c->gn_sync = v; }
     if (const char* e4 = getenv("LILIOM_SHARD_BLOCK")) {      // shard block edge in metres (power of two, 8..256): larger blocks = thinner halos
         int v = atoi(e4);

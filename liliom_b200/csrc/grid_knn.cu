@@ -1008,6 +1008,10 @@ int s2m_run(liliom_ctx* c, double pose7[7], int match_cnt, int max_num_iter, int
         if (grid2 <= c->sm_count) { rounds = 2; per_task *= 2; ntasks = ntasks2; grid = grid2; }
     }
 
+    // tuning (LILIOM_GN_GRID=full): spread a small scan's warp tasks over ALL SMs instead of filling 8-warp blocks — fewer warps
+    // per SM share the issue slots and the L1, at the price of more barrier participants
+    if (c->gn_full_grid && lanes >= 8 && grid < c->sm_count && mode == LILIOM_MODE_GN && !want_corr) grid = c->sm_count;
+
     LILI_CUDA(c, c->pose_dev.ensure(16 * sizeof(double)));
     LILI_CUDA(c, c->partials.ensure((size_t)2 * grid * kNormEq * sizeof(double)));   // two buffers (persistent kernel alternates)
     LILI_CUDA(c, c->neq.ensure(32 * sizeof(double)));
