@@ -101,7 +101,7 @@ class ClockSampler:
                     self.rows.append([x.strip() for x in out.split(",")])
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._stop.wait(0.02)
 
     def __enter__(self):
         if self.enabled:
@@ -560,6 +560,8 @@ def main():
     with ClockSampler(local_rank, enabled=(rank == 0)) as clk:
         ms_res_local, last = timed(step_resident, steps, warmup, prep_for(ctx), after_warmup=lambda: ctx.counters(reset=True))
         cnt = ctx.counters(reset=True)
+        # C-bar of the LAST timed scan's queries at its start pose, while they are still resident (the later legs replace them)
+        blk = ctx.knn_block_stats(sweeps[(steps - 1) % len(sweeps)]["guess"])
         ms_res, ms_res_ranks = over_ranks(ms_res_local)
         # ---- timed region 2: end to end with host buffers
         ms_seq_local, last_seq = timed(step_e2e, steps, warmup)
@@ -580,10 +582,10 @@ def main():
     # ---- roofline of the kNN+Jacobian kernel (algorithmic bytes per SURVEY.md §8 d)
     peak, peak_src = measured_peak()
 
-    def roofline_from(cx, cn, pose_for_stats):
+    def roofline_from(cn, blk27):
         if not cn.knn_launches:
             return None
-        nq, c27 = cx.knn_block_stats(pose_for_stats)          # resident queries of the last scan, at its start pose
+        nq, c27 = blk27                                       # resident queries of the last scan, at its start pose
         cbar27 = c27 / max(nq, 1)
         qpl = cn.knn_queries / cn.knn_launches                # device-side count: queries searched per pass
         cex = cn.knn_candidates / max(cn.knn_queries, 1)      # candidates examined per query after pruning
@@ -596,7 +598,7 @@ def main():
                 "examined": {"bytes_per_launch": bex, "achieved": bex / t_launch / 1e9, "frac": bex / t_launch / 1e9 / peak},
                 "min_bytes_per_launch": qpl * 96.0, "passes_timed": int(cn.knn_launches)}
 
-    roof = roofline_from(ctx, cnt, sweeps[(steps - 1) % len(sweeps)]["guess"])
+    roof = roofline_from(cnt, blk)
     if roof is not None:
         traffic, traffic_src = None, None
         tp = os.path.join(ROOT, "profiles", "knn_traffic.json")
@@ -633,7 +635,7 @@ def main():
                     dctx.odometry_resident(sw["guess"], ITERS, mode=L.MODE_GN, want_stats=False)
                     if k == 3:
                         dctx.counters(reset=True)
-            r = roofline_from(dctx, dctx.counters(), sweeps[23 % len(sweeps)]["guess"])
+            r = roofline_from(dctx.counters(), dctx.knn_block_stats(sweeps[23 % len(sweeps)]["guess"]))
             dctx.close()
             if r:
                 probes["surf_24k_vs_1M"] = {"what": "every surf feature of the 24k sweep a query (leaf_scan = 0), 1 M-pt map, 20 scans", **r}
@@ -659,7 +661,7 @@ def main():
                     pz, _ = bctx.scan_to_map_resident(g, ITERS, mode=L.MODE_GN)
                     if k == 2:
                         bctx.counters(reset=True)
-            r = roofline_from(bctx, bctx.counters(), g)
+            r = roofline_from(bctx.counters(), bctx.knn_block_stats(g))
             bctx.close()
             if r:
                 probes["hdl_130k_vs_10M"] = {"what": "every return of a 130k-pt HDL-64E sweep a query, 10 M-pt map (HBM-resident), 5 scans x 10 passes",

@@ -79,3 +79,60 @@ def test_shard_rule_properties():
         q = p[:500] + rng.uniform(-0.9, 0.9, (500, 3)).astype(np.float32) / np.sqrt(3)
         qo = sharding.owner_of(q, world)
         assert masks[qo, np.arange(500)].all()
+
+
+def _maint_worker(rank, world, port, out):
+    """Sharded map maintenance (api.cu push_frame_from_device / liliom_map_rebuild with a communicator), restated on the host:
+    a rank keeps the frame points within (1 m + one voxel diagonal) of a block it owns, voxel-filters its shard alone, and
+    keeps the voxels within 1 m of an owned block."""
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import oracle_lib as O
+    import bench
+    from liliom_b200 import sharding, synth
+    m, _ = synth.make_map(40000)
+    frames = bench.make_frames(m, O.PT32)
+    leaf = 0.4
+    halo_f = np.float32(1.0 + 1.7320508 * leaf + 0.05)
+    mine = []
+    for f in frames:
+        xyz = np.stack([f["x"], f["y"], f["z"]], 1)
+        mine.append(f[sharding.shard_mask(xyz, world, rank, halo=float(halo_f))])
+    ds = O.voxelgrid(np.concatenate(mine), leaf)
+    xyz = np.stack([ds["x"], ds["y"], ds["z"]], 1)
+    ds = ds[sharding.shard_mask(xyz, world, rank, halo=1.0)]
+    rows = np.stack([ds["x"], ds["y"], ds["z"]], 1).view(np.uint32)
+    n = torch.tensor([len(rows)], dtype=torch.int64)
+    sizes = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(sizes, n)
+    np.save(f"{out}.{rank}.npy", rows)
+    dist.barrier()
+    if rank == 0:
+        full = O.voxelgrid(np.concatenate(frames), leaf)
+        fx = np.stack([full["x"], full["y"], full["z"]], 1)
+        np.save(out, np.concatenate([[len(m), sum(len(f) for f in frames), len(full)], [int(s.item()) for s in sizes]]))
+        np.save(out + ".full.npy", fx)
+    dist.destroy_process_group()
+
+
+def test_sharded_map_maintenance_equals_full_filter(tmp_path):
+    sys.path.insert(0, ROOT)
+    from liliom_b200 import sharding
+    world = 2
+    out = str(tmp_path / "maint.npy")
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_maint_worker, args=(world, port, out), nprocs=world, join=True)
+    head = np.load(out)
+    n_map, n_frames_pts, n_full = int(head[0]), int(head[1]), int(head[2])
+    assert n_frames_pts == n_map                                   # the frames partition the map
+    assert n_full > 0.95 * n_map
+    full = np.load(out + ".full.npy")
+    full_rows = {r.tobytes() for r in full.view(np.uint32)}
+    for rank in range(world):
+        rows = np.load(f"{out}.{rank}.npy")
+        got = {r.tobytes() for r in rows}
+        assert got <= full_rows                                    # a shard never invents or alters a voxel centroid
+        need = full[sharding.shard_mask(full, world, rank, halo=1.0)]
+        assert {r.tobytes() for r in need.view(np.uint32)} == got  # and holds exactly the voxels its queries can reach
+        assert len(got) < n_full
