@@ -353,18 +353,33 @@ def main():
         run_reference(args)
         return
     import torch
-    import liliom_b200 as L
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU oracle")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    note = None
+    while True:
+        again = bench_body(args, note)
+        if again is None:
+            break
+        args.multi, args.workload, note = "replicas", "", again      # the sharded path failed its pre-flight on some rank: report replicas, say why
+    if world > 1:
+        dist.destroy_process_group()
 
+
+def bench_body(args, fallback_note=None):
+    import torch
+    import liliom_b200 as L
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     multi = world > 1
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU oracle")
-    torch.cuda.set_device(local_rank)
     if multi:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     sharded = multi and args.multi == "sharded"
     kind, n_map = resolve_workload(args, world)
     stream_wl = kind == "stream"
@@ -416,8 +431,54 @@ def main():
         cx.map_set_points(m)
         return len(m)
 
-    ctx = new_context(sharded)
-    n_map_installed = install_map(ctx)
+    def preflight(cx):
+        """Two scans of the sharded step before anything is timed (first call: per-iteration launches, second: the single
+        persistent launch): every rank must come back with a finite pose, and all ranks with the same one."""
+        ok, why = 1, ""
+        try:
+            sw = sweeps[0]
+            for _ in range(2):
+                cx.upload_scan(sw["pts"])
+                cx.extract_resident(sw["q"])
+                pose, _, _ = cx.odometry_resident(sw["guess"], ITERS, mode=L.MODE_GN, want_stats=False)
+            if not np.all(np.isfinite(pose)):
+                ok, why = 0, "non-finite pose"
+        except Exception as e:      # noqa: BLE001
+            ok, why, pose = 0, str(e)[:160], np.zeros(7)
+        t = torch.tensor([float(ok)] + [float(x) if np.isfinite(x) else 0.0 for x in pose], dtype=torch.float64, device="cuda")
+        lo, hi = t.clone(), t.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        if float(lo[0].item()) < 1.0:
+            return False, why or "another rank failed"
+        if float((hi[1:] - lo[1:]).abs().max().item()) != 0.0:
+            return False, "ranks disagree on the pose"
+        return True, ""
+
+    exchange_note = None
+    if sharded:
+        ctx, good = None, False
+        for mode in (["nccl"] if use_nccl_exchange else ["peer", "nccl"]):
+            use_nccl_exchange = mode == "nccl"
+            try:
+                ctx = new_context(True)
+                n_map_installed = install_map(ctx)
+                good, why = preflight(ctx)
+            except Exception as e:      # noqa: BLE001
+                good, why = False, str(e)[:160]
+            if good:
+                break
+            exchange_note = f"{mode} exchange failed its pre-flight ({why})"
+            if ctx is not None:
+                try:
+                    ctx.close()
+                except Exception:      # noqa: BLE001
+                    pass
+                ctx = None
+        if not good:
+            return "sharded path failed its pre-flight on this box (" + (exchange_note or "") + "); replicas reported instead"
+    else:
+        ctx = new_context(False)
+        n_map_installed = install_map(ctx)
     ctx.set_kernel_timing(True)
 
     # pinned host buffers for the e2e leg (the contract: inputs come from pinned host memory)
@@ -719,9 +780,8 @@ def main():
             repl = {"error": str(e)[:200]}
 
     if rank != 0:
-        if multi:
-            dist.destroy_process_group()
-        return
+        ctx.close()
+        return None
     cpu = None if (args.no_cpu_baseline or multi) else cpu_baseline_leg(kind, m, sweeps[:4])
     pose, nq = last
     per_rank = [x / steps for x in ms_res_ranks]
@@ -760,9 +820,11 @@ def main():
         line["replicas"] = repl
         if same1 and "value" in same1:
             line["speedup_vs_1gpu_same_workload"] = value / same1["value"]
+    if fallback_note or exchange_note:
+        line["note"] = "; ".join(x for x in (fallback_note, exchange_note) if x)
     print(json.dumps(line), flush=True)
-    if multi:
-        dist.destroy_process_group()
+    ctx.close()
+    return None
 
 
 if __name__ == "__main__":

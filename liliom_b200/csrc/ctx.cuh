@@ -157,9 +157,6 @@ struct liliom_ctx {
     bool map_coop = false;               // LILIOM_MAP_COOP=1: liliom_map_rebuild voxel-filters the 20-frame map with the cooperative single-launch filter
     bool dbg_timing = false;             // LILIOM_DEBUG_TIMING at create: stage clocks of the cooperative kernels, printed by s2m_run
     bool knn1_smem_set = false;          // dynamic shared memory limit raised for the one-thread-per-query kernels on this device
-    bool gn_full_grid = false;           // LILIOM_GN_GRID=full (tuning)
-    bool fast_io = false;                // LILIOM_FAST_IO=1: pose in the launch parameters, one read-back block (opt-in until measured)
-    lili::DevBuf result_dev;             // {pose7 | n_feats | VgParams} written by block 0 of the persistent kernel
     std::vector<cudaEvent_t> ev_pool;
     size_t ev_used = 0;
     std::vector<std::pair<size_t, unsigned long long>> ev_pending;  // (event pair index, queries)

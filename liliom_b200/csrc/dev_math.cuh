@@ -439,6 +439,10 @@ __device__ __forceinline__ bool solve6_ldlt(const double* s21, const double* rhs
     return ok;
 }
 
+static __device__ __noinline__ bool solve6_ldlt_damped(const double* s21, const double* rhs, double x[6], double lambda) {
+    return solve6_ldlt(s21, rhs, x, lambda, 0.0);
+}
+
 // Gauss-Newton step of LILIOM_MODE_GN with the two safeguards an undamped step lacks (the reference's own solver is
 // Ceres' trust-region LM, L/src/LidarOdometry.cpp:527-537 = LILIOM_MODE_CERES):
 //   (1) conditioning: when a pivot of H = J^T J falls below 1e-10 * max diag(H) the scan does not constrain some direction
@@ -450,16 +454,16 @@ constexpr double kGnPivotRel = 1e-10, kGnDampRel = 1e-6, kGnMaxRot = 0.35, kGnMa
 __device__ __forceinline__ bool gn_safe_step(const double* s21, const double* rhs, double d[6]) {
     const double maxd = fmax(fmax(fmax(s21[0], s21[6]), fmax(s21[11], s21[15])), fmax(s21[18], s21[20]));
     if (!(maxd > 0.0) || !isfinite(maxd)) return false;
-    bool ok = false;
-#pragma unroll 1
-    for (int attempt = 0; attempt < 2 && !ok; ++attempt)
-        ok = solve6_ldlt(s21, rhs, d, attempt == 0 ? 0.0 : kGnDampRel * maxd, attempt == 0 ? kGnPivotRel * maxd : 0.0);
+    bool ok = solve6_ldlt(s21, rhs, d, 0.0, kGnPivotRel * maxd);
+    if (!ok) ok = solve6_ldlt_damped(s21, rhs, d, kGnDampRel * maxd);      // cold path, not inlined
     if (!ok) return false;
-    const double rot = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]), tr = sqrt(d[3] * d[3] + d[4] * d[4] + d[5] * d[5]);
-    double sc = 1.0;
-    if (rot > kGnMaxRot) sc = kGnMaxRot / rot;
-    if (tr * sc > kGnMaxTrans) sc = kGnMaxTrans / tr;
-    if (sc < 1.0) {
+    // (this runs on ONE thread at the tail of every GN pass: the common case must stay two multiply-add chains and two compares)
+    const double rot2 = d[0] * d[0] + d[1] * d[1] + d[2] * d[2], tr2 = d[3] * d[3] + d[4] * d[4] + d[5] * d[5];
+    if (rot2 > kGnMaxRot * kGnMaxRot || tr2 > kGnMaxTrans * kGnMaxTrans) {
+        const double rot = sqrt(rot2), tr = sqrt(tr2);
+        double sc = 1.0;
+        if (rot > kGnMaxRot) sc = kGnMaxRot / rot;
+        if (tr * sc > kGnMaxTrans) sc = kGnMaxTrans / tr;
 #pragma unroll
         for (int k = 0; k < 6; ++k) d[k] *= sc;
     }

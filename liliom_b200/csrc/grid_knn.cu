@@ -187,8 +187,6 @@ struct KnnArgs {
     float tau0;                         // largest fp32 distance inside the gate (knn_gate_tau(max_sqd)): search pruning threshold
     float inv_block;                    // 1 / shard block edge (multi-GPU ownership)
     unsigned long long* queries_total;  // instrumentation: queries processed (device-side count), one add per pass
-    double pose0[7]; int pose_by_value; // persistent kernel, LILIOM_FAST_IO: the start pose travels in the launch parameters (no H2D copy)
-    double* result; const VgParams* vgp; // ... and block 0 leaves {pose7 | n_feats | VgParams} in one block for a single D2H copy
 };
 
 // per-thread instrumentation word: examined candidates in the low 40 bits, searched queries above (summed per block)
@@ -239,8 +237,9 @@ template <int LANES>
 __device__ __forceinline__ void knn_phases(const KnnArgs& a, const Q4& q, const D3& t, const int n_q, KnnSmem& S,
                                            double& acc, unsigned long long& cand, const float4* fpre = nullptr) {
     constexpr int GROUPS = 32 / LANES;                 // queries a warp searches concurrently
-    extern __shared__ __align__(16) unsigned char dyn_smem[];      // LANES == 1: [kRunCap][kBlock] int4 run lists (thread_knn5)
+    extern __shared__ __align__(16) unsigned char dyn_smem[];      // LANES == 1: [kRunCap][kBlock] int4 run lists | [kPendCap][kBlock] u64 (thread_knn5)
     int4* runs = reinterpret_cast<int4*>(dyn_smem) + threadIdx.x;
+    u64* pend = reinterpret_cast<u64*>(dyn_smem + (size_t)kRunCap * kBlock * sizeof(int4)) + threadIdx.x;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int sub = lane & (LANES - 1);
@@ -278,7 +277,7 @@ __device__ __forceinline__ void knn_phases(const KnnArgs& a, const Q4& q, const 
             LILI_STAMP(8);
             if (live) {
                 if (sub == 0) cand += 1ull << kCandBits;
-                if constexpr (LANES == 1) thread_knn5(sx, sy, sz, a.map, a.cell_start, a.g, a.tau0, runs, kBlock, top, cand);
+                if constexpr (LANES == 1) thread_knn5(sx, sy, sz, a.map, a.cell_start, a.g, a.tau0, runs, pend, kBlock, top, cand);
                 else group_knn5<LANES>(sx, sy, sz, a.map, a.cell_start, a.g, sub, gmask, a.tau0, top, cand, (a.dbg && blockIdx.x == 0 && threadIdx.x == 0) ? a.dbg : nullptr);
             }
             LILI_STAMP(11);
@@ -366,15 +365,21 @@ __device__ __forceinline__ void knn_phases(const KnnArgs& a, const Q4& q, const 
         __syncwarp();
         LILI_STAMP(2);
         // ---------------- phase C: lane k accumulates scalar k over the task's rows (fixed slot order)
+        // (four interleaved partial sums, folded in a fixed order: a 32-row task is a chain of 8 dependent fp64 adds instead of 32)
         if (lane < kNormEq) {
+            double p4[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll 1
-            for (int sl = 0; sl < per_task; ++sl) {
-                if (!S.rvalid[warp][sl]) continue;
-                const double* R = reinterpret_cast<const double*>(&S.rows[warp][sl]);
-                if (lane < 27) acc += R[pa] * R[pb];
-                else if (lane == 27) acc += R[7];
-                else acc += 1.0;
+            for (int s0 = 0; s0 < per_task; s0 += 4) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int sl = s0 + u;
+                    if (sl < per_task && S.rvalid[warp][sl]) {
+                        const double* R = reinterpret_cast<const double*>(&S.rows[warp][sl]);
+                        p4[u] += lane < 27 ? R[pa] * R[pb] : lane == 27 ? R[7] : 1.0;
+                    }
+                }
             }
+            acc += (p4[0] + p4[1]) + (p4[2] + p4[3]);
         }
         __syncwarp();
     }
@@ -583,12 +588,7 @@ __global__ void LILI_GN_BOUNDS k_gn_persistent(KnnArgs a, int iters, unsigned in
     __shared__ __align__(16) KnnSmem S;
     const int n_q = a.n_dev ? min(*a.n_dev, a.n) : a.n;
     if (threadIdx.x == 32) S.peer_lost = 0;
-    if (threadIdx.x < 7) {
-        // static indices only: a dynamically indexed kernel parameter would be copied to local memory as a whole
-        const int k = threadIdx.x;
-        const double byval = k == 0 ? a.pose0[0] : k == 1 ? a.pose0[1] : k == 2 ? a.pose0[2] : k == 3 ? a.pose0[3] : k == 4 ? a.pose0[4] : k == 5 ? a.pose0[5] : a.pose0[6];
-        S.pose[k] = a.pose_by_value ? byval : a.pose[k];
-    }
+    if (threadIdx.x < 7) S.pose[threadIdx.x] = a.pose[threadIdx.x];
     __syncthreads();
     const unsigned int G = gridDim.x;
     // bar_base = arrivals of all previous launches on this context (tracked by the host, advanced by iters*G per launch)
@@ -683,16 +683,6 @@ __global__ void LILI_GN_BOUNDS k_gn_persistent(KnnArgs a, int iters, unsigned in
         // the partials of this iteration may only be overwritten after every block has summed them: the next
         // barrier is behind the next write, so alternate between two partial buffers
         a.partials = (it & 1) ? a.partials - (size_t)kNormEq * G : a.partials + (size_t)kNormEq * G;
-    }
-    if (a.result && blockIdx.x == 0 && threadIdx.x == 0) {      // same layout as the pinned read-back block of s2m_run
-#pragma unroll
-        for (int k = 0; k < 7; ++k) a.result[k] = S.pose[k];
-        *reinterpret_cast<int*>(a.result + 40) = n_q;
-        if (a.vgp) {
-            const int* src = reinterpret_cast<const int*>(a.vgp);
-            int* dst = reinterpret_cast<int*>(a.result + 48);
-            for (int k = 0; k < (int)(sizeof(VgParams) / sizeof(int)); ++k) dst[k] = __ldcg(src + k);
-        }
     }
 }
 
@@ -1008,10 +998,6 @@ int s2m_run(liliom_ctx* c, double pose7[7], int match_cnt, int max_num_iter, int
         if (grid2 <= c->sm_count) { rounds = 2; per_task *= 2; ntasks = ntasks2; grid = grid2; }
     }
 
-    // tuning (LILIOM_GN_GRID=full): spread a small scan's warp tasks over ALL SMs instead of filling 8-warp blocks — fewer warps
-    // per SM share the issue slots and the L1, at the price of more barrier participants
-    if (c->gn_full_grid && lanes >= 8 && grid < c->sm_count && mode == LILIOM_MODE_GN && !want_corr) grid = c->sm_count;
-
     LILI_CUDA(c, c->pose_dev.ensure(16 * sizeof(double)));
     LILI_CUDA(c, c->partials.ensure((size_t)2 * grid * kNormEq * sizeof(double)));   // two buffers (persistent kernel alternates)
     LILI_CUDA(c, c->neq.ensure(32 * sizeof(double)));
@@ -1056,7 +1042,7 @@ int s2m_run(liliom_ctx* c, double pose7[7], int match_cnt, int max_num_iter, int
     }
 
     // one thread per query: per-thread run lists in dynamic shared memory (thread_knn5); static + dynamic exceed 48 KB
-    const size_t dyn_smem = lanes == 1 ? (size_t)kRunCap * kBlock * sizeof(int4) : 0;
+    const size_t dyn_smem = lanes == 1 ? (size_t)kRunCap * kBlock * sizeof(int4) + (size_t)kPendCap * kBlock * sizeof(u64) : 0;
     if (lanes == 1 && !c->knn1_smem_set) {
         LILI_CUDA(c, cudaFuncSetAttribute((const void*)k_knn_plane<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
         LILI_CUDA(c, cudaFuncSetAttribute((const void*)k_gn_persistent<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
@@ -1066,22 +1052,11 @@ int s2m_run(liliom_ctx* c, double pose7[7], int match_cnt, int max_num_iter, int
     const bool peer = c->peer_ready && c->peer_ptrs[c->rank] != nullptr;       // fused exchange instead of ncclAllReduce + k_gn_update
     const bool persistent = mode == LILIOM_MODE_GN && (c->nranks == 1 || peer) && iters > 0 && !want_corr &&
                             !getenv("LILIOM_NO_PERSISTENT") && grid <= c->sm_count;
-    // LILIOM_FAST_IO=1 (opt-in until measured): the persistent launch carries the start pose in its parameters and leaves
-    // pose, query count and VoxelGrid verdict in one device block, so the call needs no H2D copy and one D2H copy of 432 B
-    // instead of three small ones (each a separate ~2 us DMA on the critical path of a ~220 us scan).
-    const bool fast_io = persistent && c->fast_io;
-    if (!fast_io) {
+    {
         double p8[8] = {pose7[0], pose7[1], pose7[2], pose7[3], pose7[4], pose7[5], pose7[6], 0.0};      // [7]: peer-loss flag, cleared
         double* pin = reinterpret_cast<double*>(c->h_pin) + 56;      // pinned staging (slots 56..63 of the small block; results land in 0..55)
         memcpy(pin, p8, sizeof(p8));
         LILI_CUDA(c, cudaMemcpyAsync(c->pose_dev.p, pin, 8 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    }
-    if (fast_io) {
-        LILI_CUDA(c, c->result_dev.ensure(64 * sizeof(double)));
-        for (int k = 0; k < 7; ++k) a.pose0[k] = pose7[k];
-        a.pose_by_value = 1;
-        a.result = c->result_dev.as<double>();
-        a.vgp = c->vg_check ? c->vg_params.as<VgParams>() : nullptr;
     }
     if (persistent) {
         a.update_pose = 1;
@@ -1171,14 +1146,10 @@ int s2m_run(liliom_ctx* c, double pose7[7], int match_cnt, int max_num_iter, int
     }
     // ---- results: pose + stats in one pinned block
     double* hp = reinterpret_cast<double*>(c->h_pin);
-    if (fast_io) {
-        LILI_CUDA(c, cudaMemcpyAsync(hp, c->result_dev.p, 48 * sizeof(double) + sizeof(VgParams), cudaMemcpyDeviceToHost, c->stream));
-    } else {
-        LILI_CUDA(c, cudaMemcpyAsync(hp, c->pose_dev.p, 8 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));     // pose + peer-loss flag
-        if (out29) LILI_CUDA(c, cudaMemcpyAsync(hp + 8, c->neq.p, kNormEq * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-        if (c->d_nfeats) LILI_CUDA(c, cudaMemcpyAsync(hp + 40, c->d_nfeats, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-        if (c->vg_check) LILI_CUDA(c, cudaMemcpyAsync(hp + 48, c->vg_params.p, sizeof(VgParams), cudaMemcpyDeviceToHost, c->stream));
-    }
+    LILI_CUDA(c, cudaMemcpyAsync(hp, c->pose_dev.p, 8 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));     // pose + peer-loss flag
+    if (out29) LILI_CUDA(c, cudaMemcpyAsync(hp + 8, c->neq.p, kNormEq * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (c->d_nfeats) LILI_CUDA(c, cudaMemcpyAsync(hp + 40, c->d_nfeats, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    if (c->vg_check) LILI_CUDA(c, cudaMemcpyAsync(hp + 48, c->vg_params.p, sizeof(VgParams), cudaMemcpyDeviceToHost, c->stream));
     const bool want_stats = stats && iters > 0;
     if (want_stats) {
         size_t bytes = (size_t)iters * kStatsDoubles * sizeof(double);
@@ -1192,7 +1163,7 @@ int s2m_run(liliom_ctx* c, double pose7[7], int match_cnt, int max_num_iter, int
         c->vg_ncells = vp->overflow ? 0 : (long long)vp->div_b[0] * vp->div_b[1] * vp->div_b[2];
         c->vg_bail = vp->bail != 0;
     }
-    if (iters > 0 && peer && !fast_io && hp[7] != 0.0) {
+    if (iters > 0 && peer && hp[7] != 0.0) {
         c->last_error = "fused exchange: a peer rank did not publish its sums within the wait bound (collective call not entered on every rank?)";
         return LILIOM_E_NCCL;
     }

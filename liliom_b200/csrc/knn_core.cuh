@@ -98,10 +98,10 @@ __device__ __forceinline__ void consider(float sx, float sy, float sz, const flo
     }
 }
 
-// The query's cell and the distances to its six faces (>= 0; 0 is always a valid lower bound).
+// The query's cell and the SQUARED distances to its six faces (>= 0; 0 is always a valid lower bound).
 struct QCell {
     int cx, cy, cz;                     // grid-relative cell coordinates (may lie outside the grid)
-    float xl, xh, yl, yh, zl, zh;       // sx - lo_x, hi_x - sx, ...
+    float xl, xh, yl, yh, zl, zh;       // (sx - lo_x)^2, (hi_x - sx)^2, ... each rounded once, like a candidate's dx*dx
 };
 __device__ __forceinline__ QCell query_cell(float sx, float sy, float sz, const GridDesc& g) {
     QCell q;
@@ -109,17 +109,19 @@ __device__ __forceinline__ QCell query_cell(float sx, float sy, float sz, const 
     const float fx = floorf(sx * g.inv_cell), fy = floorf(sy * g.inv_cell), fz = floorf(sz * g.inv_cell);
     q.cx = (int)fx - g.org[0]; q.cy = (int)fy - g.org[1]; q.cz = (int)fz - g.org[2];
     const float lx = fx * cell, ly = fy * cell, lz = fz * cell;
-    q.xl = fmaxf(fsubx(sx, lx), 0.f); q.xh = fmaxf(fsubx(faddx(lx, cell), sx), 0.f);
-    q.yl = fmaxf(fsubx(sy, ly), 0.f); q.yh = fmaxf(fsubx(faddx(ly, cell), sy), 0.f);
-    q.zl = fmaxf(fsubx(sz, lz), 0.f); q.zh = fmaxf(fsubx(faddx(lz, cell), sz), 0.f);
+    const float xl = fmaxf(fsubx(sx, lx), 0.f), xh = fmaxf(fsubx(faddx(lx, cell), sx), 0.f);
+    const float yl = fmaxf(fsubx(sy, ly), 0.f), yh = fmaxf(fsubx(faddx(ly, cell), sy), 0.f);
+    const float zl = fmaxf(fsubx(sz, lz), 0.f), zh = fmaxf(fsubx(faddx(lz, cell), sz), 0.f);
+    q.xl = fmulx(xl, xl); q.xh = fmulx(xh, xh); q.yl = fmulx(yl, yl); q.yh = fmulx(yh, yh); q.zl = fmulx(zl, zl); q.zh = fmulx(zh, zh);
     return q;
 }
-// lower bound of the candidate distance over a cell at offset (ox, oy, oz) in {-1,0,1}^3, same expression and rounding
+// lower bound of the candidate distance over a cell at offset (ox, oy, oz) in {-1,0,1}^3: the candidate expression
+// ((dx*dx) + dy*dy) + dz*dz with the face distances in place of the differences, same roundings
 __device__ __forceinline__ float cell_bound(const QCell& q, int ox, int oy, int oz) {
     const float bx = ox < 0 ? q.xl : ox > 0 ? q.xh : 0.f;
     const float by = oy < 0 ? q.yl : oy > 0 ? q.yh : 0.f;
     const float bz = oz < 0 ? q.zl : oz > 0 ? q.zh : 0.f;
-    return faddx(faddx(fmulx(bx, bx), fmulx(by, by)), fmulx(bz, bz));
+    return faddx(faddx(bx, by), bz);
 }
 
 // Run of the cell-sorted map covering the cells of row (oy, oz) that can still hold a neighbour: the three x-adjacent
@@ -200,22 +202,41 @@ __device__ __forceinline__ void group_knn5(float sx, float sy, float sz, const f
 }
 
 // One thread per query (large query sets: every issue slot ranks 32 candidates; consecutive queries are spatial
-// neighbours, so the warp's loads hit the same cells in L1).  Three steps:
-//   1. the centre row (the query's own (y,z) row, three x-adjacent cells, ~1/3 of the block's points and nearly always
-//      the five nearest among them) — after it `tau` is at or near the final fifth distance;
-//   2. the eight other rows are bounded against that tau; the survivors' trimmed runs go to a per-thread list in shared
-//      memory, all their cell-table loads in flight together;
-//   3. ONE loop over the concatenated list.  A warp's trip count is then the maximum over its lanes of the total number of
-//      batches — not the sum over rows of the per-row maxima, which is what cost the first version of this kernel twice
-//      the mean (profiles/r01_knn_dense_lanes1_ncu.txt).
-// `runs`: this thread's slots of a [kRunCap][run_stride] int4 array in shared memory {begin, end, bound bits, -}.
+// neighbours, so the warp's loads hit the same cells in L1).  Every lane walks its OWN candidate list, so anything
+// conditional costs the whole warp whenever any lane takes it.  Two consequences shape this routine:
+//   * candidates are only FILTERED in the scan loops (one fp32 compare against tau); the survivors' keys are parked in a small
+//     per-thread buffer in shared memory and ranked afterwards in a dense loop.  Ranking inside the scan loop made the warp
+//     execute the 30-instruction insert network at nearly every candidate slot (P(some lane inserts) ~ 1), ~40 % of the
+//     kernel's instructions (profiles/r02_knn_dense_v1_ncu.txt);
+//   * the loops are flattened: 1. the centre row (the query's own (y,z) row, ~1/3 of the block's points and nearly always the
+//     five nearest among them) — after it tau is at or near the final fifth distance; 2. the eight other rows are bounded
+//     against that tau, the survivors' trimmed runs go to a per-thread list in shared memory, all their cell-table loads in
+//     flight together; 3. ONE loop over the concatenated list: a warp's trip count is the maximum over its lanes of the total
+//     number of batches — not the sum over rows of the per-row maxima (twice the mean in the first version of this kernel).
+// `runs`: this thread's column of a [kRunCap][stride] int4 array {begin, end, bound bits, -}; `pend`: of a [kPendCap][stride] u64 array.
 constexpr int kRunCap = 8;
+constexpr int kPendCap = 12;
 template <int BATCH1 = 8, int BATCH3 = 4>
 __device__ __forceinline__ void thread_knn5(float sx, float sy, float sz, const float4* __restrict__ map,
-                                            const int* __restrict__ cell_start, const GridDesc& g, float tau0, int4* runs, int run_stride,
+                                            const int* __restrict__ cell_start, const GridDesc& g, float tau0, int4* runs, u64* pend, int stride,
                                             Top5& top, unsigned long long& cand) {
     const QCell qc = query_cell(sx, sy, sz, g);
     float tau = tau0;
+    int npend = 0;
+    auto drain = [&]() {
+#pragma unroll 1
+        for (int j = 0; j < npend; ++j) top5_insert(top, pend[j * stride]);
+        npend = 0;
+        tau = fminf(tau, top5_dist(top.k4));        // k4 == ~0 decodes to NaN: fminf keeps tau
+    };
+    auto filter = [&](const float4& m) {
+        const float d = cand_dist(sx, sy, sz, m);
+        if (d <= tau) {
+            if (npend == kPendCap) drain();          // rare: a dense cell cluster inside the gate
+            pend[npend * stride] = make_key(d, m);
+            ++npend;
+        }
+    };
     {   // 1. centre row
         int ib, ie, b = 0, e = 0;
         if (row_cells(qc, g, 0, 0, tau, ib, ie)) { b = __ldg(cell_start + ib); e = __ldg(cell_start + ie); }
@@ -226,8 +247,9 @@ __device__ __forceinline__ void thread_knn5(float sx, float sy, float sz, const 
 #pragma unroll
             for (int i = 0; i < BATCH1; ++i) if (p0 + i < e) c[i] = __ldg(map + p0 + i);
 #pragma unroll
-            for (int i = 0; i < BATCH1; ++i) if (p0 + i < e) consider(sx, sy, sz, c[i], top, tau);
+            for (int i = 0; i < BATCH1; ++i) if (p0 + i < e) filter(c[i]);
         }
+        drain();
     }
     // 2. surviving rows: faces first (they hold the nearer cells), then corners
     int nruns = 0;
@@ -245,7 +267,7 @@ __device__ __forceinline__ void thread_knn5(float sx, float sy, float sz, const 
         }
 #pragma unroll
         for (int k = 0; k < kRunCap; ++k) {
-            if (re[k] > rb[k]) { runs[nruns * run_stride] = make_int4(rb[k], re[k], __float_as_int(bnd[k]), 0); ++nruns; }
+            if (re[k] > rb[k]) { runs[nruns * stride] = make_int4(rb[k], re[k], __float_as_int(bnd[k]), 0); ++nruns; }
         }
     }
     // 3. one flat loop over the listed runs
@@ -253,22 +275,20 @@ __device__ __forceinline__ void thread_knn5(float sx, float sy, float sz, const 
 #pragma unroll 1
     while (true) {
         if (p >= e) {
-            bool have = false;
-            while (k < nruns) {
-                const int4 r = runs[k * run_stride];
-                ++k;
-                if (__int_as_float(r.z) <= tau) { p = r.x; e = r.y; have = true; break; }   // tau has shrunk since step 2
-            }
-            if (!have) break;
+            if (k >= nruns) break;
+            const int4 r = runs[k * stride];
+            ++k;
+            p = r.x; e = r.y;
         }
         float4 c[BATCH3];
 #pragma unroll
         for (int i = 0; i < BATCH3; ++i) if (p + i < e) c[i] = __ldg(map + p + i);
 #pragma unroll
-        for (int i = 0; i < BATCH3; ++i) if (p + i < e) consider(sx, sy, sz, c[i], top, tau);
+        for (int i = 0; i < BATCH3; ++i) if (p + i < e) filter(c[i]);
         cand += (unsigned long long)(min(e - p, BATCH3));
         p += BATCH3;
     }
+    drain();
 }
 
 }  // namespace lili

@@ -1,7 +1,6 @@
 """The switches of the small-scan GN kernel must not change a single bit:
   LILIOM_GN_SYNC  = 3 counter grid barrier with a release-only arrival and a relaxed poll (default) | 1 release arrival +
                     acquire poll | 0 full fences on both sides
-  LILIOM_FAST_IO  = 1 start pose in the launch parameters, one read-back block
   fused peer exchange of one rank with itself (the whole NVLink protocol on a single GPU)
 Same candidate sets, same per-row arithmetic, same summation trees -> identical poses, correspondences and sums."""
 import os
@@ -11,16 +10,15 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
-# (unused, mode): mode % 10 = LILIOM_GN_SYNC; +10: LILIOM_FAST_IO=1; +20: fused peer exchange with itself
-VARIANTS = [(0, 3), (0, 1), (0, 0), (0, 13), (0, 23)]
+# (unused, mode): mode % 10 = LILIOM_GN_SYNC; +20: fused peer exchange with itself
+VARIANTS = [(0, 3), (0, 1), (0, 0), (0, 23)]
 
 
 def _ctx(flat, ll):
     import liliom_b200 as L
-    keys = ("LILIOM_GN_SYNC", "LILIOM_FAST_IO")
+    keys = ("LILIOM_GN_SYNC",)
     old = {k: os.environ.get(k) for k in keys}
     os.environ["LILIOM_GN_SYNC"] = str(ll % 10)
-    os.environ["LILIOM_FAST_IO"] = "1" if 10 <= ll < 20 else "0"
     try:
         c = L.Context(variant=0)             # the switches are read at liliom_create
         if ll >= 20:                         # one rank exchanging with itself: the whole protocol on a single GPU

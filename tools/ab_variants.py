@@ -1,9 +1,8 @@
 #!/usr/bin/env python
 """A/B of the small-scan GN kernel switches inside ONE process (B200, run under gpurun):
-for every (LILIOM_GN_SYNC, LILIOM_FAST_IO, LILIOM_GN_GRID) triple a fresh context is created (the switches are read at
-liliom_create), the bench's resident step (extract -> VoxelGrid -> 10 GN iterations, L2 flushed between steps) is timed with
+for every LILIOM_GN_SYNC value a fresh context is created (the switch is read at liliom_create), the bench's resident step (extract -> VoxelGrid -> 10 GN iterations, L2 flushed between steps) is timed with
 CUDA events, and the pose is compared bit-for-bit with the first configuration.  LILIOM_LIB selects a tuning build of the library.
-usage: ab_variants.py [steps] [sync:fast_io:fullgrid ...]"""
+usage: ab_variants.py [steps] [sync ...]"""
 import os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -13,8 +12,7 @@ import liliom_b200 as L
 from liliom_b200 import synth
 
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 150
-cfgs = [tuple(int(x) for x in a.split(":")) for a in sys.argv[2:]] or [(3, 0, 0), (1, 0, 0), (0, 0, 0), (3, 1, 0), (3, 0, 1), (3, 1, 1), (3, 0, 0)]
-cfgs = [(c + (0, 0))[:3] for c in cfgs]
+cfgs = [int(a) for a in sys.argv[2:]] or [3, 1, 0, 3]
 m, _ = synth.make_map(1_000_000)
 T0 = synth.default_true_pose()
 sweeps = []
@@ -26,8 +24,8 @@ flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 stream = torch.cuda.Stream()
 ref = None
 print(f"lib: {L.LIB_PATH}")
-for sync, coop, full in cfgs:
-    os.environ["LILIOM_GN_SYNC"] = str(sync); os.environ["LILIOM_FAST_IO"] = str(coop); os.environ["LILIOM_GN_GRID"] = "full" if full else "auto"
+for sync in cfgs:
+    os.environ["LILIOM_GN_SYNC"] = str(sync)
     c = L.Context(variant=0)
     c.set_stream(stream.cuda_stream)
     c.map_set_points(m)
@@ -55,4 +53,4 @@ for sync, coop, full in cfgs:
     same = "ref" if ref is None else ("bit-identical" if all(a.tobytes() == b.tobytes() for a, b in zip(poses, ref)) else "DIFFERENT POSES")
     if ref is None:
         ref = poses
-    print(f"sync={sync} fast_io={coop} full_grid={full}: {steps / (tot * 1e-3):7.0f} scans/s  step {1e3 * tot / steps:6.1f} us  GN {1e3 * cnt.knn_ms / max(cnt.knn_launches, 1):6.2f} us/pass  [{same}]", flush=True)
+    print(f"sync={sync}: {steps / (tot * 1e-3):7.0f} scans/s  step {1e3 * tot / steps:6.1f} us  GN {1e3 * cnt.knn_ms / max(cnt.knn_launches, 1):6.2f} us/pass  [{same}]", flush=True)
