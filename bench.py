@@ -45,6 +45,7 @@ sys.path.insert(0, ROOT)
 
 ITERS = 10
 N_FRAMES = 20
+SHARD_BLOCK_M = 64
 METRIC = "scans/sec (24k-pt sweep vs 1M-pt map); kNN+Jacobian HBM GB/s vs peak"
 
 
@@ -407,6 +408,8 @@ def bench_body(args, fallback_note=None):
             uid = [L.comm_get_unique_id() if rank == 0 else None]
             dist.broadcast_object_list(uid, src=0)
             cx.comm_init(uid[0], world, rank)
+            if stream_wl:
+                cx.comm_set_shard_block(SHARD_BLOCK_M)       # a 1.2 km map: 64 m cubes keep the replicated rim near 10 %
             if not use_nccl_exchange:     # fused exchange over NVLink peer memory: one launch per scan and rank, no collective call per iteration
                 hs = [None] * world
                 dist.all_gather_object(hs, cx.comm_peer_export())

@@ -240,6 +240,10 @@ int liliom_pc2_layout(int point_stride, liliom_pc2_field* fields, int cap, int* 
  * the 27 J^T J|J^T r scalars (+cost,count) then an identical 6x6 solve on every rank. */
 int liliom_comm_get_unique_id(void* id128);
 int liliom_comm_init(liliom_ctx* c, const void* id128, int nranks, int rank);
+/* Edge of the cubes the map is sharded by (metres, a power of two in [8, 256]; default 16).  Larger cubes replicate less
+ * halo (a 64 m cube with its 1 m + voxel-diagonal rim holds ~1.1x its own points, a 16 m cube ~1.45x) at a coarser load
+ * balance.  Must be the same on every rank and set before the map is installed / the first frame is pushed. */
+int liliom_comm_set_shard_block(liliom_ctx* c, int metres);
 
 /* Fused exchange over peer memory (single node, NVLink / NVSwitch; optional, after liliom_comm_init): every rank exports the
  * 64-byte cudaIpcMemHandle of its exchange buffer, the launcher all-gathers them, every rank attaches all of them in rank

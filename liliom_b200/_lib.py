@@ -60,7 +60,7 @@ EXPORTS = [
     "liliom_map_set_cloud", "liliom_correspond_surf_refl",
     "liliom_backend_edge_block", "liliom_backend_surf_block", "liliom_convert_livox", "liliom_extract_horizon_livox",
     "liliom_pc2_layout", "liliom_comm_peer_export", "liliom_comm_peer_attach",
-    "liliom_map_push_frame_device", "liliom_knn_block_stats",
+    "liliom_map_push_frame_device", "liliom_knn_block_stats", "liliom_comm_set_shard_block",
 ]
 NODE_EXPORTS = ["liliom_pre_create", "liliom_pre_destroy", "liliom_pre_imu", "liliom_pre_cloud",
                 "liliom_lo_create", "liliom_lo_destroy", "liliom_lo_edge", "liliom_lo_surf", "liliom_lo_full", "liliom_lo_run"]
@@ -144,6 +144,7 @@ def lib() -> C.CDLL:
     L.liliom_comm_peer_export.argtypes = [vp, vp]
     L.liliom_comm_peer_attach.argtypes = [vp, vp, C.c_int, C.c_int]
     L.liliom_map_push_frame_device.argtypes = [vp, vp, C.c_int, dp]
+    L.liliom_comm_set_shard_block.argtypes = [vp, C.c_int]
     L.liliom_knn_block_stats.argtypes = [vp, dp, C.POINTER(C.c_ulonglong)]
     L.liliom_pre_create.argtypes = [vp, C.c_int, dp]; L.liliom_pre_create.restype = vp
     L.liliom_pre_destroy.argtypes = [vp]; L.liliom_pre_destroy.restype = None
@@ -427,6 +428,9 @@ class Context:
     def comm_init(self, unique_id: bytes, nranks: int, rank: int):
         buf = C.create_string_buffer(unique_id, 128)
         self._check(lib().liliom_comm_init(self._h, buf, nranks, rank))
+
+    def comm_set_shard_block(self, metres: int):
+        self._check(lib().liliom_comm_set_shard_block(self._h, metres))
 
     def comm_peer_export(self) -> bytes:
         """64-byte IPC handle of this rank's exchange buffer (fused multi-GPU exchange, include/liliom.h)."""

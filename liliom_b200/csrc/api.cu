@@ -400,11 +400,11 @@ extern "C" int liliom_map_clear(liliom_ctx* c) {
 // Shared body of the two push_frame entry points: d_src = n body-frame points of point_stride bytes ON THE DEVICE.
 static int push_frame_from_device(liliom_ctx* c, const void* d_src, int n, const double pose7[7]) {
     const int stride = c->prm.point_stride;
-    if ((int)c->frames.size() >= c->prm.max_map_frames && !c->frames.empty()) {      // L/src/LidarOdometry.cpp:293-296 pop_front
-        c->frames.front().buf.release();
-        c->frames.erase(c->frames.begin());
-    }
     Frame f;
+    if ((int)c->frames.size() >= c->prm.max_map_frames && !c->frames.empty()) {      // L/src/LidarOdometry.cpp:293-296 pop_front
+        f.buf = c->frames.front().buf;          // the popped frame's allocation is recycled: cudaFree + cudaMalloc per scan cost
+        c->frames.erase(c->frames.begin());     // more than the whole map maintenance of a 10 M-point map (cudaFree synchronises)
+    }
     f.n = n;
     int rc = LILIOM_OK;
     if (n > 0) {

@@ -91,6 +91,12 @@ extern "C" int liliom_comm_init(liliom_ctx* c, const void* id128, int nranks, in
     return LILIOM_OK;
 }
 
+extern "C" int liliom_comm_set_shard_block(liliom_ctx* c, int metres) {
+    if (!c || metres < 8 || metres > 256 || (metres & (metres - 1)) != 0) return LILIOM_E_ARG;
+    c->shard_inv_block = 1.0f / (float)metres;
+    return LILIOM_OK;
+}
+
 // ---- fused exchange over NVLink / NVSwitch peer memory (SURVEY.md §8 e, "one kernel that does both") -------------------------
 // The NCCL path costs, per GN iteration, a kernel, an all-reduce of 232 bytes (~20 us of latency on 2 B200s, more than the
 // sharded search saves at 1.4k queries) and an update kernel.  Here every rank runs its persistent GN kernel; after the local

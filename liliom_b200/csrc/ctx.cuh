@@ -197,6 +197,7 @@ inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 int sort_pairs_u32(liliom_ctx* c, const uint32_t* kin, uint32_t* kout, const int* vin, int* vout, int n, int end_bit);
 int sort_pairs_u64(liliom_ctx* c, const unsigned long long* kin, unsigned long long* kout, const int* vin, int* vout, int n, int end_bit);
 int exclusive_scan_i32(liliom_ctx* c, const int* in, int* out, int n);   // out has n+1 entries (total at out[n])
+int inclusive_max_scan_i32(liliom_ctx* c, int* data, int n);            // in-place running maximum
 
 // VoxelGrid on device buffers; d_count receives the output count (int, device).
 int voxelgrid_dev(liliom_ctx* c, const void* d_in, int n, int stride, float leaf, void* d_out, int* d_count);

@@ -92,16 +92,15 @@ __global__ void k_gather_sorted(const float4* __restrict__ p, const int* __restr
     out[i] = make_float4(v.x, v.y, v.z, __int_as_float(src));   // w = index into the un-sorted map array
 }
 
-// cell_start[c] = first sorted position whose key >= c; one warp per run boundary fills the gap.
-__global__ void k_cell_bounds(const uint32_t* __restrict__ keys, int n, int ncells, int* __restrict__ cell_start) {
-    int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    int lane = threadIdx.x & 31;
-    if (w > n) return;
-    // boundary w: between sorted position w-1 and w (w == n: tail)
-    long long prev = (w == 0) ? -1 : (long long)keys[w - 1];
-    long long cur = (w == n) ? (long long)ncells : (long long)keys[w];
-    if (cur == prev) return;
-    for (long long cc = prev + 1 + lane; cc <= cur; cc += 32) cell_start[cc] = w;
+// cell_start[c] = first sorted position whose key >= c = number of points with key < c = upper bound of cell c-1.
+// Run ENDS are scattered (cell_start[key+1] = position after the run) into a zeroed table and a running maximum fills the
+// empty cells: two streaming passes over the table.  (The first version filled every gap with one warp per sorted
+// position: 724 us for a 10 M-point map, profiles/r02_stream_1gpu_launches.txt; this is ~60 us.)
+__global__ void k_cell_run_ends(const uint32_t* __restrict__ keys, int n, int* __restrict__ cell_start) {
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n) return;
+    const uint32_t k = keys[w];
+    if (w == n - 1 || keys[w + 1] != k) cell_start[(size_t)k + 1] = w + 1;
 }
 
 int grid_build(liliom_ctx* c, int m) {
@@ -161,9 +160,10 @@ int grid_build(liliom_ctx* c, int m) {
                             c->grid_vals2.as<int>(), m, bits));
     k_gather_sorted<<<cdiv(m, 256), 256, 0, c->stream>>>(pts, c->grid_vals2.as<int>(), m, c->map_sorted.as<float4>());
     LILI_TRY(launch_check(c, "k_gather_sorted"));
-    k_cell_bounds<<<cdiv(((long long)m + 1) * 32, 256), 256, 0, c->stream>>>(c->grid_keys2.as<uint32_t>(), m, g.ncells,
-                                                                          c->cell_start.as<int>());
-    LILI_TRY(launch_check(c, "k_cell_bounds"));
+    LILI_CUDA(c, cudaMemsetAsync(c->cell_start.p, 0, ((size_t)g.ncells + 2) * 4, c->stream));
+    k_cell_run_ends<<<cdiv(m, 256), 256, 0, c->stream>>>(c->grid_keys2.as<uint32_t>(), m, c->cell_start.as<int>());
+    LILI_TRY(launch_check(c, "k_cell_run_ends"));
+    LILI_TRY(inclusive_max_scan_i32(c, c->cell_start.as<int>(), g.ncells + 1));
     c->map_ready = true;
     return LILIOM_OK;
 }
@@ -237,9 +237,9 @@ template <int LANES>
 __device__ __forceinline__ void knn_phases(const KnnArgs& a, const Q4& q, const D3& t, const int n_q, KnnSmem& S,
                                            double& acc, unsigned long long& cand, const float4* fpre = nullptr) {
     constexpr int GROUPS = 32 / LANES;                 // queries a warp searches concurrently
-    extern __shared__ __align__(16) unsigned char dyn_smem[];      // LANES == 1: [kRunCap][kBlock] int4 run lists | [kPendCap][kBlock] u64 (thread_knn5)
-    int4* runs = reinterpret_cast<int4*>(dyn_smem) + threadIdx.x;
-    u64* pend = reinterpret_cast<u64*>(dyn_smem + (size_t)kRunCap * kBlock * sizeof(int4)) + threadIdx.x;
+    extern __shared__ __align__(16) unsigned char dyn_smem[];      // LANES == 1: [kRunCap][kBlock] int2 runs | [kRunCap][kBlock] float bounds (thread_knn5)
+    int2* runs = reinterpret_cast<int2*>(dyn_smem) + threadIdx.x;
+    float* bnd = reinterpret_cast<float*>(dyn_smem + (size_t)kRunCap * kBlock * sizeof(int2)) + threadIdx.x;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int sub = lane & (LANES - 1);
@@ -277,7 +277,7 @@ __device__ __forceinline__ void knn_phases(const KnnArgs& a, const Q4& q, const 
             LILI_STAMP(8);
             if (live) {
                 if (sub == 0) cand += 1ull << kCandBits;
-                if constexpr (LANES == 1) thread_knn5(sx, sy, sz, a.map, a.cell_start, a.g, a.tau0, runs, pend, kBlock, top, cand);
+                if constexpr (LANES == 1) thread_knn5(sx, sy, sz, a.map, a.cell_start, a.g, a.tau0, runs, bnd, kBlock, top, cand);
                 else group_knn5<LANES>(sx, sy, sz, a.map, a.cell_start, a.g, sub, gmask, a.tau0, top, cand, (a.dbg && blockIdx.x == 0 && threadIdx.x == 0) ? a.dbg : nullptr);
             }
             LILI_STAMP(11);
@@ -522,8 +522,13 @@ __device__ __forceinline__ void write_neq_stats(const KnnArgs& a, const KnnSmem&
 }
 
 
+// Blocks per SM of the one-thread-per-query instance: that shape is bound by latency per issued instruction (8.8 cycles at
+// ~4 warps per scheduler, profiles/r02_knn_dense_v1_ncu.txt), so it trades registers (spills in the fp64 fit) for resident warps.
+#ifndef LILI_KNN1_MINBLOCKS
+#define LILI_KNN1_MINBLOCKS 2
+#endif
 template <int LANES>
-__global__ void __launch_bounds__(kBlock, 2) k_knn_plane(KnnArgs a, const __grid_constant__ PeerArgs pa) {
+__global__ void __launch_bounds__(kBlock, LANES == 1 ? LILI_KNN1_MINBLOCKS : 2) k_knn_plane(KnnArgs a, const __grid_constant__ PeerArgs pa) {
     __shared__ __align__(16) KnnSmem S;
     if (threadIdx.x == 0) S.peer_lost = 0;
     LILI_STAMP(0);
@@ -1042,7 +1047,7 @@ int s2m_run(liliom_ctx* c, double pose7[7], int match_cnt, int max_num_iter, int
     }
 
     // one thread per query: per-thread run lists in dynamic shared memory (thread_knn5); static + dynamic exceed 48 KB
-    const size_t dyn_smem = lanes == 1 ? (size_t)kRunCap * kBlock * sizeof(int4) + (size_t)kPendCap * kBlock * sizeof(u64) : 0;
+    const size_t dyn_smem = lanes == 1 ? (size_t)kRunCap * kBlock * (sizeof(int2) + sizeof(float)) : 0;
     if (lanes == 1 && !c->knn1_smem_set) {
         LILI_CUDA(c, cudaFuncSetAttribute((const void*)k_knn_plane<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
         LILI_CUDA(c, cudaFuncSetAttribute((const void*)k_gn_persistent<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));

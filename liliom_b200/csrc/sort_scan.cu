@@ -38,4 +38,15 @@ int exclusive_scan_i32(liliom_ctx* c, const int* in, int* out, int n) {
     return LILIOM_OK;
 }
 
+// in-place inclusive running maximum of data[0..n) (used by grid_build: upper bounds of the cell runs)
+int inclusive_max_scan_i32(liliom_ctx* c, int* data, int n) {
+    if (n <= 0) return LILIOM_OK;
+    size_t need = 0;
+    LILI_CUDA(c, cub::DeviceScan::InclusiveScan(nullptr, need, data, data, cub::Max(), n, c->stream));
+    LILI_CUDA(c, c->cub_tmp.ensure(need));
+    LILI_CUDA(c, cub::DeviceScan::InclusiveScan(c->cub_tmp.p, need, data, data, cub::Max(), n, c->stream));
+    c->cnt.lib_launches++;
+    return LILIOM_OK;
+}
+
 }  // namespace lili

@@ -19,19 +19,19 @@ def _block_hash(b: np.ndarray) -> np.ndarray:
     return h
 
 
-def owner_of(xyz: np.ndarray, nranks: int) -> np.ndarray:
+def owner_of(xyz: np.ndarray, nranks: int, block: int = 16) -> np.ndarray:
     xyz = np.asarray(xyz, np.float32)
-    b = np.floor(xyz * np.float32(0.0625)).astype(np.int32)
+    b = np.floor(xyz * np.float32(1.0 / block)).astype(np.int32)
     return (_block_hash(b) % np.uint32(nranks)).astype(np.int32)
 
 
-def shard_mask(xyz: np.ndarray, nranks: int, rank: int, halo: float = 1.0) -> np.ndarray:
+def shard_mask(xyz: np.ndarray, nranks: int, rank: int, halo: float = 1.0, block: int = 16) -> np.ndarray:
     xyz = np.asarray(xyz, np.float32)
     keep = np.zeros(len(xyz), bool)
     h = np.float32(halo)
     for c in range(8):
         off = np.array([h if c & 1 else -h, h if c & 2 else -h, h if c & 4 else -h], np.float32)
-        keep |= owner_of(xyz + off, nranks) == rank
+        keep |= owner_of(xyz + off, nranks, block) == rank
     return keep
 
 
