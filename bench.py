@@ -508,14 +508,18 @@ def bench_body(args, fallback_note=None):
         torch.cuda.synchronize()
 
     def make_steps(cx):
-        """The two step functions on context cx.  Streamed workload: frame k % N_FRAMES is the oldest in the FIFO at step k
-        (it was pushed N_FRAMES pushes ago); pushing it again keeps the map's content — and the step's work — constant."""
+        """The two step functions on context cx.  Streamed workload: the frame pushed is always the one the FIFO is about to
+        drop (push number p re-pushes frame p % N_FRAMES, counted per context over ALL steps, warm-up included), so the
+        map's content — and the step's work — stay constant."""
+        pushes = [0]
+
         def step_resident(k):
             sw = sweeps[k % len(sweeps)]
             cx.extract_resident(sw["q"])
             pose, st, nds = cx.odometry_resident(sw["guess"], ITERS, mode=L.MODE_GN, want_stats=False)
             if stream_wl:
-                fd = frames_dev[k % N_FRAMES]
+                fd = frames_dev[pushes[0] % N_FRAMES]
+                pushes[0] += 1
                 cx.map_push_frame_device(fd.data_ptr(), fd.numel() // psz, ident)
                 cx.map_rebuild()
             return pose, nds
@@ -529,7 +533,8 @@ def bench_body(args, fallback_note=None):
             h2d = len(pin_sweeps[i]) * psz + len(surf) * psz + 56
             d2h = (len(surf) + len(edge) + len(cut)) * psz + len(ds) * psz + 56
             if stream_wl:
-                fh = frames_host[k % N_FRAMES]
+                fh = frames_host[pushes[0] % N_FRAMES]
+                pushes[0] += 1
                 cx.map_push_frame(fh, ident)                  # buildLocalMap's push: the frame arrives from the host
                 cx.map_rebuild()
                 h2d += len(fh) * psz + 56

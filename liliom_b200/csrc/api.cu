@@ -224,7 +224,7 @@ extern "C" void liliom_destroy(liliom_ctx* c) {
                       &c->vg_keys2, &c->vg_vals, &c->vg_vals2, &c->vg_flags, &c->vg_rank, &c->vg_params, &c->vg_out, &c->vg_minmax, &c->vg_count,
                       &c->cub_tmp, &c->vg_coop, &c->hz_ctl, &c->map_raw, &c->map_ds, &c->map_xyzw, &c->map_sorted, &c->cell_start, &c->grid_keys, &c->grid_keys2,
                       &c->grid_vals, &c->grid_vals2, &c->feats, &c->corr_valid, &c->corr_plane, &c->nn_idx, &c->nn_sqd, &c->pose_dev,
-                      &c->partials, &c->neq, &c->stats_dev, &c->counter, &c->lm_state, &c->raw_scan, &c->map_refl, &c->livox_in};
+                      &c->partials, &c->neq, &c->stats_dev, &c->counter, &c->lm_state, &c->raw_scan, &c->map_refl, &c->livox_in, &c->qstate};
     for (DevBuf* b : bufs) b->release();
     for (auto& f : c->frames) f.buf.release();
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);

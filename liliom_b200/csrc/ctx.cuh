@@ -130,6 +130,7 @@ struct liliom_ctx {
     lili::DevBuf feats;                  // float4 body-frame queries
     int n_feats = 0;
     lili::DevBuf corr_valid, corr_plane, nn_idx, nn_sqd;
+    lili::DevBuf qstate;                 // float4 per query: transformed position + fifth distance of the previous GN pass
     lili::DevBuf pose_dev;               // 7 doubles (current) + 7 (candidate)
     lili::DevBuf partials;               // grid x 29 doubles
     lili::DevBuf neq;                    // 29 doubles (reduced)

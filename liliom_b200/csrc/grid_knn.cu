@@ -185,6 +185,8 @@ struct KnnArgs {
     long long* dbg;                     // optional phase timestamps (LILIOM_DEBUG_TIMING)
     int interleave;                     // 1: deal tasks to warps block-cyclically (load balance for small scans)
     float tau0;                         // largest fp32 distance inside the gate (knn_gate_tau(max_sqd)): search pruning threshold
+    float4* qstate;                     // per query {transformed position, fifth distance} of the previous pass of this call (see coherence_tau)
+    int use_state;                      // 1: qstate holds the previous pass (per-iteration launches; the persistent kernel sets it per pass)
     float inv_block;                    // 1 / shard block edge (multi-GPU ownership)
     unsigned long long* queries_total;  // instrumentation: queries processed (device-side count), one add per pass
 };
@@ -197,6 +199,20 @@ __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
+}
+
+// Temporal coherence of the GN passes: a query whose five neighbours lay within r = sqrt(d5) at its previous position p'
+// still has those five map points within r + |p - p'| of its new position p, so its new fifth distance is at most
+// (r + |p - p'|)^2.  Starting the search with that bound instead of the gate skips most cells outright and leaves little to
+// rank — from the second pass of a scan on the poses move by centimetres.  The bound is evaluated with upward roundings and
+// a 1e-5 relative margin (the candidate distance expression carries ~3 fp32 roundings, ~2e-7), so every point of the true
+// 5-NN set passes the filter: the sets found, their order and the accept decisions are exactly those of the full search.
+__device__ __forceinline__ float coherence_tau(const float4& st, float sx, float sy, float sz, float tau0) {
+    if (!(st.w <= tau0)) return tau0;                    // no five neighbours inside the gate last time (or NaN): nothing to exploit
+    const float dx = fsubx(sx, st.x), dy = fsubx(sy, st.y), dz = fsubx(sz, st.z);
+    const float mv = __fsqrt_ru(__fadd_ru(__fadd_ru(__fmul_ru(dx, dx), __fmul_ru(dy, dy)), __fmul_ru(dz, dz)));
+    const float r = __fadd_ru(__fsqrt_ru(st.w), mv);
+    return fminf(tau0, __fmul_ru(__fmul_ru(r, r), 1.00001f));
 }
 
 // Per-query scratch a warp keeps in shared memory between the phases.
@@ -235,11 +251,10 @@ struct KnnSmem {
 // accumulates scalar k).  On return lane k < 29 of every warp holds its partial of scalar k in `acc`.
 template <int LANES>
 __device__ __forceinline__ void knn_phases(const KnnArgs& a, const Q4& q, const D3& t, const int n_q, KnnSmem& S,
-                                           double& acc, unsigned long long& cand, const float4* fpre = nullptr) {
+                                           double& acc, unsigned long long& cand, const bool use_state, const float4* fpre = nullptr) {
     constexpr int GROUPS = 32 / LANES;                 // queries a warp searches concurrently
-    extern __shared__ __align__(16) unsigned char dyn_smem[];      // LANES == 1: [kRunCap][kBlock] int2 runs | [kRunCap][kBlock] float bounds (thread_knn5)
-    int2* runs = reinterpret_cast<int2*>(dyn_smem) + threadIdx.x;
-    float* bnd = reinterpret_cast<float*>(dyn_smem + (size_t)kRunCap * kBlock * sizeof(int2)) + threadIdx.x;
+    extern __shared__ __align__(16) unsigned char dyn_smem[];      // LANES == 1: [kRunCap][kBlock] int4 run lists (thread_knn5)
+    int4* runs = reinterpret_cast<int4*>(dyn_smem) + threadIdx.x;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int sub = lane & (LANES - 1);
@@ -275,15 +290,19 @@ __device__ __forceinline__ void knn_phases(const KnnArgs& a, const Q4& q, const 
             }
             // `live` is uniform inside a lane group and the shuffles are masked per group
             LILI_STAMP(8);
+            float tau_q = a.tau0;
+            if (live && use_state) tau_q = coherence_tau(__ldcg(a.qstate + qi), sx, sy, sz, a.tau0);
             if (live) {
                 if (sub == 0) cand += 1ull << kCandBits;
-                if constexpr (LANES == 1) thread_knn5(sx, sy, sz, a.map, a.cell_start, a.g, a.tau0, runs, bnd, kBlock, top, cand);
-                else group_knn5<LANES>(sx, sy, sz, a.map, a.cell_start, a.g, sub, gmask, a.tau0, top, cand, (a.dbg && blockIdx.x == 0 && threadIdx.x == 0) ? a.dbg : nullptr);
+                if constexpr (LANES == 1) thread_knn5(sx, sy, sz, a.map, a.cell_start, a.g, tau_q, runs, kBlock, top, cand);
+                else group_knn5<LANES>(sx, sy, sz, a.map, a.cell_start, a.g, sub, gmask, tau_q, top, cand, (a.dbg && blockIdx.x == 0 && threadIdx.x == 0) ? a.dbg : nullptr);
             }
             LILI_STAMP(11);
             if (sub == 0) {
                 Slot& s = S.slots[warp][slot];
                 const bool ok = live && top.k4 != ~0ull && ((double)top5_dist(top.k4) < a.max_sqd);  // :365
+                // this pass's position and fifth distance for the next pass (a query this rank does not own keeps no bound)
+                if (qi < n_q) a.qstate[qi] = make_float4(sx, sy, sz, ok ? top5_dist(top.k4) : __int_as_float(0x7f800000));
                 s.idx[0] = ok ? top5_index(top.k0) : -1; s.idx[1] = top5_index(top.k1); s.idx[2] = top5_index(top.k2);
                 s.idx[3] = top5_index(top.k3); s.idx[4] = top5_index(top.k4);
                 s.sx = sx; s.sy = sy; s.sz = sz;
@@ -537,7 +556,7 @@ __global__ void __launch_bounds__(kBlock, LANES == 1 ? LILI_KNN1_MINBLOCKS : 2) 
     const int n_q = a.n_dev ? min(*a.n_dev, a.n) : a.n;
     double acc = 0.0;
     unsigned long long cand = 0;
-    knn_phases<LANES>(a, q, t, n_q, S, acc, cand);
+    knn_phases<LANES>(a, q, t, n_q, S, acc, cand, a.use_state != 0);
     LILI_STAMP(3);
     write_block_partials(a, S, acc, cand);
     __threadfence();
@@ -621,7 +640,7 @@ __global__ void LILI_GN_BOUNDS k_gn_persistent(KnnArgs a, int iters, unsigned in
         unsigned long long cand = 0;
         const bool stamp = a.dbg && blockIdx.x == 0 && threadIdx.x == 0 && it == 2;
         if (stamp) a.dbg[16] = clock64();
-        knn_phases<LANES>(a, q, t, n_q, S, acc, cand, keep ? &f_keep : nullptr);
+        knn_phases<LANES>(a, q, t, n_q, S, acc, cand, it > 0, keep ? &f_keep : nullptr);
         if (stamp) a.dbg[17] = clock64();
         if (sync_mode == 3 || sync_mode == 1) {
             // ---- counter barrier with the minimum of fences (default; measured 12.70 -> 11.99 us per pass against mode 0):
@@ -1036,6 +1055,9 @@ int s2m_run(liliom_ctx* c, double pose7[7], int match_cnt, int max_num_iter, int
     a.cand_total = c->time_kernels ? reinterpret_cast<unsigned long long*>(c->counter.as<unsigned char>() + 16) : nullptr;
     a.queries_total = c->time_kernels ? reinterpret_cast<unsigned long long*>(c->counter.as<unsigned char>() + 24) : nullptr;
     a.tau0 = knn_gate_tau(c->prm.knn_max_sqdist);
+    LILI_CUDA(c, c->qstate.ensure((size_t)(n > 0 ? n : 1) * sizeof(float4)));
+    a.qstate = c->qstate.as<float4>();
+    a.use_state = 0;
     a.inv_block = c->shard_inv_block;
     a.rounds = rounds; a.nranks = c->nranks; a.rank = c->rank;
     a.interleave = (lanes >= 8 && !getenv("LILIOM_NO_INTERLEAVE")) ? 1 : 0;
@@ -1047,7 +1069,7 @@ int s2m_run(liliom_ctx* c, double pose7[7], int match_cnt, int max_num_iter, int
     }
 
     // one thread per query: per-thread run lists in dynamic shared memory (thread_knn5); static + dynamic exceed 48 KB
-    const size_t dyn_smem = lanes == 1 ? (size_t)kRunCap * kBlock * (sizeof(int2) + sizeof(float)) : 0;
+    const size_t dyn_smem = lanes == 1 ? (size_t)kRunCap * kBlock * sizeof(int4) : 0;
     if (lanes == 1 && !c->knn1_smem_set) {
         LILI_CUDA(c, cudaFuncSetAttribute((const void*)k_knn_plane<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
         LILI_CUDA(c, cudaFuncSetAttribute((const void*)k_gn_persistent<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
@@ -1102,6 +1124,7 @@ int s2m_run(liliom_ctx* c, double pose7[7], int match_cnt, int max_num_iter, int
     const int launches = persistent ? 0 : ((iters == 0 && want_corr) ? 1 : iters);
     for (int it = 0; it < launches; ++it) {
         a.stats = c->stats_dev.as<double>() + (size_t)it * kStatsDoubles;
+        a.use_state = it > 0 ? 1 : 0;
         const bool multi = c->nranks > 1;
         // fused exchange, one launch per iteration (large scans: grid > one block per SM): the last block trades the sums with the
         // peers and performs the GN step itself — no ncclAllReduce, no update kernel

@@ -202,61 +202,52 @@ __device__ __forceinline__ void group_knn5(float sx, float sy, float sz, const f
 }
 
 // One thread per query (large query sets: every issue slot ranks 32 candidates; consecutive queries are spatial
-// neighbours, so the warp's loads hit the same cells in L1).  Every lane walks its OWN candidate list, so a warp pays for the
-// longest list among its lanes and for every branch any lane takes.  Three steps:
-//   1. the query's own cell — its points are the likeliest neighbours; after it tau is usually the fifth distance already;
-//   2. the other 26 cells, as up to ten runs (the two x-neighbours of the own cell, then the eight other (y,z) rows with their
-//      three x-adjacent cells as ONE run each), bounded against tau and trimmed; the survivors go to a per-thread list in
-//      shared memory with all their cell-table loads in flight together, nearest first;
-//   3. ONE loop over the concatenated list; a run whose bound has meanwhile fallen behind tau is skipped.  A warp's trip
-//      count is then the maximum over its lanes of the total number of batches — not the sum over rows of the per-row maxima,
-//      which cost the first version of this kernel twice the mean (profiles/r01_knn_dense_lanes1_ncu.txt).
-// `runs` / `bnd`: this thread's columns of a [kRunCap][stride] int2 {begin, end} and a [kRunCap][stride] float array in shared memory.
-constexpr int kRunCap = 10;
-template <int BATCH = 4>
+// neighbours, so the warp's loads hit the same cells in L1).  Three steps:
+//   1. the centre row (the query's own (y,z) row, three x-adjacent cells, ~1/3 of the block's points and nearly always
+//      the five nearest among them) — after it `tau` is at or near the final fifth distance;
+//   2. the eight other rows are bounded against that tau; the survivors' trimmed runs go to a per-thread list in shared
+//      memory, all their cell-table loads in flight together;
+//   3. ONE loop over the concatenated list.  A warp's trip count is then the maximum over its lanes of the total number of
+//      batches — not the sum over rows of the per-row maxima, which is what cost the first version of this kernel twice
+//      the mean (profiles/r01_knn_dense_lanes1_ncu.txt).
+// `runs`: this thread's slots of a [kRunCap][run_stride] int4 array in shared memory {begin, end, bound bits, -}.
+constexpr int kRunCap = 8;
+template <int BATCH1 = 8, int BATCH3 = 4>
 __device__ __forceinline__ void thread_knn5(float sx, float sy, float sz, const float4* __restrict__ map,
-                                            const int* __restrict__ cell_start, const GridDesc& g, float tau0, int2* runs, float* bnd, int stride,
+                                            const int* __restrict__ cell_start, const GridDesc& g, float tau0, int4* runs, int run_stride,
                                             Top5& top, unsigned long long& cand) {
     const QCell qc = query_cell(sx, sy, sz, g);
     float tau = tau0;
-    const bool row_ok = qc.cy >= 0 && qc.cy < g.dim[1] && qc.cz >= 0 && qc.cz < g.dim[2] && qc.cx >= -1 && qc.cx <= g.dim[0];
-    int s0 = 0, s1 = 0, s2 = 0, s3 = 0;        // starts of cells cx-1, cx, cx+1, cx+2 of the centre row (clamped to the row)
-    if (row_ok) {
-        const int* row = cell_start + (qc.cz * g.dim[1] + qc.cy) * g.dim[0];
-        const int d0 = g.dim[0];
-        s0 = __ldg(row + min(max(qc.cx - 1, 0), d0)); s1 = __ldg(row + min(max(qc.cx, 0), d0));
-        s2 = __ldg(row + min(max(qc.cx + 1, 0), d0)); s3 = __ldg(row + min(max(qc.cx + 2, 0), d0));
-    }
-    // 1. own cell
-    cand += (unsigned long long)(s2 - s1);
+    {   // 1. centre row
+        int ib, ie, b = 0, e = 0;
+        if (row_cells(qc, g, 0, 0, tau, ib, ie)) { b = __ldg(cell_start + ib); e = __ldg(cell_start + ie); }
+        cand += (unsigned long long)(e - b);
 #pragma unroll 1
-    for (int p0 = s1; p0 < s2; p0 += 8) {
-        float4 c[8];
+        for (int p0 = b; p0 < e; p0 += BATCH1) {
+            float4 c[BATCH1];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) if (p0 + i < s2) c[i] = __ldg(map + p0 + i);
+            for (int i = 0; i < BATCH1; ++i) if (p0 + i < e) c[i] = __ldg(map + p0 + i);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) if (p0 + i < s2) consider(sx, sy, sz, c[i], top, tau);
+            for (int i = 0; i < BATCH1; ++i) if (p0 + i < e) consider(sx, sy, sz, c[i], top, tau);
+        }
     }
-    // 2. the other cells, nearest first: x-neighbours, face rows, corner rows
+    // 2. surviving rows: faces first (they hold the nearer cells), then corners
     int nruns = 0;
     {
-        const float bl = cell_bound(qc, -1, 0, 0), bh = cell_bound(qc, +1, 0, 0);
-        if (s1 > s0 && bl <= tau) { runs[nruns * stride] = make_int2(s0, s1); bnd[nruns * stride] = bl; ++nruns; }
-        if (s3 > s2 && bh <= tau) { runs[nruns * stride] = make_int2(s2, s3); bnd[nruns * stride] = bh; ++nruns; }
-        int rb[8], re[8];
-        float rbnd[8];
+        int rb[kRunCap], re[kRunCap];
+        float bnd[kRunCap];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
+        for (int k = 0; k < kRunCap; ++k) {
             const int oy = k == 0 ? -1 : k == 1 ? 1 : k == 2 ? 0 : k == 3 ? 0 : (k & 1) ? 1 : -1;
             const int oz = k == 0 ? 0 : k == 1 ? 0 : k == 2 ? -1 : k == 3 ? 1 : k < 6 ? -1 : 1;
             int ib, ie;
             rb[k] = 0; re[k] = 0;
-            rbnd[k] = cell_bound(qc, 0, oy, oz);
+            bnd[k] = cell_bound(qc, 0, oy, oz);
             if (row_cells(qc, g, oy, oz, tau, ib, ie)) { rb[k] = __ldg(cell_start + ib); re[k] = __ldg(cell_start + ie); }
         }
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            if (re[k] > rb[k]) { runs[nruns * stride] = make_int2(rb[k], re[k]); bnd[nruns * stride] = rbnd[k]; ++nruns; }
+        for (int k = 0; k < kRunCap; ++k) {
+            if (re[k] > rb[k]) { runs[nruns * run_stride] = make_int4(rb[k], re[k], __float_as_int(bnd[k]), 0); ++nruns; }
         }
     }
     // 3. one flat loop over the listed runs
@@ -266,20 +257,19 @@ __device__ __forceinline__ void thread_knn5(float sx, float sy, float sz, const 
         if (p >= e) {
             bool have = false;
             while (k < nruns) {
-                const int2 r = runs[k * stride];
-                const float b = bnd[k * stride];
+                const int4 r = runs[k * run_stride];
                 ++k;
-                if (b <= tau) { p = r.x; e = r.y; have = true; break; }   // tau has shrunk since step 2
+                if (__int_as_float(r.z) <= tau) { p = r.x; e = r.y; have = true; break; }   // tau has shrunk since step 2
             }
             if (!have) break;
         }
-        float4 c[BATCH];
+        float4 c[BATCH3];
 #pragma unroll
-        for (int i = 0; i < BATCH; ++i) if (p + i < e) c[i] = __ldg(map + p + i);
+        for (int i = 0; i < BATCH3; ++i) if (p + i < e) c[i] = __ldg(map + p + i);
 #pragma unroll
-        for (int i = 0; i < BATCH; ++i) if (p + i < e) consider(sx, sy, sz, c[i], top, tau);
-        cand += (unsigned long long)(min(e - p, BATCH));
-        p += BATCH;
+        for (int i = 0; i < BATCH3; ++i) if (p + i < e) consider(sx, sy, sz, c[i], top, tau);
+        cand += (unsigned long long)(min(e - p, BATCH3));
+        p += BATCH3;
     }
 }
 
