@@ -231,22 +231,24 @@ __device__ __forceinline__ void thread_knn5(float sx, float sy, float sz, const 
             for (int i = 0; i < BATCH1; ++i) if (p0 + i < e) consider(sx, sy, sz, c[i], top, tau);
         }
     }
-    // 2. surviving rows: faces first (they hold the nearer cells), then corners
+    // 2. surviving rows: faces first (they hold the nearer cells), then corners; four rows' cell-table loads in flight at a time
     int nruns = 0;
-    {
-        int rb[kRunCap], re[kRunCap];
-        float bnd[kRunCap];
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+        int rb[4], re[4];
+        float bnd[4];
 #pragma unroll
-        for (int k = 0; k < kRunCap; ++k) {
-            const int oy = k == 0 ? -1 : k == 1 ? 1 : k == 2 ? 0 : k == 3 ? 0 : (k & 1) ? 1 : -1;
-            const int oz = k == 0 ? 0 : k == 1 ? 0 : k == 2 ? -1 : k == 3 ? 1 : k < 6 ? -1 : 1;
+        for (int k = 0; k < 4; ++k) {
+            // half 0: (oy,oz) = (-1,0) (1,0) (0,-1) (0,1)    half 1: (-1,-1) (1,-1) (-1,1) (1,1)
+            const int oy = half == 0 ? (k == 0 ? -1 : k == 1 ? 1 : 0) : ((k & 1) ? 1 : -1);
+            const int oz = half == 0 ? (k == 2 ? -1 : k == 3 ? 1 : 0) : (k < 2 ? -1 : 1);
             int ib, ie;
             rb[k] = 0; re[k] = 0;
             bnd[k] = cell_bound(qc, 0, oy, oz);
             if (row_cells(qc, g, oy, oz, tau, ib, ie)) { rb[k] = __ldg(cell_start + ib); re[k] = __ldg(cell_start + ie); }
         }
 #pragma unroll
-        for (int k = 0; k < kRunCap; ++k) {
+        for (int k = 0; k < 4; ++k) {
             if (re[k] > rb[k]) { runs[nruns * run_stride] = make_int4(rb[k], re[k], __float_as_int(bnd[k]), 0); ++nruns; }
         }
     }
