@@ -61,6 +61,7 @@ void nccl_destroy(liliom_ctx* c) {
     }
     c->peer_ready = false;
     c->peer_buf.release();
+    c->peer_local.release();
 }
 
 }  // namespace lili
@@ -111,6 +112,8 @@ extern "C" int liliom_comm_peer_export(liliom_ctx* c, void* handle64) {
     if (!c->peer_buf.p) {
         LILI_CUDA(c, c->peer_buf.ensure(peer_buf_bytes()));
         LILI_CUDA(c, cudaMemset(c->peer_buf.p, 0, c->peer_buf.cap));      // epochs start at 1: a zero word never matches
+        LILI_CUDA(c, c->peer_local.ensure(1024));
+        LILI_CUDA(c, cudaMemset(c->peer_local.p, 0, c->peer_local.cap));
         c->peer_epoch = 0;
     }
     cudaIpcMemHandle_t h;

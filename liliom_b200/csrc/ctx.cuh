@@ -55,6 +55,8 @@ struct PeerArgs {
     int nranks, rank;
     unsigned int epoch0;       // epoch of iteration 0 of this launch (monotonic across launches, identical on all ranks)
     int enabled;
+    double* lsum;              // [2 parities][32] the sums over all ranks, republished by block 0 for the other blocks of this GPU
+    unsigned int* lflag;       // [2] epoch of the republished sums
 };
 
 constexpr int kStatsDoubles = 40;   // per outer iteration on the device: n_corr, lm_iters, cost, 27, pose7, pad
@@ -146,6 +148,7 @@ struct liliom_ctx {
     void* nccl_comm = nullptr;
     int nranks = 1, rank = 0;
     float shard_inv_block = 0.0625f;     // 1 / shard block edge (LILIOM_SHARD_BLOCK, metres, power of two; must agree on all ranks)
+    lili::DevBuf peer_local;             // block 0 -> other blocks of this GPU: [2][32] doubles + 2 epoch words (fused exchange)
     lili::DevBuf peer_buf;               // this rank's exchange buffer: [2 parities][kMaxPeers][32] {epoch|lo32, epoch|hi32}
     void* peer_ptrs[lili::kMaxPeers] = {};   // every rank's buffer as mapped into this process (cudaIpcOpenMemHandle)
     bool peer_ready = false;

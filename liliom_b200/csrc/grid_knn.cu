@@ -517,6 +517,28 @@ __device__ __forceinline__ void peer_exchange(const PeerArgs& pa, unsigned int e
     __syncthreads();
 }
 
+// Inside one GPU only block 0 talks to the peers: it republishes the sums over all ranks (and the loss flag) for the other
+// blocks, which wait on one epoch word instead of polling nranks x 29 system-scope words each (148 blocks doing that cost
+// ~20 us per pass on 2 GPUs, profiles/r02_bench_2gpu_first.json).
+__device__ __forceinline__ void peer_local_publish(const PeerArgs& pa, unsigned int epoch, KnnSmem& S) {
+    double* dst = pa.lsum + (size_t)(epoch & 1u) * 32;
+    if (threadIdx.x < kNormEq) dst[threadIdx.x] = S.red[0][threadIdx.x];
+    if (threadIdx.x == kNormEq) dst[kNormEq] = S.peer_lost ? 1.0 : 0.0;
+    __syncthreads();
+    if (threadIdx.x == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(pa.lflag + (epoch & 1u)), "r"(epoch) : "memory");
+}
+__device__ __forceinline__ void peer_local_wait(const PeerArgs& pa, unsigned int epoch, KnnSmem& S) {
+    if (threadIdx.x == 0) {
+        unsigned int v;
+        do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(pa.lflag + (epoch & 1u)) : "memory"); } while (v != epoch);
+    }
+    __syncthreads();
+    const double* src = pa.lsum + (size_t)(epoch & 1u) * 32;
+    if (threadIdx.x < kNormEq) S.red[0][threadIdx.x] = __ldcg(src + threadIdx.x);
+    if (threadIdx.x == kNormEq && __ldcg(src + kNormEq) != 0.0) S.peer_lost = 1;
+    __syncthreads();
+}
+
 // One thread: 6x6 solve of the reduced normal equations in S.red[0], Plus, sign-unify -> xn.
 __device__ __forceinline__ void gn_step(const KnnSmem& S, const Q4& q, const D3& t, double xn[7]) {
     double s[kNormEq];
@@ -705,48 +727,43 @@ __global__ void LILI_GN_BOUNDS k_gn_persistent(KnnArgs a, int iters, unsigned in
         if (stamp) a.dbg[16] = clock64();
         knn_phases<LANES>(a, q, t, n_q, S, acc, cand, it > 0, keep ? &f_keep : nullptr);
         if (stamp) a.dbg[17] = clock64();
-        if (sync_mode == 3 || sync_mode == 1) {
-            // ---- counter barrier with the minimum of fences (default; measured 12.70 -> 11.99 us per pass against mode 0):
-            // one release by thread 0 after the block barrier (cumulative over bar.sync, as in cooperative groups' grid.sync;
-            // SASS: MEMBAR.ALL.GPU + RED, no L1 invalidate) and NO acquire fence after the poll.  An acquire (mode 0's
-            // __threadfence: MEMBAR.SC + CCTL.IVALL) would only add an L1 invalidation: everything this kernel reads through
-            // L1 (map, cell table, features) is immutable for the launch, and the partials are read with L2-scope loads
-            // (__ldcg) issued after the poll's control dependency and a bar.sync.  The PTX model formally asks for the acquire;
-            // LILIOM_GN_SYNC=0 restores it, and tests/test_gpu_variants.py pins both to the same bits.
-            write_block_partials(a, S, acc, cand);
-            __syncthreads();
-            if (stamp) a.dbg[18] = clock64();
-            if (threadIdx.x == 0) {
+        // ---- grid barrier + cross-block sum.  Mode 3 (default; measured 12.70 -> 11.99 us per pass against mode 0): one release by
+        // thread 0 after the block barrier (cumulative over bar.sync, as in cooperative groups' grid.sync; SASS: MEMBAR.ALL.GPU +
+        // RED, no L1 invalidate) and NO acquire fence after the relaxed poll.  An acquire would only add an L1 invalidation:
+        // everything this kernel reads through L1 (map, cell table, features) is immutable for the launch, and the partials are
+        // read with L2-scope loads (__ldcg) issued after the poll's control dependency and a bar.sync.  The PTX model formally
+        // asks for the acquire: mode 1 polls with ld.acquire (+5 % per pass, profiles/r02_ab_gn_switches.txt), mode 0 fences both
+        // sides; tests pin all three to the same bits (test_gpu_variants.py, test_persistent_barrier_stress_all_sync_modes).
+        // Multi-GPU (fused exchange): the other blocks of this GPU arrive but do not wait here — they wait for block 0's
+        // republished sums over all ranks.
+        const bool follower = pa.enabled && blockIdx.x != 0;
+        write_block_partials(a, S, acc, cand);
+        if (sync_mode == 0) __threadfence();
+        __syncthreads();
+        if (stamp) a.dbg[18] = clock64();
+        if (threadIdx.x == 0) {
+            const unsigned int target = bar_base + (unsigned int)(it + 1) * G;
+            unsigned int v;
+            if (sync_mode == 0) {
+                atomicAdd(bar, 1u);
+                if (!follower) { while ((int)(*reinterpret_cast<volatile unsigned int*>(bar) - target) < 0) { } __threadfence(); }
+            } else {
                 asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(bar), "r"(1u) : "memory");
-                const unsigned int target = bar_base + (unsigned int)(it + 1) * G;
-                unsigned int v;
-                if (sync_mode == 1) {       // formally complete: the poll is an acquire load (pairs with the release RED), bar.sync orders the block behind it
-                    do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory"); } while ((int)(v - target) < 0);
-                } else {
-                    do { asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory"); } while ((int)(v - target) < 0);
+                if (!follower) {
+                    if (sync_mode == 1) { do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory"); } while ((int)(v - target) < 0); }
+                    else { do { asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory"); } while ((int)(v - target) < 0); }
                 }
             }
-            __syncthreads();
-            if (stamp) a.dbg[19] = clock64();
-            reduce_partials(a, S);
-        } else {
-            write_block_partials(a, S, acc, cand);
-            // ---- grid barrier (generation counter; all blocks are co-resident: cooperative launch)
-            __threadfence();
-            __syncthreads();
-            if (stamp) a.dbg[18] = clock64();
-            if (threadIdx.x == 0) {
-                // monotonic arrival counter: no generation read, no reset inside the loop — one fire-and-forget RED plus polls
-                atomicAdd(bar, 1u);
-                const unsigned int target = bar_base + (unsigned int)(it + 1) * G;
-                while ((int)(*reinterpret_cast<volatile unsigned int*>(bar) - target) < 0) { }
-                __threadfence();
-            }
-            __syncthreads();
-            if (stamp) a.dbg[19] = clock64();
-            reduce_partials(a, S);
         }
-        if (pa.enabled) peer_exchange(pa, pa.epoch0 + (unsigned int)it, S, blockIdx.x == 0);     // multi-GPU: this rank's sums -> sums over all ranks
+        if (!follower) {
+            __syncthreads();
+            if (stamp) a.dbg[19] = clock64();
+            reduce_partials(a, S);
+            if (pa.enabled) {       // block 0: this rank's sums -> sums over all ranks, then on to the other blocks
+                peer_exchange(pa, pa.epoch0 + (unsigned int)it, S, true);
+                peer_local_publish(pa, pa.epoch0 + (unsigned int)it, S);
+            }
+        } else peer_local_wait(pa, pa.epoch0 + (unsigned int)it, S);
         if (stamp) a.dbg[20] = clock64();
         double* stats = stats_base ? stats_base + (size_t)it * kStatsDoubles : nullptr;
         if (threadIdx.x == 0) {
@@ -1160,6 +1177,7 @@ int s2m_run(liliom_ctx* c, double pose7[7], int match_cnt, int max_num_iter, int
         if (peer) {
             for (int p = 0; p < c->nranks; ++p) pa.buf[p] = reinterpret_cast<ulonglong2*>(c->peer_ptrs[p]);
             pa.nranks = c->nranks; pa.rank = c->rank; pa.enabled = 1;
+            pa.lsum = c->peer_local.as<double>(); pa.lflag = reinterpret_cast<unsigned int*>(c->peer_local.as<double>() + 64);
             pa.epoch0 = c->peer_epoch + 1u;          // every rank makes the same sequence of calls: same epochs everywhere
             c->peer_epoch += (unsigned int)iters;
         }

@@ -1,6 +1,6 @@
 """Host-side statement of the multi-GPU partition rule implemented in csrc/ (knn_core.cuh
-`owner_of`, api.cu `k_shard_flags`): space is cut into 16 m blocks, a block belongs to rank
-hash(block) % nranks, a query is processed by the owner of the block its transformed position
+`owner_of`, api.cu `k_shard_flags`): space is cut into 16 m blocks (shifted by half a block in z), a block belongs to rank
+(bx + 3 by + 5 bz) mod nranks, a query is processed by the owner of the block its transformed position
 falls in, and a rank's map shard holds every point whose +-halo box touches a block it owns (so the
 query's whole 1 m search ball is local).  Used by bench.py to report shard sizes and by the gloo tests."""
 from __future__ import annotations
@@ -8,21 +8,14 @@ from __future__ import annotations
 import numpy as np
 
 
-def _block_hash(b: np.ndarray) -> np.ndarray:
-    b = b.astype(np.int64)
-    with np.errstate(over="ignore"):
-        h = ((b[..., 0].astype(np.uint32) * np.uint32(73856093)) ^ (b[..., 1].astype(np.uint32) * np.uint32(19349663))
-             ^ (b[..., 2].astype(np.uint32) * np.uint32(83492791))).astype(np.uint32)
-        h ^= h >> np.uint32(15)
-        h = (h * np.uint32(0x2c1b3c6d)).astype(np.uint32)
-        h ^= h >> np.uint32(12)
-    return h
-
-
 def owner_of(xyz: np.ndarray, nranks: int, block: int = 16) -> np.ndarray:
+    """knn_core.cuh::owner_of: cube coordinates (z shifted by half an edge), linear hash bx + 3 by + 5 bz mod nranks."""
     xyz = np.asarray(xyz, np.float32)
-    b = np.floor(xyz * np.float32(1.0 / block)).astype(np.int32)
-    return (_block_hash(b) % np.uint32(nranks)).astype(np.int32)
+    inv = np.float32(1.0 / block)
+    bx = np.floor(xyz[..., 0] * inv).astype(np.int64)
+    by = np.floor(xyz[..., 1] * inv).astype(np.int64)
+    bz = np.floor(xyz[..., 2] * inv + np.float32(0.5)).astype(np.int64)
+    return np.mod(bx + 3 * by + 5 * bz, nranks).astype(np.int32)
 
 
 def shard_mask(xyz: np.ndarray, nranks: int, rank: int, halo: float = 1.0, block: int = 16) -> np.ndarray:
