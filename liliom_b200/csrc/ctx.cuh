@@ -132,8 +132,6 @@ struct liliom_ctx {
     lili::DevBuf feats;                  // float4 body-frame queries
     int n_feats = 0;
     lili::DevBuf corr_valid, corr_plane, nn_idx, nn_sqd;
-    lili::DevBuf slots_buf;              // search -> fit hand-off of the two-kernel path (48 B per query)
-    bool knn_search_smem_set = false, knn_fused = false;   // LILIOM_KNN_FUSED=1: one kernel for search + fit also for large query sets (A/B)
     lili::DevBuf qstate;                 // float4 per query: transformed position + fifth distance of the previous GN pass
     lili::DevBuf pose_dev;               // 7 doubles (current) + 7 (candidate)
     lili::DevBuf partials;               // grid x 29 doubles

@@ -185,8 +185,6 @@ struct KnnArgs {
     long long* dbg;                     // optional phase timestamps (LILIOM_DEBUG_TIMING)
     int interleave;                     // 1: deal tasks to warps block-cyclically (load balance for small scans)
     float tau0;                         // largest fp32 distance inside the gate (knn_gate_tau(max_sqd)): search pruning threshold
-    struct Slot* slots_g;               // large query sets: hand-off between the search kernel and the fit kernel, 48 B per query
-    int fit_only;                       // 1: phase A is skipped, the slots come from slots_g (written by k_knn_search1)
     float4* qstate;                     // per query {transformed position, fifth distance} of the previous pass of this call (see coherence_tau)
     int use_state;                      // 1: qstate holds the previous pass (per-iteration launches; the persistent kernel sets it per pass)
     float inv_block;                    // 1 / shard block edge (multi-GPU ownership)
@@ -275,16 +273,6 @@ __device__ __forceinline__ void knn_phases(const KnnArgs& a, const Q4& q, const 
 #pragma unroll 1
     for (int task = gw; task < ntasks; task += nw) {
         // ---------------- phase A: cooperative exact 5-NN, one query per lane group per round
-        if (a.fit_only) {      // (LANES == 1 only) searched by k_knn_search1: 48 B per query, three 16-byte loads
-            if (lane < per_task) {
-                const int qi = task * per_task + lane;
-                if (qi < n_q) {
-                    const int4* src = reinterpret_cast<const int4*>(a.slots_g + qi);
-                    int4* dst = reinterpret_cast<int4*>(&S.slots[warp][lane]);
-                    dst[0] = __ldcg(src); dst[1] = __ldcg(src + 1); dst[2] = __ldcg(src + 2);
-                }
-            }
-        } else
 #pragma unroll 1
         for (int r = 0; r < a.rounds; ++r) {
             const int slot = r * GROUPS + grp;
@@ -575,57 +563,10 @@ __device__ __forceinline__ void write_neq_stats(const KnnArgs& a, const KnnSmem&
 }
 
 
-// ---- large query sets: search and fit as two kernels.  The one-thread-per-query search is bound by latency per issued
-// instruction (8.8 cycles at ~4 resident warps per scheduler in the fused kernel, whose 128 registers are set by the fp64 fit:
-// profiles/r02_knn_dense_v1_ncu.txt); on its own it needs half the registers, so twice the warps are resident.  It leaves
-// {5 neighbour indices, transformed query, body-frame query} per query for the fit kernel (k_knn_plane<1> with fit_only).
-#ifndef LILI_SEARCH_MINBLOCKS
-#define LILI_SEARCH_MINBLOCKS 4
-#endif
-__global__ void __launch_bounds__(kBlock, LILI_SEARCH_MINBLOCKS) k_knn_search1(KnnArgs a) {
-    extern __shared__ __align__(16) unsigned char dyn_smem[];      // [kRunCap][kBlock] int4 run lists (thread_knn5)
-    int4* runs = reinterpret_cast<int4*>(dyn_smem) + threadIdx.x;
-    const int n_q = a.n_dev ? min(*a.n_dev, a.n) : a.n;
-    unsigned long long cand = 0;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int ntasks = (n_q + 31) / 32;
-#pragma unroll 1
-    for (int task = (int)blockIdx.x * kWarps + warp; task < ntasks; task += (int)gridDim.x * kWarps) {
-        const int qi = task * 32 + lane;
-        if (qi >= n_q) continue;
-        const float4 f = a.feats[qi];
-        float sx, sy, sz;
-        {   // the pose is re-read per task (14 registers that would otherwise stay live through the search)
-            const double* pp = a.pose;
-            const Q4 q{__ldg(pp), __ldg(pp + 1), __ldg(pp + 2), __ldg(pp + 3)};
-            const D3 pw = qrot_x(q, D3{(double)f.x, (double)f.y, (double)f.z});             // L/src/LidarOdometry.cpp:230-231
-            sx = (float)addx(pw.x, __ldg(pp + 4)); sy = (float)addx(pw.y, __ldg(pp + 5)); sz = (float)addx(pw.z, __ldg(pp + 6));   // :236-238
-        }
-        const bool live = !(a.nranks > 1 && owner_of(sx, sy, sz, a.nranks, a.inv_block) != a.rank);
-        Top5 top;
-        top5_init(top);
-        if (live) {
-            cand += 1ull << kCandBits;
-            const float tau_q = a.use_state ? coherence_tau(__ldcg(a.qstate + qi), sx, sy, sz, a.tau0) : a.tau0;
-            thread_knn5<4, 4>(sx, sy, sz, a.map, a.cell_start, a.g, tau_q, runs, kBlock, top, cand);
-        }
-        const bool ok = live && top.k4 != ~0ull && ((double)top5_dist(top.k4) < a.max_sqd);  // :365
-        a.qstate[qi] = make_float4(sx, sy, sz, ok ? top5_dist(top.k4) : __int_as_float(0x7f800000));
-        int4* dst = reinterpret_cast<int4*>(a.slots_g + qi);
-        dst[0] = make_int4(ok ? top5_index(top.k0) : -1, top5_index(top.k1), top5_index(top.k2), top5_index(top.k3));
-        dst[1] = make_int4(top5_index(top.k4), __float_as_int(sx), __float_as_int(sy), __float_as_int(sz));
-        dst[2] = make_int4(__float_as_int(f.x), __float_as_int(f.y), __float_as_int(f.z), 0);
-    }
-    if (a.cand_total) {      // instrumentation: one pair of atomics per warp
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) cand += __shfl_xor_sync(0xffffffffu, cand, o);
-        if (lane == 0) {
-            if (cand & kCandMask) atomicAdd(a.cand_total, cand & kCandMask);
-            if (cand >> kCandBits) atomicAdd(a.queries_total, cand >> kCandBits);
-        }
-    }
-}
-
+// (Search and fit as two kernels — the search alone runs at 64 registers and twice the resident warps — was measured twice,
+// with the exhaustive search of round 1 and with the pruned one: 62.3 vs 57.6 us per pass at 128k queries.  The search
+// alone takes 32 us at 47 % lane utilisation; what limits the one-thread-per-query shape is divergence between the lanes'
+// candidate lists, not latency hiding.  profiles/r02_knn_dense_split_ab.txt, r02_knn_search_only_ncu.txt.)
 // Blocks per SM of the one-thread-per-query instance: that shape is bound by latency per issued instruction (8.8 cycles at
 // ~4 warps per scheduler, profiles/r02_knn_dense_v1_ncu.txt), so it trades registers (spills in the fp64 fit) for resident warps.
 #ifndef LILI_KNN1_MINBLOCKS
@@ -1203,17 +1144,6 @@ int s2m_run(liliom_ctx* c, double pose7[7], int match_cnt, int max_num_iter, int
         }
     }
     const int launches = persistent ? 0 : ((iters == 0 && want_corr) ? 1 : iters);
-    // one thread per query: search and fit as two kernels (see k_knn_search1), unless the test hook wants the neighbour lists
-    const bool split = lanes == 1 && !want_corr && !persistent && !c->knn_fused;
-    if (split) {
-        LILI_CUDA(c, c->slots_buf.ensure((size_t)(n > 0 ? n : 1) * sizeof(Slot)));
-        if (!c->knn_search_smem_set) {
-            LILI_CUDA(c, cudaFuncSetAttribute((const void*)k_knn_search1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
-            c->knn_search_smem_set = true;
-        }
-    }
-    a.slots_g = split ? c->slots_buf.as<Slot>() : nullptr;
-    a.fit_only = 0;
     for (int it = 0; it < launches; ++it) {
         a.stats = c->stats_dev.as<double>() + (size_t)it * kStatsDoubles;
         a.use_state = it > 0 ? 1 : 0;
@@ -1236,15 +1166,7 @@ int s2m_run(liliom_ctx* c, double pose7[7], int match_cnt, int max_num_iter, int
             ev = c->ev_used; c->ev_used += 2;
             LILI_CUDA(c, cudaEventRecord(c->ev_pool[ev], c->stream));
         }
-        if (split) {
-            KnnArgs sa = a;
-            k_knn_search1<<<min(cdiv(cdiv(n, 32), kWarps), c->sm_count * LILI_SEARCH_MINBLOCKS), kBlock, dyn_smem, c->stream>>>(sa);
-            LILI_TRY(launch_check(c, "k_knn_search1"));
-            KnnArgs fa = a;
-            fa.fit_only = 1;
-            fa.cand_total = nullptr; fa.queries_total = nullptr;      // counted by the search kernel
-            k_knn_plane<1><<<grid, kBlock, dyn_smem, c->stream>>>(fa, pit);
-        } else if (lanes == 16) k_knn_plane<16><<<grid, kBlock, 0, c->stream>>>(a, pit);
+        if (lanes == 16) k_knn_plane<16><<<grid, kBlock, 0, c->stream>>>(a, pit);
         else if (lanes == 1) k_knn_plane<1><<<grid, kBlock, dyn_smem, c->stream>>>(a, pit);
         else if (lanes == 2) k_knn_plane<2><<<grid, kBlock, 0, c->stream>>>(a, pit);
         else if (lanes == 4) k_knn_plane<4><<<grid, kBlock, 0, c->stream>>>(a, pit);
