@@ -507,21 +507,33 @@ def bench_body(args, fallback_note=None):
             dist.barrier()
         torch.cuda.synchronize()
 
+    cx_phase_ms = {}
+
     def make_steps(cx):
         """The two step functions on context cx.  Streamed workload: the frame pushed is always the one the FIFO is about to
         drop (push number p re-pushes frame p % N_FRAMES, counted per context over ALL steps, warm-up included), so the
         map's content — and the step's work — stay constant."""
         pushes = [0]
+        phase_ms = cx_phase_ms.setdefault(id(cx), [0.0, 0.0, 0.0, 0.0, 0])      # extract, odometry, push, rebuild, steps (event-timed)
 
         def step_resident(k):
             sw = sweeps[k % len(sweeps)]
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)] if stream_wl else None
+            if ev: ev[0].record(stream)
             cx.extract_resident(sw["q"])
+            if ev: ev[1].record(stream)
             pose, st, nds = cx.odometry_resident(sw["guess"], ITERS, mode=L.MODE_GN, want_stats=False)
             if stream_wl:
+                ev[2].record(stream)
                 fd = frames_dev[pushes[0] % N_FRAMES]
                 pushes[0] += 1
                 cx.map_push_frame_device(fd.data_ptr(), fd.numel() // psz, ident)
+                ev[3].record(stream)
                 cx.map_rebuild()
+                ev[4].record(stream); ev[4].synchronize()
+                for i in range(4):
+                    phase_ms[i] += ev[i].elapsed_time(ev[i + 1])
+                phase_ms[4] += 1
             return pose, nds
 
         def step_e2e(k):
@@ -627,7 +639,12 @@ def bench_body(args, fallback_note=None):
     # ---- timed region 1: device-resident; counters cover exactly the timed steps
     cnt_box = {}
     with ClockSampler(local_rank, enabled=(rank == 0)) as clk:
-        ms_res_local, last = timed(step_resident, steps, warmup, prep_for(ctx), after_warmup=lambda: ctx.counters(reset=True))
+        def after_warm():
+            ctx.counters(reset=True)
+            for v in cx_phase_ms.values():
+                v[:] = [0.0, 0.0, 0.0, 0.0, 0]
+        ms_res_local, last = timed(step_resident, steps, warmup, prep_for(ctx), after_warmup=after_warm)
+        phases_main = list(cx_phase_ms.get(id(ctx), [0, 0, 0, 0, 0]))
         cnt = ctx.counters(reset=True)
         # C-bar of the LAST timed scan's queries at its start pose, while they are still resident (the later legs replace them)
         blk = ctx.knn_block_stats(sweeps[(steps - 1) % len(sweeps)]["guess"])
@@ -749,8 +766,11 @@ def bench_body(args, fallback_note=None):
                 s1_res, _ = make_steps(c1)
                 k1 = max(3, min(steps, 20))
                 ms1, last1 = timed(s1_res, k1, 3, prep_for(c1), collective=False)
+                ph1 = cx_phase_ms.get(id(c1), [0, 0, 0, 0, 0])
                 c1.close()
                 same1 = {"value": k1 / (ms1 * 1e-3), "unit": "scans/s", "ms_per_step": ms1 / k1, "steps": k1,
+                         "step_breakdown_ms": ({k: ph1[i] / ph1[4] for i, k in enumerate(("extract", "scan_vg_and_gn", "push_frame", "map_rebuild"))}
+                                               if ph1[4] else None),
                          "pose_max_abs_diff_vs_sharded": float(np.abs(np.asarray(last1[0]) - np.asarray(last[0])).max())
                          if (k1 - 1) % len(sweeps) == (steps - 1) % len(sweeps) else None,
                          "what": "the same streamed workload (full map, no sharding) on ONE GPU, measured by rank 0 in this run"}
@@ -821,6 +841,8 @@ def bench_body(args, fallback_note=None):
         "cpu_baseline": cpu,
         "pose_err_m": float(np.linalg.norm(np.asarray(pose)[4:] - sweeps[(steps - 1) % len(sweeps)]["T"][4:])),
     }
+    if stream_wl and phases_main[4]:
+        line["step_breakdown_ms"] = {k: phases_main[i] / phases_main[4] for i, k in enumerate(("extract", "scan_vg_and_gn", "push_frame", "map_rebuild"))}
     if multi:
         line["ms_per_step_ranks"] = {"min": min(per_rank), "median": float(np.median(per_rank)), "max": max(per_rank), "all": per_rank}
     if sharded:
