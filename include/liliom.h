@@ -223,6 +223,12 @@ int liliom_extract_horizon_livox(liliom_ctx* c, const void* custom_pts, int n, i
                                  liliom_pt48* edge_out, int edge_cap, int* n_edge,
                                  liliom_pt48* cutted_out, int cut_cap, int* n_cut);
 
+/* ---- LidarOdometry::undistortion on the device (L/src/LidarOdometry.cpp:178-199) ----
+ * Moves every point of a keyframe cloud (point_stride bytes per point, in place) to the end of the sweep:
+ * p' = slerp(I, quat; ratio) * p + ratio * trans, ratio = min(frac(intensity) / 0.1, 1).  publishCloudLast (:624-632) calls it
+ * on the three keyframe clouds with quat = identity and trans = the relative translation of the scan. */
+int liliom_undistort(liliom_ctx* c, void* pts_inout, int n, const double trans[3], const double quat_wxyz[4]);
+
 /* ---- SURVEY §8 (f3), publishing side: the PointCloud2 layout pcl::toROSMsg gives these clouds ----
  * L/src/Preprocessing.cpp:385-401, L/src/LidarOdometry.cpp:634-649: pcl::toROSMsg copies the point array verbatim into
  * sensor_msgs::PointCloud2::data (point_step = sizeof(PointT), is_dense as in the cloud, height 1) and lists the fields

@@ -60,7 +60,7 @@ EXPORTS = [
     "liliom_map_set_cloud", "liliom_correspond_surf_refl",
     "liliom_backend_edge_block", "liliom_backend_surf_block", "liliom_convert_livox", "liliom_extract_horizon_livox",
     "liliom_pc2_layout", "liliom_comm_peer_export", "liliom_comm_peer_attach",
-    "liliom_map_push_frame_device", "liliom_knn_block_stats", "liliom_comm_set_shard_block",
+    "liliom_map_push_frame_device", "liliom_knn_block_stats", "liliom_comm_set_shard_block", "liliom_undistort",
 ]
 NODE_EXPORTS = ["liliom_pre_create", "liliom_pre_destroy", "liliom_pre_imu", "liliom_pre_cloud",
                 "liliom_lo_create", "liliom_lo_destroy", "liliom_lo_edge", "liliom_lo_surf", "liliom_lo_full", "liliom_lo_run"]
@@ -145,6 +145,7 @@ def lib() -> C.CDLL:
     L.liliom_comm_peer_attach.argtypes = [vp, vp, C.c_int, C.c_int]
     L.liliom_map_push_frame_device.argtypes = [vp, vp, C.c_int, dp]
     L.liliom_comm_set_shard_block.argtypes = [vp, C.c_int]
+    L.liliom_undistort.argtypes = [vp, vp, C.c_int, dp, dp]
     L.liliom_knn_block_stats.argtypes = [vp, dp, C.POINTER(C.c_ulonglong)]
     L.liliom_pre_create.argtypes = [vp, C.c_int, dp]; L.liliom_pre_create.restype = vp
     L.liliom_pre_destroy.argtypes = [vp]; L.liliom_pre_destroy.restype = None
@@ -263,6 +264,13 @@ class Context:
         """push_frame from a DEVICE buffer of n points (point_stride bytes each), e.g. a torch CUDA tensor's data_ptr()."""
         p = np.asarray(pose7, dtype=np.float64)
         self._check(lib().liliom_map_push_frame_device(self._h, C.c_void_p(dev_ptr), n, _dptr(p)))
+
+    def undistort(self, pts: np.ndarray, trans, quat=(1.0, 0.0, 0.0, 0.0)) -> np.ndarray:
+        """LidarOdometry::undistortion on the device; returns the moved copy."""
+        out = np.ascontiguousarray(pts, dtype=self.dtype).copy()
+        t = np.asarray(trans, dtype=np.float64); q = np.asarray(quat, dtype=np.float64)
+        self._check(lib().liliom_undistort(self._h, _ptr(out), len(out), _dptr(t), _dptr(q)))
+        return out
 
     def map_rebuild(self) -> int:
         m = C.c_int()

@@ -4,6 +4,7 @@
 #include "knn_core.cuh"
 #include <new>
 #include <cstdlib>
+#include <ctime>
 
 namespace lili {
 void nccl_destroy(liliom_ctx* c);
@@ -84,6 +85,25 @@ __global__ void k_concat_frames(const __grid_constant__ ConcatTab tab, int nfram
     int f = 0;
     for (int k = 1; k < nframes; ++k) if (i >= tab.off[k]) f = k;
     out[i] = tab.src[f][i - tab.off[f]];
+}
+
+// LidarOdometry::undistortion (L/src/LidarOdometry.cpp:178-199), in place on device points
+__global__ void k_undistort(unsigned char* __restrict__ pts, int n, int stride, D3 trans, Q4 quat) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4* p0 = reinterpret_cast<float4*>(pts + (size_t)i * stride);
+    float4 a = p0[0];
+    const float intensity = *reinterpret_cast<const float*>(pts + (size_t)i * stride + (stride == 48 ? 32 : 16));
+    const int line = (int)intensity;                                                    // :181
+    const double dt_i = (double)fsubx(intensity, (float)line);                         // :182 float - int -> float, then widened
+    double ratio_i = dt_i / 0.1;                                                        // :183
+    if (ratio_i > 1) ratio_i = 1;                                                       // :185-186
+    const Q4 q_si = qslerp_x(Q4{1.0, 0.0, 0.0, 0.0}, ratio_i, quat);                    // :188-189
+    const D3 r = qrot_x(q_si, D3{(double)a.x, (double)a.y, (double)a.z});               // :193
+    a.x = (float)addx(r.x, mulx(ratio_i, trans.x));                                    // :191, :193-197
+    a.y = (float)addx(r.y, mulx(ratio_i, trans.y));
+    a.z = (float)addx(r.z, mulx(ratio_i, trans.z));
+    p0[0] = a;
 }
 
 __global__ void k_gather_refl48(const unsigned char* __restrict__ pts, int n, float* __restrict__ out) {
@@ -388,6 +408,22 @@ extern "C" int liliom_voxelgrid(liliom_ctx* c, const void* pts, int n, int strid
     return LILIOM_OK;
 }
 
+// LidarOdometry::undistortion on the device (L/src/LidarOdometry.cpp:178-199; publishCloudLast :624-632)
+extern "C" int liliom_undistort(liliom_ctx* c, void* pts_inout, int n, const double trans[3], const double quat_wxyz[4]) {
+    if (!c || n < 0 || (n > 0 && !pts_inout) || !trans || !quat_wxyz) return LILIOM_E_ARG;
+    LILI_CUDA(c, cudaSetDevice(c->device));
+    if (n == 0) return LILIOM_OK;
+    const int stride = c->prm.point_stride;
+    LILI_CUDA(c, c->raw.ensure((size_t)n * stride));
+    LILI_CUDA(c, cudaMemcpyAsync(c->raw.p, pts_inout, (size_t)n * stride, cudaMemcpyHostToDevice, c->stream));
+    k_undistort<<<cdiv(n, 256), 256, 0, c->stream>>>((unsigned char*)c->raw.p, n, stride, D3{trans[0], trans[1], trans[2]},
+                                                    Q4{quat_wxyz[0], quat_wxyz[1], quat_wxyz[2], quat_wxyz[3]});
+    LILI_TRY(launch_check(c, "k_undistort"));
+    LILI_CUDA(c, cudaMemcpyAsync(pts_inout, c->raw.p, (size_t)n * stride, cudaMemcpyDeviceToHost, c->stream));
+    LILI_CUDA(c, cudaStreamSynchronize(c->stream));
+    return LILIOM_OK;
+}
+
 // ===================== L2: map =====================
 extern "C" int liliom_map_clear(liliom_ctx* c) {
     if (!c) return LILIOM_E_ARG;
@@ -469,6 +505,13 @@ extern "C" int liliom_map_rebuild(liliom_ctx* c, int* n_map_out) {
     if (!c) return LILIOM_E_ARG;
     LILI_CUDA(c, cudaSetDevice(c->device));
     const int stride = c->prm.point_stride;
+    // LILIOM_DEBUG_TIMING: wall clock of the phases (each closed by a stream sync), printed by rank 0
+    double tph[8] = {0};
+    int nph = 0;
+    auto mark = [&]() {
+        if (c->dbg_timing && nph < 8) { cudaStreamSynchronize(c->stream); timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); tph[nph++] = ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3; }
+    };
+    mark();
     size_t total = 0;
     for (auto& f : c->frames) total += (size_t)f.n;
     c->map_ready = false; c->map_n = 0; c->map_n_global = 0;
@@ -491,6 +534,7 @@ extern "C" int liliom_map_rebuild(liliom_ctx* c, int* n_map_out) {
         if (f.n) LILI_CUDA(c, cudaMemcpyAsync((unsigned char*)c->map_raw.p + off * stride, f.buf.p, (size_t)f.n * stride, cudaMemcpyDeviceToDevice, c->stream));
         off += (size_t)f.n;
     }
+    mark();      // [1] concatenation
     int m = 0;
     if (total > 0) {
         int* hp = reinterpret_cast<int*>(c->h_pin);
@@ -513,6 +557,7 @@ extern "C" int liliom_map_rebuild(liliom_ctx* c, int* n_map_out) {
         }
         m = hp[0];
     }
+    mark();      // [2] VoxelGrid
     LILI_CUDA(c, c->map_xyzw.ensure((size_t)(m > 0 ? m : 1) * sizeof(float4)));
     LILI_TRY(repack_to_f4(c, c->map_ds.p, m, stride, c->map_xyzw.as<float4>()));
     c->map_n_global = m;
@@ -520,6 +565,7 @@ extern "C" int liliom_map_rebuild(liliom_ctx* c, int* n_map_out) {
         // Every rank ENTERS the all-reduce whatever happened locally (a rank that returned early would leave its peers waiting
         // in the collective): the local status travels as a second scalar and all ranks fail together.
         const int rc_local = install_map_from_xyzw(c, m);          // drops the (possibly incomplete) voxels beyond the 1-cell halo
+        mark();  // [3] shard filter + cell grid
         // the "< 10 map points" guard (L/src/LidarOdometry.cpp:485-488) is about the whole map: sum the owned-voxel counts
         LILI_CUDA(c, c->neq.ensure(32 * sizeof(double)));
         double* pin = reinterpret_cast<double*>(c->h_pin) + 56;
@@ -534,6 +580,13 @@ extern "C" int liliom_map_rebuild(liliom_ctx* c, int* n_map_out) {
         c->map_n_global = (int)pin[2];                  // halo voxels are counted on several ranks: an upper bound >= the true size
     } else LILI_TRY(grid_build(c, m));
     LILI_CUDA(c, cudaStreamSynchronize(c->stream));
+    mark();      // [3 or 4] cell grid (single GPU) / map-size all-reduce (sharded)
+    if (c->dbg_timing && c->rank == 0 && nph >= 4) {
+        fprintf(stderr, "[liliom_map_rebuild, us] %zu raw points, %d voxels: concat %.0f, VoxelGrid %.0f, %s %.0f", total, m, tph[1] - tph[0], tph[2] - tph[1],
+                c->nranks > 1 ? "shard filter + grid" : "grid", tph[3] - tph[2]);
+        if (nph >= 5) fprintf(stderr, ", all-reduce %.0f", tph[4] - tph[3]);
+        fprintf(stderr, "\n");
+    }
     if (n_map_out) *n_map_out = m;
     return LILIOM_OK;
 }

@@ -218,20 +218,10 @@ void LidarOdometry::computeRelative() {
     rel_pose[4] = tr.x; rel_pose[5] = tr.y; rel_pose[6] = tr.z;
 }
 
-// :178-199 with quat = identity (:626): q_si = slerp(ratio, I) = I, so the point moves by ratio_i * trans
-void LidarOdometry::undistortion(std::vector<unsigned char>& cloud, int n, const Vec3& trans) {
-    const double dt = 0.1;
-    for (int i = 0; i < n; ++i) {
-        float* p = reinterpret_cast<float*>(cloud.data() + (size_t)i * stride);
-        const float intensity = (stride == 48) ? p[8] : p[4];
-        int line = int(intensity);
-        double dt_i = intensity - line;
-        double ratio_i = dt_i / dt;
-        if (ratio_i > 1) ratio_i = 1;
-        p[0] = (float)((double)p[0] + ratio_i * trans.x);
-        p[1] = (float)((double)p[1] + ratio_i * trans.y);
-        p[2] = (float)((double)p[2] + ratio_i * trans.z);
-    }
+// :178-199, called with quat = identity (:626); the per-point loop runs on the device (liliom_undistort)
+int LidarOdometry::undistortion(std::vector<unsigned char>& cloud, int n, const Vec3& trans) {
+    const double t[3] = {trans.x, trans.y, trans.z}, ident[4] = {1.0, 0.0, 0.0, 0.0};
+    return liliom_undistort(gpu, cloud.data(), n, t, ident);
 }
 
 int LidarOdometry::publishClouds(void* kf_edge, int edge_cap, int* n_edge, void* kf_surf, int surf_cap, int* n_surf, void* kf_full,
@@ -281,9 +271,9 @@ int LidarOdometry::run(liliom_lo_output* out, void* kf_edge, int edge_cap, int* 
         kf_num = (int)pose_info_cloud_frame.size();
         if (if_to_deskew) {                                                             // publishCloudLast :624-632
             Vec3 trans{rel_pose[4], rel_pose[5], rel_pose[6]};
-            undistortion(surf_features, n_surf_features, trans);
-            undistortion(edge_features, n_edge_features, trans);
-            undistortion(full_cloud, n_full_cloud, trans);
+            if ((rc = undistortion(surf_features, n_surf_features, trans)) != LILIOM_OK) return rc;
+            if ((rc = undistortion(edge_features, n_edge_features, trans)) != LILIOM_OK) return rc;
+            if ((rc = undistortion(full_cloud, n_full_cloud, trans)) != LILIOM_OK) return rc;
         }
         rc = publishClouds(kf_edge, edge_cap, n_edge, kf_surf, surf_cap, n_surf, kf_full, full_cap, n_full);
     }

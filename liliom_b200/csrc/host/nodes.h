@@ -56,7 +56,7 @@ private:
     int updateTransformation();          // downSampleCloud(scan) + updateTransformationWithCeres
     void savePoses();
     void computeRelative();
-    void undistortion(std::vector<unsigned char>& cloud, int n, const Vec3& trans);
+    int undistortion(std::vector<unsigned char>& cloud, int n, const Vec3& trans);
     int publishClouds(void* kf_edge, int edge_cap, int* n_edge, void* kf_surf, int surf_cap, int* n_surf, void* kf_full, int full_cap, int* n_full);
 
     liliom_ctx* gpu;

@@ -118,6 +118,8 @@ void orc_pose_compose(const double abs7[7], const double rel7[7], double out7[7]
 void orc_pose_relative(const double prev7[7], const double cur7[7], double rel7[7]);
 /* LidarOdometry.cpp:246-278 transformCloud (48 B: rotates normals; 32 B: xyz+intensity only) */
 void orc_transform_cloud(const void* in, int n, int stride, const double pose7[7], void* out);
+/* LidarOdometry::undistortion, L/src/LidarOdometry.cpp:178-199 (in place) */
+void orc_undistort(void* pts, int n, int stride, const double trans[3], const double quat_wxyz[4]);
 
 /* ---- test hooks for the from-knowledge third-party restatements (oracle_math.h) ---- */
 void orc_eigen_sym3(const double a_rowmajor[9], double eval[3], double evec_rowmajor[9]);

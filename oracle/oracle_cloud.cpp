@@ -262,6 +262,27 @@ void knn5_one(const void* tree, const float q[3], int idx[5], float sqd[5]) {
 }  // namespace orc
 
 // ---------------------------------------------------------------------------------------
+// LidarOdometry::undistortion — LiLi-OM/src/LidarOdometry.cpp:178-199: every point of a keyframe cloud is moved to the end of
+// the sweep, p' = slerp(I, quat; ratio) * p + ratio * trans with ratio = min(frac(intensity) / 0.1, 1).  In place; only
+// x, y, z change.  (publishCloudLast :624-632 calls it with quat = identity and trans = the relative translation.)
+// ---------------------------------------------------------------------------------------
+extern "C" void orc_undistort(void* pts, int n, int stride, const double trans[3], const double quat_wxyz[4]) {
+    const Quat quat{quat_wxyz[0], quat_wxyz[1], quat_wxyz[2], quat_wxyz[3]};
+    const double dt = 0.1;
+    for (int i = 0; i < n; ++i) {
+        float* p = reinterpret_cast<float*>((unsigned char*)pts + (size_t)i * stride);
+        const float intensity = stride == 48 ? p[8] : p[4];
+        const int line = int(intensity);
+        const double dt_i = intensity - line;
+        double ratio_i = dt_i / dt;
+        if (ratio_i > 1) ratio_i = 1;
+        const Quat q_si = qslerp(Quat{1, 0, 0, 0}, ratio_i, quat);
+        const V3 pt_s = qrot(q_si, V3{p[0], p[1], p[2]}) + V3{ratio_i * trans[0], ratio_i * trans[1], ratio_i * trans[2]};
+        p[0] = (float)pt_s.x; p[1] = (float)pt_s.y; p[2] = (float)pt_s.z;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // LidarOdometry::transformCloud — LiLi-OM/src/LidarOdometry.cpp:246-278 (48 B: rotates the
 // normal, copies intensity+curvature); LiLi-OM-ROT/src/LidarOdometry.cpp:239-264 (32 B).
 // ---------------------------------------------------------------------------------------

@@ -58,6 +58,7 @@ def lib():
         L.orc_pose_compose.argtypes = [dp, dp, dp]; L.orc_pose_compose.restype = None
         L.orc_pose_relative.argtypes = [dp, dp, dp]; L.orc_pose_relative.restype = None
         L.orc_transform_cloud.argtypes = [vp, C.c_int, C.c_int, dp, vp]; L.orc_transform_cloud.restype = None
+        L.orc_undistort.argtypes = [vp, C.c_int, C.c_int, dp, dp]; L.orc_undistort.restype = None
         L.orc_eigen_sym3.argtypes = [dp, dp, dp]; L.orc_eigen_sym3.restype = None
         L.orc_colpiv_qr_solve.argtypes = [C.c_int, dp, dp, dp]; L.orc_colpiv_qr_solve.restype = None
         L.orc_slerp_identity.argtypes = [dp, C.c_double, dp]; L.orc_slerp_identity.restype = None
@@ -187,6 +188,13 @@ def transform_cloud(pts, pose7):
     pts = np.ascontiguousarray(pts)
     out = np.zeros_like(pts)
     lib().orc_transform_cloud(_p(pts), len(pts), pts.dtype.itemsize, _d(np.asarray(pose7, np.float64)), _p(out))
+    return out
+
+
+def undistort(pts, trans, quat=(1.0, 0.0, 0.0, 0.0)):
+    out = np.ascontiguousarray(pts).copy()
+    t = np.asarray(trans, np.float64); q = np.asarray(quat, np.float64)
+    lib().orc_undistort(_p(out), len(out), out.dtype.itemsize, _d(t), _d(q))
     return out
 
 

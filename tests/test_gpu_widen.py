@@ -154,3 +154,27 @@ def test_widen_rows_against_golden_fixtures(oracle):
     cloud = c.convert_livox(lv["records"].view(L.LIVOX20).reshape(-1))
     assert cloud.view(np.uint8).tobytes() == lv["cloud"].tobytes()
     c.close()
+
+
+def test_undistortion_on_device(oracle, world_small):
+    """(f3) LidarOdometry::undistortion (L/src/LidarOdometry.cpp:178-199) through the C ABI: bit-exact with quat = identity
+    (how publishCloudLast calls it, :624-632), within one fp32 ulp for a general quaternion (fp64 acos/sin)."""
+    import liliom_b200 as L
+    surf, edge, cut = oracle.extract_horizon(world_small["hz"], world_small["q_hz"])
+    trans = np.array([0.27, -0.04, 0.015])
+    c = L.Context(variant=0)
+    for cloud in (cut, surf, edge, cut[:0]):
+        got, want = c.undistort(cloud, trans), oracle.undistort(cloud, trans)
+        assert got.view(np.uint8).tobytes() == want.view(np.uint8).tobytes()
+    quat = np.array([0.9992, 0.01, -0.03, 0.02])
+    got, want = c.undistort(cut, trans, quat), oracle.undistort(cut, trans, quat)
+    for f in ("x", "y", "z"):
+        np.testing.assert_allclose(got[f], want[f], rtol=2.5e-7, atol=1e-6)
+    for f in ("intensity", "curvature", "nx", "ny", "nz"):
+        assert np.array_equal(got[f].view(np.uint32), want[f].view(np.uint32))
+    c.close()
+    c32 = L.Context(variant=1)
+    hdl = world_small["hdl"][:20000].copy()
+    hdl["intensity"] = (np.arange(20000) % 64 + (np.arange(20000) % 97) / 970.0).astype(np.float32)
+    assert c32.undistort(hdl, trans).view(np.uint8).tobytes() == oracle.undistort(hdl, trans).view(np.uint8).tobytes()
+    c32.close()

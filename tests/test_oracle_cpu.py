@@ -814,3 +814,39 @@ def test_pose_glue_second_restatement(oracle):
     assert np.abs(np.stack([t["x"], t["y"], t["z"]], 1).view(np.int32) - ref_p.view(np.int32)).max() <= 1
     np.testing.assert_allclose(np.stack([t["nx"], t["ny"], t["nz"]], 1), ref_n, atol=1e-6)
     assert (t["intensity"] == 3.5).all() and (t["curvature"] == 1.25).all()
+
+
+def test_undistortion_matches_numpy_restatement(oracle):
+    """LidarOdometry::undistortion (L/src/LidarOdometry.cpp:178-199) restated in NumPy from the reference source: ratio =
+    min(frac(intensity)/0.1, 1); p' = slerp(I, quat; ratio) * p + ratio * trans.  With quat = identity (the only way the
+    reference calls it, :626) the oracle must agree bit for bit; with a general quaternion to one fp32 ulp (acos/sin)."""
+    rng = np.random.default_rng(12)
+    pts = np.zeros(4000, oracle.PT48)
+    pts["x"] = rng.uniform(-50, 50, 4000).astype(np.float32); pts["y"] = rng.uniform(-50, 50, 4000).astype(np.float32)
+    pts["z"] = rng.uniform(-3, 8, 4000).astype(np.float32)
+    pts["intensity"] = (rng.integers(0, 6, 4000) + rng.uniform(0, 0.13, 4000)).astype(np.float32)    # some ratios above 1: clamped
+    pts["curvature"] = rng.uniform(0, 1, 4000).astype(np.float32); pts["nx"] = 1.0
+    trans = np.array([0.31, -0.07, 0.02])
+    line = pts["intensity"].astype(np.int32)
+    ratio = np.minimum((pts["intensity"] - line.astype(np.float32)).astype(np.float64) / 0.1, 1.0)
+    got = oracle.undistort(pts, trans)
+    for k, f in enumerate(("x", "y", "z")):
+        want = (pts[f].astype(np.float64) + ratio * trans[k]).astype(np.float32)
+        assert np.array_equal(got[f].view(np.uint32), want.view(np.uint32)), f
+    for f in ("intensity", "curvature", "nx", "w"):
+        assert np.array_equal(got[f], pts[f])
+    # general quaternion: Rodrigues with angle ratio*theta about the quaternion's axis
+    half = 0.04
+    axis = np.array([0.2, -0.5, 0.84]); axis /= np.linalg.norm(axis)
+    quat = np.concatenate([[np.cos(half)], np.sin(half) * axis])
+    got = oracle.undistort(pts, trans, quat)
+    ang = 2 * half * ratio
+    p = np.stack([pts["x"], pts["y"], pts["z"]], 1).astype(np.float64)
+    rp = (p * np.cos(ang)[:, None] + np.cross(axis, p) * np.sin(ang)[:, None] + axis * (p @ axis)[:, None] * (1 - np.cos(ang))[:, None])
+    want = rp + ratio[:, None] * trans
+    for k, f in enumerate(("x", "y", "z")):
+        np.testing.assert_allclose(got[f], want[:, k].astype(np.float32), rtol=3e-7, atol=2e-6)
+    # 32-byte points carry the time in float #4
+    p32 = np.zeros(100, oracle.PT32); p32["x"] = 1.0; p32["intensity"] = 3.05
+    g32 = oracle.undistort(p32, trans)
+    assert np.array_equal(g32["x"], (1.0 + np.float64(np.float32(3.05) - np.float32(3.0)) / 0.1 * trans[0]).astype(np.float32) * np.ones(100, np.float32))
