@@ -75,16 +75,26 @@ __global__ void k_transform_cloud(const unsigned char* __restrict__ in, int n, i
     }
 }
 
-// Concatenation of the FIFO frames (L/src/LidarOdometry.cpp:301-302) in one launch: thread i copies the i-th 16-byte word of the
-// concatenated cloud; off[] are the frames' start offsets in 16-byte words (off[nframes] = total).
-constexpr int kConcatMax = 32;
-struct ConcatTab { const float4* src[kConcatMax]; int off[kConcatMax + 1]; };
-__global__ void k_concat_frames(const __grid_constant__ ConcatTab tab, int nframes, int n16, float4* __restrict__ out) {
+// Concatenation of the FIFO frames (L/src/LidarOdometry.cpp:301-302) in ONE launch: blockIdx.y = frame, the blocks of a row
+// stream that frame's 16-byte words to its offset in the concatenated cloud.  (20 cudaMemcpyAsync calls cost ~210 us whatever
+// the size — measured on B200 for both a 10 M-point map and its 5.4 M-point shard, profiles/r02_map_rebuild_phases_before.txt.)
+constexpr int kConcatMax = 64;
+struct ConcatTab { const float4* src[kConcatMax]; long long off[kConcatMax + 1]; };      // offsets in 16-byte words
+__global__ void k_concat_frames(const __grid_constant__ ConcatTab tab, float4* __restrict__ out) {
+    const int f = blockIdx.y;
+    const long long n16 = tab.off[f + 1] - tab.off[f];
+    const float4* __restrict__ src = tab.src[f];
+    float4* __restrict__ dst = out + tab.off[f];
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (long long)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+// sharded rebuild: the shard filter and the repack to float4 {x,y,z,index} in one pass over the VoxelGrid output
+__global__ void k_compact_repack(const unsigned char* __restrict__ in, const int* __restrict__ flags, const int* __restrict__ pos, int n, int stride,
+                                 float4* __restrict__ out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n16) return;
-    int f = 0;
-    for (int k = 1; k < nframes; ++k) if (i >= tab.off[k]) f = k;
-    out[i] = tab.src[f][i - tab.off[f]];
+    if (i >= n || !flags[i]) return;
+    float4 v = *reinterpret_cast<const float4*>(in + (size_t)i * stride);
+    v.w = __int_as_float(i);
+    out[pos[i]] = v;
 }
 
 // LidarOdometry::undistortion (L/src/LidarOdometry.cpp:178-199), in place on device points
@@ -521,13 +531,17 @@ extern "C" int liliom_map_rebuild(liliom_ctx* c, int* n_map_out) {
     LILI_CUDA(c, c->map_ds.ensure((total > 0 ? total : 1) * stride));
     LILI_CUDA(c, c->vg_count.ensure(16));
     size_t off = 0;
-    if (c->map_coop && c->frames.size() <= (size_t)kConcatMax && total > 0) {      // one gather launch instead of <= 20 small copies
+    if (c->frames.size() <= (size_t)kConcatMax && total > 0) {
         ConcatTab tab{};
         int k = 0;
-        for (auto& f : c->frames) { tab.src[k] = (const float4*)f.buf.p; tab.off[k] = (int)(off * (stride / 16)); off += (size_t)f.n; ++k; }
-        for (; k <= kConcatMax; ++k) tab.off[k] = (int)(off * (stride / 16));
-        const int n16 = (int)(total * (stride / 16));
-        k_concat_frames<<<cdiv(n16, 256), 256, 0, c->stream>>>(tab, (int)c->frames.size(), n16, (float4*)c->map_raw.p);
+        size_t largest = 0;
+        for (auto& f : c->frames) {
+            tab.src[k] = (const float4*)f.buf.p; tab.off[k] = (long long)(off * (stride / 16));
+            off += (size_t)f.n; largest = f.n > (int)largest ? (size_t)f.n : largest; ++k;
+        }
+        for (; k <= kConcatMax; ++k) tab.off[k] = (long long)(off * (stride / 16));
+        const int bx = max(1, min(cdiv((long long)largest * (stride / 16), 256 * 4), c->sm_count * 4));
+        k_concat_frames<<<dim3(bx, (unsigned)c->frames.size()), 256, 0, c->stream>>>(tab, (float4*)c->map_raw.p);
         LILI_TRY(launch_check(c, "k_concat_frames"));
     } else
     for (auto& f : c->frames) {                                                    // :301-302 concatenation, oldest first
@@ -559,12 +573,33 @@ extern "C" int liliom_map_rebuild(liliom_ctx* c, int* n_map_out) {
     }
     mark();      // [2] VoxelGrid
     LILI_CUDA(c, c->map_xyzw.ensure((size_t)(m > 0 ? m : 1) * sizeof(float4)));
-    LILI_TRY(repack_to_f4(c, c->map_ds.p, m, stride, c->map_xyzw.as<float4>()));
     c->map_n_global = m;
     if (c->nranks > 1) {
         // Every rank ENTERS the all-reduce whatever happened locally (a rank that returned early would leave its peers waiting
         // in the collective): the local status travels as a second scalar and all ranks fail together.
-        const int rc_local = install_map_from_xyzw(c, m);          // drops the (possibly incomplete) voxels beyond the 1-cell halo
+        // Shard filter: drops the (possibly incomplete) voxels beyond the 1-cell halo, fused with the repack to float4.
+        auto shard_and_index = [&]() -> int {
+            int local = 0;
+            if (m > 0) {
+                LILI_CUDA(c, c->flags.ensure(((size_t)m + 2) * 4));
+                LILI_CUDA(c, c->idx_a.ensure(((size_t)m + 2) * 4));
+                float cell = 1.0f;
+                while ((double)cell * (double)cell < c->prm.knn_max_sqdist) cell *= 2.0f;
+                k_shard_flags_strided<<<cdiv(m + 1, 256), 256, 0, c->stream>>>((const unsigned char*)c->map_ds.p, m, stride, cell, c->shard_inv_block, c->nranks,
+                                                                             c->rank, c->flags.as<int>());
+                LILI_TRY(launch_check(c, "k_shard_flags_strided"));
+                LILI_TRY(exclusive_scan_i32(c, c->flags.as<int>(), c->idx_a.as<int>(), m));
+                k_compact_repack<<<cdiv(m, 256), 256, 0, c->stream>>>((const unsigned char*)c->map_ds.p, c->flags.as<int>(), c->idx_a.as<int>(), m, stride,
+                                                                     c->map_xyzw.as<float4>());
+                LILI_TRY(launch_check(c, "k_compact_repack"));
+                int* hpl = reinterpret_cast<int*>(c->h_pin) + 1024;
+                LILI_CUDA(c, cudaMemcpyAsync(hpl, c->idx_a.as<int>() + m, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+                LILI_CUDA(c, cudaStreamSynchronize(c->stream));
+                local = hpl[0];
+            }
+            return grid_build(c, local);
+        };
+        const int rc_local = shard_and_index();
         mark();  // [3] shard filter + cell grid
         // the "< 10 map points" guard (L/src/LidarOdometry.cpp:485-488) is about the whole map: sum the owned-voxel counts
         LILI_CUDA(c, c->neq.ensure(32 * sizeof(double)));
@@ -578,7 +613,10 @@ extern "C" int liliom_map_rebuild(liliom_ctx* c, int* n_map_out) {
         if (rc_local != LILIOM_OK) return rc_local;
         if (pin[3] != 0.0) { c->map_ready = false; c->last_error = "liliom_map_rebuild failed on another rank"; return LILIOM_E_NCCL; }
         c->map_n_global = (int)pin[2];                  // halo voxels are counted on several ranks: an upper bound >= the true size
-    } else LILI_TRY(grid_build(c, m));
+    } else {
+        LILI_TRY(repack_to_f4(c, c->map_ds.p, m, stride, c->map_xyzw.as<float4>()));
+        LILI_TRY(grid_build(c, m));
+    }
     LILI_CUDA(c, cudaStreamSynchronize(c->stream));
     mark();      // [3 or 4] cell grid (single GPU) / map-size all-reduce (sharded)
     if (c->dbg_timing && c->rank == 0 && nph >= 4) {

@@ -1013,7 +1013,9 @@ static void pick_shape(int n, int sm_count, int& lanes, int& rounds) {
     const long long w8 = (long long)sm_count * 8;      // warps for ~8 per SM
     rounds = 1;
     if ((long long)n >= w8 * 32) { lanes = 1; return; }
-    if ((long long)n >= w8 * 8) { lanes = 4; rounds = ((long long)n >= w8 * 16) ? 2 : 1; return; }
+    // 9.5k..38k queries: two lanes per query (measured at 16k queries, profiles/r02_knn_lanes_sweep.txt: 20.8 us per pass with
+    // 2 lanes, 22.1 with 1, 27.2 with 4, 33.5 with 8)
+    if ((long long)n >= w8 * 8) { lanes = 2; return; }
     lanes = ((long long)n * 16 / 32 <= w8 * 2) ? 16 : 8;   // tiny scans: one run per lane (9 of 16 lanes)
 }
 
