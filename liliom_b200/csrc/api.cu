@@ -232,7 +232,6 @@ extern "C" int liliom_create(liliom_ctx** out, const liliom_params* p, int devic
     if (e != cudaSuccess) { cudaStreamDestroy(c->own_stream); delete c; return LILIOM_E_CUDA; }
     if (const char* e1 = getenv("LILIOM_KNN_LANES")) { int v = atoi(e1); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16) c->force_lanes = v; }
     c->dbg_timing = getenv("LILIOM_DEBUG_TIMING") != nullptr;
-    if (const char* e9 = getenv("LILIOM_MAP_COOP")) c->map_coop = atoi(e9) != 0;
     if (const char* e5 = getenv("LILIOM_GN_SYNC")) { int v = atoi(e5); if (v == 0 || v == 1 || v == 3) c->gn_sync = v; }
     if (const char* e4 = getenv("LILIOM_SHARD_BLOCK")) {      // shard block edge in metres (power of two, 8..256): larger blocks = thinner halos
         int v = atoi(e4);
@@ -552,19 +551,9 @@ extern "C" int liliom_map_rebuild(liliom_ctx* c, int* n_map_out) {
     int m = 0;
     if (total > 0) {
         int* hp = reinterpret_cast<int*>(c->h_pin);
-        // LILIOM_MAP_COOP=1 (opt-in until measured with tools/stream_bench.py): a 20-frame Horizon map (~30k points) fits the
-        // single-launch cooperative filter liliom_voxelgrid already uses for scan-sized clouds (same bits, ~12 launches fewer);
-        // it may decline (VgParams::bail), then the sort chain runs as before.
-        bool coop = false;
-        if (c->map_coop && c->nranks == 1)
-            LILI_TRY(voxelgrid_coop(c, c->map_raw.p, (int)total, nullptr, stride, c->prm.leaf_map, c->map_ds.p, c->vg_count.as<int>(), nullptr, &coop));
-        if (coop) {
-            LILI_CUDA(c, cudaMemcpyAsync(hp, c->vg_count.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-            LILI_CUDA(c, cudaMemcpyAsync(hp + 16, c->vg_params.p, sizeof(VgParams), cudaMemcpyDeviceToHost, c->stream));
-            LILI_CUDA(c, cudaStreamSynchronize(c->stream));
-            if (reinterpret_cast<const VgParams*>(hp + 16)->bail) coop = false;
-        }
-        if (!coop) {
+        // (The single-launch cooperative filter of the scan VoxelGrid was tried here for maps of <= 32k points: within the noise
+        // of the real-size streamed lifecycle, profiles/r02_stream_real_lifecycle_mapcoop_ab.txt — not kept.)
+        {
             LILI_TRY(voxelgrid_dev(c, c->map_raw.p, (int)total, stride, c->prm.leaf_map, c->map_ds.p, c->vg_count.as<int>()));   // :316-317
             LILI_CUDA(c, cudaMemcpyAsync(hp, c->vg_count.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
             LILI_CUDA(c, cudaStreamSynchronize(c->stream));

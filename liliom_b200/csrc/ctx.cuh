@@ -158,7 +158,6 @@ struct liliom_ctx {
     int force_lanes = 0, force_rounds = 0;   // tuning override (LILIOM_KNN_LANES / LILIOM_KNN_ROUNDS)
     int gn_sync = 3;                     // persistent GN kernel grid barrier (LILIOM_GN_SYNC): 3 = release-only arrival, no acquire fence (default),
                                          // 0 = full fences on both sides
-    bool map_coop = false;               // LILIOM_MAP_COOP=1: liliom_map_rebuild voxel-filters the 20-frame map with the cooperative single-launch filter
     bool dbg_timing = false;             // LILIOM_DEBUG_TIMING at create: stage clocks of the cooperative kernels, printed by s2m_run
     bool knn1_smem_set = false;          // dynamic shared memory limit raised for the one-thread-per-query kernels on this device
     std::vector<cudaEvent_t> ev_pool;
