@@ -159,6 +159,7 @@ struct liliom_ctx {
     int gn_sync = 3;                     // persistent GN kernel grid barrier (LILIOM_GN_SYNC): 3 = release-only arrival, no acquire fence (default),
                                          // 0 = full fences on both sides
     bool dbg_timing = false;             // LILIOM_DEBUG_TIMING at create: stage clocks of the cooperative kernels, printed by s2m_run
+    bool knn_tma = false, knn_tma_smem_set = false;   // LILIOM_KNN_TMA=1: bulk-copy (cp.async.bulk + mbarrier) staging of the runs in the 16-lane search
     bool knn1_smem_set = false;          // dynamic shared memory limit raised for the one-thread-per-query kernels on this device
     std::vector<cudaEvent_t> ev_pool;
     size_t ev_used = 0;

@@ -249,12 +249,15 @@ struct KnnSmem {
 
 // One pass over this block's share of the queries at pose (q,t): phases A (search), B (fit + row), C (lane k
 // accumulates scalar k).  On return lane k < 29 of every warp holds its partial of scalar k in `acc`.
-template <int LANES>
+template <int LANES, bool TMA = false>
 __device__ __forceinline__ void knn_phases(const KnnArgs& a, const Q4& q, const D3& t, const int n_q, KnnSmem& S,
-                                           double& acc, unsigned long long& cand, const bool use_state, const float4* fpre = nullptr) {
+                                           double& acc, unsigned long long& cand, const bool use_state, const float4* fpre = nullptr,
+                                           unsigned* stage_phase = nullptr) {
     constexpr int GROUPS = 32 / LANES;                 // queries a warp searches concurrently
     extern __shared__ __align__(16) unsigned char dyn_smem[];      // LANES == 1: [kRunCap][kBlock] int4 run lists (thread_knn5)
     int4* runs = reinterpret_cast<int4*>(dyn_smem) + threadIdx.x;
+    StageTile* stage = nullptr;                                    // TMA: [kWarps][2] staging tiles (bulk-copy path of the 16-lane search)
+    if constexpr (TMA) stage = reinterpret_cast<StageTile*>(dyn_smem) + (threadIdx.x >> 5) * 2 + ((threadIdx.x & 31) >> 4);
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int sub = lane & (LANES - 1);
@@ -295,7 +298,8 @@ __device__ __forceinline__ void knn_phases(const KnnArgs& a, const Q4& q, const 
             if (live) {
                 if (sub == 0) cand += 1ull << kCandBits;
                 if constexpr (LANES == 1) thread_knn5(sx, sy, sz, a.map, a.cell_start, a.g, tau_q, runs, kBlock, top, cand);
-                else group_knn5<LANES>(sx, sy, sz, a.map, a.cell_start, a.g, sub, gmask, tau_q, top, cand, (a.dbg && blockIdx.x == 0 && threadIdx.x == 0) ? a.dbg : nullptr);
+                else group_knn5<LANES>(sx, sy, sz, a.map, a.cell_start, a.g, sub, gmask, tau_q, top, cand, (a.dbg && blockIdx.x == 0 && threadIdx.x == 0) ? a.dbg : nullptr,
+                                       stage, stage_phase);
             }
             LILI_STAMP(11);
             if (sub == 0) {
@@ -632,10 +636,17 @@ __global__ void __launch_bounds__(kBlock, LANES == 1 ? LILI_KNN1_MINBLOCKS : 2) 
 #define LILI_GN_MAXNREG 176
 #endif
 #define LILI_GN_BOUNDS __maxnreg__(LILI_GN_MAXNREG)
-template <int LANES>
+template <int LANES, bool TMA = false>
 __global__ void LILI_GN_BOUNDS k_gn_persistent(KnnArgs a, int iters, unsigned int* bar, double* stats_base, unsigned int bar_base,
                                                              int sync_mode, const __grid_constant__ PeerArgs pa) {
     __shared__ __align__(16) KnnSmem S;
+    unsigned stage_phase = 0;
+    if constexpr (TMA) {       // one mbarrier per lane group, 16 arrivals (every lane of the group, with or without a run to stage)
+        extern __shared__ __align__(16) unsigned char dyn_smem_k[];
+        StageTile* tile = reinterpret_cast<StageTile*>(dyn_smem_k) + (threadIdx.x >> 5) * 2 + ((threadIdx.x & 31) >> 4);
+        if ((threadIdx.x & 15) == 0) mbar_init(&tile->bar, 16u);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     const int n_q = a.n_dev ? min(*a.n_dev, a.n) : a.n;
     if (threadIdx.x == 32) S.peer_lost = 0;
     if (threadIdx.x < 7) S.pose[threadIdx.x] = a.pose[threadIdx.x];
@@ -666,7 +677,7 @@ __global__ void LILI_GN_BOUNDS k_gn_persistent(KnnArgs a, int iters, unsigned in
         unsigned long long cand = 0;
         const bool stamp = a.dbg && blockIdx.x == 0 && threadIdx.x == 0 && it == 2;
         if (stamp) a.dbg[16] = clock64();
-        knn_phases<LANES>(a, q, t, n_q, S, acc, cand, it > 0, keep ? &f_keep : nullptr);
+        knn_phases<LANES, TMA>(a, q, t, n_q, S, acc, cand, it > 0, keep ? &f_keep : nullptr, &stage_phase);
         if (stamp) a.dbg[17] = clock64();
         // ---- grid barrier + cross-block sum.  Mode 3 (default; measured 12.70 -> 11.99 us per pass against mode 0): one release by
         // thread 0 after the block barrier (cumulative over bar.sync, as in cooperative groups' grid.sync; SASS: MEMBAR.ALL.GPU +
@@ -1125,7 +1136,16 @@ int s2m_run(liliom_ctx* c, double pose7[7], int match_cnt, int max_num_iter, int
             c->peer_epoch += (unsigned int)iters;
         }
         void* kargs[] = {&a, &iters_arg, &bar, &stats_base, &bar_base, &sync_mode, &pa};
-        const void* fn = lanes == 16 ? (const void*)k_gn_persistent<16> : lanes == 1 ? (const void*)k_gn_persistent<1>
+        const bool tma = lanes == 16 && c->knn_tma;
+        size_t dyn_p = dyn_smem;
+        if (tma) {
+            dyn_p = (size_t)kWarps * 2 * sizeof(StageTile);
+            if (!c->knn_tma_smem_set) {
+                LILI_CUDA(c, cudaFuncSetAttribute((const void*)k_gn_persistent<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_p));
+                c->knn_tma_smem_set = true;
+            }
+        }
+        const void* fn = tma ? (const void*)k_gn_persistent<16, true> : lanes == 16 ? (const void*)k_gn_persistent<16> : lanes == 1 ? (const void*)k_gn_persistent<1>
                        : lanes == 2 ? (const void*)k_gn_persistent<2> : lanes == 4 ? (const void*)k_gn_persistent<4>
                                                                                    : (const void*)k_gn_persistent<8>;
         size_t ev = 0;
@@ -1136,7 +1156,7 @@ int s2m_run(liliom_ctx* c, double pose7[7], int match_cnt, int max_num_iter, int
             ev = c->ev_used; c->ev_used += 2;
             LILI_CUDA(c, cudaEventRecord(c->ev_pool[ev], c->stream));
         }
-        LILI_CUDA(c, cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kBlock), kargs, dyn_smem, c->stream));
+        LILI_CUDA(c, cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kBlock), kargs, dyn_p, c->stream));
         LILI_TRY(launch_check(c, "k_gn_persistent"));
         c->bar_arrivals += (unsigned int)iters * (unsigned int)grid;
         if (c->time_kernels) {

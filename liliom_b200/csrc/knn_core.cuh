@@ -140,18 +140,79 @@ __device__ __forceinline__ bool row_cells(const QCell& q, const GridDesc& g, int
     return true;
 }
 
+// ---- bulk-asynchronous staging of a lane's run in shared memory (sm_90+/sm_100a: cp.async.bulk + mbarrier; SASS UBLKCP / SYNCS) ----
+// The 16-lane search gives every (y,z) row of the 27-cell block to one lane.  Instead of pulling its run through registers in
+// batches of eight 16-byte loads (a dependent L2 round trip per batch), a lane hands the whole run to the copy engine — one
+// cp.async.bulk of 16 x length bytes into its slot of the warp's staging tile — and the 16 lanes of the query meet at one
+// mbarrier whose transaction count is the sum of their run sizes; ranking then reads shared memory.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, unsigned parity) {
+    unsigned ok;
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+constexpr int kStageCap = 24;                 // candidates per staged run (longer runs finish through registers)
+constexpr int kStageRow = kStageCap + 1;      // row pitch in float4: 25 x 16 B = 100 words -> lane k starts at bank 4k (conflict-free 16-byte reads)
+struct StageTile {                            // one per lane group (query) of a warp
+    float4 pts[9][kStageRow];
+    unsigned long long bar;
+    unsigned long long pad;
+};
+
 // LANES (2, 4, 8 or 16) lanes — mask `gmask`, lane-in-group `sub` — search the 3x3x3 cell block around
 // (sx,sy,sz); lane `sub` walks rows sub, sub+LANES, ...  Each lane pulls its run in batches of independent 16-byte
 // loads (memory-level parallelism without occupancy), ranks them into a private sorted top-5, and the group merges with
 // 5 min-butterflies.  On return every lane of the group holds the merged top-5.
 // `cand` accumulates the number of map points this lane examined.
+// `stage` (16-lane shape only, may be null): the group's staging tile; `stage_phase` its mbarrier parity, flipped per use.
 template <int LANES, int BATCH = 8>
 __device__ __forceinline__ void group_knn5(float sx, float sy, float sz, const float4* __restrict__ map,
                                            const int* __restrict__ cell_start, const GridDesc& g, int sub, unsigned gmask, float tau0,
-                                           Top5& top, unsigned long long& cand, long long* dbg = nullptr) {
+                                           Top5& top, unsigned long long& cand, long long* dbg = nullptr, StageTile* stage = nullptr,
+                                           unsigned* stage_phase = nullptr) {
     static_assert(LANES > 1, "one thread per query: thread_knn5");
     const QCell qc = query_cell(sx, sy, sz, g);
     float tau = tau0;
+    if (LANES == 16 && stage) {
+        // one row per lane (9 of the 16), the whole run staged by ONE bulk copy; all 16 lanes meet at the mbarrier
+        int b = 0, e = 0, ib, ie;
+        if (sub < 9 && row_cells(qc, g, (sub % 3) - 1, (sub / 3) - 1, tau, ib, ie)) { b = __ldg(cell_start + ib); e = __ldg(cell_start + ie); }
+        const int n1 = min(e - b, kStageCap);
+        // the tile's previous contents were read through the generic proxy: order those reads before the async-proxy write
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        if (n1 > 0) {
+            mbar_arrive_expect_tx(&stage->bar, (unsigned)n1 * 16u);
+            bulk_g2s(&stage->pts[sub][0], map + b, (unsigned)n1 * 16u, &stage->bar);
+        } else mbar_arrive(&stage->bar);
+        cand += (unsigned long long)(e - b);
+        const unsigned ph = *stage_phase;
+        while (!mbar_try_wait(&stage->bar, ph)) { }
+        *stage_phase = ph ^ 1u;
+#pragma unroll 1
+        for (int i = 0; i < n1; ++i) consider(sx, sy, sz, stage->pts[sub][i], top, tau);
+#pragma unroll 1
+        for (int p0 = b + n1; p0 < e; p0 += BATCH) {       // a run longer than the tile: the rest through registers
+            float4 c[BATCH];
+#pragma unroll
+            for (int i = 0; i < BATCH; ++i) if (p0 + i < e) c[i] = __ldg(map + p0 + i);
+#pragma unroll
+            for (int i = 0; i < BATCH; ++i) if (p0 + i < e) consider(sx, sy, sz, c[i], top, tau);
+        }
+    } else {
     auto row_range = [&](int row, int& b, int& e) {
         b = 0; e = 0;
         int ib, ie;
@@ -177,6 +238,7 @@ __device__ __forceinline__ void group_knn5(float sx, float sy, float sz, const f
             for (int i = 0; i < BATCH; ++i) if (p0 + i < e) consider(sx, sy, sz, c[i], top, tau);
         }
         b = nb; e = ne;
+    }
     }
     if (dbg) dbg[10] = clock64() + (long long)(top.k0 & 0);
     // merge: 5 rounds of "group-wide minimum of the list heads, winner pops".  The minimum is an xor

@@ -2,6 +2,8 @@
   LILIOM_GN_SYNC  = 3 counter grid barrier with a release-only arrival and a relaxed poll (default) | 1 release arrival +
                     acquire poll | 0 full fences on both sides
   fused peer exchange of one rank with itself (the whole NVLink protocol on a single GPU)
+  LILIOM_KNN_TMA  = 1 the 16-lane search stages every run with one cp.async.bulk into shared memory (mbarrier) instead of
+                    batches of 16-byte loads through registers
 Same candidate sets, same per-row arithmetic, same summation trees -> identical poses, correspondences and sums."""
 import os
 
@@ -10,18 +12,19 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
-# (unused, mode): mode % 10 = LILIOM_GN_SYNC; +20: fused peer exchange with itself
-VARIANTS = [(0, 3), (0, 1), (0, 0), (0, 23)]
+# (unused, mode): mode % 10 = LILIOM_GN_SYNC; +20: fused peer exchange with itself; +30: bulk-copy staging
+VARIANTS = [(0, 3), (0, 1), (0, 0), (0, 23), (0, 33)]
 
 
 def _ctx(flat, ll):
     import liliom_b200 as L
-    keys = ("LILIOM_GN_SYNC",)
+    keys = ("LILIOM_GN_SYNC", "LILIOM_KNN_TMA")
     old = {k: os.environ.get(k) for k in keys}
     os.environ["LILIOM_GN_SYNC"] = str(ll % 10)
+    os.environ["LILIOM_KNN_TMA"] = "1" if ll >= 30 else "0"
     try:
         c = L.Context(variant=0)             # the switches are read at liliom_create
-        if ll >= 20:                         # one rank exchanging with itself: the whole protocol on a single GPU
+        if 20 <= ll < 30:                    # one rank exchanging with itself: the whole protocol on a single GPU
             c.comm_peer_attach([c.comm_peer_export()], 0)
         return c
     finally:

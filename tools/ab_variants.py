@@ -12,7 +12,7 @@ import liliom_b200 as L
 from liliom_b200 import synth
 
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 150
-cfgs = [int(a) for a in sys.argv[2:]] or [3, 1, 0, 3]
+cfgs = [int(a) for a in sys.argv[2:]] or [3, 33, 1, 0, 3, 33]      # +30: LILIOM_KNN_TMA=1 (bulk-copy staging of the runs)
 m, _ = synth.make_map(1_000_000)
 T0 = synth.default_true_pose()
 sweeps = []
@@ -25,7 +25,7 @@ stream = torch.cuda.Stream()
 ref = None
 print(f"lib: {L.LIB_PATH}")
 for sync in cfgs:
-    os.environ["LILIOM_GN_SYNC"] = str(sync)
+    os.environ["LILIOM_GN_SYNC"] = str(sync % 10); os.environ["LILIOM_KNN_TMA"] = "1" if sync >= 30 else "0"
     c = L.Context(variant=0)
     c.set_stream(stream.cuda_stream)
     c.map_set_points(m)
