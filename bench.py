@@ -840,6 +840,8 @@ def bench_body(args, fallback_note=None):
         "roofline": roof,
         "cpu_baseline": cpu,
         "pose_err_m": float(np.linalg.norm(np.asarray(pose)[4:] - sweeps[(steps - 1) % len(sweeps)]["T"][4:])),
+        "host": {"cpus": os.cpu_count(), "cpus_usable": len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else None,
+                 "note": "one python process per GPU; every library call ends in a stream synchronise on the host"},
     }
     if stream_wl and phases_main[4]:
         line["step_breakdown_ms"] = {k: phases_main[i] / phases_main[4] for i, k in enumerate(("extract", "scan_vg_and_gn", "push_frame", "map_rebuild"))}

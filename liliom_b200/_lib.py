@@ -61,6 +61,7 @@ EXPORTS = [
     "liliom_backend_edge_block", "liliom_backend_surf_block", "liliom_convert_livox", "liliom_extract_horizon_livox",
     "liliom_pc2_layout", "liliom_comm_peer_export", "liliom_comm_peer_attach",
     "liliom_map_push_frame_device", "liliom_knn_block_stats", "liliom_comm_set_shard_block", "liliom_undistort",
+    "liliom_map_update", "liliom_map_update_device", "liliom_map_download_cloud",
 ]
 NODE_EXPORTS = ["liliom_pre_create", "liliom_pre_destroy", "liliom_pre_imu", "liliom_pre_cloud",
                 "liliom_lo_create", "liliom_lo_destroy", "liliom_lo_edge", "liliom_lo_surf", "liliom_lo_full", "liliom_lo_run"]
@@ -146,6 +147,9 @@ def lib() -> C.CDLL:
     L.liliom_map_push_frame_device.argtypes = [vp, vp, C.c_int, dp]
     L.liliom_comm_set_shard_block.argtypes = [vp, C.c_int]
     L.liliom_undistort.argtypes = [vp, vp, C.c_int, dp, dp]
+    L.liliom_map_update.argtypes = [vp, vp, C.c_int, dp, ip]
+    L.liliom_map_update_device.argtypes = [vp, vp, C.c_int, dp, ip]
+    L.liliom_map_download_cloud.argtypes = [vp, vp, C.c_int, ip]
     L.liliom_knn_block_stats.argtypes = [vp, dp, C.POINTER(C.c_ulonglong)]
     L.liliom_pre_create.argtypes = [vp, C.c_int, dp]; L.liliom_pre_create.restype = vp
     L.liliom_pre_destroy.argtypes = [vp]; L.liliom_pre_destroy.restype = None
@@ -271,6 +275,27 @@ class Context:
         t = np.asarray(trans, dtype=np.float64); q = np.asarray(quat, dtype=np.float64)
         self._check(lib().liliom_undistort(self._h, _ptr(out), len(out), _dptr(t), _dptr(q)))
         return out
+
+    def map_update(self, pts: np.ndarray, pose7) -> int:
+        """push_frame + incremental refresh of the filtered map; returns the map size."""
+        pts = np.ascontiguousarray(pts, dtype=self.dtype)
+        p = np.asarray(pose7, dtype=np.float64)
+        m = C.c_int()
+        self._check(lib().liliom_map_update(self._h, _ptr(pts), len(pts), _dptr(p), C.byref(m)))
+        return m.value
+
+    def map_update_device(self, dev_ptr: int, n: int, pose7) -> int:
+        p = np.asarray(pose7, dtype=np.float64)
+        m = C.c_int()
+        self._check(lib().liliom_map_update_device(self._h, C.c_void_p(dev_ptr), n, _dptr(p), C.byref(m)))
+        return m.value
+
+    def map_download_cloud(self) -> np.ndarray:
+        m = C.c_int()
+        self._check(lib().liliom_map_download_cloud(self._h, None, 0, C.byref(m)))
+        out = np.zeros(max(m.value, 1), self.dtype)
+        self._check(lib().liliom_map_download_cloud(self._h, _ptr(out), len(out), C.byref(m)))
+        return out[:m.value]
 
     def map_rebuild(self) -> int:
         m = C.c_int()

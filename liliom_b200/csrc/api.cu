@@ -254,7 +254,8 @@ extern "C" void liliom_destroy(liliom_ctx* c) {
                       &c->vg_keys2, &c->vg_vals, &c->vg_vals2, &c->vg_flags, &c->vg_rank, &c->vg_params, &c->vg_out, &c->vg_minmax, &c->vg_count,
                       &c->cub_tmp, &c->vg_coop, &c->hz_ctl, &c->map_raw, &c->map_ds, &c->map_xyzw, &c->map_sorted, &c->cell_start, &c->grid_keys, &c->grid_keys2,
                       &c->grid_vals, &c->grid_vals2, &c->feats, &c->corr_valid, &c->corr_plane, &c->nn_idx, &c->nn_sqd, &c->pose_dev,
-                      &c->partials, &c->neq, &c->stats_dev, &c->counter, &c->lm_state, &c->raw_scan, &c->map_refl, &c->livox_in, &c->qstate};
+                      &c->partials, &c->neq, &c->stats_dev, &c->counter, &c->lm_state, &c->raw_scan, &c->map_refl, &c->livox_in, &c->qstate, &c->inc_key[0], &c->inc_key[1], &c->inc_ref[0], &c->inc_ref[1], &c->inc_newkey[0], &c->inc_newkey[1],
+                      &c->inc_newref[0], &c->inc_newref[1], &c->inc_removed, &c->inc_rpos, &c->inc_flags, &c->inc_rank, &c->inc_mm};
     for (DevBuf* b : bufs) b->release();
     for (auto& f : c->frames) f.buf.release();
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
@@ -439,17 +440,21 @@ extern "C" int liliom_map_clear(liliom_ctx* c) {
     if (!c) return LILIOM_E_ARG;
     for (auto& f : c->frames) f.buf.release();
     c->frames.clear();
+    c->inc_valid = false;
     c->map_ready = false; c->map_n = 0; c->map_n_global = 0;
     return LILIOM_OK;
 }
 
 // Shared body of the two push_frame entry points: d_src = n body-frame points of point_stride bytes ON THE DEVICE.
-static int push_frame_from_device(liliom_ctx* c, const void* d_src, int n, const double pose7[7]) {
+static int push_frame_from_device(liliom_ctx* c, const void* d_src, int n, const double pose7[7], bool keep_inc = false) {
     const int stride = c->prm.point_stride;
+    if (!keep_inc) c->inc_valid = false;        // the entry array of liliom_map_update no longer describes the FIFO
     Frame f;
+    f.slot = (int)c->frames.size();
     if ((int)c->frames.size() >= c->prm.max_map_frames && !c->frames.empty()) {      // L/src/LidarOdometry.cpp:293-296 pop_front
         f.buf = c->frames.front().buf;          // the popped frame's allocation is recycled: cudaFree + cudaMalloc per scan cost
-        c->frames.erase(c->frames.begin());     // more than the whole map maintenance of a 10 M-point map (cudaFree synchronises)
+        f.slot = c->frames.front().slot;        // more than the whole map maintenance of a 10 M-point map (cudaFree synchronises)
+        c->frames.erase(c->frames.begin());
     }
     f.n = n;
     int rc = LILIOM_OK;
@@ -509,6 +514,74 @@ extern "C" int liliom_map_push_frame_device(liliom_ctx* c, const void* d_surf_ds
     if (!c || n < 0 || (n > 0 && !d_surf_ds_body) || !pose7) return LILIOM_E_ARG;
     LILI_CUDA(c, cudaSetDevice(c->device));
     return push_frame_from_device(c, d_surf_ds_body, n, pose7);
+}
+
+namespace lili {
+// tail shared by the rebuild and the incremental update (single GPU): c->map_ds holds m filtered points
+int map_finish_from_ds(liliom_ctx* c, int m) {
+    const int stride = c->prm.point_stride;
+    LILI_CUDA(c, c->map_xyzw.ensure((size_t)(m > 0 ? m : 1) * sizeof(float4)));
+    c->map_n_global = m;
+    LILI_TRY(repack_to_f4(c, c->map_ds.p, m, stride, c->map_xyzw.as<float4>()));
+    LILI_TRY(grid_build(c, m));
+    LILI_CUDA(c, cudaStreamSynchronize(c->stream));
+    return LILIOM_OK;
+}
+}  // namespace lili
+
+extern "C" int liliom_map_rebuild(liliom_ctx* c, int* n_map_out);
+
+// push + incremental refresh (map_inc.cu); same result as liliom_map_push_frame + liliom_map_rebuild
+static int map_update_from_device(liliom_ctx* c, const void* d_src, int n, const double pose7[7], int* n_map_out) {
+    if (n_map_out) *n_map_out = 0;
+    const bool incremental = c->nranks == 1 && c->prm.max_map_frames <= 64 && n < (1 << 24);
+    int popped_slot = -1, popped_nfin = 0;
+    if ((int)c->frames.size() >= c->prm.max_map_frames && !c->frames.empty()) { popped_slot = c->frames.front().slot; popped_nfin = c->frames.front().nfin; }
+    LILI_TRY(push_frame_from_device(c, d_src, n, pose7, incremental));
+    if (incremental) {
+        c->map_ready = false; c->map_n = 0; c->map_n_global = 0;
+        int m = 0;
+        const int rc = map_inc_update(c, popped_slot, popped_nfin, &m);
+        if (rc == LILIOM_OK) {
+            LILI_TRY(map_finish_from_ds(c, m));
+            if (n_map_out) *n_map_out = m;
+            return LILIOM_OK;
+        }
+        c->inc_valid = false;
+        if (rc != LILIOM_E_GRID) return rc;       // E_GRID: keys not representable / PCL's overflow case -> the sort chain decides
+    }
+    return liliom_map_rebuild(c, n_map_out);
+}
+
+extern "C" int liliom_map_update(liliom_ctx* c, const void* surf_ds_body, int n, const double pose7[7], int* n_map_out) {
+    if (!c || n < 0 || (n > 0 && !surf_ds_body) || !pose7) return LILIOM_E_ARG;
+    LILI_CUDA(c, cudaSetDevice(c->device));
+    const int stride = c->prm.point_stride;
+    if (n > 0) {
+        LILI_CUDA(c, c->raw.ensure((size_t)n * stride));
+        LILI_CUDA(c, cudaMemcpyAsync(c->raw.p, surf_ds_body, (size_t)n * stride, cudaMemcpyHostToDevice, c->stream));
+    }
+    return map_update_from_device(c, c->raw.p, n, pose7, n_map_out);
+}
+
+extern "C" int liliom_map_update_device(liliom_ctx* c, const void* d_surf_ds_body, int n, const double pose7[7], int* n_map_out) {
+    if (!c || n < 0 || (n > 0 && !d_surf_ds_body) || !pose7) return LILIOM_E_ARG;
+    LILI_CUDA(c, cudaSetDevice(c->device));
+    return map_update_from_device(c, d_surf_ds_body, n, pose7, n_map_out);
+}
+
+// surf_from_map_ds as a point cloud (all fields), in liliom_map_download order
+extern "C" int liliom_map_download_cloud(liliom_ctx* c, void* out, int cap, int* m_out) {
+    if (!c || !m_out) return LILIOM_E_ARG;
+    LILI_CUDA(c, cudaSetDevice(c->device));
+    if (c->nranks > 1) { c->last_error = "liliom_map_download_cloud is single-GPU"; return LILIOM_E_ARG; }
+    const int m = c->map_n_global;
+    *m_out = m;
+    if (!out) return LILIOM_OK;
+    if (m > cap) return LILIOM_E_CAPACITY;
+    if (m) LILI_CUDA(c, cudaMemcpyAsync(out, c->map_ds.p, (size_t)m * c->prm.point_stride, cudaMemcpyDeviceToHost, c->stream));
+    LILI_CUDA(c, cudaStreamSynchronize(c->stream));
+    return LILIOM_OK;
 }
 
 extern "C" int liliom_map_rebuild(liliom_ctx* c, int* n_map_out) {

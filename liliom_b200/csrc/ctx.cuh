@@ -65,6 +65,9 @@ constexpr int kNormEq = 29;         // 21 + 6 + cost + count
 struct Frame {        // one entry of recent_surf_frames (world frame, point_stride bytes per point)
     DevBuf buf;
     int n = 0;
+    // incremental map (map_inc.cu): slot id carried by the frame's entries, finite points, box (ordered ints), unrepresentable key seen
+    int slot = 0, nfin = 0, box[6] = {0, 0, 0, 0, 0, 0};
+    bool bad = false;
 };
 
 }  // namespace lili
@@ -116,6 +119,10 @@ struct liliom_ctx {
 
     // ---- map ----
     std::vector<lili::Frame> frames;     // FIFO, oldest first
+    // incremental map (liliom_map_update, map_inc.cu): entries {voxel key, slot<<24|index} sorted by (key, frame age, index), double-buffered
+    lili::DevBuf inc_key[2], inc_ref[2], inc_newkey[2], inc_newref[2], inc_removed, inc_rpos, inc_flags, inc_rank, inc_mm;
+    int inc_cur = 0, inc_E = 0;
+    bool inc_valid = false;
     lili::DevBuf map_raw;                // concatenated frames (stride bytes)
     lili::DevBuf map_ds;                 // VoxelGrid output (stride bytes) or installed float4
     lili::DevBuf map_xyzw;               // float4 in map_download order (w = index)
@@ -221,6 +228,9 @@ int s2m_run(liliom_ctx* c, double pose7[7], int match_cnt, int max_num_iter, int
 
 int horizon_extract_dev(liliom_ctx* c, int n, const double q_imu[4], int* n_surf, int* n_edge, int* n_cut, bool sync_counts = true);
 int rot_extract_dev(liliom_ctx* c, int n, const double q_imu[4], const double q_lb[4], int* n_surf, int* n_edge, int* n_cut);
+
+int map_inc_update(liliom_ctx* c, int popped_slot, int popped_nfin, int* m_out);     // map_inc.cu
+int map_finish_from_ds(liliom_ctx* c, int m);                                        // api.cu
 
 int block27_stats(liliom_ctx* c, const double pose7[7], unsigned long long out[2]);   // grid_knn.cu
 

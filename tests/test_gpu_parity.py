@@ -471,3 +471,82 @@ def test_map_too_large_for_dense_grid():
         c.map_set_points(m)
     assert e.value.code == -5           # LILIOM_E_GRID: extent needs more than 2^29 one-metre cells
     c.close()
+
+
+# ---------------------------------------------------------------- (f2) incremental device map
+@pytest.mark.parametrize("variant", [0, 1])
+def test_incremental_map_update_equals_rebuild_over_a_stream(oracle, world_small, variant):
+    """liliom_map_update (push + incremental merge of the resident voxel entries, map_inc.cu) against the oracle's
+    concat + VoxelGrid(0.4) of the last 20 frames, every scan of a 46-scan stream, every field bit for bit; and against a second
+    context that takes the two-step path (push_frame + rebuild): same cloud, same correspondences.  The stream has overlapping
+    frames (most voxels hold points of several frames), an empty frame, non-finite points, a frame of exact duplicates, and a
+    plain liliom_map_push_frame in the middle (the entry array must be rebuilt once after it)."""
+    import liliom_b200 as L
+    c = L.Context(variant=variant)
+    two = L.Context(variant=variant)
+    if variant == 0:
+        surf, _, _ = oracle.extract_horizon(world_small["hz"], world_small["q_hz"])
+        F = ["x", "y", "z", "nx", "ny", "nz", "intensity", "curvature"]
+    else:
+        rc, surf, _, _, _, _ = oracle.extract_rot(world_small["hdl"], world_small["q_hdl"], (1.0, 0, 0, 0), 64, 4)
+        F = ["x", "y", "z", "intensity"]
+    ds = oracle.voxelgrid(surf, 0.4)
+    rng = np.random.default_rng(31 + variant)
+    frames = []
+    for k in range(46):
+        pose = np.array(world_small["T"]); pose[4] += 0.11 * k; pose[5] += 0.03 * k
+        half = np.deg2rad(0.4 * k) / 2
+        pose[:4] = [np.cos(half), 0.0, 0.0, np.sin(half)]
+        sub = ds[np.sort(rng.permutation(len(ds))[: int(len(ds) * rng.uniform(0.3, 0.9))])].copy()
+        if k == 7:
+            sub = sub[:0]                                   # an empty frame
+        if k == 11:
+            sub["x"][::13] = np.nan; sub["z"][5::29] = np.inf   # non-finite points are dropped by the filter
+        if k == 17:
+            sub = np.concatenate([sub[:300]] * 3)           # exact duplicates: three members per voxel from one frame
+        world = oracle.transform_cloud(sub, pose)
+        frames.append(world)
+        if k == 23:                                         # the two separate calls on the incremental context
+            c.map_push_frame(sub, pose)
+            m = c.map_rebuild()
+        else:
+            m = c.map_update(sub, pose)
+        two.map_push_frame(sub, pose)
+        m2 = two.map_rebuild()
+        live = [f for f in frames[-20:] if len(f)]
+        want = oracle.voxelgrid(np.concatenate(live), 0.4) if live else frames[0][:0]
+        got = c.map_download_cloud()
+        assert m == m2 == len(want) == len(got), (k, m, m2, len(want))
+        _fields_equal(got, want, F)
+        a, b = c.map_download(), two.map_download()
+        assert a.view(np.uint32).tobytes() == b.view(np.uint32).tobytes(), k
+        if k in (3, 19, 20, 21, 24, 45):                    # FIFO filling, first pops, after the rebuild-all, the end
+            va, pa, ia, sa, na = c.find_surf_corr(ds, world_small["guess"])
+            vb, pb, ib, sb, nb = two.find_surf_corr(ds, world_small["guess"])
+            assert np.array_equal(va, vb) and np.array_equal(ia, ib) and pa.tobytes() == pb.tobytes() and na.tobytes() == nb.tobytes()
+    c.close(); two.close()
+
+
+def test_incremental_map_falls_back_when_keys_do_not_fit(oracle, world_small):
+    """Voxel coordinates beyond 2^20 (or PCL's int32 index overflow) cannot be keyed absolutely: liliom_map_update must take
+    the sort chain for such a FIFO and return to the incremental path once the offending frame has left it."""
+    import liliom_b200 as L
+    p = L.default_params(0); p.max_map_frames = 3
+    c = L.Context(p)
+    surf, _, _ = oracle.extract_horizon(world_small["hz"], world_small["q_hz"])
+    ds = oracle.voxelgrid(surf, 0.4)
+    ds = ds[(np.abs(ds["y"]) < 3.0) & (np.abs(ds["z"]) < 3.0)][:2000]      # a thin strip: the 1 m cell grid must still hold the stretched extent
+    assert len(ds) > 200
+    ident = np.array([1.0, 0, 0, 0, 0, 0, 0])
+    frames = []
+    for k in range(8):
+        f = ds.copy(); f["x"] += np.float32(0.37 * k)
+        if k == 2:
+            f["x"][:5] += np.float32(600000.0)              # |floor(x / 0.4)| > 2^20
+        frames.append(oracle.transform_cloud(f, ident))
+        m = c.map_update(f, ident)
+        want = oracle.voxelgrid(np.concatenate(frames[-3:]), 0.4)
+        got = c.map_download_cloud()
+        assert m == len(want) == len(got), k
+        _fields_equal(got, want, ["x", "y", "z", "nx", "ny", "nz", "intensity", "curvature"])
+    c.close()
