@@ -509,7 +509,7 @@ def bench_body(args, fallback_note=None):
 
     cx_phase_ms = {}
 
-    def make_steps(cx):
+    def make_steps(cx, incremental=False):
         """The two step functions on context cx.  Streamed workload: the frame pushed is always the one the FIFO is about to
         drop (push number p re-pushes frame p % N_FRAMES, counted per context over ALL steps, warm-up included), so the
         map's content — and the step's work — stay constant."""
@@ -527,9 +527,13 @@ def bench_body(args, fallback_note=None):
                 ev[2].record(stream)
                 fd = frames_dev[pushes[0] % N_FRAMES]
                 pushes[0] += 1
-                cx.map_push_frame_device(fd.data_ptr(), fd.numel() // psz, ident)
-                ev[3].record(stream)
-                cx.map_rebuild()
+                if incremental:     # push + incremental merge of the resident voxel entries (same resulting map)
+                    ev[3].record(stream)
+                    cx.map_update_device(fd.data_ptr(), fd.numel() // psz, ident)
+                else:
+                    cx.map_push_frame_device(fd.data_ptr(), fd.numel() // psz, ident)
+                    ev[3].record(stream)
+                    cx.map_rebuild()
                 ev[4].record(stream); ev[4].synchronize()
                 for i in range(4):
                     phase_ms[i] += ev[i].elapsed_time(ev[i + 1])
@@ -756,6 +760,26 @@ def bench_body(args, fallback_note=None):
             probes["hdl_130k_vs_10M"] = {"error": str(e)[:200]}
         roof["dense_probe"] = probes
 
+    def incremental_leg(k1, pose_ref):
+        """The streamed workload on ONE GPU with liliom_map_update in place of push_frame + rebuild: same map, same poses."""
+        try:
+            c2 = new_context(False)
+            install_map(c2)
+            s2_res, _ = make_steps(c2, incremental=True)
+            ms2, last2 = timed(s2_res, k1, 3, prep_for(c2), collective=False)
+            ph2 = cx_phase_ms.get(id(c2), [0, 0, 0, 0, 0])
+            c2.close()
+            return {"value": k1 / (ms2 * 1e-3), "unit": "scans/s", "ms_per_step": ms2 / k1, "steps": k1,
+                    "map_update_ms": (ph2[3] / ph2[4]) if ph2[4] else None,
+                    "pose_max_abs_diff_vs_rebuild": float(np.abs(np.asarray(last2[0]) - np.asarray(pose_ref)).max()),
+                    "what": "liliom_map_update (incremental merge of the resident voxel entries) instead of push_frame + rebuild"}
+        except Exception as e:      # noqa: BLE001
+            return {"error": str(e)[:200]}
+
+    inc_single = None
+    if stream_wl and not multi and not args.no_extra_legs:
+        inc_single = incremental_leg(steps, last[0])
+
     # ---- N > 1, sharded: the SAME workload on one GPU (rank 0, fewer steps), and the replicas number as a secondary key
     same1, repl = None, None
     if sharded and not args.no_extra_legs:
@@ -768,7 +792,8 @@ def bench_body(args, fallback_note=None):
                 ms1, last1 = timed(s1_res, k1, 3, prep_for(c1), collective=False)
                 ph1 = cx_phase_ms.get(id(c1), [0, 0, 0, 0, 0])
                 c1.close()
-                same1 = {"value": k1 / (ms1 * 1e-3), "unit": "scans/s", "ms_per_step": ms1 / k1, "steps": k1,
+                inc1 = incremental_leg(k1, last1[0])
+                same1 = {"value": k1 / (ms1 * 1e-3), "unit": "scans/s", "ms_per_step": ms1 / k1, "steps": k1, "incremental_map": inc1,
                          "step_breakdown_ms": ({k: ph1[i] / ph1[4] for i, k in enumerate(("extract", "scan_vg_and_gn", "push_frame", "map_rebuild"))}
                                                if ph1[4] else None),
                          "pose_max_abs_diff_vs_sharded": float(np.abs(np.asarray(last1[0]) - np.asarray(last[0])).max())
@@ -843,6 +868,8 @@ def bench_body(args, fallback_note=None):
         "host": {"cpus": os.cpu_count(), "cpus_usable": len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else None,
                  "note": "one python process per GPU; every library call ends in a stream synchronise on the host"},
     }
+    if inc_single is not None:
+        line["incremental_map"] = inc_single
     if stream_wl and phases_main[4]:
         line["step_breakdown_ms"] = {k: phases_main[i] / phases_main[4] for i, k in enumerate(("extract", "scan_vg_and_gn", "push_frame", "map_rebuild"))}
     if multi:

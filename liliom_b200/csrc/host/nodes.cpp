@@ -145,22 +145,28 @@ int LidarOdometry::buildLocalMap() {
     if (nposes <= 1) {                                                     // :283-287 map = the current (raw) surf features
         liliom_map_clear(gpu);
         const double I[7] = {1, 0, 0, 0, 0, 0, 0};
-        rc = liliom_map_push_frame(gpu, surf_features.data(), n_surf_features, I);
-        if (rc != LILIOM_OK) return rc;
         temp_map = true;
-        return liliom_map_rebuild(gpu, &n_map);
+        return liliom_map_update(gpu, surf_features.data(), n_surf_features, I, &n_map);
     }
-    if (temp_map) { liliom_map_clear(gpu); temp_map = false; }
+    if (temp_map) { liliom_map_clear(gpu); temp_map = false; map_current = false; }
     if (recent_frames < 20 || latest_frame_idx != nposes - 1) {            // :290-299
         const int i = nposes - 1;
         const PoseInfo& P = pose_info_cloud_frame[i];
         const double pose[7] = {P.qw, P.qx, P.qy, P.qz, P.x, P.y, P.z};
-        rc = liliom_map_push_frame(gpu, surf_frames[i].data(), surf_frames_n[i], pose);   // transformCloud :246-278
-        if (rc != LILIOM_OK) return rc;
         if (recent_frames < 20) recent_frames++;
         else latest_frame_idx = nposes - 1;
+        // transformCloud :246-278 + FIFO :290-299 + concatenation :301-302 + VoxelGrid(0.4) :316-317 + search structure :490, as ONE
+        // incremental call: the filtered map lives on the device across scans (liliom_map_update)
+        rc = liliom_map_update(gpu, surf_frames[i].data(), surf_frames_n[i], pose, &n_map);
+        map_current = rc == LILIOM_OK;
+        return rc;
     }
-    return liliom_map_rebuild(gpu, &n_map);                                // :301-302 + VoxelGrid(0.4) + grid
+    // No frame entered the FIFO: the reference re-concatenates and re-filters the same 20 clouds (:301-302, :316-317) and gets
+    // the cloud it already had; the resident map is that cloud.
+    if (map_current) return LILIOM_OK;
+    rc = liliom_map_rebuild(gpu, &n_map);
+    map_current = rc == LILIOM_OK;
+    return rc;
 }
 
 // :319-322 + :483-561 + keyframe decision :565-585

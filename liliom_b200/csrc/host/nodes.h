@@ -81,6 +81,7 @@ private:
     int recent_frames = 0;                                  // recent_surf_frames.size()
     int latest_frame_idx = 0;
     bool temp_map = false;                                  // the initialization map (:283-287) is in the library FIFO
+    bool map_current = false;                               // the resident filtered map describes the present FIFO
     int n_map = 0;
 
     bool kf = true;
