@@ -110,99 +110,120 @@ __device__ __forceinline__ double hypot_pos(double x, double y) {
 }
 
 // a: symmetric, lower triangle read (a00,a10,a20,a11,a21,a22). evec[r][c] = component r of eigenvector c.
+// The 3x3 case is written out on SCALARS (d0..d2, s0, s1, q00..q22): the same operations in the same order as the generic
+// loops of the algorithm, but nothing is indexed at run time, so everything lives in registers (the indexed version kept
+// diag/sub/Q in local memory: the patch stage of the Horizon extractor spent ~44k cycles per patch mostly there).
+struct Eig3State { double d0, d1, d2, s0, s1, q00, q01, q02, q10, q11, q12, q20, q21, q22; };
+
+// one Givens step of the implicit symmetric QR sweep on rows/columns (k, k+1); FIRST: k == start (no update of sub[k-1]),
+// LAST: k == end-1 (no bulge into sub[k+1]).  K = 0 or 1 selects the scalars.
+template <int K>
+__device__ __forceinline__ void eig3_step(Eig3State& S, double& x, double& z, bool first, bool last) {
+    double c, s;
+    givens_rot(x, z, c, s);
+    double& dk = K == 0 ? S.d0 : S.d1;
+    double& dk1 = K == 0 ? S.d1 : S.d2;
+    double& sk = K == 0 ? S.s0 : S.s1;
+    const double sdk = s * dk + c * sk;
+    const double dkp1 = s * sk + c * dk1;
+    dk = c * (c * dk - s * sk) - s * (c * sk - s * dk1);
+    dk1 = s * sdk + c * dkp1;
+    sk = c * sdk - s * dkp1;
+    if (!first) { if (K == 1) S.s0 = c * S.s0 - s * z; }      // sub[k-1] (only k = 1 has one)
+    x = sk;
+    if (!last) { if (K == 0) { z = -s * S.s1; S.s1 = c * S.s1; } }      // bulge (only k = 0 can have a successor)
+    if (K == 0) {
+        double a, b;
+        a = S.q00; b = S.q01; S.q00 = c * a - s * b; S.q01 = s * a + c * b;
+        a = S.q10; b = S.q11; S.q10 = c * a - s * b; S.q11 = s * a + c * b;
+        a = S.q20; b = S.q21; S.q20 = c * a - s * b; S.q21 = s * a + c * b;
+    } else {
+        double a, b;
+        a = S.q01; b = S.q02; S.q01 = c * a - s * b; S.q02 = s * a + c * b;
+        a = S.q11; b = S.q12; S.q11 = c * a - s * b; S.q12 = s * a + c * b;
+        a = S.q21; b = S.q22; S.q21 = c * a - s * b; S.q22 = s * a + c * b;
+    }
+}
+
 __device__ inline void eigen_sym3(double a00, double a10, double a20, double a11, double a21, double a22,
                                   double eval[3], double evec[3][3]) {
     double scale = fmax(fmax(fmax(fabs(a00), fabs(a10)), fmax(fabs(a20), fabs(a11))), fmax(fabs(a21), fabs(a22)));
     if (scale == 0.0) scale = 1.0;
     a00 /= scale; a10 /= scale; a20 /= scale; a11 /= scale; a21 /= scale; a22 /= scale;
-    double diag[3], sub[2];
-    double Q[3][3];
-    diag[0] = a00;
-    double v1norm2 = a20 * a20;
+    Eig3State S;
+    S.d0 = a00;
+    const double v1norm2 = a20 * a20;
     if (v1norm2 <= DBL_MIN) {
-        diag[1] = a11; diag[2] = a22; sub[0] = a10; sub[1] = a21;
-#pragma unroll
-        for (int i = 0; i < 3; ++i)
-#pragma unroll
-            for (int j = 0; j < 3; ++j) Q[i][j] = (i == j) ? 1.0 : 0.0;
+        S.d1 = a11; S.d2 = a22; S.s0 = a10; S.s1 = a21;
+        S.q00 = 1; S.q01 = 0; S.q02 = 0; S.q10 = 0; S.q11 = 1; S.q12 = 0; S.q20 = 0; S.q21 = 0; S.q22 = 1;
     } else {
-        double beta = sqrt(a10 * a10 + v1norm2);
-        double invBeta = 1.0 / beta;
-        double m01 = a10 * invBeta;
-        double m02 = a20 * invBeta;
-        double q = 2.0 * m01 * a21 + m02 * (a22 - a11);
-        diag[1] = a11 + m02 * q;
-        diag[2] = a22 - m02 * q;
-        sub[0] = beta;
-        sub[1] = a21 - m01 * q;
-        Q[0][0] = 1; Q[0][1] = 0;   Q[0][2] = 0;
-        Q[1][0] = 0; Q[1][1] = m01; Q[1][2] = m02;
-        Q[2][0] = 0; Q[2][1] = m02; Q[2][2] = -m01;
+        const double beta = sqrt(a10 * a10 + v1norm2);
+        const double invBeta = 1.0 / beta;
+        const double m01 = a10 * invBeta;
+        const double m02 = a20 * invBeta;
+        const double q = 2.0 * m01 * a21 + m02 * (a22 - a11);
+        S.d1 = a11 + m02 * q;
+        S.d2 = a22 - m02 * q;
+        S.s0 = beta;
+        S.s1 = a21 - m01 * q;
+        S.q00 = 1; S.q01 = 0;   S.q02 = 0;
+        S.q10 = 0; S.q11 = m01; S.q12 = m02;
+        S.q20 = 0; S.q21 = m02; S.q22 = -m01;
     }
     int end = 2, start = 0, iter = 0;
     const double precision_inv = 1.0 / DBL_EPSILON;
     while (end > 0) {
-        for (int i = start; i < end; ++i) {
-            if (fabs(sub[i]) < DBL_MIN) {
-                sub[i] = 0.0;
-            } else {
-                double ss = precision_inv * sub[i];
-                if (ss * ss <= (fabs(diag[i]) + fabs(diag[i + 1]))) sub[i] = 0.0;
-            }
+        // deflation test on sub[start..end)
+        if (start <= 0 && 0 < end) {
+            if (fabs(S.s0) < DBL_MIN) S.s0 = 0.0;
+            else { const double ss = precision_inv * S.s0; if (ss * ss <= (fabs(S.d0) + fabs(S.d1))) S.s0 = 0.0; }
         }
-        while (end > 0 && sub[end - 1] == 0.0) end--;
+        if (start <= 1 && 1 < end) {
+            if (fabs(S.s1) < DBL_MIN) S.s1 = 0.0;
+            else { const double ss = precision_inv * S.s1; if (ss * ss <= (fabs(S.d1) + fabs(S.d2))) S.s1 = 0.0; }
+        }
+        while (end > 0 && (end == 2 ? S.s1 : S.s0) == 0.0) end--;
         if (end <= 0) break;
         iter++;
         if (iter > 90) break;
         start = end - 1;
-        while (start > 0 && sub[start - 1] != 0.0) start--;
-        double td = (diag[end - 1] - diag[end]) * 0.5;
-        double e = sub[end - 1];
-        double mu = diag[end];
+        while (start > 0 && (start == 2 ? S.s1 : S.s0) != 0.0) start--;        // sub[start-1]
+        const double dEm1 = end == 2 ? S.d1 : S.d0, dE = end == 2 ? S.d2 : S.d1;
+        const double td = (dEm1 - dE) * 0.5;
+        const double e = end == 2 ? S.s1 : S.s0;
+        double mu = dE;
         if (td == 0.0) {
             mu -= fabs(e);
         } else if (e != 0.0) {
-            double e2 = e * e;
-            double h = hypot_pos(td, e);
+            const double e2 = e * e;
+            const double h = hypot_pos(td, e);
             if (e2 == 0.0) mu -= e / ((td + (td > 0 ? h : -h)) / e);
             else mu -= e2 / (td + (td > 0 ? h : -h));
         }
-        double x = diag[start] - mu;
-        double z = sub[start];
-        for (int k = start; k < end && z != 0.0; ++k) {
-            double c, s;
-            givens_rot(x, z, c, s);
-            double sdk = s * diag[k] + c * sub[k];
-            double dkp1 = s * sub[k] + c * diag[k + 1];
-            diag[k] = c * (c * diag[k] - s * sub[k]) - s * (c * sub[k] - s * diag[k + 1]);
-            diag[k + 1] = s * sdk + c * dkp1;
-            sub[k] = c * sdk - s * dkp1;
-            if (k > start) sub[k - 1] = c * sub[k - 1] - s * z;
-            x = sub[k];
-            if (k < end - 1) {
-                z = -s * sub[k + 1];
-                sub[k + 1] = c * sub[k + 1];
+        double x = (start == 0 ? S.d0 : S.d1) - mu;
+        double z = start == 0 ? S.s0 : S.s1;
+        if (start == 0) {
+            if (z != 0.0) {
+                eig3_step<0>(S, x, z, true, end == 1);
+                if (end == 2 && z != 0.0) eig3_step<1>(S, x, z, false, true);
             }
-#pragma unroll
-            for (int r = 0; r < 3; ++r) {
-                double qk = Q[r][k], qk1 = Q[r][k + 1];
-                Q[r][k] = c * qk - s * qk1;
-                Q[r][k + 1] = s * qk + c * qk1;
-            }
+        } else {      // start == 1, end == 2
+            if (z != 0.0) eig3_step<1>(S, x, z, true, true);
         }
     }
-    for (int i = 0; i < 2; ++i) {
-        int k = i;
-        for (int j = i + 1; j < 3; ++j) if (diag[j] < diag[k]) k = j;
-        if (k != i) {
-            double t = diag[i]; diag[i] = diag[k]; diag[k] = t;
-            for (int r = 0; r < 3; ++r) { double u = Q[r][i]; Q[r][i] = Q[r][k]; Q[r][k] = u; }
-        }
+    // ascending selection sort of (eigenvalue, column), as the generic two-pass loop does it
+    {
+        int k = 0;
+        if (S.d1 < S.d0) k = 1;
+        if (S.d2 < (k == 1 ? S.d1 : S.d0)) k = 2;
+        if (k == 1) { double t = S.d0; S.d0 = S.d1; S.d1 = t; t = S.q00; S.q00 = S.q01; S.q01 = t; t = S.q10; S.q10 = S.q11; S.q11 = t; t = S.q20; S.q20 = S.q21; S.q21 = t; }
+        else if (k == 2) { double t = S.d0; S.d0 = S.d2; S.d2 = t; t = S.q00; S.q00 = S.q02; S.q02 = t; t = S.q10; S.q10 = S.q12; S.q12 = t; t = S.q20; S.q20 = S.q22; S.q22 = t; }
+        if (S.d2 < S.d1) { double t = S.d1; S.d1 = S.d2; S.d2 = t; t = S.q01; S.q01 = S.q02; S.q02 = t; t = S.q11; S.q11 = S.q12; S.q12 = t; t = S.q21; S.q21 = S.q22; S.q22 = t; }
     }
-    for (int i = 0; i < 3; ++i) {
-        eval[i] = diag[i] * scale;
-        for (int r = 0; r < 3; ++r) evec[r][i] = Q[r][i];
-    }
+    eval[0] = S.d0 * scale; eval[1] = S.d1 * scale; eval[2] = S.d2 * scale;
+    evec[0][0] = S.q00; evec[0][1] = S.q01; evec[0][2] = S.q02;
+    evec[1][0] = S.q10; evec[1][1] = S.q11; evec[1][2] = S.q12;
+    evec[2][0] = S.q20; evec[2][1] = S.q21; evec[2][2] = S.q22;
 }
 
 // ---------------------------------------------------------------------------------------

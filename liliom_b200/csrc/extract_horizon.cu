@@ -146,10 +146,15 @@ __device__ __forceinline__ void hz_patch_eval(HzPatchSmem& P, const Pt48* __rest
             if (g1 > 0.06 && g1 > max_s) { max_s = g1; idx = j; }
         }
         P.ids_y[lane] = (max_s != 0) ? idx : -1;
-    } else if (lane == 6) {
-        int n = 0;
-        for (int e = 0; e < 36; ++e) if (W[cell_of(e)].curv > 0) P.list_s[n++] = cell_of(e);
-        P.num = n;
+    }
+    {   // ordered list of the valid cells (e = j*6 + k ascending): two ballots + prefix popcounts instead of a 36-step serial walk
+        const bool v0 = W[cell_of(lane)].curv > 0;
+        const bool v1 = lane < 4 && W[cell_of(32 + lane)].curv > 0;
+        const unsigned m0 = __ballot_sync(0xffffffffu, v0), m1 = __ballot_sync(0xffffffffu, v1);
+        const unsigned lt = (1u << lane) - 1u;
+        if (v0) P.list_s[__popc(m0 & lt)] = cell_of(lane);
+        if (v1) P.list_s[__popc(m0) + __popc(m1 & lt)] = cell_of(32 + lane);
+        if (lane == 0) P.num = __popc(m0) + __popc(m1);
     }
     __syncwarp();
     if (lane == 0) {

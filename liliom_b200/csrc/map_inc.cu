@@ -90,14 +90,22 @@ __global__ void k_inc_mark(const unsigned* __restrict__ refs, int E, int popped,
     if (i > E) return;
     removed[i] = (i < E && popped >= 0 && (int)(refs[i] >> 24) == popped) ? 1 : 0;
 }
-// surviving old entries: down by the removed entries before them, up by the new entries with a smaller key
+// surviving old entries: down by the removed entries before them, up by the new entries with a smaller key.  The entries of a
+// warp are consecutive in a sorted array, so their lower bounds in the new keys are nested between those of lanes 0 and 31:
+// two full binary searches per warp, then every lane searches only the (short) range between them.
 __global__ void k_inc_merge_old(const u64* __restrict__ keys, const unsigned* __restrict__ refs, const int* __restrict__ removed,
                                 const int* __restrict__ rpos, int E, const u64* __restrict__ newkeys, int nnew, u64* __restrict__ keys2,
                                 unsigned* __restrict__ refs2) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int ic = min(i, E - 1);
+    const u64 k = keys[ic];
+    int lb = 0;
+    if (lane == 0 || lane == 31) lb = lower_bound_u64(newkeys, nnew, k);
+    const int lo = __shfl_sync(0xffffffffu, lb, 0), hi = __shfl_sync(0xffffffffu, lb, 31);
+    if (lane != 0 && lane != 31) lb = lo + lower_bound_u64(newkeys + lo, hi - lo, k);
     if (i >= E || removed[i]) return;
-    const u64 k = keys[i];
-    const int pos = i - rpos[i] + lower_bound_u64(newkeys, nnew, k);
+    const int pos = i - rpos[i] + lb;
     keys2[pos] = k; refs2[pos] = refs[i];
 }
 // new entries (sorted by key, then index): behind every surviving old entry with key <= their own
