@@ -360,6 +360,15 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU oracle")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        # One launch-latency-bound process per GPU: keep each on the host cores next to its GPU (a doorbell rung across sockets
+        # costs more than the kernels of a 0.2 ms scan save).  Best effort; the line reports what the process ended up with.
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local_rank))
+            os.environ["LILIOM_BENCH_AFFINITY"] = "nvml"
+        except Exception as e:      # noqa: BLE001
+            os.environ["LILIOM_BENCH_AFFINITY"] = "unchanged (" + type(e).__name__ + ")"
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     note = None
@@ -868,6 +877,7 @@ def bench_body(args, fallback_note=None):
         "cpu_baseline": cpu,
         "pose_err_m": float(np.linalg.norm(np.asarray(pose)[4:] - sweeps[(steps - 1) % len(sweeps)]["T"][4:])),
         "host": {"cpus": os.cpu_count(), "cpus_usable": len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else None,
+                 "affinity": os.environ.get("LILIOM_BENCH_AFFINITY"),
                  "note": "one python process per GPU; every library call ends in a stream synchronise on the host"},
     }
     if inc_single is not None:

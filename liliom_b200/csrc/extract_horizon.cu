@@ -106,7 +106,8 @@ struct HzPatchSmem {
 // Evaluates one patch with one warp: fills P (window, lists, normals, out_s/out_e, ns/ne).
 template <bool COHERENT>
 __device__ __forceinline__ void hz_patch_eval(HzPatchSmem& P, const Pt48* __restrict__ cut, const int* __restrict__ mat, int patch, int lane,
-                                              double surf_thres, double edge_thres) {
+                                              double surf_thres, double edge_thres, long long* st = nullptr) {
+#define HZ_ST(i) do { if (st) st[i] = clock64(); } while (0)
     const int i0 = 5 + 6 * patch;
     HzCell* W = P.win;
     for (int e = lane; e < HZ_LINES * HZ_WIN; e += 32) {
@@ -122,6 +123,7 @@ __device__ __forceinline__ void hz_patch_eval(HzPatchSmem& P, const Pt48* __rest
         W[e] = h;
     }
     __syncwarp();
+    HZ_ST(0);      // window loaded
     auto cell_of = [](int e) { return (e % 6) * HZ_WIN + (e / 6 + 4); };   // patch cell e = j*6+k -> window index (k, j)
     // ---- (1) validity + depth Laplacian of the 36 patch cells, :276-279 and :310-315
     for (int e = lane; e < 36; e += 32) {
@@ -165,6 +167,7 @@ __device__ __forceinline__ void hz_patch_eval(HzPatchSmem& P, const Pt48* __rest
     }
     __syncwarp();
     const int num = P.num, nedge = P.nedge;
+    HZ_ST(1);      // Laplacians, arg-max, lists
     if (num >= 25) {                                                                              // :287 (else: `continue`, no edge either)
         // ---- (3) centroids: lanes 0-2 surf xyz (:280-289), lanes 3-5 edge xyz (:335-342); sequential sums
         if (lane < 6) {
@@ -200,6 +203,7 @@ __device__ __forceinline__ void hz_patch_eval(HzPatchSmem& P, const Pt48* __rest
             P.cov[lane] = acc;
         }
         __syncwarp();
+        HZ_ST(2);  // centroids + scatter matrices
         // ---- (5) the two eigen-solves side by side (:298, :351)
         if (lane < 2 && (lane == 0 || nedge > 0)) {
             const double* M = P.cov + 6 * lane;
@@ -210,6 +214,7 @@ __device__ __forceinline__ void hz_patch_eval(HzPatchSmem& P, const Pt48* __rest
             P.nrm[3 * lane] = (float)evec[0][col]; P.nrm[3 * lane + 1] = (float)evec[1][col]; P.nrm[3 * lane + 2] = (float)evec[2][col];
         }
         __syncwarp();
+        HZ_ST(3);  // eigen-solves
         // ---- (6) decisions, :353-382
         if (lane == 0) {
             int ns = 0, ne = 0;
@@ -234,7 +239,9 @@ __device__ __forceinline__ void hz_patch_eval(HzPatchSmem& P, const Pt48* __rest
             P.ns = ns; P.ne = ne;
         }
         __syncwarp();
+        HZ_ST(4);  // decisions
     }
+#undef HZ_ST
 }
 
 // Writes the patch's selected cells (P.out_s / P.out_e) as published points starting at dst_s / dst_e.
@@ -399,7 +406,7 @@ __global__ void __launch_bounds__(HZC_THREADS) k_hz_coop(const Pt48* __restrict_
     const int patch = b * HZC_WARPS + warp;
     HzPatchSmem& P = sm[warp];
     if (patch < HZ_PATCHES) {
-        hz_patch_eval<true>(P, cut, mat, patch, lane, surf_thres, edge_thres);
+        hz_patch_eval<true>(P, cut, mat, patch, lane, surf_thres, edge_thres, (stamp && warp == 0) ? stamp + 5 : nullptr);
         if (lane == 0) { counts[patch] = P.ns; counts[HZ_PATCHES + 1 + patch] = P.ne; }
     }
     hz_grid_barrier(bar, 3u * (unsigned int)G);
@@ -442,12 +449,12 @@ int horizon_extract_dev(liliom_ctx* c, int n, const double q_imu[4], int* n_surf
     if (coop) {
         // one cooperative launch; scratch: per-block counts behind the patch counts, barrier words in their own buffer
         if (!c->hz_ctl.p) {
-            LILI_CUDA(c, c->hz_ctl.ensure(64 + (size_t)c->sm_count * sizeof(int)));
+            LILI_CUDA(c, c->hz_ctl.ensure(128 + (size_t)c->sm_count * sizeof(int)));
             LILI_CUDA(c, cudaMemsetAsync(c->hz_ctl.p, 0, c->hz_ctl.cap, c->stream));
             c->hz_coop_calls = 0;
         }
         unsigned int* ctl = c->hz_ctl.as<unsigned int>();
-        int* blockcnt = reinterpret_cast<int*>(c->hz_ctl.as<unsigned char>() + 64);
+        int* blockcnt = reinterpret_cast<int*>(c->hz_ctl.as<unsigned char>() + 128);
         int* ncut_out = cidx + n;
         const Pt48* raw_c = raw;
         Pt48* cutp = c->cut.as<Pt48>(); Pt48* surfp = c->surf.as<Pt48>(); Pt48* edgep = c->edge.as<Pt48>();

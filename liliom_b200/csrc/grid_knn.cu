@@ -1250,10 +1250,11 @@ int s2m_run(liliom_ctx* c, double pose7[7], int match_cnt, int max_num_iter, int
         }
     }
     if (a.dbg && c->dbg_timing) {       // stage clocks of the two cooperative kernels that ran before this call (resident pipeline)
-        long long t[5];
+        long long t[10];
         if (c->hz_ctl.p && cudaMemcpy(t, c->hz_ctl.as<unsigned char>() + 16, sizeof(t), cudaMemcpyDeviceToHost) == cudaSuccess && t[4] > t[0])
-            fprintf(stderr, "[k_hz_coop, cycles, block 0] A keep-flags+barrier %lld, B de-skew/bin+barrier %lld, C patches+barrier %lld, D emit %lld\n",
-                    t[1] - t[0], t[2] - t[1], t[3] - t[2], t[4] - t[3]);
+            fprintf(stderr, "[k_hz_coop, cycles, block 0] A keep-flags+barrier %lld, B de-skew/bin+barrier %lld, C patches+barrier %lld (patch 0: window %lld, "
+                            "lists %lld, centroid+scatter %lld, eigen %lld, decisions %lld), D emit %lld\n",
+                    t[1] - t[0], t[2] - t[1], t[3] - t[2], t[5] - t[2], t[6] - t[5], t[7] - t[6], t[8] - t[7], t[9] - t[8], t[4] - t[3]);
         const long long* vs = vg_coop_stamps(c);
         if (vs && cudaMemcpy(t, vs, sizeof(t), cudaMemcpyDeviceToHost) == cudaSuccess && t[4] > t[0])
             fprintf(stderr, "[k_vg_coop, cycles, block 0] 1 hash insert+barrier %lld, 2 ranks+barrier %lld, 3 group+barrier %lld, 4 centroids %lld\n",
