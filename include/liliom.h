@@ -234,6 +234,17 @@ int liliom_extract_horizon_livox(liliom_ctx* c, const void* custom_pts, int n, i
                                  liliom_pt48* edge_out, int edge_cap, int* n_edge,
                                  liliom_pt48* cutted_out, int cut_cap, int* n_cut);
 
+/* ---- the loop-closure alignment, BackendFusion::performLoopClosure (L/src/BackendFusion.cpp:2552-2582) ----
+ * pcl::IterativeClosestPoint with the reference's settings (:2566-2570: max correspondence distance 30, 100 iterations,
+ * transformation epsilon 1e-6, euclidean fitness epsilon 1e-6) on src = latest_key_frames_ds against tgt = his_key_frames_ds
+ * (host clouds, stride 48|32|16): per iteration the nearest target point of every transformed source point (kept within
+ * max_corr_dist), the rigid transform by the SVD closed form, PCL's default convergence criteria.  T16 = getFinalTransformation()
+ * (row-major 4x4, target <- source), *fitness = getFitnessScore(), *converged = hasConverged(), *iters = iterations run.
+ * The target is installed as the context's map (use a context of its own for the backend).  fp64 where PCL is fp32; PCL's
+ * setRANSACIterations is a no-op for this class (no rejector installed), so the alignment is deterministic. */
+int liliom_icp_align(liliom_ctx* c, const void* src, int n_src, const void* tgt, int n_tgt, int stride, double max_corr_dist,
+                     int max_iter, double trans_eps, double fit_eps, double T16[16], double* fitness, int* converged, int* iters);
+
 /* ---- LidarOdometry::undistortion on the device (L/src/LidarOdometry.cpp:178-199) ----
  * Moves every point of a keyframe cloud (point_stride bytes per point, in place) to the end of the sweep:
  * p' = slerp(I, quat; ratio) * p + ratio * trans, ratio = min(frac(intensity) / 0.1, 1).  publishCloudLast (:624-632) calls it

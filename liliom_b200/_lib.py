@@ -61,7 +61,7 @@ EXPORTS = [
     "liliom_backend_edge_block", "liliom_backend_surf_block", "liliom_convert_livox", "liliom_extract_horizon_livox",
     "liliom_pc2_layout", "liliom_comm_peer_export", "liliom_comm_peer_attach",
     "liliom_map_push_frame_device", "liliom_knn_block_stats", "liliom_comm_set_shard_block", "liliom_undistort",
-    "liliom_map_update", "liliom_map_update_device", "liliom_map_download_cloud",
+    "liliom_map_update", "liliom_map_update_device", "liliom_map_download_cloud", "liliom_icp_align",
 ]
 NODE_EXPORTS = ["liliom_pre_create", "liliom_pre_destroy", "liliom_pre_imu", "liliom_pre_cloud",
                 "liliom_lo_create", "liliom_lo_destroy", "liliom_lo_edge", "liliom_lo_surf", "liliom_lo_full", "liliom_lo_run"]
@@ -150,6 +150,7 @@ def lib() -> C.CDLL:
     L.liliom_map_update.argtypes = [vp, vp, C.c_int, dp, ip]
     L.liliom_map_update_device.argtypes = [vp, vp, C.c_int, dp, ip]
     L.liliom_map_download_cloud.argtypes = [vp, vp, C.c_int, ip]
+    L.liliom_icp_align.argtypes = [vp, vp, C.c_int, vp, C.c_int, C.c_int, C.c_double, C.c_int, C.c_double, C.c_double, dp, dp, ip, ip]
     L.liliom_knn_block_stats.argtypes = [vp, dp, C.POINTER(C.c_ulonglong)]
     L.liliom_pre_create.argtypes = [vp, C.c_int, dp]; L.liliom_pre_create.restype = vp
     L.liliom_pre_destroy.argtypes = [vp]; L.liliom_pre_destroy.restype = None
@@ -296,6 +297,16 @@ class Context:
         out = np.zeros(max(m.value, 1), self.dtype)
         self._check(lib().liliom_map_download_cloud(self._h, _ptr(out), len(out), C.byref(m)))
         return out[:m.value]
+
+    def icp_align(self, src: np.ndarray, tgt: np.ndarray, max_corr_dist=30.0, max_iter=100, trans_eps=1e-6, fit_eps=1e-6):
+        """Loop-closure ICP: returns (T 4x4, fitness, converged, iterations)."""
+        s, stride = self._feats(src)
+        t, stride_t = self._feats(tgt)
+        assert stride == stride_t
+        T = np.zeros(16, np.float64); fit = C.c_double(); conv = C.c_int(); it = C.c_int()
+        self._check(lib().liliom_icp_align(self._h, _ptr(s), len(s), _ptr(t), len(t), stride, max_corr_dist, max_iter, trans_eps, fit_eps,
+                                           _dptr(T), C.byref(fit), C.byref(conv), C.byref(it)))
+        return T.reshape(4, 4), fit.value, bool(conv.value), it.value
 
     def map_rebuild(self) -> int:
         m = C.c_int()

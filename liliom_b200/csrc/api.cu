@@ -912,6 +912,28 @@ extern "C" int liliom_find_surf_corr(liliom_ctx* c, const void* feats, int n, in
     return LILIOM_OK;
 }
 
+// ===================== SURVEY §8 (f4): loop-closure alignment =====================
+extern "C" int liliom_icp_align(liliom_ctx* c, const void* src, int n_src, const void* tgt, int n_tgt, int stride, double max_corr_dist,
+                                int max_iter, double trans_eps, double fit_eps, double T16[16], double* fitness, int* converged, int* iters) {
+    if (!c || n_src < 0 || n_tgt < 0 || (n_src > 0 && !src) || (n_tgt > 0 && !tgt) || !T16 || !fitness || !converged || !iters) return LILIOM_E_ARG;
+    if ((stride != 16 && stride != 32 && stride != 48) || !(max_corr_dist > 0) || max_iter < 1) return LILIOM_E_ARG;
+    LILI_CUDA(c, cudaSetDevice(c->device));
+    if (c->nranks > 1) { c->last_error = "liliom_icp_align is single-GPU"; return LILIOM_E_ARG; }
+    // target -> the context's map (cell grid), source -> the resident query array
+    c->map_refl.release();
+    c->map_ready = false;
+    c->inc_valid = false;
+    LILI_CUDA(c, c->map_xyzw.ensure((size_t)(n_tgt > 0 ? n_tgt : 1) * sizeof(float4)));
+    LILI_CUDA(c, c->raw.ensure((size_t)(n_tgt > 0 ? n_tgt : 1) * stride));
+    if (n_tgt > 0) {
+        LILI_CUDA(c, cudaMemcpyAsync(c->raw.p, tgt, (size_t)n_tgt * stride, cudaMemcpyHostToDevice, c->stream));
+        LILI_TRY(repack_to_f4(c, c->raw.p, n_tgt, stride, c->map_xyzw.as<float4>()));
+    }
+    LILI_TRY(install_map_from_xyzw(c, n_tgt));
+    LILI_TRY(upload_feats(c, src, n_src, stride));
+    return icp_align(c, c->feats.as<float4>(), n_src, max_corr_dist, max_iter, trans_eps, fit_eps, T16, fitness, converged, iters);
+}
+
 // ===================== wire format, publishing side =====================
 // from-knowledge: POINT_CLOUD_REGISTER_POINT_STRUCT of pcl::PointXYZINormal / pcl::PointXYZI (PCL 1.8-1.10) as pcl::toROSMsg lists them
 extern "C" int liliom_pc2_layout(int point_stride, liliom_pc2_field* fields, int cap, int* point_step) {

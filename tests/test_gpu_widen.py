@@ -178,3 +178,82 @@ def test_undistortion_on_device(oracle, world_small):
     hdl["intensity"] = (np.arange(20000) % 64 + (np.arange(20000) % 97) / 970.0).astype(np.float32)
     assert c32.undistort(hdl, trans).view(np.uint8).tobytes() == oracle.undistort(hdl, trans).view(np.uint8).tobytes()
     c32.close()
+
+
+def _icp_numpy(oracle, src, tgt, max_corr=30.0, max_iter=100, trans_eps=1e-6, fit_eps=1e-6):
+    """PCL's IterativeClosestPoint loop restated on third-party numerics (from-knowledge, like icp.cu's header): exact NN from the
+    oracle's kd-tree, Umeyama (no scale) with numpy's SVD, DefaultConvergenceCriteria."""
+    tree = oracle.KdTree(tgt)
+    F = np.eye(4)
+    prev = np.finfo(np.float64).max
+    it, conv = 0, False
+    s3 = src[:, :3].astype(np.float64)
+    while True:
+        p = s3 @ F[:3, :3].T + F[:3, 3]
+        q4 = np.ones((len(p), 4), np.float32); q4[:, :3] = p.astype(np.float32)
+        idx, sqd = tree.knn5(q4)
+        keep = sqd[:, 0] <= np.float32(max_corr * max_corr)
+        if keep.sum() < 3:
+            break
+        P, Q = p[keep], tgt[idx[keep, 0], :3].astype(np.float64)
+        mp, mq = P.mean(0), Q.mean(0)
+        S = (Q - mq).T @ (P - mp) / len(P)
+        U, D, Vt = np.linalg.svd(S)
+        sg = np.ones(3)
+        if np.linalg.det(U) * np.linalg.det(Vt) < 0:
+            sg[2] = -1
+        R = U @ np.diag(sg) @ Vt
+        t = mq - R @ mp
+        Ti = np.eye(4); Ti[:3, :3] = R; Ti[:3, 3] = t
+        F = Ti @ F
+        it += 1
+        mse = float(sqd[keep, 0].astype(np.float64).mean())
+        if it >= max_iter:
+            conv = True; break
+        if 0.5 * (np.trace(R) - 1.0) >= 1.0 - trans_eps and float(t @ t) <= trans_eps:
+            conv = True; break
+        if abs(mse - prev) / prev < fit_eps or abs(mse - prev) < 1e-12:
+            conv = True; break
+        prev = mse
+    p = s3 @ F[:3, :3].T + F[:3, 3]
+    q4 = np.ones((len(p), 4), np.float32); q4[:, :3] = p.astype(np.float32)
+    _, sqd = tree.knn5(q4)
+    return F, float(sqd[:, 0].astype(np.float64).mean()), conv, it
+
+
+def test_loop_closure_icp(oracle, world_small):
+    """(f4) liliom_icp_align with the reference's settings (L/src/BackendFusion.cpp:2566-2570) recovers a known loop-closure offset
+    and follows the NumPy/kd-tree restatement of PCL's loop: same iteration count (+-1: a criterion sitting on its threshold),
+    transform within 1e-6, same verdict; a source with nothing within reach does not converge."""
+    import liliom_b200 as L
+    rng = np.random.default_rng(4)
+    m = world_small["map"]
+    near = m[(np.abs(m[:, 0]) < 45) & (np.abs(m[:, 1]) < 45)]
+    tgt = near[rng.permutation(len(near))[:30000]].copy()
+    # source: a sub-sampled, noisy copy of part of the target seen from a frame that is off by 2.5 deg / (0.6, -0.4, 0.1) m
+    ang = np.deg2rad(2.5)
+    Rz = np.array([[np.cos(ang), -np.sin(ang), 0], [np.sin(ang), np.cos(ang), 0], [0, 0, 1.0]])
+    t_true = np.array([0.6, -0.4, 0.1])
+    pick = near[rng.permutation(len(near))[:12000]]
+    src = np.ones((len(pick), 4), np.float32)
+    src[:, :3] = ((pick[:, :3].astype(np.float64) - t_true) @ Rz + rng.normal(0, 0.01, (len(pick), 3))).astype(np.float32)   # R^T (q - t)
+    c = L.Context(variant=0)
+    T, fit, conv, it = c.icp_align(src, tgt)
+    T_o, fit_o, conv_o, it_o = _icp_numpy(oracle, src, tgt)
+    assert conv and conv_o and abs(it - it_o) <= 1 and 3 <= it < 100, (it, it_o)
+    np.testing.assert_allclose(T, T_o, rtol=0, atol=2e-6 if it == it_o else 2e-4)
+    assert abs(fit - fit_o) < 1e-6 * max(1.0, fit_o)
+    # ... and it is the right answer: target <- source = (Rz, t_true) up to the noise and the sampling
+    assert np.abs(T[:3, :3] - Rz).max() < 5e-3 and np.abs(T[:3, 3] - t_true).max() < 0.05 and fit < 0.3
+    # 32-byte clouds go through the same call
+    s32 = np.zeros(len(src), L.PT32); s32["x"], s32["y"], s32["z"] = src[:, 0], src[:, 1], src[:, 2]
+    t32 = np.zeros(len(tgt), L.PT32); t32["x"], t32["y"], t32["z"] = tgt[:, 0], tgt[:, 1], tgt[:, 2]
+    c32 = L.Context(variant=1)
+    T2, fit2, conv2, it2 = c32.icp_align(s32, t32)
+    assert it2 == it and np.array_equal(T2, T) and fit2 == fit
+    c32.close()
+    # nothing within the correspondence distance: "not enough correspondences" -> not converged, identity
+    far = src.copy(); far[:, 0] += 500.0
+    T3, fit3, conv3, it3 = c.icp_align(far, tgt, max_corr_dist=5.0)
+    assert not conv3 and it3 == 0 and np.array_equal(T3, np.eye(4))
+    c.close()
