@@ -269,9 +269,16 @@ __global__ void __launch_bounds__(VGC_THREADS) k_vg_coop(const unsigned char* __
 
     // ---- phase 1: hash insert + bounding box partials
     int lo[3] = {INT_MAX, INT_MAX, INT_MAX}, hi[3] = {INT_MIN, INT_MIN, INT_MIN}, cnt = 0;
-    for (int i = gtid; i < n; i += gthreads) {
-        const float4 v = *reinterpret_cast<const float4*>(pts + (size_t)i * STRIDE);
+    // (warp-uniform trip count: the first writers of a warp append to the voxel list with ONE atomic per warp — 1-2k atomics on a
+    // single counter were a serial chain of their own)
+    for (int i0 = gtid - lane; i0 < n; i0 += gthreads) {
+        const int i = i0 + lane;
+        const bool active = i < n;
+        float4 v = make_float4(NAN, 0.f, 0.f, 0.f);
+        if (active) v = *reinterpret_cast<const float4*>(pts + (size_t)i * STRIDE);
         int slot = -1, pos = 0;
+        bool won = false;
+        unsigned long long wkey = 0;
         if (isfinite(v.x) && isfinite(v.y) && isfinite(v.z)) {
             ++cnt;
             const int a = vg_f2ord(v.x), b = vg_f2ord(v.y), c = vg_f2ord(v.z);
@@ -288,11 +295,7 @@ __global__ void __launch_bounds__(VGC_THREADS) k_vg_coop(const unsigned char* __
                 unsigned int s = (unsigned int)((key * 0x9E3779B97F4A7C15ull) >> 48) & (VGC_T - 1);
                 while (true) {
                     const unsigned long long prev = atomicCAS(&B.hkey[s], VGC_EMPTY, key);
-                    if (prev == VGC_EMPTY) {
-                        const unsigned int u = atomicAdd(&ctl[2], 1u);
-                        B.ukey[u] = key; B.uslot[u] = (int)s;
-                        break;
-                    }
+                    if (prev == VGC_EMPTY) { won = true; wkey = key; break; }
                     if (prev == key) break;
                     s = (s + 1) & (VGC_T - 1);
                 }
@@ -300,7 +303,15 @@ __global__ void __launch_bounds__(VGC_THREADS) k_vg_coop(const unsigned char* __
                 pos = atomicAdd(&B.hcnt[s], 1);
             }
         }
-        B.pslot[i] = slot; B.ppos[i] = pos;
+        const unsigned wm = __ballot_sync(0xffffffffu, won);
+        if (wm) {
+            const int leader = __ffs(wm) - 1;
+            unsigned int ubase = 0;
+            if (lane == leader) ubase = atomicAdd(&ctl[2], (unsigned int)__popc(wm));
+            ubase = __shfl_sync(0xffffffffu, ubase, leader);
+            if (won) { const unsigned int u = ubase + (unsigned int)__popc(wm & ((1u << lane) - 1u)); B.ukey[u] = wkey; B.uslot[u] = slot; }
+        }
+        if (active) { B.pslot[i] = slot; B.ppos[i] = pos; }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -382,25 +393,44 @@ __global__ void __launch_bounds__(VGC_THREADS) k_vg_coop(const unsigned char* __
             for (int v = tid; v < U; v += VGC_THREADS) S.ukeys[v] = __ldcg(&B.ukey[v]);
             __syncthreads();
         }
-        for (int u = gwarp; u < U; u += gwarps) {
-            const unsigned long long my = in_smem ? S.ukeys[u] : __ldcg(&B.ukey[u]);
-            int below = 0;
-            if (in_smem) {
+        // (block-uniform trip count: the member segments of a block's voxels are carved out of the cursor with ONE atomic per block
+        // and iteration instead of one per voxel on the same word)
+        for (int ub = 0; ub < U; ub += gwarps) {
+            const int u = ub + gwarp;
+            const bool valid = u < U;
+            int below = 0, s = 0, c = 0;
+            if (valid) {
+                const unsigned long long my = in_smem ? S.ukeys[u] : __ldcg(&B.ukey[u]);
+                if (in_smem) {
 #pragma unroll 4
-                for (int v = lane; v < U; v += 32) below += (S.ukeys[v] < my) ? 1 : 0;
-            } else {
+                    for (int v = lane; v < U; v += 32) below += (S.ukeys[v] < my) ? 1 : 0;
+                } else {
 #pragma unroll 4
-                for (int v = lane; v < U; v += 32) below += (__ldcg(&B.ukey[v]) < my) ? 1 : 0;
-            }
+                    for (int v = lane; v < U; v += 32) below += (__ldcg(&B.ukey[v]) < my) ? 1 : 0;
+                }
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) below += __shfl_xor_sync(0xffffffffu, below, o);
-            if (lane == 0) {
-                const int s = __ldcg(&B.uslot[u]);
-                const int c = __ldcg(&B.hcnt[s]);
-                if (c > VGC_VCAP) atomicOr(&ctl[1], 2u);
-                B.hoff[s] = (int)atomicAdd(&ctl[3], (unsigned int)c);
+                for (int o = 16; o > 0; o >>= 1) below += __shfl_xor_sync(0xffffffffu, below, o);
+                if (lane == 0) {
+                    s = __ldcg(&B.uslot[u]);
+                    c = __ldcg(&B.hcnt[s]);
+                    if (c > VGC_VCAP) atomicOr(&ctl[1], 2u);
+                }
+            }
+            if (lane == 0) S.red[0][warp] = c;                 // (the box partials in S.red were consumed before barrier 1)
+            __syncthreads();
+            if (tid == 0) {
+                int tot = 0;
+                for (int w = 0; w < VGC_WARPS; ++w) tot += S.red[0][w];
+                S.red[1][0] = tot ? (int)atomicAdd(&ctl[3], (unsigned int)tot) : 0;
+            }
+            __syncthreads();
+            if (valid && lane == 0) {
+                int off = S.red[1][0];
+                for (int w = 0; w < warp; ++w) off += S.red[0][w];
+                B.hoff[s] = off;
                 B.urank[u] = below;
             }
+            __syncthreads();
         }
         vgc_barrier(&ctl[0], 2u * G);
         if (stamp) stamp[2] = clock64();
