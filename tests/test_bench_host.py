@@ -57,3 +57,38 @@ def test_tools_and_entry_points_compile():
     assert len(files) >= 8
     for f in files:
         py_compile.compile(f, doraise=True)
+
+
+def test_workload_resolution_and_shared_config():
+    """Both bench arms (ours / --impl reference) must describe the SAME workload with the SAME `config` object, at N = 1 (configs[1])
+    and at N > 1 (the streamed configs[4] workload, sharded)."""
+    import argparse
+    import bench
+    a = argparse.Namespace(multi="sharded", workload="", map_points=0)
+    assert bench.resolve_workload(a, 1) == ("horizon", 1_000_000)
+    assert bench.resolve_workload(a, 8) == ("stream", 10_000_000)
+    a.multi = "replicas"
+    assert bench.resolve_workload(a, 8) == ("horizon", 1_000_000)
+    a.workload = "rot"
+    assert bench.resolve_workload(a, 1) == ("rot", 2_000_000)
+    c1 = bench.config_dict("stream", 127788, 10_000_000, 8, "sharded")
+    c2 = bench.config_dict("stream", 127788, 10_000_000, 8, "sharded")
+    assert c1 == c2 and c1["map_frames"] == bench.N_FRAMES and "streamed" in c1["workload"] and c1["multi"] == "sharded"
+    assert bench.config_dict("horizon", 20458, 1_000_000, 1, "sharded")["multi"] == "single"
+
+
+def test_stream_frames_partition_the_map():
+    """The streamed workload's 20 frames are a partition of the synthetic map (equal slabs along x, oldest first)."""
+    import numpy as np
+    import bench
+    from liliom_b200 import synth
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__))))
+    import oracle_lib as O
+    m, _ = synth.make_map(50_000)
+    frames = bench.make_frames(m, O.PT32)
+    assert len(frames) == bench.N_FRAMES and sum(len(f) for f in frames) == len(m)
+    allx = np.concatenate([f["x"] for f in frames])
+    assert np.all(np.diff(allx) >= 0)                                   # slabs in ascending x
+    got = np.sort(np.stack([np.concatenate([f[k] for f in frames]) for k in ("x", "y", "z")], 1).view([("", "f4")] * 3), axis=0)
+    want = np.sort(np.ascontiguousarray(m[:, :3]).view([("", "f4")] * 3), axis=0)
+    assert np.array_equal(got, want)
