@@ -81,44 +81,77 @@ def measured_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (recipe's clocks line).  Rank 0 only: one poller per
-    node is enough, and N pollers forking nvidia-smi at 10 Hz compete with the ranks' own host threads."""
+    """nvidia-smi clocks / throttle reasons during the timed regions (the profiling recipe's clocks line): ONE `nvidia-smi
+    --query-gpu=... -lms` process, started well before the first timed step and stopped after the last, its rows stamped on
+    arrival; summary() keeps the rows that fall inside the window.  (One looping process rather than one process per sample:
+    every nvidia-smi start-up initialises NVML and takes driver locks for several ms, which a 20-step timed region of ~10 ms
+    would feel as launch latency.)  Rank 0 only: one poller per node is enough."""
+    PERIOD_MS = 25
 
     def __init__(self, index: int, enabled: bool = True):
         self.index = index
         self.enabled = enabled
-        self.rows = []
-        self._stop = threading.Event()
+        self.rows = []            # (monotonic arrival time, fields)
+        self.t0 = self.t1 = None
+        self._p = None
         self._t = None
 
-    def _run(self):
+    def start(self):
+        if not self.enabled or self._p is not None:
+            return self
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-        while not self._stop.is_set():
+        try:
+            self._p = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                        "-lms", str(self.PERIOD_MS)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, bufsize=1)
+        except Exception:
+            self._p = None
+            return self
+
+        def reader():
             try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
+                for ln in self._p.stdout:
+                    ln = ln.strip()
+                    if ln:
+                        self.rows.append((time.monotonic(), [x.strip() for x in ln.split(",")]))
             except Exception:
                 pass
-            self._stop.wait(0.02)
+        self._t = threading.Thread(target=reader, daemon=True)
+        self._t.start()
+        return self
 
-    def __enter__(self):
-        if self.enabled:
-            self._t = threading.Thread(target=self._run, daemon=True)
-            self._t.start()
+    def __enter__(self):                      # the window: the timed regions
+        self.start()
+        self.t0 = time.monotonic()
         return self
 
     def __exit__(self, *a):
-        self._stop.set()
-        if self._t:
-            self._t.join(timeout=6)
+        self.t1 = time.monotonic()
+
+    def stop(self):
+        if self._p is not None:
+            time.sleep(2.5 * self.PERIOD_MS * 1e-3)           # let the sample after the window arrive
+            try:
+                self._p.terminate()
+                self._p.wait(timeout=3)
+            except Exception:
+                try:
+                    self._p.kill()
+                except Exception:
+                    pass
+            if self._t:
+                self._t.join(timeout=3)
+            self._p = None
 
     def summary(self):
+        self.stop()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        t0 = self.t0 if self.t0 is not None else float("-inf")
+        t1 = self.t1 if self.t1 is not None else float("inf")
+        slack = 1.5 * self.PERIOD_MS * 1e-3                    # a row is stamped when it ARRIVES, up to one period after its sample
+        inside = [r for t, r in self.rows if t0 <= t <= t1 + slack]
+        for r in inside:
             try:
                 sm.append(float(r[0])); mx.append(float(r[1]))
                 for k, nm in enumerate(names):
@@ -127,7 +160,7 @@ class ClockSampler:
             except Exception:
                 pass
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "period_ms": self.PERIOD_MS}
 
 
 def run_two_stage_pipeline(total, warmup, nbuf, stage_a, stage_b, on_start, on_end, timeout_s=120.0):
@@ -407,6 +440,7 @@ def bench_body(args, fallback_note=None):
     if args.dense_queries:
         prm.leaf_scan = 0.0        # no scan down-sampling: every surf feature is a query (roofline micro-run)
     stream = torch.cuda.Stream()
+    clk = ClockSampler(local_rank, enabled=(rank == 0)).start()      # running long before the first timed step
     ident = np.array([1.0, 0, 0, 0, 0, 0, 0])
     use_nccl_exchange = bool(os.environ.get("LILIOM_BENCH_NCCL"))
 
@@ -609,6 +643,8 @@ def bench_body(args, fallback_note=None):
         ctx.set_stream(stream.cuda_stream)
         return ms, (result["pose"], result["h2d"], result["d2h"])
 
+    step_dist = {}                  # per-step device times of the last timed() call per step function (this rank)
+
     def timed(fn, n_steps, n_warm, prep=None, after_warmup=None, collective=True):
         """n_warm untimed steps, then n_steps steps each bracketed by its own CUDA-event pair on the launch stream, a 256 MB
         L2-evicting write between them.  Returns (this rank's total ms, last result)."""
@@ -620,6 +656,7 @@ def bench_body(args, fallback_note=None):
         else: torch.cuda.synchronize()
         tot_ms = 0.0
         last = None
+        per_step = []
         with torch.cuda.stream(stream):
             for k in range(n_steps):
                 if prep: prep(k)
@@ -629,9 +666,11 @@ def bench_body(args, fallback_note=None):
                 last = fn(k)
                 e1.record(stream)
                 e1.synchronize()
-                tot_ms += e0.elapsed_time(e1)
+                per_step.append(e0.elapsed_time(e1))
+                tot_ms += per_step[-1]
         if collective: barrier()
         else: torch.cuda.synchronize()
+        step_dist[fn.__name__] = per_step
         return tot_ms, last
 
     def over_ranks(ms):
@@ -651,7 +690,7 @@ def bench_body(args, fallback_note=None):
 
     # ---- timed region 1: device-resident; counters cover exactly the timed steps
     cnt_box = {}
-    with ClockSampler(local_rank, enabled=(rank == 0)) as clk:
+    with clk:
         def after_warm():
             ctx.counters(reset=True)
             for v in cx_phase_ms.values():
@@ -672,6 +711,11 @@ def bench_body(args, fallback_note=None):
             ms_e2e, _ = over_ranks(ms_e2e_local)
     clocks = clk.summary()
     ctx.counters(reset=True)
+
+    def dist_of(name):
+        v = sorted(step_dist.get(name) or [])
+        return {"min": v[0], "median": v[len(v) // 2], "max": v[-1]} if v else None
+    step_ms = {"resident": dist_of("step_resident"), "e2e_sequential": dist_of("step_e2e")}
 
     replicas = multi and not sharded
     scans_total = steps * (world if replicas else 1)
@@ -860,7 +904,7 @@ def bench_body(args, fallback_note=None):
         "ms_per_step": ms_res / steps, "higher_is_better": True,
         "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": cfg, "run": run,
-        "gpu_launches": int(cnt.launches),
+        "step_ms": step_ms, "gpu_launches": int(cnt.launches),
         "lib_calls": int(cnt.lib_launches),
         "e2e": {"value": e2e_val, "unit": "scans/s", "ms_per_step": ms_e2e / steps,
                 "h2d_bytes_per_step": int(last_e2e[1]), "d2h_bytes_per_step": int(last_e2e[2]),

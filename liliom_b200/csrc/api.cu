@@ -230,6 +230,9 @@ extern "C" int liliom_create(liliom_ctx** out, const liliom_params* p, int devic
     c->h_pin_bytes = 1 << 20;
     e = cudaHostAlloc(&c->h_pin, c->h_pin_bytes, cudaHostAllocDefault);
     if (e != cudaSuccess) { cudaStreamDestroy(c->own_stream); delete c; return LILIOM_E_CUDA; }
+    // the GN kernel writes its results straight into this block when the device can address it (UVA: always, in practice)
+    if (cudaHostGetDevicePointer(&c->h_pin_dev, c->h_pin, 0) != cudaSuccess) { c->h_pin_dev = nullptr; (void)cudaGetLastError(); }
+    if (const char* e9 = getenv("LILIOM_HOST_RESULTS")) c->host_results = atoi(e9) != 0;
     if (const char* e1 = getenv("LILIOM_KNN_LANES")) { int v = atoi(e1); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16) c->force_lanes = v; }
     c->dbg_timing = getenv("LILIOM_DEBUG_TIMING") != nullptr;
     if (const char* e8 = getenv("LILIOM_KNN_TMA")) c->knn_tma = atoi(e8) != 0;

@@ -59,6 +59,26 @@ struct PeerArgs {
     unsigned int* lflag;       // [2] epoch of the republished sums
 };
 
+// Scan-to-map results written straight into the context's pinned host block by the persistent GN kernel (zero-copy: the
+// stream then ends with the kernel and the host reads the block after its stream synchronise), and the start pose as a
+// kernel parameter: per scan this removes one host-to-device and three device-to-host copy operations from the stream,
+// each of which costs a few microseconds of dependent latency on a ~200 us step.  Layout of host_out = s2m_run's `hp`.
+struct GnIo {
+    double pose0[8];           // start pose (wxyz, t) + cleared peer-loss flag; used when use_pose0
+    int    use_pose0;
+    int    n_vgp_words;        // 32-bit words of VgParams to forward (0: none)
+    double* host_out;          // device-visible address of the pinned block, nullptr: results stay on the device
+    const int* vgp;            // VgParams of the scan's VoxelGrid (speculation check), forwarded to host_out + 48
+};
+
+#ifdef __CUDACC__
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#endif
+
 constexpr int kStatsDoubles = 40;   // per outer iteration on the device: n_corr, lm_iters, cost, 27, pose7, pad
 constexpr int kNormEq = 29;         // 21 + 6 + cost + count
 
@@ -87,6 +107,8 @@ struct liliom_ctx {
 
     // ---- staging (pinned host) ----
     void*  h_pin = nullptr;      // small pinned block: counts, pose, stats
+    void*  h_pin_dev = nullptr;  // the same block as the device sees it (mapped); nullptr: not mappable, results are copied
+    bool   host_results = true;  // LILIOM_HOST_RESULTS=0: always copy (A/B switch)
     size_t h_pin_bytes = 0;
 
     // ---- extraction ----

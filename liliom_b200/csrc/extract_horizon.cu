@@ -380,7 +380,7 @@ __global__ void __launch_bounds__(HZC_THREADS) k_hz_coop(const Pt48* __restrict_
     // bit 31 of `call` (LILIOM_DEBUG_TIMING): block 0 leaves clock64 stamps of the stage boundaries in the spare control words
     long long* stamp = ((call >> 31) != 0u && b == 0 && tid == 0) ? reinterpret_cast<long long*>(ctl + 4) : nullptr;
     call &= 0x7fffffffu;
-    if (stamp) stamp[0] = clock64();
+    if (stamp) { stamp[0] = clock64(); stamp[10] = (long long)globaltimer_ns(); }
     unsigned int* bar = ctl + (call & 3u);
     if (b == 0 && tid == 0) ctl[(call + 1u) & 3u] = 0u;      // the next launch's barrier word
     // ---- A
@@ -439,7 +439,7 @@ __global__ void __launch_bounds__(HZC_THREADS) k_hz_coop(const Pt48* __restrict_
         hz_patch_emit(P, lane, surf + os, edge + oe);
         if (patch == HZ_PATCHES - 1 && lane == 0) { totals[0] = os + P.ns; totals[1] = oe + P.ne; }
     }
-    if (stamp) stamp[4] = clock64();
+    if (stamp) { stamp[4] = clock64(); stamp[11] = (long long)globaltimer_ns(); }
 }
 
 // raw points must already be in c->raw (n x 48 B).  Leaves cut/surf/edge on the device and the

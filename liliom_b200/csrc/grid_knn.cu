@@ -638,7 +638,7 @@ __global__ void __launch_bounds__(kBlock, LANES == 1 ? LILI_KNN1_MINBLOCKS : 2) 
 #define LILI_GN_BOUNDS __maxnreg__(LILI_GN_MAXNREG)
 template <int LANES, bool TMA = false>
 __global__ void LILI_GN_BOUNDS k_gn_persistent(KnnArgs a, int iters, unsigned int* bar, double* stats_base, unsigned int bar_base,
-                                                             int sync_mode, const __grid_constant__ PeerArgs pa) {
+                                                             int sync_mode, const __grid_constant__ PeerArgs pa, const __grid_constant__ GnIo io) {
     __shared__ __align__(16) KnnSmem S;
     unsigned stage_phase = 0;
     if constexpr (TMA) {       // one mbarrier per lane group, 16 arrivals (every lane of the group, with or without a run to stage)
@@ -649,7 +649,8 @@ __global__ void LILI_GN_BOUNDS k_gn_persistent(KnnArgs a, int iters, unsigned in
     }
     const int n_q = a.n_dev ? min(*a.n_dev, a.n) : a.n;
     if (threadIdx.x == 32) S.peer_lost = 0;
-    if (threadIdx.x < 7) S.pose[threadIdx.x] = a.pose[threadIdx.x];
+    if (threadIdx.x < 7) S.pose[threadIdx.x] = io.use_pose0 ? io.pose0[threadIdx.x] : a.pose[threadIdx.x];
+    if (a.dbg && blockIdx.x == 0 && threadIdx.x == 0) a.dbg[30] = (long long)globaltimer_ns();
     __syncthreads();
     const unsigned int G = gridDim.x;
     // bar_base = arrivals of all previous launches on this context (tracked by the host, advanced by iters*G per launch)
@@ -735,11 +736,22 @@ __global__ void LILI_GN_BOUNDS k_gn_persistent(KnnArgs a, int iters, unsigned in
             }
         }
         if (blockIdx.x == 0) write_neq_stats(a, S, stats, true);
+        if (blockIdx.x == 0 && it == iters - 1 && io.host_out) {      // results straight into the host's pinned block
+            if (threadIdx.x == 0) {
+#pragma unroll
+                for (int k = 0; k < 7; ++k) io.host_out[k] = S.pose[k];
+                io.host_out[7] = (pa.enabled && S.peer_lost) ? 1.0 : 0.0;
+                if (a.n_dev) *reinterpret_cast<int*>(io.host_out + 40) = *a.n_dev;
+            }
+            if (threadIdx.x >= 32 && threadIdx.x < 32 + io.n_vgp_words) reinterpret_cast<int*>(io.host_out + 48)[threadIdx.x - 32] = io.vgp[threadIdx.x - 32];
+            __threadfence_system();
+        }
         __syncthreads();
         // the partials of this iteration may only be overwritten after every block has summed them: the next
         // barrier is behind the next write, so alternate between two partial buffers
         a.partials = (it & 1) ? a.partials - (size_t)kNormEq * G : a.partials + (size_t)kNormEq * G;
     }
+    if (a.dbg && blockIdx.x == 0 && threadIdx.x == 0) a.dbg[31] = (long long)globaltimer_ns();
 }
 
 // GN step for the multi-GPU path: runs after the all-reduce of neq[29], identically on every rank.
@@ -1057,7 +1069,8 @@ int s2m_run(liliom_ctx* c, double pose7[7], int match_cnt, int max_num_iter, int
     }
 
     LILI_CUDA(c, c->pose_dev.ensure(16 * sizeof(double)));
-    LILI_CUDA(c, c->partials.ensure((size_t)2 * grid * kNormEq * sizeof(double)));   // two buffers (persistent kernel alternates)
+    // two buffers (the persistent kernel alternates); sized for the largest grid so that a bigger scan never reallocates mid-stream
+    LILI_CUDA(c, c->partials.ensure((size_t)2 * max(grid, c->sm_count * 2) * kNormEq * sizeof(double)));
     LILI_CUDA(c, c->neq.ensure(32 * sizeof(double)));
     LILI_CUDA(c, c->stats_dev.ensure((size_t)(iters + 1) * kStatsDoubles * sizeof(double)));
     if (!c->counter.p) {
@@ -1113,7 +1126,10 @@ int s2m_run(liliom_ctx* c, double pose7[7], int match_cnt, int max_num_iter, int
     const bool peer = c->peer_ready && c->peer_ptrs[c->rank] != nullptr;       // fused exchange instead of ncclAllReduce + k_gn_update
     const bool persistent = mode == LILIOM_MODE_GN && (c->nranks == 1 || peer) && iters > 0 && !want_corr &&
                             !getenv("LILIOM_NO_PERSISTENT") && grid <= c->sm_count;
-    {
+    // zero-copy results (GnIo): the persistent kernel takes the start pose as a parameter and leaves pose, query count and
+    // VoxelGrid parameters in the pinned block itself; only per-iteration stats / the 29 sums still travel by copy
+    const bool host_io = persistent && c->host_results && c->h_pin_dev != nullptr;
+    if (!host_io) {
         double p8[8] = {pose7[0], pose7[1], pose7[2], pose7[3], pose7[4], pose7[5], pose7[6], 0.0};      // [7]: peer-loss flag, cleared
         double* pin = reinterpret_cast<double*>(c->h_pin) + 56;      // pinned staging (slots 56..63 of the small block; results land in 0..55)
         memcpy(pin, p8, sizeof(p8));
@@ -1135,7 +1151,15 @@ int s2m_run(liliom_ctx* c, double pose7[7], int match_cnt, int max_num_iter, int
             pa.epoch0 = c->peer_epoch + 1u;          // every rank makes the same sequence of calls: same epochs everywhere
             c->peer_epoch += (unsigned int)iters;
         }
-        void* kargs[] = {&a, &iters_arg, &bar, &stats_base, &bar_base, &sync_mode, &pa};
+        GnIo io{};
+        if (host_io) {
+            for (int k = 0; k < 7; ++k) io.pose0[k] = pose7[k];
+            io.use_pose0 = 1;
+            io.host_out = reinterpret_cast<double*>(c->h_pin_dev);
+            io.vgp = c->vg_check ? c->vg_params.as<int>() : nullptr;
+            io.n_vgp_words = c->vg_check ? (int)(sizeof(VgParams) / sizeof(int)) : 0;
+        }
+        void* kargs[] = {&a, &iters_arg, &bar, &stats_base, &bar_base, &sync_mode, &pa, &io};
         const bool tma = lanes == 16 && c->knn_tma;
         size_t dyn_p = dyn_smem;
         if (tma) {
@@ -1218,10 +1242,10 @@ int s2m_run(liliom_ctx* c, double pose7[7], int match_cnt, int max_num_iter, int
     }
     // ---- results: pose + stats in one pinned block
     double* hp = reinterpret_cast<double*>(c->h_pin);
-    LILI_CUDA(c, cudaMemcpyAsync(hp, c->pose_dev.p, 8 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));     // pose + peer-loss flag
+    if (!host_io) LILI_CUDA(c, cudaMemcpyAsync(hp, c->pose_dev.p, 8 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));     // pose + peer-loss flag
     if (out29) LILI_CUDA(c, cudaMemcpyAsync(hp + 8, c->neq.p, kNormEq * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    if (c->d_nfeats) LILI_CUDA(c, cudaMemcpyAsync(hp + 40, c->d_nfeats, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    if (c->vg_check) LILI_CUDA(c, cudaMemcpyAsync(hp + 48, c->vg_params.p, sizeof(VgParams), cudaMemcpyDeviceToHost, c->stream));
+    if (c->d_nfeats && !host_io) LILI_CUDA(c, cudaMemcpyAsync(hp + 40, c->d_nfeats, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    if (c->vg_check && !host_io) LILI_CUDA(c, cudaMemcpyAsync(hp + 48, c->vg_params.p, sizeof(VgParams), cudaMemcpyDeviceToHost, c->stream));
     const bool want_stats = stats && iters > 0;
     if (want_stats) {
         size_t bytes = (size_t)iters * kStatsDoubles * sizeof(double);
@@ -1250,15 +1274,23 @@ int s2m_run(liliom_ctx* c, double pose7[7], int match_cnt, int max_num_iter, int
         }
     }
     if (a.dbg && c->dbg_timing) {       // stage clocks of the two cooperative kernels that ran before this call (resident pipeline)
-        long long t[10];
-        if (c->hz_ctl.p && cudaMemcpy(t, c->hz_ctl.as<unsigned char>() + 16, sizeof(t), cudaMemcpyDeviceToHost) == cudaSuccess && t[4] > t[0])
+        long long t[12], gt[6] = {0, 0, 0, 0, 0, 0};
+        if (c->hz_ctl.p && cudaMemcpy(t, c->hz_ctl.as<unsigned char>() + 16, sizeof(t), cudaMemcpyDeviceToHost) == cudaSuccess && t[4] > t[0]) {
+            gt[0] = t[10]; gt[1] = t[11];
             fprintf(stderr, "[k_hz_coop, cycles, block 0] A keep-flags+barrier %lld, B de-skew/bin+barrier %lld, C patches+barrier %lld (patch 0: window %lld, "
                             "lists %lld, centroid+scatter %lld, eigen %lld, decisions %lld), D emit %lld\n",
                     t[1] - t[0], t[2] - t[1], t[3] - t[2], t[5] - t[2], t[6] - t[5], t[7] - t[6], t[8] - t[7], t[9] - t[8], t[4] - t[3]);
+        }
         const long long* vs = vg_coop_stamps(c);
-        if (vs && cudaMemcpy(t, vs, sizeof(t), cudaMemcpyDeviceToHost) == cudaSuccess && t[4] > t[0])
+        if (vs && cudaMemcpy(t, vs, 7 * sizeof(long long), cudaMemcpyDeviceToHost) == cudaSuccess && t[4] > t[0]) {
+            gt[2] = t[5]; gt[3] = t[6];
             fprintf(stderr, "[k_vg_coop, cycles, block 0] 1 hash insert+barrier %lld, 2 ranks+barrier %lld, 3 group+barrier %lld, 4 centroids %lld\n",
                     t[1] - t[0], t[2] - t[1], t[3] - t[2], t[4] - t[3]);
+        }
+        if (cudaMemcpy(t, a.dbg + 30, 2 * sizeof(long long), cudaMemcpyDeviceToHost) == cudaSuccess) { gt[4] = t[0]; gt[5] = t[1]; }
+        if (gt[0] && gt[2] && gt[4])      // the step's device timeline (block 0 of each kernel, %globaltimer)
+            fprintf(stderr, "[step timeline, ns from k_hz_coop start] hz 0..%lld | gap %lld | vg %lld..%lld | gap %lld | gn %lld..%lld (%lld)\n",
+                    gt[1] - gt[0], gt[2] - gt[1], gt[2] - gt[0], gt[3] - gt[0], gt[4] - gt[3], gt[4] - gt[0], gt[5] - gt[0], gt[5] - gt[4]);
     }
     if (a.dbg) {
         long long h[24];

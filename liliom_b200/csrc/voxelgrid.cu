@@ -261,7 +261,7 @@ __global__ void __launch_bounds__(VGC_THREADS) k_vg_coop(const unsigned char* __
     // bit 31 of `call` (LILIOM_DEBUG_TIMING): block 0 leaves clock64 stamps of the phase boundaries behind the 16 control words
     long long* stamp = ((call >> 31) != 0u && blockIdx.x == 0 && tid == 0) ? reinterpret_cast<long long*>(B.ctl + 16) : nullptr;
     call &= 0x7fffffffu;
-    if (stamp) stamp[0] = clock64();
+    if (stamp) { stamp[0] = clock64(); stamp[5] = (long long)globaltimer_ns(); }
     unsigned int* ctl = B.ctl + 4 * (call & 3u);          // [0] barrier, [1] bail, [2] #voxels, [3] segment cursor
     if (blockIdx.x == 0 && tid < 4) B.ctl[4 * ((call + 1u) & 3u) + tid] = 0u;   // the next launch's slot (nobody uses it now)
     const int n = d_n ? min(*d_n, n_max) : n_max;
@@ -521,7 +521,7 @@ __global__ void __launch_bounds__(VGC_THREADS) k_vg_coop(const unsigned char* __
         }
         __syncwarp();
     }
-    if (stamp) stamp[4] = clock64();
+    if (stamp) { stamp[4] = clock64(); stamp[6] = (long long)globaltimer_ns(); }
 }
 
 // stage stamps of the last k_vg_coop launch (LILIOM_DEBUG_TIMING); nullptr before the first launch

@@ -4,6 +4,8 @@
   fused peer exchange of one rank with itself (the whole NVLink protocol on a single GPU)
   LILIOM_KNN_TMA  = 1 the 16-lane search stages every run with one cp.async.bulk into shared memory (mbarrier) instead of
                     batches of 16-byte loads through registers
+  LILIOM_HOST_RESULTS = 0 the start pose travels by a host-to-device copy and pose / query count / VoxelGrid parameters come back
+                    by three device-to-host copies, instead of a kernel parameter and stores into the mapped pinned block (default)
 Same candidate sets, same per-row arithmetic, same summation trees -> identical poses, correspondences and sums."""
 import os
 
@@ -12,16 +14,17 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
-# (unused, mode): mode % 10 = LILIOM_GN_SYNC; +20: fused peer exchange with itself; +30: bulk-copy staging
-VARIANTS = [(0, 3), (0, 1), (0, 0), (0, 23), (0, 33)]
+# (unused, mode): mode % 10 = LILIOM_GN_SYNC; +20: fused peer exchange with itself; +30: bulk-copy staging; +40: results by copies
+VARIANTS = [(0, 3), (0, 1), (0, 0), (0, 23), (0, 33), (0, 43)]
 
 
 def _ctx(flat, ll):
     import liliom_b200 as L
-    keys = ("LILIOM_GN_SYNC", "LILIOM_KNN_TMA")
+    keys = ("LILIOM_GN_SYNC", "LILIOM_KNN_TMA", "LILIOM_HOST_RESULTS")
     old = {k: os.environ.get(k) for k in keys}
     os.environ["LILIOM_GN_SYNC"] = str(ll % 10)
-    os.environ["LILIOM_KNN_TMA"] = "1" if ll >= 30 else "0"
+    os.environ["LILIOM_KNN_TMA"] = "1" if 30 <= ll < 40 else "0"
+    os.environ["LILIOM_HOST_RESULTS"] = "0" if 40 <= ll < 50 else "1"
     try:
         c = L.Context(variant=0)             # the switches are read at liliom_create
         if 20 <= ll < 30:                    # one rank exchanging with itself: the whole protocol on a single GPU

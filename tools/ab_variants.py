@@ -25,11 +25,13 @@ stream = torch.cuda.Stream()
 ref = None
 print(f"lib: {L.LIB_PATH}")
 for sync in cfgs:
-    os.environ["LILIOM_GN_SYNC"] = str(sync % 10); os.environ["LILIOM_KNN_TMA"] = "1" if sync >= 30 else "0"
+    tens = (sync // 10) % 10                      # 3: bulk-copy staging; 4: results by copies (LILIOM_HOST_RESULTS=0); +100: kernel-timing events off
+    os.environ["LILIOM_GN_SYNC"] = str(sync % 10); os.environ["LILIOM_KNN_TMA"] = "1" if tens == 3 else "0"
+    os.environ["LILIOM_HOST_RESULTS"] = "0" if tens == 4 else "1"
     c = L.Context(variant=0)
     c.set_stream(stream.cuda_stream)
     c.map_set_points(m)
-    c.set_kernel_timing(True)
+    c.set_kernel_timing(sync < 100)
     poses = []
     tot = 0.0
     with torch.cuda.stream(stream):
