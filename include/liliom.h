@@ -297,7 +297,9 @@ int liliom_get_counters(liliom_ctx* c, liliom_counters* out, int reset);
  * rank when the map is sharded), out2[1] = map points in their full 3x3x3 cell blocks.  The search itself examines fewer
  * (pruning; knn_candidates above counts those).  Not on the hot path. */
 int liliom_knn_block_stats(liliom_ctx* c, const double pose7[7], unsigned long long out2[2]);
-/* 1: bracket every kNN+Jacobian launch with CUDA events on the context stream (default 0). */
+/* on = 1: bracket every kNN+Jacobian launch with a CUDA-event pair on the context stream and count its queries /
+ * candidates on the device; on = N > 1: do so on every N-th scan-to-map call only (an event pair costs the step ~4 us each
+ * of dependent stream latency, measured: profiles/r02_ab_host_results.txt); 0 (default): off. */
 int liliom_set_kernel_timing(liliom_ctx* c, int on);
 /* Run all library work on a caller-owned CUDA stream (cudaStream_t passed as void*; NULL restores the
  * context's own stream).  Calls stay synchronous; this only lets the caller bracket them with events. */

@@ -500,8 +500,9 @@ class Context:
         self._check(lib().liliom_knn_block_stats(self._h, _dptr(p), out))
         return int(out[0]), int(out[1])
 
-    def set_kernel_timing(self, on: bool):
-        self._check(lib().liliom_set_kernel_timing(self._h, 1 if on else 0))
+    def set_kernel_timing(self, on):
+        """True / 1: time every kNN+Jacobian launch; N > 1: every N-th scan-to-map call; False / 0: off."""
+        self._check(lib().liliom_set_kernel_timing(self._h, int(on)))
 
 
 def comm_get_unique_id() -> bytes:

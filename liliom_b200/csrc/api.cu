@@ -985,5 +985,7 @@ extern "C" int liliom_knn_block_stats(liliom_ctx* c, const double pose7[7], unsi
 extern "C" int liliom_set_kernel_timing(liliom_ctx* c, int on) {
     if (!c) return LILIOM_E_ARG;
     c->time_kernels = on != 0;
+    c->time_every = on > 1 ? on : 1;
+    c->time_calls = 0;
     return LILIOM_OK;
 }

@@ -184,6 +184,8 @@ struct liliom_ctx {
     // ---- instrumentation ----
     liliom_counters cnt{};
     bool time_kernels = false;
+    int  time_every = 1;          // liliom_set_kernel_timing(c, N): time every N-th scan-to-map call
+    unsigned time_calls = 0;
     int force_lanes = 0, force_rounds = 0;   // tuning override (LILIOM_KNN_LANES / LILIOM_KNN_ROUNDS)
     int gn_sync = 3;                     // persistent GN kernel grid barrier (LILIOM_GN_SYNC): 3 = release-only arrival, no acquire fence (default),
                                          // 0 = full fences on both sides

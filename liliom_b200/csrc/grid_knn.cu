@@ -1051,6 +1051,8 @@ int s2m_run(liliom_ctx* c, double pose7[7], int match_cnt, int max_num_iter, int
     // the per-iteration stats come back through the pinned block: check its capacity before anything is enqueued
     if (stats && match_cnt > 0 && 64 * sizeof(double) + (size_t)match_cnt * kStatsDoubles * sizeof(double) > c->h_pin_bytes) return LILIOM_E_CAPACITY;
     const int iters = match_cnt;
+    // kernel timing (liliom_set_kernel_timing): an event pair + the device-side query/candidate counts on every time_every-th call
+    const bool timed = c->time_kernels && (c->time_calls++ % (unsigned)c->time_every) == 0;
     const int n_est = c->d_nfeats ? (c->last_n_feats > 0 ? min(c->last_n_feats, n) : n) : n;   // device-side count: predict from the last scan
     int lanes = 8, rounds = 1;
     pick_shape(n_est, c->sm_count, lanes, rounds);
@@ -1099,8 +1101,8 @@ int s2m_run(liliom_ctx* c, double pose7[7], int match_cnt, int max_num_iter, int
     a.nn_sqd = want_corr ? c->nn_sqd.as<float>() : nullptr;
     a.partials = c->partials.as<double>(); a.neq = c->neq.as<double>();
     a.ticket = c->counter.as<unsigned int>();
-    a.cand_total = c->time_kernels ? reinterpret_cast<unsigned long long*>(c->counter.as<unsigned char>() + 16) : nullptr;
-    a.queries_total = c->time_kernels ? reinterpret_cast<unsigned long long*>(c->counter.as<unsigned char>() + 24) : nullptr;
+    a.cand_total = timed ? reinterpret_cast<unsigned long long*>(c->counter.as<unsigned char>() + 16) : nullptr;
+    a.queries_total = timed ? reinterpret_cast<unsigned long long*>(c->counter.as<unsigned char>() + 24) : nullptr;
     a.tau0 = knn_gate_tau(c->prm.knn_max_sqdist);
     LILI_CUDA(c, c->qstate.ensure((size_t)(n > 0 ? n : 1) * sizeof(float4)));
     a.qstate = c->qstate.as<float4>();
@@ -1173,7 +1175,7 @@ int s2m_run(liliom_ctx* c, double pose7[7], int match_cnt, int max_num_iter, int
                        : lanes == 2 ? (const void*)k_gn_persistent<2> : lanes == 4 ? (const void*)k_gn_persistent<4>
                                                                                    : (const void*)k_gn_persistent<8>;
         size_t ev = 0;
-        if (c->time_kernels) {
+        if (timed) {
             if (c->ev_used + 2 > c->ev_pool.size()) {
                 for (int k = 0; k < 64; ++k) { cudaEvent_t e; LILI_CUDA(c, cudaEventCreate(&e)); c->ev_pool.push_back(e); }
             }
@@ -1183,7 +1185,7 @@ int s2m_run(liliom_ctx* c, double pose7[7], int match_cnt, int max_num_iter, int
         LILI_CUDA(c, cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kBlock), kargs, dyn_p, c->stream));
         LILI_TRY(launch_check(c, "k_gn_persistent"));
         c->bar_arrivals += (unsigned int)iters * (unsigned int)grid;
-        if (c->time_kernels) {
+        if (timed) {
             LILI_CUDA(c, cudaEventRecord(c->ev_pool[ev + 1], c->stream));
             c->ev_pending.push_back({ev, (unsigned long long)n_est * iters});
             c->ev_iters.push_back(iters);
@@ -1205,7 +1207,7 @@ int s2m_run(liliom_ctx* c, double pose7[7], int match_cnt, int max_num_iter, int
         }
         a.update_pose = (mode == LILIOM_MODE_GN && (!multi || peer_iter) && iters > 0) ? 1 : 0;
         size_t ev = 0;
-        if (c->time_kernels) {
+        if (timed) {
             if (c->ev_used + 2 > c->ev_pool.size()) {
                 for (int k = 0; k < 64; ++k) { cudaEvent_t e; LILI_CUDA(c, cudaEventCreate(&e)); c->ev_pool.push_back(e); }
             }
@@ -1218,7 +1220,7 @@ int s2m_run(liliom_ctx* c, double pose7[7], int match_cnt, int max_num_iter, int
         else if (lanes == 4) k_knn_plane<4><<<grid, kBlock, 0, c->stream>>>(a, pit);
         else k_knn_plane<8><<<grid, kBlock, 0, c->stream>>>(a, pit);
         LILI_TRY(launch_check(c, "k_knn_plane"));
-        if (c->time_kernels) {
+        if (timed) {
             LILI_CUDA(c, cudaEventRecord(c->ev_pool[ev + 1], c->stream));
             c->ev_pending.push_back({ev, (unsigned long long)n_est});
             c->ev_iters.push_back(1);
@@ -1303,7 +1305,7 @@ int s2m_run(liliom_ctx* c, double pose7[7], int match_cnt, int max_num_iter, int
                 h[1] - h[0], h[2] - h[1], h[3] - h[2], 0LL, h[4] - h[3], h[6] - h[5], h[7] - h[6], h[7] - h[0]);
     }
     // fold finished kernel timings into the counters
-    if (c->time_kernels) {
+    if (timed) {
         for (size_t k = 0; k < c->ev_pending.size(); ++k) {
             auto& pr = c->ev_pending[k];
             float ms = 0;
