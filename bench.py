@@ -595,15 +595,19 @@ def bench_body(args, fallback_note=None):
             h2d = len(pin_sweeps[i]) * psz + len(surf) * psz + 56
             d2h = (len(surf) + len(edge) + len(cut)) * psz + len(ds) * psz + 56
             if stream_wl:
-                fh = frames_host[pushes[0] % N_FRAMES]
-                pushes[0] += 1
-                cx.map_push_frame(fh, ident)                  # buildLocalMap's push: the frame arrives from the host
-                cx.map_rebuild()
-                h2d += len(fh) * psz + 56
+                h2d += push_host()
             return pose, h2d, d2h
-        return step_resident, step_e2e
 
-    step_resident, step_e2e = make_steps(ctx)
+        def push_host():
+            """buildLocalMap's push with the frame arriving from the host, then the rebuild; returns the bytes uploaded."""
+            fh = frames_host[pushes[0] % N_FRAMES]
+            pushes[0] += 1
+            cx.map_push_frame(fh, ident)
+            cx.map_rebuild()
+            return len(fh) * psz + 56
+        return step_resident, step_e2e, push_host
+
+    step_resident, step_e2e, push_host_main = make_steps(ctx)
 
     def e2e_two_nodes(n_steps, n_warm):
         """The reference runs Preprocessing and LidarOdometry as two concurrent single-threaded nodes; so does this
@@ -634,7 +638,10 @@ def bench_body(args, fallback_note=None):
             ns, ne, nc = item
             i = k % len(sweeps)
             pose, st, ds = ctx.odometry(sets[b][0][:ns], sweeps[i]["guess"], ITERS, mode=L.MODE_GN, ds_out=out_ds, pose_out=pose_buf, want_stats=False)
-            result.update(pose=np.array(pose), h2d=len(pin_sweeps[i]) * psz + ns * psz + 56, d2h=(ns + ne + nc) * psz + len(ds) * psz + 56)
+            h2d = len(pin_sweeps[i]) * psz + ns * psz + 56
+            if stream_wl:                      # the LidarOdometry node also maintains the map (buildLocalMap), after the scan
+                h2d += push_host_main()
+            result.update(pose=np.array(pose), h2d=h2d, d2h=(ns + ne + nc) * psz + len(ds) * psz + 56)
 
         barrier()
         run_two_stage_pipeline(n_warm + n_steps, n_warm, nbuf, stage_a, stage_b,
@@ -707,7 +714,7 @@ def bench_body(args, fallback_note=None):
         # ---- timed region 2: end to end with host buffers
         ms_seq_local, last_seq = timed(step_e2e, steps, warmup)
         ms_seq, _ = over_ranks(ms_seq_local)
-        if args.e2e == "sequential" or sharded or stream_wl:
+        if args.e2e == "sequential":
             ms_e2e, last_e2e = ms_seq, last_seq
         else:
             ms_e2e_local, last_e2e = e2e_two_nodes(steps, warmup)
@@ -823,7 +830,7 @@ def bench_body(args, fallback_note=None):
         try:
             c2 = new_context(False)
             install_map(c2)
-            s2_res, _ = make_steps(c2, incremental=True)
+            s2_res, _, _ = make_steps(c2, incremental=True)
             ms2, last2 = timed(s2_res, k1, 3, prep_for(c2), after_warmup=lambda: cx_phase_ms[id(c2)].__setitem__(slice(None), [0.0, 0.0, 0.0, 0.0, 0]),
                                collective=False)
             ph2 = cx_phase_ms.get(id(c2), [0, 0, 0, 0, 0])
@@ -846,7 +853,7 @@ def bench_body(args, fallback_note=None):
             try:
                 c1 = new_context(False)
                 install_map(c1)
-                s1_res, _ = make_steps(c1)
+                s1_res, _, _ = make_steps(c1)
                 k1 = max(3, min(steps, 20))
                 ms1, last1 = timed(s1_res, k1, 3, prep_for(c1), after_warmup=lambda: cx_phase_ms[id(c1)].__setitem__(slice(None), [0.0, 0.0, 0.0, 0.0, 0]),
                                    collective=False)
@@ -915,9 +922,10 @@ def bench_body(args, fallback_note=None):
                 "h2d_bytes_per_step": int(last_e2e[1]), "d2h_bytes_per_step": int(last_e2e[2]),
                 "mode": ("sequential: one host thread calls the Preprocessing-node entry point, the LidarOdometry-node entry point"
                          + (" and the map maintenance" if stream_wl else "") + " in turn"
-                         if (args.e2e == "sequential" or sharded or stream_wl) else
-                         "two-nodes: Preprocessing and LidarOdometry contexts on two host threads / CUDA streams, as the reference's two ROS "
-                         "nodes; /surf_features hop through pinned host memory; one 256 MB L2-evicting write per scan on a third stream inside "
+                         if args.e2e == "sequential" else
+                         "two-nodes: Preprocessing and LidarOdometry contexts on two host threads / CUDA streams" + (" per rank" if multi else "") +
+                         ", as the reference's two ROS nodes" + (" (the LidarOdometry thread also pushes the frame and rebuilds the map)" if stream_wl else "") +
+                         "; /surf_features hop through pinned host memory; one 256 MB L2-evicting write per scan on a third stream inside "
                          "the timed region (sequential_value: one thread, flush strictly between scans — the like-for-like figure against "
                          "the strictly sequential reference arm)"),
                 "sequential_value": scans_total / (ms_seq * 1e-3), "sequential_ms_per_step": ms_seq / steps},

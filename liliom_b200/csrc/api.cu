@@ -469,7 +469,11 @@ static int push_frame_from_device(liliom_ctx* c, const void* d_src, int n, const
             if (c->nranks == 1) {
                 k_transform_cloud<<<cdiv(n, 256), 256, 0, c->stream>>>((const unsigned char*)d_src, n, stride, q, t, (unsigned char*)f.buf.p);
                 LILI_TRY(launch_check(c, "k_transform_cloud"));
+                LILI_TRY(vg_minmax_dev(c, f.buf.p, n, nullptr, stride));                 // the frame's box, for the rebuilds it takes part in
+                int* hpb = reinterpret_cast<int*>(c->h_pin) + 1032;
+                LILI_CUDA(c, cudaMemcpyAsync(hpb, c->vg_minmax.p, 7 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
                 LILI_CUDA(c, cudaStreamSynchronize(c->stream));
+                for (int k = 0; k < 7; ++k) f.mm[k] = hpb[k];
                 return LILIOM_OK;
             }
             // sharded map maintenance: every rank receives the frame, keeps the points within (search radius + one voxel
@@ -490,9 +494,12 @@ static int push_frame_from_device(liliom_ctx* c, const void* d_src, int n, const
                                                                   (unsigned char*)f.buf.p);
             LILI_TRY(launch_check(c, "k_compact_strided"));
             int* hp = reinterpret_cast<int*>(c->h_pin) + 1024;
+            LILI_TRY(vg_minmax_dev(c, f.buf.p, n, c->idx_a.as<int>() + n, stride));     // box of the points this rank keeps
             LILI_CUDA(c, cudaMemcpyAsync(hp, c->idx_a.as<int>() + n, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+            LILI_CUDA(c, cudaMemcpyAsync(hp + 8, c->vg_minmax.p, 7 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
             LILI_CUDA(c, cudaStreamSynchronize(c->stream));
             f.n = hp[0];
+            for (int k = 0; k < 7; ++k) f.mm[k] = hp[8 + k];
             return LILIOM_OK;
         };
         rc = body();
@@ -521,12 +528,25 @@ extern "C" int liliom_map_push_frame_device(liliom_ctx* c, const void* d_surf_ds
 
 namespace lili {
 // tail shared by the rebuild and the incremental update (single GPU): c->map_ds holds m filtered points
+void frames_box(const liliom_ctx* c, int mm[7]) {
+    for (int k = 0; k < 3; ++k) { mm[k] = INT_MAX; mm[3 + k] = INT_MIN; }
+    long long nfin = 0;
+    for (const auto& f : c->frames) {
+        if (f.mm[6] <= 0) continue;
+        for (int k = 0; k < 3; ++k) { mm[k] = std::min(mm[k], f.mm[k]); mm[3 + k] = std::max(mm[3 + k], f.mm[3 + k]); }
+        nfin += f.mm[6];
+    }
+    mm[6] = (int)nfin;
+}
+
 int map_finish_from_ds(liliom_ctx* c, int m) {
     const int stride = c->prm.point_stride;
     LILI_CUDA(c, c->map_xyzw.ensure((size_t)(m > 0 ? m : 1) * sizeof(float4)));
     c->map_n_global = m;
     LILI_TRY(repack_to_f4(c, c->map_ds.p, m, stride, c->map_xyzw.as<float4>()));
-    LILI_TRY(grid_build(c, m));
+    int mm[7];
+    frames_box(c, mm);
+    LILI_TRY(grid_build(c, m, mm[6] > 0 ? mm : nullptr));
     LILI_CUDA(c, cudaStreamSynchronize(c->stream));
     return LILIOM_OK;
 }
@@ -606,6 +626,11 @@ extern "C" int liliom_map_rebuild(liliom_ctx* c, int* n_map_out) {
     LILI_CUDA(c, c->map_raw.ensure((total > 0 ? total : 1) * stride));
     LILI_CUDA(c, c->map_ds.ensure((total > 0 ? total : 1) * stride));
     LILI_CUDA(c, c->vg_count.ensure(16));
+    // bounding box and finite count of the concatenation = union over the frames (each measured once, at its push)
+    int box[7];
+    frames_box(c, box);
+    // single GPU: the centroid kernel writes the float4 map itself (no repack pass); at most `total` voxels
+    if (c->nranks == 1) LILI_CUDA(c, c->map_xyzw.ensure((total > 0 ? total : 1) * sizeof(float4)));
     size_t off = 0;
     if (c->frames.size() <= (size_t)kConcatMax && total > 0) {
         ConcatTab tab{};
@@ -631,7 +656,8 @@ extern "C" int liliom_map_rebuild(liliom_ctx* c, int* n_map_out) {
         // (The single-launch cooperative filter of the scan VoxelGrid was tried here for maps of <= 32k points: within the noise
         // of the real-size streamed lifecycle, profiles/r02_stream_real_lifecycle_mapcoop_ab.txt — not kept.)
         {
-            LILI_TRY(voxelgrid_dev(c, c->map_raw.p, (int)total, stride, c->prm.leaf_map, c->map_ds.p, c->vg_count.as<int>()));   // :316-317
+            LILI_TRY(voxelgrid_dev(c, c->map_raw.p, (int)total, stride, c->prm.leaf_map, c->map_ds.p, c->vg_count.as<int>(),   // :316-317
+                                   c->nranks == 1 ? c->map_xyzw.as<float4>() : nullptr, box));
             LILI_CUDA(c, cudaMemcpyAsync(hp, c->vg_count.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
             LILI_CUDA(c, cudaStreamSynchronize(c->stream));
         }
@@ -663,7 +689,7 @@ extern "C" int liliom_map_rebuild(liliom_ctx* c, int* n_map_out) {
                 LILI_CUDA(c, cudaStreamSynchronize(c->stream));
                 local = hpl[0];
             }
-            return grid_build(c, local);
+            return grid_build(c, local, box[6] > 0 ? box : nullptr);
         };
         const int rc_local = shard_and_index();
         mark();  // [3] shard filter + cell grid
@@ -680,8 +706,7 @@ extern "C" int liliom_map_rebuild(liliom_ctx* c, int* n_map_out) {
         if (pin[3] != 0.0) { c->map_ready = false; c->last_error = "liliom_map_rebuild failed on another rank"; return LILIOM_E_NCCL; }
         c->map_n_global = (int)pin[2];                  // halo voxels are counted on several ranks: an upper bound >= the true size
     } else {
-        LILI_TRY(repack_to_f4(c, c->map_ds.p, m, stride, c->map_xyzw.as<float4>()));
-        LILI_TRY(grid_build(c, m));
+        LILI_TRY(grid_build(c, m, box[6] > 0 ? box : nullptr));     // map_xyzw was written by the VoxelGrid's centroid kernel
     }
     LILI_CUDA(c, cudaStreamSynchronize(c->stream));
     mark();      // [3 or 4] cell grid (single GPU) / map-size all-reduce (sharded)

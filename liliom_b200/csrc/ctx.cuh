@@ -1,5 +1,6 @@
 // Internal context of libliliom_b200.so (not part of the ABI).
 #pragma once
+#include <climits>
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
@@ -88,6 +89,9 @@ struct Frame {        // one entry of recent_surf_frames (world frame, point_str
     // incremental map (map_inc.cu): slot id carried by the frame's entries, finite points, box (ordered ints), unrepresentable key seen
     int slot = 0, nfin = 0, box[6] = {0, 0, 0, 0, 0, 0};
     bool bad = false;
+    // box and finite count of the stored points (k_vg_minmax's encoding), taken when the frame was pushed: the rebuild's
+    // VoxelGrid and cell grid get their bounding boxes from the union over the frames instead of two passes over the map
+    int mm[7] = {INT_MAX, INT_MAX, INT_MAX, INT_MIN, INT_MIN, INT_MIN, 0};
 };
 
 }  // namespace lili
@@ -235,15 +239,18 @@ int exclusive_scan_i32(liliom_ctx* c, const int* in, int* out, int n);   // out 
 int inclusive_max_scan_i32(liliom_ctx* c, int* data, int n);            // in-place running maximum
 
 // VoxelGrid on device buffers; d_count receives the output count (int, device).
-int voxelgrid_dev(liliom_ctx* c, const void* d_in, int n, int stride, float leaf, void* d_out, int* d_count);
+int voxelgrid_dev(liliom_ctx* c, const void* d_in, int n, int stride, float leaf, void* d_out, int* d_count, float4* d_feats = nullptr,
+                  const int* host_mm = nullptr);
+int vg_minmax_dev(liliom_ctx* c, const void* d_in, int n_max, const int* d_n, int stride);
 // n_max = host upper bound, d_n = optional device-side count (<= n_max); d_feats (optional) also receives float4{x,y,z,index}
 int voxelgrid_coop(liliom_ctx* c, const void* d_in, int n_max, const int* d_n, int stride, float leaf, void* d_out, int* d_count, float4* d_feats,
                    bool* used);
 int voxelgrid_dev2(liliom_ctx* c, const void* d_in, int n_max, const int* d_n, int stride, float leaf, void* d_out, int* d_count, float4* d_feats,
-                   int key_bits = 32);
+                   int key_bits = 32, const int* host_mm = nullptr);
 
-// grid build from float4 points already on the device (map_xyzw[0..m)).
-int grid_build(liliom_ctx* c, int m);
+// grid build from float4 points already on the device (map_xyzw[0..m)).  host_box (optional): 6 ordered ints, a box known to
+// contain the points up to rounding of a mean (the union of the frames' boxes): no min/max pass and no host round trip.
+int grid_build(liliom_ctx* c, int m, const int* host_box = nullptr);
 
 const long long* vg_coop_stamps(liliom_ctx* c);   // voxelgrid.cu
 
@@ -257,6 +264,7 @@ int icp_align(liliom_ctx* c, const float4* d_src, int n, double max_corr_dist, i
               double T16[16], double* fitness, int* converged, int* iters);           // icp.cu
 int map_inc_update(liliom_ctx* c, int popped_slot, int popped_nfin, int* m_out);     // map_inc.cu
 int map_finish_from_ds(liliom_ctx* c, int m);                                        // api.cu
+void frames_box(const liliom_ctx* c, int mm[7]);                                     // api.cu: union of the frames' boxes
 
 int block27_stats(liliom_ctx* c, const double pose7[7], unsigned long long out[2]);   // grid_knn.cu
 

@@ -103,7 +103,7 @@ __global__ void k_cell_run_ends(const uint32_t* __restrict__ keys, int n, int* _
     if (w == n - 1 || keys[w + 1] != k) cell_start[(size_t)k + 1] = w + 1;
 }
 
-int grid_build(liliom_ctx* c, int m) {
+int grid_build(liliom_ctx* c, int m, const int* host_box) {
     c->map_ready = false;
     c->map_n = m;
     if (m <= 0) {   // empty (shard of the) map: a 1-cell grid with no points, so that collective callers still run every launch
@@ -119,15 +119,22 @@ int grid_build(liliom_ctx* c, int m) {
         return LILIOM_OK;
     }
     float4* pts = c->map_xyzw.as<float4>();
-    LILI_CUDA(c, c->vg_minmax.ensure(8 * sizeof(int)));
-    int* mm = c->vg_minmax.as<int>();
-    k_init_minmax<<<1, 32, 0, c->stream>>>(mm);
-    LILI_TRY(launch_check(c, "k_init_minmax"));
-    k_minmax_f4<<<min(cdiv(m, 256), c->sm_count * 8), 256, 0, c->stream>>>(pts, m, mm);
-    LILI_TRY(launch_check(c, "k_minmax_f4"));
     int h[6];
-    LILI_CUDA(c, cudaMemcpyAsync(h, mm, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
-    LILI_CUDA(c, cudaStreamSynchronize(c->stream));
+    // a box handed in by the caller contains the raw points; a voxel centroid (an fp32 mean of such points) can leave it by
+    // an ulp, hence one cell of padding on every side
+    const int pad = host_box ? 1 : 0;
+    if (host_box) {
+        for (int k = 0; k < 6; ++k) h[k] = host_box[k];
+    } else {
+        LILI_CUDA(c, c->vg_minmax.ensure(8 * sizeof(int)));
+        int* mm = c->vg_minmax.as<int>();
+        k_init_minmax<<<1, 32, 0, c->stream>>>(mm);
+        LILI_TRY(launch_check(c, "k_init_minmax"));
+        k_minmax_f4<<<min(cdiv(m, 256), c->sm_count * 8), 256, 0, c->stream>>>(pts, m, mm);
+        LILI_TRY(launch_check(c, "k_minmax_f4"));
+        LILI_CUDA(c, cudaMemcpyAsync(h, mm, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+        LILI_CUDA(c, cudaStreamSynchronize(c->stream));
+    }
     auto dec = [](int i) { int j = i >= 0 ? i : i ^ 0x7fffffff; float f; memcpy(&f, &j, 4); return f; };
     // cell size: smallest power of two >= sqrt(knn_max_sqdist) (1.0 for the reference's gate)
     float cell = 1.0f;
@@ -138,7 +145,7 @@ int grid_build(liliom_ctx* c, int m) {
     for (int k = 0; k < 3; ++k) {
         float lo = dec(h[k]), hi = dec(h[3 + k]);
         if (!(std::isfinite(lo) && std::isfinite(hi))) { c->last_error = "non-finite map point"; return LILIOM_E_ARG; }
-        int clo = (int)floorf(lo * g.inv_cell), chi = (int)floorf(hi * g.inv_cell);
+        int clo = (int)floorf(lo * g.inv_cell) - pad, chi = (int)floorf(hi * g.inv_cell) + pad;
         g.org[k] = clo;
         g.dim[k] = chi - clo + 1;
         nc *= g.dim[k];

@@ -7,6 +7,8 @@
 // The box / divisions are computed on the device (VgParams): no host round trip inside the call.
 #include "ctx.cuh"
 #include <climits>
+#include <cmath>
+#include <cstring>
 #include <cstdlib>
 
 namespace lili {
@@ -50,8 +52,9 @@ __global__ void k_vg_minmax(const unsigned char* __restrict__ pts, int n_max, co
     }
 }
 
-__global__ void k_vg_params(const int* __restrict__ mm, float leaf, VgParams* __restrict__ out) {
-    if (threadIdx.x != 0) return;
+struct VgBox { int mm[7]; };      // min xyz, max xyz (ordered ints), finite count — k_vg_minmax's output, by value
+
+__device__ __forceinline__ void vg_params_from(const int* mm, float leaf, VgParams* __restrict__ out) {
     VgParams p;
     p.inv_leaf = 1.0f / leaf;                       // Eigen::Array4f::Ones() / leaf_size_
     p.n_finite = mm[6];
@@ -72,6 +75,14 @@ __global__ void k_vg_params(const int* __restrict__ mm, float leaf, VgParams* __
     }
     p.mul[0] = 1; p.mul[1] = p.div_b[0]; p.mul[2] = p.div_b[0] * p.div_b[1];
     *out = p;
+}
+
+__global__ void k_vg_params(const int* __restrict__ mm, float leaf, VgParams* __restrict__ out) {
+    if (threadIdx.x == 0) vg_params_from(mm, leaf, out);
+}
+// the bounding box is already known on the host (map rebuild: the union of the frames' boxes, kept since their push)
+__global__ void k_vg_params_box(const VgBox b, float leaf, VgParams* __restrict__ out) {
+    if (threadIdx.x == 0) vg_params_from(b.mm, leaf, out);
 }
 
 __global__ void k_vg_keys(const unsigned char* __restrict__ pts, int n_max, const int* __restrict__ d_n, int stride, const VgParams* __restrict__ pp,
@@ -563,8 +574,22 @@ int voxelgrid_coop(liliom_ctx* c, const void* d_in, int n_max, const int* d_n, i
     return LILIOM_OK;
 }
 
+// box of the finite points of a device cloud, left in c->vg_minmax (7 ints, k_vg_minmax's encoding); no sync
+int vg_minmax_dev(liliom_ctx* c, const void* d_in, int n_max, const int* d_n, int stride) {
+    LILI_CUDA(c, c->vg_minmax.ensure(8 * sizeof(int)));
+    int* mm = c->vg_minmax.as<int>();
+    k_vg_init<<<1, 32, 0, c->stream>>>(mm);
+    LILI_TRY(launch_check(c, "k_vg_init"));
+    if (n_max > 0) {
+        k_vg_minmax<<<min(cdiv(n_max, 256), c->sm_count * 8), 256, 0, c->stream>>>((const unsigned char*)d_in, n_max, d_n, stride, mm);
+        LILI_TRY(launch_check(c, "k_vg_minmax"));
+    }
+    return LILIOM_OK;
+}
+
+// host_mm (optional): the cloud's box and finite count already known on the host -> no pass over the input for it
 int voxelgrid_dev2(liliom_ctx* c, const void* d_in, int n_max, const int* d_n, int stride, float leaf, void* d_out, int* d_count,
-                   float4* d_feats, int key_bits) {
+                   float4* d_feats, int key_bits, const int* host_mm) {
     if (stride != 48 && stride != 32) return LILIOM_E_ARG;
     if (n_max <= 0) {
         LILI_CUDA(c, cudaMemsetAsync(d_count, 0, sizeof(int), c->stream));
@@ -582,12 +607,19 @@ int voxelgrid_dev2(liliom_ctx* c, const void* d_in, int n_max, const int* d_n, i
     LILI_CUDA(c, c->vg_rank.ensure(((size_t)n + 2) * 4));
     int* mm = c->vg_minmax.as<int>();
     VgParams* pp = c->vg_params.as<VgParams>();
-    k_vg_init<<<1, 32, 0, c->stream>>>(mm);
-    LILI_TRY(launch_check(c, "k_vg_init"));
-    k_vg_minmax<<<min(cdiv(n, 256), c->sm_count * 8), 256, 0, c->stream>>>(in, n, d_n, stride, mm);
-    LILI_TRY(launch_check(c, "k_vg_minmax"));
-    k_vg_params<<<1, 32, 0, c->stream>>>(mm, leaf, pp);
-    LILI_TRY(launch_check(c, "k_vg_params"));
+    if (host_mm) {
+        VgBox b;
+        for (int k = 0; k < 7; ++k) b.mm[k] = host_mm[k];
+        k_vg_params_box<<<1, 32, 0, c->stream>>>(b, leaf, pp);
+        LILI_TRY(launch_check(c, "k_vg_params_box"));
+    } else {
+        k_vg_init<<<1, 32, 0, c->stream>>>(mm);
+        LILI_TRY(launch_check(c, "k_vg_init"));
+        k_vg_minmax<<<min(cdiv(n, 256), c->sm_count * 8), 256, 0, c->stream>>>(in, n, d_n, stride, mm);
+        LILI_TRY(launch_check(c, "k_vg_minmax"));
+        k_vg_params<<<1, 32, 0, c->stream>>>(mm, leaf, pp);
+        LILI_TRY(launch_check(c, "k_vg_params"));
+    }
     k_vg_keys<<<cdiv(n, 256), 256, 0, c->stream>>>(in, n, d_n, stride, pp, c->vg_keys.as<uint32_t>(), c->vg_vals.as<int>());
     LILI_TRY(launch_check(c, "k_vg_keys"));
     // key_bits < 32: the caller speculates that the voxel index fits (one onesweep pass less per 8 bits);
@@ -607,8 +639,27 @@ int voxelgrid_dev2(liliom_ctx* c, const void* d_in, int n_max, const int* d_n, i
     return LILIOM_OK;
 }
 
-int voxelgrid_dev(liliom_ctx* c, const void* d_in, int n, int stride, float leaf, void* d_out, int* d_count) {
-    return voxelgrid_dev2(c, d_in, n, nullptr, stride, leaf, d_out, d_count, nullptr, 32);
+static float vg_ord2f_host(int i) { int j = i >= 0 ? i : i ^ 0x7fffffff; float f; memcpy(&f, &j, 4); return f; }
+
+// d_feats (optional): the centroids also as float4 {x, y, z, output index}; host_mm (optional): see voxelgrid_dev2 — the
+// key width of the sort then follows from the box (k_vg_params' arithmetic repeated on the host) instead of 32 bits.
+int voxelgrid_dev(liliom_ctx* c, const void* d_in, int n, int stride, float leaf, void* d_out, int* d_count, float4* d_feats, const int* host_mm) {
+    int key_bits = 32;
+    if (host_mm && host_mm[6] > 0) {
+        const float inv_leaf = 1.0f / leaf;
+        long long cells = 1, dd = 1;
+        for (int k = 0; k < 3; ++k) {
+            const float lo = vg_ord2f_host(host_mm[k]), hi = vg_ord2f_host(host_mm[3 + k]);
+            dd *= (long long)((hi - lo) * inv_leaf) + 1;
+            cells *= (long long)((int)floorf(hi * inv_leaf) - (int)floorf(lo * inv_leaf) + 1);
+        }
+        if (dd <= (long long)INT_MAX && cells > 0 && cells < (1LL << 31)) {      // not PCL's overflow case; all-ones of the width stays free for the sentinel
+            key_bits = 1;
+            while ((1LL << key_bits) <= cells) ++key_bits;
+            if (key_bits < 8) key_bits = 8;
+        }
+    }
+    return voxelgrid_dev2(c, d_in, n, nullptr, stride, leaf, d_out, d_count, d_feats, key_bits, host_mm);
 }
 
 }  // namespace lili
