@@ -11,8 +11,9 @@
 //   k_rot_curv     11-point curvature in the literal left-to-right fp32 order (:385-394)
 //   k_rot_ring     one CTA per ring: its 6 segments in order (the picked[] marks of segment j
 //                  are visible to segment j+1, :401-500): shared-memory bitonic sort by
-//                  (curvature, index), then lane 0 walks the sorted list — <=2 sharp, <=10
-//                  less-sharp, +-5 neighbour suppression, <=4 flat, less-flat flags
+//                  (curvature, index), then warp 0 walks the sorted list 32 candidates at a time
+//                  (ballot for the next unpicked one) — <=2 sharp, <=10 less-sharp, +-5 neighbour
+//                  suppression, <=4 flat, less-flat flags
 //   k_rot_lf_*     per-ring pcl::VoxelGrid(0.6) of the less-flat points (:502-508), all rings
 //                  in one batch with 64-bit (ring, voxel) keys
 //   k_rot_edge_emit  ordered compaction of the <=10 edge picks per segment (:517-521)
@@ -213,53 +214,94 @@ __global__ void __launch_bounds__(512) k_rot_ring(const Pt32* __restrict__ cloud
                 __syncthreads();
             }
         }
-        if (threadIdx.x == 0) {
+        // The picks are sequential by definition (a pick marks its +-5 neighbours, which later candidates must see), but the
+        // candidates BETWEEN picks are not: warp 0 examines 32 sorted candidates at a time, a ballot finds the first one that
+        // is still unpicked (or the first that ends the walk), and only that one is acted on before the scan resumes behind it
+        // with the fresh marks.  Sequential steps = picks (<= 14 per segment), not candidates; one thread walking the list took
+        // ~23k of the ~30k cycles per segment (k_rot_ring 90 us, profiles/r02_stream_1gpu_launches.csv).
+        if (threadIdx.x < 32) {
+            const unsigned full = 0xffffffffu;
+            const int lane = threadIdx.x;
             auto PT = [&](int ind) -> const float4& { return S.pts[ind - sp + 5]; };
             auto gap2 = [&](int a, int b) {
                 float dX = PT(a).x - PT(b).x, dY = PT(a).y - PT(b).y, dZ = PT(a).z - PT(b).z;
                 return dX * dX + dY * dY + dZ * dZ;
             };
-            auto suppress = [&](int ind) {                                                                  // :434-451
-                for (int l = 1; l <= 5; l++) {
-                    if ((double)gap2(ind + l, ind + l - 1) > 0.05) break;
-                    S.picked[ind + l - rf] = 1;
-                }
-                for (int l = -1; l >= -5; l--) {
-                    if ((double)gap2(ind + l, ind + l + 1) > 0.05) break;
-                    S.picked[ind + l - rf] = 1;
-                }
+            // :434-451 — lanes 0-4: ind+1..ind+5, lanes 5-9: ind-1..ind-5; each side marks up to its first gap > 0.05
+            auto suppress = [&](int ind) {
+                bool brk = false;
+                int l = 0;
+                if (lane < 5) { l = lane + 1; brk = (double)gap2(ind + l, ind + l - 1) > 0.05; }
+                else if (lane < 10) { l = -(lane - 4); brk = (double)gap2(ind + l, ind + l + 1) > 0.05; }
+                const unsigned bm = __ballot_sync(full, brk);
+                const unsigned fwd = bm & 0x1fu, bwd = (bm >> 5) & 0x1fu;
+                const int nf = fwd ? __ffs(fwd) - 1 : 5, nb = bwd ? __ffs(bwd) - 1 : 5;
+                if (lane < 5) { if (lane < nf) S.picked[ind + l - rf] = 1; }
+                else if (lane < 10) { if (lane - 5 < nb) S.picked[ind + l - rf] = 1; }
+                __syncwarp();
             };
             int largest = 0, nedge = 0;
-            for (int k = L - 1; k >= 0; --k) {                                                              // :413-453
-                const unsigned long long key = S.keys[k];
-                const int ind = (int)(unsigned)(key & 0xffffffffu);
-                const float cv = __uint_as_float((unsigned)(key >> 32));
-                if (!((double)cv > 2.0)) break;      // sorted: nothing further can be picked (no side effects skipped)
-                if (S.picked[ind - rf] == 0) {
+            bool done = false;
+            for (int k = L - 1; !done && k >= 0;) {                                                         // :413-453
+                const int kk = k - lane;
+                bool stop = false, avail = false;
+                int ind = 0;
+                if (kk >= 0) {
+                    const unsigned long long key = S.keys[kk];
+                    ind = (int)(unsigned)(key & 0xffffffffu);
+                    const float cv = __uint_as_float((unsigned)(key >> 32));
+                    stop = !((double)cv > 2.0);       // sorted: nothing further can be picked (no side effects skipped)
+                    avail = !stop && S.picked[ind - rf] == 0;
+                }
+                const unsigned ms = __ballot_sync(full, stop), ma = __ballot_sync(full, avail);
+                const int fs = ms ? __ffs(ms) - 1 : 32, fa = ma ? __ffs(ma) - 1 : 32;
+                if (fa < fs) {
                     largest++;
-                    if (largest <= 2) { label[ind] = 2; seg_edge[(ring * 6 + j) * 10 + nedge++] = ind; }
-                    else if (largest <= 10) { label[ind] = 1; seg_edge[(ring * 6 + j) * 10 + nedge++] = ind; }
-                    else break;
-                    S.picked[ind - rf] = 1;
-                    suppress(ind);
-                }
+                    if (largest > 10) { done = true; continue; }
+                    const int pind = __shfl_sync(full, ind, fa);
+                    if (lane == 0) {
+                        label[pind] = largest <= 2 ? 2 : 1;
+                        seg_edge[(ring * 6 + j) * 10 + nedge] = pind;
+                        S.picked[pind - rf] = 1;
+                    }
+                    nedge++;
+                    __syncwarp();
+                    suppress(pind);
+                    k -= fa + 1;
+                } else if (fs < 32) done = true;
+                else k -= 32;
             }
-            seg_cnt[ring * 6 + j] = nedge;
+            if (lane == 0) seg_cnt[ring * 6 + j] = nedge;
             int smallest = 0;
-            for (int k = 0; k < L; ++k) {                                                                   // :456-492
-                const unsigned long long key = S.keys[k];
-                const int ind = (int)(unsigned)(key & 0xffffffffu);
-                const float cv = __uint_as_float((unsigned)(key >> 32));
-                if (!((double)cv < 0.1)) break;      // sorted ascending: the rest cannot qualify
-                const float4& p = PT(ind);
-                if ((double)(p.x * p.x + p.y * p.y + p.z * p.z) < 0.25) continue;
-                if (S.picked[ind - rf] == 0) {
-                    label[ind] = -1;
-                    smallest++;
-                    if (smallest >= 4) break;
-                    S.picked[ind - rf] = 1;
-                    suppress(ind);
+            done = false;
+            for (int k = 0; !done && k < L;) {                                                              // :456-492
+                const int kk = k + lane;
+                bool stop = false, avail = false;
+                int ind = 0;
+                if (kk < L) {
+                    const unsigned long long key = S.keys[kk];
+                    ind = (int)(unsigned)(key & 0xffffffffu);
+                    const float cv = __uint_as_float((unsigned)(key >> 32));
+                    stop = !((double)cv < 0.1);       // sorted ascending: the rest cannot qualify
+                    if (!stop) {
+                        const float4& p = PT(ind);
+                        const bool nearp = (double)(p.x * p.x + p.y * p.y + p.z * p.z) < 0.25;             // `continue`: no side effect
+                        avail = !nearp && S.picked[ind - rf] == 0;
+                    }
                 }
+                const unsigned ms = __ballot_sync(full, stop), ma = __ballot_sync(full, avail);
+                const int fs = ms ? __ffs(ms) - 1 : 32, fa = ma ? __ffs(ma) - 1 : 32;
+                if (fa < fs) {
+                    const int pind = __shfl_sync(full, ind, fa);
+                    if (lane == 0) label[pind] = -1;
+                    smallest++;
+                    if (smallest >= 4) { done = true; continue; }      // the fourth pick leaves no marks (:476-478)
+                    if (lane == 0) S.picked[pind - rf] = 1;
+                    __syncwarp();
+                    suppress(pind);
+                    k += fa + 1;
+                } else if (fs < 32) done = true;
+                else k += 32;
             }
         }
         __syncthreads();
@@ -286,16 +328,30 @@ __device__ __forceinline__ float rord2f(int i) { return __int_as_float(i >= 0 ? 
 
 __global__ void k_rot_lf_gather(const Pt32* __restrict__ cloud, const uint32_t* __restrict__ skeys, const int* __restrict__ lessflat,
                                 const int* __restrict__ lfpos, int n, int* __restrict__ lf_src, int* __restrict__ ringmm, int* __restrict__ meta) {
+    // per-ring boxes: block-local in shared memory first (the cloud is ring-major, so a block meets one to three rings), then one
+    // set of global atomics per ring the block saw — per-point global atomics on 64 x 7 words cost this kernel 38 us
+    __shared__ int s_mm[ROT_MAX_RINGS * 8];
+    for (int t = threadIdx.x; t < ROT_MAX_RINGS * 8; t += blockDim.x) { const int f = t & 7; s_mm[t] = f < 3 ? INT_MAX : (f < 6 ? INT_MIN : 0); }
+    __syncthreads();
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k == 0) meta[M_NLF] = lfpos[n];
-    if (k >= n || !lessflat[k]) return;
-    lf_src[lfpos[k]] = k;
-    const int ring = (int)skeys[k];
-    float4 a = cloud[k].a;
-    int* mm = ringmm + ring * 8;
-    atomicMin(&mm[0], rf2ord(a.x)); atomicMin(&mm[1], rf2ord(a.y)); atomicMin(&mm[2], rf2ord(a.z));
-    atomicMax(&mm[3], rf2ord(a.x)); atomicMax(&mm[4], rf2ord(a.y)); atomicMax(&mm[5], rf2ord(a.z));
-    atomicAdd(&mm[6], 1);
+    if (k < n && lessflat[k]) {
+        lf_src[lfpos[k]] = k;
+        const int ring = (int)skeys[k];
+        float4 a = cloud[k].a;
+        int* mm = s_mm + ring * 8;
+        atomicMin(&mm[0], rf2ord(a.x)); atomicMin(&mm[1], rf2ord(a.y)); atomicMin(&mm[2], rf2ord(a.z));
+        atomicMax(&mm[3], rf2ord(a.x)); atomicMax(&mm[4], rf2ord(a.y)); atomicMax(&mm[5], rf2ord(a.z));
+        atomicAdd(&mm[6], 1);
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < ROT_MAX_RINGS * 8; t += blockDim.x) {
+        const int f = t & 7;
+        if (f == 7 || s_mm[(t & ~7) + 6] == 0) continue;          // ring not seen by this block
+        if (f < 3) atomicMin(&ringmm[t], s_mm[t]);
+        else if (f < 6) atomicMax(&ringmm[t], s_mm[t]);
+        else atomicAdd(&ringmm[t], s_mm[t]);
+    }
 }
 
 __global__ void k_rot_lf_params(const int* __restrict__ ringmm, float leaf, VgParams* __restrict__ prm) {

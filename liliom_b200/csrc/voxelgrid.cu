@@ -45,10 +45,21 @@ __global__ void k_vg_minmax(const unsigned char* __restrict__ pts, int n_max, co
         }
         cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
     }
-    if ((threadIdx.x & 31) == 0 && cnt > 0) {
+    // one set of atomics per BLOCK: the seven words are single addresses, and one set per warp (9.5k warps) serialised into
+    // ~55 us at the L2 whatever the input size (measured on a 500k-point frame: push 25 -> 83 us)
+    __shared__ int s_lo[3][8], s_hi[3][8], s_cnt[8];
+    const int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) {
 #pragma unroll
-        for (int k = 0; k < 3; ++k) { atomicMin(&mm[k], lo[k]); atomicMax(&mm[3 + k], hi[k]); }
-        atomicAdd(&mm[6], cnt);
+        for (int k = 0; k < 3; ++k) { s_lo[k][w] = lo[k]; s_hi[k][w] = hi[k]; }
+        s_cnt[w] = cnt;
+    }
+    __syncthreads();
+    if (threadIdx.x < 7) {
+        const int k = threadIdx.x, nw = (blockDim.x + 31) >> 5;
+        if (k < 3) { int v = INT_MAX; for (int j = 0; j < nw; ++j) v = min(v, s_lo[k][j]); if (v != INT_MAX) atomicMin(&mm[k], v); }
+        else if (k < 6) { int v = INT_MIN; for (int j = 0; j < nw; ++j) v = max(v, s_hi[k - 3][j]); if (v != INT_MIN) atomicMax(&mm[k], v); }
+        else { int v = 0; for (int j = 0; j < nw; ++j) v += s_cnt[j]; if (v) atomicAdd(&mm[6], v); }
     }
 }
 
