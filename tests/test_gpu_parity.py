@@ -156,6 +156,37 @@ def test_map_lifecycle_matches_reference_pipeline(oracle, world_small):
     c.close()
 
 
+def test_map_rebuild_box_escape_rebuilds_exact_grid(oracle, world_small, monkeypatch):
+    """The rebuild takes the cell grid's box from the frames' boxes (no pass over the map).  A centroid outside that box must be
+    noticed (k_cell_keys' escape flag) and the grid rebuilt from the exact min/max: forced here with a box shrunk to one cell in
+    x (LILIOM_TEST_SHRINK_BOX), and the search must return exactly what it returns with the regular box."""
+    import liliom_b200 as L
+    surf, _, _ = oracle.extract_horizon(world_small["hz"], world_small["q_hz"])
+    ds = oracle.voxelgrid(surf, 0.4)
+    out = []
+    for shrink in (False, True):
+        if shrink:
+            monkeypatch.setenv("LILIOM_TEST_SHRINK_BOX", "1")
+        else:
+            monkeypatch.delenv("LILIOM_TEST_SHRINK_BOX", raising=False)
+        c = L.Context(variant=0)
+        rng = np.random.default_rng(5)
+        for k in range(6):
+            pose = np.array(world_small["T"]); pose[4] += 0.3 * k; pose[5] += 0.05 * k
+            c.map_push_frame(ds[rng.permutation(len(ds))[: len(ds) // 2]], pose)
+        m = c.map_rebuild()
+        got = c.map_download()
+        valid, plane, idx, sqd, s29 = c.find_surf_corr(ds, world_small["guess"])
+        pose, st = c.scan_to_map(ds, world_small["guess"], 5, mode=L.MODE_GN)
+        out.append((m, got.copy(), valid.copy(), idx.copy(), sqd.copy(), s29.copy(), pose.copy()))
+        c.close()
+    monkeypatch.delenv("LILIOM_TEST_SHRINK_BOX", raising=False)
+    a, b = out
+    assert a[0] == b[0] and a[0] > 1000 and a[2].sum() > 100
+    for x, y in zip(a[1:], b[1:]):
+        assert x.tobytes() == y.tobytes()
+
+
 # ---------------------------------------------------------------- extractors
 def test_horizon_extract_bit_exact(ctx48, oracle, world_small):
     surf_o, edge_o, cut_o = oracle.extract_horizon(world_small["hz"], world_small["q_hz"])
