@@ -23,6 +23,9 @@
 #include "dev_math.cuh"
 #include "detmath.h"
 #include <climits>
+#include <cstdint>
+#include <cstdio>
+#include <algorithm>
 
 namespace lili {
 
@@ -174,10 +177,14 @@ struct RingSmem {
 
 __global__ void __launch_bounds__(512) k_rot_ring(const Pt32* __restrict__ cloud, const float* __restrict__ curv, int* __restrict__ meta,
                                                   int ds_rate, int* __restrict__ label, int* __restrict__ lessflat,
-                                                  int* __restrict__ seg_edge /* [rings*6][10] */, int* __restrict__ seg_cnt /* [rings*6] */) {
+                                                  int* __restrict__ seg_edge /* [rings*6][10] */, int* __restrict__ seg_cnt /* [rings*6] */,
+                                                  long long* __restrict__ dbg /* LILIOM_DEBUG_TIMING: [rings][8] cycles */) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     RingSmem& S = *reinterpret_cast<RingSmem*>(smem_raw);
     const int ring = blockIdx.x;
+    long long t_all = 0, t_load = 0, t_sort = 0, t_walk = 0, t_flag = 0, t0 = 0;
+    const bool tm = dbg != nullptr && threadIdx.x == 0;
+    if (tm) { t_all = clock64(); for (int k = 0; k < 7; ++k) dbg[ring * 8 + k] = 0; dbg[ring * 8 + 7] = (long long)globaltimer_ns(); }
     const int rf = meta[M_RF + ring], re = meta[M_RE + ring];
     const int scanStart = rf + 5, scanEnd = re - 6;                                                         // :379-381
     for (int j = 0; j < 6; ++j) if (threadIdx.x == 0) seg_cnt[ring * 6 + j] = 0;
@@ -194,6 +201,7 @@ __global__ void __launch_bounds__(512) k_rot_ring(const Pt32* __restrict__ cloud
         if (L > ROT_SEG_CAP) { if (threadIdx.x == 0) meta[M_ERR] = 1; return; }
         int P = 1;
         while (P < L) P <<= 1;
+        if (tm) t0 = clock64();
         for (int k = threadIdx.x; k < P; k += blockDim.x) {
             unsigned long long key = ~0ull;
             if (k < L) key = ((unsigned long long)__float_as_uint(curv[sp + k]) << 32) | (unsigned)(sp + k);
@@ -201,6 +209,7 @@ __global__ void __launch_bounds__(512) k_rot_ring(const Pt32* __restrict__ cloud
         }
         for (int k = threadIdx.x; k < L + 10; k += blockDim.x) S.pts[k] = cloud[sp - 5 + k].a;
         __syncthreads();
+        if (tm) { const long long t = clock64(); t_load += t - t0; t0 = t; }
         // bitonic sort ascending on (curvature, index): curvature >= 0 so its bit pattern orders like the value
         for (int size = 2; size <= P; size <<= 1) {
             for (int stride = size >> 1; stride > 0; stride >>= 1) {
@@ -214,6 +223,7 @@ __global__ void __launch_bounds__(512) k_rot_ring(const Pt32* __restrict__ cloud
                 __syncthreads();
             }
         }
+        if (tm) { const long long t = clock64(); t_sort += t - t0; t0 = t; }
         // The picks are sequential by definition (a pick marks its +-5 neighbours, which later candidates must see), but the
         // candidates BETWEEN picks are not: warp 0 examines 32 sorted candidates at a time, a ballot finds the first one that
         // is still unpicked (or the first that ends the walk), and only that one is acted on before the scan resumes behind it
@@ -304,6 +314,7 @@ __global__ void __launch_bounds__(512) k_rot_ring(const Pt32* __restrict__ cloud
                 else k += 32;
             }
         }
+        if (tm) { const long long t = clock64(); t_walk += t - t0; t0 = t; }
         __syncthreads();
         for (int k = sp + (int)threadIdx.x; k <= ep; k += blockDim.x) {                                     // :494-499
             const float4& p = S.pts[k - sp + 5];
@@ -311,6 +322,11 @@ __global__ void __launch_bounds__(512) k_rot_ring(const Pt32* __restrict__ cloud
             lessflat[k] = (far && label[k] <= 0) ? 1 : 0;
         }
         __syncthreads();
+        if (tm) { const long long t = clock64(); t_flag += t - t0; dbg[ring * 8 + 5] = max(dbg[ring * 8 + 5], (long long)L); }
+    }
+    if (tm) {
+        dbg[ring * 8 + 0] = clock64() - t_all; dbg[ring * 8 + 1] = t_load; dbg[ring * 8 + 2] = t_sort; dbg[ring * 8 + 3] = t_walk; dbg[ring * 8 + 4] = t_flag;
+        dbg[ring * 8 + 6] = (long long)globaltimer_ns();
     }
 }
 
@@ -466,7 +482,7 @@ int rot_extract_dev(liliom_ctx* c, int n, const double q_imu[4], const double q_
     LILI_CUDA(c, c->rot_curv.ensure(N * 4)); LILI_CUDA(c, c->rot_label.ensure(N * 4));
     LILI_CUDA(c, c->rot_lessflat.ensure((N + 2) * 4)); LILI_CUDA(c, c->rot_sort.ensure((N + 2) * 4));
     LILI_CUDA(c, c->rot_picked.ensure((N + 2) * 4));         // lf_src
-    LILI_CUDA(c, c->rot_meta.ensure((M_SIZE + ROT_MAX_RINGS * 8) * 4 + ROT_MAX_RINGS * sizeof(VgParams)));
+    LILI_CUDA(c, c->rot_meta.ensure((M_SIZE + ROT_MAX_RINGS * 8) * 4 + ROT_MAX_RINGS * sizeof(VgParams) + ROT_MAX_RINGS * 8 * sizeof(long long) + 16));
     LILI_CUDA(c, c->rot_seg_edge.ensure((size_t)ROT_MAX_RINGS * 6 * 11 * 4));
     LILI_CUDA(c, c->surf.ensure(N * sizeof(Pt32)));
     LILI_CUDA(c, c->edge.ensure((size_t)ROT_MAX_RINGS * 6 * 10 * sizeof(Pt32)));
@@ -501,9 +517,31 @@ int rot_extract_dev(liliom_ctx* c, int n, const double q_imu[4], const double q_
     LILI_TRY(launch_check(c, "k_rot_curv"));
     // per-device function attribute (cheap; a process may hold contexts on several GPUs)
     LILI_CUDA(c, cudaFuncSetAttribute(k_rot_ring, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RingSmem)));
+    long long* ring_dbg = c->dbg_timing ? reinterpret_cast<long long*>(reinterpret_cast<unsigned char*>(rprm + ROT_MAX_RINGS) + 8) : nullptr;
+    if (ring_dbg) ring_dbg = reinterpret_cast<long long*>((reinterpret_cast<uintptr_t>(ring_dbg) + 7) & ~(uintptr_t)7);
     k_rot_ring<<<n_scans, 512, sizeof(RingSmem), c->stream>>>(cloud, c->rot_curv.as<float>(), meta, c->prm.ds_rate, c->rot_label.as<int>(),
-                                                              c->rot_lessflat.as<int>(), seg_edge, seg_cnt);
+                                                              c->rot_lessflat.as<int>(), seg_edge, seg_cnt, ring_dbg);
     LILI_TRY(launch_check(c, "k_rot_ring"));
+    if (ring_dbg) {       // LILIOM_DEBUG_TIMING: per-ring stage cycles of this launch
+        long long h[ROT_MAX_RINGS * 8];
+        if (cudaMemcpyAsync(h, ring_dbg, sizeof(h), cudaMemcpyDeviceToHost, c->stream) == cudaSuccess && cudaStreamSynchronize(c->stream) == cudaSuccess) {
+            long long mx = 0, sum = 0, t_first = LLONG_MAX, t_last = 0; int arg = -1, cnt = 0;
+            for (int r = 0; r < n_scans; ++r) {
+                const long long* d = h + r * 8;
+                if (d[0] <= 0) continue;
+                ++cnt; sum += d[0];
+                if (d[0] > mx) { mx = d[0]; arg = r; }
+                t_first = std::min(t_first, d[7]); t_last = std::max(t_last, d[6]);
+            }
+            if (arg >= 0) {
+                const long long* d = h + arg * 8;
+                fprintf(stderr, "[k_rot_ring, cycles] %d rings, mean %lld, slowest ring %d: %lld (loads %lld, sort %lld, walk %lld, flags %lld, longest segment %lld points); "
+                                "first block start -> last block end %lld ns\n", cnt, sum / cnt, arg, d[0], d[1], d[2], d[3], d[4], d[5], t_last - t_first);
+                long long late = 0; for (int r = 0; r < n_scans; ++r) if (h[r * 8] > 0) late = std::max(late, h[r * 8 + 7] - t_first);
+                fprintf(stderr, "[k_rot_ring] latest block start after the first: %lld ns\n", late);
+            }
+        }
+    }
     k_rot_edge_emit<<<1, 384, 0, c->stream>>>(cloud, seg_edge, seg_cnt, n_scans * 6, c->edge.as<Pt32>(), meta);
     LILI_TRY(launch_check(c, "k_rot_edge_emit"));
     // less-flat -> per-ring VoxelGrid

@@ -1087,13 +1087,14 @@ int s2m_run(liliom_ctx* c, double pose7[7], int match_cnt, int max_num_iter, int
     int per_task = (32 / lanes) * rounds;
     int ntasks = cdiv(c->d_nfeats ? max(n_est + n_est / 4, 1) : n, per_task);
     int grid = min(max(cdiv(ntasks, kWarps), 1), c->sm_count * 2);
-    // A 16-lane scan that needs more than one block per SM (2.4k-3.8k queries, e.g. a down-sampled HDL-64E sweep) would
-    // leave the single-launch path; two search rounds per warp task keep it there (measured on the configs[2] workload,
-    // 3.1k queries: per-iteration launches 21 us per pass).
-    if (lanes == 16 && rounds == 1 && !c->force_lanes && grid > c->sm_count && mode == LILIOM_MODE_GN && c->nranks == 1 && !want_corr) {
-        const int ntasks2 = cdiv(c->d_nfeats ? max(n_est + n_est / 4, 1) : n, per_task * 2);
-        const int grid2 = max(cdiv(ntasks2, kWarps), 1);
-        if (grid2 <= c->sm_count) { rounds = 2; per_task *= 2; ntasks = ntasks2; grid = grid2; }
+    // A 16-lane scan that needs more than one block per SM (1.9k-3.8k queries, e.g. a down-sampled HDL-64E sweep) would
+    // leave the single-launch path.  Eight lanes per query (four queries per warp, one round) keep it there; measured on the
+    // configs[2] workload, 3.1k queries: 13.7 us per pass, against 16.1 for two rounds of 16 lanes and 21 for per-iteration
+    // launches (profiles/r02_ab_lanes_3k.txt).
+    if (lanes == 16 && rounds == 1 && !c->force_lanes && grid > c->sm_count && mode == LILIOM_MODE_GN && !want_corr) {
+        const int ntasks8 = cdiv(c->d_nfeats ? max(n_est + n_est / 4, 1) : n, 4);
+        const int grid8 = max(cdiv(ntasks8, kWarps), 1);
+        if (grid8 <= c->sm_count) { lanes = 8; per_task = 4; ntasks = ntasks8; grid = grid8; }
     }
 
     LILI_CUDA(c, c->pose_dev.ensure(16 * sizeof(double)));
