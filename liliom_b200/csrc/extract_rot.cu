@@ -169,10 +169,18 @@ __global__ void k_rot_curv(const Pt32* __restrict__ cloud, const int* __restrict
 }
 
 // dynamic shared memory of k_rot_ring
+constexpr int ROT_FAST_CAP = 1024;         // segments up to this many points take the mask walk (one 32-rank word per lane of warp 0)
 struct RingSmem {
     unsigned long long keys[ROT_SEG_CAP];      // (curvature bits << 32) | index
     float4 pts[ROT_SEG_CAP + 16];              // segment window [sp-5, ep+5]
     unsigned char picked[ROT_RING_CAP];        // cloudNeighborPicked of this ring
+    // mask walk (L <= ROT_FAST_CAP): the sorted order as ranks, everything a pick needs precomputed in parallel
+    unsigned short ind_of_rank[ROT_FAST_CAP];  // segment-local point index at sorted rank r
+    unsigned short rank_of[ROT_FAST_CAP];      // inverse
+    unsigned char cls[ROT_FAST_CAP];           // by rank: bit 0 curvature > 2.0 (sharp candidate), bit 1 curvature < 0.1 and not within 0.5 m (flat candidate)
+    unsigned char ext[ROT_FAST_CAP];           // by point: neighbours a pick marks, forward | backward << 4 (each 0..5)
+    unsigned char brk[ROT_FAST_CAP + 16];      // by window index i: |p_i - p_(i-1)|^2 > 0.05 (:434-451's break test, one per consecutive pair)
+    unsigned int availS[32], availF[32];       // by rank: still-unpicked sharp / flat candidates
 };
 
 __global__ void __launch_bounds__(512) k_rot_ring(const Pt32* __restrict__ cloud, const float* __restrict__ curv, int* __restrict__ meta,
@@ -210,108 +218,210 @@ __global__ void __launch_bounds__(512) k_rot_ring(const Pt32* __restrict__ cloud
         for (int k = threadIdx.x; k < L + 10; k += blockDim.x) S.pts[k] = cloud[sp - 5 + k].a;
         __syncthreads();
         if (tm) { const long long t = clock64(); t_load += t - t0; t0 = t; }
-        // bitonic sort ascending on (curvature, index): curvature >= 0 so its bit pattern orders like the value
-        for (int size = 2; size <= P; size <<= 1) {
-            for (int stride = size >> 1; stride > 0; stride >>= 1) {
-                for (int t = threadIdx.x; t < P / 2; t += blockDim.x) {
-                    int lo = 2 * t - (t & (stride - 1));
-                    int hi = lo + stride;
-                    bool up = ((lo & size) == 0);
-                    unsigned long long a = S.keys[lo], b = S.keys[hi];
-                    if ((a > b) == up) { S.keys[lo] = b; S.keys[hi] = a; }
-                }
-                __syncthreads();
+        if (L <= ROT_FAST_CAP) {
+            // ---- mask walk.  The walk over the sorted candidates (:413-492) is sequential only in its PICKS (<= 14 per segment):
+            // whether a candidate qualifies (curvature class, range) and which neighbours a pick marks (the break test between
+            // consecutive points) are static, so all of that is computed in parallel first, the sorted order becomes a rank per
+            // point (counting sort: one barrier instead of the 45 of a bitonic network), and "the next unpicked candidate" is the
+            // highest / lowest set bit of a 32-word availability mask that every pick clears bits in.  Measured before, per
+            // segment of ~316 points: sort 11k cycles, walk 40k cycles of dependent single-warp instructions, kernel 90 us
+            // (profiles/r02_rot_ring_stage_cycles.txt).
+            for (int t = threadIdx.x; t < L; t += blockDim.x) {
+                const unsigned long long mine = S.keys[t];
+                int r = 0;
+#pragma unroll 8
+                for (int q = 0; q < L; ++q) r += (S.keys[q] < mine) ? 1 : 0;       // keys are unique (the index is part of them)
+                const float cv = __uint_as_float((unsigned)(mine >> 32));
+                const float4& p = S.pts[t + 5];
+                const bool nearp = (double)(p.x * p.x + p.y * p.y + p.z * p.z) < 0.25;             // :463-466 `continue`
+                unsigned char cl = 0;
+                if ((double)cv > 2.0) cl |= 1;                                                        // :416
+                if ((double)cv < 0.1 && !nearp) cl |= 2;                                              // :459
+                S.ind_of_rank[r] = (unsigned short)t;
+                S.cls[r] = cl;
+                S.rank_of[t] = (unsigned short)r;
             }
-        }
-        if (tm) { const long long t = clock64(); t_sort += t - t0; t0 = t; }
-        // The picks are sequential by definition (a pick marks its +-5 neighbours, which later candidates must see), but the
-        // candidates BETWEEN picks are not: warp 0 examines 32 sorted candidates at a time, a ballot finds the first one that
-        // is still unpicked (or the first that ends the walk), and only that one is acted on before the scan resumes behind it
-        // with the fresh marks.  Sequential steps = picks (<= 14 per segment), not candidates; one thread walking the list took
-        // ~23k of the ~30k cycles per segment (k_rot_ring 90 us, profiles/r02_stream_1gpu_launches.csv).
-        if (threadIdx.x < 32) {
-            const unsigned full = 0xffffffffu;
-            const int lane = threadIdx.x;
-            auto PT = [&](int ind) -> const float4& { return S.pts[ind - sp + 5]; };
-            auto gap2 = [&](int a, int b) {
-                float dX = PT(a).x - PT(b).x, dY = PT(a).y - PT(b).y, dZ = PT(a).z - PT(b).z;
-                return dX * dX + dY * dY + dZ * dZ;
-            };
-            // :434-451 — lanes 0-4: ind+1..ind+5, lanes 5-9: ind-1..ind-5; each side marks up to its first gap > 0.05
-            auto suppress = [&](int ind) {
-                bool brk = false;
-                int l = 0;
-                if (lane < 5) { l = lane + 1; brk = (double)gap2(ind + l, ind + l - 1) > 0.05; }
-                else if (lane < 10) { l = -(lane - 4); brk = (double)gap2(ind + l, ind + l + 1) > 0.05; }
-                const unsigned bm = __ballot_sync(full, brk);
-                const unsigned fwd = bm & 0x1fu, bwd = (bm >> 5) & 0x1fu;
-                const int nf = fwd ? __ffs(fwd) - 1 : 5, nb = bwd ? __ffs(bwd) - 1 : 5;
-                if (lane < 5) { if (lane < nf) S.picked[ind + l - rf] = 1; }
-                else if (lane < 10) { if (lane - 5 < nb) S.picked[ind + l - rf] = 1; }
-                __syncwarp();
-            };
-            int largest = 0, nedge = 0;
-            bool done = false;
-            for (int k = L - 1; !done && k >= 0;) {                                                         // :413-453
-                const int kk = k - lane;
-                bool stop = false, avail = false;
-                int ind = 0;
-                if (kk >= 0) {
-                    const unsigned long long key = S.keys[kk];
-                    ind = (int)(unsigned)(key & 0xffffffffu);
-                    const float cv = __uint_as_float((unsigned)(key >> 32));
-                    stop = !((double)cv > 2.0);       // sorted: nothing further can be picked (no side effects skipped)
-                    avail = !stop && S.picked[ind - rf] == 0;
+            for (int i = threadIdx.x + 1; i < L + 10; i += blockDim.x) {
+                const float4& a = S.pts[i]; const float4& b = S.pts[i - 1];
+                const float dX = a.x - b.x, dY = a.y - b.y, dZ = a.z - b.z;
+                S.brk[i] = ((double)(dX * dX + dY * dY + dZ * dZ) > 0.05) ? 1 : 0;
+            }
+            if (threadIdx.x < 32) { S.availS[threadIdx.x] = 0u; S.availF[threadIdx.x] = 0u; }
+            __syncthreads();
+            for (int t = threadIdx.x; t < L; t += blockDim.x) {
+                const int w = t + 5;
+                int nf = 0, nb = 0;
+                while (nf < 5 && !S.brk[w + nf + 1]) ++nf;       // forward: pairs (w+1,w), (w+2,w+1), ...
+                while (nb < 5 && !S.brk[w - nb]) ++nb;           // backward: pairs (w,w-1), (w-1,w-2), ...
+                S.ext[t] = (unsigned char)(nf | (nb << 4));
+            }
+            for (int base = 0; base < L; base += blockDim.x) {
+                const int r = base + (int)threadIdx.x;
+                bool sh = false, fl = false;
+                if (r < L) {
+                    const unsigned char cl = S.cls[r];
+                    const bool un = S.picked[sp + (int)S.ind_of_rank[r] - rf] == 0;      // marks carried over from the previous segment
+                    sh = (cl & 1) && un; fl = (cl & 2) && un;
                 }
-                const unsigned ms = __ballot_sync(full, stop), ma = __ballot_sync(full, avail);
-                const int fs = ms ? __ffs(ms) - 1 : 32, fa = ma ? __ffs(ma) - 1 : 32;
-                if (fa < fs) {
+                const unsigned ms = __ballot_sync(0xffffffffu, sh), mf = __ballot_sync(0xffffffffu, fl);
+                if ((threadIdx.x & 31) == 0 && r < L) { S.availS[r >> 5] = ms; S.availF[r >> 5] = mf; }
+            }
+            __syncthreads();
+            if (tm) { const long long t = clock64(); t_sort += t - t0; t0 = t; }
+            if (threadIdx.x < 32) {
+                const unsigned full = 0xffffffffu;
+                const int lane = threadIdx.x;
+                // a pick at segment-local point t: lane 0 marks t, lanes 1-5 its forward and lanes 6-10 its backward neighbours up to the
+                // first break; marked points leave both availability masks
+                auto mark = [&](int t) {
+                    const unsigned e = S.ext[t];
+                    int q = t;
+                    bool on = lane == 0;
+                    if (lane >= 1 && lane <= 5) { on = lane <= (int)(e & 15u); q = t + lane; }
+                    else if (lane >= 6 && lane <= 10) { on = lane - 5 <= (int)(e >> 4); q = t - (lane - 5); }
+                    if (on) {
+                        S.picked[sp + q - rf] = 1;
+                        if (q >= 0 && q < L) {
+                            const int rq = S.rank_of[q];
+                            atomicAnd(&S.availS[rq >> 5], ~(1u << (rq & 31)));
+                            atomicAnd(&S.availF[rq >> 5], ~(1u << (rq & 31)));
+                        }
+                    }
+                    __syncwarp();
+                };
+                int largest = 0, nedge = 0;
+                while (true) {                                                                              // :413-453
+                    const unsigned m = S.availS[lane];
+                    const unsigned any = __ballot_sync(full, m != 0u);
+                    if (!any) break;
                     largest++;
-                    if (largest > 10) { done = true; continue; }
-                    const int pind = __shfl_sync(full, ind, fa);
-                    if (lane == 0) {
-                        label[pind] = largest <= 2 ? 2 : 1;
-                        seg_edge[(ring * 6 + j) * 10 + nedge] = pind;
-                        S.picked[pind - rf] = 1;
-                    }
+                    if (largest > 10) break;
+                    const int lw = 31 - __clz((int)any);
+                    const unsigned mw = __shfl_sync(full, m, lw);
+                    const int t = S.ind_of_rank[(lw << 5) + 31 - __clz((int)mw)];
+                    if (lane == 0) { label[sp + t] = largest <= 2 ? 2 : 1; seg_edge[(ring * 6 + j) * 10 + nedge] = sp + t; }
                     nedge++;
-                    __syncwarp();
-                    suppress(pind);
-                    k -= fa + 1;
-                } else if (fs < 32) done = true;
-                else k -= 32;
-            }
-            if (lane == 0) seg_cnt[ring * 6 + j] = nedge;
-            int smallest = 0;
-            done = false;
-            for (int k = 0; !done && k < L;) {                                                              // :456-492
-                const int kk = k + lane;
-                bool stop = false, avail = false;
-                int ind = 0;
-                if (kk < L) {
-                    const unsigned long long key = S.keys[kk];
-                    ind = (int)(unsigned)(key & 0xffffffffu);
-                    const float cv = __uint_as_float((unsigned)(key >> 32));
-                    stop = !((double)cv < 0.1);       // sorted ascending: the rest cannot qualify
-                    if (!stop) {
-                        const float4& p = PT(ind);
-                        const bool nearp = (double)(p.x * p.x + p.y * p.y + p.z * p.z) < 0.25;             // `continue`: no side effect
-                        avail = !nearp && S.picked[ind - rf] == 0;
-                    }
+                    mark(t);
                 }
-                const unsigned ms = __ballot_sync(full, stop), ma = __ballot_sync(full, avail);
-                const int fs = ms ? __ffs(ms) - 1 : 32, fa = ma ? __ffs(ma) - 1 : 32;
-                if (fa < fs) {
-                    const int pind = __shfl_sync(full, ind, fa);
-                    if (lane == 0) label[pind] = -1;
+                if (lane == 0) seg_cnt[ring * 6 + j] = nedge;
+                int smallest = 0;
+                while (true) {                                                                              // :456-492
+                    const unsigned m = S.availF[lane];
+                    const unsigned any = __ballot_sync(full, m != 0u);
+                    if (!any) break;
+                    const int lw = __ffs((int)any) - 1;
+                    const unsigned mw = __shfl_sync(full, m, lw);
+                    const int t = S.ind_of_rank[(lw << 5) + __ffs((int)mw) - 1];
+                    if (lane == 0) label[sp + t] = -1;
                     smallest++;
-                    if (smallest >= 4) { done = true; continue; }      // the fourth pick leaves no marks (:476-478)
-                    if (lane == 0) S.picked[pind - rf] = 1;
+                    if (smallest >= 4) break;              // the fourth pick leaves no marks (:476-478)
+                    mark(t);
+                }
+            }
+        } else {
+            // bitonic sort ascending on (curvature, index): curvature >= 0 so its bit pattern orders like the value
+            for (int size = 2; size <= P; size <<= 1) {
+                for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                    for (int t = threadIdx.x; t < P / 2; t += blockDim.x) {
+                        int lo = 2 * t - (t & (stride - 1));
+                        int hi = lo + stride;
+                        bool up = ((lo & size) == 0);
+                        unsigned long long a = S.keys[lo], b = S.keys[hi];
+                        if ((a > b) == up) { S.keys[lo] = b; S.keys[hi] = a; }
+                    }
+                    __syncthreads();
+                }
+            }
+            if (tm) { const long long t = clock64(); t_sort += t - t0; t0 = t; }
+            // The picks are sequential by definition (a pick marks its +-5 neighbours, which later candidates must see), but the
+            // candidates BETWEEN picks are not: warp 0 examines 32 sorted candidates at a time, a ballot finds the first one that
+            // is still unpicked (or the first that ends the walk), and only that one is acted on before the scan resumes behind it
+            // with the fresh marks.  Sequential steps = picks (<= 14 per segment), not candidates; one thread walking the list took
+            // ~23k of the ~30k cycles per segment (k_rot_ring 90 us, profiles/r02_stream_1gpu_launches.csv).
+            if (threadIdx.x < 32) {
+                const unsigned full = 0xffffffffu;
+                const int lane = threadIdx.x;
+                auto PT = [&](int ind) -> const float4& { return S.pts[ind - sp + 5]; };
+                auto gap2 = [&](int a, int b) {
+                    float dX = PT(a).x - PT(b).x, dY = PT(a).y - PT(b).y, dZ = PT(a).z - PT(b).z;
+                    return dX * dX + dY * dY + dZ * dZ;
+                };
+                // :434-451 — lanes 0-4: ind+1..ind+5, lanes 5-9: ind-1..ind-5; each side marks up to its first gap > 0.05
+                auto suppress = [&](int ind) {
+                    bool brk = false;
+                    int l = 0;
+                    if (lane < 5) { l = lane + 1; brk = (double)gap2(ind + l, ind + l - 1) > 0.05; }
+                    else if (lane < 10) { l = -(lane - 4); brk = (double)gap2(ind + l, ind + l + 1) > 0.05; }
+                    const unsigned bm = __ballot_sync(full, brk);
+                    const unsigned fwd = bm & 0x1fu, bwd = (bm >> 5) & 0x1fu;
+                    const int nf = fwd ? __ffs(fwd) - 1 : 5, nb = bwd ? __ffs(bwd) - 1 : 5;
+                    if (lane < 5) { if (lane < nf) S.picked[ind + l - rf] = 1; }
+                    else if (lane < 10) { if (lane - 5 < nb) S.picked[ind + l - rf] = 1; }
                     __syncwarp();
-                    suppress(pind);
-                    k += fa + 1;
-                } else if (fs < 32) done = true;
-                else k += 32;
+                };
+                int largest = 0, nedge = 0;
+                bool done = false;
+                for (int k = L - 1; !done && k >= 0;) {                                                         // :413-453
+                    const int kk = k - lane;
+                    bool stop = false, avail = false;
+                    int ind = 0;
+                    if (kk >= 0) {
+                        const unsigned long long key = S.keys[kk];
+                        ind = (int)(unsigned)(key & 0xffffffffu);
+                        const float cv = __uint_as_float((unsigned)(key >> 32));
+                        stop = !((double)cv > 2.0);       // sorted: nothing further can be picked (no side effects skipped)
+                        avail = !stop && S.picked[ind - rf] == 0;
+                    }
+                    const unsigned ms = __ballot_sync(full, stop), ma = __ballot_sync(full, avail);
+                    const int fs = ms ? __ffs(ms) - 1 : 32, fa = ma ? __ffs(ma) - 1 : 32;
+                    if (fa < fs) {
+                        largest++;
+                        if (largest > 10) { done = true; continue; }
+                        const int pind = __shfl_sync(full, ind, fa);
+                        if (lane == 0) {
+                            label[pind] = largest <= 2 ? 2 : 1;
+                            seg_edge[(ring * 6 + j) * 10 + nedge] = pind;
+                            S.picked[pind - rf] = 1;
+                        }
+                        nedge++;
+                        __syncwarp();
+                        suppress(pind);
+                        k -= fa + 1;
+                    } else if (fs < 32) done = true;
+                    else k -= 32;
+                }
+                if (lane == 0) seg_cnt[ring * 6 + j] = nedge;
+                int smallest = 0;
+                done = false;
+                for (int k = 0; !done && k < L;) {                                                              // :456-492
+                    const int kk = k + lane;
+                    bool stop = false, avail = false;
+                    int ind = 0;
+                    if (kk < L) {
+                        const unsigned long long key = S.keys[kk];
+                        ind = (int)(unsigned)(key & 0xffffffffu);
+                        const float cv = __uint_as_float((unsigned)(key >> 32));
+                        stop = !((double)cv < 0.1);       // sorted ascending: the rest cannot qualify
+                        if (!stop) {
+                            const float4& p = PT(ind);
+                            const bool nearp = (double)(p.x * p.x + p.y * p.y + p.z * p.z) < 0.25;             // `continue`: no side effect
+                            avail = !nearp && S.picked[ind - rf] == 0;
+                        }
+                    }
+                    const unsigned ms = __ballot_sync(full, stop), ma = __ballot_sync(full, avail);
+                    const int fs = ms ? __ffs(ms) - 1 : 32, fa = ma ? __ffs(ma) - 1 : 32;
+                    if (fa < fs) {
+                        const int pind = __shfl_sync(full, ind, fa);
+                        if (lane == 0) label[pind] = -1;
+                        smallest++;
+                        if (smallest >= 4) { done = true; continue; }      // the fourth pick leaves no marks (:476-478)
+                        if (lane == 0) S.picked[pind - rf] = 1;
+                        __syncwarp();
+                        suppress(pind);
+                        k += fa + 1;
+                    } else if (fs < 32) done = true;
+                    else k += 32;
+                }
             }
         }
         if (tm) { const long long t = clock64(); t_walk += t - t0; t0 = t; }
