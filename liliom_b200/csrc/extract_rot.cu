@@ -23,6 +23,7 @@
 #include "dev_math.cuh"
 #include "detmath.h"
 #include <climits>
+#include <cstdlib>
 #include <cstdint>
 #include <cstdio>
 #include <algorithm>
@@ -186,7 +187,8 @@ struct RingSmem {
 __global__ void __launch_bounds__(512) k_rot_ring(const Pt32* __restrict__ cloud, const float* __restrict__ curv, int* __restrict__ meta,
                                                   int ds_rate, int* __restrict__ label, int* __restrict__ lessflat,
                                                   int* __restrict__ seg_edge /* [rings*6][10] */, int* __restrict__ seg_cnt /* [rings*6] */,
-                                                  long long* __restrict__ dbg /* LILIOM_DEBUG_TIMING: [rings][8] cycles */) {
+                                                  long long* __restrict__ dbg /* LILIOM_DEBUG_TIMING: [rings][8] cycles */,
+                                                  int fast_cap /* ROT_FAST_CAP; 0 (LILIOM_ROT_SLOW_WALK, tests): every segment takes the general path */) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     RingSmem& S = *reinterpret_cast<RingSmem*>(smem_raw);
     const int ring = blockIdx.x;
@@ -218,7 +220,7 @@ __global__ void __launch_bounds__(512) k_rot_ring(const Pt32* __restrict__ cloud
         for (int k = threadIdx.x; k < L + 10; k += blockDim.x) S.pts[k] = cloud[sp - 5 + k].a;
         __syncthreads();
         if (tm) { const long long t = clock64(); t_load += t - t0; t0 = t; }
-        if (L <= ROT_FAST_CAP) {
+        if (L <= fast_cap) {
             // ---- mask walk.  The walk over the sorted candidates (:413-492) is sequential only in its PICKS (<= 14 per segment):
             // whether a candidate qualifies (curvature class, range) and which neighbours a pick marks (the break test between
             // consecutive points) are static, so all of that is computed in parallel first, the sorted order becomes a rank per
@@ -630,7 +632,7 @@ int rot_extract_dev(liliom_ctx* c, int n, const double q_imu[4], const double q_
     long long* ring_dbg = c->dbg_timing ? reinterpret_cast<long long*>(reinterpret_cast<unsigned char*>(rprm + ROT_MAX_RINGS) + 8) : nullptr;
     if (ring_dbg) ring_dbg = reinterpret_cast<long long*>((reinterpret_cast<uintptr_t>(ring_dbg) + 7) & ~(uintptr_t)7);
     k_rot_ring<<<n_scans, 512, sizeof(RingSmem), c->stream>>>(cloud, c->rot_curv.as<float>(), meta, c->prm.ds_rate, c->rot_label.as<int>(),
-                                                              c->rot_lessflat.as<int>(), seg_edge, seg_cnt, ring_dbg);
+                                                              c->rot_lessflat.as<int>(), seg_edge, seg_cnt, ring_dbg, getenv("LILIOM_ROT_SLOW_WALK") ? 0 : ROT_FAST_CAP);
     LILI_TRY(launch_check(c, "k_rot_ring"));
     if (ring_dbg) {       // LILIOM_DEBUG_TIMING: per-ring stage cycles of this launch
         long long h[ROT_MAX_RINGS * 8];

@@ -255,6 +255,33 @@ def test_rot_extract_bit_exact(oracle, world_small, ds_rate):
     c.close()
 
 
+def test_rot_extract_walk_paths_identical(oracle, world_small, monkeypatch):
+    """k_rot_ring has two walks over a segment's sorted candidates: the availability-mask walk (segments up to 1024 points, every
+    real sensor) and the general bitonic-sort + batch walk kept for longer segments.  LILIOM_ROT_SLOW_WALK forces the general one;
+    both must give the oracle's features and labels bit for bit."""
+    import liliom_b200 as L
+    q_lb = np.array([0.999, 0.01, -0.02, 0.03]); q_lb /= np.linalg.norm(q_lb)
+    F = ["x", "y", "z", "intensity"]
+    for ds_rate in (1, 4):
+        rc, surf_o, edge_o, cut_o, lab_o, cur_o = oracle.extract_rot(world_small["hdl"], world_small["q_hdl"], q_lb, 64, ds_rate)
+        for slow in (False, True):
+            if slow:
+                monkeypatch.setenv("LILIOM_ROT_SLOW_WALK", "1")
+            else:
+                monkeypatch.delenv("LILIOM_ROT_SLOW_WALK", raising=False)
+            p = L.default_params(1)
+            p.ds_rate = ds_rate
+            c = L.Context(p)
+            surf, edge, cut = c.extract_rot(world_small["hdl"], world_small["q_hdl"], q_lb)
+            lab, cur = c.extract_rot_labels(len(cut))
+            c.close()
+            _fields_equal(cut, cut_o, F)
+            assert np.array_equal(lab, lab_o), (ds_rate, slow)
+            _fields_equal(edge, edge_o, F)
+            _fields_equal(surf, surf_o, F)
+    monkeypatch.delenv("LILIOM_ROT_SLOW_WALK", raising=False)
+
+
 def test_rot_extract_16_lines_and_errors(oracle, world_small):
     import liliom_b200 as L
     p = L.default_params(1); p.line_num = 16; p.ds_rate = 1
