@@ -714,7 +714,11 @@ def bench_body(args, fallback_note=None):
         # ---- timed region 2: end to end with host buffers
         ms_seq_local, last_seq = timed(step_e2e, steps, warmup)
         ms_seq, _ = over_ranks(ms_seq_local)
-        if args.e2e == "sequential":
+        # Sharded runs keep the one-thread e2e leg.  The two-node leg put each rank's GN exchange (a kernel that waits for its
+        # peers) next to a second host thread and context on the same GPU; it ran on 2 GPUs, but on 8 every rank's exchange
+        # hit its 6 s wait bound (gpurun_out/r2x_bench_8.err, kept as profiles/r02_two_node_sharded_8gpu_failure.txt) — not
+        # understood yet, so not shipped.
+        if args.e2e == "sequential" or sharded:
             ms_e2e, last_e2e = ms_seq, last_seq
         else:
             ms_e2e_local, last_e2e = e2e_two_nodes(steps, warmup)
@@ -922,7 +926,7 @@ def bench_body(args, fallback_note=None):
                 "h2d_bytes_per_step": int(last_e2e[1]), "d2h_bytes_per_step": int(last_e2e[2]),
                 "mode": ("sequential: one host thread calls the Preprocessing-node entry point, the LidarOdometry-node entry point"
                          + (" and the map maintenance" if stream_wl else "") + " in turn"
-                         if args.e2e == "sequential" else
+                         if (args.e2e == "sequential" or sharded) else
                          "two-nodes: Preprocessing and LidarOdometry contexts on two host threads / CUDA streams" + (" per rank" if multi else "") +
                          ", as the reference's two ROS nodes" + (" (the LidarOdometry thread also pushes the frame and rebuilds the map)" if stream_wl else "") +
                          "; /surf_features hop through pinned host memory; one 256 MB L2-evicting write per scan on a third stream inside "
