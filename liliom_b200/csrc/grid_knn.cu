@@ -1326,8 +1326,10 @@ int s2m_run(liliom_ctx* c, double pose7[7], int match_cnt, int max_num_iter, int
         cudaMemcpy(h, a.dbg, sizeof(h), cudaMemcpyDeviceToHost);
         if (h[16]) fprintf(stderr, "[persistent it=2, cycles] phases %lld, partials+fence %lld, barrier %lld, reduce %lld, solve %lld\n",
                            h[17] - h[16], h[18] - h[17], h[19] - h[18], h[20] - h[19], h[21] - h[20]);
+        if (!persistent && h[0] && h[1] > h[0])
         fprintf(stderr, "[phase A detail] pose+feat+transform %lld, first row bounds %lld, candidates+rank %lld, merge %lld, slot %lld\n",
                 h[8] - h[0], h[9] - h[8], h[10] - h[9], h[11] - h[10], h[1] - h[11]);
+        if (!persistent && h[0] && h[4] > h[0])
         fprintf(stderr, "[knn phases, cycles] blk0: start->A %lld, B %lld, C %lld, loop-end %lld, block-reduce+ticket %lld | last block: reduce %lld, solve %lld (abs tail %lld after blk0 start)\n",
                 h[1] - h[0], h[2] - h[1], h[3] - h[2], 0LL, h[4] - h[3], h[6] - h[5], h[7] - h[6], h[7] - h[0]);
     }
