@@ -281,6 +281,13 @@ int liliom_comm_set_shard_block(liliom_ctx* c, int metres);
  * nranks == 1 is accepted (self-exchange; exercises the protocol on one GPU). */
 int liliom_comm_peer_export(liliom_ctx* c, void* handle64);
 int liliom_comm_peer_attach(liliom_ctx* c, const void* handles /* nranks * 64 bytes, rank order */, int nranks, int rank);
+/* Recovery after a LILIOM_E_NCCL from the fused exchange (a rank did not publish within the wait bound): the ranks that ran
+ * the scan advanced their exchange epoch, a rank that never entered it did not, and every later scan would time out as well.
+ * Every rank reads its epoch, the application agrees on the maximum over the ranks (its own all-reduce — the ranks must meet
+ * anyway before they continue), and every rank sets maximum + 2: words left in the exchange buffers carry smaller epochs and
+ * never match a later one.  Host-side bookkeeping only; nothing is launched. */
+int liliom_comm_peer_epoch(liliom_ctx* c, unsigned int* epoch);
+int liliom_comm_peer_set_epoch(liliom_ctx* c, unsigned int epoch);
 
 /* ===================== instrumentation ===================== */
 typedef struct {

@@ -62,6 +62,7 @@ EXPORTS = [
     "liliom_pc2_layout", "liliom_comm_peer_export", "liliom_comm_peer_attach",
     "liliom_map_push_frame_device", "liliom_knn_block_stats", "liliom_comm_set_shard_block", "liliom_undistort",
     "liliom_map_update", "liliom_map_update_device", "liliom_map_download_cloud", "liliom_icp_align",
+    "liliom_comm_peer_epoch", "liliom_comm_peer_set_epoch",
 ]
 NODE_EXPORTS = ["liliom_pre_create", "liliom_pre_destroy", "liliom_pre_imu", "liliom_pre_cloud",
                 "liliom_lo_create", "liliom_lo_destroy", "liliom_lo_edge", "liliom_lo_surf", "liliom_lo_full", "liliom_lo_run"]
@@ -144,6 +145,8 @@ def lib() -> C.CDLL:
     L.liliom_pc2_layout.argtypes = [C.c_int, vp, C.c_int, ip]
     L.liliom_comm_peer_export.argtypes = [vp, vp]
     L.liliom_comm_peer_attach.argtypes = [vp, vp, C.c_int, C.c_int]
+    L.liliom_comm_peer_epoch.argtypes = [vp, C.POINTER(C.c_uint)]
+    L.liliom_comm_peer_set_epoch.argtypes = [vp, C.c_uint]
     L.liliom_map_push_frame_device.argtypes = [vp, vp, C.c_int, dp]
     L.liliom_comm_set_shard_block.argtypes = [vp, C.c_int]
     L.liliom_undistort.argtypes = [vp, vp, C.c_int, dp, dp]
@@ -487,6 +490,15 @@ class Context:
         blob = b"".join(handles)
         buf = C.create_string_buffer(blob, len(blob))
         self._check(lib().liliom_comm_peer_attach(self._h, buf, len(handles), rank))
+
+    def comm_peer_epoch(self) -> int:
+        e = C.c_uint()
+        self._check(lib().liliom_comm_peer_epoch(self._h, C.byref(e)))
+        return e.value
+
+    def comm_peer_set_epoch(self, epoch: int):
+        """Recovery after a lost exchange: every rank sets max-over-ranks(comm_peer_epoch()) + 2 (include/liliom.h)."""
+        self._check(lib().liliom_comm_peer_set_epoch(self._h, epoch))
 
     def counters(self, reset: bool = False) -> Counters:
         c = Counters()

@@ -141,3 +141,17 @@ extern "C" int liliom_comm_peer_attach(liliom_ctx* c, const void* handles, int n
     c->peer_ready = true;
     return LILIOM_OK;
 }
+
+// no way back after one lost exchange (the survivors' epochs ran ahead of the lost rank's) — see include/liliom.h
+extern "C" int liliom_comm_peer_epoch(liliom_ctx* c, unsigned int* epoch) {
+    if (!c || !epoch) return LILIOM_E_ARG;
+    *epoch = c->peer_epoch;
+    return LILIOM_OK;
+}
+
+extern "C" int liliom_comm_peer_set_epoch(liliom_ctx* c, unsigned int epoch) {
+    if (!c) return LILIOM_E_ARG;
+    if (epoch < c->peer_epoch) { c->last_error = "liliom_comm_peer_set_epoch: epochs only move forward (stale words in the exchange buffers must stay older)"; return LILIOM_E_ARG; }
+    c->peer_epoch = epoch;
+    return LILIOM_OK;
+}

@@ -89,3 +89,22 @@ def test_gn_variants_resident_pipeline(oracle, world_small):
         if ref is None:
             ref = poses[0]
         assert poses[0].tobytes() == ref.tobytes(), (flat, ll)
+
+
+def test_peer_epoch_resync(oracle, world_small):
+    """After a lost exchange the application realigns the ranks' epochs (liliom_comm_peer_epoch / _set_epoch): a scan advances the
+    epoch by its iteration count, a jump forward changes nothing in the result, a step back is refused."""
+    import liliom_b200 as L
+    surf, _, _ = oracle.extract_horizon(world_small["hz"], world_small["q_hz"])
+    ds = oracle.voxelgrid(surf, 0.4)
+    c = _ctx(0, 23)                                   # one rank exchanging with itself
+    c.map_set_points(world_small["map"])
+    e0 = c.comm_peer_epoch()
+    p1, _ = c.scan_to_map(ds, world_small["guess"], 10, mode=L.MODE_GN)
+    assert c.comm_peer_epoch() == e0 + 10
+    c.comm_peer_set_epoch(e0 + 10 + 1001)             # what max-over-ranks + 2 could look like after a loss elsewhere
+    p2, _ = c.scan_to_map(ds, world_small["guess"], 10, mode=L.MODE_GN)
+    assert p1.tobytes() == p2.tobytes() and c.comm_peer_epoch() == e0 + 10 + 1001 + 10
+    with pytest.raises(L.LiliomError):
+        c.comm_peer_set_epoch(5)
+    c.close()
