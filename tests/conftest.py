@@ -14,6 +14,8 @@ def pytest_configure(config):
 
 
 def _has_gpu():
+    if os.environ.get("LILIOM_ASSUME_GPU") == "1":      # e.g. under compute-sanitizer: skip the torch import, the library itself reports a missing device
+        return True
     try:
         import torch
         return torch.cuda.is_available()
