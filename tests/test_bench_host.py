@@ -92,3 +92,33 @@ def test_stream_frames_partition_the_map():
     got = np.sort(np.stack([np.concatenate([f[k] for f in frames]) for k in ("x", "y", "z")], 1).view([("", "f4")] * 3), axis=0)
     want = np.sort(np.ascontiguousarray(m[:, :3]).view([("", "f4")] * 3), axis=0)
     assert np.array_equal(got, want)
+
+
+def test_clock_sampler_keeps_the_rows_inside_the_window(tmp_path, monkeypatch):
+    """The clocks line of the bench comes from ONE looping `nvidia-smi -lms` process started before the timed region; only rows that
+    arrive inside the window count.  Driven here by a stand-in nvidia-smi (no GPU in this container)."""
+    import stat
+    import time
+    import bench
+    fake = tmp_path / "nvidia-smi"
+    fake.write_text("#!/bin/bash\n"
+                    "# stand-in: the first rows report a low clock (before the window), later rows the full clock with a power cap\n"
+                    "for i in $(seq 1 400); do\n"
+                    "  if [ $i -le 8 ]; then echo '345, 1965, Not Active, Not Active, Not Active, Not Active';\n"
+                    "  else echo '1965, 1965, Not Active, Not Active, Not Active, Active'; fi\n"
+                    "  sleep 0.025\n"
+                    "done\n")
+    fake.chmod(fake.stat().st_mode | stat.S_IEXEC)
+    monkeypatch.setenv("PATH", str(tmp_path) + os.pathsep + os.environ.get("PATH", ""))
+    clk = bench.ClockSampler(0, enabled=True).start()
+    time.sleep(0.5)                                  # "workload construction": rows from here must not count
+    with clk:
+        time.sleep(0.4)                              # the timed region
+    s = clk.summary()
+    assert s["samples"] >= 8 and s["sm_mhz"] == 1965.0 and s["sm_max_mhz"] == 1965.0
+    assert s["reasons"] == ["sw_power_cap"] and s["period_ms"] == bench.ClockSampler.PERIOD_MS
+    # disabled sampler (ranks != 0): no process, empty summary
+    off = bench.ClockSampler(0, enabled=False).start()
+    with off:
+        pass
+    assert off.summary()["samples"] == 0 and off.summary()["sm_mhz"] is None
