@@ -122,3 +122,28 @@ def test_clock_sampler_keeps_the_rows_inside_the_window(tmp_path, monkeypatch):
     with off:
         pass
     assert off.summary()["samples"] == 0 and off.summary()["sm_mhz"] is None
+
+
+def test_two_node_leg_is_fail_safe():
+    """bench.resolve_e2e: the optional two-node e2e leg may fail on any rank; then EVERY rank reports the one-thread figure (decided on
+    the gathered per-rank times, so the ranks' collectives stay matched) and the line says so."""
+    import bench
+    seq = (123.0, ("pose", 1, 2))
+    # one process, leg fine
+    ms, last, err = bench.resolve_e2e(lambda: (40.0, ("p", 3, 4)), lambda m: (m, [m]), *seq)
+    assert (ms, last, err) == (40.0, ("p", 3, 4), None)
+    # one process, leg raises
+    def boom():
+        raise RuntimeError("exchange timed out")
+    ms, last, err = bench.resolve_e2e(boom, lambda m: (m, [m]), *seq)
+    assert ms == 123.0 and last == ("pose", 1, 2) and "RuntimeError: exchange timed out" in err
+    # eight ranks, this one fine, another one failed: same fallback, and the gather was entered exactly once
+    calls = []
+    def gather(m):
+        calls.append(m)
+        return None, [m, 41.0, float("nan"), 39.0, 40.0, 40.0, 40.0, 40.0]
+    ms, last, err = bench.resolve_e2e(lambda: (40.0, ("p", 3, 4)), gather, *seq)
+    assert ms == 123.0 and last == ("pose", 1, 2) and "another rank" in err and calls == [40.0]
+    # eight ranks, all fine: the maximum over ranks
+    ms, last, err = bench.resolve_e2e(lambda: (40.0, ("p", 3, 4)), lambda m: (None, [m, 41.0, 39.5, 39.0, 40.0, 40.0, 40.0, 40.0]), *seq)
+    assert ms == 41.0 and err is None and last == ("p", 3, 4)
