@@ -29,6 +29,7 @@ int dm_plane_fit5(const float* m20, double nv[3]) {          // returns 1 when t
     return 0;
 }
 int dm_solve6(const double s21[21], const double rhs[6], double x[6]) { return solve6_ldlt(s21, rhs, x) ? 1 : 0; }
+int dm_gn_safe_step(const double s21[21], const double rhs[6], double d[6]) { return gn_safe_step(s21, rhs, d) ? 1 : 0; }
 void dm_pose_plus(const double x[7], const double d[6], double out[7]) { pose_plus(x, d, out); }
 void dm_eigen_sym3(const double a[6], double ev[3], double evec[9]) {     // a = {a00, a10, a20, a11, a21, a22}
     double v[3][3];

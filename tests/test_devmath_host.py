@@ -25,7 +25,7 @@ def dm():
                         "-shared", "-o", SO, src], check=True)
     L = C.CDLL(SO)
     dp, fp = C.POINTER(C.c_double), C.POINTER(C.c_float)
-    L.dm_plane_fit5.argtypes = [fp, dp]; L.dm_solve6.argtypes = [dp, dp, dp]
+    L.dm_plane_fit5.argtypes = [fp, dp]; L.dm_solve6.argtypes = [dp, dp, dp]; L.dm_gn_safe_step.argtypes = [dp, dp, dp]
     L.dm_pose_plus.argtypes = [dp, dp, dp]; L.dm_pose_plus.restype = None
     L.dm_eigen_sym3.argtypes = [dp, dp, dp]; L.dm_eigen_sym3.restype = None
     L.dm_colpiv_qr.argtypes = [dp, dp, dp]; L.dm_colpiv_qr.restype = None
@@ -120,3 +120,43 @@ def test_qrot_matches_eigen_formula(dm):
         dm.dm_qrot(_d(q), _d(v), _d(out))
         uv = 2.0 * np.cross(q[1:], v)
         np.testing.assert_allclose(out, v + q[0] * uv + np.cross(q[1:], uv), rtol=0, atol=1e-12)
+
+
+def _upper21(H):
+    return np.array([H[a, b] for a in range(6) for b in range(a, 6)], np.float64)
+
+
+def test_gn_safe_step_device_copy(dm):
+    """dev_math.cuh::gn_safe_step (the step every GN pass takes on the device) against NumPy: the plain solution on a well-posed
+    system, the Levenberg-damped solution when a pivot falls below 1e-10 * max diag, the 0.35 rad / 5 m trust region, and a refusal
+    on a zero or non-finite system (an undamped step diverges on one-wall geometry)."""
+    rng = np.random.default_rng(3)
+    d = np.zeros(6)
+    for _ in range(200):                                   # well-posed: J^T J of 400 random rows
+        J = rng.normal(size=(400, 6)) * rng.uniform(0.2, 3.0, 6)
+        H = J.T @ J; g = J.T @ (rng.normal(size=400) * 0.01)
+        assert dm.dm_gn_safe_step(_d(_upper21(H)), _d(-g), _d(d)) == 1
+        want = np.linalg.solve(H, -g)
+        assert np.allclose(d, want, rtol=1e-9, atol=1e-14)
+    for _ in range(100):                                   # rank 5 (one unobservable direction): damped system
+        J = rng.normal(size=(300, 6)); v = rng.normal(size=6); v /= np.linalg.norm(v)
+        J = J - np.outer(J @ v, v)
+        H = J.T @ J; g = J.T @ (rng.normal(size=300) * 0.01)
+        assert dm.dm_gn_safe_step(_d(_upper21(H)), _d(-g), _d(d)) == 1
+        lam = 1e-6 * H.diagonal().max()
+        want = np.linalg.solve(H + lam * np.eye(6), -g)
+        assert np.allclose(d, want, rtol=1e-6, atol=1e-10)
+        assert abs(d @ v) < 1e-3 * max(np.linalg.norm(d), 1e-12) + 1e-9          # the unobservable direction is (nearly) left alone
+    for _ in range(100):                                   # trust region: direction kept, norms clipped
+        J = rng.normal(size=(50, 6)) * 1e-3
+        H = J.T @ J; g = rng.normal(size=6) * rng.choice([1e-3, 1.0, 50.0])
+        assert dm.dm_gn_safe_step(_d(_upper21(H)), _d(-g), _d(d)) == 1
+        rot, tr = np.linalg.norm(d[:3]), np.linalg.norm(d[3:])
+        assert rot <= 0.35 * (1 + 1e-12) and tr <= 5.0 * (1 + 1e-12)
+        full = np.linalg.solve(H, -g)
+        if np.linalg.norm(full[:3]) > 0.35 or np.linalg.norm(full[3:]) > 5.0:
+            c = d @ full / (np.linalg.norm(d) * np.linalg.norm(full))
+            assert c > 1 - 1e-6 and (abs(rot - 0.35) < 1e-9 or abs(tr - 5.0) < 1e-9)
+    assert dm.dm_gn_safe_step(_d(np.zeros(21)), _d(np.ones(6)), _d(d)) == 0
+    bad = _upper21(np.eye(6)); bad[0] = np.nan
+    assert dm.dm_gn_safe_step(_d(bad), _d(np.ones(6)), _d(d)) == 0
