@@ -35,6 +35,7 @@ using namespace lili;
 
 extern "C" {
 float kc_gate_tau(double max_sqd) { return knn_gate_tau(max_sqd); }
+int kc_owner_of(float x, float y, float z, int nranks, float inv_block) { return owner_of(x, y, z, nranks, inv_block); }
 
 // map_sorted: m x {x, y, z, index bits} in cell order; returns the number of map points examined
 unsigned long long kc_thread_knn5(float sx, float sy, float sz, const float* map_sorted, const int* cell_start, float inv_cell,

@@ -33,6 +33,7 @@ def kc():
     L.kc_thread_knn5.argtypes = [C.c_float, C.c_float, C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_int), C.c_float,
                                  C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_float, C.POINTER(C.c_uint64)]
     L.kc_thread_knn5.restype = C.c_uint64
+    L.kc_owner_of.argtypes = [C.c_float, C.c_float, C.c_float, C.c_int, C.c_float]; L.kc_owner_of.restype = C.c_int
     return L
 
 
@@ -118,3 +119,24 @@ def test_pruned_search_equals_exhaustive_search(kc, seed, density):
     if density >= 12.0:
         block = np.array([((np.abs(np.floor(pts).astype(np.int64) - np.floor(q).astype(np.int64)) <= 1).all(1)).sum() for q in queries[:100]])
         assert np.mean(examined[:100]) < 0.8 * np.mean(block)
+
+
+def test_partition_rule_mirror_equals_the_device_function(kc):
+    """liliom_b200/sharding.py::owner_of (what the gloo tests and the bench's shard report use) against knn_core.cuh::owner_of compiled
+    for the host: same rank for points on both sides of cube faces, negative coordinates, the half-cube z shift, every rank count."""
+    from liliom_b200 import sharding
+    rng = np.random.default_rng(11)
+    pts = np.concatenate([
+        rng.uniform(-700, 700, (3000, 3)),
+        np.round(rng.uniform(-40, 40, (600, 3))) * 16.0 + rng.choice([-1e-3, 0.0, 1e-3], (600, 3)),          # on / beside 16 m faces
+        np.round(rng.uniform(-10, 10, (600, 3))) * 64.0 + np.array([0.0, 0.0, 32.0]) + rng.choice([-1e-3, 0.0, 1e-3], (600, 3)),
+    ]).astype(F)
+    for block in (16, 64):
+        for nranks in (1, 2, 3, 4, 8, 16):
+            want = sharding.owner_of(pts, nranks, block)
+            got = np.array([kc.kc_owner_of(F(p[0]), F(p[1]), F(p[2]), nranks, F(1.0 / block)) for p in pts], np.int32)
+            assert np.array_equal(got, want), (block, nranks)
+            assert got.min() >= 0 and got.max() < nranks
+            if nranks > 1:
+                share = np.bincount(got[:3000], minlength=nranks) / 3000.0
+                assert share.max() < 2.2 / nranks                                   # the linear hash spreads a 1.4 km stretch evenly
